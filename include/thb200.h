@@ -1,0 +1,217 @@
+/* libthb200 -- C ABI of the B200-native Theseus NLS hot path (linearize -> solve -> retract).
+ *
+ * This header is the drop-in boundary: plain C, device pointers + sizes + a cudaStream_t, no torch
+ * types.  It replaces the pybind11 torch-extension modules of the reference's theseus/extlib and the
+ * torch library calls on the per-iteration path.  Every entry point cites the reference interface it
+ * replaces (file:line relative to facebookresearch/theseus v0.2.3).
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers owned by the caller (torch tensors in the Python host).
+ *  - Batch-first, contiguous, row-major layouts identical to the reference's tensors:
+ *      SE3 [B,3,4], SO3 [B,3,3], tangent/delta [B,n], A_val [B,nnz], b [B,m], AtA [B,n,n], Atb [B,n].
+ *  - Suffix _f64 / _f32 = scalar type.  Index arrays are int32/int64 as stated.
+ *  - Return value: 0 on success, <0 = invalid argument (THB_ERR_*), >0 = CUDA runtime error code.
+ *    Numerical failure (non-positive pivot) is reported per batch item in an `info` array, like
+ *    LAPACK; the Python host raises RuntimeError iff any(info != 0) -- the same exception type the
+ *    reference loop catches (theseus/optimizer/nonlinear/nonlinear_least_squares.py:138-152).
+ *  - Every kernel is enqueued on `stream`; no entry point synchronises the device (the reference's
+ *    BaSpaCho wrappers call cudaDeviceSynchronize() after each kernel, baspacho_solver_cuda.cu:93,168,200).
+ */
+#ifndef THB200_H_
+#define THB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* thb_stream_t; /* == cudaStream_t */
+
+#define THB_OK 0
+#define THB_ERR_BAD_ARG (-1)
+#define THB_ERR_UNSUPPORTED (-2)
+#define THB_ERR_ALLOC (-3)
+
+/* Library identification: returns version (major*10000 + minor*100 + patch) and the compiled SM arch. */
+int thb_version(void);
+int thb_compiled_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cost-function groups ("schemas").  One group = all cost functions of one type with the same
+ * variable types and weight type -- what theseus/core/vectorizer.py:112-404 (Vectorize) builds by
+ * torch.cat at every evaluation; here it is a precompiled table of device pointers and offsets.
+ * ---------------------------------------------------------------------------------------------- */
+enum thb_cost_kind {
+  THB_COST_BETWEEN_SE3 = 0, /* theseus/embodied/measurements/between.py:34-45 with SE3 */
+  THB_COST_LOCAL_SE3 = 1,   /* theseus/embodied/misc/local_cost_fn.py:40-61 (Local / Difference) with SE3 */
+  THB_COST_BETWEEN_SO3 = 2,
+  THB_COST_LOCAL_SO3 = 3,
+  THB_COST_LOCAL_VECTOR = 4 /* Difference on Vector/Point: e = x - target, J = I (geometry/vector.py) */
+};
+enum thb_weight_kind {
+  THB_WEIGHT_SCALE = 0,   /* theseus/core/cost_weight.py:60-93  (ScaleCostWeight, tensor [Bw,1]) */
+  THB_WEIGHT_DIAGONAL = 1 /* theseus/core/cost_weight.py:98-139 (DiagonalCostWeight, tensor [Bw,dim]) */
+};
+enum thb_var_kind { THB_VAR_SE3 = 0, THB_VAR_SO3 = 1, THB_VAR_VECTOR = 2, THB_VAR_SE2 = 3, THB_VAR_SO2 = 4 };
+
+typedef struct thb_cost_group {
+  int32_t kind;        /* enum thb_cost_kind */
+  int32_t weight_kind; /* enum thb_weight_kind */
+  int32_t K;           /* number of cost functions in the group */
+  int32_t dim;         /* error dimension of each cost function (6 for SE3, 3 for SO3, k for Vector) */
+  /* device arrays of length K holding DEVICE pointers to each cost function's tensors */
+  const void* const* x0;  /* first optimisation variable  [Bx,...] */
+  const void* const* x1;  /* second optimisation variable (Between) or NULL */
+  const void* const* aux; /* measurement (Between) / target (Local) */
+  const void* const* w;   /* cost-weight tensor */
+  /* device int32 [K,4]: batch stride in ELEMENTS of x0,x1,aux,w (0 = batch-1 tensor broadcast to B,
+   * the broadcasting rule of theseus/core/objective.py:708-724) */
+  const int32_t* bstride;
+  /* Placement in the reference's batched-CSR Jacobian (theseus/optimizer/sparse_linearization.py:34-84): */
+  const int64_t* a_off;    /* device [K]   offset of the cost function's first row in A_val (cost_function_row_block_starts) */
+  const int32_t* a_stride; /* device [K]   entries per row (cost_function_stride) */
+  const int32_t* bp;       /* device [K,2] column offset of each variable's block inside a row (cost_function_block_pointers) */
+  const int32_t* row0;     /* device [K]   first row of the cost function in b */
+} thb_cost_group;
+
+/* Fused residual + analytic Jacobian + weighting for every (cost function, batch item) of a group;
+ * writes A_val[B,nnz] / b[B,m] (b = -weighted error) in the layout of SparseLinearization.
+ * Replaces: Vectorize._vectorize (core/vectorizer.py:382-404), Between/Local.jacobians,
+ * CostWeight.weight_jacobians_and_error (core/cost_weight.py:81-90,125-136),
+ * SparseLinearization._linearize_jacobian_impl (optimizer/sparse_linearization.py:102-140). */
+int thb_linearize_group_f64(const thb_cost_group* g, int64_t B, double* A_val, int64_t nnz, double* b, int64_t m,
+                            thb_stream_t stream);
+int thb_linearize_group_f32(const thb_cost_group* g, int64_t B, float* A_val, int64_t nnz, float* b, int64_t m,
+                            thb_stream_t stream);
+
+/* Residual-only pass: partial[c, b] = sum over the c-th chunk of cost functions of (w*e)^2 / 2.
+ * `partial` has room for thb_error_num_chunks(K) rows of B.  The caller sums the rows in order
+ * (thb_lm_control does) so the reduction is deterministic.
+ * Replaces: Objective.error / error_metric (core/objective.py:562-641) through the vectorised
+ * WEIGHTED_ERROR pass (core/vectorizer.py:406-407). */
+int thb_error_num_chunks(int32_t K);
+int thb_error_group_f64(const thb_cost_group* g, int64_t B, double* partial, thb_stream_t stream);
+int thb_error_group_f32(const thb_cost_group* g, int64_t B, float* partial, thb_stream_t stream);
+/* err[b] = sum_c partial[c,b] (fixed order). */
+int thb_error_reduce_f64(const double* partial, int32_t num_chunks, int64_t B, double* err, thb_stream_t stream);
+int thb_error_reduce_f32(const float* partial, int32_t num_chunks, int64_t B, float* err, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Retract: out_i[b] = X_i[b] * exp(step * delta[b, col_i : col_i+dof_i])   (Vector: x + step*delta)
+ * for every optimisation variable; batch items with ignore[b] != 0 keep X_i[b].
+ * Replaces: Objective.retract_vars_sequence (core/objective.py:873-914),
+ * Vectorize._vectorized_retract_optim_vars (core/vectorizer.py:410-469), LieGroup._retract_impl
+ * (geometry/lie_group.py:197-198), Variable.update masking (core/variable.py:65-69).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thb_var_table {
+  int32_t N;                 /* number of optimisation variables */
+  const void* const* x;      /* device [N] pointers to current tensors  [B,...] */
+  void* const* out;          /* device [N] pointers to output tensors   [B,...] */
+  const int32_t* kind;       /* device [N] enum thb_var_kind */
+  const int32_t* col;        /* device [N] first column in delta (Linearization.var_start_cols) */
+  const int32_t* dof;        /* device [N] */
+} thb_var_table;
+
+int thb_retract_f64(const thb_var_table* vt, int64_t B, const double* delta, int64_t n, double step,
+                    const uint8_t* ignore /* [B] or NULL */, thb_stream_t stream);
+int thb_retract_f32(const thb_var_table* vt, int64_t B, const float* delta, int64_t n, float step,
+                    const uint8_t* ignore, thb_stream_t stream);
+/* x_i[b] <- out_i[b] where keep_old[b] == 0  (objective.update(..., batch_ignore_mask=reject),
+ * nonlinear_least_squares.py:361; core/variable.py:65-69). */
+int thb_commit_f64(const thb_var_table* vt, int64_t B, const uint8_t* keep_old, thb_stream_t stream);
+int thb_commit_f32(const thb_var_table* vt, int64_t B, const uint8_t* keep_old, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gram assembly from the batched-CSR Jacobian: AtA blocks and Atb without atomics.
+ * The block structure is precomputed on the host (theseus_b200/structure.py): for every output
+ * entry e (one scalar of one variable-pair block) a list of contributing cost functions.
+ * Replaces: DenseLinearization._linearize_hessian_impl (optimizer/dense_linearization.py:58-62,
+ * At.bmm(A) / At.bmm(b)); extlib mult_MtM / add_MtM / tmat_vec (extlib/mat_mult.cu:36-79,216-243,
+ * extlib/baspacho_solver_cuda.cu:96-134).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thb_gram_plan {
+  int64_t num_entries;        /* NE: scalar entries of all (lower-triangular) variable-pair blocks */
+  const int32_t* ent_blk;     /* device [NE] block id of the entry */
+  const int16_t* ent_p;       /* device [NE] row inside the block */
+  const int16_t* ent_q;       /* device [NE] col inside the block */
+  const int64_t* blk_out;     /* device [NB] offset of block element (0,0) in one batch item's output */
+  const int32_t* blk_ld;      /* device [NB] leading dimension of the block in the output */
+  const int64_t* blk_mirror;  /* device [NB] offset of the transposed block's (0,0), or -1 */
+  const int32_t* blk_cptr;    /* device [NB+1] CSR pointer into the contribution arrays */
+  const int64_t* c_off;       /* device [NC] A_val offset of the contributing cost function's first row */
+  const int32_t* c_stride;    /* device [NC] */
+  const int32_t* c_rows;      /* device [NC] */
+  const int32_t* c_bpa;       /* device [NC] block pointer of the block-row variable */
+  const int32_t* c_bpb;       /* device [NC] block pointer of the block-col variable */
+  /* Atb plan: one entry per column */
+  int64_t n;                  /* num_cols */
+  const int32_t* col_cptr;    /* device [n+1] */
+  const int64_t* cc_off;      /* device [NCC] A_val offset of (first row, this column) */
+  const int32_t* cc_stride;   /* device [NCC] */
+  const int32_t* cc_rows;     /* device [NCC] */
+  const int32_t* cc_row0;     /* device [NCC] first row in b */
+} thb_gram_plan;
+
+/* out[b*out_bstride + ...] receives the blocks (dense AtA: out_bstride = n*n, caller pre-zeroes via
+ * thb_fill_zero); Atb[B,n]; diag[B,n] (optional, may be NULL) receives diag(AtA). */
+int thb_gram_f64(const thb_gram_plan* p, int64_t B, const double* A_val, int64_t nnz, const double* b, int64_t m,
+                 double* out, int64_t out_bstride, double* Atb, double* diag, thb_stream_t stream);
+int thb_fill_zero(void* ptr, int64_t bytes, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched dense Cholesky factor + solve with fused LM damping.
+ *   M_b = AtA_b ; diag(M_b) <- diag(M_b) * (1 + alpha_b) + beta_b ; L_b L_b^T = M_b ; x_b = M_b^-1 rhs_b
+ * (alpha,beta) follow theseus/optimizer/linear/utils.py:14-33; ellipsoidal: (lambda, eps), spherical (0, lambda).
+ * AtA is read-only (LM needs its diagonal afterwards, levenberg_marquardt.py:185-190).
+ * Workspace: thb_potrf_workspace_bytes(B, n).  info[b] = 0, or k>0 if the k-th pivot was not positive.
+ * Replaces: DenseSolver._apply_damping (optimizer/linear/dense_solver.py:38-64) +
+ * torch.linalg.cholesky + torch.cholesky_solve (dense_solver.py:159-161).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t thb_potrf_workspace_bytes(int64_t B, int64_t n);
+int thb_potrf_potrs_f64(const double* AtA, const double* rhs, const double* alpha, const double* beta, double* x,
+                        int32_t* info, int64_t B, int64_t n, void* workspace, int64_t workspace_bytes,
+                        thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Levenberg-Marquardt control (device-resident accept/reject + damping update).
+ *   den = 1/2 sum_j d_j (lam_eff_j d_j + Atb_j), d = step*delta, lam_eff = lam*diag(AtA) if ellipsoidal else lam
+ *   rho = (err_prev - err_new)/den ; reject = rho <= damping_accept
+ *   lam <- clamp(reject ? lam*up : lam/down, 1e-7, 1e7)
+ * Replaces LevenbergMarquardt._check_accept (optimizer/nonlinear/levenberg_marquardt.py:172-201).
+ * Also folds: err[b] <- reject ? err_prev : err_new; counts of rejected items -> stats[0].
+ * ---------------------------------------------------------------------------------------------- */
+int thb_lm_control_f64(const double* delta, const double* Atb, const double* diag, int64_t B, int64_t n, double step,
+                       const double* err_prev, const double* err_new, double* lam, int32_t ellipsoidal,
+                       double damping_accept, double down_ratio, double up_ratio, uint8_t* reject,
+                       double* err_out, int32_t* stats, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched CSR helpers (same semantics as theseus/extlib/mat_mult.cu:359-400, int64 indices):
+ *   thb_mat_vec : y[b,row]  = sum_k A_val[b,k] v[b,col_k]          (mat_vec,  mat_mult.cu:134-214)
+ *   thb_tmat_vec: y[b,col] += A_val[b,k] v[b,row]  (deterministic) (tmat_vec, mat_mult.cu:216-295)
+ * ---------------------------------------------------------------------------------------------- */
+int thb_mat_vec_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* row_ptr, const int64_t* col_ind,
+                    const double* A_val, const double* v, double* y, thb_stream_t stream);
+int thb_tmat_vec_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* row_ptr, const int64_t* col_ind,
+                     const double* A_val, const double* v, double* y, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone Lie-group kernels (torchlie.functional SE3 namespace, torchlie/functional/lie_group.py:332-366).
+ * Shapes: tangent [N,6], group [N,3,4], jacobian [N,6,6].
+ * ---------------------------------------------------------------------------------------------- */
+int thb_se3_exp_f64(const double* tangent, double* group, int64_t N, thb_stream_t stream);
+int thb_se3_log_f64(const double* group, double* tangent, double* jlog /* may be NULL */, int64_t N, thb_stream_t stream);
+int thb_se3_adjoint_f64(const double* group, double* adj, int64_t N, thb_stream_t stream);
+int thb_se3_inverse_f64(const double* group, double* out, int64_t N, thb_stream_t stream);
+int thb_se3_compose_f64(const double* g0, const double* g1, double* out, int64_t N, thb_stream_t stream);
+int thb_se3_exp_f32(const float* tangent, float* group, int64_t N, thb_stream_t stream);
+int thb_se3_log_f32(const float* group, float* tangent, float* jlog, int64_t N, thb_stream_t stream);
+int thb_se3_adjoint_f32(const float* group, float* adj, int64_t N, thb_stream_t stream);
+int thb_se3_inverse_f32(const float* group, float* out, int64_t N, thb_stream_t stream);
+int thb_se3_compose_f32(const float* g0, const float* g1, float* out, int64_t N, thb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THB200_H_ */

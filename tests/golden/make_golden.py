@@ -1,0 +1,223 @@
+"""Generate golden fixtures by running the REFERENCE ITSELF (facebookresearch/theseus v0.2.3).
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Writes small .npz files next to this script.  The fixtures pin oracle/ (tests/test_oracle_*.py,
+CPU) and the CUDA path (tests/test_gpu_*.py).  Nothing here is imported at test time.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def _import_reference():
+    # torchkin's vendored URDF parser imports lxml at import time; stub it.
+    lxml = types.ModuleType("lxml")
+    etree = types.ModuleType("lxml.etree")
+    import xml.etree.ElementTree as ET
+    for k in dir(ET):
+        setattr(etree, k, getattr(ET, k))
+    lxml.etree = etree
+    sys.modules["lxml"] = lxml
+    sys.modules["lxml.etree"] = etree
+    for p in (REF, REF + "/torchlie", REF + "/torchkin"):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    warnings.filterwarnings("ignore")
+    import theseus as th
+    import torchlie.functional as lieF
+    return th, lieF
+
+
+def _angle_sweep_tangents(rng, dtype, dof):
+    """Random tangents plus the reference's own angle sweep (tests/theseus_tests/geometry/test_se3.py:56-129)."""
+    out = []
+    out.append(rng.standard_normal((20, dof)))
+    for ang in [0.0, 1e-9, 1e-5, 3e-3, 4.9e-3, 5.1e-3, 9e-3, 1.1e-2, 0.19, 0.21, 1.0,
+                np.pi - 1e-3, np.pi - 1e-7, np.pi - 1e-11, np.pi, 2 * np.pi - 1e-11, 2 * np.pi - 1e-3]:
+        for _ in range(3):
+            ax = rng.standard_normal(3)
+            ax /= np.linalg.norm(ax)
+            t = np.zeros(dof)
+            t[-3:] = ax * ang
+            if dof == 6:
+                t[:3] = rng.standard_normal(3)
+            out.append(t[None])
+    # axis-aligned near-pi cases to exercise the major-diagonal selection
+    for k in range(3):
+        for sgn in (+1, -1):
+            t = np.zeros(dof)
+            t[-3 + k] = sgn * (np.pi - 1e-9)
+            if dof == 6:
+                t[:3] = rng.standard_normal(3)
+            out.append(t[None])
+    return np.concatenate(out, 0).astype(dtype)
+
+
+def make_lie(th, lieF):
+    import torch
+    rng = np.random.default_rng(0)
+    out = {}
+    for dtname, dt, tdt in (("f64", np.float64, torch.float64), ("f32", np.float32, torch.float32)):
+        from torchlie.functional import so3_impl, se3_impl
+        for gname, dof, F in (("so3", 3, so3_impl), ("se3", 6, se3_impl)):
+            tang = _angle_sweep_tangents(rng, dt, dof)
+            t = torch.from_numpy(tang)
+            G = F._exp_impl(t)
+            (jexp,), _ = F._jexp_impl(t)
+            (jlog,), logG = F._jlog_impl(G)
+            G2 = F._exp_impl(torch.from_numpy(rng.standard_normal(tang.shape).astype(dt)))
+            pre = f"{gname}_{dtname}_"
+            out[pre + "tangent"] = tang
+            out[pre + "exp"] = G.numpy()
+            out[pre + "jexp"] = jexp.numpy()
+            out[pre + "log"] = logG.numpy()
+            out[pre + "jlog"] = jlog.numpy()
+            out[pre + "adj"] = F._adjoint_impl(G).numpy()
+            out[pre + "inv"] = F._inverse_impl(G).numpy()
+            out[pre + "other"] = G2.numpy()
+            out[pre + "compose"] = F._compose_impl(G, G2).numpy()
+    np.savez_compressed(os.path.join(HERE, "lie_kat.npz"), **out)
+    print("lie_kat.npz", len(out), "arrays")
+
+
+def make_costs(th):
+    import torch
+    torch.manual_seed(1)
+    out = {}
+    for dtname, tdt in (("f64", torch.float64), ("f32", torch.float32)):
+        B = 16
+        X0 = th.SE3.rand(B, dtype=tdt)
+        X1 = th.SE3.rand(B, dtype=tdt)
+        Z = th.SE3.rand(B, dtype=tdt)
+        w = torch.rand(1, 6, dtype=tdt) + 0.5
+        cf = th.Between(X0, X1, Z, th.DiagonalCostWeight(w))
+        (J0, J1), e = cf.weighted_jacobians_error()
+        cl = th.Difference(X0, Z, th.ScaleCostWeight(torch.tensor(0.37, dtype=tdt)))
+        (Jl,), el = cl.weighted_jacobians_error()
+        pre = f"{dtname}_"
+        out.update({pre + "X0": X0.tensor.numpy(), pre + "X1": X1.tensor.numpy(), pre + "Z": Z.tensor.numpy(),
+                    pre + "w": w.numpy(), pre + "between_J0": J0.numpy(), pre + "between_J1": J1.numpy(),
+                    pre + "between_e": e.numpy(), pre + "local_J": Jl.numpy(), pre + "local_e": el.numpy()})
+    np.savez_compressed(os.path.join(HERE, "costs_kat.npz"), **out)
+    print("costs_kat.npz", len(out), "arrays")
+
+
+def _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio=0.2, init_perturb=0.0):
+    import torch
+    from theseus.utils.examples.pose_graph.dataset import PoseGraphDataset
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    rng = torch.Generator().manual_seed(seed)
+    pg, _ = PoseGraphDataset.generate_synthetic_3D(
+        num_poses=num_poses, translation_noise=0.05, rotation_noise=0.02, loop_closure_ratio=loop_closure_ratio,
+        loop_closure_outlier_ratio=0.0, dataset_size=B, batch_size=B, generator=rng, dtype=dtype)
+    if init_perturb > 0:
+        # harder start (so that LM needs all its iterations and really rejects steps): extra random right-perturbation
+        for p in pg.poses[1:]:
+            p.tensor = p.compose(th.SE3.exp_map(init_perturb * (2 * torch.rand(B, 6, dtype=dtype) - 1))).tensor
+    # objective exactly as examples/pose_graph/pose_graph_cube.py:56-83
+    objective = th.Objective(dtype=dtype)
+    for edge in pg.edges:
+        objective.add(th.Between(pg.poses[edge.i], pg.poses[edge.j], edge.relative_pose, edge.weight))
+    prior = th.Difference(var=pg.poses[0], cost_weight=th.ScaleCostWeight(torch.tensor(1e-3, dtype=dtype)),
+                          target=pg.poses[0].copy(new_name=pg.poses[0].name + "__PRIOR"))
+    objective.add(prior)
+    return pg, objective
+
+
+def make_pgo(th, name, num_poses, B, seed, iters, lm_kwargs, method="lm", full_trace=True, loop_closure_ratio=0.2,
+             init_perturb=0.0):
+    import torch
+    dtype = torch.float64
+    pg, objective = _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio, init_perturb)
+    out = {}
+    out["poses0"] = np.stack([p.tensor.numpy() for p in pg.poses], 0)            # [N,B,3,4]
+    out["edges"] = np.array([[e.i, e.j] for e in pg.edges], dtype=np.int64)        # [E,2]
+    out["meas"] = np.stack([e.relative_pose.tensor.numpy() for e in pg.edges], 0)  # [E,B,3,4]
+    out["edge_w"] = np.stack([e.weight.diagonal.tensor.numpy() for e in pg.edges], 0)  # [E,1,6]
+    out["prior_w"] = np.array(1e-3)
+    cls = th.LevenbergMarquardt if method == "lm" else th.GaussNewton
+    opt = cls(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=iters,
+              step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
+    ordering = [v.name for v in opt.linear_solver.linearization.ordering]
+    assert ordering == [p.name for p in pg.poses], "default ordering must be pose order"
+    sp = th.SparseLinearization(objective)
+    out["A_row_ptr"] = sp.A_row_ptr.astype(np.int64)
+    out["A_col_ind"] = sp.A_col_ind.astype(np.int64)
+    out["var_start_cols"] = np.array(sp.var_start_cols, dtype=np.int64)
+    tr = dict(delta=[], lam=[], Atb=[], AtA_diag=[], A_val=[], b=[], AtA=[], err=[])
+
+    def cb(optimizer, info, delta, it):
+        lin = optimizer.linear_solver.linearization
+        tr["delta"].append(delta.detach().numpy().copy())
+        tr["err"].append(info.last_err.numpy().copy())  # fp64 (err_history is stored in fp32 by the reference)
+        tr["Atb"].append(lin.Atb.squeeze(2).numpy().copy())
+        tr["AtA_diag"].append(lin.AtA.diagonal(dim1=1, dim2=2).numpy().copy())
+        if method == "lm":
+            tr["lam"].append(np.array(optimizer._damping, dtype=np.float64) * np.ones(B))
+        if full_trace and it == 0:
+            tr["AtA"].append(lin.AtA.numpy().copy())
+            tr["b"].append(lin.b.numpy().copy())
+
+    if full_trace:
+        # sparse linearization at the initial point (A_val in the reference CSR layout)
+        objective.update()
+        sp.linearize()
+        out["A_val0"] = sp.A_val.numpy().copy()
+        out["b0"] = sp.b.numpy().copy()
+        out["Atb0_sparse"] = sp.Atb.squeeze(2).numpy().copy()
+    with torch.no_grad():
+        info = opt.optimize(track_err_history=True, end_iter_callback=cb, **lm_kwargs)
+    out["err_history"] = info.err_history.numpy()
+    out["poses_final"] = np.stack([objective.optim_vars[n].tensor.numpy() for n in ordering], 0)
+    for k, v in tr.items():
+        if v:
+            out["trace_" + k] = np.stack(v, 0)
+    out["kwargs_json"] = np.array(repr(dict(method=method, iters=iters, **lm_kwargs)))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "err0", out["err_history"][:, 0], "-> errK", out["err_history"][:, -1])
+
+
+def make_dense_solver(th):
+    """Random SPD systems in the style of tests/theseus_tests/optimizer/linear/test_dense_solver.py:12-77."""
+    import torch
+    torch.manual_seed(0)
+    out = {}
+    for n in (1, 6, 10, 48, 130):
+        B = 5
+        A = torch.randn(B, n + 3, n, dtype=torch.float64)
+        AtA = A.transpose(1, 2) @ A + 0.1 * torch.eye(n, dtype=torch.float64)
+        Atb = torch.randn(B, n, 1, dtype=torch.float64)
+        lam = torch.rand(B, dtype=torch.float64) + 0.01
+        for ell in (True, False):
+            D = th.CholeskyDenseSolver._apply_damping(AtA, lam, ellipsoidal=ell, eps=1e-8)
+            L = torch.linalg.cholesky(D)
+            x = torch.cholesky_solve(Atb, L).squeeze(2)
+            out[f"n{n}_x_{'ell' if ell else 'sph'}"] = x.numpy()
+        out[f"n{n}_AtA"] = AtA.numpy()
+        out[f"n{n}_Atb"] = Atb.numpy()
+        out[f"n{n}_lam"] = lam.numpy()
+    np.savez_compressed(os.path.join(HERE, "dense_solver_kat.npz"), **out)
+    print("dense_solver_kat.npz")
+
+
+if __name__ == "__main__":
+    th, lieF = _import_reference()
+    make_lie(th, lieF)
+    make_costs(th)
+    make_dense_solver(th)
+    lm = dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
+    make_pgo(th, "pgo_small_lm", num_poses=8, B=3, seed=0, iters=6, lm_kwargs=lm, loop_closure_ratio=0.5)
+    make_pgo(th, "pgo_small_gn", num_poses=8, B=3, seed=1, iters=4, lm_kwargs={}, method="gn", loop_closure_ratio=0.5)
+    make_pgo(th, "pgo_small_lm_sph", num_poses=8, B=3, seed=2, iters=3,
+             lm_kwargs=dict(damping=0.1, adaptive_damping=True, ellipsoidal_damping=False), loop_closure_ratio=0.5)
+    make_pgo(th, "pgo64_lm", num_poses=64, B=2, seed=3, iters=10, lm_kwargs=lm, full_trace=False)
+    make_pgo(th, "pgo_small_lm_hard", num_poses=8, B=4, seed=4, iters=8, lm_kwargs=lm, loop_closure_ratio=0.5, init_perturb=0.6)
+    make_pgo(th, "pgo32_lm_hard", num_poses=32, B=3, seed=5, iters=10, lm_kwargs=lm, full_trace=False, init_perturb=0.5)

@@ -1,0 +1,23 @@
+"""theseus_b200 -- a B200-native (sm_100a) implementation of the batched nonlinear-least-squares inner loop of
+facebookresearch/theseus (linearize -> solve -> retract), behind the reference's own plugin API.
+
+    import theseus_b200 as th
+    objective = th.Objective(dtype=torch.float64)
+    objective.add(th.Between(x0, x1, z, th.DiagonalCostWeight(w)))
+    optimizer = th.LevenbergMarquardt(objective.to("cuda"), linear_solver_cls=th.CholeskyDenseSolver, max_iterations=10)
+    layer = th.TheseusLayer(optimizer)
+    values, info = layer.forward(inputs, optimizer_kwargs=dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True))
+
+All arithmetic runs in libthb200.so (hand-written CUDA behind the C ABI of include/thb200.h); there is no CPU
+or PyTorch fallback.  Importing the package does not require a GPU; evaluating anything does.
+"""
+from .geometry import Variable, Manifold, LieGroup, Vector, Point2, Point3, SE3, SO3, as_variable  # noqa: F401
+from .core import (CostWeight, ScaleCostWeight, DiagonalCostWeight, CostFunction, Between, Difference, Local,  # noqa: F401
+                   Objective)
+from .optimizer import (VariableOrdering, Linearization, DenseLinearization, SparseLinearization, LinearSolver,  # noqa: F401
+                        DenseSolver, CholeskyDenseSolver, LUDenseSolver, NonlinearLeastSquares, GaussNewton,
+                        LevenbergMarquardt, NonlinearOptimizerStatus, NonlinearOptimizerInfo, OptimizerInfo,
+                        NonlinearOptimizerParams, BackwardMode, convert_to_alpha_beta_damping_tensors)
+from .layer import TheseusLayer  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,104 @@
+"""ctypes binding of libthb200.so (the C ABI declared in include/thb200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.  The
+library is plain C ABI (device pointers, sizes, cudaStream_t) -- torch is only used by the caller
+for device memory and streams.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libthb200.so")
+_lib = None
+
+c_i32, c_i64, c_f64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_float, C.c_void_p
+
+
+class CostGroup(C.Structure):
+    _fields_ = [("kind", c_i32), ("weight_kind", c_i32), ("K", c_i32), ("dim", c_i32),
+                ("x0", c_vp), ("x1", c_vp), ("aux", c_vp), ("w", c_vp), ("bstride", c_vp),
+                ("a_off", c_vp), ("a_stride", c_vp), ("bp", c_vp), ("row0", c_vp)]
+
+
+class VarTable(C.Structure):
+    _fields_ = [("N", c_i32), ("x", c_vp), ("out", c_vp), ("kind", c_vp), ("col", c_vp), ("dof", c_vp)]
+
+
+class GramPlan(C.Structure):
+    _fields_ = [("num_entries", c_i64), ("ent_blk", c_vp), ("ent_p", c_vp), ("ent_q", c_vp),
+                ("blk_out", c_vp), ("blk_ld", c_vp), ("blk_mirror", c_vp), ("blk_cptr", c_vp),
+                ("c_off", c_vp), ("c_stride", c_vp), ("c_rows", c_vp), ("c_bpa", c_vp), ("c_bpb", c_vp),
+                ("n", c_i64), ("col_cptr", c_vp), ("cc_off", c_vp), ("cc_stride", c_vp), ("cc_rows", c_vp),
+                ("cc_row0", c_vp)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/thb200.h
+_PG, _PV, _PP = C.POINTER(CostGroup), C.POINTER(VarTable), C.POINTER(GramPlan)
+SIGNATURES = {
+    "thb_version": (c_i32, []),
+    "thb_compiled_arch": (c_i32, []),
+    "thb_linearize_group_f64": (c_i32, [_PG, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "thb_linearize_group_f32": (c_i32, [_PG, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "thb_error_num_chunks": (c_i32, [c_i32]),
+    "thb_error_group_f64": (c_i32, [_PG, c_i64, c_vp, c_vp]),
+    "thb_error_group_f32": (c_i32, [_PG, c_i64, c_vp, c_vp]),
+    "thb_error_reduce_f64": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp]),
+    "thb_error_reduce_f32": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp]),
+    "thb_retract_f64": (c_i32, [_PV, c_i64, c_vp, c_i64, c_f64, c_vp, c_vp]),
+    "thb_retract_f32": (c_i32, [_PV, c_i64, c_vp, c_i64, c_f32, c_vp, c_vp]),
+    "thb_commit_f64": (c_i32, [_PV, c_i64, c_vp, c_vp]),
+    "thb_commit_f32": (c_i32, [_PV, c_i64, c_vp, c_vp]),
+    "thb_gram_f64": (c_i32, [_PP, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "thb_fill_zero": (c_i32, [c_vp, c_i64, c_vp]),
+    "thb_potrf_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "thb_potrf_potrs_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "thb_lm_control_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64,
+                                   c_vp, c_vp, c_vp, c_vp]),
+    "thb_mat_vec_f64": (c_i32, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "thb_tmat_vec_f64": (c_i32, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+}
+for _sfx, _ in (("f64", c_f64), ("f32", c_f32)):
+    SIGNATURES[f"thb_se3_exp_{_sfx}"] = (c_i32, [c_vp, c_vp, c_i64, c_vp])
+    SIGNATURES[f"thb_se3_log_{_sfx}"] = (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp])
+    SIGNATURES[f"thb_se3_adjoint_{_sfx}"] = (c_i32, [c_vp, c_vp, c_i64, c_vp])
+    SIGNATURES[f"thb_se3_inverse_{_sfx}"] = (c_i32, [c_vp, c_vp, c_i64, c_vp])
+    SIGNATURES[f"thb_se3_compose_{_sfx}"] = (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp])
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load libthb200.so (after torch, so the CUDA runtime already mapped by torch is shared)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"libthb200.so not found at {_LIB_PATH}: build it with `python -m theseus_b200.build` "
+            "(theseus_b200 has no CPU or PyTorch fallback for its compute path)")
+    import torch  # noqa: F401  (maps libcudart first)
+    lib = C.CDLL(_LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        kind = "invalid argument" if rc < 0 else "CUDA error"
+        raise RuntimeError(f"libthb200: {what} failed with {kind} code {rc}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

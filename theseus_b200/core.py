@@ -1,0 +1,319 @@
+"""Objective / CostFunction / CostWeight: the host-side mirror of the reference plugin API for the hot path.
+
+  CostWeight, ScaleCostWeight, DiagonalCostWeight   theseus/core/cost_weight.py:20-139
+  CostFunction                                      theseus/core/cost_function.py:64-149
+  Between                                           theseus/embodied/measurements/between.py:14-60
+  Difference (Local)                                theseus/embodied/misc/local_cost_fn.py:15-70
+  Objective                                         theseus/core/objective.py:42-960
+
+What differs from the reference is *how* the objective is evaluated: instead of iterating over cost
+functions in Python and re-batching them with torch.cat at every call (theseus/core/vectorizer.py), the
+objective is compiled once into per-schema tables of device pointers and offsets (engine.py) and every
+evaluation is O(#schemas) CUDA kernels from libthb200.
+"""
+import warnings
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Union
+
+import torch
+
+from .geometry import LieGroup, Manifold, SE3, SO3, Variable, Vector, as_variable
+
+# enum thb_cost_kind / thb_weight_kind (include/thb200.h)
+COST_BETWEEN_SE3, COST_LOCAL_SE3, COST_BETWEEN_SO3, COST_LOCAL_SO3, COST_LOCAL_VECTOR = 0, 1, 2, 3, 4
+WEIGHT_SCALE, WEIGHT_DIAGONAL = 0, 1
+
+
+class CostWeight:
+    WEIGHT_KIND = -1
+
+    def __init__(self, name: Optional[str] = None):
+        self.name = name or f"{self.__class__.__name__}__{id(self)}"
+
+    def weight_tensor(self) -> Variable:
+        raise NotImplementedError
+
+    def to(self, *args, **kwargs):
+        self.weight_tensor().to(*args, **kwargs)
+
+
+class ScaleCostWeight(CostWeight):
+    """theseus/core/cost_weight.py:60-93: tensor [Bw, 1]."""
+    WEIGHT_KIND = WEIGHT_SCALE
+
+    def __init__(self, scale: Union[float, torch.Tensor, Variable], name: Optional[str] = None):
+        super().__init__(name=name)
+        self.scale = as_variable(scale)
+        if not self.scale.tensor.squeeze().ndim in [0, 1]:
+            raise ValueError("ScaleCostWeight only accepts 0- or 1-dim (batched) tensors.")
+        self.scale.tensor = self.scale.tensor.view(-1, 1)
+
+    def weight_tensor(self) -> Variable:
+        return self.scale
+
+    def is_zero(self) -> torch.Tensor:
+        return self.scale.tensor.squeeze(1) == 0
+
+    def copy(self, new_name: Optional[str] = None):
+        return ScaleCostWeight(self.scale.copy(), name=new_name)
+
+
+class DiagonalCostWeight(CostWeight):
+    """theseus/core/cost_weight.py:98-139: tensor [Bw, dim]."""
+    WEIGHT_KIND = WEIGHT_DIAGONAL
+
+    def __init__(self, diagonal: Union[Sequence[float], torch.Tensor, Variable], name: Optional[str] = None):
+        super().__init__(name=name)
+        self.diagonal = as_variable(diagonal)
+        if not self.diagonal.tensor.squeeze().ndim < 3:
+            raise ValueError("DiagonalCostWeight only accepts tensors with ndim < 3.")
+        if self.diagonal.tensor.ndim == 0:
+            self.diagonal.tensor = self.diagonal.tensor.view(1, 1)
+        if self.diagonal.tensor.ndim == 1:
+            warnings.warn("1-D diagonal input is ambiguous. Dimension will be interpreted as dof dimension and not batch dimension.")
+            self.diagonal.tensor = self.diagonal.tensor.view(1, -1)
+
+    def weight_tensor(self) -> Variable:
+        return self.diagonal
+
+    def is_zero(self) -> torch.Tensor:
+        return (self.diagonal.tensor == 0).min(dim=1)[0].bool()
+
+    def copy(self, new_name: Optional[str] = None):
+        return DiagonalCostWeight(self.diagonal.copy(), name=new_name)
+
+
+class CostFunction:
+    """theseus/core/cost_function.py:64-149.  Subclasses with a CUDA schema set COST_KIND via schema()."""
+    _ids = 0
+
+    def __init__(self, cost_weight: CostWeight, name: Optional[str] = None):
+        CostFunction._ids += 1
+        self.name = name or f"{self.__class__.__name__}__{CostFunction._ids}"
+        self.weight = cost_weight
+        self._optim_vars_attr_names: List[str] = []
+        self._aux_vars_attr_names: List[str] = []
+
+    def register_optim_vars(self, names: Sequence[str]):
+        self._optim_vars_attr_names.extend(names)
+
+    def register_aux_vars(self, names: Sequence[str]):
+        self._aux_vars_attr_names.extend(names)
+
+    @property
+    def optim_vars(self):
+        return [getattr(self, n) for n in self._optim_vars_attr_names]
+
+    @property
+    def aux_vars(self):
+        return [getattr(self, n) for n in self._aux_vars_attr_names]
+
+    def optim_var_at(self, index: int) -> Manifold:
+        return getattr(self, self._optim_vars_attr_names[index])
+
+    def num_optim_vars(self) -> int:
+        return len(self._optim_vars_attr_names)
+
+    def dim(self) -> int:
+        raise NotImplementedError
+
+    def schema(self):
+        """(cost kind enum, aux variable) for the CUDA linearize/error kernels."""
+        raise NotImplementedError(
+            f"{self.__class__.__name__} has no CUDA schema in libthb200; supported: Between/Difference on SE3, SO3, Vector")
+
+    def to(self, *args, **kwargs):
+        for v in self.optim_vars + self.aux_vars:
+            v.to(*args, **kwargs)
+        self.weight.to(*args, **kwargs)
+
+
+class Between(CostFunction):
+    """theseus/embodied/measurements/between.py:14-60: e = log(Z^-1 (X0^-1 X1))."""
+
+    def __init__(self, v0: LieGroup, v1: LieGroup, measurement: LieGroup, cost_weight: CostWeight, name: Optional[str] = None):
+        super().__init__(cost_weight, name=name)
+        self.v0, self.v1 = v0, v1
+        self.register_optim_vars(["v0", "v1"])
+        self.measurement = measurement
+        self.register_aux_vars(["measurement"])
+        if not isinstance(v0, v1.__class__) or not isinstance(v0, measurement.__class__):
+            raise ValueError("Inconsistent types between variables and measurement.")
+
+    def dim(self) -> int:
+        return self.v0.dof()
+
+    def schema(self):
+        if isinstance(self.v0, SE3):
+            return COST_BETWEEN_SE3, self.measurement
+        if isinstance(self.v0, SO3):
+            return COST_BETWEEN_SO3, self.measurement
+        return super().schema()
+
+
+class Difference(CostFunction):
+    """theseus/embodied/misc/local_cost_fn.py:15-70 (Local; `Difference` is the public alias): e = log(T^-1 X)."""
+
+    def __init__(self, var: Manifold, target: Manifold, cost_weight: CostWeight, name: Optional[str] = None):
+        super().__init__(cost_weight, name=name)
+        if not isinstance(var, target.__class__):
+            raise ValueError("Variable for the Local inconsistent with the given target.")
+        if not var.dof() == target.dof():
+            raise ValueError("Variable and target in the Local must have identical dof.")
+        self.var, self.target = var, target
+        self.register_optim_vars(["var"])
+        self.register_aux_vars(["target"])
+
+    def dim(self) -> int:
+        return self.var.dof()
+
+    def schema(self):
+        if isinstance(self.var, SE3):
+            return COST_LOCAL_SE3, self.target
+        if isinstance(self.var, SO3):
+            return COST_LOCAL_SO3, self.target
+        if isinstance(self.var, Vector):
+            return COST_LOCAL_VECTOR, self.target
+        return super().schema()
+
+
+Local = Difference
+
+
+class Objective:
+    """theseus/core/objective.py:42-960 (the subset the NLS loop uses)."""
+
+    def __init__(self, dtype: Optional[torch.dtype] = None):
+        self.optim_vars: "OrderedDict[str, Manifold]" = OrderedDict()
+        self.aux_vars: "OrderedDict[str, Variable]" = OrderedDict()
+        self.cost_functions: "OrderedDict[str, CostFunction]" = OrderedDict()
+        self.dtype = dtype or torch.get_default_dtype()
+        self.device = torch.device("cpu")
+        self._batch_size: Optional[int] = None
+        self._structure_version = 0
+        self._engine = None
+
+    # ---- construction ----
+    def add(self, cost_function: CostFunction):
+        """objective.py:210-300: registers the cost function and its variables (first-appearance order)."""
+        if cost_function.name in self.cost_functions:
+            raise ValueError(f"Two different cost function objects with the same name ({cost_function.name}) are not allowed in the same objective.")
+        for v in cost_function.optim_vars + cost_function.aux_vars + [cost_function.weight.weight_tensor()]:
+            if v.dtype != self.dtype:
+                raise ValueError(f"Tried to add cost function with dtype {v.dtype} variable {v.name} to objective of dtype {self.dtype}.")
+        self.cost_functions[cost_function.name] = cost_function
+        for v in cost_function.optim_vars:
+            if v.name in self.optim_vars and self.optim_vars[v.name] is not v:
+                raise ValueError(f"Two different variable objects with the same name ({v.name}) are not allowed in the same objective.")
+            self.optim_vars.setdefault(v.name, v)
+        for v in cost_function.aux_vars + [cost_function.weight.weight_tensor()]:
+            if v.name in self.aux_vars and self.aux_vars[v.name] is not v:
+                raise ValueError(f"Two different variable objects with the same name ({v.name}) are not allowed in the same objective.")
+            self.aux_vars.setdefault(v.name, v)
+        self._structure_version += 1
+        self._engine = None
+        self._batch_size = None
+
+    def dim(self) -> int:
+        return sum(cf.dim() for cf in self.cost_functions.values())
+
+    def size_cost_functions(self) -> int:
+        return len(self.cost_functions)
+
+    def size_variables(self) -> int:
+        return len(self.optim_vars)
+
+    def size_aux_vars(self) -> int:
+        return len(self.aux_vars)
+
+    def get_optim_var(self, name: str) -> Manifold:
+        return self.optim_vars[name]
+
+    def get_aux_var(self, name: str) -> Variable:
+        return self.aux_vars[name]
+
+    def __iter__(self):
+        return iter(self.cost_functions.values())
+
+    @property
+    def batch_size(self) -> int:
+        if self._batch_size is None:
+            self._resolve_batch_size()
+        return self._batch_size
+
+    def _resolve_batch_size(self):
+        """objective.py:708-724."""
+        sizes = set(v.tensor.shape[0] for v in self.optim_vars.values())
+        sizes |= set(v.tensor.shape[0] for v in self.aux_vars.values())
+        if len(sizes) == 1:
+            self._batch_size = next(iter(sizes))
+        elif len(sizes) == 2 and min(sizes) == 1:
+            self._batch_size = max(sizes)
+        else:
+            raise ValueError("Provided tensors must be broadcastable.")
+
+    def to(self, *args, **kwargs) -> "Objective":
+        """objective.py:938-950."""
+        for cf in self.cost_functions.values():
+            cf.to(*args, **kwargs)
+        device, dtype, *_ = torch._C._nn._parse_to(*args, **kwargs)
+        self.device = device or self.device
+        self.dtype = dtype or self.dtype
+        self._engine = None
+        return self
+
+    def update(self, input_tensors: Optional[Dict[str, torch.Tensor]] = None,
+               batch_ignore_mask: Optional[torch.Tensor] = None, _update_vectorization: bool = True):
+        """objective.py:729-811."""
+        input_tensors = input_tensors or {}
+        for var_name, tensor in input_tensors.items():
+            if tensor.ndim < 2:
+                raise ValueError(f"Input tensors must have a batch dimension and one ore more data dimensions, but tensor.ndim={tensor.ndim} for tensor with name {var_name}.")
+            if tensor.device != self.device or tensor.dtype != self.dtype:
+                raise ValueError(
+                    f"Attempted to update variable {var_name} with a ({tensor.device},{tensor.dtype}) tensor, "
+                    f"which is inconsistent with objective's expected ({self.device},{self.dtype}).")
+            if var_name in self.optim_vars:
+                self.optim_vars[var_name].update(tensor, batch_ignore_mask=batch_ignore_mask)
+            elif var_name in self.aux_vars:
+                self.aux_vars[var_name].update(tensor, batch_ignore_mask=batch_ignore_mask)
+            else:
+                warnings.warn(f"Attempted to update a tensor with name {var_name}, which is not associated to any variable in the objective.")
+        self._resolve_batch_size()
+
+    # ---- evaluation (CUDA) ----
+    def engine(self):
+        from .engine import Engine
+        if self._engine is None or self._engine.structure_version != self._structure_version:
+            self._engine = Engine(self)
+        return self._engine
+
+    def error_metric(self, input_tensors: Optional[Dict[str, torch.Tensor]] = None, also_update: bool = False) -> torch.Tensor:
+        """objective.py:615-641: 0.5 * sum((w e)^2) per batch item, shape [B]."""
+        old = {}
+        if input_tensors is not None:
+            if not also_update:
+                old = {n: self.optim_vars[n].tensor for n in self.optim_vars}
+            self.update(input_tensors)
+        err = self.engine().error_metric()
+        if input_tensors is not None and not also_update:
+            self.update(old)
+        return err
+
+    def error(self, input_tensors: Optional[Dict[str, torch.Tensor]] = None, also_update: bool = False) -> torch.Tensor:
+        """objective.py:562-613: weighted error vector [B, m] (= -b of the linearization)."""
+        old = {}
+        if input_tensors is not None:
+            if not also_update:
+                old = {n: self.optim_vars[n].tensor for n in self.optim_vars}
+            self.update(input_tensors)
+        eng = self.engine()
+        _, b = eng.linearize_sparse()
+        if input_tensors is not None and not also_update:
+            self.update(old)
+        return -b
+
+    def retract_vars_sequence(self, delta: torch.Tensor, ordering, ignore_mask: Optional[torch.Tensor] = None,
+                              force_update: bool = False):
+        """objective.py:873-914: X_i <- X_i * exp(delta_i) for the variables in `ordering` (tmp containers)."""
+        self.engine().retract_into(delta, list(ordering), 1.0, None if force_update else ignore_mask)

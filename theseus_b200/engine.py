@@ -1,0 +1,328 @@
+"""Engine: an Objective compiled into device-resident index tables + the kernel launches over them.
+
+This replaces theseus/core/vectorizer.py (Vectorize): instead of torch.cat-ing the tensors of same-schema
+cost functions at every evaluation, the objective structure is compiled ONCE into
+  * per-schema cost groups (pointer tables to every cost function's variable / measurement / weight tensor),
+  * the reference's batched-CSR layout of the Jacobian (structure.py),
+  * Gram gather plans,
+and every evaluation is O(#schemas) kernel launches from libthb200 on the current CUDA stream.
+
+Optimisation variables are kept in two engine-owned pools (current / trial) so that device pointers stay
+stable across LM iterations (no table rebuilds, CUDA-graph friendly); `Variable.tensor` of each
+optimisation variable is a [B, ...] view into the pool.
+"""
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .geometry import Manifold, Variable
+from .structure import build_gram_plan, build_structure
+
+
+def _dev(arr: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+
+
+class _Group:
+    """One cost-function schema: static placement arrays + (re)bindable pointer tables."""
+
+    def __init__(self, kind, weight_kind, dim, cost_indices):
+        self.kind, self.weight_kind, self.dim = kind, weight_kind, dim
+        self.cost_indices = cost_indices
+        self.K = len(cost_indices)
+        self.static = {}
+        self.bound = {}  # binding name -> (struct, keepalive tensors)
+
+
+class Engine:
+    def __init__(self, objective):
+        self.objective = objective
+        self.structure_version = objective._structure_version
+        self.device = torch.device(objective.device)
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                "theseus_b200: the objective must live on a CUDA device (call objective.to('cuda')); "
+                "there is no CPU implementation of the linearize/solve/retract path in this package")
+        self.dtype = objective.dtype
+        if self.dtype not in (torch.float64, torch.float32):
+            raise ValueError(f"unsupported dtype {self.dtype}")
+        self.sfx = "f64" if self.dtype == torch.float64 else "f32"
+        self.lib = _lib.load()
+
+        # ---- ordering (theseus/optimizer/variable_ordering.py:19-27: order of first appearance) ----
+        self.ordering: List[Manifold] = list(objective.optim_vars.values())
+        self.var_index = {v.name: i for i, v in enumerate(self.ordering)}
+        costs = list(objective.cost_functions.values())
+        self.costs = costs
+        cdesc = [(cf.dim(), [self.var_index[v.name] for v in cf.optim_vars]) for cf in costs]
+        self.structure = build_structure([v.dof() for v in self.ordering], cdesc)
+        S = self.structure
+        self.n, self.m, self.nnz = S.num_cols, S.num_rows, S.nnz
+
+        # ---- schema groups ----
+        groups = {}
+        self._aux_of = []
+        for f, cf in enumerate(costs):
+            kind, aux = cf.schema()
+            self._aux_of.append(aux)
+            key = (kind, cf.weight.WEIGHT_KIND, cf.dim())
+            groups.setdefault(key, []).append(f)
+        self.groups: List[_Group] = []
+        dev = self.device
+        for (kind, wkind, dim), idx in groups.items():
+            g = _Group(kind, wkind, dim, idx)
+            ii = np.array(idx, dtype=np.int64)
+            bp = np.zeros((g.K, 2), dtype=np.int32)
+            for r, f in enumerate(idx):
+                p = S.block_pointers[f]
+                bp[r, : len(p)] = p
+            g.static = dict(
+                a_off=_dev(S.row_block_starts[ii], dev), a_stride=_dev(S.stride[ii].astype(np.int32), dev),
+                bp=_dev(bp, dev), row0=_dev(S.cost_row0[ii].astype(np.int32), dev))
+            self.groups.append(g)
+        self.num_chunks = [int(self.lib.thb_error_num_chunks(g.K)) for g in self.groups]
+        self.total_chunks = int(sum(self.num_chunks))
+
+        # ---- variable table static parts ----
+        self._vt_static = dict(
+            kind=_dev(np.array([v.KIND for v in self.ordering], dtype=np.int32), dev),
+            col=_dev(S.var_start_cols.astype(np.int32), dev),
+            dof=_dev(S.var_dims.astype(np.int32), dev))
+
+        self._B = None
+        self._pool_cur = self._pool_tmp = None
+        self.cur_views: List[torch.Tensor] = []
+        self.tmp_views: List[torch.Tensor] = []
+        self._bind_stamp = {"cur": -1, "tmp": -1}
+        self._vt = None
+        self._gram_dense = None
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ pools / bindings
+    @property
+    def batch_size(self) -> int:
+        return self.objective.batch_size
+
+    def _ensure_pools(self):
+        B = self.batch_size
+        if self._B == B and self._pool_cur is not None:
+            return
+        self._B = B
+        sizes = [v.numel() for v in self.ordering]
+        offs = np.concatenate([[0], np.cumsum([B * s for s in sizes])]).astype(np.int64)
+        total = int(offs[-1])
+        self._pool_cur = torch.empty(total, dtype=self.dtype, device=self.device)
+        self._pool_tmp = torch.empty(total, dtype=self.dtype, device=self.device)
+        self.cur_views, self.tmp_views = [], []
+        for i, v in enumerate(self.ordering):
+            shp = (B,) + tuple(v.tensor.shape[1:])
+            self.cur_views.append(self._pool_cur[offs[i]:offs[i + 1]].view(shp))
+            self.tmp_views.append(self._pool_tmp[offs[i]:offs[i + 1]].view(shp))
+        self._bufs = {}
+        self._vt = None
+        self._bind_stamp = {"cur": -1, "tmp": -1}
+
+    def adopt_optim_vars(self):
+        """Move every optimisation variable into the engine-owned pool (copying the current values) so that
+        the optimiser can update them in place without touching caller-owned tensors."""
+        self._ensure_pools()
+        src, dst = [], []
+        for v, view in zip(self.ordering, self.cur_views):
+            t = v.tensor
+            if t.data_ptr() == view.data_ptr() and t.shape == view.shape:
+                continue
+            if t.device != self.device or t.dtype != self.dtype:
+                raise ValueError(f"variable {v.name} is on ({t.device},{t.dtype}), objective expects ({self.device},{self.dtype})")
+            src.append(t.expand(view.shape) if t.shape[0] != view.shape[0] else t)
+            dst.append(view)
+        if src:
+            torch._foreach_copy_(dst, src)
+            for v, view in zip(self.ordering, self.cur_views):
+                if v.tensor.data_ptr() != view.data_ptr():
+                    v.tensor = view
+
+    def _ptr_array(self, tensors) -> torch.Tensor:
+        return _dev(np.fromiter((t.data_ptr() for t in tensors), dtype=np.int64, count=len(tensors)), self.device)
+
+    def _bind(self, which: str):
+        """(Re)build the pointer tables of every group for binding `which` ('cur' = objective variables,
+        'tmp' = trial pool) if any variable tensor was rebound since the last build."""
+        if self._bind_stamp[which] == Variable._global_updates:
+            return
+        B = self.batch_size
+        if which == "tmp" or self._B is not None:
+            self._ensure_pools()
+
+        def optim_tensor(v):
+            if which == "tmp":
+                return self.tmp_views[self.var_index[v.name]]
+            t = v.tensor
+            if t.device != self.device:
+                raise ValueError(f"variable {v.name} is on {t.device}, objective is on {self.device}")
+            if not t.is_contiguous():
+                t = t.contiguous()
+                v.tensor = t
+            return t
+
+        def aux_tensor(v):
+            t = v.tensor
+            if t.device != self.device or t.dtype != self.dtype:
+                raise ValueError(f"variable {v.name} is on ({t.device},{t.dtype}), objective expects ({self.device},{self.dtype})")
+            if not t.is_contiguous():
+                t = t.contiguous()
+                v.tensor = t
+            return t
+
+        def bstride(t):
+            if t.shape[0] == B:
+                return int(t[0].numel())
+            if t.shape[0] == 1:
+                return 0
+            raise ValueError("Provided tensors must be broadcastable.")
+
+        for g in self.groups:
+            x0, x1, aux, w = [], [], [], []
+            bs = np.zeros((g.K, 4), dtype=np.int32)
+            for r, f in enumerate(g.cost_indices):
+                cf = self.costs[f]
+                ov = cf.optim_vars
+                t0 = optim_tensor(ov[0])
+                t1 = optim_tensor(ov[1]) if len(ov) > 1 else t0
+                ta = aux_tensor(self._aux_of[f])
+                tw = aux_tensor(cf.weight.weight_tensor())
+                x0.append(t0); x1.append(t1); aux.append(ta); w.append(tw)
+                bs[r] = (bstride(t0), bstride(t1), bstride(ta), bstride(tw))
+            keep = dict(x0=self._ptr_array(x0), x1=self._ptr_array(x1), aux=self._ptr_array(aux), w=self._ptr_array(w),
+                        bstride=_dev(bs, self.device), tensors=(x0, x1, aux, w))
+            st = _lib.CostGroup(
+                kind=g.kind, weight_kind=g.weight_kind, K=g.K, dim=g.dim,
+                x0=keep["x0"].data_ptr(), x1=keep["x1"].data_ptr(), aux=keep["aux"].data_ptr(), w=keep["w"].data_ptr(),
+                bstride=keep["bstride"].data_ptr(), a_off=g.static["a_off"].data_ptr(),
+                a_stride=g.static["a_stride"].data_ptr(), bp=g.static["bp"].data_ptr(), row0=g.static["row0"].data_ptr())
+            g.bound[which] = (st, keep)
+        # NOTE: _bind may itself rebind non-contiguous tensors (bumping the counter); read it afterwards.
+        self._bind_stamp[which] = Variable._global_updates
+        if which == "cur":
+            self._vt = None
+
+    def _var_table(self):
+        """thb_var_table: x = current variables, out = trial pool."""
+        self._ensure_pools()
+        self._bind("cur")
+        if self._vt is None:
+            xs = [v.tensor for v in self.ordering]
+            for v, t in zip(self.ordering, xs):
+                if t.shape[0] != self._B:
+                    raise ValueError(f"optimisation variable {v.name} has batch {t.shape[0]} != {self._B}; call adopt_optim_vars()")
+            keep = dict(x=self._ptr_array(xs), out=self._ptr_array(self.tmp_views))
+            st = _lib.VarTable(N=len(xs), x=keep["x"].data_ptr(), out=keep["out"].data_ptr(),
+                               kind=self._vt_static["kind"].data_ptr(), col=self._vt_static["col"].data_ptr(),
+                               dof=self._vt_static["dof"].data_ptr())
+            self._vt = (st, keep)
+        return self._vt[0]
+
+    def buf(self, name, shape, dtype=None, zero=False):
+        key = (name, tuple(shape), dtype or self.dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype or self.dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def buf_const(self, name, arr: np.ndarray):
+        key = ("const", name)
+        t = self._bufs.get(key)
+        if t is None:
+            t = _dev(arr, self.device)
+            self._bufs[key] = t
+        return t
+
+    # ------------------------------------------------------------------ kernels
+    def linearize_sparse(self, A_val: Optional[torch.Tensor] = None, b: Optional[torch.Tensor] = None):
+        """A_val [B,nnz], b [B,m] in the layout of SparseLinearization (optimizer/sparse_linearization.py:102-140)."""
+        self._bind("cur")
+        B = self.batch_size
+        if A_val is None:
+            A_val = self.buf("A_val", (B, self.nnz))
+        if b is None:
+            b = self.buf("b", (B, self.m))
+        fn = getattr(self.lib, f"thb_linearize_group_{self.sfx}")
+        s = _lib.stream_ptr()
+        for g in self.groups:
+            _lib.check(fn(C.byref(g.bound["cur"][0]), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, s), "linearize_group")
+        return A_val, b
+
+    def error_metric(self, which: str = "cur", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """0.5 * sum((w e)^2) per batch item (core/objective.py:615-641), deterministic two-stage reduction."""
+        self._bind(which)
+        B = self.batch_size
+        partial = self.buf("err_partial", (max(self.total_chunks, 1), B))
+        if out is None:
+            out = torch.empty(B, dtype=self.dtype, device=self.device)
+        fn = getattr(self.lib, f"thb_error_group_{self.sfx}")
+        s = _lib.stream_ptr()
+        row = 0
+        for g, nc in zip(self.groups, self.num_chunks):
+            _lib.check(fn(C.byref(g.bound[which][0]), B, _lib.ptr(partial[row:]), s), "error_group")
+            row += nc
+        _lib.check(getattr(self.lib, f"thb_error_reduce_{self.sfx}")(_lib.ptr(partial), self.total_chunks, B, _lib.ptr(out), s), "error_reduce")
+        return out
+
+    def gram_plan_dense(self):
+        if self._gram_dense is None:
+            arrs = build_gram_plan(self.structure)
+            dev = {k: _dev(v, self.device) for k, v in arrs.items() if isinstance(v, np.ndarray)}
+            st = _lib.GramPlan(
+                num_entries=int(arrs["ent_blk"].shape[0]), ent_blk=dev["ent_blk"].data_ptr(), ent_p=dev["ent_p"].data_ptr(),
+                ent_q=dev["ent_q"].data_ptr(), blk_out=dev["blk_out"].data_ptr(), blk_ld=dev["blk_ld"].data_ptr(),
+                blk_mirror=dev["blk_mirror"].data_ptr(), blk_cptr=dev["blk_cptr"].data_ptr(), c_off=dev["c_off"].data_ptr(),
+                c_stride=dev["c_stride"].data_ptr(), c_rows=dev["c_rows"].data_ptr(), c_bpa=dev["c_bpa"].data_ptr(),
+                c_bpb=dev["c_bpb"].data_ptr(), n=int(arrs["n"]), col_cptr=dev["col_cptr"].data_ptr(),
+                cc_off=dev["cc_off"].data_ptr(), cc_stride=dev["cc_stride"].data_ptr(), cc_rows=dev["cc_rows"].data_ptr(),
+                cc_row0=dev["cc_row0"].data_ptr())
+            self._gram_dense = (st, dev)
+        return self._gram_dense[0]
+
+    def gram_dense(self, A_val, b, AtA, Atb, diag):
+        """AtA [B,n,n] (zero-filled then block scatter), Atb [B,n], diag(AtA) [B,n]."""
+        if self.sfx != "f64":
+            raise NotImplementedError("dense Gram assembly is fp64-only in libthb200 r1")
+        B = self.batch_size
+        s = _lib.stream_ptr()
+        plan = self.gram_plan_dense()
+        _lib.check(self.lib.thb_fill_zero(_lib.ptr(AtA), AtA.numel() * AtA.element_size(), s), "fill_zero")
+        _lib.check(self.lib.thb_gram_f64(C.byref(plan), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, _lib.ptr(AtA),
+                                         self.n * self.n, _lib.ptr(Atb), _lib.ptr(diag), s), "gram")
+
+    def atb(self, A_val, b, Atb, diag=None):
+        plan = self.gram_plan_dense()
+        _lib.check(self.lib.thb_gram_f64(C.byref(plan), self.batch_size, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, None,
+                                         0, _lib.ptr(Atb), _lib.ptr(diag), _lib.stream_ptr()), "atb")
+
+    def retract_into(self, delta: torch.Tensor, out_vars, step: float, ignore_mask: Optional[torch.Tensor]):
+        """tmp_i <- X_i * exp(step * delta_i), masked (core/objective.py:873-914)."""
+        vt = self._var_table()
+        for v, view in zip(out_vars, self.tmp_views):
+            if v.tensor.data_ptr() != view.data_ptr():
+                v.tensor = view  # trial containers are views of the trial pool
+        B = self.batch_size
+        delta = delta.contiguous()
+        ig = None
+        if ignore_mask is not None:
+            ig = ignore_mask.to(torch.uint8) if ignore_mask.dtype != torch.uint8 else ignore_mask
+        fn = getattr(self.lib, f"thb_retract_{self.sfx}")
+        _lib.check(fn(C.byref(vt), B, _lib.ptr(delta), self.n, float(step), _lib.ptr(ig), _lib.stream_ptr()), "retract")
+        self._keep = (delta, ig)
+
+    def commit(self, keep_old_mask: Optional[torch.Tensor]):
+        """X_i[b] <- tmp_i[b] where keep_old_mask[b] == 0 (objective.update(..., batch_ignore_mask), variable.py:65-69)."""
+        vt = self._var_table()
+        km = None
+        if keep_old_mask is not None:
+            km = keep_old_mask.to(torch.uint8) if keep_old_mask.dtype != torch.uint8 else keep_old_mask
+        fn = getattr(self.lib, f"thb_commit_{self.sfx}")
+        _lib.check(fn(C.byref(vt), self.batch_size, _lib.ptr(km), _lib.stream_ptr()), "commit")
+        self._keep2 = km

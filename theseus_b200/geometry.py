@@ -1,0 +1,263 @@
+"""Variables and Lie groups: the host-side mirror of theseus.core.Variable / theseus.geometry.* for the
+types on the hot path (SE3, SO3, Vector, Point3).
+
+Same names, storage layouts and argument meaning as the reference:
+  Variable            theseus/core/variable.py:17-120     (tensor, name, update(data, batch_ignore_mask), copy)
+  Manifold / LieGroup theseus/geometry/manifold.py:31-195, theseus/geometry/lie_group.py:24-203
+  SE3 [B,3,4], SO3 [B,3,3], Vector/Point3 [B,k]            theseus/geometry/{se3,so3,vector,point_types}.py
+The group arithmetic runs in the CUDA library (theseus_b200/csrc/thb_lie.cuh through the C ABI); calling a
+compute method on a CPU tensor raises -- there is no CPU implementation in the product.
+"""
+import itertools
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"theseus_b200.{what}: tensors must live on a CUDA device (B200); the product has no CPU path")
+
+
+class Variable:
+    """theseus/core/variable.py:17-120."""
+    _ids = itertools.count(0)
+    _global_updates = 0  # bumped on every (re)binding of any variable's tensor; lets engines detect stale pointer tables in O(1)
+
+    def __init__(self, tensor: torch.Tensor, name: Optional[str] = None):
+        self._id = next(Variable._ids)
+        self._num_updates = 0
+        self.name = name if name else f"{self.__class__.__name__}__{self._id}"
+        self._tensor = None
+        self.tensor = tensor
+
+    @property
+    def tensor(self) -> torch.Tensor:
+        return self._tensor
+
+    @tensor.setter
+    def tensor(self, t: torch.Tensor):
+        self._tensor = t
+        Variable._global_updates += 1
+
+    def copy(self, new_name: Optional[str] = None) -> "Variable":
+        if not new_name:
+            new_name = f"{self.name}_copy"
+        return self.__class__(tensor=self.tensor.clone(), name=new_name) if type(self) is not Variable \
+            else Variable(self.tensor.clone(), name=new_name)
+
+    def update(self, data, batch_ignore_mask: Optional[torch.Tensor] = None):
+        tensor = data.tensor if isinstance(data, Variable) else data
+        if len(tensor.shape) != len(self.tensor.shape) or tensor.shape[1:] != self.tensor.shape[1:]:
+            raise ValueError(
+                f"Tried to update tensor {self.name} with data incompatible with original tensor shape. "
+                f"Given {tensor.shape[1:]}. Expected: {self.tensor.shape[1:]}")
+        if tensor.dtype != self.dtype:
+            raise ValueError(f"Tried to update used tensor of dtype {tensor.dtype} but Variable {self.name} has dtype {self.dtype}.")
+        if batch_ignore_mask is not None and batch_ignore_mask.any():
+            mask_shape = (-1,) + (1,) * (tensor.ndim - 1)
+            self.tensor = torch.where(batch_ignore_mask.view(mask_shape), self.tensor, tensor)
+        else:
+            self.tensor = tensor
+        self._num_updates += 1
+
+    def to(self, *args, **kwargs):
+        self.tensor = self.tensor.to(*args, **kwargs)
+
+    @property
+    def shape(self):
+        return self.tensor.shape
+
+    @property
+    def device(self):
+        return self.tensor.device
+
+    @property
+    def dtype(self):
+        return self.tensor.dtype
+
+    @property
+    def ndim(self):
+        return self.tensor.ndim
+
+    def __getitem__(self, item):
+        return self.tensor[item]
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(tensor={self.tensor}, name={self.name})"
+
+
+def as_variable(value, device=None, dtype=None, name: Optional[str] = None) -> Variable:
+    """theseus/core/variable.py:123-160 (as_variable)."""
+    if isinstance(value, Variable):
+        return value
+    t = torch.as_tensor(value)
+    if not t.is_floating_point():
+        t = t.to(torch.get_default_dtype())
+    t = t.to(device=device, dtype=dtype)
+    if t.ndim == 0:
+        t = t.view(1, 1)
+    elif t.ndim == 1:
+        t = t.view(1, -1)
+    return Variable(t, name=name)
+
+
+class Manifold(Variable):
+    """theseus/geometry/manifold.py:31-195 (dof, retract, local)."""
+    KIND = -1
+
+    def dof(self) -> int:
+        raise NotImplementedError
+
+    def numel(self) -> int:
+        return self.tensor[0].numel()
+
+    def copy(self, new_name: Optional[str] = None):
+        if not new_name:
+            new_name = f"{self.name}_copy"
+        return self.__class__(tensor=self.tensor.clone(), name=new_name)
+
+
+class Vector(Manifold):
+    """theseus/geometry/vector.py (Vector): x [+] d = x + d; local(a, b) = b - a."""
+    KIND = 2  # THB_VAR_VECTOR
+
+    def __init__(self, dof: Optional[int] = None, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None,
+                 dtype: Optional[torch.dtype] = None):
+        if tensor is None:
+            if dof is None:
+                raise ValueError("Either dof or tensor must be given")
+            tensor = torch.zeros(1, dof, dtype=dtype or torch.get_default_dtype())
+        if tensor.ndim == 1:
+            tensor = tensor.view(1, -1)
+        if tensor.ndim != 2:
+            raise ValueError("Vector tensors must have shape [batch, dof]")
+        super().__init__(tensor, name=name)
+
+    def dof(self) -> int:
+        return self.tensor.shape[1]
+
+    def retract(self, delta: torch.Tensor) -> "Vector":
+        return self.__class__(tensor=self.tensor + delta)
+
+    def local(self, other: "Vector") -> torch.Tensor:
+        return other.tensor - self.tensor
+
+
+class Point3(Vector):
+    """theseus/geometry/point_types.py (Point3)."""
+
+    def __init__(self, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None, dtype: Optional[torch.dtype] = None):
+        if tensor is not None and tensor.shape[-1] != 3:
+            raise ValueError("Point3 tensors must have shape [batch, 3]")
+        super().__init__(dof=3, tensor=tensor, name=name, dtype=dtype)
+
+
+class Point2(Vector):
+    def __init__(self, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None, dtype: Optional[torch.dtype] = None):
+        if tensor is not None and tensor.shape[-1] != 2:
+            raise ValueError("Point2 tensors must have shape [batch, 2]")
+        super().__init__(dof=2, tensor=tensor, name=name, dtype=dtype)
+
+
+def _sfx(t: torch.Tensor) -> str:
+    if t.dtype == torch.float64:
+        return "f64"
+    if t.dtype == torch.float32:
+        return "f32"
+    raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+class LieGroup(Manifold):
+    """theseus/geometry/lie_group.py:24-203."""
+
+    def retract(self, delta: torch.Tensor) -> "LieGroup":
+        return self.compose(self.exp_map(delta))
+
+    def local(self, other: "LieGroup", jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        return self.between(other).log_map(jacobians)
+
+    def between(self, other: "LieGroup") -> "LieGroup":
+        return self.inverse().compose(other)
+
+
+class SE3(LieGroup):
+    """theseus/geometry/se3.py:20 -- storage [B,3,4] = [R|t], tangent [v, w]."""
+    KIND = 0  # THB_VAR_SE3
+
+    def __init__(self, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None,
+                 dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
+        if tensor is None:
+            tensor = torch.eye(3, 4, dtype=dtype or torch.get_default_dtype()).view(1, 3, 4)
+        if tensor.ndim != 3 or tensor.shape[1:] != (3, 4):
+            raise ValueError("SE3 data tensors can only be 3x4 matrices.")  # geometry/se3.py:117-125
+        super().__init__(tensor, name=name)
+
+    def dof(self) -> int:
+        return 6
+
+    # ---- group arithmetic on the GPU (torchlie.functional.SE3 equivalents) ----
+    @staticmethod
+    def exp_map(tangent_vector: torch.Tensor) -> "SE3":
+        _require_cuda(tangent_vector, "SE3.exp_map")
+        lib = _lib.load()
+        t = tangent_vector.contiguous()
+        out = torch.empty(t.shape[0], 3, 4, dtype=t.dtype, device=t.device)
+        _lib.check(getattr(lib, f"thb_se3_exp_{_sfx(t)}")(_lib.ptr(t), _lib.ptr(out), t.shape[0], _lib.stream_ptr()), "se3_exp")
+        return SE3(tensor=out)
+
+    def log_map(self, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        g = self.tensor.contiguous()
+        _require_cuda(g, "SE3.log_map")
+        lib = _lib.load()
+        out = torch.empty(g.shape[0], 6, dtype=g.dtype, device=g.device)
+        jl = torch.empty(g.shape[0], 6, 6, dtype=g.dtype, device=g.device) if jacobians is not None else None
+        _lib.check(getattr(lib, f"thb_se3_log_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), _lib.ptr(jl), g.shape[0], _lib.stream_ptr()), "se3_log")
+        if jacobians is not None:
+            jacobians.append(jl)
+        return out
+
+    def adjoint(self) -> torch.Tensor:
+        g = self.tensor.contiguous()
+        _require_cuda(g, "SE3.adjoint")
+        lib = _lib.load()
+        out = torch.empty(g.shape[0], 6, 6, dtype=g.dtype, device=g.device)
+        _lib.check(getattr(lib, f"thb_se3_adjoint_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), g.shape[0], _lib.stream_ptr()), "se3_adjoint")
+        return out
+
+    def inverse(self) -> "SE3":
+        g = self.tensor.contiguous()
+        _require_cuda(g, "SE3.inverse")
+        lib = _lib.load()
+        out = torch.empty_like(g)
+        _lib.check(getattr(lib, f"thb_se3_inverse_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), g.shape[0], _lib.stream_ptr()), "se3_inverse")
+        return SE3(tensor=out)
+
+    def compose(self, other: "SE3") -> "SE3":
+        a, b = self.tensor.contiguous(), other.tensor.contiguous()
+        _require_cuda(a, "SE3.compose")
+        if a.shape[0] != b.shape[0]:
+            B = max(a.shape[0], b.shape[0])
+            a, b = a.expand(B, 3, 4).contiguous(), b.expand(B, 3, 4).contiguous()
+        lib = _lib.load()
+        out = torch.empty_like(a)
+        _lib.check(getattr(lib, f"thb_se3_compose_{_sfx(a)}")(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], _lib.stream_ptr()), "se3_compose")
+        return SE3(tensor=out)
+
+
+class SO3(LieGroup):
+    """theseus/geometry/so3.py:20 -- storage [B,3,3]."""
+    KIND = 1  # THB_VAR_SO3
+
+    def __init__(self, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None,
+                 dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
+        if tensor is None:
+            tensor = torch.eye(3, dtype=dtype or torch.get_default_dtype()).view(1, 3, 3)
+        if tensor.ndim != 3 or tensor.shape[1:] != (3, 3):
+            raise ValueError("SO3 data tensors can only be 3x3 matrices.")
+        super().__init__(tensor, name=name)
+
+    def dof(self) -> int:
+        return 3

@@ -1,0 +1,584 @@
+"""Linearization / LinearSolver / NonlinearLeastSquares (GaussNewton, LevenbergMarquardt): the host-side
+mirror of theseus/optimizer/{linearization,dense_linearization,sparse_linearization}.py,
+theseus/optimizer/linear/{linear_solver,dense_solver}.py and theseus/optimizer/nonlinear/*.py.
+
+Same class names, constructor / solve / optimize kwargs, info fields and error behaviour as the reference
+(a non-PD system surfaces as RuntimeError, caught by the loop under no_grad -> status FAIL,
+nonlinear_least_squares.py:138-152), so the parity tests read like the reference's own tests.  The
+arithmetic is the CUDA library; the Python below only sequences kernel launches.
+"""
+import math
+import warnings
+from dataclasses import dataclass
+from enum import Enum
+from typing import Any, Dict, Optional, Type, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .core import Objective
+from .structure import ata_block_structure
+
+
+# ------------------------------------------------------------------------------------------------ linearization
+class VariableOrdering:
+    """theseus/optimizer/variable_ordering.py:11-60 (default order = first appearance)."""
+
+    def __init__(self, objective: Objective, default_order: bool = True):
+        self.objective = objective
+        self._var_order = list(objective.optim_vars.values()) if default_order else []
+        self._var_name_to_index = {v.name: i for i, v in enumerate(self._var_order)}
+
+    def index_of(self, key: str) -> int:
+        return self._var_name_to_index[key]
+
+    def __getitem__(self, index):
+        return self._var_order[index]
+
+    def __iter__(self):
+        return iter(self._var_order)
+
+    def __len__(self):
+        return len(self._var_order)
+
+    @property
+    def complete(self):
+        return len(self._var_order) == self.objective.size_variables()
+
+
+class Linearization:
+    """theseus/optimizer/linearization.py:16-87."""
+
+    def __init__(self, objective: Objective, ordering: Optional[VariableOrdering] = None, **kwargs):
+        self.objective = objective
+        if ordering is not None and [v.name for v in ordering] != list(objective.optim_vars.keys()):
+            raise NotImplementedError("theseus_b200 r1 supports the default variable ordering only")
+        self.ordering = ordering or VariableOrdering(objective)
+        if not self.ordering.complete:
+            raise ValueError("Given variable ordering is not complete.")
+        self.var_dims = [v.dof() for v in self.ordering]
+        self.var_start_cols = list(np.concatenate([[0], np.cumsum(self.var_dims)[:-1]]).astype(int)) if self.var_dims else []
+        self.num_cols = int(sum(self.var_dims))
+        self.num_rows = objective.dim()
+
+    @property
+    def engine(self):
+        return self.objective.engine()
+
+    def linearize(self, _detach_hessian: bool = False):
+        if not self.ordering.complete:
+            raise RuntimeError("Attempted to linearize an objective with an incomplete variable order.")
+        self._linearize_hessian_impl(_detach_hessian=_detach_hessian)
+
+    @property
+    def AtA(self) -> torch.Tensor:
+        return self._ata_impl()
+
+    @property
+    def Atb(self) -> torch.Tensor:
+        return self._atb_impl()
+
+
+class SparseLinearization(Linearization):
+    """theseus/optimizer/sparse_linearization.py:19-198: batch-shared CSR pattern, A_val [B,nnz], b [B,m]."""
+
+    def __init__(self, objective: Objective, ordering: Optional[VariableOrdering] = None, **kwargs):
+        super().__init__(objective, ordering)
+        from .structure import build_structure
+        idx = {v.name: i for i, v in enumerate(self.ordering)}
+        S = build_structure(self.var_dims, [(cf.dim(), [idx[v.name] for v in cf.optim_vars]) for cf in objective.cost_functions.values()])
+        self.A_row_ptr, self.A_col_ind = S.A_row_ptr, S.A_col_ind
+        self.cost_function_block_pointers = S.block_pointers
+        self.cost_function_row_block_starts = S.row_block_starts
+        self.cost_function_stride = S.stride
+        self._structure = S
+        self.A_val: torch.Tensor = None
+        self.b: torch.Tensor = None
+        self._Atb = None
+        self._AtA_diag = None
+        self.detached_hessian = False
+
+    def _linearize_jacobian_impl(self):
+        self._Atb = None
+        self._AtA_diag = None
+        self.A_val, self.b = self.engine.linearize_sparse()
+
+    def _linearize_hessian_impl(self, _detach_hessian: bool = False):
+        self._linearize_jacobian_impl()
+        self.detached_hessian = _detach_hessian
+
+    def _ata_impl(self):
+        raise NotImplementedError("AtA is not yet implemented for SparseLinearization.")  # same as the reference
+
+    def _compute_atb_diag(self):
+        eng = self.engine
+        B = eng.batch_size
+        Atb = eng.buf("sp_Atb", (B, self.num_cols))
+        diag = eng.buf("sp_diag", (B, self.num_cols))
+        eng.atb(self.A_val, self.b, Atb, diag)
+        self._Atb, self._AtA_diag = Atb, diag
+
+    def _atb_impl(self) -> torch.Tensor:
+        if self._Atb is None:
+            self._compute_atb_diag()
+        return self._Atb.unsqueeze(2)
+
+    def diagonal_scaling(self, v: torch.Tensor) -> torch.Tensor:
+        if self._AtA_diag is None:
+            self._compute_atb_diag()
+        return self._AtA_diag * v
+
+    def Av(self, v: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        rp = eng.buf_const("A_row_ptr", self.A_row_ptr)
+        ci = eng.buf_const("A_col_ind", self.A_col_ind)
+        out = torch.empty(v.shape[0], self.num_rows, dtype=v.dtype, device=v.device)
+        _lib.check(eng.lib.thb_mat_vec_f64(v.shape[0], self.num_rows, self.num_cols, _lib.ptr(rp), _lib.ptr(ci),
+                                            _lib.ptr(self.A_val), _lib.ptr(v.contiguous()), _lib.ptr(out), _lib.stream_ptr()), "mat_vec")
+        return out
+
+    def structure(self):
+        return self._structure
+
+
+class DenseLinearization(Linearization):
+    """theseus/optimizer/dense_linearization.py:16-80.  AtA [B,n,n], Atb [B,n,1]; A [B,m,n] is materialised
+    only on request (property `A`), the hot path never forms the 99%-zero dense Jacobian."""
+
+    def __init__(self, objective: Objective, ordering: Optional[VariableOrdering] = None, **kwargs):
+        super().__init__(objective, ordering)
+        self.b: torch.Tensor = None
+        self._A_val = None
+        self._AtA = None
+        self._Atb = None
+        self._diag = None
+
+    def _linearize_jacobian_impl(self):
+        self._A_val, self.b = self.engine.linearize_sparse()
+
+    def _linearize_hessian_impl(self, _detach_hessian: bool = False):
+        self._linearize_jacobian_impl()
+        eng = self.engine
+        B, n = eng.batch_size, self.num_cols
+        self._AtA = eng.buf("AtA", (B, n, n))
+        self._Atb = eng.buf("Atb", (B, n))
+        self._diag = eng.buf("AtA_diag", (B, n))
+        eng.gram_dense(self._A_val, self.b, self._AtA, self._Atb, self._diag)
+
+    @property
+    def A(self) -> torch.Tensor:
+        """Dense Jacobian [B,m,n] scattered from the CSR values (debug / parity only)."""
+        S = self.engine.structure
+        B = self._A_val.shape[0]
+        A = torch.zeros(B, self.num_rows, self.num_cols, dtype=self._A_val.dtype, device=self._A_val.device)
+        rows = torch.from_numpy(np.repeat(np.arange(S.num_rows), np.diff(S.A_row_ptr))).to(A.device)
+        cols = torch.from_numpy(S.A_col_ind).to(A.device)
+        A[:, rows, cols] = self._A_val
+        return A
+
+    def hessian_approx(self):
+        return self._AtA
+
+    def _ata_impl(self) -> torch.Tensor:
+        return self._AtA
+
+    def _atb_impl(self) -> torch.Tensor:
+        return self._Atb.unsqueeze(2)
+
+    def Av(self, v: torch.Tensor) -> torch.Tensor:
+        return self.A.bmm(v.unsqueeze(2)).squeeze(2)
+
+    def diagonal_scaling(self, v: torch.Tensor) -> torch.Tensor:
+        return v * self._diag
+
+
+# ------------------------------------------------------------------------------------------------ linear solvers
+def convert_to_alpha_beta_damping_tensors(damping, damping_eps: float, ellipsoidal_damping: bool, batch_size: int, device, dtype):
+    """theseus/optimizer/linear/utils.py:14-33."""
+    damping = torch.as_tensor(damping).to(device=device, dtype=dtype)
+    if damping.ndim > 1:
+        raise ValueError("Damping must be a float or a 1-D tensor.")
+    if damping.ndim == 0 or damping.shape[0] == 1 and batch_size != 1:
+        damping = damping.repeat(batch_size)
+    return (damping, damping_eps * torch.ones_like(damping)) if ellipsoidal_damping else (torch.zeros_like(damping), damping)
+
+
+class LinearSolver:
+    """theseus/optimizer/linear/linear_solver.py:15-37."""
+
+    def __init__(self, objective: Objective, linearization_cls: Optional[Type[Linearization]] = None,
+                 linearization_kwargs: Optional[Dict[str, Any]] = None, **kwargs):
+        linearization_kwargs = linearization_kwargs or {}
+        self.linearization: Linearization = linearization_cls(objective, **linearization_kwargs)
+
+    def reset(self, **kwargs):
+        pass
+
+    def solve(self, damping=None, **kwargs) -> torch.Tensor:
+        raise NotImplementedError
+
+
+class DenseSolver(LinearSolver):
+    """theseus/optimizer/linear/dense_solver.py:19-123."""
+
+    def __init__(self, objective: Objective, linearization_cls: Optional[Type[Linearization]] = None,
+                 linearization_kwargs: Optional[Dict[str, Any]] = None, check_singular: bool = False):
+        linearization_cls = linearization_cls or DenseLinearization
+        if linearization_cls != DenseLinearization:
+            raise RuntimeError(
+                "DenseSolver only works with theseus.nonlinear.DenseLinearization, "
+                f"but {linearization_cls} was provided.")
+        super().__init__(objective, linearization_cls, linearization_kwargs)
+        self._check_singular = check_singular
+        self._ws = None
+
+    def solve(self, damping: Optional[Union[float, torch.Tensor]] = None, ellipsoidal_damping: bool = True,
+              damping_eps: float = 1e-8, **kwargs) -> torch.Tensor:
+        lin = self.linearization
+        return self._apply_damping_and_solve(lin.Atb, lin.AtA, damping=damping, ellipsoidal_damping=ellipsoidal_damping,
+                                             damping_eps=damping_eps)
+
+    def _apply_damping_and_solve(self, Atb: torch.Tensor, AtA: torch.Tensor, damping=None, ellipsoidal_damping: bool = True,
+                                 damping_eps: float = 1e-8) -> torch.Tensor:
+        """Damping is fused into the factorisation's load of AtA (no second [B,n,n] tensor, dense_solver.py:38-78)."""
+        if AtA.ndim != 3 or AtA.shape[1] != AtA.shape[2]:
+            raise ValueError("Matrix must have a 3 dimensions, the first one being a batch dimension, and be square.")
+        B, n, _ = AtA.shape
+        out_dtype = AtA.dtype
+        if AtA.dtype != torch.float64:
+            AtA, Atb = AtA.double(), Atb.double()  # the fp64 kernel also serves fp32 objectives (result cast back)
+        alpha = beta = None
+        if damping is not None:
+            alpha, beta = convert_to_alpha_beta_damping_tensors(damping, damping_eps, ellipsoidal_damping, B, AtA.device, AtA.dtype)
+        lib = _lib.load()
+        need = int(lib.thb_potrf_workspace_bytes(B, n))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != AtA.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=AtA.device)
+        x = torch.empty(B, n, dtype=torch.float64, device=AtA.device)
+        info = torch.empty(B, dtype=torch.int32, device=AtA.device)
+        AtA_c, rhs = AtA.contiguous(), Atb.reshape(B, n).contiguous()
+        _lib.check(lib.thb_potrf_potrs_f64(_lib.ptr(AtA_c), _lib.ptr(rhs), _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(x), _lib.ptr(info),
+                                           B, n, _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr()), "potrf_potrs")
+        self._last = (AtA_c, rhs, alpha, beta)
+        bad = info.nonzero()
+        if bad.numel() > 0:  # same visible behaviour as torch.linalg.cholesky: a RuntimeError subclass
+            k = int(bad[0, 0])
+            raise torch.linalg.LinAlgError(
+                f"linalg.cholesky: (Batch element {k}): The factorization could not be completed because the input is not "
+                f"positive-definite (the leading minor of order {int(info[k])} is not positive-definite).")
+        return x.to(out_dtype)
+
+
+class CholeskyDenseSolver(DenseSolver):
+    """theseus/optimizer/linear/dense_solver.py:144-161."""
+
+    def __init__(self, objective: Objective, linearization_cls: Optional[Type[Linearization]] = DenseLinearization,
+                 linearization_kwargs: Optional[Dict[str, Any]] = None, check_singular: bool = False):
+        super().__init__(objective, linearization_cls, linearization_kwargs, check_singular=check_singular)
+
+
+class LUDenseSolver(CholeskyDenseSolver):
+    """theseus/optimizer/linear/dense_solver.py:125-141.  AtA (+damping) is SPD, so the LU variant is served by the
+    same Cholesky kernel."""
+
+
+# ------------------------------------------------------------------------------------------------ nonlinear
+class BackwardMode(Enum):
+    UNROLL = 0
+    IMPLICIT = 1
+    TRUNCATED = 2
+    DLM = 3
+
+    @staticmethod
+    def resolve(key) -> "BackwardMode":
+        if isinstance(key, BackwardMode):
+            return key
+        if not isinstance(key, str):
+            raise ValueError("Backward mode must be th.BackwardMode or string.")
+        try:
+            return BackwardMode[key.upper()]
+        except KeyError:
+            raise ValueError(f"Unrecognized backward mode f{key}.Valid choices are unroll, implicit, truncated, dlm.")
+
+
+class NonlinearOptimizerStatus(Enum):
+    START = 0
+    CONVERGED = 1
+    MAX_ITERATIONS = 2
+    FAIL = -1
+
+
+@dataclass
+class NonlinearOptimizerParams:
+    abs_err_tolerance: float
+    rel_err_tolerance: float
+    max_iterations: int
+    step_size: float
+
+    def update(self, params_dict):
+        for param, value in params_dict.items():
+            if hasattr(self, param):
+                setattr(self, param, value)
+            else:
+                raise ValueError(f"Invalid nonlinear optimizer parameter {param}.")
+
+
+@dataclass
+class OptimizerInfo:
+    best_solution: Optional[Dict[str, torch.Tensor]]
+    status: np.ndarray
+
+
+@dataclass
+class NonlinearOptimizerInfo(OptimizerInfo):
+    converged_iter: torch.Tensor
+    best_iter: torch.Tensor
+    err_history: Optional[torch.Tensor]
+    last_err: torch.Tensor
+    best_err: torch.Tensor
+    state_history: Optional[Dict[str, torch.Tensor]]
+
+
+class NonlinearLeastSquares:
+    """theseus/optimizer/nonlinear/nonlinear_least_squares.py:57-396 + nonlinear_optimizer.py:87-294."""
+    _MAX_ALL_REJECT_ATTEMPTS = 3
+
+    def __init__(self, objective: Objective, *args, linear_solver_cls: Optional[Type[LinearSolver]] = None, vectorize: bool = False,
+                 linearization_cls: Optional[Type[Linearization]] = None, linearization_kwargs: Optional[Dict[str, Any]] = None,
+                 linear_solver_kwargs: Optional[Dict[str, Any]] = None, abs_err_tolerance: float = 1e-10,
+                 rel_err_tolerance: float = 1e-8, max_iterations: int = 20, step_size: float = 1.0, **kwargs):
+        self.objective = objective
+        self.params = NonlinearOptimizerParams(abs_err_tolerance, rel_err_tolerance, max_iterations, step_size)
+        linear_solver_cls = linear_solver_cls or CholeskyDenseSolver
+        linear_solver_kwargs = linear_solver_kwargs or {}
+        self.linear_solver = linear_solver_cls(objective, linearization_cls=linearization_cls,
+                                               linearization_kwargs=linearization_kwargs, **linear_solver_kwargs)
+        self.ordering = self.linear_solver.linearization.ordering
+        self._tmp_optim_vars = tuple(v.copy(new_name=v.name) for v in self.ordering)
+        self._objectives_version = objective._structure_version
+
+    def set_params(self, **kwargs):
+        self.params.update(kwargs)
+
+    # ---- public entry (optimizer/optimizer.py:40-53) ----
+    def optimize(self, **kwargs) -> OptimizerInfo:
+        if self._objectives_version != self.objective._structure_version:
+            raise RuntimeError("The objective was modified after optimizer construction, which is currently not supported.")
+        kwargs.pop("__FROM_THESEUS_LAYER_TOKEN__", None)
+        return self._optimize_impl(**kwargs)
+
+    # ---- bookkeeping (nonlinear_optimizer.py:109-213) ----
+    @torch.no_grad()
+    def _check_convergence(self, err: torch.Tensor, last_err: torch.Tensor):
+        if self.params.abs_err_tolerance <= 0 and self.params.rel_err_tolerance <= 0:
+            # |x| < tol is identically False for tol <= 0: no device->host sync needed for the fixed-iteration runs
+            return None
+        if err.abs().mean() < self.params.abs_err_tolerance:
+            return torch.ones_like(err).bool()
+        err_change = last_err - err
+        return (err_change.abs() < self.params.abs_err_tolerance).logical_or(
+            (err_change / last_err).abs() < self.params.rel_err_tolerance)
+
+    def _init_info(self, track_best_solution: bool, track_err_history: bool, track_state_history: bool) -> NonlinearOptimizerInfo:
+        with torch.no_grad():
+            last_err = self.objective.engine().error_metric("cur")
+        B = self.objective.batch_size
+        best_err = last_err.clone() if track_best_solution else None
+        err_history = None
+        if track_err_history:
+            err_history = torch.ones(B, self.params.max_iterations + 1) * math.inf
+            err_history[:, 0] = last_err.clone().cpu()
+        state_history = None
+        if track_state_history:
+            state_history = {}
+            for var in self.objective.optim_vars.values():
+                state_history[var.name] = torch.ones(B, *var.shape[1:], self.params.max_iterations + 1) * math.inf
+                state_history[var.name][..., 0] = var.tensor.detach().clone().cpu()
+        best_solution = None
+        if track_best_solution:
+            best_solution = {v.name: v.tensor.detach().clone().cpu() for v in self.objective.optim_vars.values()}
+        return NonlinearOptimizerInfo(
+            best_solution=best_solution, last_err=last_err, best_err=best_err,
+            status=np.array([NonlinearOptimizerStatus.START] * B),
+            converged_iter=torch.zeros_like(last_err, dtype=torch.long), best_iter=torch.zeros_like(last_err, dtype=torch.long),
+            err_history=err_history, state_history=state_history)
+
+    def _update_info(self, info: NonlinearOptimizerInfo, current_iter: int, err: torch.Tensor, converged_indices):
+        if converged_indices is None:
+            info.converged_iter += 1
+        else:
+            info.converged_iter += 1 - converged_indices.long()
+        if info.err_history is not None:
+            info.err_history[:, current_iter + 1] = err.clone().cpu()
+        if info.state_history is not None:
+            for var in self.objective.optim_vars.values():
+                info.state_history[var.name][..., current_iter + 1] = var.tensor.detach().clone().cpu()
+        if info.best_solution is not None:
+            good = err < info.best_err
+            info.best_iter[good] = current_iter
+            gc = good.cpu()
+            for var in self.objective.optim_vars.values():
+                info.best_solution[var.name][gc] = var.tensor.detach().clone()[good].cpu()
+            info.best_err = torch.minimum(info.best_err, err)
+
+    def _split_backward_iters(self, **kwargs):
+        mode = kwargs["backward_mode"]
+        if mode == BackwardMode.TRUNCATED:
+            if "backward_num_iterations" not in kwargs:
+                raise ValueError("backward_num_iterations expected but not received.")
+            bwd = min(kwargs["backward_num_iterations"], self.params.max_iterations)
+        else:
+            bwd = {BackwardMode.UNROLL: self.params.max_iterations, BackwardMode.DLM: self.params.max_iterations,
+                   BackwardMode.IMPLICIT: 1}[mode]
+        return bwd, self.params.max_iterations - bwd
+
+    # ---- the hot loop (nonlinear_least_squares.py:100-215) ----
+    def _optimize_loop(self, num_iter: int, info: NonlinearOptimizerInfo, verbose: bool, end_iter_callback=None, **kwargs) -> int:
+        eng = self.objective.engine()
+        B = self.objective.batch_size
+        converged_indices = None  # None == all False (kept on the host side to avoid a sync per iteration)
+        iters_done = 0
+        it_ = 0
+        all_reject_attempts = 0
+        lin = self.linear_solver.linearization
+        while it_ < num_iter:
+            lin.linearize()
+            try:
+                delta = self.compute_delta(**kwargs)
+            except RuntimeError as run_err:
+                msg = f"There was an error while running the linear optimizer. Original error message: {run_err}."
+                if torch.is_grad_enabled():
+                    raise RuntimeError(msg + " Backward pass will not work. To obtain the best solution seen before the error, run with torch.no_grad()")
+                warnings.warn(msg, RuntimeWarning)
+                info.status[:] = NonlinearOptimizerStatus.FAIL
+                return iters_done
+            err, all_rejected = self._step(delta, info.last_err, converged_indices, **kwargs)
+            if all_rejected:
+                all_reject_attempts += 1
+                if all_reject_attempts < NonlinearLeastSquares._MAX_ALL_REJECT_ATTEMPTS:
+                    continue
+            all_reject_attempts = 0
+            with torch.no_grad():
+                self._update_info(info, it_, err, converged_indices)
+                if verbose:
+                    print(f"Nonlinear optimizer. Iteration: {it_+1}. Error: {err.mean().item()}")
+                converged_indices = self._check_convergence(err, info.last_err)
+                if converged_indices is not None:
+                    cpu_conv = converged_indices.cpu().numpy()
+                    info.status[cpu_conv] = NonlinearOptimizerStatus.CONVERGED
+                    if cpu_conv.all():
+                        break
+                info.last_err = err
+                if end_iter_callback is not None:
+                    end_iter_callback(self, info, delta, it_)
+            iters_done += 1
+            it_ += 1
+        info.status[info.status == NonlinearOptimizerStatus.START] = NonlinearOptimizerStatus.MAX_ITERATIONS
+        return iters_done
+
+    def _optimize_impl(self, track_best_solution: bool = False, track_err_history: bool = False, track_state_history: bool = False,
+                       verbose: bool = False, backward_mode: Union[str, BackwardMode] = BackwardMode.UNROLL,
+                       end_iter_callback=None, **kwargs) -> OptimizerInfo:
+        backward_mode = BackwardMode.resolve(backward_mode)
+        if torch.is_grad_enabled() and any(v.tensor.requires_grad for v in list(self.objective.optim_vars.values()) + list(self.objective.aux_vars.values())):
+            raise NotImplementedError(
+                "theseus_b200 r1 implements the forward (no_grad) NLS path; differentiating through the solve "
+                "(SURVEY.md 8f rank 1) is not built yet -- wrap the call in torch.no_grad().")
+        kwargs_plus = {**kwargs, "backward_mode": backward_mode}
+        eng = self.objective.engine()
+        eng.adopt_optim_vars()
+        self.reset(**kwargs_plus)
+        with torch.no_grad():
+            info = self._init_info(track_best_solution, track_err_history, track_state_history)
+            if verbose:
+                print(f"Nonlinear optimizer. Iteration: 0. Error: {info.last_err.mean().item()}")
+            self._optimize_loop(num_iter=self.params.max_iterations, info=info, verbose=verbose,
+                                end_iter_callback=end_iter_callback, **kwargs)
+        info.converged_iter[torch.from_numpy(info.status == NonlinearOptimizerStatus.MAX_ITERATIONS).to(info.converged_iter.device)] = -1
+        return info
+
+    # ---- step (nonlinear_least_squares.py:296-365) ----
+    def _step(self, delta: torch.Tensor, previous_err: torch.Tensor, converged_indices, **kwargs):
+        eng = self.objective.engine()
+        step = float(self.params.step_size)
+        eng.retract_into(delta, self._tmp_optim_vars, step, converged_indices)
+        err_new = eng.error_metric("tmp")
+        reject, err, n_rej = self._complete_step(delta, err_new, previous_err, **kwargs)
+        B = self.objective.batch_size
+        if reject is not None and n_rej == B:
+            return previous_err, True
+        eng.commit(reject)
+        return err, False
+
+    def reset(self, **kwargs) -> None:
+        self.linear_solver.reset(**kwargs)
+
+    def _complete_step(self, delta, new_err, previous_err, **kwargs):
+        return None, new_err, 0
+
+    def compute_delta(self, **kwargs) -> torch.Tensor:
+        raise NotImplementedError
+
+
+class GaussNewton(NonlinearLeastSquares):
+    """theseus/optimizer/nonlinear/gauss_newton.py:17-47."""
+
+    def compute_delta(self, **kwargs) -> torch.Tensor:
+        return self.linear_solver.solve()
+
+
+class LevenbergMarquardt(NonlinearLeastSquares):
+    """theseus/optimizer/nonlinear/levenberg_marquardt.py:51-201."""
+    _MIN_DAMPING = 1.0e-7
+    _MAX_DAMPING = 1.0e7
+
+    def __init__(self, objective: Objective, *args, **kwargs):
+        super().__init__(objective, *args, **kwargs)
+        self._allows_ellipsoidal = True
+        self._allows_adaptive = True
+        self._damping: Union[float, torch.Tensor] = 0.001
+        self._stats_host = None
+
+    def reset(self, damping: float = 1e-3, adaptive_damping: bool = False, **kwargs) -> None:
+        super().reset(**kwargs)
+        if adaptive_damping:
+            self._damping = damping * torch.ones(self.objective.batch_size, device=self.objective.device, dtype=self.objective.dtype)
+        else:
+            self._damping = damping
+
+    def compute_delta(self, ellipsoidal_damping: bool = False, damping_eps: Optional[float] = None, **kwargs) -> torch.Tensor:
+        damping_eps = damping_eps if damping_eps is not None else 1e-8
+        return self.linear_solver.solve(damping=self._damping, ellipsoidal_damping=ellipsoidal_damping, damping_eps=damping_eps)
+
+    def _complete_step(self, delta, new_err, previous_err, adaptive_damping: bool = False, down_damping_ratio: float = 9.0,
+                       up_damping_ratio: float = 11.0, damping_accept: float = 0.1, ellipsoidal_damping: bool = False, **kwargs):
+        if not adaptive_damping:
+            return None, new_err, 0
+        return self._check_accept(delta, new_err, previous_err, damping_accept, down_damping_ratio, up_damping_ratio, ellipsoidal_damping)
+
+    @torch.no_grad()
+    def _check_accept(self, delta, err, previous_err, damping_accept, down_damping_ratio, up_damping_ratio, ellipsoidal_damping):
+        """levenberg_marquardt.py:172-201 as one kernel (thb_lm_control): rho test, damping update/clamp, reject mask,
+        committed error; only the number of rejected items comes back to the host (for the all-rejected retry rule)."""
+        lin = self.linear_solver.linearization
+        lib = _lib.load()
+        B, n = delta.shape
+        dev = delta.device
+        if delta.dtype != torch.float64:
+            raise NotImplementedError("LM control kernel is fp64-only in libthb200 r1")
+        Atb = lin.Atb.reshape(B, n)
+        diag = lin.diagonal_scaling(torch.ones(B, n, dtype=delta.dtype, device=dev)) if ellipsoidal_damping else None
+        reject = torch.empty(B, dtype=torch.uint8, device=dev)
+        err_out = torch.empty_like(err)
+        stats = torch.empty(4, dtype=torch.int32, device=dev)
+        if self._stats_host is None:
+            self._stats_host = torch.empty(4, dtype=torch.int32).pin_memory()
+        _lib.check(lib.thb_lm_control_f64(
+            _lib.ptr(delta), _lib.ptr(Atb), _lib.ptr(diag), B, n, float(self.params.step_size), _lib.ptr(previous_err), _lib.ptr(err),
+            _lib.ptr(self._damping), 1 if ellipsoidal_damping else 0, float(damping_accept), float(down_damping_ratio),
+            float(up_damping_ratio), _lib.ptr(reject), _lib.ptr(err_out), _lib.ptr(stats), _lib.stream_ptr()), "lm_control")
+        self._stats_host.copy_(stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n_rej = int(self._stats_host[0])
+        return reject, err_out, n_rej
