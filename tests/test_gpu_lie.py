@@ -1,0 +1,61 @@
+"""CUDA Lie kernels (through the C ABI) vs the reference's own outputs (golden) and vs the oracle on random inputs."""
+import numpy as np
+import pytest
+import torch
+
+import theseus_b200 as th
+from oracle import lie
+from helpers import load
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_se3_kernels_vs_reference_golden(dt):
+    g = load("lie_kat")
+    p = f"se3_{dt}_"
+    tol = dict(rtol=1e-9, atol=1e-10) if dt == "f64" else dict(rtol=2e-3, atol=2e-4)
+    xi = _t(g[p + "tangent"])
+    G = th.SE3.exp_map(xi)
+    np.testing.assert_allclose(G.tensor.cpu().numpy(), g[p + "exp"], **(dict(rtol=1e-10, atol=1e-12) if dt == "f64" else dict(rtol=2e-4, atol=2e-5)))
+    Gref = th.SE3(tensor=_t(g[p + "exp"]))
+    jl = []
+    lx = Gref.log_map(jacobians=jl)
+    np.testing.assert_allclose(lx.cpu().numpy(), g[p + "log"], **tol)
+    if dt == "f64":
+        np.testing.assert_allclose(jl[0].cpu().numpy(), g[p + "jlog"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(Gref.adjoint().cpu().numpy(), g[p + "adj"], **tol)
+    np.testing.assert_allclose(Gref.inverse().tensor.cpu().numpy(), g[p + "inv"], **tol)
+    other = th.SE3(tensor=_t(g[p + "other"]))
+    np.testing.assert_allclose(Gref.compose(other).tensor.cpu().numpy(), g[p + "compose"], **tol)
+
+
+def test_se3_kernels_vs_oracle_random_large():
+    rng = np.random.default_rng(11)
+    N = 100_000
+    xi = rng.standard_normal((N, 6))
+    xi[: N // 4, 3:] *= 1e-3  # exercise the near-zero branches
+    G = th.SE3.exp_map(_t(xi))
+    np.testing.assert_allclose(G.tensor.cpu().numpy(), lie.se3_exp(xi), rtol=1e-10, atol=1e-12)
+    jl = []
+    lx = G.log_map(jacobians=jl)
+    Jo, lo = lie.se3_jlog(G.tensor.cpu().numpy())
+    # log is ill-conditioned as the rotation angle approaches pi (d log ~ 1/(pi - theta)): identical formulas fed
+    # with R differing by 1 ulp differ by ~1e-16/(pi-theta)^2; keep the tight bar away from pi, a loose one near it
+    ang = np.linalg.norm(lo[:, 3:], axis=1)
+    far = ang < np.pi - 0.05
+    np.testing.assert_allclose(lx.cpu().numpy()[far], lo[far], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(jl[0].cpu().numpy()[far], Jo[far], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(lx.cpu().numpy()[~far], lo[~far], rtol=1e-4, atol=1e-4)
+    # size-independent property: log(exp(x)) == x away from pi
+    m = np.linalg.norm(xi[:, 3:], axis=1) < 3.0
+    np.testing.assert_allclose(lx.cpu().numpy()[m], xi[m], rtol=1e-8, atol=1e-9)
+
+
+def test_cpu_tensor_fails_loudly():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        th.SE3.exp_map(torch.zeros(2, 6, dtype=torch.float64))

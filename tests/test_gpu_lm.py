@@ -1,0 +1,84 @@
+"""End-to-end LM / GN through the reference-shaped API (TheseusLayer -> optimizer -> CUDA kernels) vs the reference's
+own per-iteration traces (golden fixtures written by tests/golden/make_golden.py) and vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import theseus_b200 as th
+from oracle import nls
+from helpers import load, pgo_spec, pgo_objective, lm_kwargs_of, decisive_iterations
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(g, track=True):
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g)
+    cls = th.LevenbergMarquardt if method == "lm" else th.GaussNewton
+    opt = cls(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=iters, step_size=1.0,
+              abs_err_tolerance=0, rel_err_tolerance=0)
+    trace = dict(delta=[], err=[], lam=[])
+
+    def cb(optimizer, info, delta, it):
+        trace["delta"].append(delta.cpu().numpy().copy())
+        trace["err"].append(info.last_err.cpu().numpy().copy())
+        if method == "lm":
+            trace["lam"].append((optimizer._damping * torch.ones(1, device="cuda", dtype=torch.float64)).cpu().numpy().copy()
+                                if not torch.is_tensor(optimizer._damping) else optimizer._damping.cpu().numpy().copy())
+
+    layer = th.TheseusLayer(opt)
+    inputs = {p.name: p.tensor.clone() for p in poses}
+    with torch.no_grad():
+        values, info = layer.forward(inputs, optimizer_kwargs=dict(track_err_history=True, end_iter_callback=cb, **kw))
+    return method, iters, kw, values, info, trace, poses, inputs
+
+
+@pytest.mark.parametrize("name", ["pgo_small_lm", "pgo_small_gn", "pgo_small_lm_sph", "pgo64_lm", "pgo_small_lm_hard", "pgo32_lm_hard"])
+def test_trace_vs_reference(name):
+    g = load(name)
+    method, iters, kw, values, info, trace, poses, inputs = _run(g)
+    ref_err = g["trace_err"]
+    mine = np.stack(trace["err"], 0)
+    assert mine.shape == ref_err.shape
+    np.testing.assert_allclose(mine, ref_err, rtol=1e-8)
+    spec = pgo_spec(g)
+    err0 = nls.error_metric(spec, [v["value"] for v in spec["vars"]])
+    np.testing.assert_allclose(info.err_history[:, 0].numpy(), err0, rtol=1e-6)
+    k = decisive_iterations(err0, ref_err)
+    assert k >= 2
+    for it in range(k if method == "lm" else 1):
+        dref = g["trace_delta"][it]
+        rel = np.linalg.norm(trace["delta"][it] - dref, axis=1) / np.linalg.norm(dref, axis=1)
+        assert rel.max() < 1e-5, (it, rel)  # north-star tolerance on the solution delta
+        if method == "lm":
+            np.testing.assert_allclose(trace["lam"][it], g["trace_lam"][it], rtol=1e-12)
+    final = np.stack([values[p.name].cpu().numpy() for p in poses], 0)
+    if k == iters:
+        np.testing.assert_allclose(final, g["poses_final"], rtol=1e-6, atol=1e-6)
+    else:
+        np.testing.assert_allclose(final, g["poses_final"], rtol=0, atol=5e-4)
+    assert all(s == th.NonlinearOptimizerStatus.MAX_ITERATIONS for s in info.status)
+    # the caller's input tensors are never modified in place
+    for p in poses:
+        i = int(p.name.split("__")[-1])
+        assert np.array_equal(inputs[p.name].cpu().numpy(), g["poses0"][i])
+
+
+def test_rerun_is_deterministic():
+    g = load("pgo32_lm_hard")
+    a = _run(g)[3]
+    b = _run(g)[3]
+    for k in a:
+        assert torch.equal(a[k], b[k])
+
+
+def test_convergence_status_and_early_exit():
+    g = load("pgo_small_lm_hard")
+    objective, poses = pgo_objective(th, g)
+    opt = th.LevenbergMarquardt(objective, max_iterations=30, abs_err_tolerance=1e-10, rel_err_tolerance=1e-8)
+    with torch.no_grad():
+        info = opt.optimize(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True, track_err_history=True)
+    assert all(s == th.NonlinearOptimizerStatus.CONVERGED for s in info.status)
+    assert (info.converged_iter > 0).all() and (info.converged_iter < 30).all()
+    oracle = nls.optimize(pgo_spec(g), method="lm", max_iterations=30, damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
+    np.testing.assert_allclose(info.last_err.cpu().numpy(), oracle["err_history"][:, -1], rtol=1e-7)

@@ -70,7 +70,7 @@ def build(force=False, verbose=True):
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, "-shared", "-o", lib_path()] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path()] + objs + ["-lcudart"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -257,6 +257,8 @@ class Objective:
         for cf in self.cost_functions.values():
             cf.to(*args, **kwargs)
         device, dtype, *_ = torch._C._nn._parse_to(*args, **kwargs)
+        if device is not None and device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())  # tensors report cuda:<index>
         self.device = device or self.device
         self.dtype = dtype or self.dtype
         self._engine = None
