@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/sec on the batched SE3 pose-graph (BASELINE.json config C2) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" = one pass of the hot path over one batch: one LM solve (max_iterations LM iterations of
+linearize -> damped dense Cholesky solve -> retract -> error -> accept/reject) of B=256 pose graphs with 256 SE3
+poses each (n=1536 columns), built exactly like examples/pose_graph/pose_graph_cube.py:56-83, fp64, fixed iteration
+count (abs/rel tolerance 0) with LM kwargs damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True.
+value = LM iterations per second for the whole job (all ranks' batches advance one iteration together).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel = the DMMA Cholesky),
+cpu_baseline (oracle port on the host cores, bounded sample), e2e (host buffers -> public API -> host result).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_POSES = 256
+BATCH = 256
+LM_ITERS = 10
+LM_KW = dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
+METRIC = "LM iterations/sec on batched SE3 pose-graph (256 poses, batch 256/GPU, LM + dense Cholesky, fp64)"
+WORKLOAD = "C2: synthetic SE3 pose-graph (pose_graph_cube shape: 256 poses, loop_closure_ratio 0.2), batch=256 per GPU, LM(10 it, adaptive+ellipsoidal damping) + CholeskyDenseSolver"
+
+
+def _measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def build_problem(rank, device):
+    import theseus_b200 as th
+    from theseus_b200.datasets import build_pose_graph_objective, pose_graph_synthetic_3d
+    data = pose_graph_synthetic_3d(NUM_POSES, BATCH, translation_noise=0.05, rotation_noise=0.02, loop_closure_ratio=0.2, seed=rank)
+    objective, poses = build_pose_graph_objective(th, data, device)
+    return th, data, objective, poses
+
+
+def oracle_spec(data, sl):
+    """The same workload as a numpy problem description for the oracle port (CPU baseline only)."""
+    P, M = data["poses"][:, sl].numpy(), data["meas"][:, sl].numpy()
+    spec = dict(dtype=np.dtype(np.float64), vars=[], costs=[])
+    for i in range(P.shape[0]):
+        spec["vars"].append(dict(kind="SE3", dof=6, value=P[i]))
+    w = data["info"].numpy().reshape(1, 6)
+    for e, (i, j) in enumerate(data["edges"]):
+        spec["costs"].append(dict(kind="between", group="SE3", vars=(i, j), aux=M[e], weight=("diag", w)))
+    spec["costs"].append(dict(kind="local", group="SE3", vars=(0,), aux=P[0], weight=("scale", np.full((1, 1), 1e-3))))
+    return spec
+
+
+def cpu_baseline_run(data, sample_items, iters=LM_ITERS):
+    """Oracle port (numpy restatement of the reference's CPU path: dense A, A^T A by BLAS, dense Cholesky) on a bounded
+    sample of the workload, all host threads BLAS can use.  Returns seconds for `iters` LM iterations of the sample."""
+    from oracle import nls
+    spec = oracle_spec(data, slice(0, sample_items))
+    t0 = time.perf_counter()
+    out = nls.optimize(spec, method="lm", max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0, sample_trace=False, **LM_KW)
+    dt = time.perf_counter() - t0
+    return dt, out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; /root/reference is Python and cannot travel to the
+    GPU box) on the host cores, same metric/config; each step = a bounded sample (sample_items of the 256 batch items)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from theseus_b200.datasets import pose_graph_synthetic_3d
+    sample = 4
+    data = pose_graph_synthetic_3d(NUM_POSES, sample, seed=0)
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_baseline_run(data, sample, iters=1)
+    times = []
+    for _ in range(args.steps):
+        dt, _ = cpu_baseline_run(data, sample)
+        times.append(dt)
+    t_step_sample = float(np.mean(times))
+    t_step_full = t_step_sample * BATCH / sample  # the reference's CPU path is linear in the batch (per-item BLAS calls)
+    value = LM_ITERS / t_step_full / 1.0
+    line = dict(impl="reference", metric=METRIC, value=value, unit="LM iterations/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=t_step_full * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=WORKLOAD, note="CPU oracle port of the reference path (dense A, BLAS A^T A, LAPACK potrf); time of a "
+                            f"{sample}-item sample scaled linearly to the 256-item batch"),
+                cpu_baseline=dict(value=value, unit="LM iterations/s", cores=cores, kind="port", sample=f"{sample} of 256 batch items x {LM_ITERS} LM iterations per step"),
+                e2e=dict(value=value, unit="LM iterations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        print(f"warning: WORLD_SIZE={world} != --gpus {args.gpus}", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+
+    from theseus_b200 import _lib
+    th, data, objective, poses = build_problem(rank, device)
+    lib = _lib.load()
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=LM_ITERS, step_size=1.0,
+                                abs_err_tolerance=0, rel_err_tolerance=0, process_group=pg)
+    layer = th.TheseusLayer(opt)
+    names_pose = [p.name for p in poses]
+    # ---- device-resident inputs (for `value`) and pinned host inputs (for `e2e`) ----
+    dev_inputs = {p.name: data["poses"][i].to(device) for i, p in enumerate(poses)}
+    edge_names = [cf.measurement.name for cf in objective.cost_functions.values() if hasattr(cf, "measurement")]
+    host_poses = data["poses"].pin_memory()
+    host_meas = data["meas"].pin_memory()
+    dev_pose_buf = torch.empty_like(data["poses"], device=device)
+    dev_meas_buf = torch.empty_like(data["meas"], device=device)
+    host_out = torch.empty_like(data["poses"]).pin_memory()
+    host_err = torch.empty(BATCH, dtype=torch.float64).pin_memory()
+
+    def step_resident():
+        with torch.no_grad():
+            values, info = layer.forward(dev_inputs, optimizer_kwargs=LM_KW)
+        return values, info
+
+    def step_e2e():
+        # host -> device copy of this step's inputs (initial poses + edge measurements), public API call, device -> host result
+        dev_pose_buf.copy_(host_poses, non_blocking=True)
+        dev_meas_buf.copy_(host_meas, non_blocking=True)
+        inputs = {n: dev_pose_buf[i] for i, n in enumerate(names_pose)}
+        inputs.update({n: dev_meas_buf[e] for e, n in enumerate(edge_names)})
+        with torch.no_grad():
+            values, info = layer.forward(inputs, optimizer_kwargs=LM_KW)
+        torch.stack([values[n] for n in names_pose], 0, out=dev_pose_buf)
+        host_out.copy_(dev_pose_buf, non_blocking=True)
+        host_err.copy_(info.last_err, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return info
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        values, info = step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.thb_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = int(lib.thb_launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = LM_ITERS * 1e3 / ms_step  # all ranks advance together: job-level LM iterations per second
+    final_err = info.last_err.mean().item()
+
+    # ---- e2e ----
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    h2d = host_poses.numel() * 8 + host_meas.numel() * 8
+    d2h = host_out.numel() * 8 + host_err.numel() * 8
+
+    # ---- roofline of the dominant kernel: chol_col_kernel (12 launches = one batched factorisation) ----
+    lin = opt.linear_solver.linearization
+    lin.linearize()
+    AtA = lin.AtA
+    B, n = AtA.shape[0], AtA.shape[1]
+    alpha = torch.full((B,), 1e-3, dtype=torch.float64, device=device)
+    beta = torch.full((B,), 1e-8, dtype=torch.float64, device=device)
+    infot = torch.empty(B, dtype=torch.int32, device=device)
+    need = int(lib.thb_potrf_workspace_bytes(B, n))
+    ws = torch.empty(need, dtype=torch.uint8, device=device)
+
+    def factor():
+        _lib.check(lib.thb_potrf_f64(_lib.ptr(AtA), _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(infot), B, n, _lib.ptr(ws), need, _lib.stream_ptr()), "potrf")
+
+    for _ in range(3):
+        factor()
+    reps = 10
+    ms_factor = timed(lambda: factor(), reps) / reps
+    nblk = (n + 127) // 128
+    flops = B * (n ** 3) / 3.0
+    achieved_tf = flops / (ms_factor * 1e-3) / 1e12
+    # fp64 peak: MEASURED_PEAKS.json has no fp64 entry -> cuBLAS dgemm 8192^3 measured live, same method as the driver's bf16 peak
+    a = torch.randn(8192, 8192, dtype=torch.float64, device=device)
+    bm = torch.randn(8192, 8192, dtype=torch.float64, device=device)
+    torch.matmul(a, bm)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, bm)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    peak_tf = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del a, bm
+    peaks, peaks_src = _measured_peaks()
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = 4
+        dt, out = cpu_baseline_run(data, sample)
+        t_full = dt * BATCH / sample
+        cpu = dict(value=LM_ITERS / t_full, unit="LM iterations/s", cores=os.cpu_count(), kind="port",
+                   sample=f"{sample} of {BATCH} batch items x {LM_ITERS} LM iterations ({dt:.1f} s measured), scaled linearly in batch",
+                   final_err_mean_sample=float(out["err_history"][:, -1].mean()))
+
+    line = dict(
+        metric=METRIC, value=value, unit="LM iterations/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        config=dict(workload=WORKLOAD, batch_per_gpu=BATCH, global_batch=BATCH * world, num_poses=NUM_POSES,
+                    num_edges=len(data["edges"]), rows=int(lin.num_rows), cols=int(lin.num_cols), lm_iterations_per_step=LM_ITERS,
+                    problem_iterations_per_s=value * BATCH * world,
+                    l2="working set per iteration (AtA+L = 9.7 GB) >> 126 MB L2, no flush needed",
+                    parallelism=f"batch sharded over {world} GPU(s); one all-reduce of 2 int32 per LM iteration"),
+        clocks=clocks,
+        e2e=dict(value=LM_ITERS * 1e3 / ms_e2e, unit="LM iterations/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+        gpu_launches=launches,
+        roofline=dict(bound="tensor", kernel="chol_col_kernel (fp64 DMMA, 12 launches per batched factorisation)", achieved=achieved_tf,
+                      peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf, traffic=None,
+                      flops_per_factorisation=flops, ms_per_factorisation=ms_factor,
+                      peak_source="fp64 cuBLAS dgemm 8192^3 measured live in this run (MEASURED_PEAKS.json carries no fp64 figure; "
+                                  f"its bf16/HBM entries [{peaks_src}]: {peaks.get('bf16_tflops')} TF/s, {peaks.get('hbm_gbs')} GB/s)",
+                      share_of_step=ms_factor * LM_ITERS / ms_step),
+        cpu_baseline=cpu, final_err_mean=final_err)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

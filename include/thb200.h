@@ -36,6 +36,8 @@ typedef struct CUstream_st* thb_stream_t; /* == cudaStream_t */
 /* Library identification: returns version (major*10000 + minor*100 + patch) and the compiled SM arch. */
 int thb_version(void);
 int thb_compiled_arch(void);
+/* Number of CUDA kernels this library has launched in this process so far (bench.py's gpu_launches). */
+int64_t thb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Cost-function groups ("schemas").  One group = all cost functions of one type with the same
@@ -169,6 +171,12 @@ int thb_fill_zero(void* ptr, int64_t bytes, thb_stream_t stream);
  * torch.linalg.cholesky + torch.cholesky_solve (dense_solver.py:159-161).
  * ---------------------------------------------------------------------------------------------- */
 int64_t thb_potrf_workspace_bytes(int64_t B, int64_t n);
+/* Factor only / solve only against the factor left in `workspace` by thb_potrf_f64 (any number of right-hand
+ * sides, e.g. the backward pass of the solve, theseus/optimizer/autograd/*: the factor is reused). */
+int thb_potrf_f64(const double* AtA, const double* alpha, const double* beta, int32_t* info, int64_t B, int64_t n,
+                  void* workspace, int64_t workspace_bytes, thb_stream_t stream);
+int thb_potrs_f64(const double* rhs, double* x, int64_t B, int64_t n, const void* workspace, int64_t workspace_bytes,
+                  thb_stream_t stream);
 int thb_potrf_potrs_f64(const double* AtA, const double* rhs, const double* alpha, const double* beta, double* x,
                         int32_t* info, int64_t B, int64_t n, void* workspace, int64_t workspace_bytes,
                         thb_stream_t stream);

@@ -91,6 +91,38 @@ def cost_dim(spec, cost):
     return _GROUP[cost["group"]]["dof"]
 
 
+def eval_costs(spec, values, want_jac=True):
+    """All cost functions, batched by schema like theseus/core/vectorizer.py:222-332 (Vectorize): cost functions of
+    the same (type, group, weight type) are stacked into one [K, B, ...] evaluation, then sliced back.
+    Returns a list aligned with spec["costs"] of (jacobians or None, weighted error)."""
+    B = values[0].shape[0]
+    dt = spec["dtype"]
+    groups = {}
+    for f, c in enumerate(spec["costs"]):
+        groups.setdefault((c["kind"], c["group"], c["weight"][0]), []).append(f)
+    out = [None] * len(spec["costs"])
+    for (kind, grp, wkind), idx in groups.items():
+        cs = [spec["costs"][f] for f in idx]
+        aux = np.stack([_bcast(np.asarray(c["aux"], dtype=dt), B) for c in cs], 0)          # [K,B,...]
+        w = np.stack([_bcast(np.asarray(c["weight"][1], dtype=dt), B) for c in cs], 0)       # [K,B,dim or 1]
+        x0 = np.stack([values[c["vars"][0]] for c in cs], 0)
+        if kind == "between":
+            x1 = np.stack([values[c["vars"][1]] for c in cs], 0)
+            jacs, e = between_error_jacobians(grp, x0, x1, aux, want_jac)
+        elif kind == "local":
+            jacs, e = local_error_jacobians(grp, x0, aux, want_jac)
+        else:
+            raise NotImplementedError(kind)
+        if wkind == "scale":
+            w = w.reshape(w.shape[0], B, 1)
+        e = e * w                                                                             # cost_weight.py:81-90,125-136
+        if jacs is not None:
+            jacs = [J * w[..., None] for J in jacs]
+        for r, f in enumerate(idx):
+            out[f] = ([J[r] for J in jacs] if jacs is not None else None, e[r])
+    return out
+
+
 # ----------------------------------------------------------------------------- structure
 def var_layout(spec):
     """theseus/optimizer/linearization.py:30-41: var_dims, var_start_cols, num_cols."""
@@ -152,8 +184,9 @@ def linearize_sparse(spec, values, struct=None):
     A_val = np.empty((B, len(struct["A_col_ind"])), dtype=dt)
     b = np.empty((B, struct["num_rows"]), dtype=dt)
     row = 0
+    evaluated = eval_costs(spec, values)
     for f, cost in enumerate(spec["costs"]):
-        jacs, e = cost_weighted_jacobians_error(spec, cost, values)
+        jacs, e = evaluated[f]
         d = e.shape[1]
         st, stride = struct["row_block_starts"][f], struct["stride"][f]
         blk = A_val[:, st:st + stride * d].reshape(B, d, stride)
@@ -174,8 +207,9 @@ def linearize_dense(spec, values):
     A = np.zeros((B, m, n), dtype=dt)
     b = np.zeros((B, m), dtype=dt)
     row = 0
-    for cost in spec["costs"]:
-        jacs, e = cost_weighted_jacobians_error(spec, cost, values)
+    evaluated = eval_costs(spec, values)
+    for f, cost in enumerate(spec["costs"]):
+        jacs, e = evaluated[f]
         d = e.shape[1]
         for k, J in enumerate(jacs):
             c0 = starts[cost["vars"][k]]
@@ -257,7 +291,7 @@ def retract(spec, values, delta, ignore_mask=None):
 
 def error_vector(spec, values):
     """core/objective.py:562-613: concatenated weighted errors, objective order."""
-    return np.concatenate([cost_weighted_jacobians_error(spec, c, values, want_jac=False)[1] for c in spec["costs"]], axis=1)
+    return np.concatenate([e for _, e in eval_costs(spec, values, want_jac=False)], axis=1)
 
 
 def error_metric(spec, values):

@@ -53,7 +53,11 @@ def test_se3_kernels_vs_oracle_random_large():
     np.testing.assert_allclose(lx.cpu().numpy()[~far], lo[~far], rtol=1e-4, atol=1e-4)
     # size-independent property: log(exp(x)) == x away from pi
     m = np.linalg.norm(xi[:, 3:], axis=1) < 3.0
-    np.testing.assert_allclose(lx.cpu().numpy()[m], xi[m], rtol=1e-8, atol=1e-9)
+    # NOT to 1e-9: below near_zero (theta < 5e-3) the reference's exp uses sin(t)/t ~ (1+cos t)/2 (so3_impl.py:231-233),
+    # a theta^2/12 ~ 2e-6 relative approximation of the translation part, which this implementation reproduces
+    np.testing.assert_allclose(lx.cpu().numpy()[m], xi[m], rtol=1e-5, atol=5e-6)
+    big = m & (np.linalg.norm(xi[:, 3:], axis=1) > 1e-2)
+    np.testing.assert_allclose(lx.cpu().numpy()[big], xi[big], rtol=1e-8, atol=1e-9)
 
 
 def test_cpu_tensor_fails_loudly():

@@ -37,6 +37,7 @@ _PG, _PV, _PP = C.POINTER(CostGroup), C.POINTER(VarTable), C.POINTER(GramPlan)
 SIGNATURES = {
     "thb_version": (c_i32, []),
     "thb_compiled_arch": (c_i32, []),
+    "thb_launch_count": (c_i64, []),
     "thb_linearize_group_f64": (c_i32, [_PG, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "thb_linearize_group_f32": (c_i32, [_PG, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "thb_error_num_chunks": (c_i32, [c_i32]),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "thb_gram_f64": (c_i32, [_PP, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "thb_fill_zero": (c_i32, [c_vp, c_i64, c_vp]),
     "thb_potrf_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "thb_potrf_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "thb_potrs_f64": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "thb_potrf_potrs_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "thb_lm_control_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64,
                                    c_vp, c_vp, c_vp, c_vp]),

@@ -3,37 +3,42 @@
 // Replaces torch.linalg.cholesky + torch.cholesky_solve + DenseSolver._apply_damping
 // (theseus/optimizer/linear/dense_solver.py:38-64,159-161).
 //
-// Algorithm: left-looking blocked Cholesky over 128-wide block columns.  For block column j one
-// launch runs a CTA per (matrix b, row tile i >= j):
-//   A. C = sum_{k<j} L[i,k] L[j,k]^T        DMMA (mma.sync m8n8k4 f64) main loop, cp.async 4-stage pipeline,
-//                                            operands staged in shared memory with a conflict-free padded stride
-//   B. C = (AtA tile, damping fused on the diagonal) - C      (AtA is read exactly once, never modified)
-//   C. diagonal CTA: potrf of the 128x128 tile in shared memory, then in-place triangular inverse
-//      W = L_jj^-1; stores L_jj and W; releases a per-(b,j) flag
-//   D. off-diagonal CTAs: acquire the flag, L[i,j] = C W^T as a second DMMA product (triangular k-range
-//      skipped), so the TRSM also runs on the FP64 tensor pipe
-// The diagonal CTAs have the lowest block indices of their launch, so they are resident before (or together
-// with) the CTAs that wait on them.  The left-looking order keeps every C tile in registers for its whole
-// k-loop: L is written once and AtA read once (algorithmic bytes), instead of the n/NB read-modify-write
-// sweeps of a right-looking update.
+// Algorithm: left-looking blocked Cholesky over 64-wide block columns, 128x64 output tiles.  For block column j
+// one launch runs a CTA per (matrix b, 128-row tile i at or below the diagonal block):
+//   A. C = sum_{k<64j} L[rows,k] L[cols,k]^T   DMMA (mma.sync m8n8k4 f64) main loop, cp.async 3-stage pipeline,
+//                                              operands staged in shared memory with a conflict-free padded stride
+//   B. C = (AtA tile, LM damping fused on the diagonal) - C     (AtA is read exactly once and never modified)
+//   C. the CTA holding the 64x64 diagonal block factors it (blocked 2x2: two 32x32 blocks are factored AND inverted
+//      by one warp in registers with shuffles, the rest are DMMA block products), forms W = L_jj^-1, stores
+//      L_jj and W and releases a per-(b,j) flag
+//   D. every tile row below the diagonal block: acquire the flag, L[i,j] = C W^T as a second DMMA product
+//      (triangular k-range skipped), so the TRSM also runs on the FP64 tensor pipe
+// Two CTAs are resident per SM (<=128 registers, ~98 KB shared memory each): while one CTA is in its non-tensor
+// phases (B: global loads, C: the serial 32x32 pivots, flag wait, stores) the other keeps the tensor pipe busy.
+// The diagonal CTAs have the lowest block indices of their launch, so they are resident before (or together with)
+// the CTAs that wait on them.  The left-looking order keeps every C tile in registers for its whole k-loop: L is
+// written once and AtA read once (algorithmic bytes) instead of the read-modify-write sweeps of a right-looking update.
 // Solve: x = M^-1 rhs with the stored W_j (triangular solves become mat-vecs), one CTA per matrix, HBM-bound.
 //
-// FP64 has no tcgen05 kind; the FP64 tensor pipe on sm_100a is reached with mma.sync DMMA
-// (measured here: 37.1 TFLOP/s vs 34.2 for DFMA, profiles/r01_ubench_fp64.txt).
+// FP64 has no tcgen05 kind; the FP64 tensor pipe of sm_100a is reached with mma.sync DMMA (measured on this pool:
+// 37.1 TFLOP/s DMMA vs 34.2 DFMA vs 35.4 cuBLAS dgemm, profiles/r01_ubench_fp64.txt).
 #include "thb_common.cuh"
 
 namespace thb {
 
-constexpr int NB = 128;        // tile edge
+constexpr int TM = 128;        // tile rows
+constexpr int TN = 64;         // tile cols = block-column width
 constexpr int KB = 16;         // k-step of the pipelined product
-constexpr int SA = 20;         // smem row stride (doubles) of a [128 x KB] operand tile: 2*SA mod 32 == 8 -> conflict-free DMMA fragment loads
-constexpr int SC = 132;        // smem row stride (doubles) of the 128x128 C tile (2*SC mod 32 == 8)
-constexpr int STAGES = 4;
+constexpr int SA = 20;         // smem row stride (doubles) of a [rows x KB] operand tile: 2*SA mod 32 == 8 -> conflict-free DMMA fragment loads
+constexpr int SC = 68;         // smem row stride (doubles) of the 128x64 C tile (2*SC mod 32 == 8)
+constexpr int SB32 = 36;       // row stride of the 32x32 inverse blocks
+constexpr int STAGES = 3;
 constexpr int WSTAGES = 3;
 constexpr int CHOL_THREADS = 256;
-constexpr int OPER_TILE = NB * SA;                                    // doubles per operand tile
-constexpr size_t SMEM_PHASE_A = (size_t)STAGES * 2 * OPER_TILE * 8;   // 163840
-constexpr size_t SMEM_PHASE_D = (size_t)(NB * SC + WSTAGES * OPER_TILE) * 8;  // 135168 + 61440
+constexpr int A_TILE = TM * SA;  // doubles
+constexpr int B_TILE = TN * SA;
+constexpr size_t SMEM_PHASE_A = (size_t)STAGES * (A_TILE + B_TILE) * 8;        // 92160
+constexpr size_t SMEM_PHASE_D = (size_t)(TM * SC + WSTAGES * B_TILE) * 8;      // 69632 + 30720 = 100352
 constexpr size_t CHOL_SMEM = SMEM_PHASE_A > SMEM_PHASE_D ? SMEM_PHASE_A : SMEM_PHASE_D;
 
 __device__ __forceinline__ void mma884(double& c0, double& c1, double a, double b) {
@@ -46,56 +51,248 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// stage one [128 x KB] operand tile: rows row0.. of a row-major matrix with leading dimension ld, columns k0..k0+KB
+// stage one [ROWS x KB] operand tile: ROWS consecutive rows of a row-major matrix (leading dimension ld), columns k0..k0+KB
+template <int ROWS>
 __device__ __forceinline__ void load_oper_tile(double* dst, const double* __restrict__ src, int64_t ld, int k0, int tid) {
 #pragma unroll
-  for (int q = 0; q < (NB * KB / 2) / CHOL_THREADS; q++) {
+  for (int q = 0; q < (ROWS * KB / 2) / CHOL_THREADS; q++) {
     const int chunk = tid + q * CHOL_THREADS;
     const int row = chunk >> 3, cc = chunk & 7;
     cp_async16(dst + row * SA + cc * 2, src + (int64_t)row * ld + k0 + cc * 2);
   }
 }
 
+// B operand given as rows of M:  B[k][n] = M[n][k]
+__device__ __forceinline__ void tile_mma_rows(double& c0, double& c1, const double* __restrict__ A, int lda,
+                                              const double* __restrict__ M, int ldm, int k4b, int k4e, int lr, int lc) {
+  for (int k4 = k4b; k4 < k4e; k4++) mma884(c0, c1, A[lr * lda + 4 * k4 + lc], M[lr * ldm + 4 * k4 + lc]);
+}
+// B operand given as columns of M: B[k][n] = M[k][n]
+__device__ __forceinline__ void tile_mma_cols(double& c0, double& c1, const double* __restrict__ A, int lda,
+                                              const double* __restrict__ M, int ldm, int k4b, int k4e, int lr, int lc) {
+  for (int k4 = k4b; k4 < k4e; k4++) mma884(c0, c1, A[lr * lda + 4 * k4 + lc], M[(4 * k4 + lc) * ldm + lr]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp: Cholesky of the 32x32 block at T (lower part; row stride SC) and its inverse, in registers
+// (one row / one column per lane; pivots and multipliers exchanged with warp shuffles).
+// L is written back to T (lower part), the inverse (full 32x32, zeros above the diagonal) to Wout [32][SB32].
+// Returns 0 or 1 + index of the first non-positive pivot.
+__device__ __noinline__ int warp_potrf32_inv(double* __restrict__ T, double* __restrict__ Wout, int lane) {
+  double row[32];
+#pragma unroll
+  for (int q = 0; q < 32; q++) row[q] = T[lane * SC + q];
+  int fail = 0;
+  double invd = 0.0;  // 1 / L[lane][lane]
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    const double d = __shfl_sync(0xffffffffu, row[c], c);
+    if (!(d > 0.0) && fail == 0) fail = c + 1;
+    // 1/sqrt(d) by the hardware seed + one Newton step (inline, no slow-path subroutine calls), sqrt(d) = d * rsqrt(d)
+    double inv = rsqrt(d);
+    inv = inv * (1.5 - 0.5 * d * inv * inv);
+    const double sq = d * inv;
+    if (lane == c) invd = inv;
+    const double lrc = (lane == c) ? sq : row[c] * inv;
+    row[c] = lrc;
+#pragma unroll
+    for (int q = c + 1; q < 32; q++) {
+      const double lqc = __shfl_sync(0xffffffffu, lrc, q);
+      row[q] -= lrc * lqc;  // lanes < q update entries above the diagonal that are never read
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 32; q++)
+    if (q <= lane) T[lane * SC + q] = row[q];
+  // inverse: lane c owns column c of X = L^-1 (forward substitution, rows broadcast from their owner lane)
+  double x[32];
+#pragma unroll
+  for (int r = 0; r < 32; r++) {
+    double s = (lane == r) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < r; k++) {
+      const double lrk = __shfl_sync(0xffffffffu, row[k], r);
+      s -= lrk * x[k];
+    }
+    x[r] = s * __shfl_sync(0xffffffffu, invd, r);
+  }
+#pragma unroll
+  for (int r = 0; r < 32; r++) Wout[r * SB32 + lane] = (r >= lane) ? x[r] : 0.0;
+  return fail;
+}
+
+// All 256 threads.  T: the 64x64 diagonal block inside the C tile (row stride SC), Wd: scratch [2][32][SB32],
+// Lg/ldl: where L_jj goes in global memory, Wg: where W = L_jj^-1 goes (row-major 64x64).
+__device__ __noinline__ int diag64_factor_invert(double* __restrict__ T, double* __restrict__ Wd, double* __restrict__ Lg, int64_t ldl,
+                                                 double* __restrict__ Wg) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  // 16 tiles of 8x8 per 32x32 block: two per warp
+  const int t0 = warp, t1 = warp + 8;
+  const int rt0 = t0 >> 2, ct0 = t0 & 3, rt1 = t1 >> 2, ct1 = t1 & 3;
+  double a0, a1, b0, b1;
+  // ---- block column 0 ----
+  if (warp == 0) {
+    const int f = warp_potrf32_inv(T, Wd, lane);
+    if (lane == 0 && f != 0) s_fail = f;
+  }
+  __syncthreads();
+  // panel: L10 = T10 W00^T
+  a0 = a1 = b0 = b1 = 0.0;
+  tile_mma_rows(a0, a1, T + (32 + 8 * rt0) * SC, SC, Wd + (8 * ct0) * SB32, SB32, 0, 2 * ct0 + 2, lr, lc);
+  tile_mma_rows(b0, b1, T + (32 + 8 * rt1) * SC, SC, Wd + (8 * ct1) * SB32, SB32, 0, 2 * ct1 + 2, lr, lc);
+  __syncthreads();
+  *reinterpret_cast<double2*>(&T[(32 + 8 * rt0 + lr) * SC + 8 * ct0 + 2 * lc]) = make_double2(a0, a1);
+  *reinterpret_cast<double2*>(&T[(32 + 8 * rt1 + lr) * SC + 8 * ct1 + 2 * lc]) = make_double2(b0, b1);
+  __syncthreads();
+  // trailing: T11 -= L10 L10^T   (each 8x8 tile owned by one warp)
+  a0 = a1 = b0 = b1 = 0.0;
+  tile_mma_rows(a0, a1, T + (32 + 8 * rt0) * SC, SC, T + (32 + 8 * ct0) * SC, SC, 0, 8, lr, lc);
+  tile_mma_rows(b0, b1, T + (32 + 8 * rt1) * SC, SC, T + (32 + 8 * ct1) * SC, SC, 0, 8, lr, lc);
+  {
+    double2* d0 = reinterpret_cast<double2*>(&T[(32 + 8 * rt0 + lr) * SC + 32 + 8 * ct0 + 2 * lc]);
+    double2* d1 = reinterpret_cast<double2*>(&T[(32 + 8 * rt1 + lr) * SC + 32 + 8 * ct1 + 2 * lc]);
+    double2 v0 = *d0, v1 = *d1;
+    v0.x -= a0; v0.y -= a1; v1.x -= b0; v1.y -= b1;
+    *d0 = v0;
+    *d1 = v1;
+  }
+  __syncthreads();
+  // ---- block column 1 ----
+  if (warp == 0) {
+    const int f = warp_potrf32_inv(T + 32 * SC + 32, Wd + 32 * SB32, lane);
+    if (lane == 0 && f != 0 && s_fail == 0) s_fail = 32 + f;
+  }
+  __syncthreads();
+  // ---- store L_jj (lower part; zeros above) ----
+  for (int e = tid; e < 64 * 64; e += CHOL_THREADS) {
+    const int r = e >> 6, c = e & 63;
+    Lg[(int64_t)r * ldl + c] = (c <= r) ? T[r * SC + c] : 0.0;
+  }
+  __syncthreads();
+  // ---- inverse: diagonal blocks <- W_kk (explicit zeros above the diagonal), then W10 = -(W11 L10) W00 ----
+  for (int e = tid; e < 2 * 32 * 32; e += CHOL_THREADS) {
+    const int kb = e >> 10, r = (e >> 5) & 31, c = e & 31;
+    T[(32 * kb + r) * SC + 32 * kb + c] = Wd[kb * 32 * SB32 + r * SB32 + c];
+  }
+  __syncthreads();
+  a0 = a1 = b0 = b1 = 0.0;  // X = W11 L10 (W11 lower triangular)
+  tile_mma_cols(a0, a1, T + (32 + 8 * rt0) * SC + 32, SC, T + 32 * SC + 8 * ct0, SC, 0, 2 * rt0 + 2, lr, lc);
+  tile_mma_cols(b0, b1, T + (32 + 8 * rt1) * SC + 32, SC, T + 32 * SC + 8 * ct1, SC, 0, 2 * rt1 + 2, lr, lc);
+  __syncthreads();
+  *reinterpret_cast<double2*>(&T[(32 + 8 * rt0 + lr) * SC + 8 * ct0 + 2 * lc]) = make_double2(a0, a1);
+  *reinterpret_cast<double2*>(&T[(32 + 8 * rt1 + lr) * SC + 8 * ct1 + 2 * lc]) = make_double2(b0, b1);
+  __syncthreads();
+  a0 = a1 = b0 = b1 = 0.0;  // W10 = -X W00 (W00 lower triangular)
+  tile_mma_cols(a0, a1, T + (32 + 8 * rt0) * SC, SC, T + 8 * ct0, SC, 2 * ct0, 8, lr, lc);
+  tile_mma_cols(b0, b1, T + (32 + 8 * rt1) * SC, SC, T + 8 * ct1, SC, 2 * ct1, 8, lr, lc);
+  __syncthreads();
+  *reinterpret_cast<double2*>(&T[(32 + 8 * rt0 + lr) * SC + 8 * ct0 + 2 * lc]) = make_double2(-a0, -a1);
+  *reinterpret_cast<double2*>(&T[(32 + 8 * rt1 + lr) * SC + 8 * ct1 + 2 * lc]) = make_double2(-b0, -b1);
+  __syncthreads();
+  for (int e = tid; e < 64 * 64; e += CHOL_THREADS) {
+    const int r = e >> 6, c = e & 63;
+    Wg[e] = (c <= r) ? T[r * SC + c] : 0.0;
+  }
+  return s_fail;
+}
+
 struct CholArgs {
   const double* AtA;   // [B,n,n]
   const double* alpha; // [B] or null
   const double* beta;  // [B] or null
-  double* L;           // [B,np,np]
-  double* W;           // [B,nblk,128,128]
-  int* flags;          // [B,nblk]
+  double* L;           // [B,np,np]   (np = n rounded up to a multiple of 128)
+  double* W;           // [B,nb,64,64] (nb = np/64)
+  int* flags;          // [B,nb]      W_j ready
+  int* done;           // [B,ntr]     number of finished block columns of each 128-row tile
+  const int64_t* col_start;  // [nb+1] first CTA index of every block column (one launch covers the whole factorisation)
   int32_t* info;       // [B]
   int64_t B, n, np;
-  int nblk, j;
+  int nb, ntr;
 };
 
-__global__ void __launch_bounds__(CHOL_THREADS, 1) chol_col_kernel(CholArgs p) {
+__device__ __forceinline__ void wait_ge(const int* addr, int target) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
+    if (v < target) __nanosleep(100);
+  } while (v < target);
+}
+
+__global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t b = blockIdx.x % p.B;
-  const int i = p.j + (int)(blockIdx.x / p.B);
-  const int j = p.j;
-  const bool is_diag = (i == j);
+  // CTA -> (block column j, row tile i, matrix b).  CTAs are ordered by column, the diagonal tile of a column first,
+  // the matrix index fastest: every CTA only ever waits on CTAs with a smaller block index (in-order dispatch).
+  int j;
+  {
+    int lo = 0, hi = p.nb;  // largest j with col_start[j] <= blockIdx.x
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.col_start[mid] <= (int64_t)blockIdx.x) lo = mid; else hi = mid;
+    }
+    j = lo;
+  }
+  const int64_t rel = (int64_t)blockIdx.x - p.col_start[j];
+  const int i0 = j >> 1;                     // 128-row tile that contains the diagonal block of column j
+  const int64_t b = rel % p.B;
+  const int i = i0 + (int)(rel / p.B);
+  const bool is_diag = (i == i0);
+  const int roff = (j & 1) * 64;             // row offset of the diagonal block inside its tile
   const int64_t np = p.np;
   double* Lb = p.L + b * np * np;
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps -> 64 x 32 warp tiles
+  const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps -> 32 x 32 warp tiles
   const int lr = lane >> 2, lc = lane & 3;
 
-  // ---------------- phase A: acc = sum_k L[i,k] L[j,k]^T ----------------
-  double acc[8][4][2];
+  // ---------------- phase A: acc = sum_k L[rows,k] L[cols,k]^T ----------------
+  // The accumulators start at -(AtA tile with the LM damping fused on the diagonal): the global loads are in flight
+  // while the cp.async pipeline fills, and C = AtA - sum L L^T is simply -acc at the end (AtA is read exactly once).
+  double acc[4][4][2];
+  {
+    const double* Ab = p.AtA + b * p.n * p.n;
+    const double al = (p.alpha != nullptr) ? p.alpha[b] : 0.0;
+    const double be = (p.beta != nullptr) ? p.beta[b] : 0.0;
 #pragma unroll
-  for (int mi = 0; mi < 8; mi++)
+    for (int mi = 0; mi < 4; mi++) {
+      const int64_t gr = (int64_t)i * TM + wm * 32 + mi * 8 + lr;
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int64_t gc = (int64_t)j * TN + wn * 32 + ni * 8 + lc * 2 + u;
+          double x;
+          if (gr < p.n && gc < p.n) {
+            x = Ab[gr * p.n + gc];
+            if (gr == gc) x = x + (al * x + be);  // dense_solver.py:38-64 ; linear/utils.py:14-33
+          } else {
+            x = (gr == gc) ? 1.0 : 0.0;  // identity padding
+          }
+          acc[mi][ni][u] = -x;
+        }
+      }
+    }
+  }
+  // dependencies: all earlier block columns of this row tile and of the row tile holding block row j are finished
+  if (j > 0) {
+    if (tid == 0) {
+      wait_ge(p.done + b * p.ntr + i, j);
+      if (i != i0) wait_ge(p.done + b * p.ntr + i0, j);
+    }
+    __syncthreads();
+  }
 
-  const int nk = j * (NB / KB);
-  const double* Arow = Lb + (int64_t)i * NB * np;
-  const double* Brow = Lb + (int64_t)j * NB * np;
+  const int nk = j * (TN / KB);
+  const double* Arow = Lb + (int64_t)i * TM * np;
+  const double* Brow = Lb + (int64_t)j * TN * np;
   if (nk > 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
       if (s < nk) {
-        load_oper_tile(smem + (size_t)s * 2 * OPER_TILE, Arow, np, s * KB, tid);
-        if (!is_diag) load_oper_tile(smem + (size_t)s * 2 * OPER_TILE + OPER_TILE, Brow, np, s * KB, tid);
+        load_oper_tile<TM>(smem + (size_t)s * (A_TILE + B_TILE), Arow, np, s * KB, tid);
+        if (!is_diag) load_oper_tile<TN>(smem + (size_t)s * (A_TILE + B_TILE) + A_TILE, Brow, np, s * KB, tid);
       }
       cp_async_commit();
     }
@@ -106,22 +303,22 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_col_kernel(CholArgs p) {
         const int nx = ks + STAGES - 1;
         if (nx < nk) {
           const int s = nx % STAGES;
-          load_oper_tile(smem + (size_t)s * 2 * OPER_TILE, Arow, np, nx * KB, tid);
-          if (!is_diag) load_oper_tile(smem + (size_t)s * 2 * OPER_TILE + OPER_TILE, Brow, np, nx * KB, tid);
+          load_oper_tile<TM>(smem + (size_t)s * (A_TILE + B_TILE), Arow, np, nx * KB, tid);
+          if (!is_diag) load_oper_tile<TN>(smem + (size_t)s * (A_TILE + B_TILE) + A_TILE, Brow, np, nx * KB, tid);
         }
         cp_async_commit();
       }
-      const double* As = smem + (size_t)(ks % STAGES) * 2 * OPER_TILE;
-      const double* Bs = is_diag ? As : (As + OPER_TILE);
+      const double* As = smem + (size_t)(ks % STAGES) * (A_TILE + B_TILE);
+      const double* Bs = is_diag ? (As + roff * SA) : (As + A_TILE);  // diagonal tile: the column rows are a half of its own rows
 #pragma unroll
       for (int k4 = 0; k4 < KB / 4; k4++) {
-        double a[8], bf[4];
+        double a[4], bf[4];
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++) a[mi] = As[(wm * 64 + mi * 8 + lr) * SA + k4 * 4 + lc];
+        for (int mi = 0; mi < 4; mi++) a[mi] = As[(wm * 32 + mi * 8 + lr) * SA + k4 * 4 + lc];
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) bf[ni] = Bs[(wn * 32 + ni * 8 + lr) * SA + k4 * 4 + lc];
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++)
+        for (int mi = 0; mi < 4; mi++)
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) mma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
       }
@@ -130,119 +327,54 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_col_kernel(CholArgs p) {
     __syncthreads();
   }
 
-  // ---------------- phase B: C = AtA tile (damped) - acc, to shared memory ----------------
+  // ---------------- phase B: C = -acc, to shared memory ----------------
   double* Cs = smem;
-  {
-    const double* Ab = p.AtA + b * p.n * p.n;
-    const double al = (p.alpha != nullptr) ? p.alpha[b] : 0.0;
-    const double be = (p.beta != nullptr) ? p.beta[b] : 0.0;
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++) {
-      const int r = wm * 64 + mi * 8 + lr;
-      const int64_t gr = (int64_t)i * NB + r;
+  for (int mi = 0; mi < 4; mi++) {
+    const int r = wm * 32 + mi * 8 + lr;
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++) {
-        const int c = wn * 32 + ni * 8 + lc * 2;
-        double v[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const int64_t gc = (int64_t)j * NB + c + u;
-          double x;
-          if (gr < p.n && gc < p.n) {
-            x = Ab[gr * p.n + gc];
-            if (gr == gc) x = x + (al * x + be);  // dense_solver.py:38-64 ; linear/utils.py:14-33
-          } else {
-            x = (gr == gc) ? 1.0 : 0.0;  // identity padding
-          }
-          v[u] = x - acc[mi][ni][u];
-        }
-        *reinterpret_cast<double2*>(&Cs[r * SC + c]) = make_double2(v[0], v[1]);
-      }
+    for (int ni = 0; ni < 4; ni++) {
+      const int c = wn * 32 + ni * 8 + lc * 2;
+      *reinterpret_cast<double2*>(&Cs[r * SC + c]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
     }
   }
   __syncthreads();
 
-  double* Wj = p.W + ((int64_t)b * p.nblk + j) * NB * NB;
-  int* flag = p.flags + b * p.nblk + j;
+  double* Wj = p.W + ((int64_t)b * p.nb + j) * TN * TN;
+  int* flag = p.flags + b * p.nb + j;
+  int row_lo = 0;  // first tile row that still needs the TRSM of phase D
 
   if (is_diag) {
-    // ---------------- phase C: potrf of the diagonal tile in shared memory ----------------
-    __shared__ double colbuf[NB];
-    __shared__ int s_fail;
-    if (tid == 0) s_fail = 0;
-    for (int c = 0; c < NB; c++) {
-      __syncthreads();
-      const double d = Cs[c * SC + c];
-      if (tid == 0 && !(d > 0.0) && s_fail == 0) s_fail = j * NB + c + 1;
-      const double sq = sqrt(d);
-      const double inv = 1.0 / sq;
-      if (tid >= c && tid < NB) {
-        const double v = (tid == c) ? sq : Cs[tid * SC + c] * inv;
-        colbuf[tid] = v;
-        if (tid != c) Cs[tid * SC + c] = v;  // the pivot itself is still being read by other threads
-      }
-      __syncthreads();
-      if (tid == 0) Cs[c * SC + c] = sq;
-      // trailing update: 2 threads per row
-      const int r = c + 1 + (tid >> 1);
-      if (r < NB) {
-        const double lrc = colbuf[r];
-        for (int q = c + 1 + (tid & 1); q <= r; q += 2) Cs[r * SC + q] -= lrc * colbuf[q];
-      }
-    }
-    __syncthreads();
-    if (tid == 0 && s_fail != 0) atomicCAS(p.info + b, 0, s_fail);
-    // store L_jj (lower; upper zeroed)
-    for (int e = tid; e < NB * NB; e += CHOL_THREADS) {
-      const int r = e >> 7, c = e & 127;
-      Lb[((int64_t)j * NB + r) * np + (int64_t)j * NB + c] = (c <= r) ? Cs[r * SC + c] : 0.0;
-    }
-    // in-place inverse of the lower-triangular tile: column by column from the right
-    for (int c = NB - 1; c >= 0; c--) {
-      __syncthreads();
-      const double x = 1.0 / Cs[c * SC + c];
-      const int r = c + 1 + (tid >> 1);
-      double s = 0.0;
-      if (r < NB) {
-        for (int k = c + 1 + (tid & 1); k <= r; k += 2) s += Cs[r * SC + k] * Cs[k * SC + c];
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      __syncthreads();
-      if (r < NB && (tid & 1) == 0) Cs[r * SC + c] = -s * x;
-      if (tid == 0) Cs[c * SC + c] = x;
-    }
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += CHOL_THREADS) {
-      const int r = e >> 7, c = e & 127;
-      Wj[e] = (c <= r) ? Cs[r * SC + c] : 0.0;
-    }
+    // ---------------- phase C: blocked potrf + triangular inverse of the 64x64 diagonal block ----------------
+    const int fail = diag64_factor_invert(Cs + roff * SC, smem + TM * SC, Lb + ((int64_t)j * TN) * np + (int64_t)j * TN, np, Wj);
+    if (tid == 0 && fail != 0) atomicCAS(p.info + b, 0, j * TN + fail);
     __threadfence();
     __syncthreads();
     if (tid == 0) {
       asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(flag), "r"(1) : "memory");
     }
-    return;
+    row_lo = roff + 64;         // rows of this tile below the diagonal block (none when the block is the lower half)
+    if (row_lo >= TM) {
+      if (tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p.done + b * p.ntr + i), "r"(1) : "memory");
+      return;
+    }
+  } else {
+    if (tid == 0) wait_ge(flag, 1);
+    __syncthreads();
   }
 
-  // ---------------- phase D: L[i,j] = C W^T (DMMA, triangular k-range) ----------------
-  if (tid == 0) {
-    int v = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
-      if (v == 0) __nanosleep(200);
-    } while (v == 0);
-  }
-  __syncthreads();
-  double* Ws = smem + NB * SC;
-  double acc2[2][16][2];
+  // ---------------- phase D: L[rows,j] = C W^T (DMMA, triangular k-range) ----------------
+  double* Ws = smem + TM * SC;
+  double acc2[2][8][2];
 #pragma unroll
   for (int mi = 0; mi < 2; mi++)
 #pragma unroll
-    for (int ni = 0; ni < 16; ni++) acc2[mi][ni][0] = acc2[mi][ni][1] = 0.0;
-  constexpr int NKW = NB / KB;  // 8
+    for (int ni = 0; ni < 8; ni++) acc2[mi][ni][0] = acc2[mi][ni][1] = 0.0;
+  constexpr int NKW = TN / KB;  // 4
+  const bool active = (warp * 16 >= row_lo);
 #pragma unroll
   for (int s = 0; s < WSTAGES - 1; s++) {
-    load_oper_tile(Ws + (size_t)s * OPER_TILE, Wj, NB, s * KB, tid);
+    load_oper_tile<TN>(Ws + (size_t)s * B_TILE, Wj, TN, s * KB, tid);
     cp_async_commit();
   }
 #pragma unroll
@@ -251,48 +383,56 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_col_kernel(CholArgs p) {
     __syncthreads();
     {
       const int nx = ks + WSTAGES - 1;
-      if (nx < NKW) load_oper_tile(Ws + (size_t)(nx % WSTAGES) * OPER_TILE, Wj, NB, nx * KB, tid);
+      if (nx < NKW) load_oper_tile<TN>(Ws + (size_t)(nx % WSTAGES) * B_TILE, Wj, TN, nx * KB, tid);
       cp_async_commit();
     }
-    const double* Wst = Ws + (size_t)(ks % WSTAGES) * OPER_TILE;
+    const double* Wst = Ws + (size_t)(ks % WSTAGES) * B_TILE;
+    if (active) {
 #pragma unroll
-    for (int k4 = 0; k4 < KB / 4; k4++) {
-      const int kk = ks * KB + k4 * 4;
-      double a[2];
+      for (int k4 = 0; k4 < KB / 4; k4++) {
+        const int kk = ks * KB + k4 * 4;
+        double a[2];
 #pragma unroll
-      for (int mi = 0; mi < 2; mi++) a[mi] = Cs[(warp * 16 + mi * 8 + lr) * SC + kk + lc];
+        for (int mi = 0; mi < 2; mi++) a[mi] = Cs[(warp * 16 + mi * 8 + lr) * SC + kk + lc];
 #pragma unroll
-      for (int ni = 0; ni < 16; ni++) {
-        if (ni * 8 + 7 >= kk) {  // W[c][k] == 0 for k > c: skip column blocks entirely above this k
-          const double bfr = Wst[(ni * 8 + lr) * SA + k4 * 4 + lc];
-          mma884(acc2[0][ni][0], acc2[0][ni][1], a[0], bfr);
-          mma884(acc2[1][ni][0], acc2[1][ni][1], a[1], bfr);
+        for (int ni = 0; ni < 8; ni++) {
+          if (ni * 8 + 7 >= kk) {  // W[c][k] == 0 for k > c: skip column blocks entirely above this k
+            const double bfr = Wst[(ni * 8 + lr) * SA + k4 * 4 + lc];
+            mma884(acc2[0][ni][0], acc2[0][ni][1], a[0], bfr);
+            mma884(acc2[1][ni][0], acc2[1][ni][1], a[1], bfr);
+          }
         }
       }
     }
   }
   cp_async_wait<0>();
+  if (active) {
 #pragma unroll
-  for (int mi = 0; mi < 2; mi++) {
-    const int r = warp * 16 + mi * 8 + lr;
-    double* dst = Lb + ((int64_t)i * NB + r) * np + (int64_t)j * NB;
+    for (int mi = 0; mi < 2; mi++) {
+      const int r = warp * 16 + mi * 8 + lr;
+      double* dst = Lb + ((int64_t)i * TM + r) * np + (int64_t)j * TN;
 #pragma unroll
-    for (int ni = 0; ni < 16; ni++) {
-      *reinterpret_cast<double2*>(dst + ni * 8 + lc * 2) = make_double2(acc2[mi][ni][0], acc2[mi][ni][1]);
+      for (int ni = 0; ni < 8; ni++) {
+        *reinterpret_cast<double2*>(dst + ni * 8 + lc * 2) = make_double2(acc2[mi][ni][0], acc2[mi][ni][1]);
+      }
     }
   }
+  // publish: this row tile has one more finished block column
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p.done + b * p.ntr + i), "r"(1) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
 // Solve with the stored factor: forward  y_j = W_j (rhs_j - sum_{k<j} L[j,k] y_k),
-//                               backward x_j = W_j^T (y_j - sum_{k>j} L[k,j]^T x_k).
+//                               backward x_j = W_j^T (y_j - sum_{k>j} L[k,j]^T x_k),   64-row blocks.
 struct SolveArgs {
   const double* L;
   const double* W;
   const double* rhs;  // [B,n]
   double* x;          // [B,n]
   int64_t B, n, np;
-  int nblk;
+  int nb;
 };
 
 constexpr int SOLVE_THREADS = 256;
@@ -300,46 +440,53 @@ constexpr int SOLVE_THREADS = 256;
 __global__ void __launch_bounds__(SOLVE_THREADS, 2) chol_solve_kernel(SolveArgs p) {
   extern __shared__ __align__(16) double sm[];
   double* y = sm;               // [np]
-  double* tmp = sm + p.np;      // [128]
-  double* part = tmp + NB;      // [8][128]
+  double* tmp = sm + p.np;      // [64]
+  double* part = tmp + TN;      // [8][64]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.x;
   const int64_t np = p.np;
   const double* Lb = p.L + b * np * np;
-  const double* Wb = p.W + b * p.nblk * NB * NB;
+  const double* Wb = p.W + b * p.nb * TN * TN;
   for (int64_t e = tid; e < np; e += SOLVE_THREADS) y[e] = (e < p.n) ? p.rhs[b * p.n + e] : 0.0;
   __syncthreads();
   // ---- forward ----
-  for (int j = 0; j < p.nblk; j++) {
-    const int K = j * NB;
-    // each warp: 16 rows
-    for (int rr = 0; rr < 16; rr += 2) {
-      const int r0 = warp * 16 + rr;
-      const double* row0 = Lb + ((int64_t)j * NB + r0) * np;
-      const double* row1 = row0 + np;
-      double s0 = 0.0, s1 = 0.0;
+  for (int j = 0; j < p.nb; j++) {
+    const int K = j * TN;
+    // each warp: 8 rows, four at a time
+    for (int rr = 0; rr < 8; rr += 4) {
+      const int r0 = warp * 8 + rr;
+      const double* row0 = Lb + ((int64_t)K + r0) * np;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       for (int k = lane * 2; k < K; k += 64) {
-        const double2 a0 = *reinterpret_cast<const double2*>(row0 + k);
-        const double2 a1 = *reinterpret_cast<const double2*>(row1 + k);
         const double2 yy = *reinterpret_cast<const double2*>(y + k);
+        const double2 a0 = *reinterpret_cast<const double2*>(row0 + k);
+        const double2 a1 = *reinterpret_cast<const double2*>(row0 + np + k);
+        const double2 a2 = *reinterpret_cast<const double2*>(row0 + 2 * np + k);
+        const double2 a3 = *reinterpret_cast<const double2*>(row0 + 3 * np + k);
         s0 += a0.x * yy.x + a0.y * yy.y;
         s1 += a1.x * yy.x + a1.y * yy.y;
+        s2 += a2.x * yy.x + a2.y * yy.y;
+        s3 += a3.x * yy.x + a3.y * yy.y;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o);
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
       }
       if (lane == 0) {
         tmp[r0] = y[K + r0] - s0;
         tmp[r0 + 1] = y[K + r0 + 1] - s1;
+        tmp[r0 + 2] = y[K + r0 + 2] - s2;
+        tmp[r0 + 3] = y[K + r0 + 3] - s3;
       }
     }
     __syncthreads();
-    const double* Wj = Wb + (int64_t)j * NB * NB;
-    for (int rr = 0; rr < 16; rr++) {
-      const int r = warp * 16 + rr;
-      const double* wr = Wj + r * NB;
+    const double* Wj = Wb + (int64_t)j * TN * TN;
+    for (int rr = 0; rr < 8; rr++) {
+      const int r = warp * 8 + rr;
+      const double* wr = Wj + r * TN;
       double s = 0.0;
       for (int k = lane; k <= r; k += 32) s += wr[k] * tmp[k];
 #pragma unroll
@@ -349,54 +496,42 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) chol_solve_kernel(SolveArgs 
     __syncthreads();
   }
   // ---- backward ----
-  for (int j = p.nblk - 1; j >= 0; j--) {
-    const int K = j * NB;
-    // part[w][c] = sum over rows r (this warp's share) of L[r][K+c] * x[r], r in [(j+1)*128, np)
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int64_t r = (int64_t)(j + 1) * NB + warp; r < np; r += 8) {
+  for (int j = p.nb - 1; j >= 0; j--) {
+    const int K = j * TN;
+    // part[w][c] = sum over rows r (this warp's share) of L[r][K+c] * x[r], r in [K+64, np)
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t r = (int64_t)K + TN + warp; r < np; r += 8) {
       const double xr = y[r];
-      const double* row = Lb + r * np + K + lane * 4;
-      const double2 v0 = *reinterpret_cast<const double2*>(row);
-      const double2 v1 = *reinterpret_cast<const double2*>(row + 2);
-      a0 += v0.x * xr;
-      a1 += v0.y * xr;
-      a2 += v1.x * xr;
-      a3 += v1.y * xr;
+      const double2 v = *reinterpret_cast<const double2*>(Lb + r * np + K + lane * 2);
+      a0 += v.x * xr;
+      a1 += v.y * xr;
     }
-    part[warp * NB + lane * 4 + 0] = a0;
-    part[warp * NB + lane * 4 + 1] = a1;
-    part[warp * NB + lane * 4 + 2] = a2;
-    part[warp * NB + lane * 4 + 3] = a3;
+    part[warp * TN + lane * 2 + 0] = a0;
+    part[warp * TN + lane * 2 + 1] = a1;
     __syncthreads();
-    if (tid < NB) {
+    if (tid < TN) {
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; w++) s += part[w * NB + tid];
+      for (int w = 0; w < 8; w++) s += part[w * TN + tid];
       tmp[tid] = y[K + tid] - s;
     }
     __syncthreads();
     // x_j[c] = sum_{r>=c} W[r][c] tmp[r]
-    const double* Wj = Wb + (int64_t)j * NB * NB;
-    a0 = a1 = a2 = a3 = 0.0;
-    for (int r = warp; r < NB; r += 8) {
+    const double* Wj = Wb + (int64_t)j * TN * TN;
+    a0 = a1 = 0.0;
+    for (int r = warp; r < TN; r += 8) {
       const double tr = tmp[r];
-      const double* row = Wj + r * NB + lane * 4;
-      const double2 v0 = *reinterpret_cast<const double2*>(row);
-      const double2 v1 = *reinterpret_cast<const double2*>(row + 2);
-      a0 += v0.x * tr;
-      a1 += v0.y * tr;
-      a2 += v1.x * tr;
-      a3 += v1.y * tr;
+      const double2 v = *reinterpret_cast<const double2*>(Wj + r * TN + lane * 2);
+      a0 += v.x * tr;
+      a1 += v.y * tr;
     }
-    part[warp * NB + lane * 4 + 0] = a0;
-    part[warp * NB + lane * 4 + 1] = a1;
-    part[warp * NB + lane * 4 + 2] = a2;
-    part[warp * NB + lane * 4 + 3] = a3;
+    part[warp * TN + lane * 2 + 0] = a0;
+    part[warp * TN + lane * 2 + 1] = a1;
     __syncthreads();
-    if (tid < NB) {
+    if (tid < TN) {
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; w++) s += part[w * NB + tid];
+      for (int w = 0; w < 8; w++) s += part[w * TN + tid];
       y[K + tid] = s;
     }
     __syncthreads();
@@ -406,59 +541,100 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) chol_solve_kernel(SolveArgs 
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+struct Geometry {
+  int64_t np;
+  int nb, ntr;
+  double* L;
+  double* W;
+  int* flags;
+  int* done;
+  int64_t* col_start;
+};
+static inline Geometry geometry(void* workspace, int64_t B, int64_t n) {
+  Geometry g;
+  g.np = align_up(n, TM);
+  g.nb = (int)(g.np / TN);
+  g.L = reinterpret_cast<double*>(workspace);
+  g.W = g.L + B * g.np * g.np;
+  g.ntr = (int)(g.np / TM);
+  g.flags = reinterpret_cast<int*>(g.W + B * g.nb * TN * TN);
+  g.done = g.flags + align_up(B * g.nb, 64);
+  g.col_start = reinterpret_cast<int64_t*>(g.done + align_up(B * g.ntr, 64));
+  return g;
+}
+
 }  // namespace thb
 
 extern "C" {
 
 int64_t thb_potrf_workspace_bytes(int64_t B, int64_t n) {
   if (B <= 0 || n <= 0) return 0;
-  const int64_t nblk = (n + thb::NB - 1) / thb::NB, np = nblk * thb::NB;
+  const int64_t np = thb::align_up(n, thb::TM), nb = np / thb::TN;
   int64_t bytes = B * np * np * 8;                              // L
-  bytes += B * nblk * thb::NB * thb::NB * 8;                    // W
-  bytes += thb::align_up(B * nblk * 4, 256);                    // flags
-  return bytes;
+  bytes += B * nb * thb::TN * thb::TN * 8;                      // W
+  bytes += thb::align_up(B * nb, 64) * 4;                       // flags (W_j ready)
+  bytes += thb::align_up(B * (np / thb::TM), 64) * 4;           // finished-column counters per row tile
+  bytes += (nb + 1) * 8;                                        // first CTA index of every block column
+  return thb::align_up(bytes, 256);
 }
 
-int thb_potrf_potrs_f64(const double* AtA, const double* rhs, const double* alpha, const double* beta, double* x, int32_t* info,
-                        int64_t B, int64_t n, void* workspace, int64_t workspace_bytes, thb_stream_t stream) {
-  if (B < 0 || n < 0 || AtA == nullptr || rhs == nullptr || x == nullptr || info == nullptr || workspace == nullptr)
-    return THB_ERR_BAD_ARG;
+int thb_potrf_f64(const double* AtA, const double* alpha, const double* beta, int32_t* info, int64_t B, int64_t n, void* workspace,
+                  int64_t workspace_bytes, thb_stream_t stream) {
+  if (B < 0 || n < 0 || AtA == nullptr || info == nullptr || workspace == nullptr) return THB_ERR_BAD_ARG;
   if (B == 0 || n == 0) return THB_OK;
   if (workspace_bytes < thb_potrf_workspace_bytes(B, n)) return THB_ERR_BAD_ARG;
   cudaStream_t cs = thb_cs(stream);
-  const int nblk = (int)((n + thb::NB - 1) / thb::NB);
-  const int64_t np = (int64_t)nblk * thb::NB;
-  char* ws = static_cast<char*>(workspace);
-  double* L = reinterpret_cast<double*>(ws);
-  double* W = L + B * np * np;
-  int* flags = reinterpret_cast<int*>(W + B * nblk * thb::NB * thb::NB);
-  THB_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * nblk * 4, cs));
+  thb::Geometry g = thb::geometry(workspace, B, n);
+  THB_CUDA(cudaMemsetAsync(g.flags, 0, (size_t)(thb::align_up(B * g.nb, 64) + thb::align_up(B * g.ntr, 64)) * 4, cs));
   THB_CUDA(cudaMemsetAsync(info, 0, (size_t)B * 4, cs));
+  // CTA index table (host-computed, tiny): column j owns (ntr - j/2) * B CTAs
+  int64_t starts[1026];
+  if (g.nb > 1024) return THB_ERR_UNSUPPORTED;
+  starts[0] = 0;
+  for (int j = 0; j < g.nb; j++) starts[j + 1] = starts[j] + (int64_t)(g.ntr - (j >> 1)) * B;
+  if (starts[g.nb] > 2147483647LL) return THB_ERR_UNSUPPORTED;
+  THB_CUDA(cudaMemcpyAsync(g.col_start, starts, sizeof(int64_t) * (g.nb + 1), cudaMemcpyHostToDevice, cs));
   static bool attr_set = false;
   if (!attr_set) {
     THB_CUDA(cudaFuncSetAttribute(thb::chol_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thb::CHOL_SMEM));
     attr_set = true;
   }
   thb::CholArgs a;
-  a.AtA = AtA; a.alpha = alpha; a.beta = beta; a.L = L; a.W = W; a.flags = flags; a.info = info;
-  a.B = B; a.n = n; a.np = np; a.nblk = nblk;
-  for (int j = 0; j < nblk; j++) {
-    a.j = j;
-    const int64_t grid = (int64_t)(nblk - j) * B;
-    thb::chol_col_kernel<<<(unsigned)grid, thb::CHOL_THREADS, thb::CHOL_SMEM, cs>>>(a);
-    THB_CHECK_LAUNCH();
-  }
+  a.AtA = AtA; a.alpha = alpha; a.beta = beta; a.L = g.L; a.W = g.W; a.flags = g.flags; a.done = g.done;
+  a.col_start = g.col_start; a.info = info;
+  a.B = B; a.n = n; a.np = g.np; a.nb = g.nb; a.ntr = g.ntr;
+  // ONE launch for the whole factorisation: block columns are chained through the per-tile counters, so there are
+  // no per-column launch gaps and no per-column wave-quantisation tails.
+  thb::chol_col_kernel<<<(unsigned)starts[g.nb], thb::CHOL_THREADS, thb::CHOL_SMEM, cs>>>(a);
+  THB_CHECK_LAUNCH();
+  return THB_OK;
+}
+
+int thb_potrs_f64(const double* rhs, double* x, int64_t B, int64_t n, const void* workspace, int64_t workspace_bytes,
+                  thb_stream_t stream) {
+  if (B < 0 || n < 0 || rhs == nullptr || x == nullptr || workspace == nullptr) return THB_ERR_BAD_ARG;
+  if (B == 0 || n == 0) return THB_OK;
+  if (workspace_bytes < thb_potrf_workspace_bytes(B, n)) return THB_ERR_BAD_ARG;
+  thb::Geometry g = thb::geometry(const_cast<void*>(workspace), B, n);
   thb::SolveArgs s;
-  s.L = L; s.W = W; s.rhs = rhs; s.x = x; s.B = B; s.n = n; s.np = np; s.nblk = nblk;
-  const size_t ssm = (size_t)(np + thb::NB + 8 * thb::NB) * 8;
+  s.L = g.L; s.W = g.W; s.rhs = rhs; s.x = x; s.B = B; s.n = n; s.np = g.np; s.nb = g.nb;
+  const size_t ssm = (size_t)(g.np + thb::TN + 8 * thb::TN) * 8;
   static size_t solve_smem_set = 0;
   if (ssm > 48 * 1024 && ssm > solve_smem_set) {
     THB_CUDA(cudaFuncSetAttribute(thb::chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
     solve_smem_set = ssm;
   }
-  thb::chol_solve_kernel<<<(unsigned)B, thb::SOLVE_THREADS, ssm, cs>>>(s);
+  thb::chol_solve_kernel<<<(unsigned)B, thb::SOLVE_THREADS, ssm, thb_cs(stream)>>>(s);
   THB_CHECK_LAUNCH();
   return THB_OK;
+}
+
+int thb_potrf_potrs_f64(const double* AtA, const double* rhs, const double* alpha, const double* beta, double* x, int32_t* info,
+                        int64_t B, int64_t n, void* workspace, int64_t workspace_bytes, thb_stream_t stream) {
+  if (rhs == nullptr || x == nullptr) return THB_ERR_BAD_ARG;
+  int rc = thb_potrf_f64(AtA, alpha, beta, info, B, n, workspace, workspace_bytes, stream);
+  if (rc != THB_OK) return rc;
+  return thb_potrs_f64(rhs, x, B, n, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

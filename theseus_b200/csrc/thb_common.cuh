@@ -4,8 +4,11 @@
 #include <stdint.h>
 #include "../../include/thb200.h"
 
+// every kernel launch of the library goes through this macro: it also counts launches (thb_launch_count)
+extern "C" int64_t thb_launch_counter_;
 #define THB_CHECK_LAUNCH()                               \
   do {                                                   \
+    ++thb_launch_counter_;                               \
     cudaError_t _e = cudaGetLastError();                 \
     if (_e != cudaSuccess) return static_cast<int>(_e);  \
   } while (0)

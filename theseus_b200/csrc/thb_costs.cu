@@ -529,6 +529,8 @@ template <typename T> static int commit_impl(const thb_var_table* vt, int64_t B,
 // ================================================================================================
 extern "C" {
 
+int64_t thb_launch_counter_ = 0;
+int64_t thb_launch_count(void) { return thb_launch_counter_; }
 int thb_version(void) { return 100; }
 int thb_compiled_arch(void) {
 #ifdef THB_ARCH

@@ -347,8 +347,11 @@ class NonlinearLeastSquares:
     def __init__(self, objective: Objective, *args, linear_solver_cls: Optional[Type[LinearSolver]] = None, vectorize: bool = False,
                  linearization_cls: Optional[Type[Linearization]] = None, linearization_kwargs: Optional[Dict[str, Any]] = None,
                  linear_solver_kwargs: Optional[Dict[str, Any]] = None, abs_err_tolerance: float = 1e-10,
-                 rel_err_tolerance: float = 1e-8, max_iterations: int = 20, step_size: float = 1.0, **kwargs):
+                 rel_err_tolerance: float = 1e-8, max_iterations: int = 20, step_size: float = 1.0, process_group=None, **kwargs):
         self.objective = objective
+        # Batch sharding over GPUs (no reference analogue): every rank owns a slice of the batch; the only
+        # batch-global decisions of the loop (all-rejected retry, all-converged exit, mean-error test) are all-reduced.
+        self.process_group = process_group
         self.params = NonlinearOptimizerParams(abs_err_tolerance, rel_err_tolerance, max_iterations, step_size)
         linear_solver_cls = linear_solver_cls or CholeskyDenseSolver
         linear_solver_kwargs = linear_solver_kwargs or {}
@@ -504,9 +507,8 @@ class NonlinearLeastSquares:
         step = float(self.params.step_size)
         eng.retract_into(delta, self._tmp_optim_vars, step, converged_indices)
         err_new = eng.error_metric("tmp")
-        reject, err, n_rej = self._complete_step(delta, err_new, previous_err, **kwargs)
-        B = self.objective.batch_size
-        if reject is not None and n_rej == B:
+        reject, err, all_rejected = self._complete_step(delta, err_new, previous_err, **kwargs)
+        if reject is not None and all_rejected:
             return previous_err, True
         eng.commit(reject)
         return err, False
@@ -515,7 +517,7 @@ class NonlinearLeastSquares:
         self.linear_solver.reset(**kwargs)
 
     def _complete_step(self, delta, new_err, previous_err, **kwargs):
-        return None, new_err, 0
+        return None, new_err, False
 
     def compute_delta(self, **kwargs) -> torch.Tensor:
         raise NotImplementedError
@@ -554,7 +556,7 @@ class LevenbergMarquardt(NonlinearLeastSquares):
     def _complete_step(self, delta, new_err, previous_err, adaptive_damping: bool = False, down_damping_ratio: float = 9.0,
                        up_damping_ratio: float = 11.0, damping_accept: float = 0.1, ellipsoidal_damping: bool = False, **kwargs):
         if not adaptive_damping:
-            return None, new_err, 0
+            return None, new_err, False
         return self._check_accept(delta, new_err, previous_err, damping_accept, down_damping_ratio, up_damping_ratio, ellipsoidal_damping)
 
     @torch.no_grad()
@@ -578,7 +580,13 @@ class LevenbergMarquardt(NonlinearLeastSquares):
             _lib.ptr(delta), _lib.ptr(Atb), _lib.ptr(diag), B, n, float(self.params.step_size), _lib.ptr(previous_err), _lib.ptr(err),
             _lib.ptr(self._damping), 1 if ellipsoidal_damping else 0, float(damping_accept), float(down_damping_ratio),
             float(up_damping_ratio), _lib.ptr(reject), _lib.ptr(err_out), _lib.ptr(stats), _lib.stream_ptr()), "lm_control")
+        if self.process_group is not None:
+            # the single per-iteration collective: [#rejected, #items] summed over ranks (NCCL, latency-bound)
+            import torch.distributed as dist
+            stats[1] = B
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.process_group)
         self._stats_host.copy_(stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         n_rej = int(self._stats_host[0])
-        return reject, err_out, n_rej
+        total = int(self._stats_host[1]) if self.process_group is not None else B
+        return reject, err_out, n_rej == total
