@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libthb200.so")
+_LIB_PATH = os.environ.get("THB200_LIB") or os.path.join(_HERE, "lib", "libthb200.so")  # override: kernel-variant experiments
 _lib = None
 
 c_i32, c_i64, c_f64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_float, C.c_void_p

@@ -28,18 +28,28 @@ namespace thb {
 
 constexpr int TM = 128;        // tile rows
 constexpr int TN = 64;         // tile cols = block-column width
-constexpr int KB = 16;         // k-step of the pipelined product
-constexpr int SA = 20;         // smem row stride (doubles) of a [rows x KB] operand tile: 2*SA mod 32 == 8 -> conflict-free DMMA fragment loads
+#ifndef THB_CHOL_KB
+#define THB_CHOL_KB 16
+#endif
+#ifndef THB_CHOL_STAGES
+#define THB_CHOL_STAGES 3
+#endif
+constexpr int KB = THB_CHOL_KB;  // k-step of the pipelined product
+constexpr int SA = KB + 4;     // smem row stride (doubles) of a [rows x KB] operand tile: 2*SA mod 32 == 8 -> conflict-free DMMA fragment loads
+constexpr int KB_W = 16;       // k-step of the (short) TRSM product
+constexpr int SW = KB_W + 4;
 constexpr int SC = 68;         // smem row stride (doubles) of the 128x64 C tile (2*SC mod 32 == 8)
 constexpr int SB32 = 36;       // row stride of the 32x32 inverse blocks
-constexpr int STAGES = 3;
+constexpr int STAGES = THB_CHOL_STAGES;
 constexpr int WSTAGES = 3;
 constexpr int CHOL_THREADS = 256;
 constexpr int A_TILE = TM * SA;  // doubles
 constexpr int B_TILE = TN * SA;
-constexpr size_t SMEM_PHASE_A = (size_t)STAGES * (A_TILE + B_TILE) * 8;        // 92160
-constexpr size_t SMEM_PHASE_D = (size_t)(TM * SC + WSTAGES * B_TILE) * 8;      // 69632 + 30720 = 100352
+constexpr int W_TILE = TN * SW;
+constexpr size_t SMEM_PHASE_A = (size_t)STAGES * (A_TILE + B_TILE) * 8;        // 92160 (KB=16, 3 stages)
+constexpr size_t SMEM_PHASE_D = (size_t)(TM * SC + WSTAGES * W_TILE) * 8;      // 69632 + 30720 = 100352
 constexpr size_t CHOL_SMEM = SMEM_PHASE_A > SMEM_PHASE_D ? SMEM_PHASE_A : SMEM_PHASE_D;
+static_assert(2 * (CHOL_SMEM + 1024) <= 232448, "two CTAs per SM must fit in shared memory");
 
 __device__ __forceinline__ void mma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -52,13 +62,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // stage one [ROWS x KB] operand tile: ROWS consecutive rows of a row-major matrix (leading dimension ld), columns k0..k0+KB
-template <int ROWS>
+template <int ROWS, int KBX>
 __device__ __forceinline__ void load_oper_tile(double* dst, const double* __restrict__ src, int64_t ld, int k0, int tid) {
+  constexpr int CPR = KBX / 2;  // 16-byte chunks per row
 #pragma unroll
-  for (int q = 0; q < (ROWS * KB / 2) / CHOL_THREADS; q++) {
+  for (int q = 0; q < (ROWS * CPR) / CHOL_THREADS; q++) {
     const int chunk = tid + q * CHOL_THREADS;
-    const int row = chunk >> 3, cc = chunk & 7;
-    cp_async16(dst + row * SA + cc * 2, src + (int64_t)row * ld + k0 + cc * 2);
+    const int row = chunk / CPR, cc = chunk % CPR;
+    cp_async16(dst + row * (KBX + 4) + cc * 2, src + (int64_t)row * ld + k0 + cc * 2);
   }
 }
 
@@ -285,14 +296,15 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   }
 
   const int nk = j * (TN / KB);
+  const bool skip_mma = is_diag && (wm * 32 < roff);  // odd block columns: the upper 64 rows of the diagonal tile lie above the diagonal
   const double* Arow = Lb + (int64_t)i * TM * np;
   const double* Brow = Lb + (int64_t)j * TN * np;
   if (nk > 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
       if (s < nk) {
-        load_oper_tile<TM>(smem + (size_t)s * (A_TILE + B_TILE), Arow, np, s * KB, tid);
-        if (!is_diag) load_oper_tile<TN>(smem + (size_t)s * (A_TILE + B_TILE) + A_TILE, Brow, np, s * KB, tid);
+        load_oper_tile<TM, KB>(smem + (size_t)s * (A_TILE + B_TILE), Arow, np, s * KB, tid);
+        if (!is_diag) load_oper_tile<TN, KB>(smem + (size_t)s * (A_TILE + B_TILE) + A_TILE, Brow, np, s * KB, tid);
       }
       cp_async_commit();
     }
@@ -303,13 +315,14 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
         const int nx = ks + STAGES - 1;
         if (nx < nk) {
           const int s = nx % STAGES;
-          load_oper_tile<TM>(smem + (size_t)s * (A_TILE + B_TILE), Arow, np, nx * KB, tid);
-          if (!is_diag) load_oper_tile<TN>(smem + (size_t)s * (A_TILE + B_TILE) + A_TILE, Brow, np, nx * KB, tid);
+          load_oper_tile<TM, KB>(smem + (size_t)s * (A_TILE + B_TILE), Arow, np, nx * KB, tid);
+          if (!is_diag) load_oper_tile<TN, KB>(smem + (size_t)s * (A_TILE + B_TILE) + A_TILE, Brow, np, nx * KB, tid);
         }
         cp_async_commit();
       }
       const double* As = smem + (size_t)(ks % STAGES) * (A_TILE + B_TILE);
       const double* Bs = is_diag ? (As + roff * SA) : (As + A_TILE);  // diagonal tile: the column rows are a half of its own rows
+      if (skip_mma) continue;  // rows above the diagonal block: nothing to compute (the warp still loads and syncs)
 #pragma unroll
       for (int k4 = 0; k4 < KB / 4; k4++) {
         double a[4], bf[4];
@@ -370,11 +383,11 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   for (int mi = 0; mi < 2; mi++)
 #pragma unroll
     for (int ni = 0; ni < 8; ni++) acc2[mi][ni][0] = acc2[mi][ni][1] = 0.0;
-  constexpr int NKW = TN / KB;  // 4
+  constexpr int NKW = TN / KB_W;  // 4
   const bool active = (warp * 16 >= row_lo);
 #pragma unroll
   for (int s = 0; s < WSTAGES - 1; s++) {
-    load_oper_tile<TN>(Ws + (size_t)s * B_TILE, Wj, TN, s * KB, tid);
+    load_oper_tile<TN, KB_W>(Ws + (size_t)s * W_TILE, Wj, TN, s * KB_W, tid);
     cp_async_commit();
   }
 #pragma unroll
@@ -383,21 +396,21 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
     __syncthreads();
     {
       const int nx = ks + WSTAGES - 1;
-      if (nx < NKW) load_oper_tile<TN>(Ws + (size_t)(nx % WSTAGES) * B_TILE, Wj, TN, nx * KB, tid);
+      if (nx < NKW) load_oper_tile<TN, KB_W>(Ws + (size_t)(nx % WSTAGES) * W_TILE, Wj, TN, nx * KB_W, tid);
       cp_async_commit();
     }
-    const double* Wst = Ws + (size_t)(ks % WSTAGES) * B_TILE;
+    const double* Wst = Ws + (size_t)(ks % WSTAGES) * W_TILE;
     if (active) {
 #pragma unroll
-      for (int k4 = 0; k4 < KB / 4; k4++) {
-        const int kk = ks * KB + k4 * 4;
+      for (int k4 = 0; k4 < KB_W / 4; k4++) {
+        const int kk = ks * KB_W + k4 * 4;
         double a[2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) a[mi] = Cs[(warp * 16 + mi * 8 + lr) * SC + kk + lc];
 #pragma unroll
         for (int ni = 0; ni < 8; ni++) {
           if (ni * 8 + 7 >= kk) {  // W[c][k] == 0 for k > c: skip column blocks entirely above this k
-            const double bfr = Wst[(ni * 8 + lr) * SA + k4 * 4 + lc];
+            const double bfr = Wst[(ni * 8 + lr) * SW + k4 * 4 + lc];
             mma884(acc2[0][ni][0], acc2[0][ni][1], a[0], bfr);
             mma884(acc2[1][ni][0], acc2[1][ni][1], a[1], bfr);
           }
