@@ -182,6 +182,53 @@ int thb_potrf_potrs_f64(const double* AtA, const double* rhs, const double* alph
                         thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Batched block-sparse Cholesky over a batch-shared symbolic plan (host analysis: theseus_b200/sparse.py).
+ * Replaces theseus.extlib.baspacho_solver (SymbolicDecomposition / NumericDecomposition.{add_MtM,damp,factor,solve},
+ * extlib/baspacho_solver.cpp:326-358, baspacho_solver_cuda.cu), cusolverRf refactor/solve
+ * (extlib/cusolver_lu_solver.cpp:252-310) and the CHOLMOD per-item loop (optimizer/autograd/cholmod_sparse_autograd.py:25-61).
+ *   factor storage  [B, data_size] fp64: per elimination column the diagonal block then its sub-diagonal blocks, row-major
+ *                   (filled with the AtA blocks by thb_gram_f64 using a plan whose block offsets point into this storage)
+ *   winv            [B, winv_size] fp64: inverse of every diagonal block of L (turns the triangular solves into mat-vecs)
+ * All index arrays are device arrays shared by the whole batch.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thb_sparse_plan {
+  int32_t N;          /* number of variable blocks */
+  int32_t num_levels; /* elimination-tree levels */
+  int32_t max_dim;    /* largest block dimension (<= 16) */
+  int32_t reserved;
+  int64_t n;          /* scalar dimension */
+  int64_t data_size;
+  int64_t winv_size;
+  const int32_t* dims;      /* [N] block size per elimination position */
+  const int32_t* col_start; /* [N] first scalar column (ORIGINAL order) of the variable at this position */
+  const int32_t* pstart;    /* [N] first scalar index in the permuted vector */
+  const int64_t* winv_off;  /* [N] */
+  const int64_t* diag_off;  /* [N] offset of the diagonal block */
+  const int64_t* up_a;      /* update pairs: offset of L_ik */
+  const int64_t* up_b;      /*               offset of L_jk */
+  const int32_t* up_k;      /*               dk */
+  const int64_t* u_ptr;     /* [L+1] work items of stage U per level */
+  const int64_t* u_tgt; const int16_t* u_r; const int16_t* u_c; const int16_t* u_ld; const int64_t* u_p0; const int64_t* u_p1;
+  const int64_t* f_ptr;     /* [L+1] stage F (diagonal blocks) */
+  const int64_t* f_off; const int32_t* f_dim; const int64_t* f_w; const int32_t* f_col;
+  const int64_t* t_ptr;     /* [L+1] stage T (block rows of sub-diagonal blocks) */
+  const int64_t* t_off; const int16_t* t_r; const int16_t* t_dim; const int64_t* t_w;
+  const int64_t* s_ptr;     /* [L+1] columns per level (solve) */
+  const int32_t* s_col;
+  const int64_t* fr_ptr; const int64_t* fr_off; const int32_t* fr_k; /* row lists (forward substitution) */
+  const int64_t* bc_ptr; const int64_t* bc_off; const int32_t* bc_i; /* column lists (backward substitution) */
+} thb_sparse_plan;
+
+/* diag(M_b) <- diag(M_b) * (1 + alpha_b) + beta_b on the factor storage (NumericDecomposition.damp) */
+int thb_sparse_damp_f64(const thb_sparse_plan* p, double* factor, const double* alpha, const double* beta, int64_t B,
+                        thb_stream_t stream);
+/* in-place L L^T = M (NumericDecomposition.factor); info[b] = 0 or 1 + permuted index of the first bad pivot */
+int thb_sparse_factor_f64(const thb_sparse_plan* p, double* factor, double* winv, int32_t* info, int64_t B, thb_stream_t stream);
+/* x = M^-1 rhs in the ORIGINAL variable order (NumericDecomposition.solve incl. scramble/unscramble); work: [B,n] scratch */
+int thb_sparse_solve_f64(const thb_sparse_plan* p, const double* factor, const double* winv, const double* rhs, double* x,
+                         double* work, int64_t B, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Levenberg-Marquardt control (device-resident accept/reject + damping update).
  *   den = 1/2 sum_j d_j (lam_eff_j d_j + Atb_j), d = step*delta, lam_eff = lam*diag(AtA) if ellipsoidal else lam
  *   rho = (err_prev - err_new)/den ; reject = rho <= damping_accept

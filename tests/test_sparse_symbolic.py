@@ -1,0 +1,146 @@
+"""Host logic of the block-sparse solver (no GPU): the symbolic plan (ordering, fill, levels, update lists, work items)
+is executed by a tiny numpy interpreter of the very arrays the CUDA kernels consume, and the result is checked the way
+the reference checks BaSpaCho (tests/theseus_tests/extlib/test_baspacho.py:101-114: residual of (AtA + damping) x = Atb),
+including the reference's literal 12x12 system shape (params [2,3,5,2], extlib/test_baspacho_simple.py:15-112)."""
+import numpy as np
+import pytest
+
+from theseus_b200.sparse import analyze, minimum_degree_order
+
+
+def run_plan_numpy(plan, M, rhs):
+    """Interpret plan.arrays on one SPD matrix M (original order).  Returns x with M x = rhs."""
+    A = plan.arrays
+    N, dims, cs = plan.N, plan.dims, plan.col_start
+    F = np.zeros(plan.data_size)
+    for (i, j), t in plan.blk_index.items():
+        blk = M[cs[i]:cs[i] + dims[i], cs[j]:cs[j] + dims[j]]
+        F[plan.blk_off[t]:plan.blk_off[t] + blk.size] = blk.reshape(-1)
+    W = np.zeros(plan.winv_size)
+    nlev = len(A["u_ptr"]) - 1
+    for lv in range(nlev):
+        new = {}
+        for e in range(A["u_ptr"][lv], A["u_ptr"][lv + 1]):
+            tgt, r, c, ld = A["u_tgt"][e], A["u_r"][e], A["u_c"][e], A["u_ld"][e]
+            acc = F[tgt + r * ld + c]
+            for p in range(A["u_p0"][e], A["u_p1"][e]):
+                dk = A["up_k"][p]
+                a0, b0 = A["up_a"][p] + r * dk, A["up_b"][p] + c * dk
+                acc -= F[a0:a0 + dk] @ F[b0:b0 + dk]
+            new[tgt + r * ld + c] = acc
+        for k, v in new.items():
+            F[k] = v
+        for e in range(A["f_ptr"][lv], A["f_ptr"][lv + 1]):
+            off, d, w = A["f_off"][e], A["f_dim"][e], A["f_w"][e]
+            D = np.tril(F[off:off + d * d].reshape(d, d))
+            D = D + np.tril(D, -1).T
+            L = np.linalg.cholesky(D)
+            F[off:off + d * d] = L.reshape(-1)
+            W[w:w + d * d] = np.linalg.inv(L).reshape(-1)
+        for e in range(A["t_ptr"][lv], A["t_ptr"][lv + 1]):
+            off, r, d, w = A["t_off"][e], A["t_r"][e], A["t_dim"][e], A["t_w"][e]
+            U = F[off + r * d:off + r * d + d].copy()
+            Wm = W[w:w + d * d].reshape(d, d)
+            F[off + r * d:off + r * d + d] = Wm @ U  # L[r][c] = sum_q U[q] W[c][q]
+    # solve
+    y = [rhs[cs[j]:cs[j] + dims[j]].copy() for j in range(N)]
+    for lv in range(nlev):
+        for e in range(A["s_ptr"][lv], A["s_ptr"][lv + 1]):
+            j = A["s_col"][e]
+            d = dims[j]
+            s = y[j].copy()
+            for p in range(A["fr_ptr"][j], A["fr_ptr"][j + 1]):
+                k = A["fr_k"][p]
+                dk = dims[k]
+                s -= F[A["fr_off"][p]:A["fr_off"][p] + d * dk].reshape(d, dk) @ y[k]
+            y[j] = W[A["winv_off"][j]:A["winv_off"][j] + d * d].reshape(d, d) @ s
+    for lv in reversed(range(nlev)):
+        for e in range(A["s_ptr"][lv], A["s_ptr"][lv + 1]):
+            j = A["s_col"][e]
+            d = dims[j]
+            s = y[j].copy()
+            for p in range(A["bc_ptr"][j], A["bc_ptr"][j + 1]):
+                i = A["bc_i"][p]
+                di = dims[i]
+                s -= F[A["bc_off"][p]:A["bc_off"][p] + di * d].reshape(di, d).T @ y[i]
+            y[j] = W[A["winv_off"][j]:A["winv_off"][j] + d * d].reshape(d, d).T @ s
+    x = np.zeros_like(rhs)
+    for j in range(N):
+        x[cs[j]:cs[j] + dims[j]] = y[j]
+    return x
+
+
+def random_block_spd(rng, sizes, fill):
+    """Random block-sparse SPD matrix in the style of theseus/utils/sparse_matrix_utils.py:193-227 + AtA + I."""
+    N = len(sizes)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    n = starts[-1]
+    rows = max(3 * N, 8)
+    J = np.zeros((rows * 2, n))
+    for r in range(rows):
+        vs = [v for v in range(N) if rng.random() < fill] or [int(rng.integers(N))]
+        if len(vs) == 1 and N > 1:
+            vs.append(int((vs[0] + 1 + rng.integers(N - 1)) % N))
+        for v in set(vs):
+            J[2 * r:2 * r + 2, starts[v]:starts[v + 1]] = rng.standard_normal((2, sizes[v]))
+    M = J.T @ J + np.eye(n)
+    nbr = [set([i]) for i in range(N)]
+    for i in range(N):
+        for j in range(N):
+            if np.abs(M[starts[i]:starts[i + 1], starts[j]:starts[j + 1]]).max() > 0:
+                nbr[i].add(j)
+    ptrs, inds = [0], []
+    for i in range(N):
+        inds += sorted(nbr[i])
+        ptrs.append(len(inds))
+    return M, np.array(ptrs), np.array(inds)
+
+
+@pytest.mark.parametrize("sizes,fill,ordering", [
+    ([2, 3, 5, 2], 0.6, "mindeg"),             # the reference's literal test shape
+    ([2, 3, 5, 2], 0.6, "natural"),
+    ([6] * 12, 0.15, "mindeg"),
+    ([1, 13, 2, 6, 3, 3, 6, 6, 4, 2, 5], 0.2, "mindeg"),   # param_size_range 1:13 (extlib/test_baspacho.py)
+    ([3] * 30 + [6] * 5, 0.08, "mindeg"),      # bundle-adjustment-like: many small blocks tied to a few big ones
+])
+def test_plan_solves_system(sizes, fill, ordering):
+    rng = np.random.default_rng(len(sizes) + int(fill * 100))
+    M, ptrs, inds = random_block_spd(rng, sizes, fill)
+    plan = analyze(np.array(sizes), ptrs, inds, ordering=ordering)
+    assert sorted(plan.order.tolist()) == list(range(len(sizes)))
+    rhs = rng.standard_normal(M.shape[0])
+    x = run_plan_numpy(plan, M, rhs)
+    assert np.abs(M @ x - rhs).max() < 1e-10   # the reference's criterion (extlib/test_baspacho.py:101-114)
+
+
+def test_minimum_degree_eliminates_leaves_first_and_is_deterministic():
+    # star + chain: the leaves of the star must go before the hub
+    N = 8
+    nbr = {0: [1, 2, 3, 4, 5], 5: [6], 6: [7]}
+    adj = [set([i]) for i in range(N)]
+    for a, bs in nbr.items():
+        for b in bs:
+            adj[a].add(b); adj[b].add(a)
+    ptrs, inds = [0], []
+    for i in range(N):
+        inds += sorted(adj[i]); ptrs.append(len(inds))
+    o1 = minimum_degree_order(N, np.array(ptrs), np.array(inds), np.ones(N, dtype=np.int64))
+    o2 = minimum_degree_order(N, np.array(ptrs), np.array(inds), np.ones(N, dtype=np.int64))
+    assert o1.tolist() == o2.tolist()
+    assert list(o1).index(0) > list(o1).index(1)
+
+
+def test_fill_reducing_quality_on_pose_graph_ring():
+    # 60-node ring with chords: minimum degree must beat the natural order clearly (ordering is worth 3-5x)
+    N = 60
+    adj = [set([i, (i + 1) % N, (i - 1) % N]) for i in range(N)]
+    for i in range(0, N, 7):
+        j = (i * 3 + 11) % N
+        adj[i].add(j); adj[j].add(i)
+    ptrs, inds = [0], []
+    for i in range(N):
+        inds += sorted(adj[i]); ptrs.append(len(inds))
+    sizes = np.full(N, 6)
+    a = analyze(sizes, np.array(ptrs), np.array(inds), "mindeg")
+    b = analyze(sizes, np.array(ptrs), np.array(inds), "natural")
+    assert a.stats["nnz_L"] < 0.8 * b.stats["nnz_L"]

@@ -18,6 +18,7 @@ from .optimizer import (VariableOrdering, Linearization, DenseLinearization, Spa
                         DenseSolver, CholeskyDenseSolver, LUDenseSolver, NonlinearLeastSquares, GaussNewton,
                         LevenbergMarquardt, NonlinearOptimizerStatus, NonlinearOptimizerInfo, OptimizerInfo,
                         NonlinearOptimizerParams, BackwardMode, convert_to_alpha_beta_damping_tensors)
+from .sparse_solver import BaspachoSparseSolver, BlockSparseSolver, CholmodSparseSolver, LUCudaSparseSolver  # noqa: F401
 from .layer import TheseusLayer  # noqa: F401
 
 __version__ = "0.1.0"

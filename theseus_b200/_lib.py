@@ -32,8 +32,19 @@ class GramPlan(C.Structure):
                 ("cc_row0", c_vp)]
 
 
+class SparsePlanStruct(C.Structure):
+    _fields_ = [("N", c_i32), ("num_levels", c_i32), ("max_dim", c_i32), ("reserved", c_i32),
+                ("n", c_i64), ("data_size", c_i64), ("winv_size", c_i64)] + [(k, c_vp) for k in (
+                    "dims", "col_start", "pstart", "winv_off", "diag_off", "up_a", "up_b", "up_k",
+                    "u_ptr", "u_tgt", "u_r", "u_c", "u_ld", "u_p0", "u_p1",
+                    "f_ptr", "f_off", "f_dim", "f_w", "f_col",
+                    "t_ptr", "t_off", "t_r", "t_dim", "t_w",
+                    "s_ptr", "s_col", "fr_ptr", "fr_off", "fr_k", "bc_ptr", "bc_off", "bc_i")]
+
+
 # name -> (restype, argtypes); every symbol declared in include/thb200.h
 _PG, _PV, _PP = C.POINTER(CostGroup), C.POINTER(VarTable), C.POINTER(GramPlan)
+_PS = C.POINTER(SparsePlanStruct)
 SIGNATURES = {
     "thb_version": (c_i32, []),
     "thb_compiled_arch": (c_i32, []),
@@ -55,6 +66,9 @@ SIGNATURES = {
     "thb_potrf_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "thb_potrs_f64": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "thb_potrf_potrs_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "thb_sparse_damp_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_factor_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_solve_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_lm_control_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64,
                                    c_vp, c_vp, c_vp, c_vp]),
     "thb_mat_vec_f64": (c_i32, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -377,7 +377,12 @@ class NonlinearLeastSquares:
         if self.params.abs_err_tolerance <= 0 and self.params.rel_err_tolerance <= 0:
             # |x| < tol is identically False for tol <= 0: no device->host sync needed for the fixed-iteration runs
             return None
-        if err.abs().mean() < self.params.abs_err_tolerance:
+        if self.process_group is not None:
+            from .distributed import global_mean_abs_error
+            mean_abs = global_mean_abs_error(err, self.process_group)[0]  # mean over the GLOBAL batch
+        else:
+            mean_abs = err.abs().mean()
+        if mean_abs < self.params.abs_err_tolerance:
             return torch.ones_like(err).bool()
         err_change = last_err - err
         return (err_change.abs() < self.params.abs_err_tolerance).logical_or(
@@ -470,7 +475,11 @@ class NonlinearLeastSquares:
                 if converged_indices is not None:
                     cpu_conv = converged_indices.cpu().numpy()
                     info.status[cpu_conv] = NonlinearOptimizerStatus.CONVERGED
-                    if cpu_conv.all():
+                    all_conv = bool(cpu_conv.all())
+                    if self.process_group is not None:  # every rank must take the same exit (collectives stay matched)
+                        from .distributed import all_rejected as _count_equals_total
+                        all_conv = _count_equals_total(int(cpu_conv.sum()), len(cpu_conv), self.process_group, err.device)
+                    if all_conv:
                         break
                 info.last_err = err
                 if end_iter_callback is not None:
@@ -582,9 +591,9 @@ class LevenbergMarquardt(NonlinearLeastSquares):
             float(up_damping_ratio), _lib.ptr(reject), _lib.ptr(err_out), _lib.ptr(stats), _lib.stream_ptr()), "lm_control")
         if self.process_group is not None:
             # the single per-iteration collective: [#rejected, #items] summed over ranks (NCCL, latency-bound)
-            import torch.distributed as dist
+            from .distributed import reduce_counts
             stats[1] = B
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.process_group)
+            reduce_counts(stats, self.process_group)
         self._stats_host.copy_(stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         n_rej = int(self._stats_host[0])

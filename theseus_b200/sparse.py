@@ -1,0 +1,242 @@
+"""Symbolic analysis for the batched block-sparse Cholesky (host side, batch independent, once per structure).
+
+Replaces what the reference delegates to third-party code: `BaSpaCho::createSolver` behind
+`SymbolicDecomposition(param_size, block_ptrs, block_inds, device)` (theseus/extlib/baspacho_solver.cpp:259-319),
+`cusolverSpXcsrsymamdHost` + `csrluAnalysisHost` (extlib/cusolver_lu_solver.cpp:95-196) and CHOLMOD's `analyze_AAt`
+(optimizer/linear/cholmod_sparse_solver.py:38-54).  The input is exactly what the reference hands over:
+`param_size [N]` and the CSR (`ptrs`, `inds`) of the symmetric block pattern of AtA
+(optimizer/linear/baspacho_sparse_solver.py:93-113).  The permutation / factor layout are internal ("parity
+unpinned" in the reference too: no reference test observes them); the un-permuted solution is what is checked.
+
+Steps: (1) minimum-degree ordering of the block graph (deterministic tie-break), (2) symbolic factorisation by
+elimination -> column structures, (3) elimination-tree levels (columns of one level are independent),
+(4) factor layout: per column the diagonal block then the sub-diagonal blocks, row-major,
+(5) left-looking update lists: for every block (i,j) of L the pairs (L_ik, L_jk), k < j, that update it,
+(6) flat per-level work-item arrays for the CUDA kernels (thb_sparse.cu).
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+
+def minimum_degree_order(N: int, ptrs: np.ndarray, inds: np.ndarray, weights: np.ndarray) -> np.ndarray:
+    """Greedy minimum (weighted external) degree on the elimination graph.  Returns `order` (order[k] = variable eliminated k-th)."""
+    adj = [set(int(x) for x in inds[ptrs[i]:ptrs[i + 1]] if int(x) != i) for i in range(N)]
+    import heapq
+    deg = [int(sum(weights[a] for a in adj[i])) for i in range(N)]
+    heap = [(deg[i], i) for i in range(N)]
+    heapq.heapify(heap)
+    done = [False] * N
+    order = []
+    while heap:
+        d, v = heapq.heappop(heap)
+        if done[v] or d != deg[v]:
+            continue
+        done[v] = True
+        order.append(v)
+        nb = sorted(adj[v])
+        for a in nb:
+            adj[a].discard(v)
+        for ai, a in enumerate(nb):  # clique among the neighbours
+            sa = adj[a]
+            for b in nb[ai + 1:]:
+                if b not in sa:
+                    sa.add(b)
+                    adj[b].add(a)
+        for a in nb:
+            nd = int(sum(weights[x] for x in adj[a]))
+            if nd != deg[a]:
+                deg[a] = nd
+            heapq.heappush(heap, (deg[a], a))
+        adj[v] = set()
+    return np.array(order, dtype=np.int64)
+
+
+@dataclass
+class SparsePlan:
+    N: int
+    n: int                       # scalar dimension
+    param_size: np.ndarray       # [N] original order
+    order: np.ndarray            # [N] order[k] = original variable eliminated k-th
+    pos: np.ndarray              # [N] pos[v] = elimination position of original variable v
+    dims: np.ndarray             # [N] block size per elimination position
+    col_start: np.ndarray        # [N] scalar start (original column layout) per elimination position
+    pstart: np.ndarray           # [N] scalar start in the permuted vector
+    struct: List[np.ndarray]     # per position j: sorted positions i > j with L_ij != 0
+    level: np.ndarray            # [N] etree level (0 = leaves)
+    blk_index: Dict[Tuple[int, int], int]
+    blk_off: np.ndarray          # [nblk] offset of each block of L in one batch item's factor storage
+    blk_rows: np.ndarray         # [nblk] di
+    blk_cols: np.ndarray         # [nblk] dj
+    data_size: int
+    winv_off: np.ndarray         # [N] offset of W_j = L_jj^-1 in the inverse-diagonal storage
+    winv_size: int
+    arrays: Dict[str, np.ndarray]
+    stats: Dict[str, float]
+
+
+def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering: str = "mindeg") -> SparsePlan:
+    param_size = np.asarray(param_size, dtype=np.int64)
+    N = int(param_size.shape[0])
+    if ordering == "mindeg":
+        order = minimum_degree_order(N, ptrs, inds, param_size)
+    elif ordering == "natural":
+        order = np.arange(N, dtype=np.int64)
+    else:
+        raise ValueError(ordering)
+    pos = np.empty(N, dtype=np.int64)
+    pos[order] = np.arange(N)
+    dims = param_size[order]
+    orig_start = np.concatenate([[0], np.cumsum(param_size)[:-1]]).astype(np.int64)
+    col_start = orig_start[order]
+    pstart = np.concatenate([[0], np.cumsum(dims)[:-1]]).astype(np.int64)
+    n = int(param_size.sum())
+
+    # ---- symbolic factorisation in elimination order ----
+    adj = [set() for _ in range(N)]
+    for v in range(N):
+        pv = int(pos[v])
+        for u in inds[ptrs[v]:ptrs[v + 1]]:
+            pu = int(pos[int(u)])
+            if pu != pv:
+                adj[pv].add(pu)
+    struct: List[np.ndarray] = []
+    for j in range(N):
+        s = sorted(x for x in adj[j] if x > j)
+        struct.append(np.array(s, dtype=np.int64))
+        if s:
+            p = s[0]  # etree parent: the column structure is merged into the parent's
+            adj[p].update(x for x in s if x != p)
+    parent = np.array([int(s[0]) if len(s) else -1 for s in struct], dtype=np.int64)
+    level = np.zeros(N, dtype=np.int64)
+    for j in range(N):
+        if parent[j] >= 0:
+            level[parent[j]] = max(level[parent[j]], level[j] + 1)
+    nlev = int(level.max()) + 1 if N else 0
+
+    # ---- factor layout ----
+    blk_index: Dict[Tuple[int, int], int] = {}
+    blk_off, blk_rows, blk_cols = [], [], []
+    off = 0
+    for j in range(N):
+        for i in [j] + list(struct[j]):
+            blk_index[(int(i), j)] = len(blk_off)
+            blk_off.append(off)
+            blk_rows.append(int(dims[i]))
+            blk_cols.append(int(dims[j]))
+            off += int(dims[i]) * int(dims[j])
+    data_size = off
+    winv_off = np.concatenate([[0], np.cumsum(dims * dims)[:-1]]).astype(np.int64)
+    winv_size = int((dims * dims).sum())
+    blk_off = np.array(blk_off, dtype=np.int64)
+    blk_rows = np.array(blk_rows, dtype=np.int32)
+    blk_cols = np.array(blk_cols, dtype=np.int32)
+    nblk = len(blk_off)
+
+    # ---- left-looking update lists: target block (a,b), a >= b > k, gets (L_ak, L_bk) ----
+    upd: List[List[Tuple[int, int]]] = [[] for _ in range(nblk)]
+    flops = 0
+    for k in range(N):
+        s = struct[k]
+        dk = int(dims[k])
+        flops += dk ** 3 // 3
+        ids = [blk_index[(int(i), k)] for i in s]
+        for bi in range(len(s)):
+            flops += int(dims[s[bi]]) * dk * dk  # trsm
+            for ai in range(bi, len(s)):
+                t = blk_index[(int(s[ai]), int(s[bi]))]
+                upd[t].append((ids[ai], ids[bi]))
+                flops += 2 * int(dims[s[ai]]) * int(dims[s[bi]]) * dk
+    up_ptr = np.zeros(nblk + 1, dtype=np.int64)
+    for t in range(nblk):
+        up_ptr[t + 1] = up_ptr[t] + len(upd[t])
+    up_a = np.zeros(int(up_ptr[-1]), dtype=np.int64)
+    up_b = np.zeros(int(up_ptr[-1]), dtype=np.int64)
+    up_k = np.zeros(int(up_ptr[-1]), dtype=np.int32)
+    for t in range(nblk):
+        for q, (ia, ib) in enumerate(upd[t]):
+            up_a[up_ptr[t] + q] = blk_off[ia]
+            up_b[up_ptr[t] + q] = blk_off[ib]
+            up_k[up_ptr[t] + q] = blk_cols[ia]
+
+    # ---- per-level work items ----
+    cols_by_level = [[] for _ in range(nlev)]
+    for j in range(N):
+        cols_by_level[int(level[j])].append(j)
+    # stage U: one item per scalar entry of every block of the level's columns
+    u_ptr = [0]
+    u_tgt, u_r, u_c, u_ld, u_p0, u_p1, u_diag = [], [], [], [], [], [], []
+    # stage F: one item per column (diag potrf + inverse)
+    f_ptr = [0]
+    f_off, f_dim, f_w, f_col = [], [], [], []
+    # stage T: one item per row of every sub-diagonal block
+    t_ptr = [0]
+    t_off, t_r, t_dim, t_w = [], [], [], []
+    # solve: per column row-structure (forward) and column-structure (backward)
+    row_lists: List[List[Tuple[int, int]]] = [[] for _ in range(N)]  # for target j: (offset of L_jk, k)
+    for k in range(N):
+        for i in struct[k]:
+            row_lists[int(i)].append((int(blk_off[blk_index[(int(i), k)]]), k))
+    s_ptr = [0]
+    s_col = []
+    for lv in range(nlev):
+        for j in cols_by_level[lv]:
+            dj = int(dims[j])
+            for i in [j] + list(struct[j]):
+                t = blk_index[(int(i), j)]
+                di = int(dims[i])
+                for r in range(di):
+                    for c in range(dj):
+                        if i == j and c > r:
+                            continue  # lower triangle of the diagonal block only
+                        u_tgt.append(int(blk_off[t])); u_r.append(r); u_c.append(c); u_ld.append(dj)
+                        u_p0.append(int(up_ptr[t])); u_p1.append(int(up_ptr[t + 1])); u_diag.append(1 if i == j else 0)
+                if i != j:
+                    for r in range(di):
+                        t_off.append(int(blk_off[t])); t_r.append(r); t_dim.append(dj); t_w.append(int(winv_off[j]))
+            f_off.append(int(blk_off[blk_index[(j, j)]])); f_dim.append(dj); f_w.append(int(winv_off[j])); f_col.append(j)
+            s_col.append(j)
+        u_ptr.append(len(u_tgt)); f_ptr.append(len(f_off)); t_ptr.append(len(t_off)); s_ptr.append(len(s_col))
+    # solve lists
+    fr_ptr = [0]
+    fr_off, fr_k = [], []
+    bc_ptr = [0]
+    bc_off, bc_i = [], []
+    for j in range(N):
+        for (o, k) in row_lists[j]:
+            fr_off.append(o); fr_k.append(k)
+        fr_ptr.append(len(fr_off))
+        for i in struct[j]:
+            bc_off.append(int(blk_off[blk_index[(int(i), j)]])); bc_i.append(int(i))
+        bc_ptr.append(len(bc_off))
+
+    i32, i64 = np.int32, np.int64
+    arrays = dict(
+        dims=dims.astype(i32), col_start=col_start.astype(i32), pstart=pstart.astype(i32), winv_off=winv_off.astype(i64),
+        diag_off=np.array([blk_off[blk_index[(j, j)]] for j in range(N)], dtype=i64),
+        up_a=up_a, up_b=up_b, up_k=up_k,
+        u_ptr=np.array(u_ptr, dtype=i64), u_tgt=np.array(u_tgt, dtype=i64), u_r=np.array(u_r, dtype=np.int16),
+        u_c=np.array(u_c, dtype=np.int16), u_ld=np.array(u_ld, dtype=np.int16), u_p0=np.array(u_p0, dtype=i64),
+        u_p1=np.array(u_p1, dtype=i64),
+        f_ptr=np.array(f_ptr, dtype=i64), f_off=np.array(f_off, dtype=i64), f_dim=np.array(f_dim, dtype=i32),
+        f_w=np.array(f_w, dtype=i64), f_col=np.array(f_col, dtype=i32),
+        t_ptr=np.array(t_ptr, dtype=i64), t_off=np.array(t_off, dtype=i64), t_r=np.array(t_r, dtype=np.int16),
+        t_dim=np.array(t_dim, dtype=np.int16), t_w=np.array(t_w, dtype=i64),
+        s_ptr=np.array(s_ptr, dtype=i64), s_col=np.array(s_col, dtype=i32),
+        fr_ptr=np.array(fr_ptr, dtype=i64), fr_off=np.array(fr_off, dtype=i64), fr_k=np.array(fr_k, dtype=i32),
+        bc_ptr=np.array(bc_ptr, dtype=i64), bc_off=np.array(bc_off, dtype=i64), bc_i=np.array(bc_i, dtype=i32))
+    stats = dict(nnz_L=float(data_size), flops=float(flops), levels=float(nlev), max_front=float(max((len(s) + 1 for s in struct), default=0)),
+                 num_updates=float(up_ptr[-1]))
+    return SparsePlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, col_start=col_start, pstart=pstart,
+                      struct=struct, level=level, blk_index=blk_index, blk_off=blk_off, blk_rows=blk_rows, blk_cols=blk_cols,
+                      data_size=data_size, winv_off=winv_off, winv_size=winv_size, arrays=arrays, stats=stats)
+
+
+def gram_out_offsets(plan: SparsePlan):
+    """Callable for structure.build_gram_plan: where block (a, b) of AtA (original variable indices, pos[a] >= pos[b])
+    lands in the factor storage.  Returns (offset, leading dimension, mirror=-1)."""
+    def f(a: int, b: int):
+        t = plan.blk_index[(int(plan.pos[a]), int(plan.pos[b]))]
+        return int(plan.blk_off[t]), int(plan.blk_cols[t]), -1
+    return f

@@ -94,15 +94,17 @@ def ata_block_structure(s: Structure):
     return s.var_dims.copy(), ptrs, np.array(inds, dtype=np.int64)
 
 
-def lower_blocks(s: Structure):
-    """Lower-triangular variable-pair blocks (i >= j) that are structurally non-zero in AtA, with the
-    contributing (cost function, slot a, slot b) triples.  Returns (blocks [(i,j)], contribs [list of lists])."""
+def lower_blocks(s: Structure, pos=None):
+    """Lower-triangular variable-pair blocks (i >= j, or pos[i] >= pos[j] when an elimination order is given) that are
+    structurally non-zero in AtA, with the contributing (cost function, slot a, slot b) triples.
+    Returns (blocks [(i,j)], contribs [list of lists])."""
     index = {}
     blocks, contribs = [], []
+    rank = (lambda v: v) if pos is None else (lambda v: int(pos[v]))
     for f, vs in enumerate(s.cost_vars):
         for a, i in enumerate(vs):
             for b, j in enumerate(vs):
-                if i < j:
+                if rank(i) < rank(j):
                     continue
                 key = (i, j)
                 k = index.get(key)
@@ -115,13 +117,13 @@ def lower_blocks(s: Structure):
     return blocks, contribs
 
 
-def build_gram_plan(s: Structure, out_offsets=None):
+def build_gram_plan(s: Structure, out_offsets=None, pos=None):
     """Arrays of the thb_gram_plan struct (include/thb200.h).
 
     out_offsets: None -> dense AtA [n,n] row-major (lower blocks + mirrored upper blocks);
                  or a callable (i, j) -> (offset, ld, mirror_offset) for block-sparse factor storage.
     """
-    blocks, contribs = lower_blocks(s)
+    blocks, contribs = lower_blocks(s, pos)
     n = s.num_cols
     ent_blk, ent_p, ent_q = [], [], []
     blk_out, blk_ld, blk_mirror, blk_cptr = [], [], [], [0]
