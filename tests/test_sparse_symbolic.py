@@ -19,17 +19,18 @@ def run_plan_numpy(plan, M, rhs):
     W = np.zeros(plan.winv_size)
     nlev = len(A["u_ptr"]) - 1
     for lv in range(nlev):
-        new = {}
         for e in range(A["u_ptr"][lv], A["u_ptr"][lv + 1]):
-            tgt, r, c, ld = A["u_tgt"][e], A["u_r"][e], A["u_c"][e], A["u_ld"][e]
-            acc = F[tgt + r * ld + c]
-            for p in range(A["u_p0"][e], A["u_p1"][e]):
-                dk = A["up_k"][p]
-                a0, b0 = A["up_a"][p] + r * dk, A["up_b"][p] + c * dk
-                acc -= F[a0:a0 + dk] @ F[b0:b0 + dk]
-            new[tgt + r * ld + c] = acc
-        for k, v in new.items():
-            F[k] = v
+            tgt, di, dj, diag = A["u_tgt"][e], A["u_r"][e], A["u_c"][e], A["u_ld"][e]
+            for r in range(di):
+                for c in range(dj):
+                    if diag and c > r:
+                        continue
+                    acc = F[tgt + r * dj + c]
+                    for p in range(A["u_p0"][e], A["u_p1"][e]):
+                        dk = A["up_k"][p]
+                        a0, b0 = A["up_a"][p] + r * dk, A["up_b"][p] + c * dk
+                        acc -= F[a0:a0 + dk] @ F[b0:b0 + dk]
+                    F[tgt + r * dj + c] = acc
         for e in range(A["f_ptr"][lv], A["f_ptr"][lv + 1]):
             off, d, w = A["f_off"][e], A["f_dim"][e], A["f_w"][e]
             D = np.tril(F[off:off + d * d].reshape(d, d))

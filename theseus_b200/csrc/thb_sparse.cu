@@ -50,21 +50,30 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_factor_kernel(thb_sparse_pl
   if (tid == 0) s_fail = 0;
   __syncthreads();
   for (int lv = 0; lv < p.num_levels; lv++) {
-    // ---- U: updates ----
-    for (int64_t e = p.u_ptr[lv] + tid; e < p.u_ptr[lv + 1]; e += SP_THREADS) {
-      const int64_t tgt = p.u_tgt[e];
-      const int r = p.u_r[e], c = p.u_c[e], ld = p.u_ld[e];
-      double acc = F[tgt + r * ld + c];
-      const int64_t p1 = p.u_p1[e];
-      for (int64_t q = p.u_p0[e]; q < p1; q++) {
-        const int dk = p.up_k[q];
-        const double* a = F + p.up_a[q] + r * dk;
-        const double* bb = F + p.up_b[q] + c * dk;
-        double s = 0.0;
-        for (int k = 0; k < dk; k++) s += a[k] * bb[k];
-        acc -= s;
+    // ---- U: updates.  Work item = one block; its scalars are spread over the threads (u_r/u_c = rows/cols, u_ld = is-diagonal) ----
+    {
+      const int64_t e0 = p.u_ptr[lv], e1 = p.u_ptr[lv + 1];
+      // flatten (item, scalar) with a fixed 64-slot stride per item (blocks are <= 16x16; 6x6 = 36 of 64 slots used... use exact di*dj below)
+      for (int64_t e = e0 + (tid >> 6); e < e1; e += SP_THREADS >> 6) {
+        const int di = p.u_r[e], dj = p.u_c[e];
+        const bool diag = p.u_ld[e] != 0;
+        const int64_t tgt = p.u_tgt[e];
+        const int64_t q0 = p.u_p0[e], q1 = p.u_p1[e];
+        for (int t = tid & 63; t < di * dj; t += 64) {
+          const int r = t / dj, c = t - r * dj;
+          if (diag && c > r) continue;
+          double acc = F[tgt + t];
+          for (int64_t q = q0; q < q1; q++) {
+            const int dk = p.up_k[q];
+            const double* a = F + p.up_a[q] + r * dk;
+            const double* bb = F + p.up_b[q] + c * dk;
+            double s = 0.0;
+            for (int k = 0; k < dk; k++) s += a[k] * bb[k];
+            acc -= s;
+          }
+          F[tgt + t] = acc;
+        }
       }
-      F[tgt + r * ld + c] = acc;
     }
     __syncthreads();
     // ---- F: diagonal blocks ----

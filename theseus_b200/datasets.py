@@ -98,3 +98,39 @@ def build_pose_graph_objective(th, data, device, prior_weight: float = 1e-3, bat
     objective.add(prior)
     objective.to(device)
     return objective, poses
+
+
+def pose_graph_sphere(rings: int, per_ring: int, batch_size: int, translation_noise: float = 0.05, rotation_noise: float = 0.02,
+                      radius: float = 10.0, seed: int = 0, dtype: torch.dtype = torch.float64):
+    """sphere2500-like topology: `rings` x `per_ring` poses on a sphere, odometry chain
+    i -> i+1 plus ring-to-ring edges i -> i+per_ring: E = N-1 + N-per_ring (2500 nodes -> 4949 edges).
+    Measurements = ground-truth relative pose composed with uniform noise (the noise model of generate_synthetic_3D);
+    initial poses = ground truth composed with the same noise."""
+    gen = torch.Generator().manual_seed(seed)
+    N, B = rings * per_ring, batch_size
+
+    def urand(n, scale_t, scale_r):
+        u = 2.0 * torch.rand(n, 6, generator=gen, dtype=dtype) - 1.0
+        return torch.cat([u[:, :3] * scale_t, u[:, 3:] * scale_r], dim=1)
+
+    idx = torch.arange(N)
+    ring, k = idx // per_ring, idx % per_ring
+    phi = (ring.to(dtype) + 0.5) / rings * np.pi           # polar angle
+    theta = k.to(dtype) / per_ring * 2 * np.pi
+    pos = radius * torch.stack([torch.sin(phi) * torch.cos(theta), torch.sin(phi) * torch.sin(theta), torch.cos(phi)], dim=1)
+    # orientation: yaw along the ring direction
+    R = torch.zeros(N, 3, 3, dtype=dtype)
+    c, s = torch.cos(theta), torch.sin(theta)
+    R[:, 0, 0], R[:, 0, 1], R[:, 1, 0], R[:, 1, 1], R[:, 2, 2] = c, -s, s, c, 1.0
+    gt1 = torch.cat([R, pos.unsqueeze(2)], dim=2)                               # [N,3,4]
+    # per-batch-item ground truth = shared shape perturbed a little per item
+    gt = [_compose(gt1[i:i + 1].expand(B, 3, 4), _exp_se3(urand(B, 0.2, 0.05))) for i in range(N)]
+    edges = [(i, i + 1) for i in range(N - 1)] + [(i, i + per_ring) for i in range(N - per_ring)]
+    meas = []
+    for (i, j) in edges:
+        rel = _compose(_inverse(gt[i]), gt[j])
+        meas.append(_compose(rel, _exp_se3(urand(B, translation_noise, rotation_noise))))
+    poses = [_compose(gt[i], _exp_se3(urand(B, translation_noise, rotation_noise))) for i in range(N)]
+    info = torch.tensor([1 / translation_noise] * 3 + [1 / rotation_noise] * 3, dtype=dtype)
+    return dict(poses=torch.stack(poses, 0).contiguous(), gt_poses=torch.stack(gt, 0).contiguous(), edges=edges,
+                meas=torch.stack(meas, 0).contiguous(), info=info)

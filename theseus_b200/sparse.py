@@ -164,9 +164,9 @@ def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering
     cols_by_level = [[] for _ in range(nlev)]
     for j in range(N):
         cols_by_level[int(level[j])].append(j)
-    # stage U: one item per scalar entry of every block of the level's columns
+    # stage U: one item per updated block of the level's columns: (offset, rows, cols, is_diagonal, update-pair range)
     u_ptr = [0]
-    u_tgt, u_r, u_c, u_ld, u_p0, u_p1, u_diag = [], [], [], [], [], [], []
+    u_tgt, u_r, u_c, u_ld, u_p0, u_p1 = [], [], [], [], [], []
     # stage F: one item per column (diag potrf + inverse)
     f_ptr = [0]
     f_off, f_dim, f_w, f_col = [], [], [], []
@@ -186,12 +186,10 @@ def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering
             for i in [j] + list(struct[j]):
                 t = blk_index[(int(i), j)]
                 di = int(dims[i])
-                for r in range(di):
-                    for c in range(dj):
-                        if i == j and c > r:
-                            continue  # lower triangle of the diagonal block only
-                        u_tgt.append(int(blk_off[t])); u_r.append(r); u_c.append(c); u_ld.append(dj)
-                        u_p0.append(int(up_ptr[t])); u_p1.append(int(up_ptr[t + 1])); u_diag.append(1 if i == j else 0)
+                if up_ptr[t + 1] > up_ptr[t]:  # blocks without updates (leaves) need no work item
+                    # one item per BLOCK (the kernel spreads its di*dj scalars over threads): keeps the index stream tiny
+                    u_tgt.append(int(blk_off[t])); u_r.append(di); u_c.append(dj); u_ld.append(1 if i == j else 0)
+                    u_p0.append(int(up_ptr[t])); u_p1.append(int(up_ptr[t + 1]))
                 if i != j:
                     for r in range(di):
                         t_off.append(int(blk_off[t])); t_r.append(r); t_dim.append(dj); t_w.append(int(winv_off[j]))
