@@ -49,7 +49,9 @@ enum thb_cost_kind {
   THB_COST_LOCAL_SE3 = 1,   /* theseus/embodied/misc/local_cost_fn.py:40-61 (Local / Difference) with SE3 */
   THB_COST_BETWEEN_SO3 = 2,
   THB_COST_LOCAL_SO3 = 3,
-  THB_COST_LOCAL_VECTOR = 4 /* Difference on Vector/Point: e = x - target, J = I (geometry/vector.py) */
+  THB_COST_LOCAL_VECTOR = 4, /* Difference on Vector/Point: e = x - target, J = I (geometry/vector.py) */
+  THB_COST_REPROJECTION = 5  /* theseus/embodied/measurements/reprojection.py:54-94: x0 = camera SE3, x1 = Point3,
+                                aux = focal_length [Bf,1], aux2 = image_feature_point [Bi,2], aux3 = calib_k1, aux4 = calib_k2 */
 };
 enum thb_weight_kind {
   THB_WEIGHT_SCALE = 0,   /* theseus/core/cost_weight.py:60-93  (ScaleCostWeight, tensor [Bw,1]) */
@@ -75,6 +77,11 @@ typedef struct thb_cost_group {
   const int32_t* a_stride; /* device [K]   entries per row (cost_function_stride) */
   const int32_t* bp;       /* device [K,2] column offset of each variable's block inside a row (cost_function_block_pointers) */
   const int32_t* row0;     /* device [K]   first row of the cost function in b */
+  /* further auxiliary tensors of schemas that need them (NULL otherwise) + their batch strides, device int32 [K,3] */
+  const void* const* aux2;
+  const void* const* aux3;
+  const void* const* aux4;
+  const int32_t* bstride2;
 } thb_cost_group;
 
 /* Fused residual + analytic Jacobian + weighting for every (cost function, batch item) of a group;

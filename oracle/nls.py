@@ -87,7 +87,31 @@ def cost_weighted_jacobians_error(spec, cost, values, want_jac=True):
     return weight_jacobians_error(cost["weight"], jacs, e)
 
 
+def reprojection_error_jacobians(X, p, f, z, k1, k2, want_jac=True):
+    """theseus/embodied/measurements/reprojection.py:54-94 (+ torchlie se3_impl.py:757-777 for the transform Jacobians).
+    X [...,3,4] camera pose, p [...,3] world point, f/k1/k2 [...,1], z [...,2]."""
+    R, t = X[..., :3], X[..., 3]
+    q = (R @ p[..., None])[..., 0] + t
+    proj = -q[..., :2] / q[..., 2:3]
+    n = (proj * proj).sum(axis=-1, keepdims=True)
+    pf = f * (1.0 + n * (k1 + n * k2))
+    err = proj * pf - z
+    if not want_jac:
+        return None, err
+    J = np.concatenate([R, -R @ lie.hat3(p), R], axis=-1)                       # [...,3,9]
+    dpf = f * (k1 + 2.0 * n * k2)
+    num_dden_den = q[..., :2, None] * (J[..., 2, :] / q[..., 2:3])[..., None, :]
+    proj_jac = (num_dden_den - J[..., 0:2, :]) / q[..., 2:3, None]
+    proj_sqn_jac = 2.0 * proj[..., :, None] * (proj[..., None, :] @ proj_jac)
+    Jp = proj_jac * pf[..., None] + proj_sqn_jac * dpf[..., None]
+    return [Jp[..., :6], Jp[..., 6:]], err
+
+
 def cost_dim(spec, cost):
+    if cost["kind"] == "reproj":
+        return 2
+    if cost.get("group") == "Vector":
+        return spec["vars"][cost["vars"][0]]["dof"]
     return _GROUP[cost["group"]]["dof"]
 
 
@@ -99,11 +123,39 @@ def eval_costs(spec, values, want_jac=True):
     dt = spec["dtype"]
     groups = {}
     for f, c in enumerate(spec["costs"]):
-        groups.setdefault((c["kind"], c["group"], c["weight"][0]), []).append(f)
+        groups.setdefault((c["kind"], c.get("group", "-") + (str(spec["vars"][c["vars"][0]]["dof"]) if c.get("group") == "Vector" else ""),
+                           c["weight"][0]), []).append(f)
     out = [None] * len(spec["costs"])
     for (kind, grp, wkind), idx in groups.items():
+        grp = "Vector" if grp.startswith("Vector") else grp
         cs = [spec["costs"][f] for f in idx]
+        if kind == "reproj":
+            st = lambda key: np.stack([_bcast(np.asarray(c["aux"][key], dtype=dt), B) for c in cs], 0)
+            x0 = np.stack([values[c["vars"][0]] for c in cs], 0)
+            x1 = np.stack([values[c["vars"][1]] for c in cs], 0)
+            jacs, e = reprojection_error_jacobians(x0, x1, st("f"), st("z"), st("k1"), st("k2"), want_jac)
+            w = np.stack([_bcast(np.asarray(c["weight"][1], dtype=dt), B) for c in cs], 0)
+            if wkind == "scale":
+                w = w.reshape(w.shape[0], B, 1)
+            e = e * w
+            if jacs is not None:
+                jacs = [J * w[..., None] for J in jacs]
+            for r, f in enumerate(idx):
+                out[f] = ([J[r] for J in jacs] if jacs is not None else None, e[r])
+            continue
         aux = np.stack([_bcast(np.asarray(c["aux"], dtype=dt), B) for c in cs], 0)          # [K,B,...]
+        if grp == "Vector":  # Difference on Vector/Point: e = x - target, J = I (geometry/vector.py)
+            x0 = np.stack([values[c["vars"][0]] for c in cs], 0)
+            e = x0 - aux
+            w = np.stack([_bcast(np.asarray(c["weight"][1], dtype=dt), B) for c in cs], 0)
+            if wkind == "scale":
+                w = w.reshape(w.shape[0], B, 1)
+            e = e * w
+            d = e.shape[-1]
+            J = np.broadcast_to(np.eye(d, dtype=dt), e.shape[:-1] + (d, d)) * np.broadcast_to(w, e.shape)[..., None]
+            for r, f in enumerate(idx):
+                out[f] = ([J[r]] if want_jac else None, e[r])
+            continue
         w = np.stack([_bcast(np.asarray(c["weight"][1], dtype=dt), B) for c in cs], 0)       # [K,B,dim or 1]
         x0 = np.stack([values[c["vars"][0]] for c in cs], 0)
         if kind == "between":

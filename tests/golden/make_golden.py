@@ -208,6 +208,73 @@ def make_dense_solver(th):
     print("dense_solver_kat.npz")
 
 
+def make_ba(th, name, num_cameras, num_points, B, seed, iters):
+    """Bundle adjustment as examples/bundle_adjustment.py:106-164 (Reprojection + reg priors + known-camera priors), without
+    the Huber wrapper (robust losses are a 'next' row), batch built by re-perturbing the scene per item."""
+    import random
+    import torch
+    import theseus.utils.examples as theg
+    torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
+    ba = theg.BundleAdjustmentDataset.generate_synthetic(num_cameras=num_cameras, num_points=num_points, average_track_length=4,
+                                                        track_locality=0.3, feat_random=1.5, prob_feat_is_outlier=0.0)
+    dtype = torch.float64
+    # batch: item 0 = the dataset, items 1.. = re-perturbed copies (cameras: Camera.perturbed; points: U[-0.2,0.2])
+    cam_pose = [torch.cat([c.pose.tensor] + [gc.perturbed().pose.tensor for _ in range(B - 1)], 0) for c, gc in zip(ba.cameras, ba.gt_cameras)]
+    pts = [torch.cat([p.tensor] + [gp.tensor + (torch.rand(1, 3, dtype=dtype) * 2 - 1) * 0.2 for _ in range(B - 1)], 0)
+           for p, gp in zip(ba.points, ba.gt_points)]
+    cams = [th.SE3(tensor=cam_pose[i], name=f"Cam{i}_pose") for i in range(num_cameras)]
+    points = [th.Point3(tensor=pts[i], name=f"Pt{i}") for i in range(num_points)]
+    objective = th.Objective(dtype=dtype)
+    weight = th.ScaleCostWeight(torch.tensor(1.0, dtype=dtype))
+    obs_ci, obs_pi, feats = [], [], []
+    for o, obs in enumerate(ba.observations):
+        cam = ba.cameras[obs.camera_index]
+        objective.add(th.eb.Reprojection(camera_pose=cams[obs.camera_index], world_point=points[int(obs.point_index)],
+                                         focal_length=cam.focal_length, calib_k1=cam.calib_k1, calib_k2=cam.calib_k2,
+                                         image_feature_point=obs.image_feature_point, weight=weight, name=f"reproj_{o}"))
+        obs_ci.append(obs.camera_index); obs_pi.append(int(obs.point_index)); feats.append(obs.image_feature_point.tensor.numpy())
+    zero_point3 = th.Point3(dtype=dtype, name="zero_point")
+    identity_se3 = th.SE3(dtype=dtype, name="zero_se3")
+    w = np.sqrt(1e-4)
+    damping_weight = th.ScaleCostWeight(w * torch.ones(1, dtype=dtype))
+    reg_order = list(objective.optim_vars.keys())
+    for vname in reg_order:
+        var = objective.optim_vars[vname]
+        objective.add(th.Difference(var, identity_se3 if isinstance(var, th.SE3) else zero_point3, damping_weight, name=f"reg_{vname}"))
+    camera_weight = th.ScaleCostWeight(100 * torch.ones(1, dtype=dtype))
+    known = [0, num_cameras - 1]
+    for i in known:
+        objective.add(th.Difference(cams[i], th.SE3(tensor=ba.gt_cameras[i].pose.tensor.clone(), name=f"Cam{i}_gt_pose"), camera_weight,
+                                    name=f"camera_diff_{i}"))
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=iters, step_size=1.0,
+                                abs_err_tolerance=0, rel_err_tolerance=0)
+    order = [v.name for v in opt.linear_solver.linearization.ordering]
+    sp = th.SparseLinearization(objective)
+    objective.update(); sp.linearize()
+    out = dict(cam_pose0=np.stack([c.numpy() for c in cam_pose], 0), pts0=np.stack([p.numpy() for p in pts], 0),
+               obs_cam=np.array(obs_ci), obs_pt=np.array(obs_pi), feats=np.stack(feats, 0),
+               focal=np.stack([c.focal_length.tensor.numpy() for c in ba.cameras], 0),
+               k1=np.stack([c.calib_k1.tensor.numpy() for c in ba.cameras], 0), k2=np.stack([c.calib_k2.tensor.numpy() for c in ba.cameras], 0),
+               known=np.array(known), known_pose=np.stack([ba.gt_cameras[i].pose.tensor.numpy() for i in known], 0),
+               order=np.array(order), reg_order=np.array(reg_order),
+               A_row_ptr=sp.A_row_ptr.astype(np.int64), A_col_ind=sp.A_col_ind.astype(np.int64),
+               A_val0=sp.A_val.numpy().copy(), b0=sp.b.numpy().copy())
+    tr = dict(delta=[], err=[], lam=[])
+
+    def cb(optimizer, info, delta, it):
+        tr["delta"].append(delta.numpy().copy()); tr["err"].append(info.last_err.numpy().copy())
+        tr["lam"].append(optimizer._damping.numpy().copy())
+    with torch.no_grad():
+        info = opt.optimize(track_err_history=True, end_iter_callback=cb, damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
+    out["err_history"] = info.err_history.numpy()
+    out["final"] = np.concatenate([objective.optim_vars[n].tensor.numpy().reshape(B, -1) for n in order], 1)
+    for k, v in tr.items():
+        out["trace_" + k] = np.stack(v, 0)
+    out["kwargs_json"] = np.array(repr(dict(method="lm", iters=iters, damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "err", out["err_history"][:, 0], "->", out["trace_err"][-1], "n_obs", len(obs_ci))
+
+
 if __name__ == "__main__":
     th, lieF = _import_reference()
     make_lie(th, lieF)
@@ -221,3 +288,4 @@ if __name__ == "__main__":
     make_pgo(th, "pgo64_lm", num_poses=64, B=2, seed=3, iters=10, lm_kwargs=lm, full_trace=False)
     make_pgo(th, "pgo_small_lm_hard", num_poses=8, B=4, seed=4, iters=8, lm_kwargs=lm, loop_closure_ratio=0.5, init_perturb=0.6)
     make_pgo(th, "pgo32_lm_hard", num_poses=32, B=3, seed=5, iters=10, lm_kwargs=lm, full_trace=False, init_perturb=0.5)
+    make_ba(th, "ba_small_lm", num_cameras=6, num_points=40, B=3, seed=7, iters=8)

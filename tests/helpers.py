@@ -66,3 +66,62 @@ def decisive_iterations(err0, trace_err, tol=1e-7):
         prev = trace_err[it]
         k += 1
     return k
+
+
+def ba_spec(g, dtype=np.float64):
+    """Oracle problem description of the bundle-adjustment fixture (tests/golden/ba_small_lm.npz)."""
+    order = [str(x) for x in g["order"]]
+    idx = {n: i for i, n in enumerate(order)}
+    spec = dict(dtype=np.dtype(dtype), vars=[], costs=[])
+    for n in order:
+        if n.startswith("Cam"):
+            spec["vars"].append(dict(kind="SE3", dof=6, value=g["cam_pose0"][int(n[3:].split("_")[0])].astype(dtype)))
+        else:
+            spec["vars"].append(dict(kind="Vector", dof=3, value=g["pts0"][int(n[2:])].astype(dtype)))
+    one = np.ones((1, 1), dtype=dtype)
+    for o in range(g["obs_cam"].shape[0]):
+        c, p = int(g["obs_cam"][o]), int(g["obs_pt"][o])
+        spec["costs"].append(dict(kind="reproj", vars=(idx[f"Cam{c}_pose"], idx[f"Pt{p}"]),
+                                  aux=dict(f=g["focal"][c], z=g["feats"][o], k1=g["k1"][c], k2=g["k2"][c]), weight=("scale", one)))
+    w = np.full((1, 1), np.sqrt(1e-4), dtype=dtype)
+    eye = np.eye(3, 4, dtype=dtype)[None]
+    for n in [str(x) for x in g["reg_order"]]:
+        if n.startswith("Cam"):
+            spec["costs"].append(dict(kind="local", group="SE3", vars=(idx[n],), aux=eye, weight=("scale", w)))
+        else:
+            spec["costs"].append(dict(kind="local", group="Vector", vars=(idx[n],), aux=np.zeros((1, 3), dtype=dtype), weight=("scale", w)))
+    for q, i in enumerate(g["known"]):
+        spec["costs"].append(dict(kind="local", group="SE3", vars=(idx[f"Cam{int(i)}_pose"],), aux=g["known_pose"][q].astype(dtype),
+                                  weight=("scale", np.full((1, 1), 100.0, dtype=dtype))))
+    return spec
+
+
+def ba_objective(th, g, device="cuda"):
+    """The product objective built in the same order as examples/bundle_adjustment.py:106-164."""
+    import torch
+    dtype = torch.float64
+    Nc, Np = g["cam_pose0"].shape[0], g["pts0"].shape[0]
+    cams = [th.SE3(tensor=torch.from_numpy(g["cam_pose0"][i]), name=f"Cam{i}_pose") for i in range(Nc)]
+    pts = [th.Point3(tensor=torch.from_numpy(g["pts0"][i]), name=f"Pt{i}") for i in range(Np)]
+    focal = [th.Vector(tensor=torch.from_numpy(g["focal"][i]), name=f"Cam{i}_focal_length") for i in range(Nc)]
+    k1 = [th.Vector(tensor=torch.from_numpy(g["k1"][i]), name=f"Cam{i}_calib_k1") for i in range(Nc)]
+    k2 = [th.Vector(tensor=torch.from_numpy(g["k2"][i]), name=f"Cam{i}_calib_k2") for i in range(Nc)]
+    objective = th.Objective(dtype=dtype)
+    weight = th.ScaleCostWeight(th.Variable(torch.ones(1, 1, dtype=dtype), name="reproj_weight"))
+    for o in range(g["obs_cam"].shape[0]):
+        c, p = int(g["obs_cam"][o]), int(g["obs_pt"][o])
+        objective.add(th.eb.Reprojection(camera_pose=cams[c], world_point=pts[p], focal_length=focal[c], calib_k1=k1[c], calib_k2=k2[c],
+                                         image_feature_point=th.Point2(tensor=torch.from_numpy(g["feats"][o]), name=f"Feat{o}"),
+                                         weight=weight, name=f"reproj_{o}"))
+    zero_point3 = th.Point3(tensor=torch.zeros(1, 3, dtype=dtype), name="zero_point")
+    identity_se3 = th.SE3(tensor=torch.eye(3, 4, dtype=dtype).view(1, 3, 4), name="zero_se3")
+    damping_weight = th.ScaleCostWeight(th.Variable(torch.full((1, 1), float(np.sqrt(1e-4)), dtype=dtype), name="reg_weight"))
+    for name in list(objective.optim_vars.keys()):
+        var = objective.optim_vars[name]
+        objective.add(th.Difference(var, identity_se3 if isinstance(var, th.SE3) else zero_point3, damping_weight, name=f"reg_{name}"))
+    camera_weight = th.ScaleCostWeight(th.Variable(torch.full((1, 1), 100.0, dtype=dtype), name="camera_weight"))
+    for q, i in enumerate(g["known"]):
+        objective.add(th.Difference(cams[int(i)], th.SE3(tensor=torch.from_numpy(g["known_pose"][q]), name=f"Cam{int(i)}_gt_pose"),
+                                    camera_weight, name=f"camera_diff_{int(i)}"))
+    objective.to(device)
+    return objective, cams, pts

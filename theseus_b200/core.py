@@ -17,10 +17,10 @@ from typing import Dict, List, Optional, Sequence, Union
 
 import torch
 
-from .geometry import LieGroup, Manifold, SE3, SO3, Variable, Vector, as_variable
+from .geometry import LieGroup, Manifold, Point2, Point3, SE3, SO3, Variable, Vector, as_variable
 
 # enum thb_cost_kind / thb_weight_kind (include/thb200.h)
-COST_BETWEEN_SE3, COST_LOCAL_SE3, COST_BETWEEN_SO3, COST_LOCAL_SO3, COST_LOCAL_VECTOR = 0, 1, 2, 3, 4
+COST_BETWEEN_SE3, COST_LOCAL_SE3, COST_BETWEEN_SO3, COST_LOCAL_SO3, COST_LOCAL_VECTOR, COST_REPROJECTION = 0, 1, 2, 3, 4, 5
 WEIGHT_SCALE, WEIGHT_DIAGONAL = 0, 1
 
 
@@ -178,6 +178,32 @@ class Difference(CostFunction):
 
 
 Local = Difference
+
+
+class Reprojection(CostFunction):
+    """theseus/embodied/measurements/reprojection.py:13-105: radial-distortion pinhole reprojection residual (dim 2).
+    optim vars: camera_pose (SE3), world_point (Point3); aux: focal_length, image_feature_point, calib_k1, calib_k2."""
+
+    def __init__(self, camera_pose: SE3, world_point: Point3, image_feature_point: Point2, focal_length: Vector,
+                 calib_k1: Vector = None, calib_k2: Vector = None, weight: Optional[CostWeight] = None, name: Optional[str] = None):
+        if weight is None:
+            weight = ScaleCostWeight(torch.tensor(1.0).to(dtype=camera_pose.dtype))
+        super().__init__(cost_weight=weight, name=name)
+        self.camera_pose, self.world_point = camera_pose, world_point
+        self.focal_length, self.image_feature_point = focal_length, image_feature_point
+        batch_size = camera_pose.shape[0]
+        self.calib_k1 = calib_k1 if calib_k1 is not None else Vector(
+            tensor=torch.zeros((batch_size, 1), dtype=camera_pose.dtype, device=camera_pose.device), name=f"calib_k1__{self.name}")
+        self.calib_k2 = calib_k2 if calib_k2 is not None else Vector(
+            tensor=torch.zeros((batch_size, 1), dtype=camera_pose.dtype, device=camera_pose.device), name=f"calib_k2__{self.name}")
+        self.register_optim_vars(["camera_pose", "world_point"])
+        self.register_aux_vars(["focal_length", "image_feature_point", "calib_k1", "calib_k2"])
+
+    def dim(self) -> int:
+        return 2
+
+    def schema(self):
+        return COST_REPROJECTION, [self.focal_length, self.image_feature_point, self.calib_k1, self.calib_k2]
 
 
 class Objective:

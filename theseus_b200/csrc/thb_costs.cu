@@ -26,6 +26,10 @@ template <typename T> struct GroupDev {
   const int32_t* a_stride;
   const int32_t* bp;
   const int32_t* row0;
+  const T* const* aux2;
+  const T* const* aux3;
+  const T* const* aux4;
+  const int32_t* bstride2;
 };
 
 template <typename T> static GroupDev<T> to_dev(const thb_cost_group* g) {
@@ -43,6 +47,10 @@ template <typename T> static GroupDev<T> to_dev(const thb_cost_group* g) {
   d.a_stride = g->a_stride;
   d.bp = g->bp;
   d.row0 = g->row0;
+  d.aux2 = reinterpret_cast<const T* const*>(g->aux2);
+  d.aux3 = reinterpret_cast<const T* const*>(g->aux3);
+  d.aux4 = reinterpret_cast<const T* const*>(g->aux4);
+  d.bstride2 = g->bstride2;
   return d;
 }
 
@@ -215,6 +223,106 @@ __global__ void __launch_bounds__(128) linearize_kernel(GroupDev<T> g, int64_t B
   T* brow = bvec + b * m + g.row0[k];
 #pragma unroll
   for (int r = 0; r < DIM; r++) brow[r] = -e[r];
+}
+
+// Reprojection (theseus/embodied/measurements/reprojection.py:54-94): q = R p + t, proj = -q_xy/q_z,
+// e = proj * f (1 + n (k1 + n k2)) - z with n = |proj|^2.  Jacobians by the quotient rule on
+// [R, -R hat(p) | R] (torchlie se3_impl.py:764-777), exactly as the reference composes them.
+template <typename T, bool WITH_J>
+__device__ __forceinline__ void reprojection_cost(const GroupDev<T>& g, int k, int64_t b, const T* w, T* e, T* Jc, T* Jp) {
+  T X[12], p[3];
+  load_se3(g.x0[k] + (int64_t)g.bstride[k * 4 + 0] * b, X);
+  load_n<T, 3>(g.x1[k] + (int64_t)g.bstride[k * 4 + 1] * b, p);
+  const T f = (g.aux[k] + (int64_t)g.bstride[k * 4 + 2] * b)[0];
+  const T* z = g.aux2[k] + (int64_t)g.bstride2[k * 3 + 0] * b;
+  const T k1 = (g.aux3[k] + (int64_t)g.bstride2[k * 3 + 1] * b)[0];
+  const T k2 = (g.aux4[k] + (int64_t)g.bstride2[k * 3 + 2] * b)[0];
+  T q[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) q[i] = X[i * 4 + 3] + (X[i * 4 + 0] * p[0] + X[i * 4 + 1] * p[1] + X[i * 4 + 2] * p[2]);
+  const T pr0 = -q[0] / q[2], pr1 = -q[1] / q[2];
+  const T n = pr0 * pr0 + pr1 * pr1;
+  const T pf = f * (T(1) + n * (k1 + n * k2));
+  e[0] = (pr0 * pf - z[0]) * w[0];
+  e[1] = (pr1 * pf - z[1]) * w[1];
+  if (WITH_J) {
+    const T dpf = f * (k1 + T(2) * n * k2);
+    // J (3 x 9) = [R | -R hat(p) | R]
+    T J[3][9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const T r0 = X[i * 4 + 0], r1 = X[i * 4 + 1], r2 = X[i * 4 + 2];
+      J[i][0] = r0; J[i][1] = r1; J[i][2] = r2;
+      // -(R hat(p)): hat(p) = [[0,-p2,p1],[p2,0,-p0],[-p1,p0,0]]
+      J[i][3] = -(r1 * p[2] - r2 * p[1]);
+      J[i][4] = -(-r0 * p[2] + r2 * p[0]);
+      J[i][5] = -(r0 * p[1] - r1 * p[0]);
+      J[i][6] = r0; J[i][7] = r1; J[i][8] = r2;
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+      const T jz = J[2][c] / q[2];
+      const T pj0 = (q[0] * jz - J[0][c]) / q[2];   // (N D'/D - N') / D
+      const T pj1 = (q[1] * jz - J[1][c]) / q[2];
+      const T nj = T(2) * (pr0 * pj0 + pr1 * pj1);
+      const T o0 = (pj0 * pf + (T(2) * pr0 * (pr0 * pj0 + pr1 * pj1)) * dpf) * w[0];
+      const T o1 = (pj1 * pf + (T(2) * pr1 * (pr0 * pj0 + pr1 * pj1)) * dpf) * w[1];
+      (void)nj;
+      if (c < 6) { Jc[0 * 6 + c] = o0; Jc[1 * 6 + c] = o1; }
+      else { Jp[0 * 3 + (c - 6)] = o0; Jp[1 * 3 + (c - 6)] = o1; }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) linearize_reprojection_kernel(GroupDev<T> g, int64_t B, T* __restrict__ A_val, int64_t nnz,
+                                                                     T* __restrict__ bvec, int64_t m) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)g.K * B) return;
+  const int k = (int)(t / B);
+  const int64_t b = t - (int64_t)k * B;
+  T w[2], e[2], Jc[12], Jp[6];
+  const bool masked = load_weight<T, 2>(g, k, b, w);
+  if (masked) {
+    e[0] = e[1] = T(0);
+#pragma unroll
+    for (int i = 0; i < 12; i++) Jc[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < 6; i++) Jp[i] = T(0);
+  } else {
+    reprojection_cost<T, true>(g, k, b, w, e, Jc, Jp);
+  }
+  T* Arow = A_val + b * nnz + g.a_off[k];
+  const int stride = g.a_stride[k];
+  const int bp0 = g.bp[k * 2 + 0], bp1 = g.bp[k * 2 + 1];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) Arow[r * stride + bp0 + c] = Jc[r * 6 + c];
+#pragma unroll
+    for (int c = 0; c < 3; c++) Arow[r * stride + bp1 + c] = Jp[r * 3 + c];
+  }
+  T* brow = bvec + b * m + g.row0[k];
+  brow[0] = -e[0];
+  brow[1] = -e[1];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) error_reprojection_kernel(GroupDev<T> g, int64_t B, T* __restrict__ partial) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nchunks = (g.K + kErrCostsPerThread - 1) / kErrCostsPerThread;
+  if (t >= (int64_t)nchunks * B) return;
+  const int c = (int)(t / B);
+  const int64_t b = t - (int64_t)c * B;
+  T acc = T(0);
+  const int k1 = min(g.K, (c + 1) * kErrCostsPerThread);
+  for (int k = c * kErrCostsPerThread; k < k1; k++) {
+    T w[2], e[2];
+    if (load_weight<T, 2>(g, k, b, w)) continue;
+    reprojection_cost<T, false>(g, k, b, w, e, nullptr, nullptr);
+    acc += e[0] * e[0] + e[1] * e[1];
+  }
+  partial[(int64_t)c * B + b] = acc * T(0.5);
 }
 
 // Difference on Vector/Point: e = (x - target) * w ; J = I * w   (geometry/vector.py local/jacobians)
@@ -483,6 +591,10 @@ static int linearize_group(const thb_cost_group* g, int64_t B, T* A_val, int64_t
     case THB_COST_BETWEEN_SO3: linearize_kernel<T, THB_COST_BETWEEN_SO3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
     case THB_COST_LOCAL_SO3: linearize_kernel<T, THB_COST_LOCAL_SO3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
     case THB_COST_LOCAL_VECTOR: linearize_vector_kernel<T><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
+    case THB_COST_REPROJECTION:
+      if (g->aux2 == nullptr || g->aux3 == nullptr || g->aux4 == nullptr || g->bstride2 == nullptr) return THB_ERR_BAD_ARG;
+      linearize_reprojection_kernel<T><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m);
+      break;
     default: return THB_ERR_UNSUPPORTED;
   }
   THB_CHECK_LAUNCH();
@@ -502,6 +614,10 @@ template <typename T> static int error_group(const thb_cost_group* g, int64_t B,
     case THB_COST_BETWEEN_SO3: error_kernel<T, THB_COST_BETWEEN_SO3><<<grid, 128, 0, cs>>>(d, B, partial); break;
     case THB_COST_LOCAL_SO3: error_kernel<T, THB_COST_LOCAL_SO3><<<grid, 128, 0, cs>>>(d, B, partial); break;
     case THB_COST_LOCAL_VECTOR: error_vector_kernel<T><<<grid, 128, 0, cs>>>(d, B, partial); break;
+    case THB_COST_REPROJECTION:
+      if (g->aux2 == nullptr || g->aux3 == nullptr || g->aux4 == nullptr || g->bstride2 == nullptr) return THB_ERR_BAD_ARG;
+      error_reprojection_kernel<T><<<grid, 128, 0, cs>>>(d, B, partial);
+      break;
     default: return THB_ERR_UNSUPPORTED;
   }
   THB_CHECK_LAUNCH();

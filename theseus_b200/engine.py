@@ -67,7 +67,7 @@ class Engine:
         self._aux_of = []
         for f, cf in enumerate(costs):
             kind, aux = cf.schema()
-            self._aux_of.append(aux)
+            self._aux_of.append(list(aux) if isinstance(aux, (list, tuple)) else [aux])
             key = (kind, cf.weight.WEIGHT_KIND, cf.dim())
             groups.setdefault(key, []).append(f)
         self.groups: List[_Group] = []
@@ -112,15 +112,19 @@ class Engine:
             return
         self._B = B
         sizes = [v.numel() for v in self.ordering]
-        offs = np.concatenate([[0], np.cumsum([B * s for s in sizes])]).astype(np.int64)
+        # every view starts on a 32-byte boundary (the kernels use 16-byte vector loads on SE3 elements; Point3 views
+        # of odd length would otherwise push the following variable off alignment)
+        lens = [B * s for s in sizes]
+        padded = [(n + 3) // 4 * 4 for n in lens]
+        offs = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
         total = int(offs[-1])
         self._pool_cur = torch.empty(total, dtype=self.dtype, device=self.device)
         self._pool_tmp = torch.empty(total, dtype=self.dtype, device=self.device)
         self.cur_views, self.tmp_views = [], []
         for i, v in enumerate(self.ordering):
             shp = (B,) + tuple(v.tensor.shape[1:])
-            self.cur_views.append(self._pool_cur[offs[i]:offs[i + 1]].view(shp))
-            self.tmp_views.append(self._pool_tmp[offs[i]:offs[i + 1]].view(shp))
+            self.cur_views.append(self._pool_cur[offs[i]:offs[i] + lens[i]].view(shp))
+            self.tmp_views.append(self._pool_tmp[offs[i]:offs[i] + lens[i]].view(shp))
         self._bufs = {}
         self._vt = None
         self._bind_stamp = {"cur": -1, "tmp": -1}
@@ -162,8 +166,8 @@ class Engine:
             t = v.tensor
             if t.device != self.device:
                 raise ValueError(f"variable {v.name} is on {t.device}, objective is on {self.device}")
-            if not t.is_contiguous():
-                t = t.contiguous()
+            if not t.is_contiguous() or t.data_ptr() % 16 != 0:  # kernels use 16-byte vector loads
+                t = t.clone(memory_format=torch.contiguous_format)
                 v.tensor = t
             return t
 
@@ -171,8 +175,8 @@ class Engine:
             t = v.tensor
             if t.device != self.device or t.dtype != self.dtype:
                 raise ValueError(f"variable {v.name} is on ({t.device},{t.dtype}), objective expects ({self.device},{self.dtype})")
-            if not t.is_contiguous():
-                t = t.contiguous()
+            if not t.is_contiguous() or t.data_ptr() % 16 != 0:
+                t = t.clone(memory_format=torch.contiguous_format)
                 v.tensor = t
             return t
 
@@ -185,23 +189,34 @@ class Engine:
 
         for g in self.groups:
             x0, x1, aux, w = [], [], [], []
+            extra = [[], [], []]
+            n_extra = len(self._aux_of[g.cost_indices[0]]) - 1
             bs = np.zeros((g.K, 4), dtype=np.int32)
+            bs2 = np.zeros((g.K, 3), dtype=np.int32)
             for r, f in enumerate(g.cost_indices):
                 cf = self.costs[f]
                 ov = cf.optim_vars
                 t0 = optim_tensor(ov[0])
                 t1 = optim_tensor(ov[1]) if len(ov) > 1 else t0
-                ta = aux_tensor(self._aux_of[f])
+                auxs = [aux_tensor(a) for a in self._aux_of[f]]
                 tw = aux_tensor(cf.weight.weight_tensor())
-                x0.append(t0); x1.append(t1); aux.append(ta); w.append(tw)
-                bs[r] = (bstride(t0), bstride(t1), bstride(ta), bstride(tw))
+                x0.append(t0); x1.append(t1); aux.append(auxs[0]); w.append(tw)
+                bs[r] = (bstride(t0), bstride(t1), bstride(auxs[0]), bstride(tw))
+                for q in range(n_extra):
+                    extra[q].append(auxs[1 + q])
+                    bs2[r, q] = bstride(auxs[1 + q])
             keep = dict(x0=self._ptr_array(x0), x1=self._ptr_array(x1), aux=self._ptr_array(aux), w=self._ptr_array(w),
-                        bstride=_dev(bs, self.device), tensors=(x0, x1, aux, w))
+                        bstride=_dev(bs, self.device), tensors=(x0, x1, aux, w, extra))
+            ex = [self._ptr_array(extra[q]) if n_extra > q else None for q in range(3)]
+            keep["extra"] = ex
+            keep["bstride2"] = _dev(bs2, self.device)
             st = _lib.CostGroup(
                 kind=g.kind, weight_kind=g.weight_kind, K=g.K, dim=g.dim,
                 x0=keep["x0"].data_ptr(), x1=keep["x1"].data_ptr(), aux=keep["aux"].data_ptr(), w=keep["w"].data_ptr(),
                 bstride=keep["bstride"].data_ptr(), a_off=g.static["a_off"].data_ptr(),
-                a_stride=g.static["a_stride"].data_ptr(), bp=g.static["bp"].data_ptr(), row0=g.static["row0"].data_ptr())
+                a_stride=g.static["a_stride"].data_ptr(), bp=g.static["bp"].data_ptr(), row0=g.static["row0"].data_ptr(),
+                aux2=ex[0].data_ptr() if ex[0] is not None else None, aux3=ex[1].data_ptr() if ex[1] is not None else None,
+                aux4=ex[2].data_ptr() if ex[2] is not None else None, bstride2=keep["bstride2"].data_ptr())
             g.bound[which] = (st, keep)
         # NOTE: _bind may itself rebind non-contiguous tensors (bumping the counter); read it afterwards.
         self._bind_stamp[which] = Variable._global_updates
