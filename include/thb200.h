@@ -166,6 +166,8 @@ typedef struct thb_gram_plan {
  * thb_fill_zero); Atb[B,n]; diag[B,n] (optional, may be NULL) receives diag(AtA). */
 int thb_gram_f64(const thb_gram_plan* p, int64_t B, const double* A_val, int64_t nnz, const double* b, int64_t m,
                  double* out, int64_t out_bstride, double* Atb, double* diag, thb_stream_t stream);
+int thb_gram_f32(const thb_gram_plan* p, int64_t B, const float* A_val, int64_t nnz, const float* b, int64_t m,
+                 float* out, int64_t out_bstride, float* Atb, float* diag, thb_stream_t stream);
 int thb_fill_zero(void* ptr, int64_t bytes, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -247,6 +249,10 @@ int thb_lm_control_f64(const double* delta, const double* Atb, const double* dia
                        const double* err_prev, const double* err_new, double* lam, int32_t ellipsoidal,
                        double damping_accept, double down_ratio, double up_ratio, uint8_t* reject,
                        double* err_out, int32_t* stats, thb_stream_t stream);
+
+int thb_lm_control_f32(const float* delta, const float* Atb, const float* diag, int64_t B, int64_t n, float step,
+                       const float* err_prev, const float* err_new, float* lam, int32_t ellipsoidal, float damping_accept,
+                       float down_ratio, float up_ratio, uint8_t* reject, float* err_out, int32_t* stats, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched CSR helpers (same semantics as theseus/extlib/mat_mult.cu:359-400, int64 indices):

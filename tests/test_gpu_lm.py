@@ -82,3 +82,17 @@ def test_convergence_status_and_early_exit():
     assert (info.converged_iter > 0).all() and (info.converged_iter < 30).all()
     oracle = nls.optimize(pgo_spec(g), method="lm", max_iterations=30, damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
     np.testing.assert_allclose(info.last_err.cpu().numpy(), oracle["err_history"][:, -1], rtol=1e-7)
+
+
+def test_fp32_objective_end_to_end():
+    """The reference supports fp32 objectives (constants.py:17-22).  Same problem in fp32: kernels run their float
+    instantiations with the fp32 eps table; the dense solve is served by the fp64 factorisation and cast back."""
+    g = load("pgo_small_lm_hard")
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g, dtype=torch.float32)
+    opt = th.LevenbergMarquardt(objective, max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0)
+    with torch.no_grad():
+        info = opt.optimize(track_err_history=True, **kw)
+    assert info.last_err.dtype == torch.float32
+    np.testing.assert_allclose(info.last_err.cpu().numpy(), g["trace_err"][-1], rtol=2e-3)
+    np.testing.assert_allclose(info.err_history[:, 0].numpy(), g["err_history"][:, 0], rtol=1e-3)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "thb_commit_f64": (c_i32, [_PV, c_i64, c_vp, c_vp]),
     "thb_commit_f32": (c_i32, [_PV, c_i64, c_vp, c_vp]),
     "thb_gram_f64": (c_i32, [_PP, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "thb_gram_f32": (c_i32, [_PP, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "thb_fill_zero": (c_i32, [c_vp, c_i64, c_vp]),
     "thb_potrf_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "thb_potrf_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
@@ -71,6 +72,8 @@ SIGNATURES = {
     "thb_sparse_factor_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_solve_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_lm_control_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64,
+                                   c_vp, c_vp, c_vp, c_vp]),
+    "thb_lm_control_f32": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_f32,
                                    c_vp, c_vp, c_vp, c_vp]),
     "thb_mat_vec_f64": (c_i32, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "thb_tmat_vec_f64": (c_i32, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

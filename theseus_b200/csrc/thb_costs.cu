@@ -511,7 +511,7 @@ __global__ void lm_control_kernel(const T* __restrict__ delta, const T* __restri
     const T rho = (err_prev[b] - err_new[b]) / den;
     const bool rej = rho <= accept;  // NaN compares false -> accepted, like torch's `rho <= damping_accept`
     T nl = rej ? (l * up) : (l / down);
-    nl = fmin(fmax(nl, T(1e-7)), T(1e7));
+    nl = (nl < T(1e-7)) ? T(1e-7) : ((nl > T(1e7)) ? T(1e7) : nl);
     lam[b] = nl;
     reject[b] = rej ? 1 : 0;
     err_out[b] = rej ? err_prev[b] : err_new[b];
@@ -643,6 +643,21 @@ template <typename T> static int commit_impl(const thb_var_table* vt, int64_t B,
 }  // namespace thb
 
 // ================================================================================================
+template <typename T>
+static int lm_control_impl(const T* delta, const T* Atb, const T* diag, int64_t B, int64_t n, T step, const T* err_prev, const T* err_new,
+                           T* lam, int32_t ellipsoidal, T damping_accept, T down_ratio, T up_ratio, uint8_t* reject, T* err_out,
+                           int32_t* stats, thb_stream_t s) {
+  if (B <= 0) return THB_OK;
+  if (ellipsoidal && diag == nullptr) return THB_ERR_BAD_ARG;
+  THB_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, thb_cs(s)));
+  const int threads = 128;
+  const unsigned grid = thb::grid_for(B * 32, threads);
+  thb::lm_control_kernel<T><<<grid, threads, 0, thb_cs(s)>>>(delta, Atb, diag, B, n, step, err_prev, err_new, lam, ellipsoidal,
+                                                              damping_accept, down_ratio, up_ratio, reject, err_out, stats);
+  THB_CHECK_LAUNCH();
+  return THB_OK;
+}
+
 extern "C" {
 
 int64_t thb_launch_counter_ = 0;
@@ -689,15 +704,14 @@ int thb_commit_f32(const thb_var_table* vt, int64_t B, const uint8_t* keep_old, 
 int thb_lm_control_f64(const double* delta, const double* Atb, const double* diag, int64_t B, int64_t n, double step,
                        const double* err_prev, const double* err_new, double* lam, int32_t ellipsoidal, double damping_accept,
                        double down_ratio, double up_ratio, uint8_t* reject, double* err_out, int32_t* stats, thb_stream_t s) {
-  if (B <= 0) return THB_OK;
-  if (ellipsoidal && diag == nullptr) return THB_ERR_BAD_ARG;
-  THB_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, thb_cs(s)));
-  const int threads = 128;
-  const unsigned grid = thb::grid_for(B * 32, threads);
-  thb::lm_control_kernel<double><<<grid, threads, 0, thb_cs(s)>>>(delta, Atb, diag, B, n, step, err_prev, err_new, lam, ellipsoidal,
-                                                                   damping_accept, down_ratio, up_ratio, reject, err_out, stats);
-  THB_CHECK_LAUNCH();
-  return THB_OK;
+  return lm_control_impl<double>(delta, Atb, diag, B, n, step, err_prev, err_new, lam, ellipsoidal, damping_accept, down_ratio, up_ratio,
+                                 reject, err_out, stats, s);
+}
+int thb_lm_control_f32(const float* delta, const float* Atb, const float* diag, int64_t B, int64_t n, float step, const float* err_prev,
+                       const float* err_new, float* lam, int32_t ellipsoidal, float damping_accept, float down_ratio, float up_ratio,
+                       uint8_t* reject, float* err_out, int32_t* stats, thb_stream_t s) {
+  return lm_control_impl<float>(delta, Atb, diag, B, n, step, err_prev, err_new, lam, ellipsoidal, damping_accept, down_ratio, up_ratio,
+                                reject, err_out, stats, s);
 }
 
 int thb_fill_zero(void* ptr, int64_t bytes, thb_stream_t s) {

@@ -110,24 +110,34 @@ __global__ void tmat_vec_kernel(int64_t B, int64_t num_rows, int64_t num_cols, c
 
 }  // namespace thb
 
-extern "C" {
-
-int thb_gram_f64(const thb_gram_plan* p, int64_t B, const double* A_val, int64_t nnz, const double* b, int64_t m, double* out,
-                 int64_t out_bstride, double* Atb, double* diag, thb_stream_t s) {
+template <typename T>
+static int gram_impl(const thb_gram_plan* p, int64_t B, const T* A_val, int64_t nnz, const T* b, int64_t m, T* out, int64_t out_bstride,
+                     T* Atb, T* diag, thb_stream_t s) {
   if (p == nullptr || B < 0) return THB_ERR_BAD_ARG;
   if (B == 0) return THB_OK;
   cudaStream_t cs = thb_cs(s);
   if (out != nullptr && p->num_entries > 0) {
     const int64_t total = p->num_entries * B;
-    thb::gram_kernel<double><<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(*p, B, A_val, nnz, out, out_bstride, nullptr);
+    thb::gram_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(*p, B, A_val, nnz, out, out_bstride, nullptr);
     THB_CHECK_LAUNCH();
   }
   if (Atb != nullptr && p->n > 0) {
     const int64_t total = p->n * B;
-    thb::atb_kernel<double><<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(*p, B, A_val, nnz, b, m, Atb, diag);
+    thb::atb_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(*p, B, A_val, nnz, b, m, Atb, diag);
     THB_CHECK_LAUNCH();
   }
   return THB_OK;
+}
+
+extern "C" {
+
+int thb_gram_f64(const thb_gram_plan* p, int64_t B, const double* A_val, int64_t nnz, const double* b, int64_t m, double* out,
+                 int64_t out_bstride, double* Atb, double* diag, thb_stream_t s) {
+  return gram_impl<double>(p, B, A_val, nnz, b, m, out, out_bstride, Atb, diag, s);
+}
+int thb_gram_f32(const thb_gram_plan* p, int64_t B, const float* A_val, int64_t nnz, const float* b, int64_t m, float* out,
+                 int64_t out_bstride, float* Atb, float* diag, thb_stream_t s) {
+  return gram_impl<float>(p, B, A_val, nnz, b, m, out, out_bstride, Atb, diag, s);
 }
 
 int thb_mat_vec_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* row_ptr, const int64_t* col_ind,

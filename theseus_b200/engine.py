@@ -303,19 +303,17 @@ class Engine:
 
     def gram_dense(self, A_val, b, AtA, Atb, diag):
         """AtA [B,n,n] (zero-filled then block scatter), Atb [B,n], diag(AtA) [B,n]."""
-        if self.sfx != "f64":
-            raise NotImplementedError("dense Gram assembly is fp64-only in libthb200 r1")
         B = self.batch_size
         s = _lib.stream_ptr()
         plan = self.gram_plan_dense()
         _lib.check(self.lib.thb_fill_zero(_lib.ptr(AtA), AtA.numel() * AtA.element_size(), s), "fill_zero")
-        _lib.check(self.lib.thb_gram_f64(C.byref(plan), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, _lib.ptr(AtA),
-                                         self.n * self.n, _lib.ptr(Atb), _lib.ptr(diag), s), "gram")
+        _lib.check(getattr(self.lib, f"thb_gram_{self.sfx}")(C.byref(plan), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, _lib.ptr(AtA),
+                                                               self.n * self.n, _lib.ptr(Atb), _lib.ptr(diag), s), "gram")
 
     def atb(self, A_val, b, Atb, diag=None):
         plan = self.gram_plan_dense()
-        _lib.check(self.lib.thb_gram_f64(C.byref(plan), self.batch_size, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, None,
-                                         0, _lib.ptr(Atb), _lib.ptr(diag), _lib.stream_ptr()), "atb")
+        _lib.check(getattr(self.lib, f"thb_gram_{self.sfx}")(C.byref(plan), self.batch_size, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m,
+                                                               None, 0, _lib.ptr(Atb), _lib.ptr(diag), _lib.stream_ptr()), "atb")
 
     def retract_into(self, delta: torch.Tensor, out_vars, step: float, ignore_mask: Optional[torch.Tensor]):
         """tmp_i <- X_i * exp(step * delta_i), masked (core/objective.py:873-914)."""

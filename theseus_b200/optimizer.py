@@ -576,8 +576,7 @@ class LevenbergMarquardt(NonlinearLeastSquares):
         lib = _lib.load()
         B, n = delta.shape
         dev = delta.device
-        if delta.dtype != torch.float64:
-            raise NotImplementedError("LM control kernel is fp64-only in libthb200 r1")
+        sfx = "f64" if delta.dtype == torch.float64 else "f32"
         Atb = lin.Atb.reshape(B, n)
         diag = lin.diagonal_scaling(torch.ones(B, n, dtype=delta.dtype, device=dev)) if ellipsoidal_damping else None
         reject = torch.empty(B, dtype=torch.uint8, device=dev)
@@ -585,7 +584,7 @@ class LevenbergMarquardt(NonlinearLeastSquares):
         stats = torch.empty(4, dtype=torch.int32, device=dev)
         if self._stats_host is None:
             self._stats_host = torch.empty(4, dtype=torch.int32).pin_memory()
-        _lib.check(lib.thb_lm_control_f64(
+        _lib.check(getattr(lib, f"thb_lm_control_{sfx}")(
             _lib.ptr(delta), _lib.ptr(Atb), _lib.ptr(diag), B, n, float(self.params.step_size), _lib.ptr(previous_err), _lib.ptr(err),
             _lib.ptr(self._damping), 1 if ellipsoidal_damping else 0, float(damping_accept), float(down_damping_ratio),
             float(up_damping_ratio), _lib.ptr(reject), _lib.ptr(err_out), _lib.ptr(stats), _lib.stream_ptr()), "lm_control")
