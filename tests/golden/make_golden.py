@@ -275,6 +275,35 @@ def make_ba(th, name, num_cameras, num_points, B, seed, iters):
     print(name, "err", out["err_history"][:, 0], "->", out["trace_err"][-1], "n_obs", len(obs_ci))
 
 
+def make_simple_example(th):
+    """examples/simple_example.py:17-45 (config C1): y = v exp(x), one AutoDiff cost of dim 20, GaussNewton 10 iterations,
+    default dtype float32, batch 1; forward pass only."""
+    import torch
+    torch.manual_seed(0)
+    x_true = torch.linspace(-1, 1, 20).view(1, -1)
+    y_true = 0.5 * torch.exp(x_true)
+    x = th.Variable(torch.randn_like(x_true), name="x")
+    y = th.Variable(y_true, name="y")
+    v = th.Vector(1, name="v")
+
+    def error_fn(optim_vars, aux_vars):
+        xx, yy = aux_vars
+        return yy.tensor - optim_vars[0].tensor * torch.exp(xx.tensor)
+
+    objective = th.Objective()
+    objective.add(th.AutoDiffCostFunction([v], error_fn, 20, aux_vars=[x, y], cost_weight=th.ScaleCostWeight(1.0)))
+    opt = th.GaussNewton(objective, max_iterations=10)
+    layer = th.TheseusLayer(opt)
+    phi = x_true + 0.1 * torch.ones_like(x_true)
+    with torch.no_grad():
+        sol, info = layer.forward(input_tensors={"x": phi.clone(), "v": torch.ones(1, 1)},
+                                  optimizer_kwargs=dict(track_err_history=True, track_state_history=True))
+    np.savez_compressed(os.path.join(HERE, "simple_example.npz"), x=phi.numpy(), y=y_true.numpy(), v_final=sol["v"].numpy(),
+                        err_history=info.err_history.numpy(), v_history=info.state_history["v"].numpy(),
+                        converged_iter=info.converged_iter.numpy(), status=np.array([s.value for s in info.status]))
+    print("simple_example v ->", sol["v"].numpy().ravel(), "converged_iter", info.converged_iter.numpy(), info.err_history.numpy()[0, :4])
+
+
 if __name__ == "__main__":
     th, lieF = _import_reference()
     make_lie(th, lieF)
@@ -289,3 +318,4 @@ if __name__ == "__main__":
     make_pgo(th, "pgo_small_lm_hard", num_poses=8, B=4, seed=4, iters=8, lm_kwargs=lm, loop_closure_ratio=0.5, init_perturb=0.6)
     make_pgo(th, "pgo32_lm_hard", num_poses=32, B=3, seed=5, iters=10, lm_kwargs=lm, full_trace=False, init_perturb=0.5)
     make_ba(th, "ba_small_lm", num_cameras=6, num_points=40, B=3, seed=7, iters=8)
+    make_simple_example(th)

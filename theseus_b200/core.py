@@ -206,6 +206,79 @@ class Reprojection(CostFunction):
         return COST_REPROJECTION, [self.focal_length, self.image_feature_point, self.calib_k1, self.calib_k2]
 
 
+class AutoDiffCostFunction(CostFunction):
+    """theseus/core/cost_function.py:203-420: user-defined error function, Jacobians by vmap(jacrev(err_fn)) -- kept as the
+    reference's torch.func path; the results are scattered straight into the batched-CSR Jacobian.
+    `err_fn(optim_vars, aux_vars) -> [B, dim]` receives tuples of Variable-like objects exposing `.tensor`.
+    Optimisation variables must be Euclidean (Vector / Point): projecting autograd Jacobians onto Lie tangent spaces
+    (geometry/*.project) is not built in round 1."""
+
+    def __init__(self, optim_vars: Sequence[Manifold], err_fn, dim: int, cost_weight: Optional[CostWeight] = None,
+                 aux_vars: Optional[Sequence[Variable]] = None, name: Optional[str] = None, **autograd_kwargs):
+        if cost_weight is None:
+            cost_weight = ScaleCostWeight(1.0)
+        super().__init__(cost_weight, name=name)
+        aux_vars = list(aux_vars or [])
+        if len(optim_vars) < 1:
+            raise ValueError("AutodiffCostFunction must receive at least one optimization variable.")
+        for v in optim_vars:
+            if not isinstance(v, Vector):
+                raise NotImplementedError("AutoDiffCostFunction: only Vector/Point optimisation variables are supported in theseus_b200 r1")
+        self._optim = list(optim_vars)
+        self._aux = aux_vars
+        for i, v in enumerate(self._optim):
+            setattr(self, f"_optim_var_{i}", v)
+            self._optim_vars_attr_names.append(f"_optim_var_{i}")
+        for i, v in enumerate(self._aux):
+            setattr(self, f"_aux_var_{i}", v)
+            self._aux_vars_attr_names.append(f"_aux_var_{i}")
+        self._err_fn = err_fn
+        self._dim = dim
+
+    def dim(self) -> int:
+        return self._dim
+
+    class _T:  # minimal Variable-like holder handed to the user's err_fn
+        def __init__(self, tensor):
+            self.tensor = tensor
+
+        def __getitem__(self, item):
+            return self.tensor[item]
+
+    def _weight(self, err: torch.Tensor, jacs):
+        w = self.weight.weight_tensor().tensor
+        w = w.view(-1, 1) if self.weight.WEIGHT_KIND == WEIGHT_SCALE else w
+        err = err * w
+        if jacs is not None:
+            jacs = [J * (w.unsqueeze(2) if w.ndim == 2 else w) for J in jacs]
+        return jacs, err
+
+    def generic_error(self, optim_tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Weighted error [B, dim] at the given optimisation-variable tensors."""
+        err = self._err_fn(optim_vars=tuple(self._T(t) for t in optim_tensors), aux_vars=tuple(self._T(v.tensor) for v in self._aux))
+        return self._weight(err, None)[1]
+
+    def generic_jacobians_error(self, optim_tensors: Sequence[torch.Tensor]):
+        """(weighted Jacobians [B,dim,dof_i], weighted error [B,dim]) -- cost_function.py:318-393 (vmap over jacrev)."""
+        from torch.func import jacrev, vmap
+        aux = tuple(v.tensor for v in self._aux)
+        B = max([t.shape[0] for t in optim_tensors] + [t.shape[0] for t in aux])
+        ex = lambda t: t if t.shape[0] == B else t.expand((B,) + tuple(t.shape[1:]))
+        opt_t, aux_t = tuple(ex(t) for t in optim_tensors), tuple(ex(t) for t in aux)
+
+        def one(o, a):
+            return self._err_fn(optim_vars=tuple(self._T(x.unsqueeze(0)) for x in o), aux_vars=tuple(self._T(x.unsqueeze(0)) for x in a))[0]
+
+        with torch.enable_grad():
+            jacs = vmap(jacrev(one, argnums=0))(opt_t, aux_t)
+            err = self._err_fn(optim_vars=tuple(self._T(t) for t in opt_t), aux_vars=tuple(self._T(t) for t in aux_t))
+        jacs = [j.detach() for j in jacs]  # Vector.project(., is_sparse=True) is the identity (geometry/vector.py:199-203)
+        return self._weight(err.detach(), jacs)
+
+    def schema(self):
+        return None, []
+
+
 class Objective:
     """theseus/core/objective.py:42-960 (the subset the NLS loop uses)."""
 

@@ -65,9 +65,13 @@ class Engine:
         # ---- schema groups ----
         groups = {}
         self._aux_of = []
+        self.generic = []  # cost functions without a CUDA schema (AutoDiffCostFunction): torch.func Jacobians, scattered into the CSR
         for f, cf in enumerate(costs):
             kind, aux = cf.schema()
             self._aux_of.append(list(aux) if isinstance(aux, (list, tuple)) else [aux])
+            if kind is None:
+                self.generic.append(f)
+                continue
             key = (kind, cf.weight.WEIGHT_KIND, cf.dim())
             groups.setdefault(key, []).append(f)
         self.groups: List[_Group] = []
@@ -268,7 +272,21 @@ class Engine:
         s = _lib.stream_ptr()
         for g in self.groups:
             _lib.check(fn(C.byref(g.bound["cur"][0]), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, s), "linearize_group")
+        S = self.structure
+        for f in self.generic:
+            cf = self.costs[f]
+            jacs, err = cf.generic_jacobians_error([self._expand(v.tensor) for v in cf.optim_vars])
+            d, st, off = int(S.cost_dims[f]), int(S.stride[f]), int(S.row_block_starts[f])
+            blk = A_val[:, off:off + d * st].view(B, d, st)
+            for kslot, J in enumerate(jacs):
+                p0 = int(S.block_pointers[f][kslot])
+                blk[:, :, p0:p0 + J.shape[2]] = J
+            b[:, int(S.cost_row0[f]):int(S.cost_row0[f]) + d] = -err
         return A_val, b
+
+    def _expand(self, t):
+        B = self.batch_size
+        return t if t.shape[0] == B else t.expand((B,) + tuple(t.shape[1:]))
 
     def error_metric(self, which: str = "cur", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """0.5 * sum((w e)^2) per batch item (core/objective.py:615-641), deterministic two-stage reduction."""
@@ -284,6 +302,11 @@ class Engine:
             _lib.check(fn(C.byref(g.bound[which][0]), B, _lib.ptr(partial[row:]), s), "error_group")
             row += nc
         _lib.check(getattr(self.lib, f"thb_error_reduce_{self.sfx}")(_lib.ptr(partial), self.total_chunks, B, _lib.ptr(out), s), "error_reduce")
+        for f in self.generic:
+            cf = self.costs[f]
+            ts = [self.tmp_views[self.var_index[v.name]] if which == "tmp" else self._expand(v.tensor) for v in cf.optim_vars]
+            e = cf.generic_error(ts)
+            out += (e * e).sum(dim=1) * 0.5
         return out
 
     def gram_plan_dense(self):
