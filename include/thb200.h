@@ -50,6 +50,8 @@ enum thb_cost_kind {
   THB_COST_BETWEEN_SO3 = 2,
   THB_COST_LOCAL_SO3 = 3,
   THB_COST_LOCAL_VECTOR = 4, /* Difference on Vector/Point: e = x - target, J = I (geometry/vector.py) */
+  THB_COST_BETWEEN_SE2 = 6,  /* Between with SE2 [B,4] = [x,y,cos,sin] (theseus/geometry/se2.py) */
+  THB_COST_LOCAL_SE2 = 7,    /* Difference / Local with SE2 */
   THB_COST_REPROJECTION = 5  /* theseus/embodied/measurements/reprojection.py:54-94: x0 = camera SE3, x1 = Point3,
                                 aux = focal_length [Bf,1], aux2 = image_feature_point [Bi,2], aux3 = calib_k1, aux4 = calib_k2 */
 };

@@ -377,3 +377,42 @@ def se2_inverse(T):
     x = -(c * T[..., 0] + s * T[..., 1])
     y = -(-s * T[..., 0] + c * T[..., 1])
     return np.stack([x, y, c, -s], axis=-1)
+
+
+def se2_jlog(T):
+    """theseus/geometry/se2.py:165-228 (_log_map_impl with jacobians).  Returns (J[...,3,3], xi)."""
+    dt = T.dtype
+    xi = se2_log(T)
+    ux, uy, theta = xi[..., 0], xi[..., 1], xi[..., 2]
+    cosine, sine = T[..., 2], T[..., 3]
+    d_small = np.abs(theta) < _EPS_TH[np.dtype(dt)]["se2_d_near_zero"]
+    one = np.ones((), dtype=dt)
+    theta_nz = np.where(d_small, one, theta)
+    omc_nz = np.where(d_small, one, 1 - cosine)
+    half = 0.5 * theta
+    a = np.where(d_small, 1 - theta**2 / 12.0, half * sine / omc_nz)
+    coeff = np.where(d_small, theta / 12.0 + theta**3 / 720.0, 1.0 / theta_nz - 0.5 * sine / omc_nz)
+    J = np.zeros(T.shape[:-1] + (3, 3), dtype=dt)
+    J[..., 0, 0] = a
+    J[..., 1, 1] = a
+    J[..., 0, 1] = -half
+    J[..., 1, 0] = half
+    J[..., 0, 2] = coeff * ux + 0.5 * uy
+    J[..., 1, 2] = coeff * uy - 0.5 * ux
+    J[..., 2, 2] = 1
+    return J, xi
+
+
+def se2_adjoint(T):
+    """theseus/geometry/se2.py:309-316."""
+    out = np.zeros(T.shape[:-1] + (3, 3), dtype=T.dtype)
+    c, s = T[..., 2], T[..., 3]
+    out[..., 0, 0], out[..., 0, 1], out[..., 1, 0], out[..., 1, 1] = c, -s, s, c
+    out[..., 0, 2] = T[..., 1]
+    out[..., 1, 2] = -T[..., 0]
+    out[..., 2, 2] = 1
+    return out
+
+
+def se2_retract(T, delta):
+    return se2_compose(T, se2_exp(delta))

@@ -25,6 +25,8 @@ _GROUP = {
                 log=lie.se3_log, adjoint=lie.se3_adjoint, exp=lie.se3_exp),
     "SO3": dict(dof=3, inverse=lie.so3_inverse, compose=lie.so3_compose, jlog=lie.so3_jlog,
                 log=lie.so3_log, adjoint=lie.so3_adjoint, exp=lie.so3_exp),
+    "SE2": dict(dof=3, inverse=lie.se2_inverse, compose=lie.se2_compose, jlog=lie.se2_jlog,
+                log=lie.se2_log, adjoint=lie.se2_adjoint, exp=lie.se2_exp),
 }
 
 
@@ -330,6 +332,8 @@ def retract(spec, values, delta, ignore_mask=None):
             new = lie.se3_retract(values[i], d)
         elif v["kind"] == "SO3":
             new = lie.so3_retract(values[i], d)
+        elif v["kind"] == "SE2":
+            new = lie.se2_retract(values[i], d)
         elif v["kind"] == "Vector":
             new = values[i] + d
         else:

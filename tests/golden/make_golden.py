@@ -304,6 +304,59 @@ def make_simple_example(th):
     print("simple_example v ->", sol["v"].numpy().ravel(), "converged_iter", info.converged_iter.numpy(), info.err_history.numpy()[0, :4])
 
 
+def make_se2(th):
+    """SE2 (config C4's group): exp/log/compose/inverse/adjoint KATs, Between/Difference Jacobians and a small 2-D pose-graph
+    LM trace, all from the reference classes (theseus/geometry/se2.py, embodied/measurements/between.py)."""
+    import torch
+    torch.manual_seed(11)
+    dt = torch.float64
+    out = {}
+    B = 24
+    xi = torch.randn(B, 3, dtype=dt)
+    xi[:6, 2] *= 1e-7   # near-zero branches (se2 eps 1e-6 / 1e-3)
+    xi[6:10, 2] *= 1e-4
+    G = th.SE2.exp_map(xi)
+    H = th.SE2.exp_map(torch.randn(B, 3, dtype=dt))
+    jl = []
+    out.update(tangent=xi.numpy(), exp=G.tensor.numpy(), log=G.log_map(jacobians=jl).numpy(), jlog=jl[0].numpy(),
+               adj=G.adjoint().numpy(), inv=G.inverse().tensor.numpy(), other=H.tensor.numpy(), compose=G.compose(H).tensor.numpy())
+    Z = th.SE2.exp_map(torch.randn(B, 3, dtype=dt))
+    w = torch.rand(1, 3, dtype=dt) + 0.5
+    (J0, J1), e = th.Between(G, H, Z, th.DiagonalCostWeight(w)).weighted_jacobians_error()
+    (Jl,), el = th.Difference(G, Z, th.ScaleCostWeight(torch.tensor(0.7, dtype=dt))).weighted_jacobians_error()
+    out.update(Z=Z.tensor.numpy(), w=w.numpy(), between_J0=J0.numpy(), between_J1=J1.numpy(), between_e=e.numpy(),
+               local_J=Jl.numpy(), local_e=el.numpy())
+    # small 2-D pose graph: ring of N poses with odometry + a few chords, batch 3
+    N, Bp = 7, 3
+    gt = [th.SE2.exp_map(torch.zeros(Bp, 3, dtype=dt))]
+    for i in range(1, N):
+        gt.append(gt[-1].compose(th.SE2.exp_map(torch.tensor([[1.0, 0.1, 0.6]], dtype=dt).repeat(Bp, 1) + 0.1 * torch.randn(Bp, 3, dtype=dt))))
+    edges = [(i, i + 1) for i in range(N - 1)] + [(0, 3), (2, 6), (1, 5)]
+    poses = [th.SE2(tensor=gt[i].compose(th.SE2.exp_map(0.2 * torch.randn(Bp, 3, dtype=dt))).tensor, name=f"P{i}") for i in range(N)]
+    objective = th.Objective(dtype=dt)
+    meas = []
+    for k, (i, j) in enumerate(edges):
+        z = gt[i].inverse().compose(gt[j]).compose(th.SE2.exp_map(0.02 * torch.randn(Bp, 3, dtype=dt)))
+        z = th.SE2(tensor=z.tensor, name=f"Z{k}")
+        meas.append(z.tensor.numpy())
+        objective.add(th.Between(poses[i], poses[j], z, th.DiagonalCostWeight(th.Variable(torch.tensor([[10.0, 10.0, 20.0]], dtype=dt), name=f"W{k}"))))
+    objective.add(th.Difference(poses[0], th.SE2(tensor=gt[0].tensor.clone(), name="P0_prior"), th.ScaleCostWeight(torch.tensor(5.0, dtype=dt))))
+    poses0 = np.stack([p.tensor.numpy().copy() for p in poses], 0)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=6, abs_err_tolerance=0, rel_err_tolerance=0)
+    tr = dict(delta=[], err=[])
+
+    def cb(optimizer, info, delta, it):
+        tr["delta"].append(delta.numpy().copy()); tr["err"].append(info.last_err.numpy().copy())
+    objective.update()
+    with torch.no_grad():
+        info = opt.optimize(track_err_history=True, end_iter_callback=cb, damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)
+    out.update(pg_poses0=poses0, pg_edges=np.array(edges), pg_meas=np.stack(meas, 0), pg_prior=gt[0].tensor.numpy(),
+               pg_err0=info.err_history[:, 0].numpy(), pg_trace_err=np.stack(tr["err"], 0), pg_trace_delta=np.stack(tr["delta"], 0),
+               pg_final=np.stack([p.tensor.numpy() for p in poses], 0))
+    np.savez_compressed(os.path.join(HERE, "se2_kat.npz"), **out)
+    print("se2_kat.npz pose-graph err", out["pg_err0"], "->", out["pg_trace_err"][-1])
+
+
 if __name__ == "__main__":
     th, lieF = _import_reference()
     make_lie(th, lieF)
@@ -319,3 +372,4 @@ if __name__ == "__main__":
     make_pgo(th, "pgo32_lm_hard", num_poses=32, B=3, seed=5, iters=10, lm_kwargs=lm, full_trace=False, init_perturb=0.5)
     make_ba(th, "ba_small_lm", num_cameras=6, num_points=40, B=3, seed=7, iters=8)
     make_simple_example(th)
+    make_se2(th)

@@ -125,3 +125,29 @@ def ba_objective(th, g, device="cuda"):
                                     camera_weight, name=f"camera_diff_{int(i)}"))
     objective.to(device)
     return objective, cams, pts
+
+
+def se2_pg_spec(g, dtype=np.float64):
+    spec = dict(dtype=np.dtype(dtype), vars=[], costs=[])
+    for i in range(g["pg_poses0"].shape[0]):
+        spec["vars"].append(dict(kind="SE2", dof=3, value=g["pg_poses0"][i].astype(dtype)))
+    w = np.array([[10.0, 10.0, 20.0]], dtype=dtype)
+    for k, (i, j) in enumerate(g["pg_edges"]):
+        spec["costs"].append(dict(kind="between", group="SE2", vars=(int(i), int(j)), aux=g["pg_meas"][k].astype(dtype), weight=("diag", w)))
+    spec["costs"].append(dict(kind="local", group="SE2", vars=(0,), aux=g["pg_prior"].astype(dtype), weight=("scale", np.full((1, 1), 5.0, dtype=dtype))))
+    return spec
+
+
+def se2_pg_objective(th, g, device="cuda"):
+    import torch
+    dt = torch.float64
+    poses = [th.SE2(tensor=torch.from_numpy(g["pg_poses0"][i]), name=f"P{i}") for i in range(g["pg_poses0"].shape[0])]
+    objective = th.Objective(dtype=dt)
+    for k, (i, j) in enumerate(g["pg_edges"]):
+        z = th.SE2(tensor=torch.from_numpy(g["pg_meas"][k]), name=f"Z{k}")
+        objective.add(th.Between(poses[int(i)], poses[int(j)], z,
+                                 th.DiagonalCostWeight(th.Variable(torch.tensor([[10.0, 10.0, 20.0]], dtype=dt), name=f"W{k}")), name=f"btw{k}"))
+    objective.add(th.Difference(poses[0], th.SE2(tensor=torch.from_numpy(g["pg_prior"]), name="P0_prior"),
+                                th.ScaleCostWeight(torch.tensor(5.0, dtype=dt)), name="prior"))
+    objective.to(device)
+    return objective, poses

@@ -17,10 +17,11 @@ from typing import Dict, List, Optional, Sequence, Union
 
 import torch
 
-from .geometry import LieGroup, Manifold, Point2, Point3, SE3, SO3, Variable, Vector, as_variable
+from .geometry import LieGroup, Manifold, Point2, Point3, SE2, SE3, SO3, Variable, Vector, as_variable
 
 # enum thb_cost_kind / thb_weight_kind (include/thb200.h)
 COST_BETWEEN_SE3, COST_LOCAL_SE3, COST_BETWEEN_SO3, COST_LOCAL_SO3, COST_LOCAL_VECTOR, COST_REPROJECTION = 0, 1, 2, 3, 4, 5
+COST_BETWEEN_SE2, COST_LOCAL_SE2 = 6, 7
 WEIGHT_SCALE, WEIGHT_DIAGONAL = 0, 1
 
 
@@ -148,6 +149,8 @@ class Between(CostFunction):
             return COST_BETWEEN_SE3, self.measurement
         if isinstance(self.v0, SO3):
             return COST_BETWEEN_SO3, self.measurement
+        if isinstance(self.v0, SE2):
+            return COST_BETWEEN_SE2, self.measurement
         return super().schema()
 
 
@@ -172,6 +175,8 @@ class Difference(CostFunction):
             return COST_LOCAL_SE3, self.target
         if isinstance(self.var, SO3):
             return COST_LOCAL_SO3, self.target
+        if isinstance(self.var, SE2):
+            return COST_LOCAL_SE2, self.target
         if isinstance(self.var, Vector):
             return COST_LOCAL_VECTOR, self.target
         return super().schema()

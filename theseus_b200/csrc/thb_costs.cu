@@ -184,6 +184,43 @@ __device__ __forceinline__ void so3_cost(const GroupDev<T>& g, int k, int64_t b,
   for (int r = 0; r < 3; r++) e[r] *= w[r];
 }
 
+template <typename T, bool WITH_J, bool BETWEEN>
+__device__ __forceinline__ void se2_cost(const GroupDev<T>& g, int k, int64_t b, const T* w, T* e, T* J0, T* J1) {
+  T X0[4], Z[4], D[4], E[4];
+  load_n<T, 4>(g.x0[k] + (int64_t)g.bstride[k * 4 + 0] * b, X0);
+  load_n<T, 4>(g.aux[k] + (int64_t)g.bstride[k * 4 + 2] * b, Z);
+  if (BETWEEN) {
+    T X1[4];
+    load_n<T, 4>(g.x1[k] + (int64_t)g.bstride[k * 4 + 1] * b, X1);
+    se2_between(X0, X1, D);
+    se2_between(Z, D, E);
+  } else {
+    se2_between(Z, X0, E);
+  }
+  T Jl[9];
+  se2_log_jlog<T, WITH_J>(E, e, Jl);
+#pragma unroll
+  for (int r = 0; r < 3; r++) e[r] *= w[r];
+  if (WITH_J) {
+    if (BETWEEN) {
+      T Di[4], Ad[9];
+      se2_inverse(D, Di);
+      se2_adjoint(Di, Ad);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const T s = Jl[r * 3 + 0] * Ad[0 * 3 + c] + Jl[r * 3 + 1] * Ad[1 * 3 + c] + Jl[r * 3 + 2] * Ad[2 * 3 + c];
+          J0[r * 3 + c] = (-s) * w[r];
+          J1[r * 3 + c] = Jl[r * 3 + c] * w[r];
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; i++) J0[i] = Jl[i] * w[i / 3];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <typename T, int KIND>
 __global__ void __launch_bounds__(128) linearize_kernel(GroupDev<T> g, int64_t B, T* __restrict__ A_val, int64_t nnz,
@@ -193,7 +230,8 @@ __global__ void __launch_bounds__(128) linearize_kernel(GroupDev<T> g, int64_t B
   const int k = (int)(t / B);
   const int64_t b = t - (int64_t)k * B;
   constexpr int DIM = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_LOCAL_SE3) ? 6 : 3;
-  constexpr bool BETWEEN = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_BETWEEN_SO3);
+  constexpr bool BETWEEN = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_BETWEEN_SO3 || KIND == THB_COST_BETWEEN_SE2);
+  constexpr bool IS_SE2 = (KIND == THB_COST_BETWEEN_SE2 || KIND == THB_COST_LOCAL_SE2);
   T w[DIM], e[DIM], J0[DIM * DIM], J1[DIM * DIM];
   const bool masked = load_weight<T, DIM>(g, k, b, w);
   if (masked) {
@@ -203,6 +241,8 @@ __global__ void __launch_bounds__(128) linearize_kernel(GroupDev<T> g, int64_t B
     for (int i = 0; i < DIM * DIM; i++) { J0[i] = T(0); J1[i] = T(0); }
   } else if (DIM == 6) {
     se3_cost<T, true, BETWEEN>(g, k, b, w, e, J0, J1);
+  } else if (IS_SE2) {
+    se2_cost<T, true, BETWEEN>(g, k, b, w, e, J0, J1);
   } else {
     so3_cost<T, true, BETWEEN>(g, k, b, w, e, J0, J1);
   }
@@ -356,7 +396,8 @@ __global__ void __launch_bounds__(128) error_kernel(GroupDev<T> g, int64_t B, T*
   const int c = (int)(t / B);
   const int64_t b = t - (int64_t)c * B;
   constexpr int DIM = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_LOCAL_SE3) ? 6 : 3;
-  constexpr bool BETWEEN = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_BETWEEN_SO3);
+  constexpr bool BETWEEN = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_BETWEEN_SO3 || KIND == THB_COST_BETWEEN_SE2);
+  constexpr bool IS_SE2 = (KIND == THB_COST_BETWEEN_SE2 || KIND == THB_COST_LOCAL_SE2);
   T acc = T(0);
   const int k1 = min(g.K, (c + 1) * kErrCostsPerThread);
   for (int k = c * kErrCostsPerThread; k < k1; k++) {
@@ -364,6 +405,7 @@ __global__ void __launch_bounds__(128) error_kernel(GroupDev<T> g, int64_t B, T*
     const bool masked = load_weight<T, DIM>(g, k, b, w);
     if (masked) continue;
     if (DIM == 6) se3_cost<T, false, BETWEEN>(g, k, b, w, e, nullptr, nullptr);
+    else if (IS_SE2) se2_cost<T, false, BETWEEN>(g, k, b, w, e, nullptr, nullptr);
     else so3_cost<T, false, BETWEEN>(g, k, b, w, e, nullptr, nullptr);
 #pragma unroll
     for (int r = 0; r < DIM; r++) acc += e[r] * e[r];
@@ -464,6 +506,23 @@ __global__ void __launch_bounds__(128) retract_kernel(VarDev<T> v, int64_t B, co
     }
 #pragma unroll
     for (int q = 0; q < 9; q++) op[q] = O[q];
+  } else if (kind == THB_VAR_SE2) {
+    const T* xp = v.x[i] + b * 4;
+    T* op = v.out[i] + b * 4;
+    T X[4], O[4];
+    load_n<T, 4>(xp, X);
+    if (keep) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) O[q] = X[q];
+    } else {
+      T xi[3], G[4];
+#pragma unroll
+      for (int q = 0; q < 3; q++) xi[q] = d[q] * step;
+      se2_exp(xi, G);
+      se2_compose(X, G, O);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) op[q] = O[q];
   } else {  // Vector / Point: x + delta
     const int dof = v.dof[i];
     const T* xp = v.x[i] + b * dof;
@@ -590,6 +649,8 @@ static int linearize_group(const thb_cost_group* g, int64_t B, T* A_val, int64_t
     case THB_COST_LOCAL_SE3: linearize_kernel<T, THB_COST_LOCAL_SE3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
     case THB_COST_BETWEEN_SO3: linearize_kernel<T, THB_COST_BETWEEN_SO3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
     case THB_COST_LOCAL_SO3: linearize_kernel<T, THB_COST_LOCAL_SO3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
+    case THB_COST_BETWEEN_SE2: linearize_kernel<T, THB_COST_BETWEEN_SE2><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
+    case THB_COST_LOCAL_SE2: linearize_kernel<T, THB_COST_LOCAL_SE2><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
     case THB_COST_LOCAL_VECTOR: linearize_vector_kernel<T><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
     case THB_COST_REPROJECTION:
       if (g->aux2 == nullptr || g->aux3 == nullptr || g->aux4 == nullptr || g->bstride2 == nullptr) return THB_ERR_BAD_ARG;
@@ -613,6 +674,8 @@ template <typename T> static int error_group(const thb_cost_group* g, int64_t B,
     case THB_COST_LOCAL_SE3: error_kernel<T, THB_COST_LOCAL_SE3><<<grid, 128, 0, cs>>>(d, B, partial); break;
     case THB_COST_BETWEEN_SO3: error_kernel<T, THB_COST_BETWEEN_SO3><<<grid, 128, 0, cs>>>(d, B, partial); break;
     case THB_COST_LOCAL_SO3: error_kernel<T, THB_COST_LOCAL_SO3><<<grid, 128, 0, cs>>>(d, B, partial); break;
+    case THB_COST_BETWEEN_SE2: error_kernel<T, THB_COST_BETWEEN_SE2><<<grid, 128, 0, cs>>>(d, B, partial); break;
+    case THB_COST_LOCAL_SE2: error_kernel<T, THB_COST_LOCAL_SE2><<<grid, 128, 0, cs>>>(d, B, partial); break;
     case THB_COST_LOCAL_VECTOR: error_vector_kernel<T><<<grid, 128, 0, cs>>>(d, B, partial); break;
     case THB_COST_REPROJECTION:
       if (g->aux2 == nullptr || g->aux3 == nullptr || g->aux4 == nullptr || g->bstride2 == nullptr) return THB_ERR_BAD_ARG;

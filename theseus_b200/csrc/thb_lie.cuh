@@ -287,4 +287,76 @@ template <typename T> __device__ __forceinline__ void so3_between(const T* A, co
     for (int j = 0; j < 3; j++) C[i * 3 + j] = A[0 * 3 + i] * B[0 * 3 + j] + A[1 * 3 + i] * B[1 * 3 + j] + A[2 * 3 + i] * B[2 * 3 + j];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SE2 (theseus/geometry/se2.py): storage [x, y, cos, sin], tangent [ux, uy, theta]; eps theseus/global_params.py:46-59
+template <typename T> struct Se2Eps;
+template <> struct Se2Eps<float> { static constexpr float near_zero = 3e-2f, d_near_zero = 1e-1f; };
+template <> struct Se2Eps<double> { static constexpr double near_zero = 1e-6, d_near_zero = 1e-3; };
+
+// C = A * B (se2.py:318-332)
+template <typename T> __device__ __forceinline__ void se2_compose(const T* A, const T* B, T* C) {
+  C[0] = A[2] * B[0] - A[3] * B[1] + A[0];
+  C[1] = A[3] * B[0] + A[2] * B[1] + A[1];
+  C[2] = A[2] * B[2] - A[3] * B[3];
+  C[3] = A[3] * B[2] + A[2] * B[3];
+}
+// C = A^-1 (se2.py:334-339)
+template <typename T> __device__ __forceinline__ void se2_inverse(const T* A, T* C) {
+  C[0] = -(A[2] * A[0] + A[3] * A[1]);
+  C[1] = -(-A[3] * A[0] + A[2] * A[1]);
+  C[2] = A[2];
+  C[3] = -A[3];
+}
+template <typename T> __device__ __forceinline__ void se2_between(const T* A, const T* B, T* C) {
+  T Ai[4];
+  se2_inverse(A, Ai);
+  se2_compose(Ai, B, C);
+}
+// exp (se2.py:239-268)
+template <typename T> __device__ __forceinline__ void se2_exp(const T* xi, T* G) {
+  const T theta = xi[2];
+  T s, c;
+  t_sincos(theta, &s, &c);
+  const bool small = (theta < T(0) ? -theta : theta) < Se2Eps<T>::near_zero;
+  const T theta_nz = small ? T(1) : theta;
+  const T sbt = small ? (T(1) - theta * theta / T(6)) : (s / theta_nz);
+  const T cmo = small ? (-theta / T(2) + theta * theta * theta / T(24)) : ((c - T(1)) / theta_nz);
+  G[0] = sbt * xi[0] + cmo * xi[1];
+  G[1] = sbt * xi[1] - cmo * xi[0];
+  G[2] = c;
+  G[3] = s;
+}
+// log + jlog (se2.py:165-228); J row-major 3x3
+template <typename T, bool WITH_J> __device__ __forceinline__ void se2_log_jlog(const T* G, T* xi, T* J) {
+  const T cosine = G[2], sine = G[3];
+  const T theta = t_atan2(sine, cosine);
+  const T at = theta < T(0) ? -theta : theta;
+  const bool small = at < Se2Eps<T>::near_zero;
+  const T sine_nz = small ? T(1) : sine;
+  const T a = T(0.5) * (T(1) + cosine) * (small ? (T(1) + sine * sine / T(6)) : (theta / sine_nz));
+  const T half = T(0.5) * theta;
+  const T ux = a * G[0] + half * G[1];
+  const T uy = a * G[1] - half * G[0];
+  xi[0] = ux;
+  xi[1] = uy;
+  xi[2] = theta;
+  if (WITH_J) {
+    const bool dsmall = at < Se2Eps<T>::d_near_zero;
+    const T theta_nz = dsmall ? T(1) : theta;
+    const T omc_nz = dsmall ? T(1) : (T(1) - cosine);
+    const T d = dsmall ? (T(1) - theta * theta / T(12)) : (half * sine / omc_nz);
+    const T coeff = dsmall ? (theta / T(12) + theta * theta * theta / T(720)) : (T(1) / theta_nz - T(0.5) * sine / omc_nz);
+    J[0] = d;      J[1] = -half;  J[2] = coeff * ux + T(0.5) * uy;
+    J[3] = half;   J[4] = d;      J[5] = coeff * uy - T(0.5) * ux;
+    J[6] = T(0);   J[7] = T(0);   J[8] = T(1);
+  }
+}
+// adjoint (se2.py:309-316)
+template <typename T> __device__ __forceinline__ void se2_adjoint(const T* G, T* Ad) {
+  Ad[0] = G[2]; Ad[1] = -G[3]; Ad[2] = G[1];
+  Ad[3] = G[3]; Ad[4] = G[2];  Ad[5] = -G[0];
+  Ad[6] = T(0); Ad[7] = T(0);  Ad[8] = T(1);
+}
+
 }  // namespace thb

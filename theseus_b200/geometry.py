@@ -261,3 +261,23 @@ class SO3(LieGroup):
 
     def dof(self) -> int:
         return 3
+
+
+class SE2(LieGroup):
+    """theseus/geometry/se2.py:21 -- storage [B,4] = [x, y, cos, sin], tangent [ux, uy, theta]."""
+    KIND = 3  # THB_VAR_SE2
+
+    def __init__(self, x_y_theta: Optional[torch.Tensor] = None, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None,
+                 dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
+        if x_y_theta is not None and tensor is not None:
+            raise ValueError("Please provide only one of x_y_theta or tensor.")
+        if x_y_theta is not None:
+            tensor = torch.cat([x_y_theta[:, :2], x_y_theta[:, 2:3].cos(), x_y_theta[:, 2:3].sin()], dim=1)
+        if tensor is None:
+            tensor = torch.tensor([[0.0, 0.0, 1.0, 0.0]], dtype=dtype or torch.get_default_dtype())
+        if tensor.ndim != 2 or tensor.shape[1] != 4:
+            raise ValueError("SE2 data tensors can only be 4D vectors.")  # geometry/se2.py:219-224
+        super().__init__(tensor, name=name)
+
+    def dof(self) -> int:
+        return 3
