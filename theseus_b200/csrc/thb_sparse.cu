@@ -18,7 +18,7 @@
 namespace thb {
 
 constexpr int SP_MAXD = 16;
-constexpr int SP_THREADS = 256;
+constexpr int SP_THREADS = 512;
 
 __global__ void __launch_bounds__(SP_THREADS) sparse_damp_kernel(thb_sparse_plan p, double* __restrict__ factor,
                                                                  const double* __restrict__ alpha, const double* __restrict__ beta, int64_t B) {
@@ -40,78 +40,123 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_damp_kernel(thb_sparse_plan
   *D = *D * (1.0 + a) + be;
 }
 
+// d x d Cholesky + inverse of one diagonal block held in registers (D known at compile time) or local memory (generic).
+template <int D>
+__device__ __noinline__ int potrf_inv_small(double* __restrict__ Dg, double* __restrict__ Wj, int d) {
+  constexpr int LD = (D > 0) ? D : SP_MAXD;
+  if (D > 0) d = D;
+  double a[LD * LD];
+#pragma unroll
+  for (int r = 0; r < LD; r++)
+#pragma unroll
+    for (int c = 0; c < LD; c++)
+      if (r < d && c <= r) a[r * LD + c] = Dg[r * d + c];
+  int fail = 0;
+#pragma unroll
+  for (int c = 0; c < LD; c++) {
+    if (c < d) {
+      double dd = a[c * LD + c];
+#pragma unroll
+      for (int k = 0; k < LD; k++)
+        if (k < c) dd -= a[c * LD + k] * a[c * LD + k];
+      if (!(dd > 0.0) && fail == 0) fail = c + 1;
+      const double inv = rsqrt(dd);
+      a[c * LD + c] = dd * inv;
+#pragma unroll
+      for (int r = 0; r < LD; r++) {
+        if (r > c && r < d) {
+          double sacc = a[r * LD + c];
+#pragma unroll
+          for (int k = 0; k < LD; k++)
+            if (k < c) sacc -= a[r * LD + k] * a[c * LD + k];
+          a[r * LD + c] = sacc * inv;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < LD; r++)
+#pragma unroll
+    for (int c = 0; c < LD; c++)
+      if (r < d && c < d) Dg[r * d + c] = (c <= r) ? a[r * LD + c] : 0.0;
+  // inverse of the lower-triangular block, column by column
+#pragma unroll
+  for (int c = 0; c < LD; c++) {
+    if (c < d) {
+      double x[LD];
+#pragma unroll
+      for (int r = 0; r < LD; r++) {
+        if (r < d) {
+          if (r < c) { x[r] = 0.0; }
+          else {
+            double sacc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < LD; k++)
+              if (k >= c && k < r) sacc -= a[r * LD + k] * x[k];
+            x[r] = sacc / a[r * LD + r];
+          }
+          Wj[r * d + c] = x[r];
+        }
+      }
+    }
+  }
+  return fail;
+}
+
 __global__ void __launch_bounds__(SP_THREADS) sparse_factor_kernel(thb_sparse_plan p, double* __restrict__ factor, double* __restrict__ winv,
                                                                    int32_t* __restrict__ info) {
   const int64_t b = blockIdx.x;
   double* F = factor + b * p.data_size;
   double* W = winv + b * p.winv_size;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = SP_THREADS / 32;
   __shared__ int s_fail;
   if (tid == 0) s_fail = 0;
   __syncthreads();
   for (int lv = 0; lv < p.num_levels; lv++) {
-    // ---- U: updates.  Work item = one block; its scalars are spread over the threads (u_r/u_c = rows/cols, u_ld = is-diagonal) ----
+    // ---- U: updates.  One warp per block; lane l owns scalars l, l+32, ... of the block (u_r/u_c = rows/cols, u_ld = is-diagonal) ----
     {
-      const int64_t e0 = p.u_ptr[lv], e1 = p.u_ptr[lv + 1];
-      // flatten (item, scalar) with a fixed 64-slot stride per item (blocks are <= 16x16; 6x6 = 36 of 64 slots used... use exact di*dj below)
-      for (int64_t e = e0 + (tid >> 6); e < e1; e += SP_THREADS >> 6) {
+      const int64_t e1 = p.u_ptr[lv + 1];
+      for (int64_t e = p.u_ptr[lv] + warp; e < e1; e += NW) {
         const int di = p.u_r[e], dj = p.u_c[e];
         const bool diag = p.u_ld[e] != 0;
         const int64_t tgt = p.u_tgt[e];
         const int64_t q0 = p.u_p0[e], q1 = p.u_p1[e];
-        for (int t = tid & 63; t < di * dj; t += 64) {
+        for (int t = lane; t < di * dj; t += 32) {
           const int r = t / dj, c = t - r * dj;
           if (diag && c > r) continue;
-          double acc = F[tgt + t];
-          for (int64_t q = q0; q < q1; q++) {
-            const int dk = p.up_k[q];
-            const double* a = F + p.up_a[q] + r * dk;
-            const double* bb = F + p.up_b[q] + c * dk;
-            double s = 0.0;
-            for (int k = 0; k < dk; k++) s += a[k] * bb[k];
-            acc -= s;
+          double acc0 = 0.0, acc1 = 0.0;
+          int64_t q = q0;
+          for (; q + 1 < q1; q += 2) {  // two independent update pairs in flight
+            const int dk0 = p.up_k[q], dk1 = p.up_k[q + 1];
+            const double* a0 = F + p.up_a[q] + r * dk0;
+            const double* b0 = F + p.up_b[q] + c * dk0;
+            const double* a1 = F + p.up_a[q + 1] + r * dk1;
+            const double* b1 = F + p.up_b[q + 1] + c * dk1;
+            for (int k = 0; k < dk0; k++) acc0 += a0[k] * b0[k];
+            for (int k = 0; k < dk1; k++) acc1 += a1[k] * b1[k];
           }
-          F[tgt + t] = acc;
+          if (q < q1) {
+            const int dk0 = p.up_k[q];
+            const double* a0 = F + p.up_a[q] + r * dk0;
+            const double* b0 = F + p.up_b[q] + c * dk0;
+            for (int k = 0; k < dk0; k++) acc0 += a0[k] * b0[k];
+          }
+          F[tgt + t] -= (acc0 + acc1);
         }
       }
     }
     __syncthreads();
-    // ---- F: diagonal blocks ----
+    // ---- F: diagonal blocks (one thread per column; 6x6 and 3x3 fully in registers) ----
     for (int64_t e = p.f_ptr[lv] + tid; e < p.f_ptr[lv + 1]; e += SP_THREADS) {
       const int d = p.f_dim[e];
       double* D = F + p.f_off[e];
       double* Wj = W + p.f_w[e];
-      double a[SP_MAXD * SP_MAXD];
-      for (int r = 0; r < d; r++)
-        for (int c = 0; c <= r; c++) a[r * SP_MAXD + c] = D[r * d + c];
-      int fail = 0;
-      for (int c = 0; c < d; c++) {
-        double dd = a[c * SP_MAXD + c];
-        for (int k = 0; k < c; k++) dd -= a[c * SP_MAXD + k] * a[c * SP_MAXD + k];
-        if (!(dd > 0.0) && fail == 0) fail = p.pstart[p.f_col[e]] + c + 1;
-        const double sq = sqrt(dd);
-        a[c * SP_MAXD + c] = sq;
-        const double inv = 1.0 / sq;
-        for (int r = c + 1; r < d; r++) {
-          double s = a[r * SP_MAXD + c];
-          for (int k = 0; k < c; k++) s -= a[r * SP_MAXD + k] * a[c * SP_MAXD + k];
-          a[r * SP_MAXD + c] = s * inv;
-        }
-      }
-      if (fail != 0) atomicCAS(&s_fail, 0, fail);
-      for (int r = 0; r < d; r++)
-        for (int c = 0; c < d; c++) D[r * d + c] = (c <= r) ? a[r * SP_MAXD + c] : 0.0;
-      // inverse of the lower-triangular block, column by column
-      for (int c = 0; c < d; c++) {
-        double x[SP_MAXD];
-        for (int r = 0; r < d; r++) {
-          if (r < c) { x[r] = 0.0; continue; }
-          double s = (r == c) ? 1.0 : 0.0;
-          for (int k = c; k < r; k++) s -= a[r * SP_MAXD + k] * x[k];
-          x[r] = s / a[r * SP_MAXD + r];
-        }
-        for (int r = 0; r < d; r++) Wj[r * d + c] = x[r];
-      }
+      int fail;
+      if (d == 6) fail = potrf_inv_small<6>(D, Wj, 6);
+      else if (d == 3) fail = potrf_inv_small<3>(D, Wj, 3);
+      else fail = potrf_inv_small<0>(D, Wj, d);
+      if (fail != 0) atomicCAS(&s_fail, 0, p.pstart[p.f_col[e]] + fail);
     }
     __syncthreads();
     // ---- T: L_ij[r,:] = U_ij[r,:] W_j^T ----
@@ -122,9 +167,9 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_factor_kernel(thb_sparse_pl
       double u[SP_MAXD];
       for (int q = 0; q < d; q++) u[q] = row[q];
       for (int c = 0; c < d; c++) {
-        double s = 0.0;
-        for (int q = 0; q <= c; q++) s += u[q] * Wj[c * d + q];
-        row[c] = s;
+        double sacc = 0.0;
+        for (int q = 0; q <= c; q++) sacc += u[q] * Wj[c * d + q];
+        row[c] = sacc;
       }
     }
     __syncthreads();
@@ -133,6 +178,7 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_factor_kernel(thb_sparse_pl
 }
 
 // x = (L L^T)^-1 rhs in the original variable order.  work [B,n] holds the permuted vector.
+// One warp per column: the lanes split the column's block list, partial sums are combined with shuffles.
 __global__ void __launch_bounds__(SP_THREADS) sparse_solve_kernel(thb_sparse_plan p, const double* __restrict__ factor,
                                                                   const double* __restrict__ winv, const double* __restrict__ rhs,
                                                                   double* __restrict__ x, double* __restrict__ work) {
@@ -141,65 +187,87 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_solve_kernel(thb_sparse_pla
   const double* W = winv + b * p.winv_size;
   const double* rb = rhs + b * p.n;
   double* y = work + b * p.n;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = SP_THREADS / 32;
   // forward: y_j = W_j (rhs_j - sum_k L_jk y_k); the permutation is folded into the load (K8 scramble, baspacho_solver_cuda.cu:216-232)
   for (int lv = 0; lv < p.num_levels; lv++) {
-    for (int64_t e = p.s_ptr[lv] + tid; e < p.s_ptr[lv + 1]; e += SP_THREADS) {
+    for (int64_t e = p.s_ptr[lv] + warp; e < p.s_ptr[lv + 1]; e += NW) {
       const int j = p.s_col[e];
       const int d = p.dims[j];
       double s[SP_MAXD];
-      const double* src = rb + p.col_start[j];
-      for (int r = 0; r < d; r++) s[r] = src[r];
-      for (int64_t q = p.fr_ptr[j]; q < p.fr_ptr[j + 1]; q++) {
+#pragma unroll
+      for (int r = 0; r < SP_MAXD; r++) s[r] = 0.0;
+      for (int64_t q = p.fr_ptr[j] + lane; q < p.fr_ptr[j + 1]; q += 32) {
         const int k = p.fr_k[q];
         const int dk = p.dims[k];
         const double* L = F + p.fr_off[q];
         const double* yk = y + p.pstart[k];
-        for (int r = 0; r < d; r++) {
-          double a = 0.0;
-          for (int c = 0; c < dk; c++) a += L[r * dk + c] * yk[c];
-          s[r] -= a;
+#pragma unroll
+        for (int r = 0; r < SP_MAXD; r++) {
+          if (r < d) {
+            double a = 0.0;
+            for (int c = 0; c < dk; c++) a += L[r * dk + c] * yk[c];
+            s[r] += a;
+          }
         }
       }
-      const double* Wj = W + p.winv_off[j];
-      double* yj = y + p.pstart[j];
-      for (int r = 0; r < d; r++) {
+#pragma unroll
+      for (int r = 0; r < SP_MAXD; r++) {
+        if (r < d) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+          s[r] = rb[p.col_start[j] + r] - s[r];
+        }
+      }
+      if (lane < d) {
+        const double* Wj = W + p.winv_off[j];
         double a = 0.0;
-        for (int c = 0; c <= r; c++) a += Wj[r * d + c] * s[c];
-        yj[r] = a;
+#pragma unroll
+        for (int c = 0; c < SP_MAXD; c++)
+          if (c <= lane && c < d) a += Wj[lane * d + c] * s[c];
+        y[p.pstart[j] + lane] = a;
       }
     }
     __syncthreads();
   }
   // backward: x_j = W_j^T (y_j - sum_i L_ij^T x_i)
   for (int lv = p.num_levels - 1; lv >= 0; lv--) {
-    for (int64_t e = p.s_ptr[lv] + tid; e < p.s_ptr[lv + 1]; e += SP_THREADS) {
+    for (int64_t e = p.s_ptr[lv] + warp; e < p.s_ptr[lv + 1]; e += NW) {
       const int j = p.s_col[e];
       const int d = p.dims[j];
       double s[SP_MAXD];
-      double* yj = y + p.pstart[j];
-      for (int r = 0; r < d; r++) s[r] = yj[r];
-      for (int64_t q = p.bc_ptr[j]; q < p.bc_ptr[j + 1]; q++) {
+#pragma unroll
+      for (int r = 0; r < SP_MAXD; r++) s[r] = 0.0;
+      for (int64_t q = p.bc_ptr[j] + lane; q < p.bc_ptr[j + 1]; q += 32) {
         const int i = p.bc_i[q];
         const int di = p.dims[i];
         const double* L = F + p.bc_off[q];
         const double* xi = y + p.pstart[i];
         for (int r = 0; r < di; r++) {
           const double xr = xi[r];
-          for (int c = 0; c < d; c++) s[c] -= L[r * d + c] * xr;
+#pragma unroll
+          for (int c = 0; c < SP_MAXD; c++)
+            if (c < d) s[c] += L[r * d + c] * xr;
         }
       }
-      const double* Wj = W + p.winv_off[j];
-      double out[SP_MAXD];
-      for (int c = 0; c < d; c++) {
-        double a = 0.0;
-        for (int r = c; r < d; r++) a += Wj[r * d + c] * s[r];
-        out[c] = a;
+      double* yj = y + p.pstart[j];
+#pragma unroll
+      for (int c = 0; c < SP_MAXD; c++) {
+        if (c < d) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+          s[c] = yj[c] - s[c];
+        }
       }
-      double* dst = x + b * p.n + p.col_start[j];
-      for (int c = 0; c < d; c++) {
-        yj[c] = out[c];
-        dst[c] = out[c];  // un-permute on store (K8 unscramble, baspacho_solver_cuda.cu:234-250)
+      __syncwarp();
+      if (lane < d) {
+        const double* Wj = W + p.winv_off[j];
+        double a = 0.0;
+#pragma unroll
+        for (int r = 0; r < SP_MAXD; r++)
+          if (r >= lane && r < d) a += Wj[r * d + lane] * s[r];
+        yj[lane] = a;
+        x[b * p.n + p.col_start[j] + lane] = a;  // un-permute on store (K8 unscramble, baspacho_solver_cuda.cu:234-250)
       }
     }
     __syncthreads();
