@@ -55,6 +55,7 @@ enum thb_cost_kind {
   THB_COST_REPROJECTION = 5  /* theseus/embodied/measurements/reprojection.py:54-94: x0 = camera SE3, x1 = Point3,
                                 aux = focal_length [Bf,1], aux2 = image_feature_point [Bi,2], aux3 = calib_k1, aux4 = calib_k2 */
 };
+enum thb_robust_kind { THB_ROBUST_NONE = 0, THB_ROBUST_WELSCH = 1, THB_ROBUST_HUBER = 2 };
 enum thb_weight_kind {
   THB_WEIGHT_SCALE = 0,   /* theseus/core/cost_weight.py:60-93  (ScaleCostWeight, tensor [Bw,1]) */
   THB_WEIGHT_DIAGONAL = 1 /* theseus/core/cost_weight.py:98-139 (DiagonalCostWeight, tensor [Bw,dim]) */
@@ -84,6 +85,12 @@ typedef struct thb_cost_group {
   const void* const* aux3;
   const void* const* aux4;
   const int32_t* bstride2;
+  /* Robust wrapper (theseus/core/robust_cost_function.py:87-135, robust_loss.py:33-52): 0 = none, 1 = Welsch, 2 = Huber.
+   * log_radius: device [K] pointers to the log_loss_radius tensors [Br,1]; bstride_lr: device int32 [K]. */
+  int32_t robust_kind;
+  int32_t reserved0;
+  const void* const* log_radius;
+  const int32_t* bstride_lr;
 } thb_cost_group;
 
 /* Fused residual + analytic Jacobian + weighting for every (cost function, batch item) of a group;

@@ -109,6 +109,24 @@ def reprojection_error_jacobians(X, p, f, z, k1, k2, want_jac=True):
     return [Jp[..., :6], Jp[..., 6:]], err
 
 
+def robust_apply(robust, jacs, e):
+    """theseus/core/robust_cost_function.py:87-135 with the losses of robust_loss.py:33-52.
+    robust = (kind, log_radius [..,1]); e weighted error [...,dim].  With jacs: linearisation rescale; without: the
+    'hacky' error whose squared norm equals rho(||e||^2)."""
+    kind, log_radius = robust
+    radius = np.exp(log_radius)
+    x = (e ** 2).sum(axis=-1, keepdims=True)
+    if jacs is not None:
+        lin = np.exp(-x / (radius + 1e-20)) if kind == "welsch" else np.sqrt(radius / np.maximum(x, radius) + 1e-20)
+        sc = np.sqrt(lin + 1e-20)
+        return [sc[..., None] * J for J in jacs], sc * e
+    if kind == "welsch":
+        val = radius - radius * np.exp(-x / (radius + 1e-20))
+    else:
+        val = np.where(x > radius, 2 * np.sqrt(radius * np.maximum(x, radius) + 1e-20) - radius, x)
+    return None, np.ones_like(e) * np.sqrt(val / e.shape[-1] + 1e-20)
+
+
 def cost_dim(spec, cost):
     if cost["kind"] == "reproj":
         return 2
@@ -128,6 +146,14 @@ def eval_costs(spec, values, want_jac=True):
         groups.setdefault((c["kind"], c.get("group", "-") + (str(spec["vars"][c["vars"][0]]["dof"]) if c.get("group") == "Vector" else ""),
                            c["weight"][0]), []).append(f)
     out = [None] * len(spec["costs"])
+
+    def put(f, jac_list, err):
+        c = spec["costs"][f]
+        if c.get("robust") is not None:
+            rk, lr = c["robust"]
+            jac_list, err = robust_apply((rk, _bcast(np.asarray(lr, dtype=dt), B)), jac_list, err)
+        out[f] = (jac_list, err)
+
     for (kind, grp, wkind), idx in groups.items():
         grp = "Vector" if grp.startswith("Vector") else grp
         cs = [spec["costs"][f] for f in idx]
@@ -143,7 +169,7 @@ def eval_costs(spec, values, want_jac=True):
             if jacs is not None:
                 jacs = [J * w[..., None] for J in jacs]
             for r, f in enumerate(idx):
-                out[f] = ([J[r] for J in jacs] if jacs is not None else None, e[r])
+                put(f, [J[r] for J in jacs] if jacs is not None else None, e[r])
             continue
         aux = np.stack([_bcast(np.asarray(c["aux"], dtype=dt), B) for c in cs], 0)          # [K,B,...]
         if grp == "Vector":  # Difference on Vector/Point: e = x - target, J = I (geometry/vector.py)
@@ -173,7 +199,7 @@ def eval_costs(spec, values, want_jac=True):
         if jacs is not None:
             jacs = [J * w[..., None] for J in jacs]
         for r, f in enumerate(idx):
-            out[f] = ([J[r] for J in jacs] if jacs is not None else None, e[r])
+            put(f, [J[r] for J in jacs] if jacs is not None else None, e[r])
     return out
 
 

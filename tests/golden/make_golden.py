@@ -109,7 +109,7 @@ def make_costs(th):
     print("costs_kat.npz", len(out), "arrays")
 
 
-def _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio=0.2, init_perturb=0.0):
+def _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio=0.2, init_perturb=0.0, robust=None, outlier_ratio=0.0):
     import torch
     from theseus.utils.examples.pose_graph.dataset import PoseGraphDataset
     torch.manual_seed(seed)
@@ -117,15 +117,19 @@ def _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio=0.2, init_p
     rng = torch.Generator().manual_seed(seed)
     pg, _ = PoseGraphDataset.generate_synthetic_3D(
         num_poses=num_poses, translation_noise=0.05, rotation_noise=0.02, loop_closure_ratio=loop_closure_ratio,
-        loop_closure_outlier_ratio=0.0, dataset_size=B, batch_size=B, generator=rng, dtype=dtype)
+        loop_closure_outlier_ratio=outlier_ratio, dataset_size=B, batch_size=B, generator=rng, dtype=dtype)
     if init_perturb > 0:
         # harder start (so that LM needs all its iterations and really rejects steps): extra random right-perturbation
         for p in pg.poses[1:]:
             p.tensor = p.compose(th.SE3.exp_map(init_perturb * (2 * torch.rand(B, 6, dtype=dtype) - 1))).tensor
     # objective exactly as examples/pose_graph/pose_graph_cube.py:56-83
     objective = th.Objective(dtype=dtype)
+    log_loss_radius = th.Vector(tensor=torch.tensor([[0.5]], dtype=dtype), name="log_loss_radius")
     for edge in pg.edges:
-        objective.add(th.Between(pg.poses[edge.i], pg.poses[edge.j], edge.relative_pose, edge.weight))
+        cf = th.Between(pg.poses[edge.i], pg.poses[edge.j], edge.relative_pose, edge.weight)
+        if robust == "welsch":  # as examples/pose_graph/pose_graph_synthetic.py builds its robust relative-pose costs
+            cf = th.RobustCostFunction(cf, th.WelschLoss, log_loss_radius, name=f"robust_{cf.name}")
+        objective.add(cf)
     prior = th.Difference(var=pg.poses[0], cost_weight=th.ScaleCostWeight(torch.tensor(1e-3, dtype=dtype)),
                           target=pg.poses[0].copy(new_name=pg.poses[0].name + "__PRIOR"))
     objective.add(prior)
@@ -133,16 +137,19 @@ def _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio=0.2, init_p
 
 
 def make_pgo(th, name, num_poses, B, seed, iters, lm_kwargs, method="lm", full_trace=True, loop_closure_ratio=0.2,
-             init_perturb=0.0):
+             init_perturb=0.0, robust=None, outlier_ratio=0.0):
     import torch
     dtype = torch.float64
-    pg, objective = _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio, init_perturb)
+    pg, objective = _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio, init_perturb, robust, outlier_ratio)
+    out_robust = robust
     out = {}
     out["poses0"] = np.stack([p.tensor.numpy() for p in pg.poses], 0)            # [N,B,3,4]
     out["edges"] = np.array([[e.i, e.j] for e in pg.edges], dtype=np.int64)        # [E,2]
     out["meas"] = np.stack([e.relative_pose.tensor.numpy() for e in pg.edges], 0)  # [E,B,3,4]
     out["edge_w"] = np.stack([e.weight.diagonal.tensor.numpy() for e in pg.edges], 0)  # [E,1,6]
     out["prior_w"] = np.array(1e-3)
+    out["robust"] = np.array(robust or "")
+    out["log_loss_radius"] = np.array([[0.5]])
     cls = th.LevenbergMarquardt if method == "lm" else th.GaussNewton
     opt = cls(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=iters,
               step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
@@ -208,7 +215,7 @@ def make_dense_solver(th):
     print("dense_solver_kat.npz")
 
 
-def make_ba(th, name, num_cameras, num_points, B, seed, iters):
+def make_ba(th, name, num_cameras, num_points, B, seed, iters, robust=False):
     """Bundle adjustment as examples/bundle_adjustment.py:106-164 (Reprojection + reg priors + known-camera priors), without
     the Huber wrapper (robust losses are a 'next' row), batch built by re-perturbing the scene per item."""
     import random
@@ -226,12 +233,16 @@ def make_ba(th, name, num_cameras, num_points, B, seed, iters):
     points = [th.Point3(tensor=pts[i], name=f"Pt{i}") for i in range(num_points)]
     objective = th.Objective(dtype=dtype)
     weight = th.ScaleCostWeight(torch.tensor(1.0, dtype=dtype))
+    log_loss_radius = th.Vector(1, name="log_loss_radius", dtype=dtype)
     obs_ci, obs_pi, feats = [], [], []
     for o, obs in enumerate(ba.observations):
         cam = ba.cameras[obs.camera_index]
-        objective.add(th.eb.Reprojection(camera_pose=cams[obs.camera_index], world_point=points[int(obs.point_index)],
-                                         focal_length=cam.focal_length, calib_k1=cam.calib_k1, calib_k2=cam.calib_k2,
-                                         image_feature_point=obs.image_feature_point, weight=weight, name=f"reproj_{o}"))
+        cf = th.eb.Reprojection(camera_pose=cams[obs.camera_index], world_point=points[int(obs.point_index)],
+                                focal_length=cam.focal_length, calib_k1=cam.calib_k1, calib_k2=cam.calib_k2,
+                                image_feature_point=obs.image_feature_point, weight=weight, name=f"reproj_{o}")
+        if robust:  # examples/bundle_adjustment.py:122-128 (HuberLoss, log_loss_radius = 0)
+            cf = th.RobustCostFunction(cf, th.HuberLoss, log_loss_radius, name=f"robust_{cf.name}")
+        objective.add(cf)
         obs_ci.append(obs.camera_index); obs_pi.append(int(obs.point_index)); feats.append(obs.image_feature_point.tensor.numpy())
     zero_point3 = th.Point3(dtype=dtype, name="zero_point")
     identity_se3 = th.SE3(dtype=dtype, name="zero_se3")
@@ -258,7 +269,7 @@ def make_ba(th, name, num_cameras, num_points, B, seed, iters):
                known=np.array(known), known_pose=np.stack([ba.gt_cameras[i].pose.tensor.numpy() for i in known], 0),
                order=np.array(order), reg_order=np.array(reg_order),
                A_row_ptr=sp.A_row_ptr.astype(np.int64), A_col_ind=sp.A_col_ind.astype(np.int64),
-               A_val0=sp.A_val.numpy().copy(), b0=sp.b.numpy().copy())
+               A_val0=sp.A_val.numpy().copy(), b0=sp.b.numpy().copy(), robust=np.array("huber" if robust else ""))
     tr = dict(delta=[], err=[], lam=[])
 
     def cb(optimizer, info, delta, it):
@@ -373,3 +384,6 @@ if __name__ == "__main__":
     make_ba(th, "ba_small_lm", num_cameras=6, num_points=40, B=3, seed=7, iters=8)
     make_simple_example(th)
     make_se2(th)
+    make_ba(th, "ba_small_huber", num_cameras=6, num_points=40, B=3, seed=8, iters=8, robust=True)
+    make_pgo(th, "pgo_small_welsch", num_poses=10, B=3, seed=9, iters=8, lm_kwargs=lm, loop_closure_ratio=0.6, robust="welsch",
+             outlier_ratio=0.3, init_perturb=0.0)

@@ -17,9 +17,13 @@ def pgo_spec(g, dtype=np.float64):
     spec = dict(dtype=np.dtype(dtype), vars=[], costs=[])
     for i in range(poses0.shape[0]):
         spec["vars"].append(dict(kind="SE3", dof=6, value=poses0[i].astype(dtype)))
+    robust = str(g["robust"]) if "robust" in g.files else ""
     for e in range(edges.shape[0]):
-        spec["costs"].append(dict(kind="between", group="SE3", vars=(int(edges[e, 0]), int(edges[e, 1])),
-                                  aux=meas[e].astype(dtype), weight=("diag", edge_w[e].astype(dtype))))
+        c = dict(kind="between", group="SE3", vars=(int(edges[e, 0]), int(edges[e, 1])),
+                 aux=meas[e].astype(dtype), weight=("diag", edge_w[e].astype(dtype)))
+        if robust:
+            c["robust"] = (robust, g["log_loss_radius"].astype(dtype))
+        spec["costs"].append(c)
     spec["costs"].append(dict(kind="local", group="SE3", vars=(0,), aux=poses0[0].astype(dtype),
                               weight=("scale", np.full((1, 1), float(g["prior_w"]), dtype=dtype))))
     return spec
@@ -32,11 +36,16 @@ def pgo_objective(th, g, device="cuda", dtype=None):
     poses0, edges, meas, edge_w = g["poses0"], g["edges"], g["meas"], g["edge_w"]
     poses = [th.SE3(tensor=torch.from_numpy(poses0[i]).to(dtype), name=f"VERTEX_SE3__{i}") for i in range(poses0.shape[0])]
     objective = th.Objective(dtype=dtype)
+    robust = str(g["robust"]) if "robust" in g.files else ""
+    llr = th.Vector(tensor=torch.from_numpy(g["log_loss_radius"]).to(dtype), name="log_loss_radius") if robust else None
     for e in range(edges.shape[0]):
         i, j = int(edges[e, 0]), int(edges[e, 1])
         z = th.SE3(tensor=torch.from_numpy(meas[e]).to(dtype), name=f"EDGE_SE3__{e}_{i}_{j}")
         w = th.DiagonalCostWeight(th.Variable(torch.from_numpy(edge_w[e]).to(dtype), name=f"EDGE_WEIGHT__{e}"))
-        objective.add(th.Between(poses[i], poses[j], z, w, name=f"between_{e}"))
+        cf = th.Between(poses[i], poses[j], z, w, name=f"between_{e}")
+        if robust:
+            cf = th.RobustCostFunction(cf, th.WelschLoss, llr, name=f"robust_between_{e}")
+        objective.add(cf)
     prior = th.Difference(poses[0], th.SE3(tensor=torch.from_numpy(poses0[0]).to(dtype), name="VERTEX_SE3__0__PRIOR"),
                           th.ScaleCostWeight(torch.tensor(float(g["prior_w"]), dtype=dtype)), name="prior")
     objective.add(prior)
@@ -81,8 +90,11 @@ def ba_spec(g, dtype=np.float64):
     one = np.ones((1, 1), dtype=dtype)
     for o in range(g["obs_cam"].shape[0]):
         c, p = int(g["obs_cam"][o]), int(g["obs_pt"][o])
-        spec["costs"].append(dict(kind="reproj", vars=(idx[f"Cam{c}_pose"], idx[f"Pt{p}"]),
-                                  aux=dict(f=g["focal"][c], z=g["feats"][o], k1=g["k1"][c], k2=g["k2"][c]), weight=("scale", one)))
+        cd = dict(kind="reproj", vars=(idx[f"Cam{c}_pose"], idx[f"Pt{p}"]),
+                  aux=dict(f=g["focal"][c], z=g["feats"][o], k1=g["k1"][c], k2=g["k2"][c]), weight=("scale", one))
+        if "robust" in g.files and str(g["robust"]):
+            cd["robust"] = (str(g["robust"]), np.zeros((1, 1), dtype=dtype))
+        spec["costs"].append(cd)
     w = np.full((1, 1), np.sqrt(1e-4), dtype=dtype)
     eye = np.eye(3, 4, dtype=dtype)[None]
     for n in [str(x) for x in g["reg_order"]]:
@@ -110,9 +122,14 @@ def ba_objective(th, g, device="cuda"):
     weight = th.ScaleCostWeight(th.Variable(torch.ones(1, 1, dtype=dtype), name="reproj_weight"))
     for o in range(g["obs_cam"].shape[0]):
         c, p = int(g["obs_cam"][o]), int(g["obs_pt"][o])
-        objective.add(th.eb.Reprojection(camera_pose=cams[c], world_point=pts[p], focal_length=focal[c], calib_k1=k1[c], calib_k2=k2[c],
-                                         image_feature_point=th.Point2(tensor=torch.from_numpy(g["feats"][o]), name=f"Feat{o}"),
-                                         weight=weight, name=f"reproj_{o}"))
+        cf = th.eb.Reprojection(camera_pose=cams[c], world_point=pts[p], focal_length=focal[c], calib_k1=k1[c], calib_k2=k2[c],
+                                image_feature_point=th.Point2(tensor=torch.from_numpy(g["feats"][o]), name=f"Feat{o}"),
+                                weight=weight, name=f"reproj_{o}")
+        if "robust" in g.files and str(g["robust"]):
+            if o == 0:
+                huber_radius = th.Vector(tensor=torch.zeros(1, 1, dtype=dtype), name="log_loss_radius")
+            cf = th.RobustCostFunction(cf, th.HuberLoss, huber_radius, name=f"robust_reproj_{o}")
+        objective.add(cf)
     zero_point3 = th.Point3(tensor=torch.zeros(1, 3, dtype=dtype), name="zero_point")
     identity_se3 = th.SE3(tensor=torch.eye(3, 4, dtype=dtype).view(1, 3, 4), name="zero_se3")
     damping_weight = th.ScaleCostWeight(th.Variable(torch.full((1, 1), float(np.sqrt(1e-4)), dtype=dtype), name="reg_weight"))

@@ -11,8 +11,9 @@ from helpers import load, ba_objective, ba_spec, lm_kwargs_of, decisive_iteratio
 pytestmark = pytest.mark.gpu
 
 
-def test_ba_linearization_matches_reference():
-    g = load("ba_small_lm")
+@pytest.mark.parametrize("name", ["ba_small_lm", "ba_small_huber"])
+def test_ba_linearization_matches_reference(name):
+    g = load(name)
     objective, cams, pts = ba_objective(th, g)
     lin = th.SparseLinearization(objective)
     assert [v.name for v in lin.ordering] == [str(x) for x in g["order"]]
@@ -24,9 +25,10 @@ def test_ba_linearization_matches_reference():
     np.testing.assert_allclose(objective.error_metric().cpu().numpy(), nls.error_metric(spec, [v["value"] for v in spec["vars"]]), rtol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["ba_small_lm", "ba_small_huber"])
 @pytest.mark.parametrize("solver", ["dense", "sparse"])
-def test_ba_lm_trace(solver):
-    g = load("ba_small_lm")
+def test_ba_lm_trace(solver, name):
+    g = load(name)
     method, iters, kw = lm_kwargs_of(g)
     objective, cams, pts = ba_objective(th, g)
     if solver == "dense":

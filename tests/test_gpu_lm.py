@@ -33,7 +33,7 @@ def _run(g, track=True):
     return method, iters, kw, values, info, trace, poses, inputs
 
 
-@pytest.mark.parametrize("name", ["pgo_small_lm", "pgo_small_gn", "pgo_small_lm_sph", "pgo64_lm", "pgo_small_lm_hard", "pgo32_lm_hard"])
+@pytest.mark.parametrize("name", ["pgo_small_lm", "pgo_small_gn", "pgo_small_lm_sph", "pgo64_lm", "pgo_small_lm_hard", "pgo32_lm_hard", "pgo_small_welsch"])
 def test_trace_vs_reference(name):
     g = load(name)
     method, iters, kw, values, info, trace, poses, inputs = _run(g)

@@ -1,13 +1,15 @@
 """Oracle vs the reference on the bundle-adjustment fixture (Reprojection + Difference on SE3 / Point3): CSR structure
 bit-exact, linearization, and the complete LM trace."""
 import numpy as np
+import pytest
 
 from oracle import nls
 from helpers import load, ba_spec, lm_kwargs_of, decisive_iterations
 
 
-def test_ba_structure_and_linearization():
-    g = load("ba_small_lm")
+@pytest.mark.parametrize("name", ["ba_small_lm", "ba_small_huber"])
+def test_ba_structure_and_linearization(name):
+    g = load(name)
     spec = ba_spec(g)
     st = nls.sparse_structure(spec)
     assert np.array_equal(st["A_row_ptr"], g["A_row_ptr"]) and np.array_equal(st["A_col_ind"], g["A_col_ind"])
@@ -16,8 +18,9 @@ def test_ba_structure_and_linearization():
     np.testing.assert_allclose(b, g["b0"], rtol=1e-9, atol=1e-9)
 
 
-def test_ba_lm_trace():
-    g = load("ba_small_lm")
+@pytest.mark.parametrize("name", ["ba_small_lm", "ba_small_huber"])
+def test_ba_lm_trace(name):
+    g = load(name)
     method, iters, kw = lm_kwargs_of(g)
     spec = ba_spec(g)
     out = nls.optimize(spec, method=method, max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0, **kw)

@@ -18,7 +18,8 @@ class CostGroup(C.Structure):
     _fields_ = [("kind", c_i32), ("weight_kind", c_i32), ("K", c_i32), ("dim", c_i32),
                 ("x0", c_vp), ("x1", c_vp), ("aux", c_vp), ("w", c_vp), ("bstride", c_vp),
                 ("a_off", c_vp), ("a_stride", c_vp), ("bp", c_vp), ("row0", c_vp),
-                ("aux2", c_vp), ("aux3", c_vp), ("aux4", c_vp), ("bstride2", c_vp)]
+                ("aux2", c_vp), ("aux3", c_vp), ("aux4", c_vp), ("bstride2", c_vp),
+                ("robust_kind", c_i32), ("reserved0", c_i32), ("log_radius", c_vp), ("bstride_lr", c_vp)]
 
 
 class VarTable(C.Structure):

@@ -211,6 +211,54 @@ class Reprojection(CostFunction):
         return COST_REPROJECTION, [self.focal_length, self.image_feature_point, self.calib_k1, self.calib_k2]
 
 
+class RobustLoss:
+    """theseus/core/robust_loss.py:13-30 (only the kind is needed on the host; the formulas live in thb_costs.cu)."""
+    ROBUST_KIND = 0
+
+
+class WelschLoss(RobustLoss):
+    """robust_loss.py:33-41."""
+    ROBUST_KIND = 1
+
+
+class HuberLoss(RobustLoss):
+    """robust_loss.py:43-52."""
+    ROBUST_KIND = 2
+
+
+class RobustCostFunction(CostFunction):
+    """theseus/core/robust_cost_function.py:16-160: wraps a cost function; linearisation rescales J and e by
+    sqrt(rho'(||w e||^2) + 1e-20), the error metric sees rho(||w e||^2).  Fused into the wrapped schema's kernels."""
+
+    def __init__(self, cost_function: CostFunction, loss_cls, log_loss_radius: Variable, flatten_dims: bool = False,
+                 name: Optional[str] = None):
+        if flatten_dims:
+            raise NotImplementedError("RobustCostFunction(flatten_dims=True) is not built in theseus_b200 r1")
+        if not (isinstance(loss_cls, type) and issubclass(loss_cls, RobustLoss) and loss_cls.ROBUST_KIND > 0):
+            raise NotImplementedError("supported robust losses: WelschLoss, HuberLoss")
+        self.cost_function = cost_function
+        super().__init__(cost_function.weight, name=name)
+        for attr in cost_function._optim_vars_attr_names:
+            setattr(self, attr, getattr(cost_function, attr))
+            self._optim_vars_attr_names.append(attr)
+        for attr in cost_function._aux_vars_attr_names:
+            setattr(self, attr, getattr(cost_function, attr))
+            self._aux_vars_attr_names.append(attr)
+        self.log_loss_radius = log_loss_radius
+        self._aux_vars_attr_names.append("log_loss_radius")
+        self.loss = loss_cls()
+        self.robust_kind = loss_cls.ROBUST_KIND
+
+    def dim(self) -> int:
+        return self.cost_function.dim()
+
+    def schema(self):
+        kind, aux = self.cost_function.schema()
+        if kind == COST_LOCAL_VECTOR or kind is None:
+            raise NotImplementedError("RobustCostFunction over Vector differences / AutoDiff costs is not built in theseus_b200 r1")
+        return kind, aux
+
+
 class AutoDiffCostFunction(CostFunction):
     """theseus/core/cost_function.py:203-420: user-defined error function, Jacobians by vmap(jacrev(err_fn)) -- kept as the
     reference's torch.func path; the results are scattered straight into the batched-CSR Jacobian.

@@ -30,6 +30,9 @@ template <typename T> struct GroupDev {
   const T* const* aux3;
   const T* const* aux4;
   const int32_t* bstride2;
+  int robust_kind;
+  const T* const* log_radius;
+  const int32_t* bstride_lr;
 };
 
 template <typename T> static GroupDev<T> to_dev(const thb_cost_group* g) {
@@ -51,7 +54,35 @@ template <typename T> static GroupDev<T> to_dev(const thb_cost_group* g) {
   d.aux3 = reinterpret_cast<const T* const*>(g->aux3);
   d.aux4 = reinterpret_cast<const T* const*>(g->aux4);
   d.bstride2 = g->bstride2;
+  d.robust_kind = g->robust_kind;
+  d.log_radius = reinterpret_cast<const T* const*>(g->log_radius);
+  d.bstride_lr = g->bstride_lr;
   return d;
+}
+
+// Robust wrapper (theseus/core/robust_cost_function.py:87-135; losses robust_loss.py:33-52; _EPS = _LOSS_EPS = 1e-20).
+// x = squared norm of the weighted error.  linearize: rescale = sqrt(rho'(x) + eps) applied to J and e;
+// evaluate: the error metric sees rho(x) (+ dim*eps) instead of x.
+template <typename T> __device__ __forceinline__ T t_exp(T x);
+template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+template <typename T> __device__ __forceinline__ T robust_radius(const GroupDev<T>& g, int k, int64_t b) {
+  return t_exp((g.log_radius[k] + (int64_t)g.bstride_lr[k] * b)[0]);
+}
+template <typename T> __device__ __forceinline__ T robust_rescale(const GroupDev<T>& g, int k, int64_t b, T x) {
+  const T radius = robust_radius(g, k, b);
+  T lin;
+  if (g.robust_kind == THB_ROBUST_WELSCH) lin = t_exp(-x / (radius + T(1e-20)));
+  else lin = t_sqrt(radius / (x > radius ? x : radius) + T(1e-20));
+  return t_sqrt(lin + T(1e-20));
+}
+template <typename T> __device__ __forceinline__ T robust_value(const GroupDev<T>& g, int k, int64_t b, T x, int dim) {
+  const T radius = robust_radius(g, k, b);
+  T val;
+  if (g.robust_kind == THB_ROBUST_WELSCH) val = radius - radius * t_exp(-x / (radius + T(1e-20)));
+  else val = (x > radius) ? (T(2) * t_sqrt(radius * (x > radius ? x : radius) + T(1e-20)) - radius) : x;
+  // the reference spreads rho over `dim` entries sqrt(rho/dim + eps); their squares sum to rho + dim*eps
+  return val + T(dim) * T(1e-20);
 }
 
 template <typename T, int N> __device__ __forceinline__ void load_n(const T* p, T* r) {
@@ -246,6 +277,16 @@ __global__ void __launch_bounds__(128) linearize_kernel(GroupDev<T> g, int64_t B
   } else {
     so3_cost<T, true, BETWEEN>(g, k, b, w, e, J0, J1);
   }
+  if (g.robust_kind != THB_ROBUST_NONE && !masked) {
+    T x = T(0);
+#pragma unroll
+    for (int r = 0; r < DIM; r++) x += e[r] * e[r];
+    const T sc = robust_rescale(g, k, b, x);
+#pragma unroll
+    for (int r = 0; r < DIM; r++) e[r] *= sc;
+#pragma unroll
+    for (int i = 0; i < DIM * DIM; i++) { J0[i] *= sc; if (BETWEEN) J1[i] *= sc; }
+  }
   T* Arow = A_val + b * nnz + g.a_off[k];
   const int stride = g.a_stride[k];
   const int bp0 = g.bp[k * 2 + 0];
@@ -331,6 +372,15 @@ __global__ void __launch_bounds__(128) linearize_reprojection_kernel(GroupDev<T>
     for (int i = 0; i < 6; i++) Jp[i] = T(0);
   } else {
     reprojection_cost<T, true>(g, k, b, w, e, Jc, Jp);
+    if (g.robust_kind != THB_ROBUST_NONE) {
+      const T sc = robust_rescale(g, k, b, e[0] * e[0] + e[1] * e[1]);
+      e[0] *= sc;
+      e[1] *= sc;
+#pragma unroll
+      for (int i = 0; i < 12; i++) Jc[i] *= sc;
+#pragma unroll
+      for (int i = 0; i < 6; i++) Jp[i] *= sc;
+    }
   }
   T* Arow = A_val + b * nnz + g.a_off[k];
   const int stride = g.a_stride[k];
@@ -360,7 +410,8 @@ __global__ void __launch_bounds__(128) error_reprojection_kernel(GroupDev<T> g, 
     T w[2], e[2];
     if (load_weight<T, 2>(g, k, b, w)) continue;
     reprojection_cost<T, false>(g, k, b, w, e, nullptr, nullptr);
-    acc += e[0] * e[0] + e[1] * e[1];
+    const T x = e[0] * e[0] + e[1] * e[1];
+    acc += (g.robust_kind != THB_ROBUST_NONE) ? robust_value(g, k, b, x, 2) : x;
   }
   partial[(int64_t)c * B + b] = acc * T(0.5);
 }
@@ -407,8 +458,10 @@ __global__ void __launch_bounds__(128) error_kernel(GroupDev<T> g, int64_t B, T*
     if (DIM == 6) se3_cost<T, false, BETWEEN>(g, k, b, w, e, nullptr, nullptr);
     else if (IS_SE2) se2_cost<T, false, BETWEEN>(g, k, b, w, e, nullptr, nullptr);
     else so3_cost<T, false, BETWEEN>(g, k, b, w, e, nullptr, nullptr);
+    T x = T(0);
 #pragma unroll
-    for (int r = 0; r < DIM; r++) acc += e[r] * e[r];
+    for (int r = 0; r < DIM; r++) x += e[r] * e[r];
+    acc += (g.robust_kind != THB_ROBUST_NONE) ? robust_value(g, k, b, x, DIM) : x;
   }
   partial[(int64_t)c * B + b] = acc * T(0.5);
 }

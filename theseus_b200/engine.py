@@ -72,12 +72,13 @@ class Engine:
             if kind is None:
                 self.generic.append(f)
                 continue
-            key = (kind, cf.weight.WEIGHT_KIND, cf.dim())
+            key = (kind, cf.weight.WEIGHT_KIND, cf.dim(), int(getattr(cf, "robust_kind", 0)))
             groups.setdefault(key, []).append(f)
         self.groups: List[_Group] = []
         dev = self.device
-        for (kind, wkind, dim), idx in groups.items():
+        for (kind, wkind, dim, robust), idx in groups.items():
             g = _Group(kind, wkind, dim, idx)
+            g.robust = robust
             ii = np.array(idx, dtype=np.int64)
             bp = np.zeros((g.K, 2), dtype=np.int32)
             for r, f in enumerate(idx):
@@ -214,13 +215,21 @@ class Engine:
             ex = [self._ptr_array(extra[q]) if n_extra > q else None for q in range(3)]
             keep["extra"] = ex
             keep["bstride2"] = _dev(bs2, self.device)
+            lr_ptr = lr_bs = None
+            if g.robust:
+                lrs = [aux_tensor(self.costs[f].log_loss_radius) for f in g.cost_indices]
+                lr_ptr = self._ptr_array(lrs)
+                lr_bs = _dev(np.array([bstride(t) for t in lrs], dtype=np.int32), self.device)
+                keep["lr"] = (lrs, lr_ptr, lr_bs)
             st = _lib.CostGroup(
                 kind=g.kind, weight_kind=g.weight_kind, K=g.K, dim=g.dim,
                 x0=keep["x0"].data_ptr(), x1=keep["x1"].data_ptr(), aux=keep["aux"].data_ptr(), w=keep["w"].data_ptr(),
                 bstride=keep["bstride"].data_ptr(), a_off=g.static["a_off"].data_ptr(),
                 a_stride=g.static["a_stride"].data_ptr(), bp=g.static["bp"].data_ptr(), row0=g.static["row0"].data_ptr(),
                 aux2=ex[0].data_ptr() if ex[0] is not None else None, aux3=ex[1].data_ptr() if ex[1] is not None else None,
-                aux4=ex[2].data_ptr() if ex[2] is not None else None, bstride2=keep["bstride2"].data_ptr())
+                aux4=ex[2].data_ptr() if ex[2] is not None else None, bstride2=keep["bstride2"].data_ptr(),
+                robust_kind=g.robust, reserved0=0, log_radius=lr_ptr.data_ptr() if lr_ptr is not None else None,
+                bstride_lr=lr_bs.data_ptr() if lr_bs is not None else None)
             g.bound[which] = (st, keep)
         # NOTE: _bind may itself rebind non-contiguous tensors (bumping the counter); read it afterwards.
         self._bind_stamp[which] = Variable._global_updates
