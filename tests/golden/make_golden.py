@@ -368,6 +368,24 @@ def make_se2(th):
     print("se2_kat.npz pose-graph err", out["pg_err0"], "->", out["pg_trace_err"][-1])
 
 
+def make_so3(th):
+    """SO3 Between / Difference Jacobians + a retract KAT from the reference (theseus/geometry/so3.py, torchlie so3_impl.py)."""
+    import torch
+    torch.manual_seed(21)
+    dt = torch.float64
+    B = 20
+    X0, X1, Z = th.SO3.rand(B, dtype=dt), th.SO3.rand(B, dtype=dt), th.SO3.rand(B, dtype=dt)
+    w = torch.rand(1, 3, dtype=dt) + 0.5
+    (J0, J1), e = th.Between(X0, X1, Z, th.DiagonalCostWeight(w)).weighted_jacobians_error()
+    (Jl,), el = th.Difference(X0, Z, th.ScaleCostWeight(torch.tensor(1.3, dtype=dt))).weighted_jacobians_error()
+    delta = 0.3 * torch.randn(B, 3, dtype=dt)
+    R = X0.retract(delta)
+    np.savez_compressed(os.path.join(HERE, "so3_kat.npz"), X0=X0.tensor.numpy(), X1=X1.tensor.numpy(), Z=Z.tensor.numpy(), w=w.numpy(),
+                        between_J0=J0.numpy(), between_J1=J1.numpy(), between_e=e.numpy(), local_J=Jl.numpy(), local_e=el.numpy(),
+                        delta=delta.numpy(), retract=R.tensor.numpy())
+    print("so3_kat.npz")
+
+
 if __name__ == "__main__":
     th, lieF = _import_reference()
     make_lie(th, lieF)
@@ -384,6 +402,7 @@ if __name__ == "__main__":
     make_ba(th, "ba_small_lm", num_cameras=6, num_points=40, B=3, seed=7, iters=8)
     make_simple_example(th)
     make_se2(th)
+    make_so3(th)
     make_ba(th, "ba_small_huber", num_cameras=6, num_points=40, B=3, seed=8, iters=8, robust=True)
     make_pgo(th, "pgo_small_welsch", num_poses=10, B=3, seed=9, iters=8, lm_kwargs=lm, loop_closure_ratio=0.6, robust="welsch",
              outlier_ratio=0.3, init_perturb=0.0)
