@@ -38,6 +38,21 @@ def test_dense_linearization_matches_reference():
     np.testing.assert_allclose(d.cpu().numpy(), g["trace_AtA_diag"][0], rtol=1e-9, atol=1e-8)
 
 
+def test_dense_ata_exact_over_repeated_linearizations():
+    """The zero background of AtA is written once per buffer; every later linearization must still give A^T A exactly
+    (pattern blocks are overwritten, nothing accumulates), also after the variables moved."""
+    g = load("pgo_small_lm")
+    objective, poses = pgo_objective(th, g)
+    lin = th.DenseLinearization(objective)
+    for rep in range(3):
+        lin.linearize()
+        A = lin.A
+        ref = A.transpose(1, 2) @ A
+        np.testing.assert_allclose(lin.AtA.cpu().numpy(), ref.cpu().numpy(), rtol=1e-11, atol=1e-9)
+        for p in poses[1:4]:
+            p.update(th.SE3.exp_map(0.05 * torch.randn(p.shape[0], 6, dtype=p.dtype, device=p.device)).compose(p).tensor)
+
+
 def test_error_metric_and_retract_vs_oracle():
     g = load("pgo64_lm")
     objective, poses = pgo_objective(th, g)

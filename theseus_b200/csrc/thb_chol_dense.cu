@@ -84,6 +84,13 @@ __device__ __forceinline__ void tile_mma_cols(double& c0, double& c1, const doub
   for (int k4 = k4b; k4 < k4e; k4++) mma884(c0, c1, A[lr * lda + 4 * k4 + lc], M[(4 * k4 + lc) * ldm + lr]);
 }
 
+#ifdef THB_CHOL_TIMING
+__device__ long long thb_chol_timing[16 * 65536];
+#define THB_TICK(slot) do { if (threadIdx.x == 0 && blockIdx.x < 65536) thb_chol_timing[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#else
+#define THB_TICK(slot) do {} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // One warp: Cholesky of the 32x32 block at T (lower part; row stride SC) and its inverse, in registers
 // (one row / one column per lane; pivots and multipliers exchanged with warp shuffles).
@@ -145,12 +152,14 @@ __device__ __noinline__ int diag64_factor_invert(double* __restrict__ T, double*
   const int t0 = warp, t1 = warp + 8;
   const int rt0 = t0 >> 2, ct0 = t0 & 3, rt1 = t1 >> 2, ct1 = t1 & 3;
   double a0, a1, b0, b1;
-  // ---- block column 0 ----
-  if (warp == 0) {
+  // ---- block column 0 ----  (which warp runs the serial pivots makes no measurable difference: first and last tried)
+  constexpr int PIVOT_WARP = 0;
+  if (warp == PIVOT_WARP) {
     const int f = warp_potrf32_inv(T, Wd, lane);
     if (lane == 0 && f != 0) s_fail = f;
   }
   __syncthreads();
+  THB_TICK(8);
   // panel: L10 = T10 W00^T
   a0 = a1 = b0 = b1 = 0.0;
   tile_mma_rows(a0, a1, T + (32 + 8 * rt0) * SC, SC, Wd + (8 * ct0) * SB32, SB32, 0, 2 * ct0 + 2, lr, lc);
@@ -172,12 +181,14 @@ __device__ __noinline__ int diag64_factor_invert(double* __restrict__ T, double*
     *d1 = v1;
   }
   __syncthreads();
+  THB_TICK(9);
   // ---- block column 1 ----
-  if (warp == 0) {
+  if (warp == PIVOT_WARP) {
     const int f = warp_potrf32_inv(T + 32 * SC + 32, Wd + 32 * SB32, lane);
     if (lane == 0 && f != 0 && s_fail == 0) s_fail = 32 + f;
   }
   __syncthreads();
+  THB_TICK(10);
   // ---- store L_jj (lower part; zeros above) ----
   for (int e = tid; e < 64 * 64; e += CHOL_THREADS) {
     const int r = e >> 6, c = e & 63;
@@ -204,6 +215,7 @@ __device__ __noinline__ int diag64_factor_invert(double* __restrict__ T, double*
   *reinterpret_cast<double2*>(&T[(32 + 8 * rt0 + lr) * SC + 8 * ct0 + 2 * lc]) = make_double2(-a0, -a1);
   *reinterpret_cast<double2*>(&T[(32 + 8 * rt1 + lr) * SC + 8 * ct1 + 2 * lc]) = make_double2(-b0, -b1);
   __syncthreads();
+  THB_TICK(11);
   for (int e = tid; e < 64 * 64; e += CHOL_THREADS) {
     const int r = e >> 6, c = e & 63;
     Wg[e] = (c <= r) ? T[r * SC + c] : 0.0;
@@ -259,6 +271,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   const int lr = lane >> 2, lc = lane & 3;
 
   // ---------------- phase A: acc = sum_k L[rows,k] L[cols,k]^T ----------------
+  THB_TICK(0);
   // The accumulators start at -(AtA tile with the LM damping fused on the diagonal): the global loads are in flight
   // while the cp.async pipeline fills, and C = AtA - sum L L^T is simply -acc at the end (AtA is read exactly once).
   double acc[4][4][2];
@@ -295,6 +308,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
     __syncthreads();
   }
 
+  THB_TICK(1);
   const int nk = j * (TN / KB);
   const bool skip_mma = is_diag && (wm * 32 < roff);  // odd block columns: the upper 64 rows of the diagonal tile lie above the diagonal
   const double* Arow = Lb + (int64_t)i * TM * np;
@@ -340,6 +354,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
     __syncthreads();
   }
 
+  THB_TICK(2);
   // ---------------- phase B: C = -acc, to shared memory ----------------
   double* Cs = smem;
 #pragma unroll
@@ -353,6 +368,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   }
   __syncthreads();
 
+  THB_TICK(3);
   double* Wj = p.W + ((int64_t)b * p.nb + j) * TN * TN;
   int* flag = p.flags + b * p.nb + j;
   int row_lo = 0;  // first tile row that still needs the TRSM of phase D
@@ -376,6 +392,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
     __syncthreads();
   }
 
+  THB_TICK(4);
   // ---------------- phase D: L[rows,j] = C W^T (DMMA, triangular k-range) ----------------
   double* Ws = smem + TM * SC;
   double acc2[2][8][2];
@@ -430,10 +447,12 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
       }
     }
   }
+  THB_TICK(5);
   // publish: this row tile has one more finished block column
   __threadfence();
   __syncthreads();
   if (tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p.done + b * p.ntr + i), "r"(1) : "memory");
+  THB_TICK(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -641,6 +660,12 @@ int thb_potrs_f64(const double* rhs, double* x, int64_t B, int64_t n, const void
   THB_CHECK_LAUNCH();
   return THB_OK;
 }
+
+#ifdef THB_CHOL_TIMING
+int thb_debug_chol_timing(long long* host_out, int64_t count) {
+  return (int)cudaMemcpyFromSymbol(host_out, thb::thb_chol_timing, sizeof(long long) * count);
+}
+#endif
 
 int thb_potrf_potrs_f64(const double* AtA, const double* rhs, const double* alpha, const double* beta, double* x, int32_t* info,
                         int64_t B, int64_t n, void* workspace, int64_t workspace_bytes, thb_stream_t stream) {

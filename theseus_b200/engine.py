@@ -104,6 +104,7 @@ class Engine:
         self._bind_stamp = {"cur": -1, "tmp": -1}
         self._vt = None
         self._gram_dense = None
+        self._zero_filled = None  # (data_ptr, numel) of the AtA buffer whose off-pattern entries are known to be zero
         self._bufs = {}
 
     # ------------------------------------------------------------------ pools / bindings
@@ -334,11 +335,18 @@ class Engine:
         return self._gram_dense[0]
 
     def gram_dense(self, A_val, b, AtA, Atb, diag):
-        """AtA [B,n,n] (zero-filled then block scatter), Atb [B,n], diag(AtA) [B,n]."""
+        """AtA [B,n,n] (block scatter over a zero background), Atb [B,n], diag(AtA) [B,n].
+
+        The block pattern of AtA is fixed by the objective's structure and the Gram kernel overwrites every pattern
+        block, so the 8*B*n^2-byte zero fill (4.8 GB, ~1.9 ms at C2) is paid once per buffer, not once per iteration.
+        Nothing downstream writes AtA (the damping is fused into the factorisation's load)."""
         B = self.batch_size
         s = _lib.stream_ptr()
         plan = self.gram_plan_dense()
-        _lib.check(self.lib.thb_fill_zero(_lib.ptr(AtA), AtA.numel() * AtA.element_size(), s), "fill_zero")
+        key = (AtA.data_ptr(), AtA.numel())
+        if self._zero_filled != key:
+            _lib.check(self.lib.thb_fill_zero(_lib.ptr(AtA), AtA.numel() * AtA.element_size(), s), "fill_zero")
+            self._zero_filled = key
         _lib.check(getattr(self.lib, f"thb_gram_{self.sfx}")(C.byref(plan), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, _lib.ptr(AtA),
                                                                self.n * self.n, _lib.ptr(Atb), _lib.ptr(diag), s), "gram")
 
