@@ -169,6 +169,10 @@ typedef struct thb_gram_plan {
   const int32_t* cc_stride;   /* device [NCC] */
   const int32_t* cc_rows;     /* device [NCC] */
   const int32_t* cc_row0;     /* device [NCC] first row in b */
+  /* per-block view (block-per-thread kernels: thb_sparse_lane_gram_f64) */
+  int64_t num_blocks;         /* NB */
+  const int32_t* blk_rows;    /* device [NB] rows of the block (its columns are blk_ld for packed block storage) */
+  const int32_t* blk_cols;    /* device [NB] columns of the block */
 } thb_gram_plan;
 
 /* out[b*out_bstride + ...] receives the blocks (dense AtA: out_bstride = n*n, caller pre-zeroes via
@@ -247,6 +251,54 @@ int thb_sparse_solve_f64(const thb_sparse_plan* p, const double* factor, const d
                          double* work, int64_t B, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Block-sparse Cholesky, batch-lane layout (thb_sparse_lane.cu): the same four BaSpaCho operations
+ * (add_MtM / damp / factor / solve, extlib/baspacho_solver.cpp:93-257) for large batches.  The factor storage is
+ * INTERLEAVED over the batch: element e of item b lives at factor[e * Bp + b], Bp = thb_sparse_lane_padded_batch(B)
+ * (B rounded up to 32), so one warp runs one block operation for 32 batch items with coalesced accesses.
+ *   factor [data_size, Bp] fp64   same per-item element order as thb_sparse_plan (blocks of L, row-major)
+ *   diagl  [diag_size, Bp] fp64   Cholesky factors of the diagonal blocks (row-major d x d, RECIPROCAL diagonal)
+ *   work   [n, Bp]         fp64   permuted right-hand side / solution
+ * Block sizes must be in {1,2,3,6} (THB_ERR_UNSUPPORTED otherwise: use the thb_sparse_plan entry points).
+ * `launches` is a HOST array [num_launches][5] = (kind, di, dj, begin, end) in execution order (level by level;
+ * kinds below); every other pointer is a device array.  Elimination-tree levels are separate kernel launches.
+ * ---------------------------------------------------------------------------------------------- */
+enum { THB_LANE_U = 0, THB_LANE_T = 1, THB_LANE_S = 2, THB_LANE_UH = 3 };
+typedef struct thb_sparse_lane_plan {
+  int64_t N;            /* number of variable blocks */
+  int64_t n;            /* scalar dimension */
+  int64_t data_size;    /* doubles per batch item in `factor` */
+  int64_t diag_size;    /* doubles per batch item in `diagl` (sum of d^2) */
+  int64_t num_launches;
+  const int32_t* launches;  /* HOST [num_launches,5] */
+  const int32_t* dims;      /* [N] block size per elimination position */
+  const int32_t* col_start; /* [N] first scalar column (ORIGINAL order) */
+  const int32_t* pstart;    /* [N] first scalar index in the permuted vector */
+  const int64_t* dl_off;    /* [N] offset of the diagonal factor in diagl */
+  const int64_t* diag_off;  /* [N] offset of the diagonal block in factor */
+  const int64_t* up_a; const int64_t* up_b; const int32_t* up_k;    /* update pairs (offset of L_ik, of L_jk, dk) */
+  const int64_t* u_tgt; const int64_t* u_p0; const int64_t* u_p1;   /* U items: target offset, pair range */
+  const int64_t* t_off; const int64_t* t_diag; const int64_t* t_dl; /* T items: block, its column's diagonal block, diagl slot */
+  const int32_t* t_pstart;                                          /*          first permuted scalar of the column (info) */
+  const int32_t* s_col;                                             /* S items: columns */
+  /* row lists (forward substitution): per column j the blocks L_jk: offset, first permuted scalar of k, dim of k */
+  const int64_t* fr_ptr; const int64_t* fr_off; const int32_t* fr_p; const int32_t* fr_d;
+  /* column lists (backward substitution): per column j the blocks L_ij: offset, first permuted scalar of i, dim of i */
+  const int64_t* bc_ptr; const int64_t* bc_off; const int32_t* bc_p; const int32_t* bc_d;
+} thb_sparse_lane_plan;
+
+int64_t thb_sparse_lane_padded_batch(int64_t B);
+/* add_MtM: AtA blocks -> factor (lane layout); the caller zero-fills factor first (fill-in blocks start at 0) */
+int thb_sparse_lane_gram_f64(const thb_gram_plan* g, int64_t B, const double* A_val, int64_t nnz, double* factor, thb_stream_t stream);
+int thb_sparse_lane_damp_f64(const thb_sparse_lane_plan* p, double* factor, const double* alpha, const double* beta, int64_t B,
+                             thb_stream_t stream);
+/* info[b] = 0 or 1 + permuted index of a non-positive pivot */
+int thb_sparse_lane_factor_f64(const thb_sparse_lane_plan* p, double* factor, double* diagl, int32_t* info, int64_t B,
+                               thb_stream_t stream);
+/* rhs, x: [B, n] row-major in the ORIGINAL variable order (scramble / unscramble folded into the substitutions) */
+int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs,
+                              double* x, double* work, int64_t B, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Levenberg-Marquardt control (device-resident accept/reject + damping update).
  *   den = 1/2 sum_j d_j (lam_eff_j d_j + Atb_j), d = step*delta, lam_eff = lam*diag(AtA) if ellipsoidal else lam
  *   rho = (err_prev - err_new)/den ; reject = rho <= damping_accept
@@ -272,6 +324,21 @@ int thb_mat_vec_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t
                     const double* A_val, const double* v, double* y, thb_stream_t stream);
 int thb_tmat_vec_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* row_ptr, const int64_t* col_ind,
                      const double* A_val, const double* v, double* y, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of the linear solve x = (AtA + D)^-1 At b with respect to A_val [B,nnz] and b [B,m]
+ * (optimizer/autograd/common.py:11-48 compute_A_grad -- a Python loop over the m rows in the reference -- and
+ * the backward() of baspacho_sparse_autograd.py:117-168 / cholmod_sparse_autograd.py:64-110 / lu_cuda_sparse_autograd.py:86-155).
+ * H [B,n] = (AtA + D)^-1 grad_x is obtained by the caller with the factor of the forward pass (thb_potrs_f64 /
+ * thb_sparse_solve_f64 / thb_sparse_lane_solve_f64).  Then
+ *   b_grad[b,r]  = (A H)[r]
+ *   A_grad[b,k]  = (b - A x)[r] H[c] - (A H)[r] x[c] - 2 alpha_b H[c] x[c] A[k]        (entry k = (r,c))
+ * detach_hessian != 0 : A_grad[b,k] = b[r] H[c]  (the reference's _detach_hessian GN step).
+ * alpha may be NULL (no multiplicative damping); A_grad or b_grad may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int thb_solve_backward_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* row_ptr, const int64_t* col_ind,
+                           const double* A_val, const double* b, const double* x, const double* H, const double* alpha,
+                           int32_t detach_hessian, double* A_grad, double* b_grad, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone Lie-group kernels (torchlie.functional SE3 namespace, torchlie/functional/lie_group.py:332-366).

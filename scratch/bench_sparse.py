@@ -6,13 +6,14 @@ from theseus_b200.datasets import pose_graph_synthetic_3d, pose_graph_sphere, bu
 which = sys.argv[1] if len(sys.argv) > 1 else "c5"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 iters = 10
+layout = sys.argv[3] if len(sys.argv) > 3 else None
 t0 = time.time()
 data = pose_graph_sphere(50, 50, B) if which == "c5" else pose_graph_synthetic_3d(256, B)
 print("data", round(time.time() - t0, 1), "s", "edges", len(data["edges"]), flush=True)
 t0 = time.time()
 objective, poses = build_pose_graph_objective(th, data, torch.device("cuda", 0))
 opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
-                            max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0)
+                            max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0, linear_solver_kwargs=dict(layout=layout))
 print("objective+symbolic", round(time.time() - t0, 1), "s", opt.linear_solver.symbolic_stats, flush=True)
 kw = dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
 inputs = {p.name: data["poses"][i].cuda() for i, p in enumerate(poses)}

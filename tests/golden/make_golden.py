@@ -3,7 +3,9 @@
 Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 Writes small .npz files next to this script.  The fixtures pin oracle/ (tests/test_oracle_*.py,
-CPU) and the CUDA path (tests/test_gpu_*.py).  Nothing here is imported at test time.
+CPU) and the CUDA path (tests/test_gpu_*.py).  At test time only the pure problem builders backward_problem / backward_inputs /
+BACKWARD_CASES are loaded from this file (so generator and test build the same problem); the reference is imported under __main__ only.
+    python tests/golden/make_golden.py backward     # regenerates backward_kat.npz alone
 """
 import os
 import sys
@@ -386,8 +388,81 @@ def make_so3(th):
     print("so3_kat.npz")
 
 
+def backward_problem(th, torch, dtype=None):
+    """Shared by the generator (th = reference) and tests/test_gpu_backward.py (th = theseus_b200): exponential curve fit
+    y = a exp(b x) + c with optimisation variables ab (Vector 2), c (Vector 1), a data cost (AutoDiff, dim 12) and a prior on ab."""
+    dtype = dtype or torch.float64
+    N = 12
+    ab = th.Vector(2, name="ab", dtype=dtype)
+    c = th.Vector(1, name="c", dtype=dtype)
+    x = th.Variable(torch.zeros(1, N, dtype=dtype), name="x")
+    y = th.Variable(torch.zeros(1, N, dtype=dtype), name="y")
+    t = th.Variable(torch.zeros(1, 2, dtype=dtype), name="t")
+
+    def data_err(optim_vars, aux_vars):
+        p, cc = optim_vars
+        xx, yy = aux_vars
+        return yy.tensor - (p.tensor[:, 0:1] * torch.exp(p.tensor[:, 1:2] * xx.tensor) + cc.tensor)
+
+    def prior_err(optim_vars, aux_vars):
+        return optim_vars[0].tensor - aux_vars[0].tensor
+
+    objective = th.Objective(dtype=dtype)
+    objective.add(th.AutoDiffCostFunction([ab, c], data_err, N, aux_vars=[x, y], cost_weight=th.ScaleCostWeight(torch.tensor(1.0, dtype=dtype)), name="data"))
+    objective.add(th.AutoDiffCostFunction([ab], prior_err, 2, aux_vars=[t], cost_weight=th.ScaleCostWeight(torch.tensor(0.3, dtype=dtype)), name="prior"))
+    return objective
+
+
+def backward_inputs(torch, B=3, seed=21):
+    g = torch.Generator().manual_seed(seed)
+    N = 12
+    x = torch.linspace(-1, 1, N, dtype=torch.float64).repeat(B, 1) + 0.05 * torch.randn(B, N, generator=g, dtype=torch.float64)
+    a = 1.0 + 0.3 * torch.rand(B, 1, generator=g, dtype=torch.float64)
+    b = 0.5 + 0.3 * torch.rand(B, 1, generator=g, dtype=torch.float64)
+    y = a * torch.exp(b * x) + 0.2 + 0.02 * torch.randn(B, N, generator=g, dtype=torch.float64)
+    t = torch.cat([a, b], 1) + 0.1 * torch.randn(B, 2, generator=g, dtype=torch.float64)
+    ab0 = torch.cat([a, b], 1) + 0.2 * torch.randn(B, 2, generator=g, dtype=torch.float64)
+    c0 = torch.zeros(B, 1, dtype=torch.float64)
+    w = torch.randn(B, 3, generator=g, dtype=torch.float64)
+    return dict(x=x, y=y, t=t, ab=ab0, c=c0), w
+
+
+BACKWARD_CASES = {
+    "implicit_gn": ("gn", 12, dict(backward_mode="implicit")),
+    "unroll_gn": ("gn", 5, dict(backward_mode="unroll")),
+    "truncated_lm": ("lm", 10, dict(backward_mode="truncated", backward_num_iterations=3, damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)),
+    "unroll_lm": ("lm", 6, dict(backward_mode="unroll", damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)),
+    "implicit_lm": ("lm", 12, dict(backward_mode="implicit", damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)),
+}
+
+
+def make_backward(th):
+    """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
+    import torch
+    out = {}
+    for name, (method, iters, kw) in BACKWARD_CASES.items():
+        objective = backward_problem(th, torch)
+        cls = th.GaussNewton if method == "gn" else th.LevenbergMarquardt
+        opt = cls(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
+        layer = th.TheseusLayer(opt)
+        inp, w = backward_inputs(torch)
+        leaves = {k: inp[k].clone().requires_grad_(True) for k in ("x", "y", "t")}
+        sol, info = layer.forward({**leaves, "ab": inp["ab"].clone(), "c": inp["c"].clone()}, optimizer_kwargs=dict(kw))
+        loss = (torch.cat([sol["ab"], sol["c"]], 1) ** 2 * w).sum()
+        loss.backward()
+        out[name + "_ab"] = sol["ab"].detach().numpy(); out[name + "_c"] = sol["c"].detach().numpy()
+        for k in leaves:
+            out[name + "_grad_" + k] = leaves[k].grad.numpy()
+        out[name + "_loss"] = np.array(loss.item())
+        print("backward", name, "loss", loss.item(), "|grad_y|", float(leaves["y"].grad.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "backward_kat.npz"), **out)
+
+
 if __name__ == "__main__":
     th, lieF = _import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "backward":
+        make_backward(th)
+        sys.exit(0)
     make_lie(th, lieF)
     make_costs(th)
     make_dense_solver(th)
@@ -406,3 +481,4 @@ if __name__ == "__main__":
     make_ba(th, "ba_small_huber", num_cameras=6, num_points=40, B=3, seed=8, iters=8, robust=True)
     make_pgo(th, "pgo_small_welsch", num_poses=10, B=3, seed=9, iters=8, lm_kwargs=lm, loop_closure_ratio=0.6, robust="welsch",
              outlier_ratio=0.3, init_perturb=0.0)
+    make_backward(th)

@@ -26,7 +26,7 @@ def test_ba_linearization_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", ["ba_small_lm", "ba_small_huber"])
-@pytest.mark.parametrize("solver", ["dense", "sparse"])
+@pytest.mark.parametrize("solver", ["dense", "sparse", "sparse_lane"])
 def test_ba_lm_trace(solver, name):
     g = load(name)
     method, iters, kw = lm_kwargs_of(g)
@@ -35,7 +35,8 @@ def test_ba_lm_trace(solver, name):
         opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0)
     else:
         opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
-                                    max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0)
+                                    max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0,
+                                    linear_solver_kwargs=dict(layout="lane" if solver == "sparse_lane" else "item"))
         # minimum degree must eliminate the (many, cheap) points before the cameras
         plan = opt.linear_solver._plan
         first_cam = min(int(plan.pos[i]) for i, v in enumerate(opt.linear_solver.linearization.ordering) if v.dof() == 6)

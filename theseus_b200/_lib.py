@@ -31,7 +31,20 @@ class GramPlan(C.Structure):
                 ("blk_out", c_vp), ("blk_ld", c_vp), ("blk_mirror", c_vp), ("blk_cptr", c_vp),
                 ("c_off", c_vp), ("c_stride", c_vp), ("c_rows", c_vp), ("c_bpa", c_vp), ("c_bpb", c_vp),
                 ("n", c_i64), ("col_cptr", c_vp), ("cc_off", c_vp), ("cc_stride", c_vp), ("cc_rows", c_vp),
-                ("cc_row0", c_vp)]
+                ("cc_row0", c_vp), ("num_blocks", c_i64), ("blk_rows", c_vp), ("blk_cols", c_vp)]
+
+
+def make_gram_plan(arrs, dev):
+    """thb_gram_plan from structure.build_gram_plan's arrays (`arrs`) and their device copies (`dev`)."""
+    return GramPlan(
+        num_entries=int(arrs["ent_blk"].shape[0]), ent_blk=dev["ent_blk"].data_ptr(), ent_p=dev["ent_p"].data_ptr(),
+        ent_q=dev["ent_q"].data_ptr(), blk_out=dev["blk_out"].data_ptr(), blk_ld=dev["blk_ld"].data_ptr(),
+        blk_mirror=dev["blk_mirror"].data_ptr(), blk_cptr=dev["blk_cptr"].data_ptr(), c_off=dev["c_off"].data_ptr(),
+        c_stride=dev["c_stride"].data_ptr(), c_rows=dev["c_rows"].data_ptr(), c_bpa=dev["c_bpa"].data_ptr(),
+        c_bpb=dev["c_bpb"].data_ptr(), n=int(arrs["n"]), col_cptr=dev["col_cptr"].data_ptr(),
+        cc_off=dev["cc_off"].data_ptr(), cc_stride=dev["cc_stride"].data_ptr(), cc_rows=dev["cc_rows"].data_ptr(),
+        cc_row0=dev["cc_row0"].data_ptr(), num_blocks=int(arrs["blk_out"].shape[0]), blk_rows=dev["blk_rows"].data_ptr(),
+        blk_cols=dev["blk_cols"].data_ptr())
 
 
 class SparsePlanStruct(C.Structure):
@@ -44,9 +57,16 @@ class SparsePlanStruct(C.Structure):
                     "s_ptr", "s_col", "fr_ptr", "fr_off", "fr_k", "bc_ptr", "bc_off", "bc_i")]
 
 
+class SparseLanePlanStruct(C.Structure):
+    _fields_ = [("N", c_i64), ("n", c_i64), ("data_size", c_i64), ("diag_size", c_i64), ("num_launches", c_i64)] + [(k, c_vp) for k in (
+        "launches", "dims", "col_start", "pstart", "dl_off", "diag_off", "up_a", "up_b", "up_k", "u_tgt", "u_p0", "u_p1",
+        "t_off", "t_diag", "t_dl", "t_pstart", "s_col", "fr_ptr", "fr_off", "fr_p", "fr_d", "bc_ptr", "bc_off", "bc_p", "bc_d")]
+
+
 # name -> (restype, argtypes); every symbol declared in include/thb200.h
 _PG, _PV, _PP = C.POINTER(CostGroup), C.POINTER(VarTable), C.POINTER(GramPlan)
 _PS = C.POINTER(SparsePlanStruct)
+_PL = C.POINTER(SparseLanePlanStruct)
 SIGNATURES = {
     "thb_version": (c_i32, []),
     "thb_compiled_arch": (c_i32, []),
@@ -72,6 +92,12 @@ SIGNATURES = {
     "thb_sparse_damp_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_factor_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_solve_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_padded_batch": (c_i64, [c_i64]),
+    "thb_sparse_lane_gram_f64": (c_i32, [_PP, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "thb_sparse_lane_damp_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_factor_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_solve_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_solve_backward_f64": (c_i32, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "thb_lm_control_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64,
                                    c_vp, c_vp, c_vp, c_vp]),
     "thb_lm_control_f32": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_f32,

@@ -311,7 +311,7 @@ class AutoDiffCostFunction(CostFunction):
         err = self._err_fn(optim_vars=tuple(self._T(t) for t in optim_tensors), aux_vars=tuple(self._T(v.tensor) for v in self._aux))
         return self._weight(err, None)[1]
 
-    def generic_jacobians_error(self, optim_tensors: Sequence[torch.Tensor]):
+    def generic_jacobians_error(self, optim_tensors: Sequence[torch.Tensor], differentiable: bool = False):
         """(weighted Jacobians [B,dim,dof_i], weighted error [B,dim]) -- cost_function.py:318-393 (vmap over jacrev)."""
         from torch.func import jacrev, vmap
         aux = tuple(v.tensor for v in self._aux)
@@ -325,6 +325,8 @@ class AutoDiffCostFunction(CostFunction):
         with torch.enable_grad():
             jacs = vmap(jacrev(one, argnums=0))(opt_t, aux_t)
             err = self._err_fn(optim_vars=tuple(self._T(t) for t in opt_t), aux_vars=tuple(self._T(t) for t in aux_t))
+        if differentiable:  # backward modes: keep the graph to the aux variables / weights / variable values
+            return self._weight(err, list(jacs))
         jacs = [j.detach() for j in jacs]  # Vector.project(., is_sparse=True) is the identity (geometry/vector.py:199-203)
         return self._weight(err.detach(), jacs)
 

@@ -108,6 +108,44 @@ __global__ void tmat_vec_kernel(int64_t B, int64_t num_rows, int64_t num_cols, c
   y[t] = acc;
 }
 
+// Backward of x = (AtA + D)^-1 At b with respect to A_val and b, given H = (AtA + D)^-1 grad_x:
+//   b_grad = A H,   A_grad[r,c] = (b - A x)[r] H[c] - (A H)[r] x[c]  - 2 alpha H[c] x[c] A[r,c]
+// (optimizer/autograd/common.py:11-48: a Python loop over the m rows there; derivation in baspacho_sparse_autograd.py:68-115).
+// One thread per (batch item, row): the two row dot products and the row's slice of A_grad in one pass.
+__global__ void __launch_bounds__(256) solve_backward_kernel(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* __restrict__ row_ptr,
+                                                             const int64_t* __restrict__ col_ind, const double* __restrict__ A_val,
+                                                             const double* __restrict__ bvec, const double* __restrict__ x,
+                                                             const double* __restrict__ H, const double* __restrict__ alpha, int detach,
+                                                             double* __restrict__ A_grad, double* __restrict__ b_grad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * num_rows) return;
+  const int64_t bi = t / num_rows, row = t - bi * num_rows;
+  const int64_t nnz = row_ptr[num_rows];
+  const double* A = A_val + bi * nnz;
+  const double* xb = x + bi * num_cols;
+  const double* Hb = H + bi * num_cols;
+  const int64_t k0 = row_ptr[row], k1 = row_ptr[row + 1];
+  double ah = 0.0, ax = 0.0;
+  for (int64_t k = k0; k < k1; k++) {
+    const int64_t c = col_ind[k];
+    const double a = A[k];
+    ah += a * Hb[c];
+    ax += a * xb[c];
+  }
+  if (b_grad != nullptr) b_grad[t] = ah;
+  if (A_grad == nullptr) return;
+  const double res = detach ? bvec[t] : bvec[t] - ax;
+  const double al2 = (alpha != nullptr) ? 2.0 * alpha[bi] : 0.0;
+  double* G = A_grad + bi * nnz;
+  for (int64_t k = k0; k < k1; k++) {
+    const int64_t c = col_ind[k];
+    const double h = Hb[c], xv = xb[c];
+    double g = detach ? res * h : res * h - ah * xv;
+    if (al2 > 0.0) g -= A[k] * al2 * h * xv;
+    G[k] = g;
+  }
+}
+
 }  // namespace thb
 
 template <typename T>
@@ -148,6 +186,18 @@ int thb_mat_vec_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t
   THB_CHECK_LAUNCH();
   return THB_OK;
 }
+int thb_solve_backward_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* row_ptr, const int64_t* col_ind,
+                           const double* A_val, const double* b, const double* x, const double* H, const double* alpha,
+                           int32_t detach_hessian, double* A_grad, double* b_grad, thb_stream_t s) {
+  if (row_ptr == nullptr || col_ind == nullptr || A_val == nullptr || b == nullptr || x == nullptr || H == nullptr) return THB_ERR_BAD_ARG;
+  if (B <= 0 || num_rows <= 0) return THB_OK;
+  const int64_t total = B * num_rows;
+  thb::solve_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, thb_cs(s)>>>(B, num_rows, num_cols, row_ptr, col_ind, A_val, b, x, H, alpha,
+                                                                                     detach_hessian, A_grad, b_grad);
+  THB_CHECK_LAUNCH();
+  return THB_OK;
+}
+
 int thb_tmat_vec_f64(int64_t B, int64_t num_rows, int64_t num_cols, const int64_t* row_ptr, const int64_t* col_ind,
                      const double* A_val, const double* v, double* y, thb_stream_t s) {
   if (B <= 0 || num_cols <= 0) return THB_OK;

@@ -1,0 +1,518 @@
+// Batched block-sparse Cholesky, "batch-lane" execution model, fp64.
+//
+// Same job and same symbolic plan as thb_sparse.cu (BaSpaCho NumericDecomposition::{add_MtM,damp,factor,solve},
+// theseus/extlib/baspacho_solver.cpp:93-257, baspacho_solver_cuda.cu:96-293), different mapping onto the machine:
+//
+//   * every batch item has the SAME sparsity structure (one symbolic decomposition per objective, baspacho_sparse_solver.py:58-113),
+//     so the factorisation is one fixed sequence of small block operations executed for B different sets of numbers.
+//     Here a batch item is a LANE: the factor storage is interleaved, element e of item b at factor[e * Bp + b]
+//     (Bp = B rounded up to 32), so a warp that executes one block operation for 32 batch items issues perfectly
+//     coalesced 256-byte loads and stores and has no divergence; block indices are warp-uniform (broadcast loads);
+//   * a thread keeps a whole di x dj block in registers (kernels are compiled per block shape, dims in {1,2,3,6}:
+//     Vector/Point2/Point3/SO3/SE2/SE3), so the left-looking update of a block is a register-tiled rank-dk update chain:
+//     (di+dj) loads per di*dj FMAs, the target is read and written once;
+//   * elimination-tree levels are separate launches (the work lists are per level and per block shape, sparse.py:_lane_lists);
+//     inside a launch all work items are independent, there are no atomics and the result is deterministic.
+//
+// Stages per level:  U  target(i,j) <- M_ij - sum_k L_ik L_jk^T            (one thread per (batch item, block))
+//                    T  L_jj = chol(target(j,j)) in registers (recomputed by every block of the column: 56 FMAs, cheaper
+//                       than a launch), L_ij = target(i,j) L_jj^-T; the diagonal factor goes to a separate store `diagl`
+//                       with RECIPROCAL diagonal entries (the substitutions multiply instead of divide)
+// Solve: per level forward (y_j = L_jj^-1 (rhs_j - sum_k L_jk y_k)), then per level backward, permutation folded into the
+// first load / last store (K8 scramble/unscramble, baspacho_solver_cuda.cu:216-250).
+#include "thb_common.cuh"
+
+namespace thb {
+
+constexpr int LN_WARPS = 4;  // warps per CTA; one warp = 32 batch lanes of one work item
+
+// Compile-time fence: every element of x must be in a register here, i.e. all the loads that produce x are issued before any
+// instruction that consumes the fenced values.  Without it the compiler sinks each load next to its FMA and recycles one
+// register, which turns 36-72 independent loads into a chain of dependent memory latencies (measured: 10 us per 6x6 block).
+template <int N>
+__device__ __forceinline__ void loads_issued(double (&x)[N]) {
+  constexpr int G = 12;
+#pragma unroll
+  for (int i = 0; i + G <= N; i += G)
+    asm volatile("" : "+d"(x[i]), "+d"(x[i + 1]), "+d"(x[i + 2]), "+d"(x[i + 3]), "+d"(x[i + 4]), "+d"(x[i + 5]), "+d"(x[i + 6]),
+                 "+d"(x[i + 7]), "+d"(x[i + 8]), "+d"(x[i + 9]), "+d"(x[i + 10]), "+d"(x[i + 11]));
+#pragma unroll
+  for (int i = N / G * G; i < N; i++) asm volatile("" : "+d"(x[i]));
+}
+
+// acc[r][c] -= sum_k A[r][k] B[c][k]   (A: di x DK at a_off, B: dj x DK at b_off, both row-major, lane-interleaved)
+template <int DI, int DJ, int DK>
+__device__ __forceinline__ void pair_update(double (&acc)[DI * DJ], const double* Fb, int64_t a_off, int64_t b_off, int64_t Bp) {
+  constexpr int KS = (DK >= 3) ? 3 : DK;  // columns of the pair staged at once: KS*(DI+DJ) loads in flight
+#pragma unroll
+  for (int k0 = 0; k0 < DK; k0 += KS) {
+    double v[KS * (DI + DJ)];
+#pragma unroll
+    for (int k = 0; k < KS; k++) {
+#pragma unroll
+      for (int r = 0; r < DI; r++) v[k * (DI + DJ) + r] = Fb[(a_off + r * DK + k0 + k) * Bp];
+#pragma unroll
+      for (int c = 0; c < DJ; c++) v[k * (DI + DJ) + DI + c] = Fb[(b_off + c * DK + k0 + k) * Bp];
+    }
+    loads_issued(v);
+#pragma unroll
+    for (int k = 0; k < KS; k++)
+#pragma unroll
+      for (int r = 0; r < DI; r++)
+#pragma unroll
+        for (int c = 0; c < DJ; c++) acc[r * DJ + c] -= v[k * (DI + DJ) + r] * v[k * (DI + DJ) + DI + c];
+  }
+}
+
+template <int DI, int DJ>
+__device__ __forceinline__ void pair_update_any(double (&acc)[DI * DJ], const double* Fb, int64_t a_off, int64_t b_off, int dk,
+                                                int64_t Bp) {
+  if (dk == 6) pair_update<DI, DJ, 6>(acc, Fb, a_off, b_off, Bp);
+  else if (dk == 3) pair_update<DI, DJ, 3>(acc, Fb, a_off, b_off, Bp);
+  else if (dk == 2) pair_update<DI, DJ, 2>(acc, Fb, a_off, b_off, Bp);
+  else pair_update<DI, DJ, 1>(acc, Fb, a_off, b_off, Bp);
+}
+
+struct LaneArgs {
+  const int64_t* up_a; const int64_t* up_b; const int32_t* up_k;
+  const int64_t* u_tgt; const int64_t* u_p0; const int64_t* u_p1;
+  const int64_t* t_off; const int64_t* t_diag; const int64_t* t_dl; const int32_t* t_pstart;
+  int begin, end, nbx;
+  int64_t B, Bp;
+};
+
+// ---- U: one warp = one target block x 32 batch items ----
+template <int DI, int DJ>
+__global__ void __launch_bounds__(32 * LN_WARPS) lane_update_kernel(LaneArgs p, double* __restrict__ F) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int item = p.begin + (blockIdx.x / p.nbx) * LN_WARPS + warp;
+  if (item >= p.end || b >= p.B) return;
+  double* Fb = F + b;
+  const int64_t tgt = p.u_tgt[item];
+  double acc[DI * DJ];
+#pragma unroll
+  for (int e = 0; e < DI * DJ; e++) acc[e] = Fb[(tgt + e) * p.Bp];
+  const int64_t q1 = p.u_p1[item];
+  for (int64_t q = p.u_p0[item]; q < q1; q++) pair_update_any<DI, DJ>(acc, Fb, p.up_a[q], p.up_b[q], p.up_k[q], p.Bp);
+#pragma unroll
+  for (int e = 0; e < DI * DJ; e++) Fb[(tgt + e) * p.Bp] = acc[e];
+}
+
+// ---- U, heavy targets: the CTA's 8 warps split the update pairs of ONE target block; partial sums are combined through shared
+// memory in a fixed order (deterministic).  Used for blocks with >= LANE_HEAVY pairs (sparse.py): a single thread walking a list
+// of pairs is a chain of dependent memory latencies, and at the top of the elimination tree that chain is the critical path.
+constexpr int LH_WARPS = 8;
+template <int DI, int DJ>
+__global__ void __launch_bounds__(32 * LH_WARPS, 1) lane_update_heavy_kernel(LaneArgs p, double* __restrict__ F) {
+  __shared__ double red[(LH_WARPS / 2) * DI * DJ * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int item = p.begin + (blockIdx.x / p.nbx);
+  const bool live = b < p.B;
+  const double* Fb = F + (live ? b : 0);
+  double acc[DI * DJ];
+#pragma unroll
+  for (int e = 0; e < DI * DJ; e++) acc[e] = 0.0;
+  const int64_t q1 = p.u_p1[item];
+  if (live)
+    for (int64_t q = p.u_p0[item] + warp; q < q1; q += LH_WARPS) pair_update_any<DI, DJ>(acc, Fb, p.up_a[q], p.up_b[q], p.up_k[q], p.Bp);
+  // phase 1: warps 4..7 -> warps 0..3 ; phase 2: warps 1..3 -> warp 0
+  if (warp >= LH_WARPS / 2) {
+#pragma unroll
+    for (int e = 0; e < DI * DJ; e++) red[((warp - LH_WARPS / 2) * DI * DJ + e) * 32 + lane] = acc[e];
+  }
+  __syncthreads();
+  if (warp < LH_WARPS / 2) {
+#pragma unroll
+    for (int e = 0; e < DI * DJ; e++) acc[e] += red[(warp * DI * DJ + e) * 32 + lane];
+  }
+  __syncthreads();
+  if (warp > 0 && warp < LH_WARPS / 2) {
+#pragma unroll
+    for (int e = 0; e < DI * DJ; e++) red[((warp - 1) * DI * DJ + e) * 32 + lane] = acc[e];
+  }
+  __syncthreads();
+  if (warp == 0 && live) {
+    const int64_t tgt = p.u_tgt[item];
+    double* Fw = F + b;
+#pragma unroll
+    for (int e = 0; e < DI * DJ; e++) {
+      double s = acc[e];
+#pragma unroll
+      for (int w = 0; w < LH_WARPS / 2 - 1; w++) s += red[(w * DI * DJ + e) * 32 + lane];
+      Fw[(tgt + e) * p.Bp] += s;  // acc holds -(sum of products)
+    }
+  }
+}
+
+// ---- T: Cholesky of the column's diagonal block (registers) + triangular solve of this block ----
+template <int DI, int DJ>
+__global__ void __launch_bounds__(32 * LN_WARPS) lane_trsm_kernel(LaneArgs p, double* __restrict__ F, double* __restrict__ DL,
+                                                                  int32_t* __restrict__ info) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int item = p.begin + (blockIdx.x / p.nbx) * LN_WARPS + warp;
+  if (item >= p.end || b >= p.B) return;
+  double* Fb = F + b;
+  const int64_t off = p.t_off[item], dg = p.t_diag[item];
+  double d[DJ * DJ], inv[DJ];
+#pragma unroll
+  for (int r = 0; r < DJ; r++)
+#pragma unroll
+    for (int c = 0; c <= r; c++) d[r * DJ + c] = Fb[(dg + r * DJ + c) * p.Bp];
+  int fail = 0;
+#pragma unroll
+  for (int c = 0; c < DJ; c++) {
+    double dd = d[c * DJ + c];
+#pragma unroll
+    for (int k = 0; k < c; k++) dd -= d[c * DJ + k] * d[c * DJ + k];
+    if (!(dd > 0.0) && fail == 0) fail = c + 1;
+    inv[c] = rsqrt(dd);
+    d[c * DJ + c] = dd * inv[c];
+#pragma unroll
+    for (int r = c + 1; r < DJ; r++) {
+      double s = d[r * DJ + c];
+#pragma unroll
+      for (int k = 0; k < c; k++) s -= d[r * DJ + k] * d[c * DJ + k];
+      d[r * DJ + c] = s * inv[c];
+    }
+  }
+  if (off == dg) {
+    if constexpr (DI == DJ) {
+      double* Dl = DL + p.t_dl[item] * p.Bp + b;
+#pragma unroll
+      for (int r = 0; r < DJ; r++)
+#pragma unroll
+        for (int c = 0; c < DJ; c++) Dl[(r * DJ + c) * p.Bp] = (c < r) ? d[r * DJ + c] : (c == r ? inv[c] : 0.0);
+      if (fail != 0) atomicCAS(info + b, 0, p.t_pstart[item] + fail);
+    }
+    return;
+  }
+  double x[DI * DJ];
+#pragma unroll
+  for (int e = 0; e < DI * DJ; e++) x[e] = Fb[(off + e) * p.Bp];
+#pragma unroll
+  for (int c = 0; c < DJ; c++) {
+#pragma unroll
+    for (int r = 0; r < DI; r++) {
+      double s = x[r * DJ + c];
+#pragma unroll
+      for (int k = 0; k < c; k++) s -= x[r * DJ + k] * d[c * DJ + k];
+      x[r * DJ + c] = s * inv[c];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < DI * DJ; e++) Fb[(off + e) * p.Bp] = x[e];
+}
+
+struct LaneSolveArgs {
+  const int32_t* s_col; const int32_t* pstart; const int32_t* col_start; const int64_t* dl_off;
+  const int64_t* fr_ptr; const int64_t* fr_off; const int32_t* fr_p; const int32_t* fr_d;
+  const int64_t* bc_ptr; const int64_t* bc_off; const int32_t* bc_p; const int32_t* bc_d;
+  int begin, end, nbx;
+  int64_t B, Bp, n;
+};
+
+constexpr int LS_WARPS = 16;  // substitution kernels: the CTA's warps split the block list of ONE column (x 32 batch items)
+
+// s[r] -= sum_c L[r][c] v[c]  (L: DJ x DK row-major at off, v at Y[(pv + c)]).  All loads are issued before the first FMA:
+// written as load-FMA pairs ptxas recycles one register and serialises the 42 loads (measured: 10 us per block).
+template <int DJ, int DK>
+__device__ __forceinline__ void blk_mv(double (&s)[DJ], const double* Fb, int64_t off, const double* Yb, int pv, int64_t Bp) {
+  double v[DK], l[DJ * DK];
+#pragma unroll
+  for (int c = 0; c < DK; c++) v[c] = Yb[(int64_t)(pv + c) * Bp];
+#pragma unroll
+  for (int e = 0; e < DJ * DK; e++) l[e] = Fb[(off + e) * Bp];
+  loads_issued(l);
+#pragma unroll
+  for (int r = 0; r < DJ; r++)
+#pragma unroll
+    for (int c = 0; c < DK; c++) s[r] -= l[r * DK + c] * v[c];
+}
+// s[c] -= sum_r L[r][c] v[r]  (L: DI x DJ row-major at off)
+template <int DJ, int DI>
+__device__ __forceinline__ void blk_tmv(double (&s)[DJ], const double* Fb, int64_t off, const double* Yb, int pv, int64_t Bp) {
+  double v[DI], l[DI * DJ];
+#pragma unroll
+  for (int r = 0; r < DI; r++) v[r] = Yb[(int64_t)(pv + r) * Bp];
+#pragma unroll
+  for (int e = 0; e < DI * DJ; e++) l[e] = Fb[(off + e) * Bp];
+  loads_issued(l);
+#pragma unroll
+  for (int r = 0; r < DI; r++)
+#pragma unroll
+    for (int c = 0; c < DJ; c++) s[c] -= l[r * DJ + c] * v[r];
+}
+
+// partial sums of warps 1.. -> shared memory -> warp 0 (fixed order: deterministic)
+template <int DJ>
+__device__ __forceinline__ void reduce_to_warp0(double (&s)[DJ], double* red, int warp, int lane) {
+  if (warp > 0) {
+#pragma unroll
+    for (int r = 0; r < DJ; r++) red[((warp - 1) * DJ + r) * 32 + lane] = s[r];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int r = 0; r < DJ; r++)
+      for (int w = 0; w < LS_WARPS - 1; w++) s[r] += red[(w * DJ + r) * 32 + lane];
+  }
+}
+
+template <int DJ>
+__global__ void __launch_bounds__(32 * LS_WARPS, 1) lane_forward_kernel(LaneSolveArgs p, const double* F, const double* __restrict__ DL,
+                                                                     const double* __restrict__ rhs, double* Y) {
+  __shared__ double red[(LS_WARPS - 1) * DJ * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int item = p.begin + (blockIdx.x / p.nbx);
+  const bool live = b < p.B;
+  const int j = p.s_col[item];
+  const double* Fb = F + (live ? b : 0);
+  double* Yb = Y + (live ? b : 0);
+  double s[DJ];
+#pragma unroll
+  for (int r = 0; r < DJ; r++) s[r] = 0.0;
+  if (live) {
+    const int64_t q1 = p.fr_ptr[j + 1];
+    for (int64_t q = p.fr_ptr[j] + warp; q < q1; q += LS_WARPS) {
+      const int dk = p.fr_d[q], pk = p.fr_p[q];
+      const int64_t off = p.fr_off[q];
+      if (dk == 6) blk_mv<DJ, 6>(s, Fb, off, Yb, pk, p.Bp);
+      else if (dk == 3) blk_mv<DJ, 3>(s, Fb, off, Yb, pk, p.Bp);
+      else if (dk == 2) blk_mv<DJ, 2>(s, Fb, off, Yb, pk, p.Bp);
+      else blk_mv<DJ, 1>(s, Fb, off, Yb, pk, p.Bp);
+    }
+  }
+  reduce_to_warp0<DJ>(s, red, warp, lane);
+  if (warp != 0 || !live) return;
+  double dl[DJ * DJ];
+  const double* Dl = DL + p.dl_off[j] * p.Bp + b;
+#pragma unroll
+  for (int r = 0; r < DJ; r++)
+#pragma unroll
+    for (int c = 0; c <= r; c++) dl[r * DJ + c] = Dl[(r * DJ + c) * p.Bp];
+  const int pj = p.pstart[j];
+#pragma unroll
+  for (int r = 0; r < DJ; r++) {
+    double v = s[r] + rhs[b * p.n + p.col_start[j] + r];  // scramble on load
+#pragma unroll
+    for (int c = 0; c < r; c++) v -= dl[r * DJ + c] * s[c];
+    s[r] = v * dl[r * DJ + r];
+    Yb[(int64_t)(pj + r) * p.Bp] = s[r];
+  }
+}
+
+template <int DJ>
+__global__ void __launch_bounds__(32 * LS_WARPS, 1) lane_backward_kernel(LaneSolveArgs p, const double* F, const double* __restrict__ DL,
+                                                                      double* Y, double* __restrict__ x) {
+  __shared__ double red[(LS_WARPS - 1) * DJ * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int item = p.begin + (blockIdx.x / p.nbx);
+  const bool live = b < p.B;
+  const int j = p.s_col[item];
+  const double* Fb = F + (live ? b : 0);
+  double* Yb = Y + (live ? b : 0);
+  double s[DJ];
+#pragma unroll
+  for (int c = 0; c < DJ; c++) s[c] = 0.0;
+  if (live) {
+    const int64_t q1 = p.bc_ptr[j + 1];
+    for (int64_t q = p.bc_ptr[j] + warp; q < q1; q += LS_WARPS) {
+      const int di = p.bc_d[q], pi = p.bc_p[q];
+      const int64_t off = p.bc_off[q];
+      if (di == 6) blk_tmv<DJ, 6>(s, Fb, off, Yb, pi, p.Bp);
+      else if (di == 3) blk_tmv<DJ, 3>(s, Fb, off, Yb, pi, p.Bp);
+      else if (di == 2) blk_tmv<DJ, 2>(s, Fb, off, Yb, pi, p.Bp);
+      else blk_tmv<DJ, 1>(s, Fb, off, Yb, pi, p.Bp);
+    }
+  }
+  reduce_to_warp0<DJ>(s, red, warp, lane);
+  if (warp != 0 || !live) return;
+  const int pj = p.pstart[j];
+  double dl[DJ * DJ];
+  const double* Dl = DL + p.dl_off[j] * p.Bp + b;
+#pragma unroll
+  for (int r = 0; r < DJ; r++)
+#pragma unroll
+    for (int c = 0; c <= r; c++) dl[r * DJ + c] = Dl[(r * DJ + c) * p.Bp];
+#pragma unroll
+  for (int c = 0; c < DJ; c++) s[c] += Yb[(int64_t)(pj + c) * p.Bp];
+#pragma unroll
+  for (int c = DJ - 1; c >= 0; c--) {
+    double v = s[c];
+#pragma unroll
+    for (int r = c + 1; r < DJ; r++) v -= dl[r * DJ + c] * s[r];
+    s[c] = v * dl[c * DJ + c];
+    Yb[(int64_t)(pj + c) * p.Bp] = s[c];
+    x[b * p.n + p.col_start[j] + c] = s[c];  // unscramble on store
+  }
+}
+
+__global__ void __launch_bounds__(256) lane_damp_kernel(thb_sparse_lane_plan p, double* __restrict__ F, const double* __restrict__ alpha,
+                                                        const double* __restrict__ beta, int64_t B, int64_t Bp) {
+  // diag <- diag * (1 + alpha_b) + beta_b   (extlib/baspacho_solver.cpp:181-183, baspacho_solver_cuda.cu:171-185)
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = t / Bp, b = t - e * Bp;
+  if (e >= p.n || b >= B) return;
+  int lo = 0, hi = (int)p.N;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.pstart[mid] <= e) lo = mid; else hi = mid;
+  }
+  const int d = p.dims[lo];
+  const int r = (int)(e - p.pstart[lo]);
+  double* D = F + (p.diag_off[lo] + (int64_t)r * d + r) * Bp + b;
+  const double a = alpha != nullptr ? alpha[b] : 0.0, be = beta != nullptr ? beta[b] : 0.0;
+  *D = *D * (1.0 + a) + be;
+}
+
+// add_MtM into the lane-interleaved factor storage (K6, baspacho_solver_cuda.cu:96-134; no atomics).  One thread per
+// (batch item, block of AtA): for every cost function touching the variable pair it reads the two Jacobian blocks
+// row by row (rows*(di+dj) loads, each row segment contiguous in A_val[b,:]) and accumulates the di x dj product in
+// registers; the store is coalesced over the batch.  Block sizes <= 6 (the lane kernels' domain).
+__global__ void __launch_bounds__(128) lane_gram_kernel(thb_gram_plan p, int64_t B, int64_t Bp, const double* __restrict__ A_val, int64_t nnz,
+                                                        double* __restrict__ F) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t blk = t / Bp, b = t - blk * Bp;
+  if (blk >= p.num_blocks || b >= B) return;
+  const int di = p.blk_rows[blk], dj = p.blk_cols[blk];
+  const double* A = A_val + b * nnz;
+  double acc[36];
+#pragma unroll
+  for (int e = 0; e < 36; e++) acc[e] = 0.0;
+  const int c1 = p.blk_cptr[blk + 1];
+  for (int c = p.blk_cptr[blk]; c < c1; c++) {
+    const double* base = A + p.c_off[c];
+    const int stride = p.c_stride[c];
+    const int rows = p.c_rows[c];
+    const int oa = p.c_bpa[c], ob = p.c_bpb[c];
+    for (int r = 0; r < rows; r++) {
+      double ja[6], jb[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) ja[q] = q < di ? base[r * stride + oa + q] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) jb[q] = q < dj ? base[r * stride + ob + q] : 0.0;
+#pragma unroll
+      for (int pp = 0; pp < 6; pp++)
+#pragma unroll
+        for (int qq = 0; qq < 6; qq++) acc[pp * 6 + qq] += ja[pp] * jb[qq];
+    }
+  }
+  double* o = F + p.blk_out[blk] * Bp + b;
+  const int ld = p.blk_ld[blk];
+#pragma unroll
+  for (int pp = 0; pp < 6; pp++)
+#pragma unroll
+    for (int qq = 0; qq < 6; qq++)
+      if (pp < di && qq < dj) o[(int64_t)(pp * ld + qq) * Bp] = acc[pp * 6 + qq];
+}
+
+}  // namespace thb
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+#define LN_DIM_OK(d) ((d) == 1 || (d) == 2 || (d) == 3 || (d) == 6)
+#define LN_SWITCH_DJ(DI, dj, CALL)                                                          \
+  switch (dj) { case 1: { CALL(DI, 1); } break; case 2: { CALL(DI, 2); } break; case 3: { CALL(DI, 3); } break; case 6: { CALL(DI, 6); } break; default: return THB_ERR_UNSUPPORTED; }
+#define LN_SWITCH(di, dj, CALL)                                                             \
+  switch (di) { case 1: LN_SWITCH_DJ(1, dj, CALL) break; case 2: LN_SWITCH_DJ(2, dj, CALL) break; case 3: LN_SWITCH_DJ(3, dj, CALL) break; \
+                case 6: LN_SWITCH_DJ(6, dj, CALL) break; default: return THB_ERR_UNSUPPORTED; }
+#define LN_SWITCH1(dj, CALL)                                                                \
+  switch (dj) { case 1: { CALL(1); } break; case 2: { CALL(2); } break; case 3: { CALL(3); } break; case 6: { CALL(6); } break; default: return THB_ERR_UNSUPPORTED; }
+
+extern "C" {
+
+int64_t thb_sparse_lane_padded_batch(int64_t B) { return (B + 31) / 32 * 32; }
+
+int thb_sparse_lane_gram_f64(const thb_gram_plan* g, int64_t B, const double* A_val, int64_t nnz, double* factor, thb_stream_t s) {
+  if (g == nullptr || A_val == nullptr || factor == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (B == 0 || g->num_blocks == 0) return THB_OK;
+  const int64_t Bp = thb_sparse_lane_padded_batch(B);
+  const int64_t total = g->num_blocks * Bp;
+  thb::lane_gram_kernel<<<(unsigned)((total + 127) / 128), 128, 0, thb_cs(s)>>>(*g, B, Bp, A_val, nnz, factor);
+  THB_CHECK_LAUNCH();
+  return THB_OK;
+}
+
+int thb_sparse_lane_damp_f64(const thb_sparse_lane_plan* p, double* factor, const double* alpha, const double* beta, int64_t B, thb_stream_t s) {
+  if (p == nullptr || factor == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (B == 0 || p->n == 0) return THB_OK;
+  const int64_t Bp = thb_sparse_lane_padded_batch(B);
+  const int64_t total = p->n * Bp;
+  thb::lane_damp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, thb_cs(s)>>>(*p, factor, alpha, beta, B, Bp);
+  THB_CHECK_LAUNCH();
+  return THB_OK;
+}
+
+int thb_sparse_lane_factor_f64(const thb_sparse_lane_plan* p, double* factor, double* diagl, int32_t* info, int64_t B, thb_stream_t s) {
+  if (p == nullptr || factor == nullptr || diagl == nullptr || info == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (B == 0 || p->N == 0) return THB_OK;
+  cudaStream_t cs = thb_cs(s);
+  THB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * B, cs));
+  thb::LaneArgs a;
+  a.up_a = p->up_a; a.up_b = p->up_b; a.up_k = p->up_k;
+  a.u_tgt = p->u_tgt; a.u_p0 = p->u_p0; a.u_p1 = p->u_p1;
+  a.t_off = p->t_off; a.t_diag = p->t_diag; a.t_dl = p->t_dl; a.t_pstart = p->t_pstart;
+  a.B = B; a.Bp = thb_sparse_lane_padded_batch(B); a.nbx = (int)(a.Bp / 32);
+  for (int64_t l = 0; l < p->num_launches; l++) {
+    const int32_t* L = p->launches + 5 * l;
+    const int kind = L[0], di = L[1], dj = L[2];
+    a.begin = L[3]; a.end = L[4];
+    const int items = a.end - a.begin;
+    if (items <= 0 || kind == THB_LANE_S) continue;
+    const unsigned grid_w = (unsigned)(((items + thb::LN_WARPS - 1) / thb::LN_WARPS) * a.nbx);
+    if (kind == THB_LANE_U) {
+#define CALL_U(DI, DJ) thb::lane_update_kernel<DI, DJ><<<grid_w, 32 * thb::LN_WARPS, 0, cs>>>(a, factor)
+      LN_SWITCH(di, dj, CALL_U)
+    } else if (kind == THB_LANE_UH) {
+      const unsigned grid_h = (unsigned)(items * a.nbx);
+#define CALL_UH(DI, DJ) thb::lane_update_heavy_kernel<DI, DJ><<<grid_h, 32 * thb::LH_WARPS, 0, cs>>>(a, factor)
+      LN_SWITCH(di, dj, CALL_UH)
+    } else if (kind == THB_LANE_T) {
+#define CALL_T(DI, DJ) thb::lane_trsm_kernel<DI, DJ><<<grid_w, 32 * thb::LN_WARPS, 0, cs>>>(a, factor, diagl, info)
+      LN_SWITCH(di, dj, CALL_T)
+    } else {
+      return THB_ERR_BAD_ARG;
+    }
+    THB_CHECK_LAUNCH();
+  }
+  return THB_OK;
+}
+
+int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs, double* x,
+                              double* work, int64_t B, thb_stream_t s) {
+  if (p == nullptr || factor == nullptr || diagl == nullptr || rhs == nullptr || x == nullptr || work == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (B == 0 || p->N == 0) return THB_OK;
+  cudaStream_t cs = thb_cs(s);
+  thb::LaneSolveArgs a;
+  a.s_col = p->s_col; a.pstart = p->pstart; a.col_start = p->col_start; a.dl_off = p->dl_off;
+  a.fr_ptr = p->fr_ptr; a.fr_off = p->fr_off; a.fr_p = p->fr_p; a.fr_d = p->fr_d;
+  a.bc_ptr = p->bc_ptr; a.bc_off = p->bc_off; a.bc_p = p->bc_p; a.bc_d = p->bc_d;
+  a.B = B; a.Bp = thb_sparse_lane_padded_batch(B); a.nbx = (int)(a.Bp / 32); a.n = p->n;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int64_t q = 0; q < p->num_launches; q++) {
+      const int64_t l = pass == 0 ? q : p->num_launches - 1 - q;
+      const int32_t* L = p->launches + 5 * l;
+      if (L[0] != THB_LANE_S) continue;
+      const int dj = L[2];
+      a.begin = L[3]; a.end = L[4];
+      const int items = a.end - a.begin;
+      if (items <= 0) continue;
+      const unsigned grid_w = (unsigned)(items * a.nbx);
+      if (pass == 0) {
+#define CALL_F(DJ) thb::lane_forward_kernel<DJ><<<grid_w, 32 * thb::LS_WARPS, 0, cs>>>(a, factor, diagl, rhs, work)
+        LN_SWITCH1(dj, CALL_F)
+      } else {
+#define CALL_B(DJ) thb::lane_backward_kernel<DJ><<<grid_w, 32 * thb::LS_WARPS, 0, cs>>>(a, factor, diagl, work, x)
+        LN_SWITCH1(dj, CALL_B)
+      }
+      THB_CHECK_LAUNCH();
+    }
+  }
+  return THB_OK;
+}
+
+}  // extern "C"

@@ -294,6 +294,26 @@ class Engine:
             b[:, int(S.cost_row0[f]):int(S.cost_row0[f]) + d] = -err
         return A_val, b
 
+    def linearize_sparse_differentiable(self):
+        """(A_val, b) as autograd tensors: same layout, values from the cost functions' torch.func Jacobians without detaching, so
+        gradients reach the auxiliary variables / cost weights / current variable values.  Only objectives whose cost functions
+        all take this path are supported on the tape (NonlinearLeastSquares._optimize_impl_differentiable checks)."""
+        if self.groups:
+            raise NotImplementedError("differentiable linearization: fused-kernel cost functions have no autograd path")
+        B, S = self.batch_size, self.structure
+        A_val = torch.zeros(B, self.nnz, dtype=self.dtype, device=self.device)
+        b = torch.zeros(B, self.m, dtype=self.dtype, device=self.device)
+        for f in self.generic:
+            cf = self.costs[f]
+            jacs, err = cf.generic_jacobians_error([self._expand(v.tensor) for v in cf.optim_vars], differentiable=True)
+            d, st, off = int(S.cost_dims[f]), int(S.stride[f]), int(S.row_block_starts[f])
+            blk = A_val[:, off:off + d * st].view(B, d, st)
+            for kslot, J in enumerate(jacs):
+                p0 = int(S.block_pointers[f][kslot])
+                blk[:, :, p0:p0 + J.shape[2]] = J
+            b[:, int(S.cost_row0[f]):int(S.cost_row0[f]) + d] = -err
+        return A_val, b
+
     def _expand(self, t):
         B = self.batch_size
         return t if t.shape[0] == B else t.expand((B,) + tuple(t.shape[1:]))
@@ -323,14 +343,7 @@ class Engine:
         if self._gram_dense is None:
             arrs = build_gram_plan(self.structure)
             dev = {k: _dev(v, self.device) for k, v in arrs.items() if isinstance(v, np.ndarray)}
-            st = _lib.GramPlan(
-                num_entries=int(arrs["ent_blk"].shape[0]), ent_blk=dev["ent_blk"].data_ptr(), ent_p=dev["ent_p"].data_ptr(),
-                ent_q=dev["ent_q"].data_ptr(), blk_out=dev["blk_out"].data_ptr(), blk_ld=dev["blk_ld"].data_ptr(),
-                blk_mirror=dev["blk_mirror"].data_ptr(), blk_cptr=dev["blk_cptr"].data_ptr(), c_off=dev["c_off"].data_ptr(),
-                c_stride=dev["c_stride"].data_ptr(), c_rows=dev["c_rows"].data_ptr(), c_bpa=dev["c_bpa"].data_ptr(),
-                c_bpb=dev["c_bpb"].data_ptr(), n=int(arrs["n"]), col_cptr=dev["col_cptr"].data_ptr(),
-                cc_off=dev["cc_off"].data_ptr(), cc_stride=dev["cc_stride"].data_ptr(), cc_rows=dev["cc_rows"].data_ptr(),
-                cc_row0=dev["cc_row0"].data_ptr())
+            st = _lib.make_gram_plan(arrs, dev)
             self._gram_dense = (st, dev)
         return self._gram_dense[0]
 

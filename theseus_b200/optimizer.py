@@ -66,9 +66,12 @@ class Linearization:
     def engine(self):
         return self.objective.engine()
 
-    def linearize(self, _detach_hessian: bool = False):
+    def linearize(self, _detach_hessian: bool = False, differentiable: bool = False):
+        """differentiable=True (backward modes): the Jacobian values / residuals come out as autograd tensors built from the
+        cost functions' torch.func Jacobians (core.AutoDiffCostFunction), not from the fused kernels."""
         if not self.ordering.complete:
             raise RuntimeError("Attempted to linearize an objective with an incomplete variable order.")
+        self._differentiable = differentiable
         self._linearize_hessian_impl(_detach_hessian=_detach_hessian)
 
     @property
@@ -102,7 +105,10 @@ class SparseLinearization(Linearization):
     def _linearize_jacobian_impl(self):
         self._Atb = None
         self._AtA_diag = None
-        self.A_val, self.b = self.engine.linearize_sparse()
+        if getattr(self, "_differentiable", False):
+            self.A_val, self.b = self.engine.linearize_sparse_differentiable()
+        else:
+            self.A_val, self.b = self.engine.linearize_sparse()
 
     def _linearize_hessian_impl(self, _detach_hessian: bool = False):
         self._linearize_jacobian_impl()
@@ -155,10 +161,14 @@ class DenseLinearization(Linearization):
         self._diag = None
 
     def _linearize_jacobian_impl(self):
-        self._A_val, self.b = self.engine.linearize_sparse()
+        if getattr(self, "_differentiable", False):
+            self._A_val, self.b = self.engine.linearize_sparse_differentiable()
+        else:
+            self._A_val, self.b = self.engine.linearize_sparse()
 
     def _linearize_hessian_impl(self, _detach_hessian: bool = False):
         self._linearize_jacobian_impl()
+        self.detached_hessian = _detach_hessian
         eng = self.engine
         B, n = eng.batch_size, self.num_cols
         self._AtA = eng.buf("AtA", (B, n, n))
@@ -236,8 +246,59 @@ class DenseSolver(LinearSolver):
     def solve(self, damping: Optional[Union[float, torch.Tensor]] = None, ellipsoidal_damping: bool = True,
               damping_eps: float = 1e-8, **kwargs) -> torch.Tensor:
         lin = self.linearization
+        A_val, b = getattr(lin, "_A_val", None), getattr(lin, "b", None)
+        if A_val is not None and b is not None:
+            from .autograd import LinearSolveFunction, wants_grad
+            if wants_grad(A_val, b):  # differentiable solve: x as a function of the Jacobian values and residuals
+                return LinearSolveFunction.apply(A_val, b, self, damping, ellipsoidal_damping, damping_eps,
+                                                 bool(getattr(lin, "detached_hessian", False)))
         return self._apply_damping_and_solve(lin.Atb, lin.AtA, damping=damping, ellipsoidal_damping=ellipsoidal_damping,
                                              damping_eps=damping_eps)
+
+    # ---- backend of autograd.LinearSolveFunction: the same system rebuilt from (A_val, b) in fp64 ----
+    def _solve_nograd(self, A_val, b, damping, ellipsoidal_damping, damping_eps):
+        out_dtype = A_val.dtype
+        A64, b64 = A_val.detach().double().contiguous(), b.detach().double().contiguous()
+        alpha = beta = None
+        if damping is not None:
+            alpha, beta = convert_to_alpha_beta_damping_tensors(damping, damping_eps, ellipsoidal_damping, A64.shape[0], A64.device, torch.float64)
+        Atb = self._numeric(A64, b64, alpha, beta)
+        x = self._substitute(Atb)
+        return x.to(out_dtype), (A64, b64, x, alpha, beta)
+
+    def _numeric(self, A_val, b, alpha, beta):
+        eng = self.linearization.engine
+        lib = _lib.load()
+        B, n = A_val.shape[0], self.linearization.num_cols
+        s = _lib.stream_ptr()
+        st = getattr(self, "_bw", None)
+        if st is None or st["AtA"].shape[0] != B or st["AtA"].device != A_val.device:
+            st = dict(AtA=torch.zeros(B, n, n, dtype=torch.float64, device=A_val.device),
+                      Atb=torch.empty(B, n, dtype=torch.float64, device=A_val.device),
+                      ws=torch.empty(int(lib.thb_potrf_workspace_bytes(B, n)), dtype=torch.uint8, device=A_val.device),
+                      info=torch.empty(B, dtype=torch.int32, device=A_val.device))
+            self._bw = st
+        plan = eng.gram_plan_dense()
+        _lib.check(lib.thb_gram_f64(C.byref(plan), B, _lib.ptr(A_val), A_val.shape[1], _lib.ptr(b), b.shape[1], _lib.ptr(st["AtA"]), n * n,
+                                    _lib.ptr(st["Atb"]), None, s), "gram")
+        _lib.check(lib.thb_potrf_f64(_lib.ptr(st["AtA"]), _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(st["info"]), B, n, _lib.ptr(st["ws"]),
+                                     st["ws"].numel(), s), "potrf")
+        self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
+        self._keep_bw = (A_val, b, alpha, beta)
+        bad = st["info"].nonzero()
+        if bad.numel() > 0:
+            k = int(bad[0, 0])
+            raise torch.linalg.LinAlgError(f"linalg.cholesky: (Batch element {k}): The factorization could not be completed because the "
+                                           f"input is not positive-definite (the leading minor of order {int(st['info'][k])} is not positive-definite).")
+        return st["Atb"]
+
+    def _substitute(self, rhs: torch.Tensor) -> torch.Tensor:
+        st = self._bw
+        B, n = rhs.shape
+        rhs = rhs.contiguous()
+        x = torch.empty(B, n, dtype=torch.float64, device=rhs.device)
+        _lib.check(_lib.load().thb_potrs_f64(_lib.ptr(rhs), _lib.ptr(x), B, n, _lib.ptr(st["ws"]), st["ws"].numel(), _lib.stream_ptr()), "potrs")
+        return x
 
     def _apply_damping_and_solve(self, Atb: torch.Tensor, AtA: torch.Tensor, damping=None, ellipsoidal_damping: bool = True,
                                  damping_eps: float = 1e-8) -> torch.Tensor:
@@ -494,9 +555,8 @@ class NonlinearLeastSquares:
                        end_iter_callback=None, **kwargs) -> OptimizerInfo:
         backward_mode = BackwardMode.resolve(backward_mode)
         if torch.is_grad_enabled() and any(v.tensor.requires_grad for v in list(self.objective.optim_vars.values()) + list(self.objective.aux_vars.values())):
-            raise NotImplementedError(
-                "theseus_b200 r1 implements the forward (no_grad) NLS path; differentiating through the solve "
-                "(SURVEY.md 8f rank 1) is not built yet -- wrap the call in torch.no_grad().")
+            return self._optimize_impl_differentiable(track_best_solution, track_err_history, track_state_history, verbose, backward_mode,
+                                                      end_iter_callback, **kwargs)
         kwargs_plus = {**kwargs, "backward_mode": backward_mode}
         eng = self.objective.engine()
         eng.adopt_optim_vars()
@@ -509,6 +569,128 @@ class NonlinearLeastSquares:
                                 end_iter_callback=end_iter_callback, **kwargs)
         info.converged_iter[torch.from_numpy(info.status == NonlinearOptimizerStatus.MAX_ITERATIONS).to(info.converged_iter.device)] = -1
         return info
+
+    # ---- backward modes (nonlinear_least_squares.py:233-294, theseus_layer.py:45-97) ----
+    def _optimize_impl_differentiable(self, track_best_solution, track_err_history, track_state_history, verbose, backward_mode,
+                                      end_iter_callback, **kwargs) -> OptimizerInfo:
+        """UNROLL: every iteration on the autograd tape.  TRUNCATED: the last `backward_num_iterations` only.  IMPLICIT: the whole
+        loop under no_grad, then ONE differentiable, undamped Gauss-Newton step with the Hessian detached (implicit function
+        theorem at the fixed point).  On the tape an iteration is: differentiable linearization (torch.func Jacobians of the
+        AutoDiffCostFunctions) -> autograd.LinearSolveFunction (fused CUDA forward, closed-form CUDA backward) -> x + delta."""
+        from .core import AutoDiffCostFunction
+        from .geometry import Vector
+        if backward_mode == BackwardMode.DLM:
+            raise NotImplementedError("BackwardMode.DLM is not built (SURVEY.md 8: out of scope)")
+        bad_cf = [cf.name for cf in self.objective.cost_functions.values() if not isinstance(cf, AutoDiffCostFunction)]
+        bad_v = [v.name for v in self.ordering if not isinstance(v, Vector)]
+        if bad_cf or bad_v:
+            raise NotImplementedError(
+                "theseus_b200: differentiating through the optimizer is built for objectives of AutoDiffCostFunctions over Vector "
+                f"variables; fused-kernel cost functions {bad_cf[:3]} / Lie-group variables {bad_v[:3]} have no autograd path yet "
+                "-- wrap the call in torch.no_grad().")
+        kwargs_plus = {**kwargs, "backward_mode": backward_mode}
+        self.reset(**kwargs_plus)
+        with torch.no_grad():
+            info = self._init_info(track_best_solution, track_err_history, track_state_history)
+        bwd_iters, nograd_iters = self._split_backward_iters(**kwargs_plus)
+        if backward_mode == BackwardMode.UNROLL:
+            self._optimize_loop_differentiable(bwd_iters, info, verbose, end_iter_callback, False, **kwargs)
+            info.converged_iter[torch.from_numpy(info.status == NonlinearOptimizerStatus.MAX_ITERATIONS).to(info.converged_iter.device)] = -1
+            return info
+        with torch.no_grad():
+            self.objective.engine().adopt_optim_vars()
+            done0 = self._optimize_loop(num_iter=nograd_iters, info=info, verbose=verbose, end_iter_callback=end_iter_callback, **kwargs)
+        with torch.no_grad():
+            ginfo = self._init_info(track_best_solution, track_err_history, track_state_history)
+        done1 = self._optimize_loop_differentiable(bwd_iters, ginfo, verbose, end_iter_callback, backward_mode == BackwardMode.IMPLICIT, **kwargs)
+        self._merge_infos(ginfo, done0, done1, info)
+        return info
+
+    def _merge_infos(self, ginfo, done0: int, done1: int, info) -> None:
+        """nonlinear_optimizer.py:215-271: fold the grad-loop's bookkeeping into the no-grad loop's."""
+        total = min(done0 + done1, self.params.max_iterations)
+        info.status = ginfo.status
+        info.converged_iter = ginfo.converged_iter + done0
+        info.converged_iter[torch.from_numpy(ginfo.status == NonlinearOptimizerStatus.MAX_ITERATIONS).to(info.converged_iter.device)] = -1
+        info.last_err = ginfo.last_err
+        if info.err_history is not None:
+            info.err_history[:, done0:total + 1] = ginfo.err_history[:, :total + 1 - done0]
+        if info.state_history is not None:
+            for k in info.state_history:
+                info.state_history[k][..., done0:total + 1] = ginfo.state_history[k][..., :total + 1 - done0]
+        if info.best_solution is not None:
+            better = (ginfo.best_err < info.best_err).cpu()
+            for k in info.best_solution:
+                info.best_solution[k][better] = ginfo.best_solution[k][better]
+            info.best_iter[better.to(info.best_iter.device)] = ginfo.best_iter[better.to(info.best_iter.device)] + done0
+            info.best_err = torch.minimum(info.best_err, ginfo.best_err)
+
+    def _optimize_loop_differentiable(self, num_iter: int, info, verbose: bool, end_iter_callback, last_implicit_step: bool, **kwargs) -> int:
+        """nonlinear_least_squares.py:100-215 with every value-carrying op on the autograd tape (Vector variables: retract = +)."""
+        eng = self.objective.engine()
+        lin = self.linear_solver.linearization
+        S = eng.structure
+        converged = None
+        iters_done = it_ = rejects_in_a_row = 0
+        while it_ < num_iter:
+            lin.linearize(_detach_hessian=last_implicit_step, differentiable=True)
+            try:
+                if last_implicit_step:
+                    try:
+                        delta = self.linear_solver.solve()  # the implicit-function derivation wants a plain GN step
+                    except RuntimeError:
+                        if kwargs.get("__strict_implicit_final_gn__", False):
+                            raise
+                        delta = self.compute_delta(**kwargs)
+                else:
+                    delta = self.compute_delta(**kwargs)
+            except RuntimeError as run_err:
+                raise RuntimeError(f"There was an error while running the linear optimizer. Original error message: {run_err}. "
+                                   "Backward pass will not work. To obtain the best solution seen before the error, run with torch.no_grad()")
+            step = 1.0 if (last_implicit_step and not kwargs.get("__keep_final_step_size__", False)) else float(self.params.step_size)
+            olds = [v.tensor for v in self.ordering]
+            news = []
+            for v, old, c0, d in zip(self.ordering, olds, S.var_start_cols, S.var_dims):
+                new = old + step * delta[:, int(c0):int(c0) + int(d)].view(delta.shape[0], *old.shape[1:])
+                if converged is not None and not last_implicit_step:
+                    new = torch.where(converged.view(-1, *([1] * (new.ndim - 1))), old.expand_as(new), new)
+                news.append(new)
+            for v, new in zip(self.ordering, news):
+                v.update(new)
+            with torch.no_grad():
+                err_new = eng.error_metric("cur")
+            reject, err, all_rejected = (None, err_new, False) if last_implicit_step else \
+                self._complete_step(delta.detach(), err_new, info.last_err, **kwargs)
+            if reject is not None:
+                if all_rejected:
+                    for v, old in zip(self.ordering, olds):
+                        v.update(old)
+                    rejects_in_a_row += 1
+                    if rejects_in_a_row < NonlinearLeastSquares._MAX_ALL_REJECT_ATTEMPTS:
+                        continue
+                    err = info.last_err
+                else:
+                    rj = reject.bool()
+                    for v, old, new in zip(self.ordering, olds, news):
+                        v.update(torch.where(rj.view(-1, *([1] * (new.ndim - 1))), old.expand_as(new), new))
+            rejects_in_a_row = 0
+            with torch.no_grad():
+                self._update_info(info, it_, err, converged)
+                if verbose:
+                    print(f"Nonlinear optimizer. Iteration: {it_+1}. Error: {err.mean().item()}")
+                converged = self._check_convergence(err, info.last_err)
+                if converged is not None:
+                    cpu_conv = converged.cpu().numpy()
+                    info.status[cpu_conv] = NonlinearOptimizerStatus.CONVERGED
+                    if bool(cpu_conv.all()):
+                        break
+                info.last_err = err
+                if end_iter_callback is not None:
+                    end_iter_callback(self, info, delta, it_)
+            iters_done += 1
+            it_ += 1
+        info.status[info.status == NonlinearOptimizerStatus.START] = NonlinearOptimizerStatus.MAX_ITERATIONS
+        return iters_done
 
     # ---- step (nonlinear_least_squares.py:296-365) ----
     def _step(self, delta: torch.Tensor, previous_err: torch.Tensor, converged_indices, **kwargs):

@@ -74,6 +74,7 @@ class SparsePlan:
     winv_size: int
     arrays: Dict[str, np.ndarray]
     stats: Dict[str, float]
+    lane: Dict[str, np.ndarray] = None   # work lists of the batch-lane kernels (thb_sparse_lane.cu), see _lane_lists
 
 
 def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering: str = "mindeg") -> SparsePlan:
@@ -224,11 +225,66 @@ def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering
         s_ptr=np.array(s_ptr, dtype=i64), s_col=np.array(s_col, dtype=i32),
         fr_ptr=np.array(fr_ptr, dtype=i64), fr_off=np.array(fr_off, dtype=i64), fr_k=np.array(fr_k, dtype=i32),
         bc_ptr=np.array(bc_ptr, dtype=i64), bc_off=np.array(bc_off, dtype=i64), bc_i=np.array(bc_i, dtype=i32))
+    lane = _lane_lists(N, nlev, cols_by_level, struct, dims, blk_index, blk_off, up_ptr, winv_off, pstart)
+    fr_k_arr, bc_i_arr = np.array(fr_k, dtype=np.int64), np.array(bc_i, dtype=np.int64)
+    lane.update(fr_p=pstart[fr_k_arr].astype(np.int32), fr_d=dims[fr_k_arr].astype(np.int32),
+                bc_p=pstart[bc_i_arr].astype(np.int32), bc_d=dims[bc_i_arr].astype(np.int32))
     stats = dict(nnz_L=float(data_size), flops=float(flops), levels=float(nlev), max_front=float(max((len(s) + 1 for s in struct), default=0)),
                  num_updates=float(up_ptr[-1]))
     return SparsePlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, col_start=col_start, pstart=pstart,
                       struct=struct, level=level, blk_index=blk_index, blk_off=blk_off, blk_rows=blk_rows, blk_cols=blk_cols,
-                      data_size=data_size, winv_off=winv_off, winv_size=winv_size, arrays=arrays, stats=stats)
+                      data_size=data_size, winv_off=winv_off, winv_size=winv_size, arrays=arrays, stats=stats, lane=lane)
+
+
+LANE_DIMS = (1, 2, 3, 6)   # block sizes the batch-lane kernels are instantiated for (thb_sparse_lane.cu)
+LANE_HEAVY = 8             # update pairs per target block from which the split-K variant of the update kernel is used
+LN_U, LN_T, LN_S, LN_UH = 0, 1, 2, 3
+
+
+def _lane_lists(N, nlev, cols_by_level, struct, dims, blk_index, blk_off, up_ptr, winv_off, pstart):
+    """Work lists for the batch-lane kernels: per level, the target blocks grouped by (rows, cols) class, because those
+    kernels keep a whole block in registers and are compiled per block shape.  `launches` is a HOST array of
+    (kind, di, dj, begin, end) rows in execution order: kind U = left-looking update of blocks [begin,end) of u_*,
+    UH = the same for blocks with many update pairs (split over 8 warps), T = diagonal factor + triangular solve of blocks
+    [begin,end) of t_*, S = columns [begin,end) of s_col for the substitutions (forward: in order, backward: reversed)."""
+    u_tgt, u_p0, u_p1 = [], [], []
+    t_off, t_diag, t_dl, t_pstart = [], [], [], []
+    s_col = []
+    launches = []
+    for lv in range(nlev):
+        ucls: Dict[Tuple[int, int, int], list] = {}
+        tcls: Dict[Tuple[int, int], list] = {}
+        scls: Dict[int, list] = {}
+        for j in cols_by_level[lv]:
+            dj = int(dims[j])
+            scls.setdefault(dj, []).append(j)
+            dg = int(blk_off[blk_index[(j, j)]])
+            for i in [j] + [int(x) for x in struct[j]]:
+                t = blk_index[(i, j)]
+                di = int(dims[i])
+                npairs = int(up_ptr[t + 1] - up_ptr[t])
+                if npairs > 0:
+                    ucls.setdefault((1 if npairs >= LANE_HEAVY else 0, di, dj), []).append(t)
+                tcls.setdefault((di, dj), []).append((t, dg, j))
+        for (heavy, di, dj) in sorted(ucls):
+            b0 = len(u_tgt)
+            for t in ucls[(heavy, di, dj)]:
+                u_tgt.append(int(blk_off[t])); u_p0.append(int(up_ptr[t])); u_p1.append(int(up_ptr[t + 1]))
+            launches.append((LN_UH if heavy else LN_U, di, dj, b0, len(u_tgt)))
+        for (di, dj) in sorted(tcls):
+            b0 = len(t_off)
+            for (t, dg, j) in tcls[(di, dj)]:
+                t_off.append(int(blk_off[t])); t_diag.append(dg); t_dl.append(int(winv_off[j])); t_pstart.append(int(pstart[j]))
+            launches.append((LN_T, di, dj, b0, len(t_off)))
+        for dj in sorted(scls):
+            b0 = len(s_col)
+            s_col.extend(scls[dj])
+            launches.append((LN_S, dj, dj, b0, len(s_col)))
+    i64 = np.int64
+    return dict(u_tgt=np.array(u_tgt, dtype=i64), u_p0=np.array(u_p0, dtype=i64), u_p1=np.array(u_p1, dtype=i64),
+                t_off=np.array(t_off, dtype=i64), t_diag=np.array(t_diag, dtype=i64), t_dl=np.array(t_dl, dtype=i64),
+                t_pstart=np.array(t_pstart, dtype=np.int32), s_col=np.array(s_col, dtype=np.int32),
+                launches=np.array(launches, dtype=np.int32).reshape(-1, 5))
 
 
 def gram_out_offsets(plan: SparsePlan):

@@ -13,16 +13,17 @@ import numpy as np
 import torch
 
 from . import _lib
+from .autograd import LinearSolveFunction, wants_grad
 from .core import Objective
 from .optimizer import (Linearization, LinearSolver, SparseLinearization, convert_to_alpha_beta_damping_tensors)
-from .sparse import analyze, gram_out_offsets
+from .sparse import LANE_DIMS, analyze, gram_out_offsets
 from .structure import ata_block_structure, build_gram_plan
 
 
 class BaspachoSparseSolver(LinearSolver):
     def __init__(self, objective: Objective, linearization_cls: Optional[Type[Linearization]] = None,
                  linearization_kwargs: Optional[Dict[str, Any]] = None, num_solver_contexts=1, batch_size: Optional[int] = None,
-                 auto_reset: bool = True, dev: Optional[str] = None, ordering: str = "mindeg", **kwargs):
+                 auto_reset: bool = True, dev: Optional[str] = None, ordering: str = "mindeg", layout: Optional[str] = None, **kwargs):
         linearization_cls = linearization_cls or SparseLinearization
         if not linearization_cls == SparseLinearization:
             raise RuntimeError(
@@ -31,12 +32,13 @@ class BaspachoSparseSolver(LinearSolver):
         super().__init__(objective, linearization_cls, linearization_kwargs, **kwargs)
         self.linearization: SparseLinearization = self.linearization
         self._ordering = ordering
+        self._layout = layout
         self._plan = None
         self._dev = None
         self.reset()
 
     @classmethod
-    def from_structure(cls, structure, ordering: str = "mindeg") -> "BaspachoSparseSolver":
+    def from_structure(cls, structure, ordering: str = "mindeg", layout: Optional[str] = None) -> "BaspachoSparseSolver":
         """Solver over a bare CSR structure with hand-filled `linearization.A_val / b` -- the pattern of the reference's own
         solver tests (void Objective + filled linearization, tests/theseus_tests/optimizer/linear/test_baspacho_sparse_solver.py:15-41)."""
         class _Lin:
@@ -49,7 +51,7 @@ class BaspachoSparseSolver(LinearSolver):
                 return self._S
         self = cls.__new__(cls)
         self.linearization = _Lin(structure)
-        self._ordering, self._plan, self._dev = ordering, None, None
+        self._ordering, self._plan, self._dev, self._layout = ordering, None, None, layout
         self.reset()
         return self
 
@@ -62,6 +64,18 @@ class BaspachoSparseSolver(LinearSolver):
         self.param_size, self.block_ptrs, self.block_inds = param_size, ptrs, inds  # the reference's SymbolicDecomposition inputs
         self._plan = analyze(param_size, ptrs, inds, ordering=self._ordering)
         self._gram_arrays = build_gram_plan(S, out_offsets=gram_out_offsets(self._plan), pos=self._plan.pos)
+
+    def layout_for(self, B: int) -> str:
+        """'lane' (batch-interleaved factor, one warp = 32 batch items, thb_sparse_lane.cu) or 'item' (one CTA per batch item,
+        thb_sparse.cu).  Default: lane whenever a warp can be filled and every block size is one the lane kernels are built for."""
+        lane_ok = all(int(d) in LANE_DIMS for d in self._plan.dims)
+        if self._layout is not None:
+            if self._layout not in ("lane", "item"):
+                raise ValueError(f"layout must be 'lane' or 'item', got {self._layout}")
+            if self._layout == "lane" and not lane_ok:
+                raise ValueError(f"layout='lane' needs block sizes in {LANE_DIMS}")
+            return self._layout
+        return "lane" if (lane_ok and B >= 32) else "item"
 
     @property
     def symbolic_stats(self):
@@ -77,14 +91,22 @@ class BaspachoSparseSolver(LinearSolver):
                                    **{k: dev[k].data_ptr() for k in dev})
         g = self._gram_arrays
         gdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in g.items() if isinstance(v, np.ndarray)}
-        gst = _lib.GramPlan(
-            num_entries=int(g["ent_blk"].shape[0]), ent_blk=gdev["ent_blk"].data_ptr(), ent_p=gdev["ent_p"].data_ptr(),
-            ent_q=gdev["ent_q"].data_ptr(), blk_out=gdev["blk_out"].data_ptr(), blk_ld=gdev["blk_ld"].data_ptr(),
-            blk_mirror=gdev["blk_mirror"].data_ptr(), blk_cptr=gdev["blk_cptr"].data_ptr(), c_off=gdev["c_off"].data_ptr(),
-            c_stride=gdev["c_stride"].data_ptr(), c_rows=gdev["c_rows"].data_ptr(), c_bpa=gdev["c_bpa"].data_ptr(),
-            c_bpb=gdev["c_bpb"].data_ptr(), n=int(g["n"]), col_cptr=gdev["col_cptr"].data_ptr(), cc_off=gdev["cc_off"].data_ptr(),
-            cc_stride=gdev["cc_stride"].data_ptr(), cc_rows=gdev["cc_rows"].data_ptr(), cc_row0=gdev["cc_row0"].data_ptr())
-        self._dev = dict(device=device, plan=st, keep=dev, gram=gst, gkeep=gdev, bufs={})
+        gst = _lib.make_gram_plan(g, gdev)
+        # batch-lane plan: shares the batch-independent arrays above, adds the per-level / per-shape work lists
+        ln = P.lane
+        ldev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in ln.items() if k != "launches"}
+        launches = np.ascontiguousarray(ln["launches"], dtype=np.int32)
+        lst = _lib.SparseLanePlanStruct(
+            N=P.N, n=P.n, data_size=P.data_size, diag_size=P.winv_size, num_launches=int(launches.shape[0]),
+            launches=launches.ctypes.data, dims=dev["dims"].data_ptr(), col_start=dev["col_start"].data_ptr(),
+            pstart=dev["pstart"].data_ptr(), dl_off=dev["winv_off"].data_ptr(), diag_off=dev["diag_off"].data_ptr(),
+            up_a=dev["up_a"].data_ptr(), up_b=dev["up_b"].data_ptr(), up_k=dev["up_k"].data_ptr(),
+            u_tgt=ldev["u_tgt"].data_ptr(), u_p0=ldev["u_p0"].data_ptr(), u_p1=ldev["u_p1"].data_ptr(),
+            t_off=ldev["t_off"].data_ptr(), t_diag=ldev["t_diag"].data_ptr(), t_dl=ldev["t_dl"].data_ptr(),
+            t_pstart=ldev["t_pstart"].data_ptr(), s_col=ldev["s_col"].data_ptr(),
+            fr_ptr=dev["fr_ptr"].data_ptr(), fr_off=dev["fr_off"].data_ptr(), fr_p=ldev["fr_p"].data_ptr(), fr_d=ldev["fr_d"].data_ptr(),
+            bc_ptr=dev["bc_ptr"].data_ptr(), bc_off=dev["bc_off"].data_ptr(), bc_p=ldev["bc_p"].data_ptr(), bc_d=ldev["bc_d"].data_ptr())
+        self._dev = dict(device=device, plan=st, keep=dev, gram=gst, gkeep=gdev, bufs={}, lane=lst, lkeep=(ldev, launches))
         return self._dev
 
     # ---- numeric phase (baspacho_sparse_autograd.py:21-65) ----
@@ -94,44 +116,85 @@ class BaspachoSparseSolver(LinearSolver):
         A_val, b = lin.A_val, lin.b
         if A_val is None:
             raise RuntimeError("linearize() must be called before solve()")
+        if wants_grad(A_val, b):
+            detach = bool(getattr(lin, "detached_hessian", False))
+            return LinearSolveFunction.apply(A_val, b, self, damping, ellipsoidal_damping, damping_eps, detach)
+        return self._solve_nograd(A_val, b, damping, ellipsoidal_damping, damping_eps)[0]
+
+    def _solve_nograd(self, A_val, b, damping, ellipsoidal_damping, damping_eps):
         out_dtype = A_val.dtype
-        if A_val.dtype != torch.float64:
-            A_val, b = A_val.double(), b.double()
-        B = A_val.shape[0]
-        device = A_val.device
-        d = self._device_plan(device)
-        P = self._plan
-        lib = _lib.load()
-        s = _lib.stream_ptr()
-        key = (B,)
-        if d["bufs"].get("key") != key:
-            d["bufs"] = dict(key=key,
-                             factor=torch.empty(B, P.data_size, dtype=torch.float64, device=device),
-                             winv=torch.empty(B, P.winv_size, dtype=torch.float64, device=device),
-                             Atb=torch.empty(B, P.n, dtype=torch.float64, device=device),
-                             work=torch.empty(B, P.n, dtype=torch.float64, device=device),
-                             info=torch.empty(B, dtype=torch.int32, device=device))
-        bufs = d["bufs"]
-        factor, winv, Atb, work, info = bufs["factor"], bufs["winv"], bufs["Atb"], bufs["work"], bufs["info"]
-        nnz, m = A_val.shape[1], b.shape[1]
-        # add_MtM + tmat_vec: every structurally non-zero block of L's pattern that is not in AtA must start at zero
-        _lib.check(lib.thb_fill_zero(_lib.ptr(factor), factor.numel() * 8, s), "fill_zero")
-        _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(factor), P.data_size,
-                                    _lib.ptr(Atb), None, s), "gram(sparse)")
+        A64, b64 = A_val.detach(), b.detach()
+        if A64.dtype != torch.float64:
+            A64, b64 = A64.double(), b64.double()  # the sparse path computes in fp64 like the reference (baspacho_sparse_autograd.py:41,65)
+        A64, b64 = A64.contiguous(), b64.contiguous()
+        alpha = beta = None
         if damping is not None:
-            alpha, beta = convert_to_alpha_beta_damping_tensors(damping, damping_eps, ellipsoidal_damping, B, device, torch.float64)
-            _lib.check(lib.thb_sparse_damp_f64(C.byref(d["plan"]), _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta), B, s), "sparse_damp")
-            self._keep = (alpha, beta)
-        _lib.check(lib.thb_sparse_factor_f64(C.byref(d["plan"]), _lib.ptr(factor), _lib.ptr(winv), _lib.ptr(info), B, s), "sparse_factor")
-        x = torch.empty(B, P.n, dtype=torch.float64, device=device)
-        _lib.check(lib.thb_sparse_solve_f64(C.byref(d["plan"]), _lib.ptr(factor), _lib.ptr(winv), _lib.ptr(Atb), _lib.ptr(x), _lib.ptr(work), B, s),
-                   "sparse_solve")
-        self._last = (A_val, b)
+            alpha, beta = convert_to_alpha_beta_damping_tensors(damping, damping_eps, ellipsoidal_damping, A64.shape[0], A64.device, torch.float64)
+        Atb = self._numeric(A64, b64, alpha, beta)
+        x = self._substitute(Atb)
+        self._raise_if_bad(self._dev["bufs"]["info"])
+        return x.to(out_dtype), (A64, b64, x, alpha, beta)
+
+    @staticmethod
+    def _raise_if_bad(info):
         bad = info.nonzero()
         if bad.numel() > 0:
             k = int(bad[0, 0])
             raise RuntimeError(f"block-sparse Cholesky: batch element {k}: matrix is not positive definite (pivot {int(info[k])})")
-        return x.to(out_dtype)
+
+    def _numeric(self, A_val, b, alpha, beta):
+        """add_MtM -> damp -> factor (+ Atb) on fp64 inputs; leaves the factor in the solver's buffers."""
+        B, device = A_val.shape[0], A_val.device
+        d = self._device_plan(device)
+        P = self._plan
+        lib = _lib.load()
+        s = _lib.stream_ptr()
+        layout = self.layout_for(B)
+        key = (B, layout)
+        if d["bufs"].get("key") != key:
+            Bp = int(lib.thb_sparse_lane_padded_batch(B))
+            shape = (lambda k: (k, Bp)) if layout == "lane" else (lambda k: (B, k))
+            d["bufs"] = dict(key=key, factor=torch.empty(shape(P.data_size), dtype=torch.float64, device=device),
+                             diag=torch.empty(shape(P.winv_size), dtype=torch.float64, device=device),   # W_j = L_jj^-1 (item) / L_jj with reciprocal diagonal (lane)
+                             work=torch.empty(shape(P.n), dtype=torch.float64, device=device),
+                             Atb=torch.empty(B, P.n, dtype=torch.float64, device=device),
+                             info=torch.empty(B, dtype=torch.int32, device=device))
+        bufs = d["bufs"]
+        factor, diag, Atb, info = bufs["factor"], bufs["diag"], bufs["Atb"], bufs["info"]
+        nnz, m = A_val.shape[1], b.shape[1]
+        self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
+        # every structurally non-zero block of L that is not in AtA (fill-in) must start at zero
+        _lib.check(lib.thb_fill_zero(_lib.ptr(factor), factor.numel() * 8, s), "fill_zero")
+        if layout == "lane":
+            _lib.check(lib.thb_sparse_lane_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(factor), s), "gram(lane)")
+            _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, None, 0, _lib.ptr(Atb), None, s), "Atb")
+            if alpha is not None:
+                _lib.check(lib.thb_sparse_lane_damp_f64(C.byref(d["lane"]), _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta), B, s), "lane_damp")
+            _lib.check(lib.thb_sparse_lane_factor_f64(C.byref(d["lane"]), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info), B, s), "lane_factor")
+        else:
+            _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(factor), P.data_size,
+                                        _lib.ptr(Atb), None, s), "gram(sparse)")
+            if alpha is not None:
+                _lib.check(lib.thb_sparse_damp_f64(C.byref(d["plan"]), _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta), B, s), "sparse_damp")
+            _lib.check(lib.thb_sparse_factor_f64(C.byref(d["plan"]), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info), B, s), "sparse_factor")
+        self._keep = (A_val, b, alpha, beta)
+        return Atb
+
+    def _substitute(self, rhs: torch.Tensor) -> torch.Tensor:
+        """x = (L L^T)^-1 rhs with the factor of the last _numeric call (NumericDecomposition.solve); rhs, x: [B,n] fp64."""
+        d, P = self._dev, self._plan
+        bufs = d["bufs"]
+        B, layout = bufs["key"]
+        lib = _lib.load()
+        rhs = rhs.contiguous()
+        x = torch.empty(B, P.n, dtype=torch.float64, device=rhs.device)
+        if layout == "lane":
+            _lib.check(lib.thb_sparse_lane_solve_f64(C.byref(d["lane"]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
+                                                     _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "lane_solve")
+        else:
+            _lib.check(lib.thb_sparse_solve_f64(C.byref(d["plan"]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
+                                                _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "sparse_solve")
+        return x
 
 
 BlockSparseSolver = BaspachoSparseSolver

@@ -127,10 +127,13 @@ def build_gram_plan(s: Structure, out_offsets=None, pos=None):
     n = s.num_cols
     ent_blk, ent_p, ent_q = [], [], []
     blk_out, blk_ld, blk_mirror, blk_cptr = [], [], [], [0]
+    blk_rows, blk_cols = [], []
     c_off, c_stride, c_rows, c_bpa, c_bpb = [], [], [], [], []
     for k, (i, j) in enumerate(blocks):
         di, dj = int(s.var_dims[i]), int(s.var_dims[j])
         pp, qq = np.meshgrid(np.arange(di), np.arange(dj), indexing="ij")
+        blk_rows.append(di)
+        blk_cols.append(dj)
         ent_blk.append(np.full(di * dj, k, dtype=np.int32))
         ent_p.append(pp.reshape(-1).astype(np.int16))
         ent_q.append(qq.reshape(-1).astype(np.int16))
@@ -174,6 +177,7 @@ def build_gram_plan(s: Structure, out_offsets=None, pos=None):
         ent_blk=cat(ent_blk, np.int32), ent_p=cat(ent_p, np.int16), ent_q=cat(ent_q, np.int16),
         blk_out=np.array(blk_out, dtype=np.int64), blk_ld=np.array(blk_ld, dtype=np.int32),
         blk_mirror=np.array(blk_mirror, dtype=np.int64), blk_cptr=np.array(blk_cptr, dtype=np.int32),
+        blk_rows=np.array(blk_rows, dtype=np.int32), blk_cols=np.array(blk_cols, dtype=np.int32),
         c_off=np.array(c_off, dtype=np.int64), c_stride=np.array(c_stride, dtype=np.int32),
         c_rows=np.array(c_rows, dtype=np.int32), c_bpa=np.array(c_bpa, dtype=np.int32),
         c_bpb=np.array(c_bpb, dtype=np.int32),
