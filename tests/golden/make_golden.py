@@ -430,8 +430,10 @@ def backward_inputs(torch, B=3, seed=21):
 BACKWARD_CASES = {
     "implicit_gn": ("gn", 12, dict(backward_mode="implicit")),
     "unroll_gn": ("gn", 5, dict(backward_mode="unroll")),
-    "truncated_lm": ("lm", 10, dict(backward_mode="truncated", backward_num_iterations=3, damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)),
-    "unroll_lm": ("lm", 6, dict(backward_mode="unroll", damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)),
+    # LM with adaptive damping on the tape: every taped iteration must be a DECISIVE one (clear error reduction), otherwise the
+    # accept/reject of a converged step is rounding noise and so is which steps carry gradient -> strong damping, few iterations
+    "truncated_lm": ("lm", 5, dict(backward_mode="truncated", backward_num_iterations=2, damping=2.0, adaptive_damping=True, ellipsoidal_damping=True)),
+    "unroll_lm": ("lm", 4, dict(backward_mode="unroll", damping=2.0, adaptive_damping=True, ellipsoidal_damping=True)),
     "implicit_lm": ("lm", 12, dict(backward_mode="implicit", damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)),
 }
 
@@ -447,7 +449,10 @@ def make_backward(th):
         layer = th.TheseusLayer(opt)
         inp, w = backward_inputs(torch)
         leaves = {k: inp[k].clone().requires_grad_(True) for k in ("x", "y", "t")}
-        sol, info = layer.forward({**leaves, "ab": inp["ab"].clone(), "c": inp["c"].clone()}, optimizer_kwargs=dict(kw))
+        sol, info = layer.forward({**leaves, "ab": inp["ab"].clone(), "c": inp["c"].clone()}, optimizer_kwargs=dict(kw, track_err_history=True))
+        eh = info.err_history.numpy()
+        out[name + "_err_history"] = eh
+        print("   rel. error reduction per iteration:", np.array2string(((eh[:, :-1] - eh[:, 1:]) / eh[:, :-1]).min(axis=0), precision=2))
         loss = (torch.cat([sol["ab"], sol["c"]], 1) ** 2 * w).sum()
         loss.backward()
         out[name + "_ab"] = sol["ab"].detach().numpy(); out[name + "_c"] = sol["c"].detach().numpy()

@@ -36,8 +36,9 @@ def csr_on_device(lin, device):
     """(A_row_ptr, A_col_ind, m, n) with int64 device index tensors, cached on the linearization object."""
     c = getattr(lin, "_csr_dev", None)
     if c is None or c[0].device != device:
-        c = (torch.from_numpy(np.ascontiguousarray(lin.A_row_ptr, dtype=np.int64)).to(device),
-             torch.from_numpy(np.ascontiguousarray(lin.A_col_ind, dtype=np.int64)).to(device), int(lin.num_rows), int(lin.num_cols))
+        S = lin if hasattr(lin, "A_row_ptr") else lin.engine.structure  # DenseLinearization: the CSR lives in the engine's structure
+        c = (torch.from_numpy(np.ascontiguousarray(S.A_row_ptr, dtype=np.int64)).to(device),
+             torch.from_numpy(np.ascontiguousarray(S.A_col_ind, dtype=np.int64)).to(device), int(lin.num_rows), int(lin.num_cols))
         lin._csr_dev = c
     return c
 
@@ -47,6 +48,8 @@ class LinearSolveFunction(torch.autograd.Function):
     def forward(ctx, A_val, b, solver, damping, ellipsoidal_damping, damping_eps, detach_hessian):
         x, (A64, b64, x64, alpha, beta) = solver._solve_nograd(A_val, b, damping, ellipsoidal_damping, damping_eps)
         ctx.solver, ctx.stamp, ctx.detach = solver, solver._factor_stamp, detach_hessian
+        # the LM control kernel updates the damping tensor IN PLACE after every step: keep this iteration's values
+        alpha, beta = (alpha.clone(), beta.clone()) if alpha is not None else (None, None)
         ctx.saved = (A64, b64, x64, alpha, beta)
         ctx.in_dtypes = (A_val.dtype, b.dtype)
         return x

@@ -7,6 +7,7 @@ Same class names, constructor / solve / optimize kwargs, info fields and error b
 nonlinear_least_squares.py:138-152), so the parity tests read like the reference's own tests.  The
 arithmetic is the CUDA library; the Python below only sequences kernel launches.
 """
+import ctypes as C
 import math
 import warnings
 from dataclasses import dataclass
