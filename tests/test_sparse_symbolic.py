@@ -71,6 +71,81 @@ def run_plan_numpy(plan, M, rhs):
     return x
 
 
+def run_lane_plan_numpy(plan, M, rhs):
+    """Interpret plan.lane (the work lists of thb_sparse_lane.cu) in launch order: U / UH = left-looking update of a block,
+    T = Cholesky of the column's diagonal block (to `diagl`, reciprocal diagonal) + triangular solve of the block, S = substitutions."""
+    A, Ln = plan.arrays, plan.lane
+    N, dims, cs = plan.N, plan.dims, plan.col_start
+    F = np.zeros(plan.data_size)
+    for (i, j), t in plan.blk_index.items():
+        blk = M[cs[i]:cs[i] + dims[i], cs[j]:cs[j] + dims[j]]
+        F[plan.blk_off[t]:plan.blk_off[t] + blk.size] = blk.reshape(-1)
+    DL = np.zeros(plan.winv_size)
+    seen_u = set()
+    for kind, di, dj, b0, b1 in Ln["launches"]:
+        if kind in (0, 3):
+            for e in range(b0, b1):
+                tgt = Ln["u_tgt"][e]
+                assert tgt not in seen_u
+                seen_u.add(tgt)
+                T = F[tgt:tgt + di * dj].reshape(di, dj).copy()
+                npairs = Ln["u_p1"][e] - Ln["u_p0"][e]
+                assert (npairs >= 8) == (kind == 3)
+                for p in range(Ln["u_p0"][e], Ln["u_p1"][e]):
+                    dk = A["up_k"][p]
+                    T -= F[A["up_a"][p]:A["up_a"][p] + di * dk].reshape(di, dk) @ F[A["up_b"][p]:A["up_b"][p] + dj * dk].reshape(dj, dk).T
+                F[tgt:tgt + di * dj] = T.reshape(-1)
+        elif kind == 1:
+            diag_writes = {}
+            for e in range(b0, b1):   # every item reads the PRE-factor diagonal block: collect, then write
+                off, dg, dl = Ln["t_off"][e], Ln["t_diag"][e], Ln["t_dl"][e]
+                D = np.tril(F[dg:dg + dj * dj].reshape(dj, dj))
+                L = np.linalg.cholesky(D + np.tril(D, -1).T)
+                if off == dg:
+                    assert di == dj
+                    Lr = L.copy()
+                    Lr[np.arange(dj), np.arange(dj)] = 1.0 / np.diag(L)
+                    diag_writes[dl] = Lr
+                else:
+                    X = np.linalg.solve(L, F[off:off + di * dj].reshape(di, dj).T).T   # X L^T = U
+                    F[off:off + di * dj] = X.reshape(-1)
+            for dl, Lr in diag_writes.items():
+                DL[dl:dl + Lr.size] = Lr.reshape(-1)
+
+    def diag_solve(j, s, transpose):
+        d = dims[j]
+        Lr = DL[A["winv_off"][j]:A["winv_off"][j] + d * d].reshape(d, d).copy()
+        Lr[np.arange(d), np.arange(d)] = 1.0 / np.diag(Lr)
+        return np.linalg.solve(Lr.T if transpose else Lr, s)
+
+    y = [None] * N
+    S_launches = [l for l in Ln["launches"] if l[0] == 2]
+    for _, dj, _, b0, b1 in S_launches:
+        for j in Ln["s_col"][b0:b1]:
+            assert dims[j] == dj
+            s = rhs[cs[j]:cs[j] + dj].copy()
+            for p in range(A["fr_ptr"][j], A["fr_ptr"][j + 1]):
+                dk, pk = Ln["fr_d"][p], Ln["fr_p"][p]
+                k = int(np.searchsorted(plan.pstart, pk))
+                assert plan.pstart[k] == pk and dims[k] == dk and y[k] is not None
+                s -= F[A["fr_off"][p]:A["fr_off"][p] + dj * dk].reshape(dj, dk) @ y[k]
+            y[j] = diag_solve(j, s, False)
+    xs = [None] * N
+    for _, dj, _, b0, b1 in reversed(S_launches):
+        for j in Ln["s_col"][b0:b1]:
+            s = y[j].copy()
+            for p in range(A["bc_ptr"][j], A["bc_ptr"][j + 1]):
+                di, pi = Ln["bc_d"][p], Ln["bc_p"][p]
+                i = int(np.searchsorted(plan.pstart, pi))
+                assert plan.pstart[i] == pi and dims[i] == di and xs[i] is not None
+                s -= F[A["bc_off"][p]:A["bc_off"][p] + di * dj].reshape(di, dj).T @ xs[i]
+            xs[j] = diag_solve(j, s, True)
+    x = np.zeros_like(rhs)
+    for j in range(N):
+        x[cs[j]:cs[j] + dims[j]] = xs[j]
+    return x
+
+
 def random_block_spd(rng, sizes, fill):
     """Random block-sparse SPD matrix in the style of theseus/utils/sparse_matrix_utils.py:193-227 + AtA + I."""
     N = len(sizes)
@@ -112,6 +187,30 @@ def test_plan_solves_system(sizes, fill, ordering):
     rhs = rng.standard_normal(M.shape[0])
     x = run_plan_numpy(plan, M, rhs)
     assert np.abs(M @ x - rhs).max() < 1e-10   # the reference's criterion (extlib/test_baspacho.py:101-114)
+
+
+@pytest.mark.parametrize("sizes,fill,ordering", [
+    ([6] * 12, 0.15, "mindeg"),
+    ([6] * 14, 0.9, "natural"),                  # dense: the last blocks have >= 8 update pairs (split-K launches)
+    ([1, 2, 3, 6, 3, 3, 6, 6, 2, 1, 6], 0.25, "mindeg"),
+    ([3] * 30 + [6] * 5, 0.08, "mindeg"),
+])
+def test_lane_work_lists_solve_system(sizes, fill, ordering):
+    """The per-level / per-shape launch list of the batch-lane kernels, executed in order by a numpy interpreter."""
+    rng = np.random.default_rng(len(sizes) + int(fill * 100) + 1)
+    M, ptrs, inds = random_block_spd(rng, sizes, fill)
+    plan = analyze(np.array(sizes), ptrs, inds, ordering=ordering)
+    launches = plan.lane["launches"]
+    assert launches.dtype == np.int32 and launches.shape[1] == 5
+    if fill > 0.5:
+        assert (launches[:, 0] == 3).any()
+    rhs = rng.standard_normal(M.shape[0])
+    x = run_lane_plan_numpy(plan, M, rhs)
+    assert np.abs(M @ x - rhs).max() < 1e-10
+    # every block of L is triangular-solved exactly once, every column substituted exactly once
+    nT = sum(b1 - b0 for k, _, _, b0, b1 in launches if k == 1)
+    nS = sum(b1 - b0 for k, _, _, b0, b1 in launches if k == 2)
+    assert nT == len(plan.blk_off) and nS == plan.N
 
 
 def test_minimum_degree_eliminates_leaves_first_and_is_deterministic():
