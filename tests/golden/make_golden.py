@@ -438,6 +438,74 @@ BACKWARD_CASES = {
 }
 
 
+def autodiff_lie_problem(th, torch, inputs):
+    """Point-set alignment with AutoDiffCostFunctions over Lie-group variables (err_fn works on the raw storage tensors):
+    SE3 pose T3: e = R p + t - q (K=6 points), SE2 pose T2: e = R(cos,sin) p2 + t2 - q2 (K=5 points).  Shared by generator and tests."""
+    dtype = torch.float64
+    T3 = th.SE3(tensor=inputs["T3"].clone(), name="T3")
+    T2 = th.SE2(tensor=inputs["T2"].clone(), name="T2")
+    p, q = th.Variable(inputs["p"].clone(), name="p"), th.Variable(inputs["q"].clone(), name="q")
+    p2, q2 = th.Variable(inputs["p2"].clone(), name="p2"), th.Variable(inputs["q2"].clone(), name="q2")
+
+    def err3(optim_vars, aux_vars):
+        g = optim_vars[0].tensor
+        pp, qq = aux_vars[0].tensor, aux_vars[1].tensor          # [B,K,3]
+        r = torch.einsum("bij,bkj->bki", g[:, :, :3], pp) + g[:, None, :, 3] - qq
+        return r.reshape(r.shape[0], -1)
+
+    def err2(optim_vars, aux_vars):
+        g = optim_vars[0].tensor                                  # [B,4] = x, y, cos, sin
+        pp, qq = aux_vars[0].tensor, aux_vars[1].tensor          # [B,K,2]
+        c, s_ = g[:, None, 2], g[:, None, 3]
+        rx = c * pp[..., 0] - s_ * pp[..., 1] + g[:, None, 0] - qq[..., 0]
+        ry = s_ * pp[..., 0] + c * pp[..., 1] + g[:, None, 1] - qq[..., 1]
+        return torch.stack((rx, ry), dim=-1).reshape(g.shape[0], -1)
+
+    objective = th.Objective(dtype=dtype)
+    objective.add(th.AutoDiffCostFunction([T3], err3, 18, aux_vars=[p, q], cost_weight=th.ScaleCostWeight(torch.tensor(1.5, dtype=dtype)), name="align3"))
+    objective.add(th.AutoDiffCostFunction([T2], err2, 10, aux_vars=[p2, q2], cost_weight=th.ScaleCostWeight(torch.tensor(0.7, dtype=dtype)), name="align2"))
+    return objective
+
+
+def make_autodiff_lie(th):
+    """AutoDiffCostFunction over SE3 / SE2 variables: vmap(jacrev) Euclidean Jacobians + project (cost_function.py:343-393)."""
+    import torch
+    g = torch.Generator().manual_seed(33)
+    B = 3
+    d = torch.float64
+    Tgt3 = th.SE3.exp_map(0.6 * torch.randn(B, 6, generator=g, dtype=d))
+    Tgt2 = th.SE2.exp_map(0.8 * torch.randn(B, 3, generator=g, dtype=d))
+    p = torch.randn(B, 6, 3, generator=g, dtype=d)
+    q = torch.einsum("bij,bkj->bki", Tgt3.tensor[:, :, :3], p) + Tgt3.tensor[:, None, :, 3] + 0.01 * torch.randn(B, 6, 3, generator=g, dtype=d)
+    p2 = torch.randn(B, 5, 2, generator=g, dtype=d)
+    c, s_ = Tgt2.tensor[:, None, 2], Tgt2.tensor[:, None, 3]
+    q2 = torch.stack((c * p2[..., 0] - s_ * p2[..., 1] + Tgt2.tensor[:, None, 0], s_ * p2[..., 0] + c * p2[..., 1] + Tgt2.tensor[:, None, 1]), -1)
+    q2 = q2 + 0.01 * torch.randn(B, 5, 2, generator=g, dtype=d)
+    T3_0 = th.SE3.exp_map(0.3 * torch.randn(B, 6, generator=g, dtype=d)).compose(Tgt3)
+    T2_0 = th.SE2.exp_map(0.3 * torch.randn(B, 3, generator=g, dtype=d)).compose(Tgt2)
+    inputs = dict(T3=T3_0.tensor, T2=T2_0.tensor, p=p, q=q, p2=p2, q2=q2)
+    objective = autodiff_lie_problem(th, torch, inputs)
+    iters = 6
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=iters, step_size=1.0,
+                                abs_err_tolerance=0, rel_err_tolerance=0)
+    lin = th.SparseLinearization(objective)
+    objective.update()
+    lin.linearize()
+    out = {k: v.numpy() for k, v in inputs.items()}
+    out["A_val0"], out["b0"] = lin.A_val.numpy().copy(), lin.b.numpy().copy()
+    deltas, errs = [], []
+
+    def cb(optimizer, info, delta, it):
+        deltas.append(delta.detach().numpy().copy()); errs.append(info.last_err.detach().numpy().copy())
+
+    with torch.no_grad():
+        info = opt.optimize(end_iter_callback=cb, damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
+    out["trace_delta"], out["trace_err"] = np.stack(deltas, 0), np.stack(errs, 0)
+    out["final_T3"], out["final_T2"] = objective.get_optim_var("T3").tensor.numpy(), objective.get_optim_var("T2").tensor.numpy()
+    np.savez_compressed(os.path.join(HERE, "autodiff_lie.npz"), **out)
+    print("autodiff_lie err trace", np.stack(errs, 0)[:, 0])
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -468,6 +536,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "backward":
         make_backward(th)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "autodiff_lie":
+        make_autodiff_lie(th)
+        sys.exit(0)
     make_lie(th, lieF)
     make_costs(th)
     make_dense_solver(th)
@@ -487,3 +558,4 @@ if __name__ == "__main__":
     make_pgo(th, "pgo_small_welsch", num_poses=10, B=3, seed=9, iters=8, lm_kwargs=lm, loop_closure_ratio=0.6, robust="welsch",
              outlier_ratio=0.3, init_perturb=0.0)
     make_backward(th)
+    make_autodiff_lie(th)

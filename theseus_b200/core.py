@@ -263,8 +263,8 @@ class AutoDiffCostFunction(CostFunction):
     """theseus/core/cost_function.py:203-420: user-defined error function, Jacobians by vmap(jacrev(err_fn)) -- kept as the
     reference's torch.func path; the results are scattered straight into the batched-CSR Jacobian.
     `err_fn(optim_vars, aux_vars) -> [B, dim]` receives tuples of Variable-like objects exposing `.tensor`.
-    Optimisation variables must be Euclidean (Vector / Point): projecting autograd Jacobians onto Lie tangent spaces
-    (geometry/*.project) is not built in round 1."""
+    Lie-group optimisation variables: the user's err_fn works on the raw storage tensors (`.tensor`, e.g. SE3 [B,3,4]) with torch
+    ops, the Euclidean Jacobians are projected onto the tangent space like `v.project(jac, is_sparse=True)` (cost_function.py:389-391)."""
 
     def __init__(self, optim_vars: Sequence[Manifold], err_fn, dim: int, cost_weight: Optional[CostWeight] = None,
                  aux_vars: Optional[Sequence[Variable]] = None, name: Optional[str] = None, **autograd_kwargs):
@@ -275,8 +275,8 @@ class AutoDiffCostFunction(CostFunction):
         if len(optim_vars) < 1:
             raise ValueError("AutodiffCostFunction must receive at least one optimization variable.")
         for v in optim_vars:
-            if not isinstance(v, Vector):
-                raise NotImplementedError("AutoDiffCostFunction: only Vector/Point optimisation variables are supported in theseus_b200 r1")
+            if not isinstance(v, Manifold):
+                raise ValueError("AutoDiffCostFunction optimisation variables must be Manifold instances")
         self._optim = list(optim_vars)
         self._aux = aux_vars
         for i, v in enumerate(self._optim):
@@ -325,10 +325,11 @@ class AutoDiffCostFunction(CostFunction):
         with torch.enable_grad():
             jacs = vmap(jacrev(one, argnums=0))(opt_t, aux_t)
             err = self._err_fn(optim_vars=tuple(self._T(t) for t in opt_t), aux_vars=tuple(self._T(t) for t in aux_t))
+        # Euclidean -> tangent space (identity for Vector, geometry/vector.py:199-203)
+        jacs = [type(v).project_tensor(t, j) for v, t, j in zip(self._optim, opt_t, jacs)]
         if differentiable:  # backward modes: keep the graph to the aux variables / weights / variable values
-            return self._weight(err, list(jacs))
-        jacs = [j.detach() for j in jacs]  # Vector.project(., is_sparse=True) is the identity (geometry/vector.py:199-203)
-        return self._weight(err.detach(), jacs)
+            return self._weight(err, jacs)
+        return self._weight(err.detach(), [j.detach() for j in jacs])
 
     def schema(self):
         return None, []

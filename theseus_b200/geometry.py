@@ -119,6 +119,17 @@ class Manifold(Variable):
             new_name = f"{self.name}_copy"
         return self.__class__(tensor=self.tensor.clone(), name=new_name)
 
+    @staticmethod
+    def project_tensor(group: torch.Tensor, euclidean_grad: torch.Tensor) -> torch.Tensor:
+        """Euclidean Jacobian [B, dim, *group_shape] (derivative w.r.t. the group's storage entries, what vmap(jacrev) gives)
+        -> tangent-space Jacobian [B, dim, dof]: `Manifold.project(., is_sparse=True)` of the reference, plain torch ops."""
+        raise NotImplementedError
+
+
+def _vee_skew_part(T: torch.Tensor) -> torch.Tensor:
+    """(T32 - T23, T13 - T31, T21 - T12) of the leading 3x3 of T [..., 3, >=3] (so3_impl.py:977-986)."""
+    return torch.stack((T[..., 2, 1] - T[..., 1, 2], T[..., 0, 2] - T[..., 2, 0], T[..., 1, 0] - T[..., 0, 1]), dim=-1)
+
 
 class Vector(Manifold):
     """theseus/geometry/vector.py (Vector): x [+] d = x + d; local(a, b) = b - a."""
@@ -141,6 +152,10 @@ class Vector(Manifold):
 
     def retract(self, delta: torch.Tensor) -> "Vector":
         return self.__class__(tensor=self.tensor + delta)
+
+    @staticmethod
+    def project_tensor(group: torch.Tensor, euclidean_grad: torch.Tensor) -> torch.Tensor:
+        return euclidean_grad  # geometry/vector.py:199-203
 
     def local(self, other: "Vector") -> torch.Tensor:
         return other.tensor - self.tensor
@@ -197,6 +212,12 @@ class SE3(LieGroup):
 
     def dof(self) -> int:
         return 6
+
+    @staticmethod
+    def project_tensor(group: torch.Tensor, euclidean_grad: torch.Tensor) -> torch.Tensor:
+        # left_project (torchlie lie_group.py:36-48): project(R^T G), project = [last column, vee of the skew part] (se3_impl.py:911-923)
+        T = group[:, None, :, :3].transpose(-1, -2) @ euclidean_grad
+        return torch.cat((T[..., 3], _vee_skew_part(T)), dim=-1)
 
     # ---- group arithmetic on the GPU (torchlie.functional.SE3 equivalents) ----
     @staticmethod
@@ -262,6 +283,10 @@ class SO3(LieGroup):
     def dof(self) -> int:
         return 3
 
+    @staticmethod
+    def project_tensor(group: torch.Tensor, euclidean_grad: torch.Tensor) -> torch.Tensor:
+        return _vee_skew_part(group[:, None].transpose(-1, -2) @ euclidean_grad)  # so3_impl.py:977-986 after the left action
+
 
 class SE2(LieGroup):
     """theseus/geometry/se2.py:21 -- storage [B,4] = [x, y, cos, sin], tangent [ux, uy, theta]."""
@@ -281,3 +306,11 @@ class SE2(LieGroup):
 
     def dof(self) -> int:
         return 3
+
+    @staticmethod
+    def project_tensor(group: torch.Tensor, euclidean_grad: torch.Tensor) -> torch.Tensor:
+        # geometry/se2.py:341-358 (is_sparse branch): storage [x, y, cos, sin]
+        cs = group[:, None, 2:]                                   # (cos, sin)
+        perp = torch.stack((-group[:, 3], group[:, 2]), dim=1)[:, None]  # (-sin, cos)
+        g_xy, g_cs = euclidean_grad[..., :2], euclidean_grad[..., 2:]
+        return torch.stack(((g_xy * cs).sum(-1), (g_xy * perp).sum(-1), (g_cs * perp).sum(-1)), dim=-1)
