@@ -322,7 +322,11 @@ def main():
         e2e=dict(value=LM_ITERS * 1e3 / ms_e2e * world, unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
         gpu_launches=launches,
         roofline=dict(bound="tensor", kernel="chol_col_kernel (fp64 DMMA left-looking Cholesky, one launch = one batched factorisation of 256 matrices)", achieved=achieved_tf,
-                      peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf, traffic=None,
+                      peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
+                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this kernel at this size
+                      # (profiles/r01g_chol_col_ncu_full_details.txt): 31.61 GB + 2.78 GB; algorithmic bytes 4.8 GB -- the left-looking
+                      # panels are re-streamed (2.7 TB/s, L2 hit 49 %), the kernel is bound by the FP64 tensor pipe (70.7 % active), not by HBM
+                      traffic=34.40e9, traffic_unit="bytes per launch (ncu, B=256, n=1536)", algorithmic_bytes=8.0 * BATCH * lin.num_cols ** 2,
                       flops_per_factorisation=flops, ms_per_factorisation=ms_factor,
                       peak_source="fp64 cuBLAS dgemm 8192^3 measured live in this run (MEASURED_PEAKS.json carries no fp64 figure; "
                                   f"its bf16/HBM entries [{peaks_src}]: {peaks.get('bf16_tflops')} TF/s, {peaks.get('hbm_gbs')} GB/s)",

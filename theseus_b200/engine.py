@@ -102,6 +102,8 @@ class Engine:
         self.cur_views: List[torch.Tensor] = []
         self.tmp_views: List[torch.Tensor] = []
         self._bind_stamp = {"cur": -1, "tmp": -1}
+        self._bind_sig = {}
+        self._sig_vars = None
         self._vt = None
         self._gram_dense = None
         self._zero_filled = None  # (data_ptr, numel) of the AtA buffer whose off-pattern entries are known to be zero
@@ -134,6 +136,7 @@ class Engine:
         self._bufs = {}
         self._vt = None
         self._bind_stamp = {"cur": -1, "tmp": -1}
+        self._bind_sig = {}
 
     def adopt_optim_vars(self):
         """Move every optimisation variable into the engine-owned pool (copying the current values) so that
@@ -161,6 +164,14 @@ class Engine:
         """(Re)build the pointer tables of every group for binding `which` ('cur' = objective variables,
         'tmp' = trial pool) if any variable tensor was rebound since the last build."""
         if self._bind_stamp[which] == Variable._global_updates:
+            return
+        # Some variable was rebound since the tables were built.  The common case inside a training / serving loop is that every
+        # tensor still lives where it did (objective.update() + adopt_optim_vars() put the new VALUES into the same pool views and
+        # the caller re-uses its input buffers): compare the device pointers before paying for the rebuild (~10 ms at C2: Python over
+        # every cost function + pageable H2D copies of the pointer tables).
+        sig = self._bind_signature(which)
+        if sig is not None and sig == self._bind_sig.get(which):
+            self._bind_stamp[which] = Variable._global_updates
             return
         B = self.batch_size
         if which == "tmp" or self._B is not None:
@@ -234,8 +245,36 @@ class Engine:
             g.bound[which] = (st, keep)
         # NOTE: _bind may itself rebind non-contiguous tensors (bumping the counter); read it afterwards.
         self._bind_stamp[which] = Variable._global_updates
+        self._bind_sig[which] = self._bind_signature(which)
         if which == "cur":
             self._vt = None
+
+    def _bind_signature(self, which: str):
+        """(data_ptr, batch) of every tensor the pointer tables of binding `which` refer to, or None if a tensor would need a
+        contiguous/aligned copy (then the full rebuild handles it)."""
+        if self._sig_vars is None:
+            vs = []
+            for g in self.groups:
+                for f in g.cost_indices:
+                    cf = self.costs[f]
+                    vs.extend(self._aux_of[f])
+                    vs.append(cf.weight.weight_tensor())
+                    if g.robust:
+                        vs.append(cf.log_loss_radius)
+            vs.extend(self.ordering)
+            seen, uniq = set(), []
+            for v in vs:
+                if id(v) not in seen:
+                    seen.add(id(v)); uniq.append(v)
+            self._sig_vars = uniq
+        sig = [self._B if which == "tmp" else -1]
+        for v in self._sig_vars:
+            t = v.tensor
+            p = t.data_ptr()
+            if p % 16 != 0 or not t.is_contiguous():
+                return None
+            sig.append(p); sig.append(t.shape[0])
+        return tuple(sig)
 
     def _var_table(self):
         """thb_var_table: x = current variables, out = trial pool."""
