@@ -506,6 +506,40 @@ def make_autodiff_lie(th):
     print("autodiff_lie err trace", np.stack(errs, 0)[:, 0])
 
 
+BACKWARD_LIE_CASES = {
+    "implicit_gn": ("gn", 10, dict(backward_mode="implicit")),
+    "unroll_gn": ("gn", 4, dict(backward_mode="unroll")),
+    "unroll_lm": ("lm", 3, dict(backward_mode="unroll", damping=1.0, adaptive_damping=True, ellipsoidal_damping=True)),
+}
+
+
+def make_backward_lie(th):
+    """Backward modes with Lie-group variables: the SE3 + SE2 point-alignment objective of make_autodiff_lie, gradients of an outer
+    loss on the optimised poses w.r.t. the observed points q, q2 (the tactile-style use: learn the measurement model end to end)."""
+    import torch
+    base = dict(np.load(os.path.join(HERE, "autodiff_lie.npz")))
+    out = {}
+    for name, (method, iters, kw) in BACKWARD_LIE_CASES.items():
+        inputs = {k: torch.from_numpy(base[k]) for k in ("T3", "T2", "p", "q", "p2", "q2")}
+        objective = autodiff_lie_problem(th, torch, inputs)
+        cls = th.GaussNewton if method == "gn" else th.LevenbergMarquardt
+        opt = cls(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
+        layer = th.TheseusLayer(opt)
+        leaves = {k: inputs[k].clone().requires_grad_(True) for k in ("q", "q2", "p")}
+        sol, info = layer.forward({**leaves, "T3": inputs["T3"].clone(), "T2": inputs["T2"].clone()}, optimizer_kwargs=dict(kw, track_err_history=True))
+        eh = info.err_history.numpy()
+        print("   rel. error reduction per iteration:", np.array2string(((eh[:, :-1] - eh[:, 1:]) / eh[:, :-1]).min(axis=0), precision=2))
+        wgt3 = torch.linspace(0.5, 1.5, 12, dtype=torch.float64).view(1, 3, 4)
+        wgt2 = torch.linspace(-1.0, 1.0, 4, dtype=torch.float64).view(1, 4)
+        loss = (sol["T3"] * wgt3).sum() + (sol["T2"] * wgt2).sum()
+        loss.backward()
+        out[name + "_T3"], out[name + "_T2"] = sol["T3"].detach().numpy(), sol["T2"].detach().numpy()
+        for k in leaves:
+            out[name + "_grad_" + k] = leaves[k].grad.numpy()
+        print("backward_lie", name, "loss", loss.item(), "|grad_q|", float(leaves["q"].grad.abs().max()), "|grad_q2|", float(leaves["q2"].grad.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "backward_lie_kat.npz"), **out)
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -539,6 +573,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "autodiff_lie":
         make_autodiff_lie(th)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "backward_lie":
+        make_backward_lie(th)
+        sys.exit(0)
     make_lie(th, lieF)
     make_costs(th)
     make_dense_solver(th)
@@ -559,3 +596,4 @@ if __name__ == "__main__":
              outlier_ratio=0.3, init_perturb=0.0)
     make_backward(th)
     make_autodiff_lie(th)
+    make_backward_lie(th)

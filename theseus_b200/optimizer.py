@@ -579,15 +579,14 @@ class NonlinearLeastSquares:
         theorem at the fixed point).  On the tape an iteration is: differentiable linearization (torch.func Jacobians of the
         AutoDiffCostFunctions) -> autograd.LinearSolveFunction (fused CUDA forward, closed-form CUDA backward) -> x + delta."""
         from .core import AutoDiffCostFunction
-        from .geometry import Vector
         if backward_mode == BackwardMode.DLM:
             raise NotImplementedError("BackwardMode.DLM is not built (SURVEY.md 8: out of scope)")
         bad_cf = [cf.name for cf in self.objective.cost_functions.values() if not isinstance(cf, AutoDiffCostFunction)]
-        bad_v = [v.name for v in self.ordering if not isinstance(v, Vector)]
+        bad_v = [v.name for v in self.ordering if v.KIND not in (0, 1, 2, 3)]
         if bad_cf or bad_v:
             raise NotImplementedError(
-                "theseus_b200: differentiating through the optimizer is built for objectives of AutoDiffCostFunctions over Vector "
-                f"variables; fused-kernel cost functions {bad_cf[:3]} / Lie-group variables {bad_v[:3]} have no autograd path yet "
+                "theseus_b200: differentiating through the optimizer is built for objectives of AutoDiffCostFunctions (over Vector / SE2 / "
+                f"SE3 / SO3 variables); fused-kernel cost functions {bad_cf[:3]} / variables {bad_v[:3]} have no autograd path yet "
                 "-- wrap the call in torch.no_grad().")
         kwargs_plus = {**kwargs, "backward_mode": backward_mode}
         self.reset(**kwargs_plus)
@@ -627,7 +626,8 @@ class NonlinearLeastSquares:
             info.best_err = torch.minimum(info.best_err, ginfo.best_err)
 
     def _optimize_loop_differentiable(self, num_iter: int, info, verbose: bool, end_iter_callback, last_implicit_step: bool, **kwargs) -> int:
-        """nonlinear_least_squares.py:100-215 with every value-carrying op on the autograd tape (Vector variables: retract = +)."""
+        """nonlinear_least_squares.py:100-215 with every value-carrying op on the autograd tape (retraction: lie_torch.retract)."""
+        from . import lie_torch
         eng = self.objective.engine()
         lin = self.linear_solver.linearization
         S = eng.structure
@@ -652,7 +652,8 @@ class NonlinearLeastSquares:
             olds = [v.tensor for v in self.ordering]
             news = []
             for v, old, c0, d in zip(self.ordering, olds, S.var_start_cols, S.var_dims):
-                new = old + step * delta[:, int(c0):int(c0) + int(d)].view(delta.shape[0], *old.shape[1:])
+                new = lie_torch.retract(v.KIND, old if old.shape[0] == delta.shape[0] else old.expand(delta.shape[0], *old.shape[1:]),
+                                        step * delta[:, int(c0):int(c0) + int(d)])
                 if converged is not None and not last_implicit_step:
                     new = torch.where(converged.view(-1, *([1] * (new.ndim - 1))), old.expand_as(new), new)
                 news.append(new)
