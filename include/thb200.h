@@ -251,6 +251,24 @@ int thb_sparse_solve_f64(const thb_sparse_plan* p, const double* factor, const d
                          double* work, int64_t B, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Symbolic analysis (host code, thb_symbolic.cu): ordering, fill, elimination-tree levels, factor layout and the work lists of
+ * both numeric back ends.  Replaces SymbolicDecomposition(param_size i64[N], sparse_struct_ptrs i64[N+1], sparse_struct_inds i64,
+ * device) of theseus/extlib/baspacho_solver.cpp:259-319 (and cusolver's symamd + csrluAnalysis, extlib/cusolver_lu_solver.cpp:95-196).
+ * All three input arrays are HOST arrays, exactly what baspacho_sparse_solver.py:93-113 builds.  ordering: 0 = minimum degree,
+ * 1 = natural.  The handle owns named host arrays (the fields of thb_sparse_plan / thb_sparse_lane_plan, the latter prefixed
+ * "ln_", plus order / pos / level / struct_ptr / struct_idx / blk_off / blk_i / blk_j / blk_rows / blk_cols / up_ptr) and the
+ * scalars N, n, data_size, winv_size, nnz_L, flops, levels, max_front, num_updates.  The caller uploads the arrays it needs.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thb_symbolic thb_symbolic;
+int thb_symbolic_create(const int64_t* param_size, int64_t N, const int64_t* blk_ptrs, const int64_t* blk_inds, int32_t ordering,
+                        thb_symbolic** out);
+void thb_symbolic_destroy(thb_symbolic* s);
+int64_t thb_symbolic_array_count(const thb_symbolic* s, const char* name);      /* elements, -1 if unknown */
+int32_t thb_symbolic_array_elem_bytes(const thb_symbolic* s, const char* name); /* 2, 4 or 8 */
+int thb_symbolic_array_copy(const thb_symbolic* s, const char* name, void* dst, int64_t dst_bytes);
+double thb_symbolic_stat(const thb_symbolic* s, const char* name);
+
+/* ------------------------------------------------------------------------------------------------
  * Block-sparse Cholesky, batch-lane layout (thb_sparse_lane.cu): the same four BaSpaCho operations
  * (add_MtM / damp / factor / solve, extlib/baspacho_solver.cpp:93-257) for large batches.  The factor storage is
  * INTERLEAVED over the batch: element e of item b lives at factor[e * Bp + b], Bp = thb_sparse_lane_padded_batch(B)

@@ -5,7 +5,7 @@ including the reference's literal 12x12 system shape (params [2,3,5,2], extlib/t
 import numpy as np
 import pytest
 
-from theseus_b200.sparse import analyze, minimum_degree_order
+from theseus_b200.sparse import analyze, analyze_py, minimum_degree_order
 
 
 def run_plan_numpy(plan, M, rhs):
@@ -211,6 +211,28 @@ def test_lane_work_lists_solve_system(sizes, fill, ordering):
     nT = sum(b1 - b0 for k, _, _, b0, b1 in launches if k == 1)
     nS = sum(b1 - b0 for k, _, _, b0, b1 in launches if k == 2)
     assert nT == len(plan.blk_off) and nS == plan.N
+
+
+@pytest.mark.parametrize("sizes,fill,ordering", [
+    ([2, 3, 5, 2], 0.6, "mindeg"), ([6] * 14, 0.9, "natural"), ([1, 2, 3, 6, 3, 3, 6, 6, 2, 1, 6], 0.25, "mindeg"),
+    ([3] * 30 + [6] * 5, 0.08, "mindeg"), ([6] * 120, 0.03, "mindeg"),
+])
+def test_native_symbolic_equals_python_specification(sizes, fill, ordering):
+    """thb_symbolic_create (C++, csrc/thb_symbolic.cu) against sparse.analyze_py: every array of both numeric back ends, the
+    ordering, the structure, the statistics -- bit for bit (integer data)."""
+    rng = np.random.default_rng(len(sizes))
+    M, ptrs, inds = random_block_spd(rng, sizes, fill)
+    a, b = analyze(np.array(sizes), ptrs, inds, ordering=ordering), analyze_py(np.array(sizes), ptrs, inds, ordering=ordering)
+    assert set(a.arrays) == set(b.arrays) and set(a.lane) == set(b.lane)
+    for k in a.arrays:
+        assert a.arrays[k].dtype == b.arrays[k].dtype and np.array_equal(a.arrays[k], b.arrays[k]), k
+    for k in a.lane:
+        assert a.lane[k].dtype == b.lane[k].dtype and a.lane[k].shape == b.lane[k].shape and np.array_equal(a.lane[k], b.lane[k]), k
+    for k in ("order", "pos", "dims", "col_start", "pstart", "level", "blk_off", "blk_rows", "blk_cols", "winv_off"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.blk_index == b.blk_index and a.stats == b.stats
+    assert all(np.array_equal(x, y) for x, y in zip(a.struct, b.struct))
+    assert (a.N, a.n, a.data_size, a.winv_size) == (b.N, b.n, b.data_size, b.winv_size)
 
 
 def test_minimum_degree_eliminates_leaves_first_and_is_deterministic():

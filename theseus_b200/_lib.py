@@ -92,6 +92,12 @@ SIGNATURES = {
     "thb_sparse_damp_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_factor_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_solve_f64": (c_i32, [_PS, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_symbolic_create": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp]),
+    "thb_symbolic_destroy": (None, [c_vp]),
+    "thb_symbolic_array_count": (c_i64, [c_vp, C.c_char_p]),
+    "thb_symbolic_array_elem_bytes": (c_i32, [c_vp, C.c_char_p]),
+    "thb_symbolic_array_copy": (c_i32, [c_vp, C.c_char_p, c_vp, c_i64]),
+    "thb_symbolic_stat": (C.c_double, [c_vp, C.c_char_p]),
     "thb_sparse_lane_padded_batch": (c_i64, [c_i64]),
     "thb_sparse_lane_gram_f64": (c_i32, [_PP, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "thb_sparse_lane_damp_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp]),

@@ -77,7 +77,59 @@ class SparsePlan:
     lane: Dict[str, np.ndarray] = None   # work lists of the batch-lane kernels (thb_sparse_lane.cu), see _lane_lists
 
 
+_PLAN_KEYS = ("dims", "col_start", "pstart", "winv_off", "diag_off", "up_a", "up_b", "up_k", "u_ptr", "u_tgt", "u_r", "u_c", "u_ld", "u_p0",
+              "u_p1", "f_ptr", "f_off", "f_dim", "f_w", "f_col", "t_ptr", "t_off", "t_r", "t_dim", "t_w", "s_ptr", "s_col", "fr_ptr",
+              "fr_off", "fr_k", "bc_ptr", "bc_off", "bc_i")
+_LANE_KEYS = ("u_tgt", "u_p0", "u_p1", "t_off", "t_diag", "t_dl", "t_pstart", "s_col", "launches", "fr_p", "fr_d", "bc_p", "bc_d")
+_NP_OF_BYTES = {2: np.int16, 4: np.int32, 8: np.int64}
+
+
 def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering: str = "mindeg") -> SparsePlan:
+    """Symbolic analysis by the native library (thb_symbolic_create, csrc/thb_symbolic.cu); `analyze_py` below is the same
+    algorithm in Python -- the executable specification the tests compare against, array by array."""
+    import ctypes as C
+    from . import _lib
+    if ordering not in ("mindeg", "natural"):
+        raise ValueError(ordering)
+    lib = _lib.load()
+    ps = np.ascontiguousarray(param_size, dtype=np.int64)
+    pt = np.ascontiguousarray(ptrs, dtype=np.int64)
+    ix = np.ascontiguousarray(inds, dtype=np.int64)
+    N = int(ps.shape[0])
+    h = C.c_void_p()
+    _lib.check(lib.thb_symbolic_create(ps.ctypes.data, N, pt.ctypes.data, ix.ctypes.data, 0 if ordering == "mindeg" else 1, C.byref(h)),
+               "symbolic_create")
+    try:
+        def arr(name):
+            cnt = int(lib.thb_symbolic_array_count(h, name.encode()))
+            if cnt < 0:
+                raise KeyError(name)
+            out = np.empty(cnt, dtype=_NP_OF_BYTES[int(lib.thb_symbolic_array_elem_bytes(h, name.encode()))])
+            _lib.check(lib.thb_symbolic_array_copy(h, name.encode(), out.ctypes.data, out.nbytes), f"symbolic array {name}")
+            return out
+
+        def stat(name):
+            return float(lib.thb_symbolic_stat(h, name.encode()))
+        arrays = {k: arr(k) for k in _PLAN_KEYS}
+        lane = {k: arr("ln_" + k) for k in _LANE_KEYS}
+        lane["launches"] = lane["launches"].reshape(-1, 5)
+        order, pos, level = arr("order"), arr("pos"), arr("level")
+        sp, si = arr("struct_ptr"), arr("struct_idx")
+        blk_off, blk_i, blk_j = arr("blk_off"), arr("blk_i"), arr("blk_j")
+        blk_rows, blk_cols = arr("blk_rows"), arr("blk_cols")
+        stats = {k: stat(k) for k in ("nnz_L", "flops", "levels", "max_front", "num_updates")}
+        n, data_size, winv_size = int(stat("n")), int(stat("data_size")), int(stat("winv_size"))
+        dims, col_start, pstart = arr("dims64"), arr("col_start64"), arr("pstart64")
+    finally:
+        lib.thb_symbolic_destroy(h)
+    struct = [si[sp[j]:sp[j + 1]] for j in range(N)]
+    blk_index = {(int(i), int(j)): t for t, (i, j) in enumerate(zip(blk_i.tolist(), blk_j.tolist()))}
+    return SparsePlan(N=N, n=n, param_size=ps, order=order, pos=pos, dims=dims, col_start=col_start, pstart=pstart, struct=struct, level=level,
+                      blk_index=blk_index, blk_off=blk_off, blk_rows=blk_rows, blk_cols=blk_cols, data_size=data_size,
+                      winv_off=arrays["winv_off"], winv_size=winv_size, arrays=arrays, stats=stats, lane=lane)
+
+
+def analyze_py(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering: str = "mindeg") -> SparsePlan:
     param_size = np.asarray(param_size, dtype=np.int64)
     N = int(param_size.shape[0])
     if ordering == "mindeg":
