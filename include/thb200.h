@@ -373,6 +373,30 @@ int thb_se3_adjoint_f32(const float* group, float* adj, int64_t N, thb_stream_t 
 int thb_se3_inverse_f32(const float* group, float* out, int64_t N, thb_stream_t stream);
 int thb_se3_compose_f32(const float* g0, const float* g1, float* out, int64_t N, thb_stream_t stream);
 
+/* SO3 (torchlie/functional/so3_impl.py:220-261 exp, :390-433 log, :442-479 jlog, :669-672 compose, :561-563 inverse; adjoint = R)
+ * and SE2 (theseus/geometry/se2.py:239-300 exp_map, :165-228 log_map + Jacobian, :309-316 adjoint, :318-332 compose, :334-339 inverse).
+ * Shapes: SO3 tangent [N,3], group [N,3,3], jacobian [N,3,3]; SE2 tangent [N,3] = [ux,uy,theta], group [N,4] = [x,y,cos,sin]. */
+int thb_so3_exp_f64(const double* tangent, double* group, int64_t N, thb_stream_t stream);
+int thb_so3_log_f64(const double* group, double* tangent, double* jlog /* may be NULL */, int64_t N, thb_stream_t stream);
+int thb_so3_adjoint_f64(const double* group, double* adj, int64_t N, thb_stream_t stream);
+int thb_so3_inverse_f64(const double* group, double* out, int64_t N, thb_stream_t stream);
+int thb_so3_compose_f64(const double* g0, const double* g1, double* out, int64_t N, thb_stream_t stream);
+int thb_se2_exp_f64(const double* tangent, double* group, int64_t N, thb_stream_t stream);
+int thb_se2_log_f64(const double* group, double* tangent, double* jlog /* may be NULL */, int64_t N, thb_stream_t stream);
+int thb_se2_adjoint_f64(const double* group, double* adj, int64_t N, thb_stream_t stream);
+int thb_se2_inverse_f64(const double* group, double* out, int64_t N, thb_stream_t stream);
+int thb_se2_compose_f64(const double* g0, const double* g1, double* out, int64_t N, thb_stream_t stream);
+int thb_so3_exp_f32(const float* tangent, float* group, int64_t N, thb_stream_t stream);
+int thb_so3_log_f32(const float* group, float* tangent, float* jlog /* may be NULL */, int64_t N, thb_stream_t stream);
+int thb_so3_adjoint_f32(const float* group, float* adj, int64_t N, thb_stream_t stream);
+int thb_so3_inverse_f32(const float* group, float* out, int64_t N, thb_stream_t stream);
+int thb_so3_compose_f32(const float* g0, const float* g1, float* out, int64_t N, thb_stream_t stream);
+int thb_se2_exp_f32(const float* tangent, float* group, int64_t N, thb_stream_t stream);
+int thb_se2_log_f32(const float* group, float* tangent, float* jlog /* may be NULL */, int64_t N, thb_stream_t stream);
+int thb_se2_adjoint_f32(const float* group, float* adj, int64_t N, thb_stream_t stream);
+int thb_se2_inverse_f32(const float* group, float* out, int64_t N, thb_stream_t stream);
+int thb_se2_compose_f32(const float* g0, const float* g1, float* out, int64_t N, thb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,3 +63,37 @@ def test_se3_kernels_vs_oracle_random_large():
 def test_cpu_tensor_fails_loudly():
     with pytest.raises(RuntimeError, match="CUDA"):
         th.SE3.exp_map(torch.zeros(2, 6, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_so3_kernels_vs_reference_golden(dt):
+    """Stand-alone SO3 kernels (thb_so3_*) against torchlie.functional outputs incl. the reference's angle sweep (lie_kat.npz)."""
+    g = load("lie_kat")
+    tdt = torch.float64 if dt == "f64" else torch.float32
+    tol = dict(rtol=1e-9, atol=1e-10) if dt == "f64" else dict(rtol=2e-3, atol=2e-4)
+    P = lambda k: torch.from_numpy(g[f"so3_{dt}_{k}"]).to(tdt).cuda()
+    X = th.SO3.exp_map(P("tangent"))
+    np.testing.assert_allclose(X.tensor.cpu().numpy(), g[f"so3_{dt}_exp"], **(dict(rtol=1e-10, atol=1e-12) if dt == "f64" else dict(rtol=2e-4, atol=2e-5)))
+    Y = th.SO3(tensor=P("exp"))
+    jac = []
+    w = Y.log_map(jacobians=jac)
+    np.testing.assert_allclose(w.cpu().numpy(), g[f"so3_{dt}_log"], **tol)
+    if dt == "f64":
+        np.testing.assert_allclose(jac[0].cpu().numpy(), g[f"so3_{dt}_jlog"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(Y.adjoint().cpu().numpy(), g[f"so3_{dt}_adj"], **tol)
+    np.testing.assert_allclose(Y.inverse().tensor.cpu().numpy(), g[f"so3_{dt}_inv"], **tol)
+    np.testing.assert_allclose(Y.compose(th.SO3(tensor=P("other"))).tensor.cpu().numpy(), g[f"so3_{dt}_compose"], **tol)
+
+
+def test_se2_kernels_vs_reference_golden():
+    """Stand-alone SE2 kernels (thb_se2_*) against theseus.geometry.SE2 outputs (se2_kat.npz)."""
+    g = load("se2_kat")
+    P = lambda k: torch.from_numpy(g[k]).cuda()
+    np.testing.assert_allclose(th.SE2.exp_map(P("tangent")).tensor.cpu().numpy(), g["exp"], rtol=1e-12, atol=1e-14)
+    Y = th.SE2(tensor=P("exp"))
+    jac = []
+    np.testing.assert_allclose(Y.log_map(jacobians=jac).cpu().numpy(), g["log"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(jac[0].cpu().numpy(), g["jlog"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(Y.adjoint().cpu().numpy(), g["adj"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(Y.inverse().tensor.cpu().numpy(), g["inv"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(Y.compose(th.SE2(tensor=P("other"))).tensor.cpu().numpy(), g["compose"], rtol=1e-12, atol=1e-14)

@@ -198,6 +198,56 @@ class LieGroup(Manifold):
         return self.inverse().compose(other)
 
 
+def _group_ops(cls, prefix: str, dof: int, jshape):
+    """Attach exp_map / log_map / adjoint / inverse / compose backed by the stand-alone kernels thb_<prefix>_* (csrc/thb_lie_ops.cu)."""
+    def _shape(t):
+        return tuple(t.shape[1:])
+
+    def exp_map(tangent_vector: torch.Tensor):
+        _require_cuda(tangent_vector, f"{cls.__name__}.exp_map")
+        t = tangent_vector.contiguous()
+        out = torch.empty((t.shape[0],) + cls._GROUP_SHAPE, dtype=t.dtype, device=t.device)
+        _lib.check(getattr(_lib.load(), f"thb_{prefix}_exp_{_sfx(t)}")(_lib.ptr(t), _lib.ptr(out), t.shape[0], _lib.stream_ptr()), f"{prefix}_exp")
+        return cls(tensor=out)
+
+    def log_map(self, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        g = self.tensor.contiguous()
+        _require_cuda(g, f"{cls.__name__}.log_map")
+        out = torch.empty(g.shape[0], dof, dtype=g.dtype, device=g.device)
+        jl = torch.empty((g.shape[0],) + jshape, dtype=g.dtype, device=g.device) if jacobians is not None else None
+        _lib.check(getattr(_lib.load(), f"thb_{prefix}_log_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), _lib.ptr(jl), g.shape[0], _lib.stream_ptr()), f"{prefix}_log")
+        if jacobians is not None:
+            jacobians.append(jl)
+        return out
+
+    def adjoint(self) -> torch.Tensor:
+        g = self.tensor.contiguous()
+        _require_cuda(g, f"{cls.__name__}.adjoint")
+        out = torch.empty((g.shape[0],) + jshape, dtype=g.dtype, device=g.device)
+        _lib.check(getattr(_lib.load(), f"thb_{prefix}_adjoint_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), g.shape[0], _lib.stream_ptr()), f"{prefix}_adjoint")
+        return out
+
+    def inverse(self):
+        g = self.tensor.contiguous()
+        _require_cuda(g, f"{cls.__name__}.inverse")
+        out = torch.empty_like(g)
+        _lib.check(getattr(_lib.load(), f"thb_{prefix}_inverse_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), g.shape[0], _lib.stream_ptr()), f"{prefix}_inverse")
+        return cls(tensor=out)
+
+    def compose(self, other):
+        a, b = self.tensor.contiguous(), other.tensor.contiguous()
+        _require_cuda(a, f"{cls.__name__}.compose")
+        if a.shape[0] != b.shape[0]:
+            B = max(a.shape[0], b.shape[0])
+            a, b = a.expand((B,) + _shape(a)).contiguous(), b.expand((B,) + _shape(b)).contiguous()
+        out = torch.empty_like(a)
+        _lib.check(getattr(_lib.load(), f"thb_{prefix}_compose_{_sfx(a)}")(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], _lib.stream_ptr()), f"{prefix}_compose")
+        return cls(tensor=out)
+
+    cls.exp_map = staticmethod(exp_map)
+    cls.log_map, cls.adjoint, cls.inverse, cls.compose = log_map, adjoint, inverse, compose
+
+
 class SE3(LieGroup):
     """theseus/geometry/se3.py:20 -- storage [B,3,4] = [R|t], tangent [v, w]."""
     KIND = 0  # THB_VAR_SE3
@@ -314,3 +364,8 @@ class SE2(LieGroup):
         perp = torch.stack((-group[:, 3], group[:, 2]), dim=1)[:, None]  # (-sin, cos)
         g_xy, g_cs = euclidean_grad[..., :2], euclidean_grad[..., 2:]
         return torch.stack(((g_xy * cs).sum(-1), (g_xy * perp).sum(-1), (g_cs * perp).sum(-1)), dim=-1)
+
+
+SO3._GROUP_SHAPE, SE2._GROUP_SHAPE = (3, 3), (4,)
+_group_ops(SO3, "so3", 3, (3, 3))   # torchlie.functional.SO3: exp / log (+jlog) / adjoint / inv / compose
+_group_ops(SE2, "se2", 3, (3, 3))   # theseus.geometry.SE2: exp_map / log_map (+Jacobian) / adjoint / inverse / compose
