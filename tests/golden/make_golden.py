@@ -217,14 +217,14 @@ def make_dense_solver(th):
     print("dense_solver_kat.npz")
 
 
-def make_ba(th, name, num_cameras, num_points, B, seed, iters, robust=False):
+def make_ba(th, name, num_cameras, num_points, B, seed, iters, robust=False, track_length=4):
     """Bundle adjustment as examples/bundle_adjustment.py:106-164 (Reprojection + reg priors + known-camera priors), without
     the Huber wrapper (robust losses are a 'next' row), batch built by re-perturbing the scene per item."""
     import random
     import torch
     import theseus.utils.examples as theg
     torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
-    ba = theg.BundleAdjustmentDataset.generate_synthetic(num_cameras=num_cameras, num_points=num_points, average_track_length=4,
+    ba = theg.BundleAdjustmentDataset.generate_synthetic(num_cameras=num_cameras, num_points=num_points, average_track_length=track_length,
                                                         track_locality=0.3, feat_random=1.5, prob_feat_is_outlier=0.0)
     dtype = torch.float64
     # batch: item 0 = the dataset, items 1.. = re-perturbed copies (cameras: Camera.perturbed; points: U[-0.2,0.2])
@@ -573,6 +573,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "autodiff_lie":
         make_autodiff_lie(th)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ba_c3":   # config C3 at full size (50 cameras x 1000 points x 8 observations per point, Huber)
+        make_ba(th, "ba_c3_huber", num_cameras=50, num_points=1000, B=2, seed=11, iters=5, robust=True, track_length=8)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "backward_lie":
         make_backward_lie(th)
         sys.exit(0)
@@ -597,3 +600,4 @@ if __name__ == "__main__":
     make_backward(th)
     make_autodiff_lie(th)
     make_backward_lie(th)
+    make_ba(th, "ba_c3_huber", num_cameras=50, num_points=1000, B=2, seed=11, iters=5, robust=True, track_length=8)

@@ -25,7 +25,7 @@ def test_ba_linearization_matches_reference(name):
     np.testing.assert_allclose(objective.error_metric().cpu().numpy(), nls.error_metric(spec, [v["value"] for v in spec["vars"]]), rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["ba_small_lm", "ba_small_huber"])
+@pytest.mark.parametrize("name", ["ba_small_lm", "ba_small_huber", "ba_c3_huber"])   # ba_c3_huber: config C3 at full size (50 x 1000 x 8)
 @pytest.mark.parametrize("solver", ["dense", "sparse", "sparse_lane"])
 def test_ba_lm_trace(solver, name):
     g = load(name)
@@ -57,5 +57,5 @@ def test_ba_lm_trace(solver, name):
         rel = np.linalg.norm(deltas[it] - dref, axis=1) / np.linalg.norm(dref, axis=1)
         assert rel.max() < 1e-5, (it, rel)
         np.testing.assert_allclose(lams[it], g["trace_lam"][it], rtol=1e-12)
-    final = np.concatenate([v.tensor.cpu().numpy().reshape(3, -1) for v in opt.linear_solver.linearization.ordering], 1)
+    final = np.concatenate([v.tensor.cpu().numpy().reshape(v.tensor.shape[0], -1) for v in opt.linear_solver.linearization.ordering], 1)
     np.testing.assert_allclose(final, g["final"], rtol=1e-5, atol=1e-5)
