@@ -184,7 +184,8 @@ def main():
     th, data, objective, poses = build_problem(rank, device)
     lib = _lib.load()
     opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=LM_ITERS, step_size=1.0,
-                                abs_err_tolerance=0, rel_err_tolerance=0, process_group=pg)
+                                abs_err_tolerance=0, rel_err_tolerance=0, process_group=pg,
+                                cuda_graph=os.environ.get("THB_BENCH_GRAPH", "1") != "0")
     layer = th.TheseusLayer(opt)
     names_pose = [p.name for p in poses]
     # ---- device-resident inputs (for `value`) and pinned host inputs (for `e2e`) ----
@@ -239,9 +240,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = lib.thb_launch_count()
+    l0 = _lib.total_launches()
     ms_total = timed(step_resident, args.steps)
-    launches = int(lib.thb_launch_count() - l0)
+    launches = int(_lib.total_launches() - l0)  # direct launches + kernels replayed from the captured iteration graph
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     # whole-job aggregate: every rank advances its own 256-problem batch, so the job completes `world` batched LM iterations
@@ -317,7 +318,8 @@ def main():
                     num_edges=len(data["edges"]), rows=int(lin.num_rows), cols=int(lin.num_cols), lm_iterations_per_step=LM_ITERS,
                     problem_iterations_per_s=value * BATCH,
                     l2="working set per iteration (AtA+L = 9.7 GB) >> 126 MB L2, no flush needed",
-                    parallelism=f"batch sharded over {world} GPU(s); one all-reduce of 2 int32 per LM iteration"),
+                    parallelism=f"batch sharded over {world} GPU(s); one all-reduce of 2 int32 per LM iteration",
+                    cuda_graph=bool(opt.cuda_graph)),
         clocks=clocks,
         e2e=dict(value=LM_ITERS * 1e3 / ms_e2e * world, unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
         gpu_launches=launches,

@@ -22,7 +22,8 @@ objective, cams, pts = ba_objective(th, g)
 iters = 10
 skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(
     linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization, linear_solver_kwargs=dict(layout=solver))
-opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw)
+opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0,
+                            cuda_graph=len(sys.argv) > 3 and sys.argv[3] == "graph", **skw)
 print("objective + symbolic", round(time.time() - t0, 2), "s", getattr(opt.linear_solver, "symbolic_stats", None), flush=True)
 kw = dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
 inputs = {n: v.tensor.clone() for n, v in objective.optim_vars.items()}

@@ -85,3 +85,35 @@ def test_info_bookkeeping_best_solution_and_histories():
     np.testing.assert_allclose(info.state_history[name][..., 0].numpy(), g["poses0"][3], rtol=1e-6)
     np.testing.assert_allclose(info.best_err.cpu().numpy(), g["trace_err"].min(axis=0), rtol=1e-8)
     assert (info.converged_iter == -1).all() and all(s == th.NonlinearOptimizerStatus.MAX_ITERATIONS for s in info.status)
+
+
+@pytest.mark.parametrize("solver", ["dense", "sparse_lane"])
+@pytest.mark.parametrize("name", ["pgo_small_lm", "pgo_small_gn", "pgo64_lm"])
+def test_cuda_graph_mode_is_bitwise_identical_to_eager(name, solver):
+    """cuda_graph=True replays the captured iteration body; same kernels, same order -> identical bits; also across repeated
+    optimize() calls (graph reuse) and with the all-rejected / non-PD bookkeeping read after each replay."""
+    from helpers import load, pgo_objective, lm_kwargs_of
+    g = load(name)
+    method, iters, kw = lm_kwargs_of(g)
+    cls = th.LevenbergMarquardt if method == "lm" else th.GaussNewton
+    skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(
+        linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization, linear_solver_kwargs=dict(layout="lane"))
+    res = {}
+    for mode in (False, True):
+        objective, poses = pgo_objective(th, g)
+        opt = cls(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, cuda_graph=mode, **skw)
+        layer = th.TheseusLayer(opt)
+        inputs = {p.name: p.tensor.clone() for p in poses}
+        outs = []
+        for rep in range(2):   # second call re-uses the captured graph
+            with torch.no_grad():
+                vals, info = layer.forward(inputs, optimizer_kwargs=dict(kw, track_err_history=True))
+            outs.append((torch.stack([vals[p.name] for p in poses]).cpu().numpy().copy(), info.err_history.numpy().copy(),
+                         info.last_err.cpu().numpy().copy()))
+        res[mode] = outs
+        if mode:
+            assert opt._graph is not None
+    for rep in range(2):
+        for a, b in zip(res[False][rep], res[True][rep]):
+            assert np.array_equal(a, b)
+    assert np.array_equal(res[True][0][0], res[True][1][0])

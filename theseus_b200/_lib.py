@@ -148,6 +148,16 @@ def load():
     return lib
 
 
+# Kernel launches replayed from captured CUDA graphs (optimizer cuda_graph=True) do not pass through the library's entry points;
+# the optimizer adds (kernels in the captured body) per replay here so that launch accounting stays truthful.
+replayed_launches = 0
+
+
+def total_launches() -> int:
+    """Kernels of libthb200 launched in this process so far: direct launches (thb_launch_count) + graph replays."""
+    return int(load().thb_launch_count()) + replayed_launches
+
+
 def check(rc, what):
     if rc != 0:
         kind = "invalid argument" if rc < 0 else "CUDA error"

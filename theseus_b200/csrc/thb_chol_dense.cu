@@ -595,6 +595,16 @@ static inline Geometry geometry(void* workspace, int64_t B, int64_t n) {
   return g;
 }
 
+// First CTA index of every block column: column j owns (ntr - j/2) * B CTAs, so col_start[j] = B * (j*ntr - floor((j-1)^2/4)).
+// Filled on the device (not copied from a host array): the entry point must be capturable into a CUDA graph, and a captured H2D
+// copy would re-read a dead stack address at every replay.
+__global__ void chol_col_start_kernel(int64_t* __restrict__ col_start, int nb, int ntr, int64_t B) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > nb) return;
+  const int64_t jm1 = j > 0 ? j - 1 : 0;
+  col_start[j] = B * ((int64_t)j * ntr - (jm1 * jm1) / 4);
+}
+
 }  // namespace thb
 
 extern "C" {
@@ -625,7 +635,8 @@ int thb_potrf_f64(const double* AtA, const double* alpha, const double* beta, in
   starts[0] = 0;
   for (int j = 0; j < g.nb; j++) starts[j + 1] = starts[j] + (int64_t)(g.ntr - (j >> 1)) * B;
   if (starts[g.nb] > 2147483647LL) return THB_ERR_UNSUPPORTED;
-  THB_CUDA(cudaMemcpyAsync(g.col_start, starts, sizeof(int64_t) * (g.nb + 1), cudaMemcpyHostToDevice, cs));
+  thb::chol_col_start_kernel<<<(unsigned)((g.nb + 1 + 255) / 256), 256, 0, cs>>>(g.col_start, (int)g.nb, (int)g.ntr, B);
+  THB_CHECK_LAUNCH();
   static bool attr_set = false;
   if (!attr_set) {
     THB_CUDA(cudaFuncSetAttribute(thb::chol_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thb::CHOL_SMEM));

@@ -104,6 +104,7 @@ class Engine:
         self._bind_stamp = {"cur": -1, "tmp": -1}
         self._bind_sig = {}
         self._sig_vars = None
+        self.table_version = 0
         self._vt = None
         self._gram_dense = None
         self._zero_filled = None  # (data_ptr, numel) of the AtA buffer whose off-pattern entries are known to be zero
@@ -246,6 +247,7 @@ class Engine:
         # NOTE: _bind may itself rebind non-contiguous tensors (bumping the counter); read it afterwards.
         self._bind_stamp[which] = Variable._global_updates
         self._bind_sig[which] = self._bind_signature(which)
+        self.table_version += 1  # captured CUDA graphs hold the old tables' device pointers: optimizers re-capture on a change
         if which == "cur":
             self._vt = None
 

@@ -323,13 +323,20 @@ class DenseSolver(LinearSolver):
         _lib.check(lib.thb_potrf_potrs_f64(_lib.ptr(AtA_c), _lib.ptr(rhs), _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(x), _lib.ptr(info),
                                            B, n, _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr()), "potrf_potrs")
         self._last = (AtA_c, rhs, alpha, beta)
+        self._last_info = info
+        if getattr(self, "defer_info_check", False):  # CUDA-graph capture: no host sync here, check_info() is called after the replay
+            return x.to(out_dtype)
+        return self.check_info(x.to(out_dtype))
+
+    def check_info(self, x=None):
+        info = self._last_info
         bad = info.nonzero()
         if bad.numel() > 0:  # same visible behaviour as torch.linalg.cholesky: a RuntimeError subclass
             k = int(bad[0, 0])
             raise torch.linalg.LinAlgError(
                 f"linalg.cholesky: (Batch element {k}): The factorization could not be completed because the input is not "
                 f"positive-definite (the leading minor of order {int(info[k])} is not positive-definite).")
-        return x.to(out_dtype)
+        return x
 
 
 class CholeskyDenseSolver(DenseSolver):
@@ -409,8 +416,13 @@ class NonlinearLeastSquares:
     def __init__(self, objective: Objective, *args, linear_solver_cls: Optional[Type[LinearSolver]] = None, vectorize: bool = False,
                  linearization_cls: Optional[Type[Linearization]] = None, linearization_kwargs: Optional[Dict[str, Any]] = None,
                  linear_solver_kwargs: Optional[Dict[str, Any]] = None, abs_err_tolerance: float = 1e-10,
-                 rel_err_tolerance: float = 1e-8, max_iterations: int = 20, step_size: float = 1.0, process_group=None, **kwargs):
+                 rel_err_tolerance: float = 1e-8, max_iterations: int = 20, step_size: float = 1.0, process_group=None,
+                 cuda_graph: bool = False, **kwargs):
         self.objective = objective
+        # cuda_graph=True: the iteration body (linearize -> solve -> retract -> error -> accept/reject -> commit) is captured once
+        # into a CUDA graph and replayed; per iteration the host only reads 16 bytes of statistics (no reference analogue).
+        self.cuda_graph = cuda_graph
+        self._graph = None
         # Batch sharding over GPUs (no reference analogue): every rank owns a slice of the batch; the only
         # batch-global decisions of the loop (all-rejected retry, all-converged exit, mean-error test) are all-reduced.
         self.process_group = process_group
@@ -507,6 +519,9 @@ class NonlinearLeastSquares:
     def _optimize_loop(self, num_iter: int, info: NonlinearOptimizerInfo, verbose: bool, end_iter_callback=None, **kwargs) -> int:
         eng = self.objective.engine()
         B = self.objective.batch_size
+        if kwargs.pop("cuda_graph", self.cuda_graph) and self.params.abs_err_tolerance <= 0 and self.params.rel_err_tolerance <= 0 \
+                and not torch.is_grad_enabled():
+            return self._optimize_loop_graphed(num_iter, info, verbose, end_iter_callback, **kwargs)
         converged_indices = None  # None == all False (kept on the host side to avoid a sync per iteration)
         iters_done = 0
         it_ = 0
@@ -544,6 +559,92 @@ class NonlinearLeastSquares:
                     if all_conv:
                         break
                 info.last_err = err
+                if end_iter_callback is not None:
+                    end_iter_callback(self, info, delta, it_)
+            iters_done += 1
+            it_ += 1
+        info.status[info.status == NonlinearOptimizerStatus.START] = NonlinearOptimizerStatus.MAX_ITERATIONS
+        return iters_done
+
+    # ---- the same loop with the iteration body replayed from a CUDA graph ----
+    def _iteration_body(self, prev_err: torch.Tensor, **kwargs):
+        """One iteration on the current stream, no host reads: returns (delta, err, reject or None, stats or None)."""
+        eng = self.objective.engine()
+        self.linear_solver.linearization.linearize()
+        delta = self.compute_delta(**kwargs)
+        eng.retract_into(delta, self._tmp_optim_vars, float(self.params.step_size), None)
+        err_new = eng.error_metric("tmp")
+        reject, err, stats = self._complete_step(delta, err_new, prev_err, **kwargs)
+        stats = stats if torch.is_tensor(stats) else None  # GN / non-adaptive LM: no accept test, nothing to read back
+        eng.commit(reject)  # all-rejected == every item keeps its old value: the commit is unconditional
+        prev_err.copy_(err)  # rejected items carry their previous error (the control kernel folds that in)
+        return delta, err, reject, stats
+
+    def _optimize_loop_graphed(self, num_iter: int, info: NonlinearOptimizerInfo, verbose: bool, end_iter_callback=None, **kwargs) -> int:
+        eng = self.objective.engine()
+        B = self.objective.batch_size
+        solver = self.linear_solver
+        d = getattr(self, "_damping", None)
+        if d is not None and not torch.is_tensor(d):  # a python-float damping would be copied host->device inside the capture
+            self._damping = torch.full((B,), float(d), dtype=self.objective.dtype, device=self.objective.device)
+        eng._bind("cur"); eng._bind("tmp")  # pointer tables current BEFORE deciding whether the captured graph is still valid
+        key = (B, eng.table_version, id(getattr(self, "_damping", None)) if torch.is_tensor(getattr(self, "_damping", None)) else None,
+               tuple(sorted((k, repr(v)) for k, v in kwargs.items())))
+        g = self._graph
+        if g is None or g["key"] != key:
+            prev = info.last_err.clone()
+            solver.defer_info_check, self._capturing = True, True
+            try:
+                # warm-up on a side stream (allocations, plan uploads, lazy initialisation), restoring the state it advanced
+                state = [v.tensor.clone() for v in self.ordering]
+                damp = self._damping.clone() if torch.is_tensor(getattr(self, "_damping", None)) else None
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._iteration_body(prev, **kwargs)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                for v, t in zip(self.ordering, state):
+                    v.tensor.copy_(t)
+                if damp is not None:
+                    self._damping.copy_(damp)
+                prev.copy_(info.last_err)
+                key = (key[0], eng.table_version) + key[2:]
+                graph = torch.cuda.CUDAGraph()
+                l0 = int(_lib.load().thb_launch_count())
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (NCCL watchdog, samplers) may touch CUDA
+                    out = self._iteration_body(prev, **kwargs)
+                body_launches = int(_lib.load().thb_launch_count()) - l0
+            finally:
+                solver.defer_info_check, self._capturing = False, False
+            g = self._graph = dict(key=key, graph=graph, prev=prev, out=out, launches=body_launches)
+        else:
+            g["prev"].copy_(info.last_err)
+        delta, err, reject, stats = g["out"]
+        iters_done = it_ = all_reject_attempts = 0
+        while it_ < num_iter:
+            g["graph"].replay()
+            _lib.replayed_launches += g["launches"]
+            all_rejected = False
+            if stats is not None:
+                all_rejected = self._read_stats(stats, B)
+            try:
+                solver.check_info()
+            except RuntimeError as run_err:
+                warnings.warn(f"There was an error while running the linear optimizer. Original error message: {run_err}.", RuntimeWarning)
+                info.status[:] = NonlinearOptimizerStatus.FAIL
+                return iters_done
+            if all_rejected:
+                all_reject_attempts += 1
+                if all_reject_attempts < NonlinearLeastSquares._MAX_ALL_REJECT_ATTEMPTS:
+                    continue
+            all_reject_attempts = 0
+            with torch.no_grad():
+                cur_err = err.clone()
+                self._update_info(info, it_, cur_err, None)
+                if verbose:
+                    print(f"Nonlinear optimizer. Iteration: {it_+1}. Error: {cur_err.mean().item()}")
+                info.last_err = cur_err
                 if end_iter_callback is not None:
                     end_iter_callback(self, info, delta, it_)
             iters_done += 1
@@ -738,7 +839,12 @@ class LevenbergMarquardt(NonlinearLeastSquares):
     def reset(self, damping: float = 1e-3, adaptive_damping: bool = False, **kwargs) -> None:
         super().reset(**kwargs)
         if adaptive_damping:
-            self._damping = damping * torch.ones(self.objective.batch_size, device=self.objective.device, dtype=self.objective.dtype)
+            d = self._damping
+            B = self.objective.batch_size
+            if torch.is_tensor(d) and d.shape == (B,) and d.dtype == self.objective.dtype and d.device == torch.device(self.objective.device):
+                d.fill_(damping)  # same buffer every call: its address is baked into a captured graph; the control kernel updates it in place
+            else:
+                self._damping = damping * torch.ones(B, device=self.objective.device, dtype=self.objective.dtype)
         else:
             self._damping = damping
 
@@ -766,12 +872,19 @@ class LevenbergMarquardt(NonlinearLeastSquares):
         reject = torch.empty(B, dtype=torch.uint8, device=dev)
         err_out = torch.empty_like(err)
         stats = torch.empty(4, dtype=torch.int32, device=dev)
-        if self._stats_host is None:
-            self._stats_host = torch.empty(4, dtype=torch.int32).pin_memory()
         _lib.check(getattr(lib, f"thb_lm_control_{sfx}")(
             _lib.ptr(delta), _lib.ptr(Atb), _lib.ptr(diag), B, n, float(self.params.step_size), _lib.ptr(previous_err), _lib.ptr(err),
             _lib.ptr(self._damping), 1 if ellipsoidal_damping else 0, float(damping_accept), float(down_damping_ratio),
             float(up_damping_ratio), _lib.ptr(reject), _lib.ptr(err_out), _lib.ptr(stats), _lib.stream_ptr()), "lm_control")
+        self._keep_control = (delta, Atb, diag, err, previous_err)
+        if getattr(self, "_capturing", False):  # CUDA-graph capture: the statistics are read after the replay (_read_stats)
+            return reject, err_out, stats
+        return reject, err_out, self._read_stats(stats, B)
+
+    def _read_stats(self, stats, B) -> bool:
+        """all-rejected? -- the ONE host read per iteration (16 bytes)."""
+        if self._stats_host is None:
+            self._stats_host = torch.empty(4, dtype=torch.int32).pin_memory()
         if self.process_group is not None:
             # the single per-iteration collective: [#rejected, #items] summed over ranks (NCCL, latency-bound)
             from .distributed import reduce_counts
@@ -781,4 +894,4 @@ class LevenbergMarquardt(NonlinearLeastSquares):
         torch.cuda.current_stream().synchronize()
         n_rej = int(self._stats_host[0])
         total = int(self._stats_host[1]) if self.process_group is not None else B
-        return reject, err_out, n_rej == total
+        return n_rej == total

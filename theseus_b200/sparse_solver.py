@@ -132,8 +132,14 @@ class BaspachoSparseSolver(LinearSolver):
             alpha, beta = convert_to_alpha_beta_damping_tensors(damping, damping_eps, ellipsoidal_damping, A64.shape[0], A64.device, torch.float64)
         Atb = self._numeric(A64, b64, alpha, beta)
         x = self._substitute(Atb)
-        self._raise_if_bad(self._dev["bufs"]["info"])
+        self._last_info = self._dev["bufs"]["info"]
+        if not getattr(self, "defer_info_check", False):  # CUDA-graph capture: no host sync here, check_info() after the replay
+            self.check_info()
         return x.to(out_dtype), (A64, b64, x, alpha, beta)
+
+    def check_info(self, x=None):
+        self._raise_if_bad(self._last_info)
+        return x
 
     @staticmethod
     def _raise_if_bad(info):
