@@ -92,18 +92,20 @@ __device__ long long thb_chol_timing[16 * 65536];
 #endif
 
 // ------------------------------------------------------------------------------------------------
-// One warp: Cholesky of the 32x32 block at T (lower part; row stride SC) and its inverse, in registers
-// (one row / one column per lane; pivots and multipliers exchanged with warp shuffles).
-// L is written back to T (lower part), the inverse (full 32x32, zeros above the diagonal) to Wout [32][SB32].
+// One warp: Cholesky of the NxN block at T (lower part; row stride SC) and its inverse, in registers (one row / one column per
+// lane, lanes >= N idle; pivots and multipliers exchanged with warp shuffles).
+// L is written back to T (lower part), the inverse (full NxN, zeros above the diagonal) to Wout (row stride SB32).
 // Returns 0 or 1 + index of the first non-positive pivot.
-__device__ __noinline__ int warp_potrf32_inv(double* __restrict__ T, double* __restrict__ Wout, int lane) {
-  double row[32];
+template <int N>
+__device__ __noinline__ int warp_potrf_inv(double* __restrict__ T, double* __restrict__ Wout, int lane) {
+  const int ln = lane < N ? lane : 0;  // idle lanes shadow lane 0 (their results are never stored)
+  double row[N];
 #pragma unroll
-  for (int q = 0; q < 32; q++) row[q] = T[lane * SC + q];
+  for (int q = 0; q < N; q++) row[q] = T[ln * SC + q];
   int fail = 0;
   double invd = 0.0;  // 1 / L[lane][lane]
 #pragma unroll
-  for (int c = 0; c < 32; c++) {
+  for (int c = 0; c < N; c++) {
     const double d = __shfl_sync(0xffffffffu, row[c], c);
     if (!(d > 0.0) && fail == 0) fail = c + 1;
     // 1/sqrt(d) by the hardware seed + one Newton step (inline, no slow-path subroutine calls), sqrt(d) = d * rsqrt(d)
@@ -114,18 +116,20 @@ __device__ __noinline__ int warp_potrf32_inv(double* __restrict__ T, double* __r
     const double lrc = (lane == c) ? sq : row[c] * inv;
     row[c] = lrc;
 #pragma unroll
-    for (int q = c + 1; q < 32; q++) {
+    for (int q = c + 1; q < N; q++) {
       const double lqc = __shfl_sync(0xffffffffu, lrc, q);
       row[q] -= lrc * lqc;  // lanes < q update entries above the diagonal that are never read
     }
   }
+  if (lane < N) {
 #pragma unroll
-  for (int q = 0; q < 32; q++)
-    if (q <= lane) T[lane * SC + q] = row[q];
+    for (int q = 0; q < N; q++)
+      if (q <= lane) T[lane * SC + q] = row[q];
+  }
   // inverse: lane c owns column c of X = L^-1 (forward substitution, rows broadcast from their owner lane)
-  double x[32];
+  double x[N];
 #pragma unroll
-  for (int r = 0; r < 32; r++) {
+  for (int r = 0; r < N; r++) {
     double s = (lane == r) ? 1.0 : 0.0;
 #pragma unroll
     for (int k = 0; k < r; k++) {
@@ -134,9 +138,70 @@ __device__ __noinline__ int warp_potrf32_inv(double* __restrict__ T, double* __r
     }
     x[r] = s * __shfl_sync(0xffffffffu, invd, r);
   }
+  if (lane < N) {
 #pragma unroll
-  for (int r = 0; r < 32; r++) Wout[r * SB32 + lane] = (r >= lane) ? x[r] : 0.0;
+    for (int r = 0; r < N; r++) Wout[r * SB32 + lane] = (r >= lane) ? x[r] : 0.0;
+  }
   return fail;
+}
+
+#ifndef THB_CHOL_LEAF
+#define THB_CHOL_LEAF 8
+#endif
+
+// All 256 threads: Cholesky + inverse of the NxN block at T (row stride SC; L in place, lower part) -> Wb (row stride SB32; full
+// block, zeros above the diagonal).  N == THB_CHOL_LEAF: one warp does it in registers.  Otherwise the same 2x2 recursion as one
+// level up: factor+invert T00, L10 = T10 W00^T, T11 -= L10 L10^T, factor+invert T11, W10 = -W11 L10 W00 -- the products as DMMA on
+// 8x8 tiles (one warp per tile).  Small leaves matter because the serial pivots are scalar FP64 instructions that compete for the
+// FP64 pipe with the DMMA stream of the co-resident CTA: a 32x32 register leaf costs 33-57 us there, four 8x8 leaves + tile
+// products a fraction of it (profiles/r01_chol_history.md).  The return value is valid on warp 0.
+template <int N>
+__device__ __forceinline__ int block_factor_invert(double* __restrict__ T, double* __restrict__ Wb, int warp, int lane) {
+  if constexpr (N <= THB_CHOL_LEAF) {
+    int f = 0;
+    if (warp == 0) f = warp_potrf_inv<N>(T, Wb, lane);
+    __syncthreads();
+    return f;
+  } else {
+    constexpr int H = N / 2, TPB = H / 8;  // half size, 8x8 tiles per side of a half block
+    const int lr = lane >> 2, lc = lane & 3;
+    const int rt = warp / TPB, ct = warp % TPB;
+    const bool own = warp < TPB * TPB;
+    double a0 = 0.0, a1 = 0.0;
+    const int f0 = block_factor_invert<H>(T, Wb, warp, lane);
+    // panel: L10 = T10 W00^T
+    if (own) tile_mma_rows(a0, a1, T + (H + 8 * rt) * SC, SC, Wb + (8 * ct) * SB32, SB32, 0, 2 * ct + 2, lr, lc);
+    __syncthreads();
+    if (own) *reinterpret_cast<double2*>(&T[(H + 8 * rt + lr) * SC + 8 * ct + 2 * lc]) = make_double2(a0, a1);
+    __syncthreads();
+    // trailing: T11 -= L10 L10^T
+    if (own) {
+      a0 = a1 = 0.0;
+      tile_mma_rows(a0, a1, T + (H + 8 * rt) * SC, SC, T + (H + 8 * ct) * SC, SC, 0, H / 4, lr, lc);
+      double2* d = reinterpret_cast<double2*>(&T[(H + 8 * rt + lr) * SC + H + 8 * ct + 2 * lc]);
+      double2 v = *d;
+      v.x -= a0; v.y -= a1;
+      *d = v;
+    }
+    __syncthreads();
+    const int f1 = block_factor_invert<H>(T + H * SC + H, Wb + H * SB32 + H, warp, lane);
+    // inverse: X = W11 L10 (W11 lower triangular) parked in the W01 corner, then W10 = -X W00, then W01 = 0
+    if (own) {
+      a0 = a1 = 0.0;
+      tile_mma_cols(a0, a1, Wb + (H + 8 * rt) * SB32 + H, SB32, T + H * SC + 8 * ct, SC, 0, 2 * rt + 2, lr, lc);
+      *reinterpret_cast<double2*>(&Wb[(8 * rt + lr) * SB32 + H + 8 * ct + 2 * lc]) = make_double2(a0, a1);
+    }
+    __syncthreads();
+    if (own) {
+      a0 = a1 = 0.0;
+      tile_mma_cols(a0, a1, Wb + (8 * rt) * SB32 + H, SB32, Wb + 8 * ct, SB32, 2 * ct, H / 4, lr, lc);
+      *reinterpret_cast<double2*>(&Wb[(H + 8 * rt + lr) * SB32 + 8 * ct + 2 * lc]) = make_double2(-a0, -a1);
+    }
+    __syncthreads();
+    if (own) *reinterpret_cast<double2*>(&Wb[(8 * rt + lr) * SB32 + H + 8 * ct + 2 * lc]) = make_double2(0.0, 0.0);
+    __syncthreads();
+    return f0 != 0 ? f0 : (f1 != 0 ? H + f1 : 0);
+  }
 }
 
 // All 256 threads.  T: the 64x64 diagonal block inside the C tile (row stride SC), Wd: scratch [2][32][SB32],
@@ -152,11 +217,10 @@ __device__ __noinline__ int diag64_factor_invert(double* __restrict__ T, double*
   const int t0 = warp, t1 = warp + 8;
   const int rt0 = t0 >> 2, ct0 = t0 & 3, rt1 = t1 >> 2, ct1 = t1 & 3;
   double a0, a1, b0, b1;
-  // ---- block column 0 ----  (which warp runs the serial pivots makes no measurable difference: first and last tried)
-  constexpr int PIVOT_WARP = 0;
-  if (warp == PIVOT_WARP) {
-    const int f = warp_potrf32_inv(T, Wd, lane);
-    if (lane == 0 && f != 0) s_fail = f;
+  // ---- block column 0 ----
+  {
+    const int f = block_factor_invert<32>(T, Wd, warp, lane);
+    if (tid == 0 && f != 0) s_fail = f;
   }
   __syncthreads();
   THB_TICK(8);
@@ -183,9 +247,9 @@ __device__ __noinline__ int diag64_factor_invert(double* __restrict__ T, double*
   __syncthreads();
   THB_TICK(9);
   // ---- block column 1 ----
-  if (warp == PIVOT_WARP) {
-    const int f = warp_potrf32_inv(T + 32 * SC + 32, Wd + 32 * SB32, lane);
-    if (lane == 0 && f != 0 && s_fail == 0) s_fail = 32 + f;
+  {
+    const int f = block_factor_invert<32>(T + 32 * SC + 32, Wd + 32 * SB32, warp, lane);
+    if (tid == 0 && f != 0 && s_fail == 0) s_fail = 32 + f;
   }
   __syncthreads();
   THB_TICK(10);
