@@ -540,6 +540,48 @@ def make_backward_lie(th):
     np.savez_compressed(os.path.join(HERE, "backward_lie_kat.npz"), **out)
 
 
+G2O_3D = """VERTEX_SE3:QUAT 0 0 0 0 0 0 0 1
+VERTEX_SE3:QUAT 1 1.02 0.03 -0.01 0.01 0.02 0.10 0.994
+VERTEX_SE3:QUAT 2 2.05 0.10 0.02 -0.02 0.03 0.25 0.967
+VERTEX_SE3:QUAT 3 2.90 0.95 0.05 0.05 -0.01 0.60 0.798
+EDGE_SE3:QUAT 0 1 1.0 0.0 0.0 0.0 0.0 0.0998 0.995 100 0 0 0 0 0 100 0 0 0 0 100 0 0 0 400 0 0 400 0 400
+EDGE_SE3:QUAT 1 2 1.0 0.1 0.0 0.0 0.0 0.149 0.9888 90 1 0 0 0 0 110 0 2 0 0 95 0 0 0 380 0 0 420 3 410
+EDGE_SE3:QUAT 2 3 1.0 0.5 0.0 0.02 0.0 0.38 0.9248 100 0 0 0 0 0 100 0 0 0 0 100 0 0 0 400 0 0 400 0 400
+EDGE_SE3:QUAT 0 3 2.9 1.0 0.0 0.0 0.0 0.64 0.7684 50 0 0 0 0 0 50 0 0 0 0 50 0 0 0 200 0 0 200 0 200
+"""
+
+
+def make_io(th):
+    """On-disk formats: the g2o reader (pose_graph/dataset.py:35-104) and the BAL loader (bundle_adjustment/data.py:166-207) of the
+    reference on small files committed next to this script."""
+    import torch
+    import theseus.utils.examples as theg
+    from theseus.utils.examples.pose_graph.dataset import read_3D_g2o_file
+    g2o = os.path.join(HERE, "io_small.g2o")
+    with open(g2o, "w") as f:
+        f.write(G2O_3D)
+    n, verts, edges = read_3D_g2o_file(g2o, dtype=torch.float64)
+    out = dict(g2o_n=np.array(n), g2o_verts=np.concatenate([v.tensor.numpy() for v in verts], 0),
+               g2o_edge_ij=np.array([[e.i, e.j] for e in edges]), g2o_edge_pose=np.concatenate([e.relative_pose.tensor.numpy() for e in edges], 0),
+               g2o_edge_w=np.concatenate([e.weight.diagonal.tensor.numpy() for e in edges], 0))
+    torch.manual_seed(5); np.random.seed(5)
+    import random
+    random.seed(5)
+    ba = theg.BundleAdjustmentDataset.generate_synthetic(num_cameras=3, num_points=8, average_track_length=2, track_locality=0.3)
+    bal = os.path.join(HERE, "io_small_bal.txt")
+    ba.save_to_file(bal)
+    cams, pts, obs = theg.BundleAdjustmentDataset.load_bal_dataset(bal)
+    out.update(bal_cam_pose=np.concatenate([c.pose.tensor.numpy() for c in cams], 0),
+               bal_cam_f=np.concatenate([c.focal_length.tensor.numpy() for c in cams], 0),
+               bal_cam_k1=np.concatenate([c.calib_k1.tensor.numpy() for c in cams], 0),
+               bal_cam_k2=np.concatenate([c.calib_k2.tensor.numpy() for c in cams], 0),
+               bal_pts=np.concatenate([p.tensor.numpy() for p in pts], 0),
+               bal_obs=np.array([[o.camera_index, o.point_index] for o in obs]),
+               bal_feat=np.concatenate([o.image_feature_point.tensor.numpy() for o in obs], 0))
+    np.savez_compressed(os.path.join(HERE, "io_kat.npz"), **out)
+    print("io_kat: g2o", n, "vertices", len(edges), "edges; bal", len(cams), "cameras", len(pts), "points", len(obs), "observations")
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -576,6 +618,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ba_c3":   # config C3 at full size (50 cameras x 1000 points x 8 observations per point, Huber)
         make_ba(th, "ba_c3_huber", num_cameras=50, num_points=1000, B=2, seed=11, iters=5, robust=True, track_length=8)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "io":
+        make_io(th)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "backward_lie":
         make_backward_lie(th)
         sys.exit(0)
@@ -601,3 +646,4 @@ if __name__ == "__main__":
     make_autodiff_lie(th)
     make_backward_lie(th)
     make_ba(th, "ba_c3_huber", num_cameras=50, num_points=1000, B=2, seed=11, iters=5, robust=True, track_length=8)
+    make_io(th)

@@ -21,5 +21,6 @@ from .optimizer import (VariableOrdering, Linearization, DenseLinearization, Spa
                         NonlinearOptimizerParams, BackwardMode, convert_to_alpha_beta_damping_tensors)
 from .sparse_solver import BaspachoSparseSolver, BlockSparseSolver, CholmodSparseSolver, LUCudaSparseSolver  # noqa: F401
 from .layer import TheseusLayer  # noqa: F401
+from . import io_formats  # noqa: F401  (g2o / BAL readers: th.io_formats.read_3D_g2o_file, load_bal_dataset)
 
 __version__ = "0.1.0"
