@@ -152,7 +152,7 @@ def make_pgo(th, name, num_poses, B, seed, iters, lm_kwargs, method="lm", full_t
     out["prior_w"] = np.array(1e-3)
     out["robust"] = np.array(robust or "")
     out["log_loss_radius"] = np.array([[0.5]])
-    cls = th.LevenbergMarquardt if method == "lm" else th.GaussNewton
+    cls = {"lm": th.LevenbergMarquardt, "gn": th.GaussNewton, "dogleg": th.Dogleg}[method]
     opt = cls(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=iters,
               step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
     ordering = [v.name for v in opt.linear_solver.linearization.ordering]
@@ -171,6 +171,8 @@ def make_pgo(th, name, num_poses, B, seed, iters, lm_kwargs, method="lm", full_t
         tr["AtA_diag"].append(lin.AtA.diagonal(dim1=1, dim2=2).numpy().copy())
         if method == "lm":
             tr["lam"].append(np.array(optimizer._damping, dtype=np.float64) * np.ones(B))
+        if method == "dogleg":
+            tr["lam"].append(optimizer._trust_region.view(-1).numpy().copy())   # trace_lam = trust-region radius after the step
         if full_trace and it == 0:
             tr["AtA"].append(lin.AtA.numpy().copy())
             tr["b"].append(lin.b.numpy().copy())
@@ -618,6 +620,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ba_c3":   # config C3 at full size (50 cameras x 1000 points x 8 observations per point, Huber)
         make_ba(th, "ba_c3_huber", num_cameras=50, num_points=1000, B=2, seed=11, iters=5, robust=True, track_length=8)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dogleg":
+        make_pgo(th, "pgo_small_dogleg", num_poses=8, B=4, seed=12, iters=8, lm_kwargs=dict(trust_region_init=0.3), method="dogleg",
+                 loop_closure_ratio=0.5, init_perturb=0.6, full_trace=False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "io":
         make_io(th)
         sys.exit(0)
@@ -647,3 +653,5 @@ if __name__ == "__main__":
     make_backward_lie(th)
     make_ba(th, "ba_c3_huber", num_cameras=50, num_points=1000, B=2, seed=11, iters=5, robust=True, track_length=8)
     make_io(th)
+    make_pgo(th, "pgo_small_dogleg", num_poses=8, B=4, seed=12, iters=8, lm_kwargs=dict(trust_region_init=0.3), method="dogleg",
+             loop_closure_ratio=0.5, init_perturb=0.6, full_trace=False)

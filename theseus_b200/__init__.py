@@ -17,7 +17,7 @@ from .core import (CostWeight, ScaleCostWeight, DiagonalCostWeight, CostFunction
 from . import embodied as eb  # noqa: F401  (th.eb.Reprojection, like the reference)
 from .optimizer import (VariableOrdering, Linearization, DenseLinearization, SparseLinearization, LinearSolver,  # noqa: F401
                         DenseSolver, CholeskyDenseSolver, LUDenseSolver, NonlinearLeastSquares, GaussNewton,
-                        LevenbergMarquardt, NonlinearOptimizerStatus, NonlinearOptimizerInfo, OptimizerInfo,
+                        LevenbergMarquardt, TrustRegion, Dogleg, NonlinearOptimizerStatus, NonlinearOptimizerInfo, OptimizerInfo,
                         NonlinearOptimizerParams, BackwardMode, convert_to_alpha_beta_damping_tensors)
 from .sparse_solver import BaspachoSparseSolver, BlockSparseSolver, CholmodSparseSolver, LUCudaSparseSolver  # noqa: F401
 from .layer import TheseusLayer  # noqa: F401

@@ -198,7 +198,15 @@ class DenseLinearization(Linearization):
         return self._Atb.unsqueeze(2)
 
     def Av(self, v: torch.Tensor) -> torch.Tensor:
-        return self.A.bmm(v.unsqueeze(2)).squeeze(2)
+        """A v from the CSR values (dense_linearization.py:73-74 does A.bmm(v) on the 99 %-zero dense Jacobian)."""
+        eng = self.engine
+        S = eng.structure
+        rp, ci = eng.buf_const("A_row_ptr", S.A_row_ptr), eng.buf_const("A_col_ind", S.A_col_ind)
+        A64, v64 = self._A_val.double().contiguous(), v.double().contiguous()
+        out = torch.empty(v.shape[0], self.num_rows, dtype=torch.float64, device=v.device)
+        _lib.check(eng.lib.thb_mat_vec_f64(v.shape[0], self.num_rows, self.num_cols, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(A64), _lib.ptr(v64),
+                                            _lib.ptr(out), _lib.stream_ptr()), "mat_vec")
+        return out.to(v.dtype)
 
     def diagonal_scaling(self, v: torch.Tensor) -> torch.Tensor:
         return v * self._diag
@@ -895,3 +903,84 @@ class LevenbergMarquardt(NonlinearLeastSquares):
         n_rej = int(self._stats_host[0])
         total = int(self._stats_host[1]) if self.process_group is not None else B
         return n_rej == total
+
+
+class TrustRegion(NonlinearLeastSquares):
+    """theseus/optimizer/nonlinear/trust_region.py:24-151 (Nocedal & Wright ch. 4): the step is accepted / the radius adapted from
+    rho = actual / predicted reduction, the prediction from the linearization already on the device (Atb, A v)."""
+
+    def __init__(self, objective: Objective, *args, **kwargs):
+        super().__init__(objective, *args, **kwargs)
+        self._trust_region: torch.Tensor = None
+
+    def reset(self, trust_region_init: float = 0.5, **kwargs) -> None:
+        super().reset(**kwargs)
+        self._trust_region = trust_region_init * torch.ones(self.objective.batch_size, 1, device=self.objective.device, dtype=self.objective.dtype)
+
+    def _compute_delta_impl(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def compute_delta(self, **kwargs) -> torch.Tensor:
+        return self._compute_delta_impl()
+
+    @staticmethod
+    def _squared_norm(tensor: torch.Tensor, keepdim: bool = True) -> torch.Tensor:
+        return (tensor ** 2).sum(dim=1, keepdim=keepdim)
+
+    def _predicted_error(self, previous_error: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
+        lin = self.linear_solver.linearization
+        Adelta = lin.Av(delta)
+        grad = -lin.Atb.squeeze(2)
+        return previous_error + (delta * grad).sum(dim=1) + 0.5 * TrustRegion._squared_norm(Adelta, keepdim=False)
+
+    def _compute_rho(self, delta, previous_err, new_err) -> torch.Tensor:
+        pred_err = self._predicted_error(previous_err, delta)
+        return ((previous_err - new_err) / (previous_err - pred_err)).view(-1, 1)
+
+    @torch.no_grad()
+    def _complete_step(self, delta, new_err, previous_err, accept_threshold: float = 0.0, shrink_threshold: float = 0.25,
+                       expand_threshold: float = 0.75, shrink_ratio: float = 0.25, expand_ratio: float = 2.0,
+                       min_trust_region: float = 1.0e-5, max_trust_region: float = 1.0e5, **kwargs):
+        good = (0.0 < shrink_ratio <= 1.0) and (expand_ratio >= 1.0) and (shrink_threshold < expand_threshold) and (accept_threshold < shrink_threshold)
+        if not good:
+            raise ValueError("Invalid parameters for TrustRegionMethod. Values must satisfy <accept/shrink>_threshold < expand_threshold, "
+                             "shrink_ratio in (0, 1], and expand_ratio > 1.0.")
+        rho = self._compute_rho(delta, previous_err, new_err)
+        tr = torch.where(rho < shrink_threshold, self._trust_region * shrink_ratio, self._trust_region)
+        tr = torch.where(rho > expand_threshold, tr * expand_ratio, tr)
+        self._trust_region = tr.clamp(min_trust_region, max_trust_region)
+        reject = (rho < accept_threshold).view(-1)
+        err = torch.where(reject, previous_err, new_err)
+        return reject, err, bool(reject.all())
+
+
+class Dogleg(TrustRegion):
+    """theseus/optimizer/nonlinear/dogleg.py:14-105: Gauss-Newton step if it lies inside the trust region, else the dogleg path
+    between the Cauchy point and the Gauss-Newton point.  The factorisation, A v, retraction and error are the fused kernels; the
+    path arithmetic is a handful of [B,n] vector operations."""
+    EPS = 1e-7
+
+    def _compute_delta_impl(self) -> torch.Tensor:
+        tr2 = self._trust_region ** 2
+        delta_gn = self.linear_solver.solve()
+        if (TrustRegion._squared_norm(delta_gn) < tr2).all():
+            return delta_gn
+        lin = self.linear_solver.linearization
+        delta_sd = lin.Atb.squeeze(2)
+        Adelta_sd_norm_2 = TrustRegion._squared_norm(lin.Av(delta_sd))
+        grad_norm_2 = TrustRegion._squared_norm(delta_sd)
+        cauchy = grad_norm_2 / (Adelta_sd_norm_2 + Dogleg.EPS)
+        delta_c = delta_sd * cauchy
+        delta_c_norm_2 = grad_norm_2 * (cauchy ** 2)
+        inside = delta_c_norm_2 <= tr2
+        delta_dogleg = delta_c if bool(inside.all()) else torch.where(inside, delta_c, delta_c * self._trust_region / (delta_c_norm_2 + Dogleg.EPS).sqrt())
+        if bool(inside.any()):
+            diff = delta_gn - delta_c
+            a = TrustRegion._squared_norm(diff)
+            b = (2 * delta_c * diff).sum(dim=1, keepdim=True)
+            c = delta_c_norm_2 - tr2
+            disc = ((b ** 2) - 4 * a * c).clamp(Dogleg.EPS)
+            tau = ((-b + disc.sqrt()) / (2 * a + Dogleg.EPS)).clamp(max=1.0)
+            delta_dogleg = torch.where(inside, delta_c + tau * diff, delta_dogleg)
+        return delta_dogleg
+
