@@ -584,6 +584,58 @@ def make_io(th):
     print("io_kat: g2o", n, "vertices", len(edges), "edges; bal", len(cams), "cameras", len(pts), "points", len(obs), "observations")
 
 
+BACKWARD_PGO_CASES = {
+    # (fixture, method, iters, optimizer kwargs)
+    "plain_implicit_gn": ("pgo_small_lm_hard", "gn", 8, dict(backward_mode="implicit")),
+    "plain_unroll_lm": ("pgo_small_lm_hard", "lm", 3, dict(backward_mode="unroll", damping=1.0, adaptive_damping=True, ellipsoidal_damping=True)),
+    "welsch_implicit_lm": ("pgo_small_welsch", "lm", 8, dict(backward_mode="implicit", damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)),
+    "welsch_unroll_lm": ("pgo_small_welsch", "lm", 3, dict(backward_mode="unroll", damping=1.0, adaptive_damping=True, ellipsoidal_damping=True)),
+}
+
+
+def backward_pgo_run(th, torch, case, device="cpu", solver_kwargs=None):
+    """Shared by the generator (th = reference) and tests/test_gpu_backward.py (th = theseus_b200): pose graph of a committed fixture
+    with Between (+ Welsch) costs, leaves = every edge's DiagonalCostWeight, the prior's scale and the robust log-radius; outer loss =
+    fixed random weights dotted with the optimised poses.  Returns (poses [N,B,3,4], grads dict)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE)))
+    from helpers import load, pgo_objective
+    fixture, method, iters, kw = BACKWARD_PGO_CASES[case]
+    g = load(fixture)
+    objective, poses = pgo_objective(th, g, device=device)
+    leaves = {}
+    for name, cf in objective.cost_functions.items():
+        inner = getattr(cf, "cost_function", cf)
+        wt = inner.weight
+        leaves["w_" + inner.name] = (wt.diagonal if hasattr(wt, "diagonal") else wt.scale).tensor
+        if hasattr(cf, "log_loss_radius"):
+            leaves["log_loss_radius"] = cf.log_loss_radius.tensor
+    for t in leaves.values():
+        t.requires_grad_(True)
+    cls = th.GaussNewton if method == "gn" else th.LevenbergMarquardt
+    opt = cls(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **(solver_kwargs or dict(linear_solver_cls=th.CholeskyDenseSolver)))
+    layer = th.TheseusLayer(opt)
+    sol, info = layer.forward({p.name: p.tensor.clone() for p in poses}, optimizer_kwargs=dict(kw))
+    gen = torch.Generator().manual_seed(77)
+    P = torch.stack([sol[p.name] for p in poses], 0)
+    Wfix = torch.randn(P.shape, generator=gen, dtype=torch.float64).to(P.device)
+    (P * Wfix).sum().backward()
+    return P.detach(), {k: v.grad.detach() for k, v in leaves.items()}
+
+
+def make_backward_pgo(th):
+    """Backward modes through the reference's own Between / RobustCostFunction (torchlie analytic Jacobians, autograd through them)."""
+    import torch
+    out = {}
+    for case in BACKWARD_PGO_CASES:
+        P, grads = backward_pgo_run(th, torch, case)
+        out[case + "_poses"] = P.numpy()
+        for k, v in grads.items():
+            out[case + "_grad_" + k] = v.numpy()
+        print("backward_pgo", case, "max |grad w|", max(float(v.abs().max()) for k, v in grads.items() if k.startswith("w_")),
+              "grad log_radius", grads.get("log_loss_radius"))
+    np.savez_compressed(os.path.join(HERE, "backward_pgo_kat.npz"), **out)
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -624,6 +676,9 @@ if __name__ == "__main__":
         make_pgo(th, "pgo_small_dogleg", num_poses=8, B=4, seed=12, iters=8, lm_kwargs=dict(trust_region_init=0.3), method="dogleg",
                  loop_closure_ratio=0.5, init_perturb=0.6, full_trace=False)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "backward_pgo":
+        make_backward_pgo(th)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "io":
         make_io(th)
         sys.exit(0)
@@ -655,3 +710,4 @@ if __name__ == "__main__":
     make_io(th)
     make_pgo(th, "pgo_small_dogleg", num_poses=8, B=4, seed=12, iters=8, lm_kwargs=dict(trust_region_init=0.3), method="dogleg",
              loop_closure_ratio=0.5, init_perturb=0.6, full_trace=False)
+    make_backward_pgo(th)

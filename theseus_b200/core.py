@@ -128,6 +128,48 @@ class CostFunction:
             v.to(*args, **kwargs)
         self.weight.to(*args, **kwargs)
 
+    # ---- torch path: AutoDiffCostFunction always, the fused-kernel cost functions only on the autograd tape of the backward modes ----
+    def _torch_error(self, optim_tensors: Sequence[torch.Tensor], aux_tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Unweighted error [B, dim] from raw storage tensors with differentiable torch ops (lie_torch.py)."""
+        raise NotImplementedError(f"{self.__class__.__name__} has no torch restatement: it cannot be put on the autograd tape")
+
+    def _torch_aux(self) -> List[Variable]:
+        return self.aux_vars
+
+    def _weight(self, err: torch.Tensor, jacs):
+        w = self.weight.weight_tensor().tensor
+        w = w.view(-1, 1) if self.weight.WEIGHT_KIND == WEIGHT_SCALE else w
+        err = err * w
+        if jacs is not None:
+            jacs = [J * (w.unsqueeze(2) if w.ndim == 2 else w) for J in jacs]
+        return jacs, err
+
+    def generic_jacobians_error(self, optim_tensors: Sequence[torch.Tensor], differentiable: bool = False):
+        """(weighted Jacobians [B,dim,dof_i], weighted error [B,dim]) by vmap(jacrev(error)) + tangent-space projection
+        (cost_function.py:318-393, v.project(jac, is_sparse=True)).  differentiable=True keeps the graph to the aux variables /
+        weights / variable values (backward modes)."""
+        from torch.func import jacrev, vmap
+        ovars = self.optim_vars
+        aux = tuple(v.tensor for v in self._torch_aux())
+        B = max([t.shape[0] for t in optim_tensors] + [t.shape[0] for t in aux])
+        ex = lambda t: t if t.shape[0] == B else t.expand((B,) + tuple(t.shape[1:]))
+        opt_t, aux_t = tuple(ex(t) for t in optim_tensors), tuple(ex(t) for t in aux)
+
+        def one(o, a):
+            return self._torch_error(tuple(x.unsqueeze(0) for x in o), tuple(x.unsqueeze(0) for x in a))[0]
+
+        with torch.enable_grad():
+            jacs = vmap(jacrev(one, argnums=0))(opt_t, aux_t)
+            err = self._torch_error(opt_t, aux_t)
+        jacs = [type(v).project_tensor(t, j) for v, t, j in zip(ovars, opt_t, jacs)]  # Euclidean -> tangent space (identity for Vector)
+        if differentiable:
+            return self._weight(err, jacs)
+        return self._weight(err.detach(), [j.detach() for j in jacs])
+
+    def generic_error(self, optim_tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Weighted error [B, dim] at the given optimisation-variable tensors."""
+        return self._weight(self._torch_error(tuple(optim_tensors), tuple(v.tensor for v in self._torch_aux())), None)[1]
+
 
 class Between(CostFunction):
     """theseus/embodied/measurements/between.py:14-60: e = log(Z^-1 (X0^-1 X1))."""
@@ -143,6 +185,11 @@ class Between(CostFunction):
 
     def dim(self) -> int:
         return self.v0.dof()
+
+    def _torch_error(self, optim_tensors, aux_tensors):
+        from . import lie_torch
+        k = self.v0.KIND
+        return lie_torch.local(k, aux_tensors[0], lie_torch.between(k, optim_tensors[0], optim_tensors[1]))  # between.py:34-37
 
     def schema(self):
         if isinstance(self.v0, SE3):
@@ -169,6 +216,10 @@ class Difference(CostFunction):
 
     def dim(self) -> int:
         return self.var.dof()
+
+    def _torch_error(self, optim_tensors, aux_tensors):
+        from . import lie_torch
+        return lie_torch.local(self.var.KIND, aux_tensors[0], optim_tensors[0])  # local_cost_fn.py:40-43
 
     def schema(self):
         if isinstance(self.var, SE3):
@@ -206,6 +257,14 @@ class Reprojection(CostFunction):
 
     def dim(self) -> int:
         return 2
+
+    def _torch_error(self, optim_tensors, aux_tensors):
+        X, p = optim_tensors
+        f, z, k1, k2 = aux_tensors
+        q = (X[..., :3] @ p[..., None])[..., 0] + X[..., 3]              # reprojection.py:54-66
+        proj = -q[..., :2] / q[..., 2:3]
+        n = (proj * proj).sum(dim=-1, keepdim=True)
+        return proj * (f * (1.0 + n * (k1 + n * k2))) - z
 
     def schema(self):
         return COST_REPROJECTION, [self.focal_length, self.image_feature_point, self.calib_k1, self.calib_k2]
@@ -251,6 +310,20 @@ class RobustCostFunction(CostFunction):
 
     def dim(self) -> int:
         return self.cost_function.dim()
+
+    def generic_jacobians_error(self, optim_tensors, differentiable: bool = False):
+        """robust_cost_function.py:115-135: J, e of the wrapped cost rescaled by sqrt(rho'(||w e||^2) + eps)."""
+        jacs, err = self.cost_function.generic_jacobians_error(optim_tensors, differentiable=differentiable)
+        radius = self.log_loss_radius.tensor.exp()
+        x = (err ** 2).sum(dim=1, keepdim=True)
+        if self.robust_kind == WelschLoss.ROBUST_KIND:
+            lin = torch.exp(-x / (radius + 1e-20))                        # robust_loss.py:33-41
+        else:
+            lin = torch.sqrt(radius / torch.max(x, radius) + 1e-20)       # robust_loss.py:43-52 (Huber)
+        sc = torch.sqrt(lin + 1e-20)
+        if not differentiable:
+            sc = sc.detach()
+        return [sc.unsqueeze(2) * J for J in jacs], sc * err
 
     def schema(self):
         kind, aux = self.cost_function.schema()
@@ -298,38 +371,11 @@ class AutoDiffCostFunction(CostFunction):
         def __getitem__(self, item):
             return self.tensor[item]
 
-    def _weight(self, err: torch.Tensor, jacs):
-        w = self.weight.weight_tensor().tensor
-        w = w.view(-1, 1) if self.weight.WEIGHT_KIND == WEIGHT_SCALE else w
-        err = err * w
-        if jacs is not None:
-            jacs = [J * (w.unsqueeze(2) if w.ndim == 2 else w) for J in jacs]
-        return jacs, err
+    def _torch_error(self, optim_tensors, aux_tensors):
+        return self._err_fn(optim_vars=tuple(self._T(t) for t in optim_tensors), aux_vars=tuple(self._T(t) for t in aux_tensors))
 
-    def generic_error(self, optim_tensors: Sequence[torch.Tensor]) -> torch.Tensor:
-        """Weighted error [B, dim] at the given optimisation-variable tensors."""
-        err = self._err_fn(optim_vars=tuple(self._T(t) for t in optim_tensors), aux_vars=tuple(self._T(v.tensor) for v in self._aux))
-        return self._weight(err, None)[1]
-
-    def generic_jacobians_error(self, optim_tensors: Sequence[torch.Tensor], differentiable: bool = False):
-        """(weighted Jacobians [B,dim,dof_i], weighted error [B,dim]) -- cost_function.py:318-393 (vmap over jacrev)."""
-        from torch.func import jacrev, vmap
-        aux = tuple(v.tensor for v in self._aux)
-        B = max([t.shape[0] for t in optim_tensors] + [t.shape[0] for t in aux])
-        ex = lambda t: t if t.shape[0] == B else t.expand((B,) + tuple(t.shape[1:]))
-        opt_t, aux_t = tuple(ex(t) for t in optim_tensors), tuple(ex(t) for t in aux)
-
-        def one(o, a):
-            return self._err_fn(optim_vars=tuple(self._T(x.unsqueeze(0)) for x in o), aux_vars=tuple(self._T(x.unsqueeze(0)) for x in a))[0]
-
-        with torch.enable_grad():
-            jacs = vmap(jacrev(one, argnums=0))(opt_t, aux_t)
-            err = self._err_fn(optim_vars=tuple(self._T(t) for t in opt_t), aux_vars=tuple(self._T(t) for t in aux_t))
-        # Euclidean -> tangent space (identity for Vector, geometry/vector.py:199-203)
-        jacs = [type(v).project_tensor(t, j) for v, t, j in zip(self._optim, opt_t, jacs)]
-        if differentiable:  # backward modes: keep the graph to the aux variables / weights / variable values
-            return self._weight(err, jacs)
-        return self._weight(err.detach(), [j.detach() for j in jacs])
+    def _torch_aux(self):
+        return self._aux
 
     def schema(self):
         return None, []

@@ -337,15 +337,12 @@ class Engine:
 
     def linearize_sparse_differentiable(self):
         """(A_val, b) as autograd tensors: same layout, values from the cost functions' torch.func Jacobians without detaching, so
-        gradients reach the auxiliary variables / cost weights / current variable values.  Only objectives whose cost functions
-        all take this path are supported on the tape (NonlinearLeastSquares._optimize_impl_differentiable checks)."""
-        if self.groups:
-            raise NotImplementedError("differentiable linearization: fused-kernel cost functions have no autograd path")
+        gradients reach the auxiliary variables / cost weights / current variable values.  AutoDiffCostFunctions use the user's
+        err_fn, the fused-kernel cost functions their torch restatement (core.CostFunction._torch_error)."""
         B, S = self.batch_size, self.structure
         A_val = torch.zeros(B, self.nnz, dtype=self.dtype, device=self.device)
         b = torch.zeros(B, self.m, dtype=self.dtype, device=self.device)
-        for f in self.generic:
-            cf = self.costs[f]
+        for f, cf in enumerate(self.costs):  # every cost function through its torch restatement (O(#costs) torch calls: taped steps only)
             jacs, err = cf.generic_jacobians_error([self._expand(v.tensor) for v in cf.optim_vars], differentiable=True)
             d, st, off = int(S.cost_dims[f]), int(S.stride[f]), int(S.row_block_starts[f])
             blk = A_val[:, off:off + d * st].view(B, d, st)

@@ -75,3 +75,106 @@ def retract(kind: int, X: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
     if kind == 3:
         return se2_retract(X, delta)
     raise NotImplementedError(f"differentiable retraction for variable kind {kind}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# inverse / compose / log: torch restatements used to put the fused-kernel cost functions (Between, Difference, Reprojection) on the
+# autograd tape of the backward modes.  torchlie so3_impl.py:390-433 (_log_impl_helper), se3_impl.py:354-396, :578-581, :703-708;
+# theseus/geometry/se2.py:165-228, :318-339.
+_NEAR_PI = {torch.float32: 1e-2, torch.float64: 1e-7}
+
+
+def so3_log(R: torch.Tensor):
+    sa = 0.5 * torch.stack((R[..., 2, 1] - R[..., 1, 2], R[..., 0, 2] - R[..., 2, 0], R[..., 1, 0] - R[..., 0, 1]), dim=-1)
+    cosine = 0.5 * (R[..., 0, 0] + R[..., 1, 1] + R[..., 2, 2] - 1)
+    sine = sa.norm(dim=-1)
+    theta = torch.atan2(sine, cosine)
+    nz = theta < _NEAR_ZERO[R.dtype]
+    npi = 1 + cosine <= _NEAR_PI[R.dtype]
+    nzp = nz | npi
+    one = torch.ones((), dtype=R.dtype, device=R.device)
+    sine_nz = torch.where(nzp, one, sine)
+    scale = torch.where(nzp, 1 + sine ** 2 / 6, theta / sine_nz)
+    ret = sa * scale[..., None]
+    # near pi: axis from the dominant column of (R + R^T)/2 - cos I
+    d = torch.diagonal(R, dim1=-2, dim2=-1)
+    major = ((d[..., 1] > d[..., 0]) & (d[..., 1] > d[..., 2])).long() + 2 * ((d[..., 2] > d[..., 0]) & (d[..., 2] > d[..., 1])).long()
+    onehot = (major[..., None] == torch.arange(3, device=R.device)).to(R.dtype)  # (one_hot has no vmap batching rule)
+    row = (R * onehot[..., :, None]).sum(dim=-2)
+    col = (R * onehot[..., None, :]).sum(dim=-1)
+    sel = 0.5 * (row + col) - onehot * cosine[..., None]
+    axis = sel / torch.where(nz, one, sel.norm(dim=-1))[..., None]
+    sgn_t = torch.sign((sa * onehot).sum(dim=-1))
+    sgn = torch.where(sgn_t != 0, sgn_t, one)
+    out = torch.where(npi[..., None], axis * (theta * sgn)[..., None], ret)
+    return out, (theta, sine, cosine)
+
+
+def se3_log(T: torch.Tensor) -> torch.Tensor:
+    w, (theta, sine, cosine) = so3_log(T[..., :3])
+    nz = theta < _NEAR_ZERO[T.dtype]
+    one = torch.ones((), dtype=T.dtype, device=T.device)
+    theta2 = theta ** 2
+    st = sine * theta
+    tcm2 = 2 * cosine - 2
+    tcm2_nz = torch.where(nz, one, tcm2)
+    theta2_nz = torch.where(nz, one, theta2)
+    a = torch.where(nz, 1 - theta2 / 12, -st / tcm2_nz)
+    b = torch.where(nz, 1.0 / 12 + theta2 / 720, (st + tcm2) / (theta2_nz * tcm2_nz))
+    t = T[..., 3]
+    lin = a[..., None] * t - 0.5 * torch.linalg.cross(w, t) + b[..., None] * (w * (w * t).sum(-1, keepdim=True))
+    return torch.cat((lin, w), dim=-1)
+
+
+def se3_inverse(T: torch.Tensor) -> torch.Tensor:
+    Rt = T[..., :3].transpose(-1, -2)
+    return torch.cat((Rt, -(Rt @ T[..., 3:])), dim=-1)
+
+
+def se3_compose(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    return torch.cat((A[..., :3] @ B[..., :3], A[..., :3] @ B[..., 3:] + A[..., 3:]), dim=-1)
+
+
+def se2_log(T: torch.Tensor) -> torch.Tensor:
+    cosine, sine = T[..., 2], T[..., 3]
+    theta = torch.atan2(sine, cosine)
+    small = theta.abs() < _SE2_NEAR_ZERO[T.dtype]
+    sine_nz = torch.where(small, torch.ones((), dtype=T.dtype, device=T.device), sine)
+    a = 0.5 * (1 + cosine) * torch.where(small, 1 + sine ** 2 / 6, theta / sine_nz)
+    b = 0.5 * theta
+    return torch.stack((a * T[..., 0] + b * T[..., 1], a * T[..., 1] - b * T[..., 0], theta), dim=-1)
+
+
+def se2_inverse(T: torch.Tensor) -> torch.Tensor:
+    c, s = T[..., 2], T[..., 3]
+    return torch.stack((-(c * T[..., 0] + s * T[..., 1]), -(-s * T[..., 0] + c * T[..., 1]), c, -s), dim=-1)
+
+
+def se2_compose(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    c0, s0, c1, s1 = A[..., 2], A[..., 3], B[..., 2], B[..., 3]
+    return torch.stack((c0 * B[..., 0] - s0 * B[..., 1] + A[..., 0], s0 * B[..., 0] + c0 * B[..., 1] + A[..., 1],
+                        c0 * c1 - s0 * s1, s0 * c1 + c0 * s1), dim=-1)
+
+
+def local(kind: int, X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
+    """log(X^-1 Y): `X.local(Y)` of the reference (lie_group.py:163-170); Vector: Y - X."""
+    if kind == 2:
+        return Y - X
+    if kind == 0:
+        return se3_log(se3_compose(se3_inverse(X), Y))
+    if kind == 1:
+        return so3_log(X.transpose(-1, -2) @ Y)[0]
+    if kind == 3:
+        return se2_log(se2_compose(se2_inverse(X), Y))
+    raise NotImplementedError(f"local() for variable kind {kind}")
+
+
+def between(kind: int, X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
+    """X^-1 Y (lie_group.py:150-161)."""
+    if kind == 0:
+        return se3_compose(se3_inverse(X), Y)
+    if kind == 1:
+        return X.transpose(-1, -2) @ Y
+    if kind == 3:
+        return se2_compose(se2_inverse(X), Y)
+    raise NotImplementedError(f"between() for variable kind {kind}")

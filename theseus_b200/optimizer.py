@@ -687,16 +687,18 @@ class NonlinearLeastSquares:
         loop under no_grad, then ONE differentiable, undamped Gauss-Newton step with the Hessian detached (implicit function
         theorem at the fixed point).  On the tape an iteration is: differentiable linearization (torch.func Jacobians of the
         AutoDiffCostFunctions) -> autograd.LinearSolveFunction (fused CUDA forward, closed-form CUDA backward) -> x + delta."""
-        from .core import AutoDiffCostFunction
+        from .core import CostFunction
         if backward_mode == BackwardMode.DLM:
             raise NotImplementedError("BackwardMode.DLM is not built (SURVEY.md 8: out of scope)")
-        bad_cf = [cf.name for cf in self.objective.cost_functions.values() if not isinstance(cf, AutoDiffCostFunction)]
+        def has_torch(cf):
+            inner = getattr(cf, "cost_function", cf)
+            return type(inner)._torch_error is not CostFunction._torch_error
+        bad_cf = [cf.name for cf in self.objective.cost_functions.values() if not has_torch(cf)]
         bad_v = [v.name for v in self.ordering if v.KIND not in (0, 1, 2, 3)]
         if bad_cf or bad_v:
             raise NotImplementedError(
-                "theseus_b200: differentiating through the optimizer is built for objectives of AutoDiffCostFunctions (over Vector / SE2 / "
-                f"SE3 / SO3 variables); fused-kernel cost functions {bad_cf[:3]} / variables {bad_v[:3]} have no autograd path yet "
-                "-- wrap the call in torch.no_grad().")
+                f"theseus_b200: cost functions {bad_cf[:3]} / variables {bad_v[:3]} have no torch restatement, so they cannot be put on "
+                "the autograd tape of the backward modes -- wrap the call in torch.no_grad().")
         kwargs_plus = {**kwargs, "backward_mode": backward_mode}
         self.reset(**kwargs_plus)
         with torch.no_grad():
