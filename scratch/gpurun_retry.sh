@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: gpurun_retry.sh <timeout> <command string>   -- retries while the pod answers "busy" (exit code 3)
 t=$1; shift
-for i in $(seq 1 20); do
+for i in $(seq 1 70); do
   /usr/local/graft/bin/gpurun --timeout $t -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
