@@ -602,6 +602,10 @@ def backward_pgo_run(th, torch, case, device="cpu", solver_kwargs=None):
     fixture, method, iters, kw = BACKWARD_PGO_CASES[case]
     g = load(fixture)
     objective, poses = pgo_objective(th, g, device=device)
+    # gauge: the fixture's prior has weight 1e-3 (cond(AtA) ~ 4e8), which makes an UN-damped GN step -- what the implicit mode ends
+    # with -- reproducible only to ~1e-6 between two correct implementations; a firm prior on pose 0 makes the comparison sharp
+    gauge_target = th.SE3(tensor=poses[0].tensor.detach().clone(), name="GAUGE_TARGET")
+    objective.add(th.Difference(poses[0], gauge_target, th.ScaleCostWeight(torch.tensor(10.0, dtype=torch.float64).to(poses[0].tensor.device)), name="gauge"))
     leaves = {}
     for name, cf in objective.cost_functions.items():
         inner = getattr(cf, "cost_function", cf)
