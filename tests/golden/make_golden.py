@@ -640,6 +640,24 @@ def make_backward_pgo(th):
     np.savez_compressed(os.path.join(HERE, "backward_pgo_kat.npz"), **out)
 
 
+def make_moving_frame(th):
+    """MovingFrameBetween (embodied/measurements/moving_frame_between.py): weighted error + analytic Jacobians for SE2 and SE3."""
+    import torch
+    torch.manual_seed(3)
+    d = torch.float64
+    out = {}
+    for name, cls in (("se2", th.SE2), ("se3", th.SE3)):
+        B = 6
+        vs = [cls.rand(B, dtype=d) for _ in range(5)]
+        w = torch.rand(1, vs[0].dof(), dtype=d) + 0.5
+        cf = th.eb.MovingFrameBetween(vs[0], vs[1], vs[2], vs[3], vs[4], th.DiagonalCostWeight(w))
+        jacs, e = cf.weighted_jacobians_error()
+        out.update({f"{name}_in": np.stack([v.tensor.numpy() for v in vs], 0), f"{name}_w": w.numpy(), f"{name}_e": e.numpy(),
+                    f"{name}_J": np.stack([j.numpy() for j in jacs], 0)})
+    np.savez_compressed(os.path.join(HERE, "moving_frame_kat.npz"), **out)
+    print("moving_frame_kat", {k: v.shape for k, v in out.items()})
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -683,6 +701,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "backward_pgo":
         make_backward_pgo(th)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "moving_frame":
+        make_moving_frame(th)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "io":
         make_io(th)
         sys.exit(0)
@@ -715,3 +736,4 @@ if __name__ == "__main__":
     make_pgo(th, "pgo_small_dogleg", num_poses=8, B=4, seed=12, iters=8, lm_kwargs=dict(trust_region_init=0.3), method="dogleg",
              loop_closure_ratio=0.5, init_perturb=0.6, full_trace=False)
     make_backward_pgo(th)
+    make_moving_frame(th)

@@ -59,3 +59,17 @@ def test_between_and_local_jacobians_match_reference_analytic_ones():
         # autograd differentiates the closed form exactly; the reference's analytic jlog switches to truncated series below
         # d_near_zero (1e-3 for SE2), a ~1e-8 relative difference in those rows
         np.testing.assert_allclose(J[0].numpy(), g["local_J"], rtol=1e-6, atol=1e-8)
+
+
+def test_moving_frame_between_matches_reference():
+    """th.eb.MovingFrameBetween (4 variables, torch path) against the reference's chained analytic Jacobians (moving_frame_kat.npz)."""
+    g = load("moving_frame_kat")
+    for name, cls in (("se2", th.SE2), ("se3", th.SE3)):
+        ins = [torch.from_numpy(x) for x in g[f"{name}_in"]]
+        vs = [cls(tensor=t) for t in ins]
+        cf = th.eb.MovingFrameBetween(vs[0], vs[1], vs[2], vs[3], vs[4], th.DiagonalCostWeight(torch.from_numpy(g[f"{name}_w"])))
+        assert cf.dim() == vs[0].dof() and cf.num_optim_vars() == 4 and cf.schema() == (None, [])
+        J, e = cf.generic_jacobians_error(ins[:4])
+        np.testing.assert_allclose(e.numpy(), g[f"{name}_e"], rtol=1e-10, atol=1e-12)
+        for q in range(4):
+            np.testing.assert_allclose(J[q].numpy(), g[f"{name}_J"][q], rtol=1e-8, atol=1e-10)

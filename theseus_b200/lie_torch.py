@@ -178,3 +178,22 @@ def between(kind: int, X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
     if kind == 3:
         return se2_compose(se2_inverse(X), Y)
     raise NotImplementedError(f"between() for variable kind {kind}")
+
+
+def velocity_to_tangent(kind: int, D: torch.Tensor, dD: torch.Tensor) -> torch.Tensor:
+    """Tangent coordinates xi of velocities dD = D hat(xi) of a group element D: xi = vee(D^-1 dD).
+    D [B, *g], dD [B, K, *g] (K velocities per element) -> [B, K, dof]."""
+    if kind == 0:   # SE3: D^-1 dD = [R^T dR | R^T dt]
+        M = D[:, None, :, :3].transpose(-1, -2) @ dD
+        w = 0.5 * torch.stack((M[..., 2, 1] - M[..., 1, 2], M[..., 0, 2] - M[..., 2, 0], M[..., 1, 0] - M[..., 0, 1]), dim=-1)
+        return torch.cat((M[..., 3], w), dim=-1)
+    if kind == 1:
+        M = D[:, None].transpose(-1, -2) @ dD
+        return 0.5 * torch.stack((M[..., 2, 1] - M[..., 1, 2], M[..., 0, 2] - M[..., 2, 0], M[..., 1, 0] - M[..., 0, 1]), dim=-1)
+    if kind == 3:   # SE2 storage [x, y, cos, sin]
+        c, s_ = D[:, None, 2], D[:, None, 3]
+        vx = c * dD[..., 0] + s_ * dD[..., 1]
+        vy = -s_ * dD[..., 0] + c * dD[..., 1]
+        return torch.stack((vx, vy, c * dD[..., 3] - s_ * dD[..., 2]), dim=-1)
+    raise NotImplementedError(f"velocity_to_tangent for variable kind {kind}")
+
