@@ -654,6 +654,30 @@ def make_moving_frame(th):
         jacs, e = cf.weighted_jacobians_error()
         out.update({f"{name}_in": np.stack([v.tensor.numpy() for v in vs], 0), f"{name}_w": w.numpy(), f"{name}_e": e.numpy(),
                     f"{name}_J": np.stack([j.numpy() for j in jacs], 0)})
+    # quasi-static pushing (embodied/motionmodel/quasi_static_pushing_planar.py), SE2
+    B = 6
+    vs = [th.SE2.rand(B, dtype=d) for _ in range(4)]
+    c2 = torch.rand(B, 1, dtype=d) + 0.1
+    w = torch.rand(1, 3, dtype=d) + 0.5
+    cf = th.eb.QuasiStaticPushingPlanar(vs[0], vs[1], vs[2], vs[3], th.Variable(c2), th.DiagonalCostWeight(w))
+    jacs, e = cf.weighted_jacobians_error()
+    out.update(qsp_in=np.stack([v.tensor.numpy() for v in vs], 0), qsp_c2=c2.numpy(), qsp_w=w.numpy(), qsp_e=e.numpy(),
+               qsp_J=np.stack([j.numpy() for j in jacs], 0))
+    # effector-object contact (embodied/collision/eff_obj_contact.py): random smooth SDF grid, effector positions inside and outside
+    B = 8
+    rows, cols = 12, 15
+    yy, xx = torch.meshgrid(torch.arange(rows, dtype=d), torch.arange(cols, dtype=d), indexing="ij")
+    sdf = (((xx - 7.0) * 0.1) ** 2 + ((yy - 5.5) * 0.1) ** 2).sqrt().unsqueeze(0) - 0.35 + 0.01 * torch.randn(1, rows, cols, dtype=d)
+    origin = torch.tensor([[-0.7, -0.55]], dtype=d)
+    obj = th.SE2.rand(B, dtype=d)
+    eff_xy_obj = torch.rand(B, 2, dtype=d) * torch.tensor([1.3, 1.0], dtype=d) + origin   # inside the grid (object frame) ...
+    eff_xy_obj[-1] = torch.tensor([5.0, 5.0], dtype=d)                                       # ... except the last one
+    eff = th.SE2(x_y_theta=torch.cat([obj.transform_from(eff_xy_obj).tensor, torch.rand(B, 1, dtype=d)], 1))
+    w = torch.rand(1, 1, dtype=d) + 0.5
+    cf = th.eb.EffectorObjectContactPlanar(obj, eff, origin, sdf, 0.1, torch.tensor(0.05, dtype=d), th.ScaleCostWeight(w))
+    jacs, e = cf.weighted_jacobians_error()
+    out.update(eoc_obj=obj.tensor.numpy(), eoc_eff=eff.tensor.numpy(), eoc_sdf=sdf.numpy(), eoc_origin=origin.numpy(), eoc_w=w.numpy(),
+               eoc_e=e.numpy(), eoc_J=np.stack([j.numpy() for j in jacs], 0))
     np.savez_compressed(os.path.join(HERE, "moving_frame_kat.npz"), **out)
     print("moving_frame_kat", {k: v.shape for k, v in out.items()})
 

@@ -73,3 +73,29 @@ def test_moving_frame_between_matches_reference():
         np.testing.assert_allclose(e.numpy(), g[f"{name}_e"], rtol=1e-10, atol=1e-12)
         for q in range(4):
             np.testing.assert_allclose(J[q].numpy(), g[f"{name}_J"][q], rtol=1e-8, atol=1e-10)
+
+
+def test_quasi_static_pushing_planar_matches_reference():
+    g = load("moving_frame_kat")
+    ins = [torch.from_numpy(x) for x in g["qsp_in"]]
+    vs = [th.SE2(tensor=t) for t in ins]
+    cf = th.eb.QuasiStaticPushingPlanar(vs[0], vs[1], vs[2], vs[3], th.Variable(torch.from_numpy(g["qsp_c2"])),
+                                        th.DiagonalCostWeight(torch.from_numpy(g["qsp_w"])))
+    assert cf.dim() == 3 and cf.num_optim_vars() == 4
+    J, e = cf.generic_jacobians_error(ins)
+    np.testing.assert_allclose(e.numpy(), g["qsp_e"], rtol=1e-11, atol=1e-12)
+    for q in range(4):
+        np.testing.assert_allclose(J[q].numpy(), g["qsp_J"][q], rtol=1e-9, atol=1e-11)
+
+
+def test_effector_object_contact_planar_matches_reference():
+    g = load("moving_frame_kat")
+    P = lambda k: torch.from_numpy(g["eoc_" + k])
+    cf = th.eb.EffectorObjectContactPlanar(th.SE2(tensor=P("obj")), th.SE2(tensor=P("eff")), P("origin"), P("sdf"), 0.1,
+                                           torch.tensor(0.05, dtype=torch.float64), th.ScaleCostWeight(P("w")))
+    assert cf.dim() == 1
+    J, e = cf.generic_jacobians_error([P("obj"), P("eff")])
+    np.testing.assert_allclose(e.numpy(), g["eoc_e"], rtol=1e-11, atol=1e-13)
+    assert e[-1].item() == abs(0.0 - 0.05) * float(g["eoc_w"].ravel()[0])          # out of the grid: boundary value 0
+    for q in range(2):
+        np.testing.assert_allclose(J[q].numpy(), g["eoc_J"][q], rtol=1e-9, atol=1e-11)
