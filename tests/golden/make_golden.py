@@ -682,6 +682,83 @@ def make_moving_frame(th):
     print("moving_frame_kat", {k: v.shape for k, v in out.items()})
 
 
+def tactile_problem(th, torch, inputs, device="cpu"):
+    """A planar-pushing (tactile-style, config C4's cost set) objective shared by generator and tests: T object poses o_t and T
+    effector poses e_t (SE2); per step: EffectorObjectContactPlanar(o_t, e_t), Difference(e_t, measured effector pose);
+    between steps: QuasiStaticPushingPlanar(o_t, o_t+1, e_t, e_t+1), MovingFrameBetween(o_t, o_t+1, e_t, e_t+1, measurement);
+    a prior on o_0.  inputs: dict of tensors (see make_tactile)."""
+    d = torch.float64
+    T = inputs["obj"].shape[0]
+    objs = [th.SE2(tensor=inputs["obj"][t].clone().to(device), name=f"obj_{t}") for t in range(T)]
+    effs = [th.SE2(tensor=inputs["eff"][t].clone().to(device), name=f"eff_{t}") for t in range(T)]
+    c2 = th.Variable(inputs["c_square"].clone().to(device), name="c_square")
+    radius = th.Variable(inputs["eff_radius"].clone().to(device), name="eff_radius")
+    sdf = th.Variable(inputs["sdf"].clone().to(device), name="sdf_data")
+    origin = th.Point2(tensor=inputs["sdf_origin"].clone().to(device), name="sdf_origin")
+    cell = th.Variable(inputs["sdf_cell"].clone().to(device), name="sdf_cell")
+    w = lambda v, n: th.ScaleCostWeight(th.Variable(torch.tensor([[v]], dtype=d).to(device), name=n))
+    w_qsp, w_eoc, w_mfb, w_eff, w_prior = w(2.0, "w_qsp"), w(3.0, "w_eoc"), w(1.5, "w_mfb"), w(10.0, "w_eff"), w(10.0, "w_prior")
+    objective = th.Objective(dtype=d)
+    for t in range(T):
+        objective.add(th.eb.EffectorObjectContactPlanar(objs[t], effs[t], origin, sdf, cell, radius, w_eoc, name=f"eoc_{t}"))
+        objective.add(th.Difference(effs[t], th.SE2(tensor=inputs["eff_meas"][t].clone().to(device), name=f"eff_meas_{t}"), w_eff, name=f"effprior_{t}"))
+    for t in range(T - 1):
+        objective.add(th.eb.QuasiStaticPushingPlanar(objs[t], objs[t + 1], effs[t], effs[t + 1], c2, w_qsp, name=f"qsp_{t}"))
+        objective.add(th.eb.MovingFrameBetween(objs[t], objs[t + 1], effs[t], effs[t + 1],
+                                               th.SE2(tensor=inputs["mfb_meas"][t].clone().to(device), name=f"mfb_meas_{t}"), w_mfb, name=f"mfb_{t}"))
+    objective.add(th.Difference(objs[0], th.SE2(tensor=inputs["obj"][0].clone().to(device), name="obj0_prior"), w_prior, name="objprior"))
+    return objective, objs, effs, dict(c_square=c2, eff_radius=radius, w_qsp=w_qsp.scale, w_eoc=w_eoc.scale, w_mfb=w_mfb.scale)
+
+
+def make_tactile(th):
+    """LM trace + implicit-mode gradients of the planar-pushing objective above, by the reference (dense solver, fp64)."""
+    import torch
+    torch.manual_seed(17)
+    d = torch.float64
+    T, B = 5, 4
+    rows, cols = 16, 16
+    yy, xx = torch.meshgrid(torch.arange(rows, dtype=d), torch.arange(cols, dtype=d), indexing="ij")
+    sdf = (((xx - 7.5) * 0.05) ** 2 + ((yy - 7.5) * 0.05) ** 2).sqrt().unsqueeze(0) - 0.2    # disc of radius 0.2 centred in the object frame
+    obj_gt = [th.SE2(x_y_theta=torch.cat([0.05 * t + 0.02 * torch.randn(B, 2, dtype=d), 0.1 * t + 0.05 * torch.randn(B, 1, dtype=d)], 1)) for t in range(T)]
+    ang = [torch.rand(B, 1, dtype=d) * 6.28 for _ in range(T)]
+    eff_gt = [th.SE2(x_y_theta=torch.cat([obj_gt[t].transform_from(0.25 * torch.cat([a.cos(), a.sin()], 1)).tensor, torch.zeros(B, 1, dtype=d)], 1))
+              for t, a in enumerate(ang)]
+    noise = lambda g, s: g.compose(th.SE2.exp_map(s * torch.randn(B, 3, dtype=d)))
+    inputs = dict(obj=torch.stack([noise(g, 0.05).tensor for g in obj_gt], 0), eff=torch.stack([noise(g, 0.02).tensor for g in eff_gt], 0),
+                  eff_meas=torch.stack([g.tensor for g in eff_gt], 0),
+                  mfb_meas=torch.stack([noise(obj_gt[t].between(eff_gt[t]).between(obj_gt[t + 1].between(eff_gt[t + 1])), 0.01).tensor for t in range(T - 1)], 0),
+                  c_square=torch.tensor([[0.3]], dtype=d), eff_radius=torch.tensor([[0.05]], dtype=d), sdf=sdf,
+                  sdf_origin=torch.tensor([[-0.375, -0.375]], dtype=d), sdf_cell=torch.tensor([[0.05]], dtype=d))
+    out = {k: v.numpy() for k, v in inputs.items()}
+    lm = dict(damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)
+    # forward trace
+    objective, objs, effs, leaves = tactile_problem(th, torch, inputs)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=8, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
+    errs, deltas = [], []
+
+    def cb(optimizer, info, delta, it):
+        errs.append(info.last_err.detach().numpy().copy()); deltas.append(delta.detach().numpy().copy())
+    with torch.no_grad():
+        objective.update()
+        out["err0"] = objective.error_metric().numpy()
+        info = opt.optimize(end_iter_callback=cb, **lm)
+    out["trace_err"], out["trace_delta"] = np.stack(errs, 0), np.stack(deltas, 0)
+    out["final_obj"] = np.stack([o.tensor.numpy() for o in objs], 0)
+    # implicit-mode gradients w.r.t. c_square, eff_radius and three cost weights
+    objective, objs, effs, leaves = tactile_problem(th, torch, inputs)
+    for v in leaves.values():
+        v.tensor.requires_grad_(True)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=8, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
+    sol, info = th.TheseusLayer(opt).forward({v.name: v.tensor.clone() for v in objs + effs}, optimizer_kwargs=dict(lm, backward_mode="implicit"))
+    gen = torch.Generator().manual_seed(5)
+    P = torch.stack([sol[o.name] for o in objs], 0)
+    (P * torch.randn(P.shape, generator=gen, dtype=d)).sum().backward()
+    for k, v in leaves.items():
+        out["grad_" + k] = v.tensor.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "tactile_kat.npz"), **out)
+    print("tactile_kat err", out["err0"], "->", out["trace_err"][-1], "grads", {k: float(np.abs(out["grad_" + k]).max()) for k in leaves})
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -725,6 +802,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "backward_pgo":
         make_backward_pgo(th)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tactile":
+        make_tactile(th)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "moving_frame":
         make_moving_frame(th)
         sys.exit(0)
@@ -761,3 +841,4 @@ if __name__ == "__main__":
              loop_closure_ratio=0.5, init_perturb=0.6, full_trace=False)
     make_backward_pgo(th)
     make_moving_frame(th)
+    make_tactile(th)

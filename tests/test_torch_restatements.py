@@ -99,3 +99,21 @@ def test_effector_object_contact_planar_matches_reference():
     assert e[-1].item() == abs(0.0 - 0.05) * float(g["eoc_w"].ravel()[0])          # out of the grid: boundary value 0
     for q in range(2):
         np.testing.assert_allclose(J[q].numpy(), g["eoc_J"][q], rtol=1e-9, atol=1e-11)
+
+
+def test_tactile_objective_error_metric_matches_reference_on_the_torch_path():
+    """The planar-pushing objective of tests/golden/tactile_kat.npz (config C4's cost set) assembled with this package: the sum of the
+    cost functions' torch-path errors reproduces the reference's objective.error_metric() at the initial point."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    g = load("tactile_kat")
+    inputs = {k: torch.from_numpy(g[k]) for k in ("obj", "eff", "eff_meas", "mfb_meas", "c_square", "eff_radius", "sdf", "sdf_origin", "sdf_cell")}
+    objective, objs, effs, leaves = G.tactile_problem(th, torch, inputs)
+    assert objective.size_cost_functions() == 5 * 2 + 4 * 2 + 1 and len(objective.optim_vars) == 10
+    total = 0.0
+    for cf in objective.cost_functions.values():
+        e = cf.generic_error([v.tensor for v in cf.optim_vars])
+        total = total + 0.5 * (e ** 2).sum(dim=1)
+    np.testing.assert_allclose(total.numpy(), g["err0"], rtol=1e-12)
