@@ -759,6 +759,46 @@ def make_tactile(th):
     print("tactile_kat err", out["err0"], "->", out["trace_err"][-1], "grads", {k: float(np.abs(out["grad_" + k]).max()) for k in leaves})
 
 
+def make_c5(th):
+    """Config C5's problem at full size (2 500 SE3 poses on a sphere, 4 949 edges + prior, n = 15 000), one batch item, 3 LM iterations
+    with the reference's CholeskyDenseSolver on the CPU (dense A is 3.6 GB, AtA 1.8 GB: minutes).  Input data from this repository's
+    generator (theseus_b200.datasets.pose_graph_sphere: plain torch input fabrication), fixture in the pgo_* format."""
+    import time
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    sys.path.insert(0, os.path.dirname(HERE))
+    from theseus_b200.datasets import pose_graph_sphere
+    from helpers import pgo_objective
+    data = pose_graph_sphere(50, 50, 1, seed=0)
+    E = len(data["edges"])
+    g = dict(poses0=data["poses"].numpy(), edges=np.array(data["edges"], dtype=np.int64), meas=data["meas"].numpy(),
+             edge_w=np.tile(data["info"].numpy().reshape(1, 1, 6), (E, 1, 1)), prior_w=np.array(1e-3), robust=np.array(""),
+             log_loss_radius=np.array([[0.5]]))
+
+    class G(dict):
+        files = list(g.keys())
+    t0 = time.time()
+    objective, poses = pgo_objective(th, G(g), device="cpu")
+    iters = 3
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=iters, step_size=1.0,
+                                abs_err_tolerance=0, rel_err_tolerance=0)
+    errs, deltas = [], []
+
+    def cb(optimizer, info, delta, it):
+        errs.append(info.last_err.numpy().copy()); deltas.append(delta.numpy().copy())
+        print("  c5 iteration", it, "err", info.last_err.numpy(), round(time.time() - t0, 1), "s", flush=True)
+    lm = dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
+    with torch.no_grad():
+        objective.update()
+        g["err0"] = objective.error_metric().numpy()
+        opt.optimize(end_iter_callback=cb, **lm)
+    g["trace_err"], g["trace_delta"] = np.stack(errs, 0), np.stack(deltas, 0)
+    g["poses_final"] = np.stack([p.tensor.numpy() for p in poses], 0)
+    g["kwargs_json"] = np.array(repr(dict(method="lm", iters=iters, **lm)))
+    np.savez_compressed(os.path.join(HERE, "pgo_c5_lm.npz"), **g)
+    print("pgo_c5_lm err0", g["err0"], "->", g["trace_err"][-1], "took", round(time.time() - t0, 1), "s")
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -801,6 +841,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "backward_pgo":
         make_backward_pgo(th)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c5":
+        make_c5(th)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tactile":
         make_tactile(th)

@@ -57,3 +57,27 @@ def test_tactile_implicit_gradients():
     for k, v in leaves.items():
         ref = g["grad_" + k]
         assert np.abs(v.tensor.grad.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), k
+
+
+@pytest.mark.parametrize("layout", ["item", "lane"])
+def test_c5_full_size_sparse_lm_trace(layout):
+    """Config C5's pose graph at full size (2 500 poses, n = 15 000), one batch item: the block-sparse solver's LM trace against the
+    reference's dense-solver trace (tests/golden/pgo_c5_lm.npz, generated on the CPU by make_golden.py c5).  Same parked status."""
+    from helpers import pgo_objective, lm_kwargs_of
+    g = load("pgo_c5_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
+                                max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0,
+                                linear_solver_kwargs=dict(layout=layout))
+    errs, deltas = [], []
+
+    def cb(optimizer, info, delta, it):
+        errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+    with torch.no_grad():
+        np.testing.assert_allclose(objective.error_metric().cpu().numpy(), g["err0"], rtol=1e-10)
+        opt.optimize(end_iter_callback=cb, **kw)
+    np.testing.assert_allclose(np.stack(errs, 0), g["trace_err"], rtol=1e-7)
+    for it in range(decisive_iterations(g["err0"], g["trace_err"])):
+        rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
+        assert rel.max() < 1e-5, (it, rel)
