@@ -231,8 +231,27 @@ def test_native_symbolic_equals_python_specification(sizes, fill, ordering):
     for k in ("order", "pos", "dims", "col_start", "pstart", "level", "blk_off", "blk_rows", "blk_cols", "winv_off"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert a.blk_index == b.blk_index and a.stats == b.stats
+    assert np.array_equal(a.chain_of, b.chain_of) and np.array_equal(a.chain_level, b.chain_level)
     assert all(np.array_equal(x, y) for x, y in zip(a.struct, b.struct))
     assert (a.N, a.n, a.data_size, a.winv_size) == (b.N, b.n, b.data_size, b.winv_size)
+
+
+def test_chains_are_fundamental_supernodes():
+    """Chain partition (the unit of the round-2 numeric phase): consecutive columns, nested structures, a tree of chains."""
+    rng = np.random.default_rng(9)
+    M, ptrs, inds = random_block_spd(rng, [6] * 60, 0.05)
+    p = analyze(np.array([6] * 60), ptrs, inds)
+    N = p.N
+    parent = [int(p.struct[j][0]) if len(p.struct[j]) else -1 for j in range(N)]
+    assert p.chain_of[0] == 0 and (np.diff(p.chain_of) >= 0).all() and (np.diff(p.chain_of) <= 1).all()   # chains are runs of columns
+    for j in range(N - 1):
+        if p.chain_of[j] == p.chain_of[j + 1]:
+            assert parent[j] == j + 1 and set(p.struct[j].tolist()) == {j + 1} | set(p.struct[j + 1].tolist())
+            assert sum(1 for q in range(N) if parent[q] == j + 1) == 1
+    for j in range(N):   # a chain sits above all chains that feed it
+        if parent[j] >= 0 and p.chain_of[parent[j]] != p.chain_of[j]:
+            assert p.chain_level[p.chain_of[parent[j]]] > p.chain_level[p.chain_of[j]]
+    assert p.stats["num_chains"] == p.chain_of.max() + 1 <= N and p.stats["chain_levels"] <= p.stats["levels"]
 
 
 def test_minimum_degree_eliminates_leaves_first_and_is_deterministic():

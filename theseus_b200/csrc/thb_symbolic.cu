@@ -265,6 +265,29 @@ int thb_symbolic_create(const int64_t* param_size, int64_t N, const int64_t* blk
     struct_ptr.push_back((i64)struct_idx.size());
     max_front = std::max(max_front, (i64)st[j].size() + 1);
   }
+  // ---- chains (fundamental supernodes): j, j+1, ... with parent(j) = j+1, |struct(j)| = |struct(j+1)| + 1, j the only child ----
+  std::vector<i64> nchild(N, 0), chain_of(N, -1), chain_level;
+  for (i64 j = 0; j < N; j++) if (parent[j] >= 0) nchild[parent[j]]++;
+  i64 nchains = 0;
+  for (i64 j = 0; j < N; j++) {
+    if (chain_of[j] >= 0) continue;
+    chain_of[j] = nchains;
+    i64 k = j;
+    while (true) {
+      const i64 p = parent[k];
+      if (p != k + 1 || nchild[p] != 1 || st[k].size() != st[p].size() + 1) break;
+      chain_of[p] = nchains;
+      k = p;
+    }
+    nchains++;
+  }
+  chain_level.assign(nchains, 0);
+  for (i64 j = 0; j < N; j++) {
+    const i64 p = parent[j];
+    if (p >= 0 && chain_of[p] != chain_of[j]) chain_level[chain_of[p]] = std::max(chain_level[chain_of[p]], chain_level[chain_of[j]] + 1);
+  }
+  i64 chain_levels = 0;
+  for (i64 c = 0; c < nchains; c++) chain_levels = std::max(chain_levels, chain_level[c] + 1);
   auto to32 = [](const std::vector<i64>& v) { return std::vector<i32>(v.begin(), v.end()); };
 
   thb_symbolic* S = new thb_symbolic();
@@ -272,6 +295,7 @@ int thb_symbolic_create(const int64_t* param_size, int64_t N, const int64_t* blk
   A["order"] = make_arr(order); A["pos"] = make_arr(pos); A["level"] = make_arr(level);
   A["dims64"] = make_arr(dims); A["col_start64"] = make_arr(col_start); A["pstart64"] = make_arr(pstart);
   A["struct_ptr"] = make_arr(struct_ptr); A["struct_idx"] = make_arr(struct_idx);
+  A["chain_of"] = make_arr(chain_of); A["chain_level"] = make_arr(chain_level);
   A["blk_off"] = make_arr(blk_off); A["blk_i"] = make_arr(blk_i); A["blk_j"] = make_arr(blk_j);
   A["blk_rows"] = make_arr(blk_rows); A["blk_cols"] = make_arr(blk_cols); A["up_ptr"] = make_arr(up_ptr);
   // thb_sparse_plan arrays (names == struct fields)
@@ -293,6 +317,7 @@ int thb_symbolic_create(const int64_t* param_size, int64_t N, const int64_t* blk
   S->stats["N"] = (double)N; S->stats["n"] = (double)n; S->stats["data_size"] = (double)data_size; S->stats["winv_size"] = (double)winv_size;
   S->stats["nnz_L"] = (double)data_size; S->stats["flops"] = flops; S->stats["levels"] = (double)nlev;
   S->stats["max_front"] = (double)max_front; S->stats["num_updates"] = (double)up_ptr[nblk];
+  S->stats["num_chains"] = (double)nchains; S->stats["chain_levels"] = (double)chain_levels;
   *out = S;
   return THB_OK;
 }

@@ -75,6 +75,8 @@ class SparsePlan:
     arrays: Dict[str, np.ndarray]
     stats: Dict[str, float]
     lane: Dict[str, np.ndarray] = None   # work lists of the batch-lane kernels (thb_sparse_lane.cu), see _lane_lists
+    chain_of: np.ndarray = None          # [N] fundamental-supernode ("chain") index of every column, see _chains
+    chain_level: np.ndarray = None       # [num_chains] level of the chain in the chain tree
 
 
 _PLAN_KEYS = ("dims", "col_start", "pstart", "winv_off", "diag_off", "up_a", "up_b", "up_k", "u_ptr", "u_tgt", "u_r", "u_c", "u_ld", "u_p0",
@@ -117,7 +119,8 @@ def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering
         sp, si = arr("struct_ptr"), arr("struct_idx")
         blk_off, blk_i, blk_j = arr("blk_off"), arr("blk_i"), arr("blk_j")
         blk_rows, blk_cols = arr("blk_rows"), arr("blk_cols")
-        stats = {k: stat(k) for k in ("nnz_L", "flops", "levels", "max_front", "num_updates")}
+        stats = {k: stat(k) for k in ("nnz_L", "flops", "levels", "max_front", "num_updates", "num_chains", "chain_levels")}
+        chain_of, chain_level = arr("chain_of"), arr("chain_level")
         n, data_size, winv_size = int(stat("n")), int(stat("data_size")), int(stat("winv_size"))
         dims, col_start, pstart = arr("dims64"), arr("col_start64"), arr("pstart64")
     finally:
@@ -126,7 +129,8 @@ def analyze(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering
     blk_index = {(int(i), int(j)): t for t, (i, j) in enumerate(zip(blk_i.tolist(), blk_j.tolist()))}
     return SparsePlan(N=N, n=n, param_size=ps, order=order, pos=pos, dims=dims, col_start=col_start, pstart=pstart, struct=struct, level=level,
                       blk_index=blk_index, blk_off=blk_off, blk_rows=blk_rows, blk_cols=blk_cols, data_size=data_size,
-                      winv_off=arrays["winv_off"], winv_size=winv_size, arrays=arrays, stats=stats, lane=lane)
+                      winv_off=arrays["winv_off"], winv_size=winv_size, arrays=arrays, stats=stats, lane=lane,
+                      chain_of=chain_of, chain_level=chain_level)
 
 
 def analyze_py(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, ordering: str = "mindeg") -> SparsePlan:
@@ -277,15 +281,48 @@ def analyze_py(param_size: np.ndarray, ptrs: np.ndarray, inds: np.ndarray, order
         s_ptr=np.array(s_ptr, dtype=i64), s_col=np.array(s_col, dtype=i32),
         fr_ptr=np.array(fr_ptr, dtype=i64), fr_off=np.array(fr_off, dtype=i64), fr_k=np.array(fr_k, dtype=i32),
         bc_ptr=np.array(bc_ptr, dtype=i64), bc_off=np.array(bc_off, dtype=i64), bc_i=np.array(bc_i, dtype=i32))
+    chain_of, chain_level = _chains(N, struct, parent)
     lane = _lane_lists(N, nlev, cols_by_level, struct, dims, blk_index, blk_off, up_ptr, winv_off, pstart)
     fr_k_arr, bc_i_arr = np.array(fr_k, dtype=np.int64), np.array(bc_i, dtype=np.int64)
     lane.update(fr_p=pstart[fr_k_arr].astype(np.int32), fr_d=dims[fr_k_arr].astype(np.int32),
                 bc_p=pstart[bc_i_arr].astype(np.int32), bc_d=dims[bc_i_arr].astype(np.int32))
     stats = dict(nnz_L=float(data_size), flops=float(flops), levels=float(nlev), max_front=float(max((len(s) + 1 for s in struct), default=0)),
-                 num_updates=float(up_ptr[-1]))
+                 num_updates=float(up_ptr[-1]), num_chains=float(len(chain_level)),
+                 chain_levels=float(chain_level.max() + 1 if len(chain_level) else 0))
     return SparsePlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, col_start=col_start, pstart=pstart,
                       struct=struct, level=level, blk_index=blk_index, blk_off=blk_off, blk_rows=blk_rows, blk_cols=blk_cols,
-                      data_size=data_size, winv_off=winv_off, winv_size=winv_size, arrays=arrays, stats=stats, lane=lane)
+                      data_size=data_size, winv_off=winv_off, winv_size=winv_size, arrays=arrays, stats=stats, lane=lane,
+                      chain_of=chain_of, chain_level=chain_level)
+
+
+def _chains(N, struct, parent):
+    """Fundamental supernodes ("chains"): maximal runs j, j+1, ... with parent(j) = j+1, struct(j) = {j+1} + struct(j+1) and j the only
+    child of j+1.  Returns (chain_of [N]: index of the column's chain, chain_level [num_chains]: level in the chain tree).  Not used by
+    the round-1 kernels; it is the partition the round-2 numeric phase will run on (profiles/r01f_sparse_lane_notes.md)."""
+    nchild = np.zeros(N, dtype=np.int64)
+    for j in range(N):
+        if parent[j] >= 0:
+            nchild[parent[j]] += 1
+    chain_of = np.full(N, -1, dtype=np.int64)
+    nchains = 0
+    for j in range(N):
+        if chain_of[j] >= 0:
+            continue
+        chain_of[j] = nchains
+        k = j
+        while True:
+            p = int(parent[k])
+            if p != k + 1 or nchild[p] != 1 or len(struct[k]) != len(struct[p]) + 1:
+                break
+            chain_of[p] = nchains   # struct(k) = {p} + struct(p) follows from the equal sizes (struct(k) minus {p} is a subset of struct(p))
+            k = p
+        nchains += 1
+    chain_level = np.zeros(nchains, dtype=np.int64)
+    for j in range(N):
+        p = int(parent[j])
+        if p >= 0 and chain_of[p] != chain_of[j]:
+            chain_level[chain_of[p]] = max(chain_level[chain_of[p]], chain_level[chain_of[j]] + 1)
+    return chain_of, chain_level
 
 
 LANE_DIMS = (1, 2, 3, 6)   # block sizes the batch-lane kernels are instantiated for (thb_sparse_lane.cu)
