@@ -5,7 +5,7 @@ including the reference's literal 12x12 system shape (params [2,3,5,2], extlib/t
 import numpy as np
 import pytest
 
-from theseus_b200.sparse import analyze, analyze_py, minimum_degree_order
+from theseus_b200.sparse import analyze, analyze_py, minimum_degree_order, root_split
 
 
 def run_plan_numpy(plan, M, rhs):
@@ -234,6 +234,129 @@ def test_native_symbolic_equals_python_specification(sizes, fill, ordering):
     assert np.array_equal(a.chain_of, b.chain_of) and np.array_equal(a.chain_level, b.chain_level)
     assert all(np.array_equal(x, y) for x, y in zip(a.struct, b.struct))
     assert (a.N, a.n, a.data_size, a.winv_size) == (b.N, b.n, b.data_size, b.winv_size)
+
+
+def run_root_split_numpy(plan, sp, M, rhs):
+    """Interpret sparse.root_split: lane work lists for the columns below the cut, then the dense root (Schur complement assembled from
+    the bottom columns' update pairs, numpy Cholesky standing in for the dense DMMA kernel), substitutions split the same way."""
+    A, Ln = plan.arrays, sp["bottom"]
+    N, dims, cs, cut = plan.N, plan.dims, plan.col_start, sp["cut"]
+    F = np.zeros(plan.data_size)
+    for (i, j), t in plan.blk_index.items():
+        blk = M[cs[i]:cs[i] + dims[i], cs[j]:cs[j] + dims[j]]
+        F[plan.blk_off[t]:plan.blk_off[t] + blk.size] = blk.reshape(-1)
+    DL = np.zeros(plan.winv_size)
+
+    def update(tgt, di, dj, p0, p1):
+        T = F[tgt:tgt + di * dj].reshape(di, dj).copy()
+        for p in range(p0, p1):
+            dk = A["up_k"][p]
+            T -= F[A["up_a"][p]:A["up_a"][p] + di * dk].reshape(di, dk) @ F[A["up_b"][p]:A["up_b"][p] + dj * dk].reshape(dj, dk).T
+        F[tgt:tgt + di * dj] = T.reshape(-1)
+
+    for kind, di, dj, b0, b1 in Ln["launches"]:
+        if kind in (0, 3):
+            for e in range(b0, b1):
+                update(Ln["u_tgt"][e], di, dj, Ln["u_p0"][e], Ln["u_p1"][e])
+        elif kind == 1:
+            writes = {}
+            for e in range(b0, b1):
+                off, dg, dl = Ln["t_off"][e], Ln["t_diag"][e], Ln["t_dl"][e]
+                D = np.tril(F[dg:dg + dj * dj].reshape(dj, dj))
+                L = np.linalg.cholesky(D + np.tril(D, -1).T)
+                if off == dg:
+                    Lr = L.copy(); Lr[np.arange(dj), np.arange(dj)] = 1.0 / np.diag(L); writes[dl] = Lr
+                else:
+                    F[off:off + di * dj] = np.linalg.solve(L, F[off:off + di * dj].reshape(di, dj).T).T.reshape(-1)
+            for dl, Lr in writes.items():
+                DL[dl:dl + Lr.size] = Lr.reshape(-1)
+    # root: assemble, copy to a dense matrix, factor densely
+    blk_dims = {int(plan.blk_off[t]): (int(dims[i]), int(dims[j])) for (i, j), t in plan.blk_index.items()}
+    for e in range(len(sp["ru_tgt"])):
+        di, dj = blk_dims[int(sp["ru_tgt"][e])]
+        update(sp["ru_tgt"][e], di, dj, sp["ru_p0"][e], sp["ru_p1"][e])
+    nt = sp["root_dof"]
+    S = np.zeros((nt, nt))
+    for e in range(len(sp["rb_off"])):
+        di, dj, r0, c0, off = sp["rb_di"][e], sp["rb_dj"][e], sp["rb_row"][e], sp["rb_col"][e], sp["rb_off"][e]
+        S[r0:r0 + di, c0:c0 + dj] = F[off:off + di * dj].reshape(di, dj)
+    S = np.tril(S) + np.tril(S, -1).T
+    Lroot = np.linalg.cholesky(S)
+
+    def diag_solve(j, s, transpose):
+        d = dims[j]
+        Lr = DL[A["winv_off"][j]:A["winv_off"][j] + d * d].reshape(d, d).copy()
+        Lr[np.arange(d), np.arange(d)] = 1.0 / np.diag(Lr)
+        return np.linalg.solve(Lr.T if transpose else Lr, s)
+
+    y = [None] * N
+    S_l = [l for l in Ln["launches"] if l[0] == 2]
+    for _, dj, _, b0, b1 in S_l:
+        for j in Ln["s_col"][b0:b1]:
+            assert j < cut
+            s = rhs[cs[j]:cs[j] + dj].copy()
+            for p in range(A["fr_ptr"][j], A["fr_ptr"][j + 1]):
+                k = A["fr_k"][p]
+                s -= F[A["fr_off"][p]:A["fr_off"][p] + dj * dims[k]].reshape(dj, dims[k]) @ y[k]
+            y[j] = diag_solve(j, s, False)
+    sr = np.zeros(nt)
+    for q, j in enumerate(range(cut, N)):
+        s = rhs[cs[j]:cs[j] + dims[j]].copy()
+        for p in range(sp["rf_p0"][q], sp["rf_p1"][q]):
+            k = A["fr_k"][p]
+            assert k < cut
+            s -= F[A["fr_off"][p]:A["fr_off"][p] + dims[j] * dims[k]].reshape(dims[j], dims[k]) @ y[k]
+        sr[plan.pstart[j] - sp["root_start"]:plan.pstart[j] - sp["root_start"] + dims[j]] = s
+    xr = np.linalg.solve(Lroot.T, np.linalg.solve(Lroot, sr))
+    xs = [None] * N
+    for j in range(cut, N):
+        xs[j] = xr[plan.pstart[j] - sp["root_start"]:plan.pstart[j] - sp["root_start"] + dims[j]]
+    for _, dj, _, b0, b1 in reversed(S_l):
+        for j in Ln["s_col"][b0:b1]:
+            s = y[j].copy()
+            for p in range(A["bc_ptr"][j], A["bc_ptr"][j + 1]):
+                i = A["bc_i"][p]
+                s -= F[A["bc_off"][p]:A["bc_off"][p] + dims[i] * dj].reshape(dims[i], dj).T @ xs[i]
+            xs[j] = diag_solve(j, s, True)
+    x = np.zeros_like(rhs)
+    for j in range(N):
+        x[cs[j]:cs[j] + dims[j]] = xs[j]
+    return x
+
+
+def test_root_split_solves_system():
+    """sparse.root_split (dense trailing block + lane lists below it) on a pose-graph-like structure with a long top chain."""
+    rng = np.random.default_rng(21)
+    N = 40
+    sizes = [6] * N
+    # ring + chords: minimum degree ends with a dense separator chain
+    starts = np.arange(N + 1) * 6
+    rows = []
+    for i in range(N):
+        for jn in ((i + 1) % N, (i + 7) % N):
+            J = np.zeros((3, 6 * N)); J[:, starts[i]:starts[i + 1]] = rng.standard_normal((3, 6)); J[:, starts[jn]:starts[jn + 1]] = rng.standard_normal((3, 6))
+            rows.append(J)
+    Jm = np.concatenate(rows, 0)
+    M = Jm.T @ Jm + np.eye(6 * N)
+    nbr = [set([i]) for i in range(N)]
+    for i in range(N):
+        for jn in ((i + 1) % N, (i + 7) % N):
+            nbr[i].add(jn); nbr[jn].add(i)
+    ptrs, inds = [0], []
+    for i in range(N):
+        inds += sorted(nbr[i]); ptrs.append(len(inds))
+    plan = analyze(np.array(sizes), np.array(ptrs), np.array(inds))
+    sp = root_split(plan, max_root_dof=1024, min_root_cols=4)
+    assert sp is not None and 4 <= N - sp["cut"] and sp["root_dof"] == 6 * (N - sp["cut"])
+    assert len(sp["ru_tgt"]) > 0 and (sp["pair_k"][sp["ru_p0"][0]:sp["ru_p1"][0]] < sp["cut"]).all()
+    rhs = rng.standard_normal(6 * N)
+    x = run_root_split_numpy(plan, sp, M, rhs)
+    assert np.abs(M @ x - rhs).max() < 1e-9
+    # smaller root on request; no root when the tail is too short
+    sp2 = root_split(plan, max_root_dof=24, min_root_cols=4)
+    assert sp2 is not None and sp2["root_dof"] == 24
+    assert np.abs(M @ run_root_split_numpy(plan, sp2, M, rhs) - rhs).max() < 1e-9
+    assert root_split(plan, max_root_dof=12, min_root_cols=4) is None
 
 
 def test_chains_are_fundamental_supernodes():

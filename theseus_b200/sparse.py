@@ -383,3 +383,79 @@ def gram_out_offsets(plan: SparsePlan):
         t = plan.blk_index[(int(plan.pos[a]), int(plan.pos[b]))]
         return int(plan.blk_off[t]), int(plan.blk_cols[t]), -1
     return f
+
+
+def root_split(plan: SparsePlan, max_root_dof: int = 1024, min_root_cols: int = 8):
+    """Round-2 building block (host side, CPU-tested; no kernel consumes it yet -- see profiles/r01f_sparse_lane_notes.md).
+
+    The top of the elimination tree is a long chain whose columns form a DENSE trailing block (C5: the last 64 columns, 384 dof):
+    ~200 serial one-column levels for the lane kernels, a < 1 ms job for the dense DMMA Cholesky.  This splits a plan at `cut`:
+      * bottom: columns < cut with the usual per-level lane work lists (their blocks in root ROWS are ordinary blocks of those columns),
+      * root assembly: for every root block (i, j), i >= j >= cut, the update pairs that come from bottom columns (k < cut: a prefix
+        of the block's pair list) -> S = A_root - sum_k L_ik L_jk^T, copied into a dense [B, nt, nt] matrix and factored there,
+      * root substitution: per root column the blocks L_jk, k < cut, to fold the bottom part of y into the dense right-hand side.
+    Returns None if the plan has no useful dense root, else a dict of arrays."""
+    N, dims, pstart = plan.N, plan.dims, plan.pstart
+    if N == 0:
+        return None
+    last = plan.chain_of[N - 1]
+    cut = int(np.argmax(plan.chain_of == last))
+    while int(dims[cut:].sum()) > max_root_dof:
+        cut += 1
+    if N - cut < min_root_cols:
+        return None
+    for j in range(cut, N):
+        assert np.array_equal(plan.struct[j], np.arange(j + 1, N)), "the root must be a dense trailing block"
+    A = plan.arrays
+    nblk = len(plan.blk_off)
+    blk_j = np.empty(nblk, dtype=np.int64)
+    blk_i = np.empty(nblk, dtype=np.int64)
+    for (i, j), t in plan.blk_index.items():
+        blk_i[t], blk_j[t] = i, j
+    # source column of every update pair (pairs of a block are stored in increasing k)
+    up_ptr = np.zeros(nblk + 1, dtype=np.int64)
+    # rebuild up_ptr from the U items of both back ends is awkward; recompute it from the structure instead
+    counts = np.zeros(nblk, dtype=np.int64)
+    for k in range(N):
+        s_ = plan.struct[k]
+        for bi in range(len(s_)):
+            for ai in range(bi, len(s_)):
+                counts[plan.blk_index[(int(s_[ai]), int(s_[bi]))]] += 1
+    up_ptr[1:] = np.cumsum(counts)
+    src_blk = np.searchsorted(plan.blk_off, A["up_a"], side="right") - 1
+    pair_k = blk_j[src_blk]
+    level_cut = int(plan.level[cut])
+    assert all(int(plan.level[j]) < level_cut for j in range(cut)) and all(int(plan.level[j]) >= level_cut for j in range(cut, N))
+    nlev_bottom = level_cut
+    cols_by_level = [[] for _ in range(nlev_bottom)]
+    for j in range(cut):
+        cols_by_level[int(plan.level[j])].append(j)
+    bottom = _lane_lists(N, nlev_bottom, cols_by_level, plan.struct, dims, plan.blk_index, plan.blk_off, up_ptr, plan.winv_off, pstart)
+    # root assembly: (target offset, first pair, one-past-last pair with k < cut), dense placement of every root block
+    ru_tgt, ru_p0, ru_p1, rb_off, rb_row, rb_col, rb_di, rb_dj = [], [], [], [], [], [], [], []
+    root0 = int(pstart[cut])
+    for j in range(cut, N):
+        for i in range(j, N):
+            t = plan.blk_index[(i, j)]
+            p0, p1 = int(up_ptr[t]), int(up_ptr[t + 1])
+            n_bottom = int(np.searchsorted(pair_k[p0:p1], cut, side="left"))
+            assert (pair_k[p0:p0 + n_bottom] < cut).all() and (pair_k[p0 + n_bottom:p1] >= cut).all()
+            if n_bottom > 0:
+                ru_tgt.append(int(plan.blk_off[t])); ru_p0.append(p0); ru_p1.append(p0 + n_bottom)
+            rb_off.append(int(plan.blk_off[t])); rb_row.append(int(pstart[i]) - root0); rb_col.append(int(pstart[j]) - root0)
+            rb_di.append(int(dims[i])); rb_dj.append(int(dims[j]))
+    # root substitution: per root column the prefix of its row list that lies in bottom columns
+    rf_p0, rf_p1 = [], []
+    for j in range(cut, N):
+        p0, p1 = int(A["fr_ptr"][j]), int(A["fr_ptr"][j + 1])
+        ks = A["fr_k"][p0:p1]
+        n_bottom = int(np.searchsorted(ks, cut, side="left"))
+        assert (ks[:n_bottom] < cut).all() and (ks[n_bottom:] >= cut).all()
+        rf_p0.append(p0); rf_p1.append(p0 + n_bottom)
+    i64 = np.int64
+    return dict(cut=cut, root_dof=int(dims[cut:].sum()), root_start=root0, bottom=bottom, up_ptr=up_ptr, pair_k=pair_k,
+                ru_tgt=np.array(ru_tgt, dtype=i64), ru_p0=np.array(ru_p0, dtype=i64), ru_p1=np.array(ru_p1, dtype=i64),
+                rb_off=np.array(rb_off, dtype=i64), rb_row=np.array(rb_row, dtype=np.int32), rb_col=np.array(rb_col, dtype=np.int32),
+                rb_di=np.array(rb_di, dtype=np.int32), rb_dj=np.array(rb_dj, dtype=np.int32),
+                rf_p0=np.array(rf_p0, dtype=i64), rf_p1=np.array(rf_p1, dtype=i64))
+
