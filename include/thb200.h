@@ -312,6 +312,36 @@ int thb_sparse_lane_damp_f64(const thb_sparse_lane_plan* p, double* factor, cons
 /* info[b] = 0 or 1 + permuted index of a non-positive pivot */
 int thb_sparse_lane_factor_f64(const thb_sparse_lane_plan* p, double* factor, double* diagl, int32_t* info, int64_t B,
                                thb_stream_t stream);
+/* Dense root of the elimination tree (sparse.py:root_split; opt-in `layout="lane_root"` of the Python solver, new in round 1 and
+ * not yet profiled): the top chain of the tree is a dense trailing block [nt, nt]; the lane kernels run on the columns below the
+ * cut (a thb_sparse_lane_plan whose launch list stops there and ends with the root's assembly updates), the root itself goes
+ * through thb_potrf_f64 / thb_potrs_f64.  All pointers device arrays except `segments` (HOST, [num_segments,3] = block size, begin,
+ * end into root_cols). */
+typedef struct thb_sparse_lane_root {
+  int64_t num_blocks;   /* blocks (i, j), i >= j >= cut, of the root */
+  int64_t num_cols;     /* root columns */
+  int64_t nt;           /* scalar size of the root */
+  int64_t root_start;   /* first permuted scalar index of the root */
+  int64_t num_segments;
+  const int32_t* segments;  /* HOST */
+  const int64_t* rb_off; const int32_t* rb_row; const int32_t* rb_col; const int32_t* rb_di; const int32_t* rb_dj; /* [num_blocks] */
+  const int64_t* rf_p0; const int64_t* rf_p1;  /* [num_cols] bottom part of each root column's row list (indices into fr_*) */
+  const int32_t* root_cols;                    /* [num_cols] elimination positions, grouped by block size (see segments) */
+  const int32_t* root_dims;                    /* [num_cols] block sizes */
+} thb_sparse_lane_root;
+/* S [B, nt, nt] (batch-major, row-major; lower triangle = the assembled root, strict upper = 0) <- lane factor storage */
+int thb_sparse_lane_root_gather_f64(const thb_sparse_lane_root* r, const double* factor, double* S, int64_t B, thb_stream_t stream);
+/* forward / backward substitution of the columns in the plan's launch list only (thb_sparse_lane_solve_f64 = forward then backward) */
+int thb_sparse_lane_forward_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs, double* work,
+                                int64_t B, thb_stream_t stream);
+int thb_sparse_lane_backward_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, double* work, double* x, int64_t B,
+                                 thb_stream_t stream);
+/* rhs_dense [B, nt] = permuted rhs of the root minus the contribution of the bottom columns (after thb_sparse_lane_forward_f64) */
+int thb_sparse_lane_root_rhs_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_root* r, const double* factor, const double* rhs,
+                                 const double* work, double* rhs_dense, int64_t B, thb_stream_t stream);
+/* root solution x_dense [B, nt] -> work (for thb_sparse_lane_backward_f64) and x [B, n] (original order) */
+int thb_sparse_lane_root_scatter_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_root* r, const double* x_dense, double* work, double* x,
+                                     int64_t B, thb_stream_t stream);
 /* rhs, x: [B, n] row-major in the ORIGINAL variable order (scramble / unscramble folded into the substitutions) */
 int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs,
                               double* x, double* work, int64_t B, thb_stream_t stream);

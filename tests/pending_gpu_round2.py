@@ -1,5 +1,5 @@
 """NOT COLLECTED (no test_ prefix in the file name) -- written at the end of round 1 when the GPU budget was spent; run it first thing
-in round 2 (`python -m pytest tests/pending_gpu_tactile.py -m gpu`) and rename to test_gpu_tactile.py once green.
+in round 2 (`python -m pytest tests/pending_gpu_round2.py -m gpu`) and rename to test_gpu_tactile.py once green.
 
 Config C4's cost set (planar pushing / tactile pose estimation: QuasiStaticPushingPlanar, EffectorObjectContactPlanar,
 MovingFrameBetween, SE2 priors) through the GPU engine: LM trace and implicit-mode gradients against the reference
@@ -59,7 +59,7 @@ def test_tactile_implicit_gradients():
         assert np.abs(v.tensor.grad.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), k
 
 
-@pytest.mark.parametrize("layout", ["item", "lane"])
+@pytest.mark.parametrize("layout", ["item", "lane", "lane_root"])
 def test_c5_full_size_sparse_lm_trace(layout):
     """Config C5's pose graph at full size (2 500 poses, n = 15 000), one batch item: the block-sparse solver's LM trace against the
     reference's dense-solver trace (tests/golden/pgo_c5_lm.npz, generated on the CPU by make_golden.py c5).  Same parked status."""
@@ -81,3 +81,34 @@ def test_c5_full_size_sparse_lm_trace(layout):
     for it in range(decisive_iterations(g["err0"], g["trace_err"])):
         rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
         assert rel.max() < 1e-5, (it, rel)
+
+
+def test_lane_root_layout_matches_lane_layout():
+    """Opt-in layout='lane_root' (dense DMMA factorisation of the top chain of the elimination tree, sparse.root_split) against the plain
+    lane layout and the dense residual, on a ring-with-chords structure whose minimum-degree order ends in a dense separator chain.
+    The host half (work lists) is verified on the CPU: tests/test_sparse_symbolic.py::test_root_split_solves_system."""
+    from theseus_b200.structure import build_structure
+    from test_gpu_sparse_solver import _dense_system
+    rng = np.random.default_rng(5)
+    N, B = 60, 70
+    costs = [(3, [i, (i + 1) % N]) for i in range(N)] + [(3, [i, (i + 7) % N]) for i in range(N)] + [(6, [i]) for i in range(N)]
+    costs = [(d, sorted(vs)) for d, vs in costs]
+    S = build_structure([6] * N, costs)
+    A_val = torch.from_numpy(rng.standard_normal((B, S.nnz))).cuda()
+    b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
+    alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
+    xs = {}
+    for layout in ("lane_root", "lane"):
+        solver = th.BaspachoSparseSolver.from_structure(S, layout=layout)
+        solver.linearization.A_val, solver.linearization.b = A_val, b
+        xs[layout] = (solver.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-6).cpu().numpy(), solver.solve().cpu().numpy())
+        if layout == "lane_root":
+            assert solver._root is not None and solver._dev["nt"] >= 48
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    for k, (mul, add) in enumerate(((1 + alpha.cpu().numpy()[:, None], 1e-6), (1.0, 0.0))):
+        M = AtA.copy()
+        M[:, idx, idx] = M[:, idx, idx] * mul + add
+        res = np.einsum("bij,bj->bi", M, xs["lane_root"][k]) - Atb
+        assert np.abs(res).max() < 1e-10 * np.abs(M).sum(axis=2).max() * max(1.0, np.abs(xs["lane_root"][k]).max())
+        assert np.abs(xs["lane_root"][k] - xs["lane"][k]).max() < 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(xs["lane"][k]).max())

@@ -67,6 +67,14 @@ class SparseLanePlanStruct(C.Structure):
 _PG, _PV, _PP = C.POINTER(CostGroup), C.POINTER(VarTable), C.POINTER(GramPlan)
 _PS = C.POINTER(SparsePlanStruct)
 _PL = C.POINTER(SparseLanePlanStruct)
+
+
+class SparseLaneRootStruct(C.Structure):
+    _fields_ = [("num_blocks", c_i64), ("num_cols", c_i64), ("nt", c_i64), ("root_start", c_i64), ("num_segments", c_i64)] + [(k, c_vp) for k in (
+        "segments", "rb_off", "rb_row", "rb_col", "rb_di", "rb_dj", "rf_p0", "rf_p1", "root_cols", "root_dims")]
+
+
+_PR = C.POINTER(SparseLaneRootStruct)
 SIGNATURES = {
     "thb_version": (c_i32, []),
     "thb_compiled_arch": (c_i32, []),
@@ -103,6 +111,11 @@ SIGNATURES = {
     "thb_sparse_lane_damp_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_factor_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_solve_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_forward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_backward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_root_gather_f64": (c_i32, [_PR, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_root_rhs_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_root_scatter_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_solve_backward_f64": (c_i32, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "thb_lm_control_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_vp, c_vp, c_vp, c_i32, c_f64, c_f64, c_f64,
                                    c_vp, c_vp, c_vp, c_vp]),

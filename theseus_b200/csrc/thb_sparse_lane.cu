@@ -352,6 +352,82 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 1) lane_backward_kernel(LaneSol
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Dense root (sparse.py:root_split): the top chain of the elimination tree is a dense trailing block; it is copied out of the
+// lane-interleaved storage into a batch-major dense matrix, factored / solved by the dense DMMA kernels (thb_potrf_f64 /
+// thb_potrs_f64), and its part of the solution copied back.
+struct LaneRootArgs {
+  const int64_t* rb_off; const int32_t* rb_row; const int32_t* rb_col; const int32_t* rb_di; const int32_t* rb_dj;  // root blocks
+  int64_t num_blocks;
+  const int64_t* rf_p0; const int64_t* rf_p1;       // per root column: range of its row-list entries that lie in bottom columns
+  const int32_t* root_cols;                         // [num_cols] elimination positions of the root columns (grouped by block size)
+  const int32_t* root_dims;                         // [num_cols] their block sizes
+  int64_t num_cols, nt, root_start;
+};
+
+// S[b, r0+r, c0+c] = factor[(off + r*dj + c)*Bp + b]; one thread per (batch item, block element), lanes over b (coalesced reads)
+__global__ void __launch_bounds__(256) lane_root_gather_kernel(LaneRootArgs r, const double* __restrict__ F, double* __restrict__ S, int64_t B,
+                                                               int64_t Bp) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t q = t / Bp, b = t - q * Bp;  // q = blk * 36 + e  (blocks are at most 6x6)
+  const int64_t blk = q / 36;
+  const int e = (int)(q - blk * 36);
+  if (blk >= r.num_blocks || b >= B) return;
+  const int di = r.rb_di[blk], dj = r.rb_dj[blk];
+  if (e >= di * dj) return;
+  const int rr = e / dj, cc = e - rr * dj;
+  S[b * r.nt * r.nt + (int64_t)(r.rb_row[blk] + rr) * r.nt + r.rb_col[blk] + cc] = F[(r.rb_off[blk] + e) * Bp + b];
+}
+
+// rhs_dense[b, pstart_j - root_start + r] = rhs[b, col_start_j + r] - sum over the bottom part of row j's list of L_jk y_k
+template <int DJ>
+__global__ void __launch_bounds__(32 * LS_WARPS, 1) lane_root_rhs_kernel(LaneSolveArgs p, LaneRootArgs r, const double* F, const double* __restrict__ rhs,
+                                                                         const double* Y, double* __restrict__ rhs_dense) {
+  __shared__ double red[(LS_WARPS - 1) * DJ * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int item = p.begin + (blockIdx.x / p.nbx);
+  const bool live = b < p.B;
+  const int j = r.root_cols[item];
+  const double* Fb = F + (live ? b : 0);
+  const double* Yb = Y + (live ? b : 0);
+  double s[DJ];
+#pragma unroll
+  for (int q = 0; q < DJ; q++) s[q] = 0.0;
+  if (live) {
+    const int64_t q1 = r.rf_p1[item];
+    for (int64_t q = r.rf_p0[item] + warp; q < q1; q += LS_WARPS) {
+      const int dk = p.fr_d[q], pk = p.fr_p[q];
+      const int64_t off = p.fr_off[q];
+      if (dk == 6) blk_mv<DJ, 6>(s, Fb, off, Yb, pk, p.Bp);
+      else if (dk == 3) blk_mv<DJ, 3>(s, Fb, off, Yb, pk, p.Bp);
+      else if (dk == 2) blk_mv<DJ, 2>(s, Fb, off, Yb, pk, p.Bp);
+      else blk_mv<DJ, 1>(s, Fb, off, Yb, pk, p.Bp);
+    }
+  }
+  reduce_to_warp0<DJ>(s, red, warp, lane);
+  if (warp != 0 || !live) return;
+  const int64_t e0 = p.pstart[j] - r.root_start;
+#pragma unroll
+  for (int q = 0; q < DJ; q++) rhs_dense[b * r.nt + e0 + q] = s[q] + rhs[b * p.n + p.col_start[j] + q];
+}
+
+// x of the root: dense [B, nt] -> permuted lane vector (for the bottom columns' backward substitution) and the caller's x (unscrambled)
+__global__ void __launch_bounds__(256) lane_root_scatter_kernel(LaneSolveArgs p, LaneRootArgs r, const double* __restrict__ x_dense, double* __restrict__ Y,
+                                                                double* __restrict__ x) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t q = t / p.Bp, b = t - q * p.Bp;  // q = column slot * 6 + component
+  const int64_t c = q / 6;
+  const int comp = (int)(q - c * 6);
+  if (c >= r.num_cols || b >= p.B) return;
+  const int j = r.root_cols[c];
+  const int64_t e0 = p.pstart[j] - r.root_start;
+  if (comp >= r.root_dims[c]) return;
+  const double v = x_dense[b * r.nt + e0 + comp];
+  Y[(int64_t)(p.pstart[j] + comp) * p.Bp + b] = v;
+  x[b * p.n + p.col_start[j] + comp] = v;
+}
+
 __global__ void __launch_bounds__(256) lane_damp_kernel(thb_sparse_lane_plan p, double* __restrict__ F, const double* __restrict__ alpha,
                                                         const double* __restrict__ beta, int64_t B, int64_t Bp) {
   // diag <- diag * (1 + alpha_b) + beta_b   (extlib/baspacho_solver.cpp:181-183, baspacho_solver_cuda.cu:171-185)
@@ -482,17 +558,26 @@ int thb_sparse_lane_factor_f64(const thb_sparse_lane_plan* p, double* factor, do
   return THB_OK;
 }
 
-int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs, double* x,
-                              double* work, int64_t B, thb_stream_t s) {
-  if (p == nullptr || factor == nullptr || diagl == nullptr || rhs == nullptr || x == nullptr || work == nullptr || B < 0) return THB_ERR_BAD_ARG;
-  if (B == 0 || p->N == 0) return THB_OK;
-  cudaStream_t cs = thb_cs(s);
+static thb::LaneSolveArgs lane_solve_args(const thb_sparse_lane_plan* p, int64_t B) {
   thb::LaneSolveArgs a;
   a.s_col = p->s_col; a.pstart = p->pstart; a.col_start = p->col_start; a.dl_off = p->dl_off;
   a.fr_ptr = p->fr_ptr; a.fr_off = p->fr_off; a.fr_p = p->fr_p; a.fr_d = p->fr_d;
   a.bc_ptr = p->bc_ptr; a.bc_off = p->bc_off; a.bc_p = p->bc_p; a.bc_d = p->bc_d;
+  a.begin = a.end = 0;
   a.B = B; a.Bp = thb_sparse_lane_padded_batch(B); a.nbx = (int)(a.Bp / 32); a.n = p->n;
+  return a;
+}
+
+// passes: bit 0 = forward substitution, bit 1 = backward substitution (thb_sparse_lane_solve_f64 = both)
+static int lane_solve_passes(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs, double* x, double* work,
+                             int64_t B, int passes, thb_stream_t s) {
+  if (p == nullptr || factor == nullptr || diagl == nullptr || work == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (((passes & 1) && rhs == nullptr) || ((passes & 2) && x == nullptr)) return THB_ERR_BAD_ARG;
+  if (B == 0 || p->N == 0) return THB_OK;
+  cudaStream_t cs = thb_cs(s);
+  thb::LaneSolveArgs a = lane_solve_args(p, B);
   for (int pass = 0; pass < 2; pass++) {
+    if (!(passes & (1 << pass))) continue;
     for (int64_t q = 0; q < p->num_launches; q++) {
       const int64_t l = pass == 0 ? q : p->num_launches - 1 - q;
       const int32_t* L = p->launches + 5 * l;
@@ -512,6 +597,70 @@ int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* facto
       THB_CHECK_LAUNCH();
     }
   }
+  return THB_OK;
+}
+
+int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs, double* x,
+                              double* work, int64_t B, thb_stream_t s) {
+  return lane_solve_passes(p, factor, diagl, rhs, x, work, B, 3, s);
+}
+int thb_sparse_lane_forward_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs, double* work,
+                                int64_t B, thb_stream_t s) {
+  return lane_solve_passes(p, factor, diagl, rhs, nullptr, work, B, 1, s);
+}
+int thb_sparse_lane_backward_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, double* work, double* x, int64_t B,
+                                 thb_stream_t s) {
+  return lane_solve_passes(p, factor, diagl, nullptr, x, work, B, 2, s);
+}
+
+static thb::LaneRootArgs lane_root_args(const thb_sparse_lane_root* r) {
+  thb::LaneRootArgs a;
+  a.rb_off = r->rb_off; a.rb_row = r->rb_row; a.rb_col = r->rb_col; a.rb_di = r->rb_di; a.rb_dj = r->rb_dj; a.num_blocks = r->num_blocks;
+  a.rf_p0 = r->rf_p0; a.rf_p1 = r->rf_p1; a.root_cols = r->root_cols; a.root_dims = r->root_dims; a.num_cols = r->num_cols; a.nt = r->nt; a.root_start = r->root_start;
+  return a;
+}
+
+int thb_sparse_lane_root_gather_f64(const thb_sparse_lane_root* r, const double* factor, double* S, int64_t B, thb_stream_t s) {
+  if (r == nullptr || factor == nullptr || S == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (B == 0 || r->num_blocks == 0) return THB_OK;
+  cudaStream_t cs = thb_cs(s);
+  const int64_t Bp = thb_sparse_lane_padded_batch(B);
+  THB_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)(B * r->nt * r->nt), cs));  // the strict upper triangle stays zero
+  const int64_t total = r->num_blocks * 36 * Bp;
+  thb::lane_root_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(lane_root_args(r), factor, S, B, Bp);
+  THB_CHECK_LAUNCH();
+  return THB_OK;
+}
+
+int thb_sparse_lane_root_rhs_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_root* r, const double* factor, const double* rhs,
+                                 const double* work, double* rhs_dense, int64_t B, thb_stream_t s) {
+  if (p == nullptr || r == nullptr || factor == nullptr || rhs == nullptr || work == nullptr || rhs_dense == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (B == 0 || r->num_cols == 0) return THB_OK;
+  cudaStream_t cs = thb_cs(s);
+  thb::LaneSolveArgs a = lane_solve_args(p, B);
+  const thb::LaneRootArgs ra = lane_root_args(r);
+  // root columns grouped by block size on the host: seg [3*q] = dim, [3*q+1] = begin, [3*q+2] = end (indices into root_cols)
+  for (int64_t q = 0; q < r->num_segments; q++) {
+    const int dj = r->segments[3 * q];
+    a.begin = r->segments[3 * q + 1]; a.end = r->segments[3 * q + 2];
+    const int items = a.end - a.begin;
+    if (items <= 0) continue;
+    const unsigned grid_w = (unsigned)(items * a.nbx);
+#define CALL_RR(DJ) thb::lane_root_rhs_kernel<DJ><<<grid_w, 32 * thb::LS_WARPS, 0, cs>>>(a, ra, factor, rhs, work, rhs_dense)
+    LN_SWITCH1(dj, CALL_RR)
+    THB_CHECK_LAUNCH();
+  }
+  return THB_OK;
+}
+
+int thb_sparse_lane_root_scatter_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_root* r, const double* x_dense, double* work, double* x,
+                                     int64_t B, thb_stream_t s) {
+  if (p == nullptr || r == nullptr || x_dense == nullptr || work == nullptr || x == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (B == 0 || r->num_cols == 0) return THB_OK;
+  thb::LaneSolveArgs a = lane_solve_args(p, B);
+  const int64_t total = r->num_cols * 6 * a.Bp;
+  thb::lane_root_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, thb_cs(s)>>>(a, lane_root_args(r), x_dense, work, x);
+  THB_CHECK_LAUNCH();
   return THB_OK;
 }
 

@@ -459,3 +459,40 @@ def root_split(plan: SparsePlan, max_root_dof: int = 1024, min_root_cols: int = 
                 rb_di=np.array(rb_di, dtype=np.int32), rb_dj=np.array(rb_dj, dtype=np.int32),
                 rf_p0=np.array(rf_p0, dtype=i64), rf_p1=np.array(rf_p1, dtype=i64))
 
+
+def root_lane_lists(plan: SparsePlan, sp) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
+    """Work lists of the opt-in `lane_root` layout from a root_split: (lane lists = the bottom columns' lists followed by the root's
+    assembly updates, grouped by block shape like every U launch; root arrays for thb_sparse_lane_root)."""
+    bottom = sp["bottom"]
+    u_tgt, u_p0, u_p1 = list(bottom["u_tgt"]), list(bottom["u_p0"]), list(bottom["u_p1"])
+    launches = [tuple(int(x) for x in row) for row in bottom["launches"]]
+    shape_of = {int(o): (int(a), int(b)) for o, a, b in zip(sp["rb_off"], sp["rb_di"], sp["rb_dj"])}
+    cls: Dict[Tuple[int, int, int], list] = {}
+    for e in range(len(sp["ru_tgt"])):
+        di, dj = shape_of[int(sp["ru_tgt"][e])]
+        heavy = 1 if int(sp["ru_p1"][e] - sp["ru_p0"][e]) >= LANE_HEAVY else 0
+        cls.setdefault((heavy, di, dj), []).append(e)
+    for (heavy, di, dj) in sorted(cls):
+        b0 = len(u_tgt)
+        for e in cls[(heavy, di, dj)]:
+            u_tgt.append(int(sp["ru_tgt"][e])); u_p0.append(int(sp["ru_p0"][e])); u_p1.append(int(sp["ru_p1"][e]))
+        launches.append((LN_UH if heavy else LN_U, di, dj, b0, len(u_tgt)))
+    i64 = np.int64
+    lane = dict(bottom)
+    lane.update(u_tgt=np.array(u_tgt, dtype=i64), u_p0=np.array(u_p0, dtype=i64), u_p1=np.array(u_p1, dtype=i64),
+                launches=np.array(launches, dtype=np.int32).reshape(-1, 5),
+                fr_p=plan.lane["fr_p"], fr_d=plan.lane["fr_d"], bc_p=plan.lane["bc_p"], bc_d=plan.lane["bc_d"])
+    cut = sp["cut"]
+    root_cols = np.arange(cut, plan.N, dtype=np.int32)
+    order = np.argsort(plan.dims[cut:], kind="stable")          # root columns grouped by block size for the rhs kernel
+    cols_sorted = root_cols[order]
+    segs, b0 = [], 0
+    ds = plan.dims[cut:][order]
+    for q in range(1, len(ds) + 1):
+        if q == len(ds) or ds[q] != ds[b0]:
+            segs.append((int(ds[b0]), b0, q)); b0 = q
+    root = dict(rb_off=sp["rb_off"], rb_row=sp["rb_row"], rb_col=sp["rb_col"], rb_di=sp["rb_di"], rb_dj=sp["rb_dj"],
+                rf_p0=sp["rf_p0"][order], rf_p1=sp["rf_p1"][order], root_cols=cols_sorted.astype(np.int32), root_dims=ds.astype(np.int32),
+                segments=np.array(segs, dtype=np.int32).reshape(-1, 3), nt=sp["root_dof"], root_start=sp["root_start"])
+    return lane, root
+

@@ -16,7 +16,7 @@ from . import _lib
 from .autograd import LinearSolveFunction, wants_grad
 from .core import Objective
 from .optimizer import (Linearization, LinearSolver, SparseLinearization, convert_to_alpha_beta_damping_tensors)
-from .sparse import LANE_DIMS, analyze, gram_out_offsets
+from .sparse import LANE_DIMS, analyze, gram_out_offsets, root_lane_lists, root_split
 from .structure import ata_block_structure, build_gram_plan
 
 
@@ -70,12 +70,22 @@ class BaspachoSparseSolver(LinearSolver):
         thb_sparse.cu).  Default: lane whenever a warp can be filled and every block size is one the lane kernels are built for."""
         lane_ok = all(int(d) in LANE_DIMS for d in self._plan.dims)
         if self._layout is not None:
-            if self._layout not in ("lane", "item"):
-                raise ValueError(f"layout must be 'lane' or 'item', got {self._layout}")
-            if self._layout == "lane" and not lane_ok:
-                raise ValueError(f"layout='lane' needs block sizes in {LANE_DIMS}")
+            if self._layout not in ("lane", "item", "lane_root"):
+                raise ValueError(f"layout must be 'lane', 'item' or 'lane_root', got {self._layout}")
+            if self._layout != "item" and not lane_ok:
+                raise ValueError(f"layout='{self._layout}' needs block sizes in {LANE_DIMS}")
+            if self._layout == "lane_root" and self._root_split() is None:
+                raise ValueError("layout='lane_root': this structure has no dense root (top chain too short)")
             return self._layout
         return "lane" if (lane_ok and B >= 32) else "item"
+
+    def _root_split(self):
+        """Dense-root split of the plan (sparse.root_split), computed on first use.  Opt-in layout 'lane_root': the lane kernels
+        below the cut, the dense DMMA Cholesky for the root -- written at the end of round 1, not yet timed on a GPU."""
+        if not hasattr(self, "_root"):
+            sp = root_split(self._plan)
+            self._root = None if sp is None else (sp,) + root_lane_lists(self._plan, sp)
+        return self._root
 
     @property
     def symbolic_stats(self):
@@ -107,6 +117,28 @@ class BaspachoSparseSolver(LinearSolver):
             fr_ptr=dev["fr_ptr"].data_ptr(), fr_off=dev["fr_off"].data_ptr(), fr_p=ldev["fr_p"].data_ptr(), fr_d=ldev["fr_d"].data_ptr(),
             bc_ptr=dev["bc_ptr"].data_ptr(), bc_off=dev["bc_off"].data_ptr(), bc_p=ldev["bc_p"].data_ptr(), bc_d=ldev["bc_d"].data_ptr())
         self._dev = dict(device=device, plan=st, keep=dev, gram=gst, gkeep=gdev, bufs={}, lane=lst, lkeep=(ldev, launches))
+        if self._layout == "lane_root":
+            sp, rl, rr = self._root_split()
+            rdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in rl.items() if k != "launches"}
+            rlaunch = np.ascontiguousarray(rl["launches"], dtype=np.int32)
+            rst = _lib.SparseLanePlanStruct(
+                N=P.N, n=P.n, data_size=P.data_size, diag_size=P.winv_size, num_launches=int(rlaunch.shape[0]),
+                launches=rlaunch.ctypes.data, dims=dev["dims"].data_ptr(), col_start=dev["col_start"].data_ptr(),
+                pstart=dev["pstart"].data_ptr(), dl_off=dev["winv_off"].data_ptr(), diag_off=dev["diag_off"].data_ptr(),
+                up_a=dev["up_a"].data_ptr(), up_b=dev["up_b"].data_ptr(), up_k=dev["up_k"].data_ptr(),
+                u_tgt=rdev["u_tgt"].data_ptr(), u_p0=rdev["u_p0"].data_ptr(), u_p1=rdev["u_p1"].data_ptr(),
+                t_off=rdev["t_off"].data_ptr(), t_diag=rdev["t_diag"].data_ptr(), t_dl=rdev["t_dl"].data_ptr(),
+                t_pstart=rdev["t_pstart"].data_ptr(), s_col=rdev["s_col"].data_ptr(),
+                fr_ptr=dev["fr_ptr"].data_ptr(), fr_off=dev["fr_off"].data_ptr(), fr_p=rdev["fr_p"].data_ptr(), fr_d=rdev["fr_d"].data_ptr(),
+                bc_ptr=dev["bc_ptr"].data_ptr(), bc_off=dev["bc_off"].data_ptr(), bc_p=rdev["bc_p"].data_ptr(), bc_d=rdev["bc_d"].data_ptr())
+            qdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in rr.items() if isinstance(v, np.ndarray) and k != "segments"}
+            segs = np.ascontiguousarray(rr["segments"], dtype=np.int32)
+            qst = _lib.SparseLaneRootStruct(
+                num_blocks=int(rr["rb_off"].shape[0]), num_cols=int(rr["root_cols"].shape[0]), nt=int(rr["nt"]), root_start=int(rr["root_start"]),
+                num_segments=int(segs.shape[0]), segments=segs.ctypes.data, rb_off=qdev["rb_off"].data_ptr(), rb_row=qdev["rb_row"].data_ptr(),
+                rb_col=qdev["rb_col"].data_ptr(), rb_di=qdev["rb_di"].data_ptr(), rb_dj=qdev["rb_dj"].data_ptr(), rf_p0=qdev["rf_p0"].data_ptr(),
+                rf_p1=qdev["rf_p1"].data_ptr(), root_cols=qdev["root_cols"].data_ptr(), root_dims=qdev["root_dims"].data_ptr())
+            self._dev.update(lane_root=rst, root=qst, rkeep=(rdev, rlaunch, qdev, segs), nt=int(rr["nt"]))
         return self._dev
 
     # ---- numeric phase (baspacho_sparse_autograd.py:21-65) ----
@@ -159,24 +191,38 @@ class BaspachoSparseSolver(LinearSolver):
         key = (B, layout)
         if d["bufs"].get("key") != key:
             Bp = int(lib.thb_sparse_lane_padded_batch(B))
-            shape = (lambda k: (k, Bp)) if layout == "lane" else (lambda k: (B, k))
+            shape = (lambda k: (k, Bp)) if layout != "item" else (lambda k: (B, k))
             d["bufs"] = dict(key=key, factor=torch.empty(shape(P.data_size), dtype=torch.float64, device=device),
                              diag=torch.empty(shape(P.winv_size), dtype=torch.float64, device=device),   # W_j = L_jj^-1 (item) / L_jj with reciprocal diagonal (lane)
                              work=torch.empty(shape(P.n), dtype=torch.float64, device=device),
                              Atb=torch.empty(B, P.n, dtype=torch.float64, device=device),
                              info=torch.empty(B, dtype=torch.int32, device=device))
+            if layout == "lane_root":
+                nt = d["nt"]
+                d["bufs"].update(S=torch.empty(B, nt, nt, dtype=torch.float64, device=device),
+                                 ws=torch.empty(int(lib.thb_potrf_workspace_bytes(B, nt)), dtype=torch.uint8, device=device),
+                                 rhs_root=torch.empty(B, nt, dtype=torch.float64, device=device),
+                                 x_root=torch.empty(B, nt, dtype=torch.float64, device=device),
+                                 info_root=torch.empty(B, dtype=torch.int32, device=device))
         bufs = d["bufs"]
         factor, diag, Atb, info = bufs["factor"], bufs["diag"], bufs["Atb"], bufs["info"]
         nnz, m = A_val.shape[1], b.shape[1]
         self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
         # every structurally non-zero block of L that is not in AtA (fill-in) must start at zero
         _lib.check(lib.thb_fill_zero(_lib.ptr(factor), factor.numel() * 8, s), "fill_zero")
-        if layout == "lane":
+        if layout in ("lane", "lane_root"):
+            lplan = d["lane"] if layout == "lane" else d["lane_root"]   # lane_root: launch list = bottom columns + the root's assembly updates
             _lib.check(lib.thb_sparse_lane_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(factor), s), "gram(lane)")
             _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, None, 0, _lib.ptr(Atb), None, s), "Atb")
             if alpha is not None:
                 _lib.check(lib.thb_sparse_lane_damp_f64(C.byref(d["lane"]), _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta), B, s), "lane_damp")
-            _lib.check(lib.thb_sparse_lane_factor_f64(C.byref(d["lane"]), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info), B, s), "lane_factor")
+            _lib.check(lib.thb_sparse_lane_factor_f64(C.byref(lplan), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info), B, s), "lane_factor")
+            if layout == "lane_root":   # dense root: copy the assembled Schur complement out and factor it on the DMMA kernel
+                _lib.check(lib.thb_sparse_lane_root_gather_f64(C.byref(d["root"]), _lib.ptr(factor), _lib.ptr(bufs["S"]), B, s), "root_gather")
+                _lib.check(lib.thb_potrf_f64(_lib.ptr(bufs["S"]), None, None, _lib.ptr(bufs["info_root"]), B, d["nt"], _lib.ptr(bufs["ws"]),
+                                             bufs["ws"].numel(), s), "root_potrf")
+                torch.maximum(info, torch.where(bufs["info_root"] > 0, bufs["info_root"] + int(self._root[2]["root_start"]), bufs["info_root"]),
+                              out=info)
         else:
             _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(factor), P.data_size,
                                         _lib.ptr(Atb), None, s), "gram(sparse)")
@@ -197,6 +243,16 @@ class BaspachoSparseSolver(LinearSolver):
         if layout == "lane":
             _lib.check(lib.thb_sparse_lane_solve_f64(C.byref(d["lane"]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
                                                      _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "lane_solve")
+        elif layout == "lane_root":
+            s = _lib.stream_ptr()
+            lp, rt = C.byref(d["lane_root"]), C.byref(d["root"])
+            F, D, W = _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(bufs["work"])
+            _lib.check(lib.thb_sparse_lane_forward_f64(lp, F, D, _lib.ptr(rhs), W, B, s), "lane_forward")
+            _lib.check(lib.thb_sparse_lane_root_rhs_f64(lp, rt, F, _lib.ptr(rhs), W, _lib.ptr(bufs["rhs_root"]), B, s), "root_rhs")
+            _lib.check(lib.thb_potrs_f64(_lib.ptr(bufs["rhs_root"]), _lib.ptr(bufs["x_root"]), B, d["nt"], _lib.ptr(bufs["ws"]), bufs["ws"].numel(), s),
+                       "root_potrs")
+            _lib.check(lib.thb_sparse_lane_root_scatter_f64(lp, rt, _lib.ptr(bufs["x_root"]), W, _lib.ptr(x), B, s), "root_scatter")
+            _lib.check(lib.thb_sparse_lane_backward_f64(lp, F, D, W, _lib.ptr(x), B, s), "lane_backward")
         else:
             _lib.check(lib.thb_sparse_solve_f64(C.byref(d["plan"]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
                                                 _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "sparse_solve")
