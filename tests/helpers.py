@@ -7,8 +7,18 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+class Fixture(dict):
+    """A golden fixture read ONCE into memory (an NpzFile decompresses the whole array on every g[key]: 20 s for the 8000-observation
+    bundle-adjustment fixture when accessed inside loops).  Keeps the `.files` attribute the helpers use."""
+
+    @property
+    def files(self):
+        return list(self.keys())
+
+
 def load(name):
-    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    with np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False) as z:
+        return Fixture({k: z[k] for k in z.files})
 
 
 def pgo_spec(g, dtype=np.float64):
