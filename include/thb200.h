@@ -194,7 +194,7 @@ int thb_fill_zero(void* ptr, int64_t bytes, thb_stream_t stream);
  * ---------------------------------------------------------------------------------------------- */
 int64_t thb_potrf_workspace_bytes(int64_t B, int64_t n);
 /* Factor only / solve only against the factor left in `workspace` by thb_potrf_f64 (any number of right-hand
- * sides, e.g. the backward pass of the solve, theseus/optimizer/autograd/*: the factor is reused). */
+ * sides, e.g. the backward pass of the solve, theseus/optimizer/autograd/: the factor is reused). */
 int thb_potrf_f64(const double* AtA, const double* alpha, const double* beta, int32_t* info, int64_t B, int64_t n,
                   void* workspace, int64_t workspace_bytes, thb_stream_t stream);
 int thb_potrs_f64(const double* rhs, double* x, int64_t B, int64_t n, const void* workspace, int64_t workspace_bytes,

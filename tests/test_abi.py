@@ -30,6 +30,20 @@ def test_library_builds_and_exports_declared_symbols():
     assert lib.thb_error_num_chunks(17) == 3
 
 
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/thb200.h must compile as plain C (no C++-isms, no torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        return
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "thb200.h"\nint main(void) { thb_cost_group g; thb_sparse_lane_root r; (void)g; (void)r; return thb_version() > 0 ? 0 : 1; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_sass_is_blackwell_and_uses_fp64_tensor_pipe():
     import shutil
     import subprocess
