@@ -5,7 +5,7 @@ including the reference's literal 12x12 system shape (params [2,3,5,2], extlib/t
 import numpy as np
 import pytest
 
-from theseus_b200.sparse import analyze, analyze_py, minimum_degree_order, root_split
+from theseus_b200.sparse import analyze, analyze_py, chain_tiles, minimum_degree_order, root_split
 
 
 def run_plan_numpy(plan, M, rhs):
@@ -357,6 +357,99 @@ def test_root_split_solves_system():
     assert sp2 is not None and sp2["root_dof"] == 24
     assert np.abs(M @ run_root_split_numpy(plan, sp2, M, rhs) - rhs).max() < 1e-9
     assert root_split(plan, max_root_dof=12, min_root_cols=4) is None
+
+
+def run_chain_tiles_numpy(plan, ct, M, rhs):
+    """Interpret sparse.chain_tiles: per level (1) the external updates of the tiles due at this level, each source block of a step
+    fetched ONCE per tile, (2) the internal updates of the level's columns, (3) the diagonal / triangular stage; then the ordinary
+    substitutions (run_plan_numpy's lists)."""
+    A = plan.arrays
+    N, dims, cs = plan.N, plan.dims, plan.col_start
+    F = np.zeros(plan.data_size)
+    for (i, j), t in plan.blk_index.items():
+        blk = M[cs[i]:cs[i] + dims[i], cs[j]:cs[j] + dims[j]]
+        F[plan.blk_off[t]:plan.blk_off[t] + blk.size] = blk.reshape(-1)
+    blk_ij = {t: ij for ij, t in plan.blk_index.items()}
+
+    def B(t):
+        i, j = blk_ij[t]
+        return F[plan.blk_off[t]:plan.blk_off[t] + dims[i] * dims[j]].reshape(dims[i], dims[j])
+
+    def setB(t, V):
+        F[plan.blk_off[t]:plan.blk_off[t] + V.size] = V.reshape(-1)
+
+    W = np.zeros(plan.winv_size)
+    done_pairs = 0
+    for lv, L in enumerate(ct["per_level"]):
+        for tile in L["tiles"]:
+            acc = {t: B(t).copy() for (_, _, t) in tile["targets"]}
+            for (k, ro, co) in tile["steps"]:
+                staged = {x: B(x).copy() for x in set(ro + co) if x >= 0}     # one fetch per source block and step
+                for (a, b, t) in tile["targets"]:
+                    if ro[a] >= 0 and co[b] >= 0:
+                        acc[t] -= staged[ro[a]] @ staged[co[b]].T
+                        done_pairs += 1
+            for t, V in acc.items():
+                setB(t, V)
+        for (t, p0, p1) in L["u_int"]:
+            V = B(t).copy()
+            i, j = blk_ij[t]
+            for p in range(p0, p1):
+                dk = A["up_k"][p]
+                V -= F[A["up_a"][p]:A["up_a"][p] + dims[i] * dk].reshape(dims[i], dk) @ F[A["up_b"][p]:A["up_b"][p] + dims[j] * dk].reshape(dims[j], dk).T
+                done_pairs += 1
+            setB(t, V)
+        for j in L["cols"]:
+            tj = plan.blk_index[(j, j)]
+            D = np.tril(B(tj))
+            Lj = np.linalg.cholesky(D + np.tril(D, -1).T)
+            setB(tj, Lj)
+            W[A["winv_off"][j]:A["winv_off"][j] + dims[j] ** 2] = np.linalg.inv(Lj).reshape(-1)
+            for i in plan.struct[j]:
+                t = plan.blk_index[(int(i), j)]
+                setB(t, np.linalg.solve(Lj, B(t).T).T)
+    assert done_pairs == int(plan.stats["num_updates"]) == ct["updates"] + sum(p1 - p0 for L in ct["per_level"] for (_, p0, p1) in L["u_int"])
+    # substitutions exactly as run_plan_numpy (item-layout lists; W = inverse diagonal factors)
+    nlev = len(A["s_ptr"]) - 1
+    y = [rhs[cs[j]:cs[j] + dims[j]].copy() for j in range(N)]
+    for lv in range(nlev):
+        for e in range(A["s_ptr"][lv], A["s_ptr"][lv + 1]):
+            j = A["s_col"][e]
+            s = y[j].copy()
+            for p in range(A["fr_ptr"][j], A["fr_ptr"][j + 1]):
+                k = A["fr_k"][p]
+                s -= F[A["fr_off"][p]:A["fr_off"][p] + dims[j] * dims[k]].reshape(dims[j], dims[k]) @ y[k]
+            y[j] = W[A["winv_off"][j]:A["winv_off"][j] + dims[j] ** 2].reshape(dims[j], dims[j]) @ s
+    for lv in reversed(range(nlev)):
+        for e in range(A["s_ptr"][lv], A["s_ptr"][lv + 1]):
+            j = A["s_col"][e]
+            s = y[j].copy()
+            for p in range(A["bc_ptr"][j], A["bc_ptr"][j + 1]):
+                i = A["bc_i"][p]
+                s -= F[A["bc_off"][p]:A["bc_off"][p] + dims[i] * dims[j]].reshape(dims[i], dims[j]).T @ y[i]
+            y[j] = W[A["winv_off"][j]:A["winv_off"][j] + dims[j] ** 2].reshape(dims[j], dims[j]).T @ s
+    x = np.zeros_like(rhs)
+    for j in range(N):
+        x[cs[j]:cs[j] + dims[j]] = y[j]
+    return x
+
+
+@pytest.mark.parametrize("sizes,fill,width,rows", [([6] * 30, 0.08, 4, 4), ([3, 6] * 14, 0.12, 2, 3), ([6] * 16, 0.9, 4, 4), ([2, 3, 6, 1] * 8, 0.1, 8, 2)])
+def test_chain_tiles_schedule_solves_system(sizes, fill, width, rows):
+    """The tiled-update schedule (sparse.chain_tiles: pieces of chains, external pairs per (piece, row tile) with every source block
+    fetched once per step, internal pairs per column) performs exactly the plan's update pairs and factorises correctly."""
+    rng = np.random.default_rng(len(sizes) * 7 + width)
+    M, ptrs, inds = random_block_spd(rng, sizes, fill)
+    plan = analyze(np.array(sizes), ptrs, inds)
+    ct = chain_tiles(plan, max_width=width, tile_rows=rows)
+    pf = ct["piece_first"]
+    for j in range(plan.N):   # pieces are runs of <= width columns inside one chain
+        assert pf[j] <= j < pf[j] + width and plan.chain_of[pf[j]] == plan.chain_of[j]
+    rhs = rng.standard_normal(M.shape[0])
+    x = run_chain_tiles_numpy(plan, ct, M, rhs)
+    assert np.abs(M @ x - rhs).max() < 1e-9
+    if ct["updates"]:
+        assert ct["block_loads"] <= 2 * ct["updates"]     # never worse than streaming both operands of every update
 
 
 def test_chains_are_fundamental_supernodes():

@@ -496,3 +496,81 @@ def root_lane_lists(plan: SparsePlan, sp) -> Tuple[Dict[str, np.ndarray], Dict[s
                 segments=np.array(segs, dtype=np.int32).reshape(-1, 3), nt=sp["root_dof"], root_start=sp["root_start"])
     return lane, root
 
+
+def chain_tiles(plan: SparsePlan, max_width: int = 4, tile_rows: int = 4):
+    """Round-2 building block (host side, specification level: Python lists, checked by a numpy interpreter in
+    tests/test_sparse_symbolic.py; no kernel consumes it yet).  The schedule of the TILED update stage:
+
+      * chains (fundamental supernodes) are cut into pieces of <= max_width consecutive columns;
+      * the update pairs of every block (i, j) split into EXTERNAL ones (source column k before the first column j0 of j's piece;
+        a prefix of the pair list) and INTERNAL ones (j0 <= k < j);
+      * external updates run per TILE = (piece, tile_rows consecutive rows of the piece's row structure): the tile's targets are the
+        blocks (i, j), i in the row tile, j in the piece, i >= j; for every source column k that updates any of them the tile needs at
+        most tile_rows + max_width source blocks L_ik, L_jk -- staged once (shared memory on the GPU) and used by all targets of the
+        tile that have both.  This is where the 1.96 -> 0.70 block loads per update come from (profiles/r01f_sparse_lane_notes.md);
+      * a piece's tiles are due at the level of its first column (all external sources are descendants of j0, hence finished);
+        internal updates and the diagonal/triangular stage stay per column and per level as today.
+
+    Returns dict(piece_first [N], per_level: list over levels of dict(tiles=[...], u_int=[(block id, p0, p1)], cols=[...]), up_ptr,
+    block_loads, updates) with tiles = dict(targets=[(row slot, col slot, block id)], steps=[(k, [row block id or -1]*tile_rows,
+    [col block id or -1]*width)])."""
+    N, dims = plan.N, plan.dims
+    struct = [np.asarray(s_, dtype=np.int64) for s_ in plan.struct]
+    nblk = len(plan.blk_off)
+    counts = np.zeros(nblk, dtype=np.int64)
+    pair_k: List[List[int]] = [[] for _ in range(nblk)]
+    for k in range(N):
+        s_ = struct[k]
+        for bi in range(len(s_)):
+            for ai in range(bi, len(s_)):
+                t = plan.blk_index[(int(s_[ai]), int(s_[bi]))]
+                counts[t] += 1
+                pair_k[t].append(k)
+    up_ptr = np.zeros(nblk + 1, dtype=np.int64)
+    up_ptr[1:] = np.cumsum(counts)
+    # pieces
+    piece_first = np.zeros(N, dtype=np.int64)
+    j = 0
+    while j < N:
+        c = plan.chain_of[j]
+        e = j
+        while e + 1 < N and plan.chain_of[e + 1] == c and e + 1 - j < max_width:
+            e += 1
+        piece_first[j:e + 1] = j
+        j = e + 1
+    rowset = [set() for _ in range(N)]  # rowset[x] = {k : L_xk != 0}
+    for k in range(N):
+        for i in struct[k]:
+            rowset[int(i)].add(k)
+    nlev = int(plan.level.max()) + 1 if N else 0
+    per_level = [dict(tiles=[], u_int=[], cols=[]) for _ in range(nlev)]
+    block_loads = updates = 0
+    for j0 in sorted(set(piece_first.tolist())):
+        cols = [j for j in range(j0, N) if piece_first[j] == j0]
+        j1 = cols[-1]
+        rows = cols + [int(x) for x in struct[j1]]
+        lv0 = int(plan.level[j0])
+        for r0 in range(0, len(rows), tile_rows):
+            rt = rows[r0:r0 + tile_rows]
+            targets = [(a, b, plan.blk_index[(i, jj)]) for a, i in enumerate(rt) for b, jj in enumerate(cols) if i >= jj]
+            ks = sorted(set(k for (_, _, t) in targets for k in pair_k[t] if k < j0))
+            steps = []
+            for k in ks:
+                ro = [plan.blk_index[(i, k)] if k in rowset[i] else -1 for i in rt] + [-1] * (tile_rows - len(rt))
+                co = [plan.blk_index[(jj, k)] if k in rowset[jj] else -1 for jj in cols]
+                steps.append((k, ro, co))
+                block_loads += len(set(x for x in ro + co if x >= 0))
+                updates += sum(1 for (a, b, t) in targets if ro[a] >= 0 and co[b] >= 0)
+            if steps:
+                per_level[lv0]["tiles"].append(dict(targets=targets, steps=steps, piece=(j0, j1)))
+    for j in range(N):
+        lv = int(plan.level[j])
+        per_level[lv]["cols"].append(j)
+        for i in [j] + [int(x) for x in struct[j]]:
+            t = plan.blk_index[(i, j)]
+            ks = pair_k[t]
+            n_ext = int(np.searchsorted(np.asarray(ks, dtype=np.int64), piece_first[j], side="left"))
+            if n_ext < len(ks):
+                per_level[lv]["u_int"].append((t, int(up_ptr[t]) + n_ext, int(up_ptr[t + 1])))
+    return dict(piece_first=piece_first, per_level=per_level, up_ptr=up_ptr, block_loads=block_loads, updates=updates)
+
