@@ -415,6 +415,54 @@ class Objective:
         self._engine = None
         self._batch_size = None
 
+    # ---- queries / removal (objective.py:302-470) ----
+    def get_cost_function(self, name: str) -> CostFunction:
+        return self.cost_functions.get(name, None)
+
+    def has_cost_function(self, name: str) -> bool:
+        return name in self.cost_functions
+
+    def has_optim_var(self, name: str) -> bool:
+        return name in self.optim_vars
+
+    def has_aux_var(self, name: str) -> bool:
+        return name in self.aux_vars
+
+    def _cost_variables(self, cf: CostFunction):
+        return cf.optim_vars, cf.aux_vars + [cf.weight.weight_tensor()]
+
+    def get_functions_connected_to_optim_var(self, variable: Union[str, Manifold]) -> List[CostFunction]:
+        name = variable if isinstance(variable, str) else variable.name
+        if name not in self.optim_vars:
+            raise ValueError(f"Optimization variable named {name} is not in the objective.")
+        return [cf for cf in self.cost_functions.values() if any(v.name == name for v in cf.optim_vars)]
+
+    def get_functions_connected_to_aux_var(self, aux_var: Union[str, Variable]) -> List[CostFunction]:
+        name = aux_var if isinstance(aux_var, str) else aux_var.name
+        if name not in self.aux_vars:
+            raise ValueError(f"Aux variable named {name} is not in the objective.")
+        return [cf for cf in self.cost_functions.values() if any(v.name == name for v in self._cost_variables(cf)[1])]
+
+    def erase(self, name: str):
+        """objective.py:395-416: removes the cost function and every variable no other cost function uses; the compiled engine
+        (pointer tables, CSR structure, symbolic plans) is rebuilt at the next use."""
+        if name not in self.cost_functions:
+            warnings.warn("This cost function is not in the objective, nothing to be done.")
+            return
+        del self.cost_functions[name]
+        used_o = set(v.name for cf in self.cost_functions.values() for v in cf.optim_vars)
+        used_a = set(v.name for cf in self.cost_functions.values() for v in self._cost_variables(cf)[1])
+        for k in [k for k in self.optim_vars if k not in used_o]:
+            del self.optim_vars[k]
+        for k in [k for k in self.aux_vars if k not in used_a]:
+            del self.aux_vars[k]
+        self._structure_version += 1
+        self._engine = None
+        self._batch_size = None
+
+    def size(self) -> tuple:
+        return len(self.cost_functions), len(self.optim_vars), len(self.aux_vars)
+
     def dim(self) -> int:
         return sum(cf.dim() for cf in self.cost_functions.values())
 
