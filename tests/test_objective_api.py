@@ -49,3 +49,19 @@ def test_duplicate_names_are_rejected_like_the_reference():
     with pytest.raises(ValueError, match="same name"):
         obj.add(th.Difference(obj.get_optim_var("a"), th.SE3(name="t3", dtype=d), th.ScaleCostWeight(th.Variable(torch.ones(1, 1, dtype=d), name="w4")),
                               name="prior"))
+
+
+def test_random_generators_give_valid_group_elements():
+    g = torch.Generator().manual_seed(0)
+    for fn in (th.rand_se3, th.randn_se3):
+        T = fn(5, generator=g, dtype=torch.float64).tensor
+        assert T.shape == (5, 3, 4)
+        R = T[:, :, :3]
+        assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, dtype=torch.float64).expand(5, 3, 3), atol=1e-12)
+        assert torch.allclose(torch.linalg.det(R), torch.ones(5, dtype=torch.float64), atol=1e-12)
+    R = th.rand_so3(4, generator=g, dtype=torch.float64).tensor
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, dtype=torch.float64).expand(4, 3, 3), atol=1e-12)
+    X = th.rand_se2(6, generator=g, dtype=torch.float64).tensor
+    assert X.shape == (6, 4) and torch.allclose(X[:, 2] ** 2 + X[:, 3] ** 2, torch.ones(6, dtype=torch.float64), atol=1e-14)
+    assert th.rand_vector(3, 7, generator=g).tensor.shape == (3, 7) and th.randn_point3(2, generator=g).tensor.shape == (2, 3)
+    assert th.rand_point2(2, generator=g).tensor.shape == (2, 2)

@@ -21,6 +21,8 @@ from .optimizer import (VariableOrdering, Linearization, DenseLinearization, Spa
                         NonlinearOptimizerParams, BackwardMode, convert_to_alpha_beta_damping_tensors)
 from .sparse_solver import BaspachoSparseSolver, BlockSparseSolver, CholmodSparseSolver, LUCudaSparseSolver  # noqa: F401
 from .layer import TheseusLayer  # noqa: F401
+from .functional import (adjoint, between, compose, exp_map, inverse, local, log_map, retract, rand_vector, randn_vector,  # noqa: F401
+                         rand_point2, randn_point2, rand_point3, randn_point3, rand_so3, randn_so3, rand_se3, randn_se3, rand_se2, randn_se2)
 from . import io_formats  # noqa: F401  (g2o / BAL readers: th.io_formats.read_3D_g2o_file, load_bal_dataset)
 
 __version__ = "0.1.0"
