@@ -12,6 +12,7 @@ objective is compiled once into per-schema tables of device pointers and offsets
 evaluation is O(#schemas) CUDA kernels from libthb200.
 """
 import warnings
+from enum import Enum
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -332,6 +333,25 @@ class RobustCostFunction(CostFunction):
         return kind, aux
 
 
+class AutogradMode(Enum):
+    """theseus/core/cost_function.py:152-170.  Every mode is served by the vmap(jacrev) path here (the three modes of the reference give
+    the same Jacobians; they differ in how torch computes them)."""
+    DENSE = 0
+    LOOP_BATCH = 1
+    VMAP = 2
+
+    @staticmethod
+    def resolve(key) -> "AutogradMode":
+        if isinstance(key, AutogradMode):
+            return key
+        if not isinstance(key, str):
+            raise ValueError("Autograd mode must be of type th.AutogradMode or string.")
+        try:
+            return AutogradMode[key.upper()]
+        except KeyError:
+            raise ValueError(f"Unrecognized autograd mode {key}. Valid choices are dense, loop_batch, vmap.")
+
+
 class AutoDiffCostFunction(CostFunction):
     """theseus/core/cost_function.py:203-420: user-defined error function, Jacobians by vmap(jacrev(err_fn)) -- kept as the
     reference's torch.func path; the results are scattered straight into the batched-CSR Jacobian.
@@ -340,7 +360,8 @@ class AutoDiffCostFunction(CostFunction):
     ops, the Euclidean Jacobians are projected onto the tangent space like `v.project(jac, is_sparse=True)` (cost_function.py:389-391)."""
 
     def __init__(self, optim_vars: Sequence[Manifold], err_fn, dim: int, cost_weight: Optional[CostWeight] = None,
-                 aux_vars: Optional[Sequence[Variable]] = None, name: Optional[str] = None, **autograd_kwargs):
+                 aux_vars: Optional[Sequence[Variable]] = None, name: Optional[str] = None,
+                 autograd_mode: Union[str, "AutogradMode"] = "vmap", **autograd_kwargs):
         if cost_weight is None:
             cost_weight = ScaleCostWeight(1.0)
         super().__init__(cost_weight, name=name)
@@ -360,6 +381,7 @@ class AutoDiffCostFunction(CostFunction):
             self._aux_vars_attr_names.append(f"_aux_var_{i}")
         self._err_fn = err_fn
         self._dim = dim
+        self._autograd_mode = AutogradMode.resolve(autograd_mode)
 
     def dim(self) -> int:
         return self._dim
