@@ -280,7 +280,7 @@ double thb_symbolic_stat(const thb_symbolic* s, const char* name);
  * `launches` is a HOST array [num_launches][5] = (kind, di, dj, begin, end) in execution order (level by level;
  * kinds below); every other pointer is a device array.  Elimination-tree levels are separate kernel launches.
  * ---------------------------------------------------------------------------------------------- */
-enum { THB_LANE_U = 0, THB_LANE_T = 1, THB_LANE_S = 2, THB_LANE_UH = 3 };
+enum { THB_LANE_U = 0, THB_LANE_T = 1, THB_LANE_S = 2, THB_LANE_UH = 3, THB_LANE_TU = 4 /* tiled external updates, below */ };
 typedef struct thb_sparse_lane_plan {
   int64_t N;            /* number of variable blocks */
   int64_t n;            /* scalar dimension */
@@ -342,6 +342,25 @@ int thb_sparse_lane_root_rhs_f64(const thb_sparse_lane_plan* p, const thb_sparse
 /* root solution x_dense [B, nt] -> work (for thb_sparse_lane_backward_f64) and x [B, n] (original order) */
 int thb_sparse_lane_root_scatter_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_root* r, const double* x_dense, double* work, double* x,
                                      int64_t B, thb_stream_t stream);
+/* Tiled external updates (opt-in layout `lane_tiled`; host lists: theseus_b200/sparse.py:tile_lane_lists).  The columns of a
+ * fundamental supernode ("chain", cut into pieces of <= 4 columns) share their row structure, so the left-looking updates that reach
+ * a piece from outside it (source column k before the piece: BaSpaCho's per-supernode "eliminateBoard" work, baspacho_solver_cuda.cu
+ * via NumericDecomposition::factor, extlib/baspacho_solver.cpp:171-199) are done per TILE of 4 rows x 4 columns of 6x6 blocks by ONE
+ * CTA of 16 warps (warp = one target block x 32 batch lanes, accumulators in registers): per source column k the <= 8 source blocks
+ * L_(row),k and L_(column),k are staged ONCE in shared memory (cp.async, double buffered) and used by every target that has both,
+ * instead of being streamed from L2/HBM once per update pair.  A launch row (THB_LANE_TU, 6, 6, begin, end) of the plan's launch
+ * list runs tiles [begin, end).  All pointers device arrays. */
+#define THB_TILE_ROWS 4
+#define THB_TILE_COLS 4
+typedef struct thb_sparse_lane_tiles {
+  int64_t num_tiles, num_steps;
+  const int64_t* tile_tgt;   /* [num_tiles, 16] offset of target block (row slot a, column slot b) at a*4+b, -1 if absent */
+  const int64_t* step_ptr;   /* [num_tiles+1] k steps of a tile */
+  const int64_t* step_src;   /* [num_steps, 8] offsets of L_(row slot 0..3),k then L_(column slot 0..3),k; -1 = structurally zero */
+} thb_sparse_lane_tiles;
+/* thb_sparse_lane_factor_f64 for a launch list that may contain THB_LANE_TU rows */
+int thb_sparse_lane_factor_tiled_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_tiles* t, double* factor, double* diagl,
+                                     int32_t* info, int64_t B, thb_stream_t stream);
 /* rhs, x: [B, n] row-major in the ORIGINAL variable order (scramble / unscramble folded into the substitutions) */
 int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs,
                               double* x, double* work, int64_t B, thb_stream_t stream);

@@ -71,10 +71,11 @@ def run_plan_numpy(plan, M, rhs):
     return x
 
 
-def run_lane_plan_numpy(plan, M, rhs):
+def run_lane_plan_numpy(plan, M, rhs, lane=None, tiles=None):
     """Interpret plan.lane (the work lists of thb_sparse_lane.cu) in launch order: U / UH = left-looking update of a block,
-    T = Cholesky of the column's diagonal block (to `diagl`, reciprocal diagonal) + triangular solve of the block, S = substitutions."""
-    A, Ln = plan.arrays, plan.lane
+    T = Cholesky of the column's diagonal block (to `diagl`, reciprocal diagonal) + triangular solve of the block, S = substitutions,
+    TU (with `tiles`, sparse.tile_lane_lists) = tiled external updates: per k step every target with both sources present."""
+    A, Ln = plan.arrays, (plan.lane if lane is None else lane)
     N, dims, cs = plan.N, plan.dims, plan.col_start
     F = np.zeros(plan.data_size)
     for (i, j), t in plan.blk_index.items():
@@ -95,6 +96,21 @@ def run_lane_plan_numpy(plan, M, rhs):
                     dk = A["up_k"][p]
                     T -= F[A["up_a"][p]:A["up_a"][p] + di * dk].reshape(di, dk) @ F[A["up_b"][p]:A["up_b"][p] + dj * dk].reshape(dj, dk).T
                 F[tgt:tgt + di * dj] = T.reshape(-1)
+        elif kind == 4:
+            TR, TC, D = 4, 4, 6
+            assert di == D and dj == D
+            for t in range(b0, b1):
+                tg = tiles["tile_tgt"][t]
+                acc = {w: F[tg[w]:tg[w] + D * D].reshape(D, D).copy() for w in range(TR * TC) if tg[w] >= 0}
+                assert tiles["step_ptr"][t + 1] > tiles["step_ptr"][t]
+                for st in range(tiles["step_ptr"][t], tiles["step_ptr"][t + 1]):
+                    src = tiles["step_src"][st]
+                    for w in acc:
+                        ro, co = src[w // TC], src[TR + w % TC]
+                        if ro >= 0 and co >= 0:
+                            acc[w] -= F[ro:ro + D * D].reshape(D, D) @ F[co:co + D * D].reshape(D, D).T
+                for w, V in acc.items():
+                    F[tg[w]:tg[w] + D * D] = V.reshape(-1)
         elif kind == 1:
             diag_writes = {}
             for e in range(b0, b1):   # every item reads the PRE-factor diagonal block: collect, then write
@@ -211,6 +227,40 @@ def test_lane_work_lists_solve_system(sizes, fill, ordering):
     nT = sum(b1 - b0 for k, _, _, b0, b1 in launches if k == 1)
     nS = sum(b1 - b0 for k, _, _, b0, b1 in launches if k == 2)
     assert nT == len(plan.blk_off) and nS == plan.N
+
+
+@pytest.mark.parametrize("sizes,fill,ordering,expect_tiles", [
+    ([6] * 14, 0.9, "natural", True),      # one dense chain: the pieces after the first get their external updates from tiles
+    ([6] * 40, 0.06, "mindeg", True),
+    ([6] * 30 + [3] * 10, 0.07, "mindeg", True),   # mixed sizes: tiles that touch a 3-block stay on the per-block path
+    ([3] * 30 + [6] * 5, 0.08, "mindeg", False),
+])
+def test_tiled_lane_lists_solve_system(sizes, fill, ordering, expect_tiles):
+    """`lane_tiled` layout: flat tile arrays + reduced U lists (sparse.tile_lane_lists), executed by the numpy interpreter."""
+    from theseus_b200.sparse import tile_lane_lists
+    rng = np.random.default_rng(len(sizes) + int(fill * 100) + 7)
+    M, ptrs, inds = random_block_spd(rng, sizes, fill)
+    plan = analyze(np.array(sizes), ptrs, inds, ordering=ordering)
+    lane, tiles = tile_lane_lists(plan)
+    T = tiles["tile_tgt"].shape[0]
+    assert tiles["tile_tgt"].shape == (T, 16) and tiles["step_ptr"].shape == (T + 1,) and tiles["step_src"].shape[1] == 8
+    if expect_tiles:
+        assert T > 0
+    tiled_launches = [l for l in lane["launches"] if l[0] == 4]
+    assert sum(l[4] - l[3] for l in tiled_launches) == T
+    rhs = rng.standard_normal(M.shape[0])
+    x = run_lane_plan_numpy(plan, M, rhs, lane=lane, tiles=tiles)
+    assert np.abs(M @ x - rhs).max() < 1e-10
+    # update pairs: every pair is done exactly once, by a tile step or by a U item
+    n_u = int((lane["u_p1"] - lane["u_p0"]).sum())
+    n_t = 0
+    for t in range(T):
+        tg = tiles["tile_tgt"][t]
+        for st in range(tiles["step_ptr"][t], tiles["step_ptr"][t + 1]):
+            src = tiles["step_src"][st]
+            n_t += sum(1 for w in range(16) if tg[w] >= 0 and src[w // 4] >= 0 and src[4 + w % 4] >= 0)
+    assert n_u + n_t == len(plan.arrays["up_a"])
+    print(f"tiles={T} tile updates={n_t} per-block updates={n_u}")
 
 
 @pytest.mark.parametrize("sizes,fill,ordering", [

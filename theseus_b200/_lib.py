@@ -74,7 +74,12 @@ class SparseLaneRootStruct(C.Structure):
         "segments", "rb_off", "rb_row", "rb_col", "rb_di", "rb_dj", "rf_p0", "rf_p1", "root_cols", "root_dims")]
 
 
+class SparseLaneTilesStruct(C.Structure):
+    _fields_ = [("num_tiles", c_i64), ("num_steps", c_i64), ("tile_tgt", c_vp), ("step_ptr", c_vp), ("step_src", c_vp)]
+
+
 _PR = C.POINTER(SparseLaneRootStruct)
+_PT = C.POINTER(SparseLaneTilesStruct)
 SIGNATURES = {
     "thb_version": (c_i32, []),
     "thb_compiled_arch": (c_i32, []),
@@ -110,6 +115,7 @@ SIGNATURES = {
     "thb_sparse_lane_gram_f64": (c_i32, [_PP, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "thb_sparse_lane_damp_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_factor_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_factor_tiled_f64": (c_i32, [_PL, _PT, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_solve_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_forward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_backward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),

@@ -146,6 +146,83 @@ __global__ void __launch_bounds__(32 * LH_WARPS, 1) lane_update_heavy_kernel(Lan
   }
 }
 
+// ---- TU: tiled external updates of a chain piece (sparse.py:tile_lane_lists) ----
+// One CTA = one tile (TR rows x TC columns of D x D target blocks) x 32 batch lanes; warp w owns target (w / TC, w % TC) in registers.
+// Per k step the NS = TR + TC source blocks are copied ONCE into shared memory ([slot][element][lane]: every row is a coalesced
+// 256-byte segment in global memory and conflict-free in shared memory), double buffered with cp.async so the copy of step s+1
+// runs under the FP64 work of step s; a target takes part in a step iff both its row and its column source exist.
+struct LaneTileArgs {
+  const int64_t* tile_tgt; const int64_t* step_ptr; const int64_t* step_src;
+  int begin; int64_t Bp;
+};
+
+__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D, int TR, int TC>
+__global__ void __launch_bounds__(32 * TR * TC, 1) lane_tile_update_kernel(LaneTileArgs p, double* F) {
+  constexpr int NS = TR + TC, E = D * D, NW = TR * TC, ROWS = NS * E;
+  extern __shared__ double tile_sm[];  // [2][NS][E][32]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tile = p.begin + (int)blockIdx.x;
+  double* Fb = F + (int64_t)blockIdx.y * 32 + lane;   // padded lanes (b >= B) hold zeros / unused storage inside [*, Bp]: computed, harmless
+  const int64_t tgt = p.tile_tgt[(int64_t)tile * NW + w];
+  const int a = w / TC, b = w % TC;
+  double acc[E];
+  if (tgt >= 0) {
+#pragma unroll
+    for (int e = 0; e < E; e++) acc[e] = Fb[(tgt + e) * p.Bp];
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; e++) acc[e] = 0.0;
+  }
+  const int64_t s0 = p.step_ptr[tile], s1 = p.step_ptr[tile + 1];
+  auto stage = [&](int64_t s, int buf) {
+    const int64_t* src = p.step_src + s * NS;
+    double* dst = tile_sm + (size_t)buf * ROWS * 32 + lane;
+#pragma unroll 6
+    for (int r = w; r < ROWS; r += NW) {
+      const int slot = r / E, e = r - slot * E;
+      const int64_t off = src[slot];
+      if (off >= 0) cp_async_8(dst + r * 32, Fb + (off + e) * p.Bp);
+    }
+    cp_async_commit();
+  };
+  if (s0 < s1) stage(s0, 0);
+  for (int64_t s = s0; s < s1; s++) {
+    const int buf = (int)(s - s0) & 1;
+    if (s + 1 < s1) { stage(s + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int64_t ro = p.step_src[s * NS + a], co = p.step_src[s * NS + TR + b];
+    if (tgt >= 0 && ro >= 0 && co >= 0) {
+      const double* R = tile_sm + ((size_t)buf * ROWS + a * E) * 32 + lane;
+      const double* Cc = tile_sm + ((size_t)buf * ROWS + (TR + b) * E) * 32 + lane;
+#pragma unroll
+      for (int q = 0; q < D; q++) {
+        double rv[D], cv[D];
+#pragma unroll
+        for (int r = 0; r < D; r++) rv[r] = R[(r * D + q) * 32];
+#pragma unroll
+        for (int c = 0; c < D; c++) cv[c] = Cc[(c * D + q) * 32];
+#pragma unroll
+        for (int r = 0; r < D; r++)
+#pragma unroll
+          for (int c = 0; c < D; c++) acc[r * D + c] -= rv[r] * cv[c];
+      }
+    }
+    __syncthreads();  // buffer `buf` is refilled by the stage() of the next iteration
+  }
+  if (tgt >= 0) {
+#pragma unroll
+    for (int e = 0; e < E; e++) Fb[(tgt + e) * p.Bp] = acc[e];
+  }
+}
+
 // ---- T: Cholesky of the column's diagonal block (registers) + triangular solve of this block ----
 template <int DI, int DJ>
 __global__ void __launch_bounds__(32 * LN_WARPS) lane_trsm_kernel(LaneArgs p, double* __restrict__ F, double* __restrict__ DL,
@@ -523,7 +600,8 @@ int thb_sparse_lane_damp_f64(const thb_sparse_lane_plan* p, double* factor, cons
   return THB_OK;
 }
 
-int thb_sparse_lane_factor_f64(const thb_sparse_lane_plan* p, double* factor, double* diagl, int32_t* info, int64_t B, thb_stream_t s) {
+static int lane_factor_impl(const thb_sparse_lane_plan* p, const thb_sparse_lane_tiles* tiles, double* factor, double* diagl, int32_t* info,
+                            int64_t B, thb_stream_t s) {
   if (p == nullptr || factor == nullptr || diagl == nullptr || info == nullptr || B < 0) return THB_ERR_BAD_ARG;
   if (B == 0 || p->N == 0) return THB_OK;
   cudaStream_t cs = thb_cs(s);
@@ -550,12 +628,33 @@ int thb_sparse_lane_factor_f64(const thb_sparse_lane_plan* p, double* factor, do
     } else if (kind == THB_LANE_T) {
 #define CALL_T(DI, DJ) thb::lane_trsm_kernel<DI, DJ><<<grid_w, 32 * thb::LN_WARPS, 0, cs>>>(a, factor, diagl, info)
       LN_SWITCH(di, dj, CALL_T)
+    } else if (kind == THB_LANE_TU) {
+      if (tiles == nullptr || di != 6 || dj != 6 || a.end > tiles->num_tiles) return THB_ERR_BAD_ARG;
+      constexpr int TR = THB_TILE_ROWS, TC = THB_TILE_COLS;
+      constexpr int smem = 2 * (TR + TC) * 36 * 32 * (int)sizeof(double);
+      auto kern = thb::lane_tile_update_kernel<6, TR, TC>;
+      static bool smem_opted_in = false;   // idempotent; not a stream operation (legal under CUDA-graph capture)
+      if (!smem_opted_in) { THB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_opted_in = true; }
+      thb::LaneTileArgs ta;
+      ta.tile_tgt = tiles->tile_tgt; ta.step_ptr = tiles->step_ptr; ta.step_src = tiles->step_src;
+      ta.begin = a.begin; ta.Bp = a.Bp;
+      kern<<<dim3((unsigned)items, (unsigned)a.nbx), 32 * TR * TC, smem, cs>>>(ta, factor);
     } else {
       return THB_ERR_BAD_ARG;
     }
     THB_CHECK_LAUNCH();
   }
   return THB_OK;
+}
+
+int thb_sparse_lane_factor_f64(const thb_sparse_lane_plan* p, double* factor, double* diagl, int32_t* info, int64_t B, thb_stream_t s) {
+  return lane_factor_impl(p, nullptr, factor, diagl, info, B, s);
+}
+
+int thb_sparse_lane_factor_tiled_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_tiles* t, double* factor, double* diagl,
+                                     int32_t* info, int64_t B, thb_stream_t s) {
+  if (t == nullptr) return THB_ERR_BAD_ARG;
+  return lane_factor_impl(p, t, factor, diagl, info, B, s);
 }
 
 static thb::LaneSolveArgs lane_solve_args(const thb_sparse_lane_plan* p, int64_t B) {

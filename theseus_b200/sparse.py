@@ -327,15 +327,18 @@ def _chains(N, struct, parent):
 
 LANE_DIMS = (1, 2, 3, 6)   # block sizes the batch-lane kernels are instantiated for (thb_sparse_lane.cu)
 LANE_HEAVY = 8             # update pairs per target block from which the split-K variant of the update kernel is used
-LN_U, LN_T, LN_S, LN_UH = 0, 1, 2, 3
+LN_U, LN_T, LN_S, LN_UH, LN_TU = 0, 1, 2, 3, 4
+TILE_DIM, TILE_ROWS, TILE_COLS = 6, 4, 4   # the tiled update kernel is instantiated for 6x6 blocks in 4 x 4 tiles (thb_sparse_lane.cu)
 
 
-def _lane_lists(N, nlev, cols_by_level, struct, dims, blk_index, blk_off, up_ptr, winv_off, pstart):
+def _lane_lists(N, nlev, cols_by_level, struct, dims, blk_index, blk_off, up_ptr, winv_off, pstart, u_start=None, pre_launches=None):
     """Work lists for the batch-lane kernels: per level, the target blocks grouped by (rows, cols) class, because those
     kernels keep a whole block in registers and are compiled per block shape.  `launches` is a HOST array of
     (kind, di, dj, begin, end) rows in execution order: kind U = left-looking update of blocks [begin,end) of u_*,
     UH = the same for blocks with many update pairs (split over 8 warps), T = diagonal factor + triangular solve of blocks
-    [begin,end) of t_*, S = columns [begin,end) of s_col for the substitutions (forward: in order, backward: reversed)."""
+    [begin,end) of t_*, S = columns [begin,end) of s_col for the substitutions (forward: in order, backward: reversed).
+    `u_start[t]` (optional) = first update pair of block t that is still to be done by a U launch (the earlier ones are covered by
+    a tile launch, tile_lane_lists); `pre_launches[lv]` (optional) = launch rows that open level lv."""
     u_tgt, u_p0, u_p1 = [], [], []
     t_off, t_diag, t_dl, t_pstart = [], [], [], []
     s_col = []
@@ -344,6 +347,8 @@ def _lane_lists(N, nlev, cols_by_level, struct, dims, blk_index, blk_off, up_ptr
         ucls: Dict[Tuple[int, int, int], list] = {}
         tcls: Dict[Tuple[int, int], list] = {}
         scls: Dict[int, list] = {}
+        if pre_launches is not None:
+            launches.extend(pre_launches[lv])
         for j in cols_by_level[lv]:
             dj = int(dims[j])
             scls.setdefault(dj, []).append(j)
@@ -351,14 +356,15 @@ def _lane_lists(N, nlev, cols_by_level, struct, dims, blk_index, blk_off, up_ptr
             for i in [j] + [int(x) for x in struct[j]]:
                 t = blk_index[(i, j)]
                 di = int(dims[i])
-                npairs = int(up_ptr[t + 1] - up_ptr[t])
+                first = int(up_ptr[t]) if u_start is None else int(u_start[t])
+                npairs = int(up_ptr[t + 1]) - first
                 if npairs > 0:
                     ucls.setdefault((1 if npairs >= LANE_HEAVY else 0, di, dj), []).append(t)
                 tcls.setdefault((di, dj), []).append((t, dg, j))
         for (heavy, di, dj) in sorted(ucls):
             b0 = len(u_tgt)
             for t in ucls[(heavy, di, dj)]:
-                u_tgt.append(int(blk_off[t])); u_p0.append(int(up_ptr[t])); u_p1.append(int(up_ptr[t + 1]))
+                u_tgt.append(int(blk_off[t])); u_p0.append(int(up_ptr[t]) if u_start is None else int(u_start[t])); u_p1.append(int(up_ptr[t + 1]))
             launches.append((LN_UH if heavy else LN_U, di, dj, b0, len(u_tgt)))
         for (di, dj) in sorted(tcls):
             b0 = len(t_off)
@@ -574,3 +580,61 @@ def chain_tiles(plan: SparsePlan, max_width: int = 4, tile_rows: int = 4):
                 per_level[lv]["u_int"].append((t, int(up_ptr[t]) + n_ext, int(up_ptr[t + 1])))
     return dict(piece_first=piece_first, per_level=per_level, up_ptr=up_ptr, block_loads=block_loads, updates=updates)
 
+
+
+def tile_lane_lists(plan: SparsePlan) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
+    """Work lists of the opt-in `lane_tiled` layout: the chain_tiles schedule flattened for thb_sparse_lane_factor_tiled_f64.
+
+    Tiles whose targets and sources are all TILE_DIM x TILE_DIM blocks become rows of the tile arrays
+      tile_tgt  [T, TILE_ROWS*TILE_COLS]  offset of target block (row slot a, column slot b) at a*TILE_COLS+b, -1 if absent
+      step_ptr  [T+1]                      k steps of tile t = step_ptr[t] .. step_ptr[t+1]
+      step_src  [S, TILE_ROWS+TILE_COLS]   offsets of the source blocks L_(row a),k (first TILE_ROWS entries) and L_(column b),k, -1 if zero
+    and a launch row (LN_TU, 6, 6, first tile, one past last tile) opens the level of the piece's first column; the update pairs they
+    cover (a prefix of each target's pair list) are dropped from the U / UH items.  Every other block keeps its full pair list.
+    Returns (lane lists, tile arrays)."""
+    ct = chain_tiles(plan, max_width=TILE_COLS, tile_rows=TILE_ROWS)
+    N, dims = plan.N, plan.dims
+    up_ptr = ct["up_ptr"]
+    nblk = len(plan.blk_off)
+    blk_shape = np.zeros((nblk, 2), dtype=np.int64)
+    blk_col = np.zeros(nblk, dtype=np.int64)
+    for (i, j), t in plan.blk_index.items():
+        blk_shape[t] = (dims[i], dims[j])
+        blk_col[t] = j
+    nlev = len(ct["per_level"])
+    u_start = up_ptr[:-1].copy()
+    tile_tgt, step_ptr, step_src = [], [0], []
+    pre = [[] for _ in range(nlev)]
+    # pairs of a block are stored in increasing source column k: the external ones (k < first column of the piece) are a prefix
+    A = plan.arrays
+    src_blk = np.searchsorted(plan.blk_off, A["up_a"], side="right") - 1
+    pair_k = blk_col[src_blk]
+    for lv in range(nlev):
+        t0 = len(tile_tgt)
+        for tile in ct["per_level"][lv]["tiles"]:
+            ids = [t for (_, _, t) in tile["targets"]] + [x for (_, ro, co) in tile["steps"] for x in ro + co if x >= 0]
+            if not all(blk_shape[t][0] == TILE_DIM and blk_shape[t][1] == TILE_DIM for t in ids):
+                continue
+            row = [-1] * (TILE_ROWS * TILE_COLS)
+            j0 = tile["piece"][0]
+            for (a, b, t) in tile["targets"]:
+                row[a * TILE_COLS + b] = int(plan.blk_off[t])
+                p0, p1 = int(up_ptr[t]), int(up_ptr[t + 1])
+                n_ext = int(np.searchsorted(pair_k[p0:p1], j0, side="left"))
+                assert (pair_k[p0:p0 + n_ext] < j0).all() and (pair_k[p0 + n_ext:p1] >= j0).all()
+                u_start[t] = p0 + n_ext
+            tile_tgt.append(row)
+            for (_, ro, co) in tile["steps"]:
+                co = list(co) + [-1] * (TILE_COLS - len(co))
+                step_src.append([int(plan.blk_off[x]) if x >= 0 else -1 for x in list(ro) + co])
+            step_ptr.append(len(step_src))
+        if len(tile_tgt) > t0:
+            pre[lv].append((LN_TU, TILE_DIM, TILE_DIM, t0, len(tile_tgt)))
+    cols_by_level = [list(ct["per_level"][lv]["cols"]) for lv in range(nlev)]
+    lane = _lane_lists(N, nlev, cols_by_level, plan.struct, dims, plan.blk_index, plan.blk_off, up_ptr, plan.winv_off, plan.pstart,
+                       u_start=u_start, pre_launches=pre)
+    lane.update(fr_p=plan.lane["fr_p"], fr_d=plan.lane["fr_d"], bc_p=plan.lane["bc_p"], bc_d=plan.lane["bc_d"])
+    i64 = np.int64
+    tiles = dict(tile_tgt=np.array(tile_tgt, dtype=i64).reshape(-1, TILE_ROWS * TILE_COLS), step_ptr=np.array(step_ptr, dtype=i64),
+                 step_src=np.array(step_src, dtype=i64).reshape(-1, TILE_ROWS + TILE_COLS))
+    return lane, tiles

@@ -16,7 +16,7 @@ from . import _lib
 from .autograd import LinearSolveFunction, wants_grad
 from .core import Objective
 from .optimizer import (Linearization, LinearSolver, SparseLinearization, convert_to_alpha_beta_damping_tensors)
-from .sparse import LANE_DIMS, analyze, gram_out_offsets, root_lane_lists, root_split
+from .sparse import LANE_DIMS, analyze, gram_out_offsets, root_lane_lists, root_split, tile_lane_lists
 from .structure import ata_block_structure, build_gram_plan
 
 
@@ -70,8 +70,8 @@ class BaspachoSparseSolver(LinearSolver):
         thb_sparse.cu).  Default: lane whenever a warp can be filled and every block size is one the lane kernels are built for."""
         lane_ok = all(int(d) in LANE_DIMS for d in self._plan.dims)
         if self._layout is not None:
-            if self._layout not in ("lane", "item", "lane_root"):
-                raise ValueError(f"layout must be 'lane', 'item' or 'lane_root', got {self._layout}")
+            if self._layout not in ("lane", "item", "lane_root", "lane_tiled"):
+                raise ValueError(f"layout must be 'lane', 'item', 'lane_root' or 'lane_tiled', got {self._layout}")
             if self._layout != "item" and not lane_ok:
                 raise ValueError(f"layout='{self._layout}' needs block sizes in {LANE_DIMS}")
             if self._layout == "lane_root" and self._root_split() is None:
@@ -104,6 +104,33 @@ class BaspachoSparseSolver(LinearSolver):
         gst = _lib.make_gram_plan(g, gdev)
         # batch-lane plan: shares the batch-independent arrays above, adds the per-level / per-shape work lists
         ln = P.lane
+        lst, ldev, launches = self._lane_struct(ln, dev, device)
+        self._dev = dict(device=device, plan=st, keep=dev, gram=gst, gkeep=gdev, bufs={}, lane=lst, lkeep=(ldev, launches))
+        if self._layout == "lane_root":
+            sp, rl, rr = self._root_split()
+            rst, rdev, rlaunch = self._lane_struct(rl, dev, device)
+            qdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in rr.items() if isinstance(v, np.ndarray) and k != "segments"}
+            segs = np.ascontiguousarray(rr["segments"], dtype=np.int32)
+            qst = _lib.SparseLaneRootStruct(
+                num_blocks=int(rr["rb_off"].shape[0]), num_cols=int(rr["root_cols"].shape[0]), nt=int(rr["nt"]), root_start=int(rr["root_start"]),
+                num_segments=int(segs.shape[0]), segments=segs.ctypes.data, rb_off=qdev["rb_off"].data_ptr(), rb_row=qdev["rb_row"].data_ptr(),
+                rb_col=qdev["rb_col"].data_ptr(), rb_di=qdev["rb_di"].data_ptr(), rb_dj=qdev["rb_dj"].data_ptr(), rf_p0=qdev["rf_p0"].data_ptr(),
+                rf_p1=qdev["rf_p1"].data_ptr(), root_cols=qdev["root_cols"].data_ptr(), root_dims=qdev["root_dims"].data_ptr())
+            self._dev.update(lane_root=rst, root=qst, rkeep=(rdev, rlaunch, qdev, segs), nt=int(rr["nt"]))
+        if self._layout == "lane_tiled":
+            tl, tt = self._tile_lists()
+            tst, tdev, tlaunch = self._lane_struct(tl, dev, device)
+            ttdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in tt.items()}
+            tiles = _lib.SparseLaneTilesStruct(num_tiles=int(tt["tile_tgt"].shape[0]), num_steps=int(tt["step_src"].shape[0]),
+                                               tile_tgt=ttdev["tile_tgt"].data_ptr(), step_ptr=ttdev["step_ptr"].data_ptr(),
+                                               step_src=ttdev["step_src"].data_ptr())
+            self._dev.update(lane_tiled=tst, tiles=tiles, tkeep=(tdev, tlaunch, ttdev))
+        return self._dev
+
+    def _lane_struct(self, ln, dev, device):
+        """thb_sparse_lane_plan over the plan's batch-independent device arrays `dev` + the work lists `ln` (uploaded here).
+        Returns (struct, device arrays, host launch list) -- the caller keeps the last two alive."""
+        P = self._plan
         ldev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in ln.items() if k != "launches"}
         launches = np.ascontiguousarray(ln["launches"], dtype=np.int32)
         lst = _lib.SparseLanePlanStruct(
@@ -116,30 +143,13 @@ class BaspachoSparseSolver(LinearSolver):
             t_pstart=ldev["t_pstart"].data_ptr(), s_col=ldev["s_col"].data_ptr(),
             fr_ptr=dev["fr_ptr"].data_ptr(), fr_off=dev["fr_off"].data_ptr(), fr_p=ldev["fr_p"].data_ptr(), fr_d=ldev["fr_d"].data_ptr(),
             bc_ptr=dev["bc_ptr"].data_ptr(), bc_off=dev["bc_off"].data_ptr(), bc_p=ldev["bc_p"].data_ptr(), bc_d=ldev["bc_d"].data_ptr())
-        self._dev = dict(device=device, plan=st, keep=dev, gram=gst, gkeep=gdev, bufs={}, lane=lst, lkeep=(ldev, launches))
-        if self._layout == "lane_root":
-            sp, rl, rr = self._root_split()
-            rdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in rl.items() if k != "launches"}
-            rlaunch = np.ascontiguousarray(rl["launches"], dtype=np.int32)
-            rst = _lib.SparseLanePlanStruct(
-                N=P.N, n=P.n, data_size=P.data_size, diag_size=P.winv_size, num_launches=int(rlaunch.shape[0]),
-                launches=rlaunch.ctypes.data, dims=dev["dims"].data_ptr(), col_start=dev["col_start"].data_ptr(),
-                pstart=dev["pstart"].data_ptr(), dl_off=dev["winv_off"].data_ptr(), diag_off=dev["diag_off"].data_ptr(),
-                up_a=dev["up_a"].data_ptr(), up_b=dev["up_b"].data_ptr(), up_k=dev["up_k"].data_ptr(),
-                u_tgt=rdev["u_tgt"].data_ptr(), u_p0=rdev["u_p0"].data_ptr(), u_p1=rdev["u_p1"].data_ptr(),
-                t_off=rdev["t_off"].data_ptr(), t_diag=rdev["t_diag"].data_ptr(), t_dl=rdev["t_dl"].data_ptr(),
-                t_pstart=rdev["t_pstart"].data_ptr(), s_col=rdev["s_col"].data_ptr(),
-                fr_ptr=dev["fr_ptr"].data_ptr(), fr_off=dev["fr_off"].data_ptr(), fr_p=rdev["fr_p"].data_ptr(), fr_d=rdev["fr_d"].data_ptr(),
-                bc_ptr=dev["bc_ptr"].data_ptr(), bc_off=dev["bc_off"].data_ptr(), bc_p=rdev["bc_p"].data_ptr(), bc_d=rdev["bc_d"].data_ptr())
-            qdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in rr.items() if isinstance(v, np.ndarray) and k != "segments"}
-            segs = np.ascontiguousarray(rr["segments"], dtype=np.int32)
-            qst = _lib.SparseLaneRootStruct(
-                num_blocks=int(rr["rb_off"].shape[0]), num_cols=int(rr["root_cols"].shape[0]), nt=int(rr["nt"]), root_start=int(rr["root_start"]),
-                num_segments=int(segs.shape[0]), segments=segs.ctypes.data, rb_off=qdev["rb_off"].data_ptr(), rb_row=qdev["rb_row"].data_ptr(),
-                rb_col=qdev["rb_col"].data_ptr(), rb_di=qdev["rb_di"].data_ptr(), rb_dj=qdev["rb_dj"].data_ptr(), rf_p0=qdev["rf_p0"].data_ptr(),
-                rf_p1=qdev["rf_p1"].data_ptr(), root_cols=qdev["root_cols"].data_ptr(), root_dims=qdev["root_dims"].data_ptr())
-            self._dev.update(lane_root=rst, root=qst, rkeep=(rdev, rlaunch, qdev, segs), nt=int(rr["nt"]))
-        return self._dev
+        return lst, ldev, launches
+
+    def _tile_lists(self):
+        """Work lists of the opt-in layout 'lane_tiled' (sparse.tile_lane_lists), computed on first use."""
+        if not hasattr(self, "_tiles"):
+            self._tiles = tile_lane_lists(self._plan)
+        return self._tiles
 
     # ---- numeric phase (baspacho_sparse_autograd.py:21-65) ----
     def solve(self, damping: Optional[Union[float, torch.Tensor]] = None, ellipsoidal_damping: bool = True,
@@ -210,13 +220,17 @@ class BaspachoSparseSolver(LinearSolver):
         self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
         # every structurally non-zero block of L that is not in AtA (fill-in) must start at zero
         _lib.check(lib.thb_fill_zero(_lib.ptr(factor), factor.numel() * 8, s), "fill_zero")
-        if layout in ("lane", "lane_root"):
-            lplan = d["lane"] if layout == "lane" else d["lane_root"]   # lane_root: launch list = bottom columns + the root's assembly updates
+        if layout in ("lane", "lane_root", "lane_tiled"):
+            lplan = d[layout]   # lane_root: launch list = bottom columns + the root's assembly updates; lane_tiled: + tile launches
             _lib.check(lib.thb_sparse_lane_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(factor), s), "gram(lane)")
             _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, None, 0, _lib.ptr(Atb), None, s), "Atb")
             if alpha is not None:
                 _lib.check(lib.thb_sparse_lane_damp_f64(C.byref(d["lane"]), _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta), B, s), "lane_damp")
-            _lib.check(lib.thb_sparse_lane_factor_f64(C.byref(lplan), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info), B, s), "lane_factor")
+            if layout == "lane_tiled":
+                _lib.check(lib.thb_sparse_lane_factor_tiled_f64(C.byref(lplan), C.byref(d["tiles"]), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info),
+                                                                B, s), "lane_factor_tiled")
+            else:
+                _lib.check(lib.thb_sparse_lane_factor_f64(C.byref(lplan), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info), B, s), "lane_factor")
             if layout == "lane_root":   # dense root: copy the assembled Schur complement out and factor it on the DMMA kernel
                 _lib.check(lib.thb_sparse_lane_root_gather_f64(C.byref(d["root"]), _lib.ptr(factor), _lib.ptr(bufs["S"]), B, s), "root_gather")
                 _lib.check(lib.thb_potrf_f64(_lib.ptr(bufs["S"]), None, None, _lib.ptr(bufs["info_root"]), B, d["nt"], _lib.ptr(bufs["ws"]),
@@ -240,8 +254,8 @@ class BaspachoSparseSolver(LinearSolver):
         lib = _lib.load()
         rhs = rhs.contiguous()
         x = torch.empty(B, P.n, dtype=torch.float64, device=rhs.device)
-        if layout == "lane":
-            _lib.check(lib.thb_sparse_lane_solve_f64(C.byref(d["lane"]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
+        if layout in ("lane", "lane_tiled"):
+            _lib.check(lib.thb_sparse_lane_solve_f64(C.byref(d[layout]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
                                                      _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "lane_solve")
         elif layout == "lane_root":
             s = _lib.stream_ptr()
