@@ -26,3 +26,15 @@ print(f"launches: {len(kinds)} (TU {int((kinds==4).sum())}, U {int((kinds==0).su
       f"vs plain lane {len(P.lane['launches'])}")
 heavy = lane["launches"][kinds == 3]
 print("largest remaining per-block pair list:", int((lane["u_p1"] - lane["u_p0"]).max()) if len(lane["u_p0"]) else 0)
+
+# the same with the dense root split off (layout lane_tiled_root): the root's assembly is ONE tile launch
+from theseus_b200.sparse import root_split
+sp = root_split(P)
+lane, tiles = tile_lane_lists(P, sp)
+kinds = lane["launches"][:, 0]
+last_tu = [l for l in lane["launches"] if l[0] == 4][-1]
+steps = np.diff(tiles["step_ptr"])
+asm = steps[last_tu[3]:last_tu[4]]
+print(f"with root split at column {sp['cut']} (root {sp['root_dof']} dof): launches {len(kinds)} (TU {int((kinds==4).sum())}, U {int((kinds==0).sum())}, "
+      f"UH {int((kinds==3).sum())}, T {int((kinds==1).sum())}, S {int((kinds==2).sum())}); tiles {tiles['tile_tgt'].shape[0]}, k steps {tiles['step_src'].shape[0]}; "
+      f"bottom tiles: max {int(steps[:last_tu[3]].max())} steps; root assembly launch: {len(asm)} tiles, {int(asm.sum())} steps, max {int(asm.max())} per tile")

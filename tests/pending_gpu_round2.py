@@ -114,9 +114,10 @@ def test_lane_root_layout_matches_lane_layout():
         assert np.abs(xs["lane_root"][k] - xs["lane"][k]).max() < 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(xs["lane"][k]).max())
 
 
+@pytest.mark.parametrize("tiled", ["lane_tiled", "lane_tiled_root"])
 @pytest.mark.parametrize("B", [32, 70])
-def test_lane_tiled_layout_matches_lane_layout(B):
-    """Opt-in layout='lane_tiled' (external updates of chain pieces as 4x4 tiles with the source blocks staged in shared memory,
+def test_lane_tiled_layout_matches_lane_layout(B, tiled):
+    """Opt-in layouts 'lane_tiled' / 'lane_tiled_root' (the latter: + dense root, its assembly as one tile launch) (external updates of chain pieces as 4x4 tiles with the source blocks staged in shared memory,
     thb_sparse_lane.cu:lane_tile_update_kernel) against the plain lane layout and the dense residual; same ring-with-chords structure
     (its elimination tree has chains of every width up to the dense separator).  The host half (flat tile arrays) is verified on the
     CPU: tests/test_sparse_symbolic.py::test_tiled_lane_lists_solve_system."""
@@ -131,12 +132,13 @@ def test_lane_tiled_layout_matches_lane_layout(B):
     b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
     alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
     xs = {}
-    for layout in ("lane_tiled", "lane"):
+    for layout in (tiled, "lane"):
         solver = th.BaspachoSparseSolver.from_structure(S, layout=layout)
         solver.linearization.A_val, solver.linearization.b = A_val, b
         xs[layout] = (solver.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-6).cpu().numpy(), solver.solve().cpu().numpy())
-        if layout == "lane_tiled":
+        if layout == tiled:
             assert solver._tiles[1]["tile_tgt"].shape[0] > 0
+    xs["lane_tiled"] = xs[tiled]
     AtA, Atb = _dense_system(S, A_val, b)
     idx = np.arange(S.num_cols)
     for k, (mul, add) in enumerate(((1 + alpha.cpu().numpy()[:, None], 1e-6), (1.0, 0.0))):

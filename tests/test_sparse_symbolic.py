@@ -71,6 +71,24 @@ def run_plan_numpy(plan, M, rhs):
     return x
 
 
+def apply_tiles_numpy(F, tiles, b0, b1, di, dj):
+    """Launch row (TU, 6, 6, b0, b1): what lane_tile_update_kernel<6,4,4> does to the factor storage."""
+    TR, TC, D = 4, 4, 6
+    assert di == D and dj == D
+    for t in range(b0, b1):
+        tg = tiles["tile_tgt"][t]
+        acc = {w: F[tg[w]:tg[w] + D * D].reshape(D, D).copy() for w in range(TR * TC) if tg[w] >= 0}
+        assert tiles["step_ptr"][t + 1] > tiles["step_ptr"][t]
+        for st in range(tiles["step_ptr"][t], tiles["step_ptr"][t + 1]):
+            src = tiles["step_src"][st]
+            for w in acc:
+                ro, co = src[w // TC], src[TR + w % TC]
+                if ro >= 0 and co >= 0:
+                    acc[w] -= F[ro:ro + D * D].reshape(D, D) @ F[co:co + D * D].reshape(D, D).T
+        for w, V in acc.items():
+            F[tg[w]:tg[w] + D * D] = V.reshape(-1)
+
+
 def run_lane_plan_numpy(plan, M, rhs, lane=None, tiles=None):
     """Interpret plan.lane (the work lists of thb_sparse_lane.cu) in launch order: U / UH = left-looking update of a block,
     T = Cholesky of the column's diagonal block (to `diagl`, reciprocal diagonal) + triangular solve of the block, S = substitutions,
@@ -97,20 +115,7 @@ def run_lane_plan_numpy(plan, M, rhs, lane=None, tiles=None):
                     T -= F[A["up_a"][p]:A["up_a"][p] + di * dk].reshape(di, dk) @ F[A["up_b"][p]:A["up_b"][p] + dj * dk].reshape(dj, dk).T
                 F[tgt:tgt + di * dj] = T.reshape(-1)
         elif kind == 4:
-            TR, TC, D = 4, 4, 6
-            assert di == D and dj == D
-            for t in range(b0, b1):
-                tg = tiles["tile_tgt"][t]
-                acc = {w: F[tg[w]:tg[w] + D * D].reshape(D, D).copy() for w in range(TR * TC) if tg[w] >= 0}
-                assert tiles["step_ptr"][t + 1] > tiles["step_ptr"][t]
-                for st in range(tiles["step_ptr"][t], tiles["step_ptr"][t + 1]):
-                    src = tiles["step_src"][st]
-                    for w in acc:
-                        ro, co = src[w // TC], src[TR + w % TC]
-                        if ro >= 0 and co >= 0:
-                            acc[w] -= F[ro:ro + D * D].reshape(D, D) @ F[co:co + D * D].reshape(D, D).T
-                for w, V in acc.items():
-                    F[tg[w]:tg[w] + D * D] = V.reshape(-1)
+            apply_tiles_numpy(F, tiles, b0, b1, di, dj)
         elif kind == 1:
             diag_writes = {}
             for e in range(b0, b1):   # every item reads the PRE-factor diagonal block: collect, then write
@@ -286,10 +291,10 @@ def test_native_symbolic_equals_python_specification(sizes, fill, ordering):
     assert (a.N, a.n, a.data_size, a.winv_size) == (b.N, b.n, b.data_size, b.winv_size)
 
 
-def run_root_split_numpy(plan, sp, M, rhs):
+def run_root_split_numpy(plan, sp, M, rhs, lane=None, tiles=None):
     """Interpret sparse.root_split: lane work lists for the columns below the cut, then the dense root (Schur complement assembled from
     the bottom columns' update pairs, numpy Cholesky standing in for the dense DMMA kernel), substitutions split the same way."""
-    A, Ln = plan.arrays, sp["bottom"]
+    A, Ln = plan.arrays, (sp["bottom"] if lane is None else lane)   # `lane` (tile_lane_lists with a split): root assembly included
     N, dims, cs, cut = plan.N, plan.dims, plan.col_start, sp["cut"]
     F = np.zeros(plan.data_size)
     for (i, j), t in plan.blk_index.items():
@@ -308,6 +313,8 @@ def run_root_split_numpy(plan, sp, M, rhs):
         if kind in (0, 3):
             for e in range(b0, b1):
                 update(Ln["u_tgt"][e], di, dj, Ln["u_p0"][e], Ln["u_p1"][e])
+        elif kind == 4:
+            apply_tiles_numpy(F, tiles, b0, b1, di, dj)
         elif kind == 1:
             writes = {}
             for e in range(b0, b1):
@@ -322,7 +329,7 @@ def run_root_split_numpy(plan, sp, M, rhs):
                 DL[dl:dl + Lr.size] = Lr.reshape(-1)
     # root: assemble, copy to a dense matrix, factor densely
     blk_dims = {int(plan.blk_off[t]): (int(dims[i]), int(dims[j])) for (i, j), t in plan.blk_index.items()}
-    for e in range(len(sp["ru_tgt"])):
+    for e in range(len(sp["ru_tgt"]) if lane is None else 0):
         di, dj = blk_dims[int(sp["ru_tgt"][e])]
         update(sp["ru_tgt"][e], di, dj, sp["ru_p0"][e], sp["ru_p1"][e])
     nt = sp["root_dof"]
@@ -407,6 +414,23 @@ def test_root_split_solves_system():
     assert sp2 is not None and sp2["root_dof"] == 24
     assert np.abs(M @ run_root_split_numpy(plan, sp2, M, rhs) - rhs).max() < 1e-9
     assert root_split(plan, max_root_dof=12, min_root_cols=4) is None
+    # tiled bottom + tiled root assembly (layout lane_tiled_root): same answer from the flat lists
+    from theseus_b200.sparse import tile_lane_lists
+    for s_ in (sp, sp2):
+        lane, tiles = tile_lane_lists(plan, s_)
+        tu = [l for l in lane["launches"] if l[0] == 4]
+        assert tu and tuple(lane["launches"][-1][:1]) in ((4,), (0,), (3,))   # the assembly closes the list
+        assert all(j < s_["cut"] for l in lane["launches"] if l[0] == 2 for j in lane["s_col"][l[3]:l[4]])
+        assert np.abs(M @ run_root_split_numpy(plan, s_, M, rhs, lane=lane, tiles=tiles) - rhs).max() < 1e-9
+        # pairs: bottom columns complete, root blocks only their k < cut part
+        n_t = 0
+        for t in range(tiles["tile_tgt"].shape[0]):
+            tg = tiles["tile_tgt"][t]
+            for st in range(tiles["step_ptr"][t], tiles["step_ptr"][t + 1]):
+                src = tiles["step_src"][st]
+                n_t += sum(1 for w in range(16) if tg[w] >= 0 and src[w // 4] >= 0 and src[4 + w % 4] >= 0)
+        n_all = int((s_["bottom"]["u_p1"] - s_["bottom"]["u_p0"]).sum() + (s_["ru_p1"] - s_["ru_p0"]).sum())
+        assert n_t + int((lane["u_p1"] - lane["u_p0"]).sum()) == n_all
 
 
 def run_chain_tiles_numpy(plan, ct, M, rhs):

@@ -503,7 +503,7 @@ def root_lane_lists(plan: SparsePlan, sp) -> Tuple[Dict[str, np.ndarray], Dict[s
     return lane, root
 
 
-def chain_tiles(plan: SparsePlan, max_width: int = 4, tile_rows: int = 4):
+def chain_tiles(plan: SparsePlan, max_width: int = 4, tile_rows: int = 4, breaks=()):
     """Round-2 building block (host side, specification level: Python lists, checked by a numpy interpreter in
     tests/test_sparse_symbolic.py; no kernel consumes it yet).  The schedule of the TILED update stage:
 
@@ -540,7 +540,7 @@ def chain_tiles(plan: SparsePlan, max_width: int = 4, tile_rows: int = 4):
     while j < N:
         c = plan.chain_of[j]
         e = j
-        while e + 1 < N and plan.chain_of[e + 1] == c and e + 1 - j < max_width:
+        while e + 1 < N and plan.chain_of[e + 1] == c and e + 1 - j < max_width and (e + 1) not in breaks:   # breaks: forced piece starts
             e += 1
         piece_first[j:e + 1] = j
         j = e + 1
@@ -582,8 +582,9 @@ def chain_tiles(plan: SparsePlan, max_width: int = 4, tile_rows: int = 4):
 
 
 
-def tile_lane_lists(plan: SparsePlan) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
-    """Work lists of the opt-in `lane_tiled` layout: the chain_tiles schedule flattened for thb_sparse_lane_factor_tiled_f64.
+def tile_lane_lists(plan: SparsePlan, sp=None) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
+    """Work lists of the opt-in `lane_tiled` / `lane_tiled_root` layouts: the chain_tiles schedule flattened for
+    thb_sparse_lane_factor_tiled_f64.
 
     Tiles whose targets and sources are all TILE_DIM x TILE_DIM blocks become rows of the tile arrays
       tile_tgt  [T, TILE_ROWS*TILE_COLS]  offset of target block (row slot a, column slot b) at a*TILE_COLS+b, -1 if absent
@@ -591,8 +592,16 @@ def tile_lane_lists(plan: SparsePlan) -> Tuple[Dict[str, np.ndarray], Dict[str, 
       step_src  [S, TILE_ROWS+TILE_COLS]   offsets of the source blocks L_(row a),k (first TILE_ROWS entries) and L_(column b),k, -1 if zero
     and a launch row (LN_TU, 6, 6, first tile, one past last tile) opens the level of the piece's first column; the update pairs they
     cover (a prefix of each target's pair list) are dropped from the U / UH items.  Every other block keeps its full pair list.
+
+    With a root split `sp` (root_split): the columns below the cut as above; the root's ASSEMBLY (update pairs with k < cut into root
+    blocks: the Schur complement that the dense kernel factors) becomes ONE tile launch after the last bottom level -- every tile of a
+    root piece with its steps restricted to k < cut, all independent of each other -- followed by the per-block items of the root blocks
+    no tile covers.  (Without the split those tiles sit one piece per level at the top of the tree, a serial chain of long k loops.)
     Returns (lane lists, tile arrays)."""
-    ct = chain_tiles(plan, max_width=TILE_COLS, tile_rows=TILE_ROWS)
+    cut = plan.N
+    if sp is not None:
+        cut = int(sp["cut"])
+    ct = chain_tiles(plan, max_width=TILE_COLS, tile_rows=TILE_ROWS, breaks=(cut,))
     N, dims = plan.N, plan.dims
     up_ptr = ct["up_ptr"]
     nblk = len(plan.blk_off)
@@ -602,6 +611,7 @@ def tile_lane_lists(plan: SparsePlan) -> Tuple[Dict[str, np.ndarray], Dict[str, 
         blk_shape[t] = (dims[i], dims[j])
         blk_col[t] = j
     nlev = len(ct["per_level"])
+    level_cut = int(plan.level[cut]) if cut < N else nlev
     u_start = up_ptr[:-1].copy()
     tile_tgt, step_ptr, step_src = [], [0], []
     pre = [[] for _ in range(nlev)]
@@ -609,30 +619,67 @@ def tile_lane_lists(plan: SparsePlan) -> Tuple[Dict[str, np.ndarray], Dict[str, 
     A = plan.arrays
     src_blk = np.searchsorted(plan.blk_off, A["up_a"], side="right") - 1
     pair_k = blk_col[src_blk]
-    for lv in range(nlev):
+
+    def emit(tile, steps, k_end):
+        """Append one tile with the given steps; marks the pairs with k < k_end of its targets as done.  False if not all 6x6."""
+        ids = [t for (_, _, t) in tile["targets"]] + [x for (_, ro, co) in steps for x in ro + co if x >= 0]
+        if not steps or not all(blk_shape[t][0] == TILE_DIM and blk_shape[t][1] == TILE_DIM for t in ids):
+            return False
+        row = [-1] * (TILE_ROWS * TILE_COLS)
+        for (a, b, t) in tile["targets"]:
+            row[a * TILE_COLS + b] = int(plan.blk_off[t])
+            p0, p1 = int(up_ptr[t]), int(up_ptr[t + 1])
+            n_ext = int(np.searchsorted(pair_k[p0:p1], k_end, side="left"))
+            assert (pair_k[p0:p0 + n_ext] < k_end).all() and (pair_k[p0 + n_ext:p1] >= k_end).all()
+            u_start[t] = p0 + n_ext
+        tile_tgt.append(row)
+        for (_, ro, co) in steps:
+            co = list(co) + [-1] * (TILE_COLS - len(co))
+            step_src.append([int(plan.blk_off[x]) if x >= 0 else -1 for x in list(ro) + co])
+        step_ptr.append(len(step_src))
+        return True
+
+    for lv in range(min(nlev, level_cut)):
         t0 = len(tile_tgt)
         for tile in ct["per_level"][lv]["tiles"]:
-            ids = [t for (_, _, t) in tile["targets"]] + [x for (_, ro, co) in tile["steps"] for x in ro + co if x >= 0]
-            if not all(blk_shape[t][0] == TILE_DIM and blk_shape[t][1] == TILE_DIM for t in ids):
-                continue
-            row = [-1] * (TILE_ROWS * TILE_COLS)
-            j0 = tile["piece"][0]
-            for (a, b, t) in tile["targets"]:
-                row[a * TILE_COLS + b] = int(plan.blk_off[t])
-                p0, p1 = int(up_ptr[t]), int(up_ptr[t + 1])
-                n_ext = int(np.searchsorted(pair_k[p0:p1], j0, side="left"))
-                assert (pair_k[p0:p0 + n_ext] < j0).all() and (pair_k[p0 + n_ext:p1] >= j0).all()
-                u_start[t] = p0 + n_ext
-            tile_tgt.append(row)
-            for (_, ro, co) in tile["steps"]:
-                co = list(co) + [-1] * (TILE_COLS - len(co))
-                step_src.append([int(plan.blk_off[x]) if x >= 0 else -1 for x in list(ro) + co])
-            step_ptr.append(len(step_src))
+            assert tile["piece"][1] < cut
+            emit(tile, tile["steps"], tile["piece"][0])
         if len(tile_tgt) > t0:
             pre[lv].append((LN_TU, TILE_DIM, TILE_DIM, t0, len(tile_tgt)))
-    cols_by_level = [list(ct["per_level"][lv]["cols"]) for lv in range(nlev)]
-    lane = _lane_lists(N, nlev, cols_by_level, plan.struct, dims, plan.blk_index, plan.blk_off, up_ptr, plan.winv_off, plan.pstart,
+    nlev_bottom = min(nlev, level_cut)
+    cols_by_level = [[j for j in ct["per_level"][lv]["cols"]] for lv in range(nlev_bottom)]
+    assert all(j < cut for L in cols_by_level for j in L)
+    lane = _lane_lists(N, nlev_bottom, cols_by_level, plan.struct, dims, plan.blk_index, plan.blk_off, up_ptr, plan.winv_off, plan.pstart,
                        u_start=u_start, pre_launches=pre)
+    if sp is not None:
+        u_tgt, u_p0, u_p1 = list(lane["u_tgt"]), list(lane["u_p0"]), list(lane["u_p1"])
+        launches = [tuple(int(x) for x in row) for row in lane["launches"]]
+        t0 = len(tile_tgt)
+        for lv in range(level_cut, nlev):
+            for tile in ct["per_level"][lv]["tiles"]:
+                assert tile["piece"][0] >= cut
+                emit(tile, [st for st in tile["steps"] if st[0] < cut], cut)
+        if len(tile_tgt) > t0:
+            launches.append((LN_TU, TILE_DIM, TILE_DIM, t0, len(tile_tgt)))
+        # root blocks no tile covers: their assembly pairs (k < cut) stay per block, grouped by shape like every U launch
+        off_to_blk = {int(o): t for t, o in enumerate(plan.blk_off)}
+        cls: Dict[Tuple[int, int, int], list] = {}
+        for e in range(len(sp["ru_tgt"])):
+            t = off_to_blk[int(sp["ru_tgt"][e])]
+            assert int(sp["ru_p0"][e]) == int(up_ptr[t])
+            first = int(u_start[t])
+            if first < int(sp["ru_p1"][e]):
+                assert first == int(sp["ru_p0"][e])   # a root block is covered by a tile entirely or not at all
+                heavy = 1 if int(sp["ru_p1"][e]) - first >= LANE_HEAVY else 0
+                cls.setdefault((heavy, int(blk_shape[t][0]), int(blk_shape[t][1])), []).append(e)
+        for (heavy, di, dj) in sorted(cls):
+            b0 = len(u_tgt)
+            for e in cls[(heavy, di, dj)]:
+                u_tgt.append(int(sp["ru_tgt"][e])); u_p0.append(int(sp["ru_p0"][e])); u_p1.append(int(sp["ru_p1"][e]))
+            launches.append((LN_UH if heavy else LN_U, di, dj, b0, len(u_tgt)))
+        i64 = np.int64
+        lane.update(u_tgt=np.array(u_tgt, dtype=i64), u_p0=np.array(u_p0, dtype=i64), u_p1=np.array(u_p1, dtype=i64),
+                    launches=np.array(launches, dtype=np.int32).reshape(-1, 5))
     lane.update(fr_p=plan.lane["fr_p"], fr_d=plan.lane["fr_d"], bc_p=plan.lane["bc_p"], bc_d=plan.lane["bc_d"])
     i64 = np.int64
     tiles = dict(tile_tgt=np.array(tile_tgt, dtype=i64).reshape(-1, TILE_ROWS * TILE_COLS), step_ptr=np.array(step_ptr, dtype=i64),

@@ -20,6 +20,10 @@ from .sparse import LANE_DIMS, analyze, gram_out_offsets, root_lane_lists, root_
 from .structure import ata_block_structure, build_gram_plan
 
 
+_ROOT_LAYOUTS = ("lane_root", "lane_tiled_root")     # dense DMMA factorisation of the top chain of the elimination tree
+_TILED_LAYOUTS = ("lane_tiled", "lane_tiled_root")   # supernodal tile kernel for the external updates of chain pieces
+
+
 class BaspachoSparseSolver(LinearSolver):
     def __init__(self, objective: Objective, linearization_cls: Optional[Type[Linearization]] = None,
                  linearization_kwargs: Optional[Dict[str, Any]] = None, num_solver_contexts=1, batch_size: Optional[int] = None,
@@ -70,12 +74,12 @@ class BaspachoSparseSolver(LinearSolver):
         thb_sparse.cu).  Default: lane whenever a warp can be filled and every block size is one the lane kernels are built for."""
         lane_ok = all(int(d) in LANE_DIMS for d in self._plan.dims)
         if self._layout is not None:
-            if self._layout not in ("lane", "item", "lane_root", "lane_tiled"):
-                raise ValueError(f"layout must be 'lane', 'item', 'lane_root' or 'lane_tiled', got {self._layout}")
+            if self._layout not in ("lane", "item", "lane_root", "lane_tiled", "lane_tiled_root"):
+                raise ValueError(f"layout must be 'lane', 'item', 'lane_root', 'lane_tiled' or 'lane_tiled_root', got {self._layout}")
             if self._layout != "item" and not lane_ok:
                 raise ValueError(f"layout='{self._layout}' needs block sizes in {LANE_DIMS}")
-            if self._layout == "lane_root" and self._root_split() is None:
-                raise ValueError("layout='lane_root': this structure has no dense root (top chain too short)")
+            if self._layout in _ROOT_LAYOUTS and self._root_split() is None:
+                raise ValueError(f"layout='{self._layout}': this structure has no dense root (top chain too short)")
             return self._layout
         return "lane" if (lane_ok and B >= 32) else "item"
 
@@ -106,9 +110,8 @@ class BaspachoSparseSolver(LinearSolver):
         ln = P.lane
         lst, ldev, launches = self._lane_struct(ln, dev, device)
         self._dev = dict(device=device, plan=st, keep=dev, gram=gst, gkeep=gdev, bufs={}, lane=lst, lkeep=(ldev, launches))
-        if self._layout == "lane_root":
+        if self._layout in _ROOT_LAYOUTS:
             sp, rl, rr = self._root_split()
-            rst, rdev, rlaunch = self._lane_struct(rl, dev, device)
             qdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in rr.items() if isinstance(v, np.ndarray) and k != "segments"}
             segs = np.ascontiguousarray(rr["segments"], dtype=np.int32)
             qst = _lib.SparseLaneRootStruct(
@@ -116,15 +119,18 @@ class BaspachoSparseSolver(LinearSolver):
                 num_segments=int(segs.shape[0]), segments=segs.ctypes.data, rb_off=qdev["rb_off"].data_ptr(), rb_row=qdev["rb_row"].data_ptr(),
                 rb_col=qdev["rb_col"].data_ptr(), rb_di=qdev["rb_di"].data_ptr(), rb_dj=qdev["rb_dj"].data_ptr(), rf_p0=qdev["rf_p0"].data_ptr(),
                 rf_p1=qdev["rf_p1"].data_ptr(), root_cols=qdev["root_cols"].data_ptr(), root_dims=qdev["root_dims"].data_ptr())
-            self._dev.update(lane_root=rst, root=qst, rkeep=(rdev, rlaunch, qdev, segs), nt=int(rr["nt"]))
-        if self._layout == "lane_tiled":
+            self._dev.update(root=qst, qkeep=(qdev, segs), nt=int(rr["nt"]))
+            if self._layout == "lane_root":
+                rst, rdev, rlaunch = self._lane_struct(rl, dev, device)
+                self._dev.update(lane_root=rst, rkeep=(rdev, rlaunch))
+        if self._layout in _TILED_LAYOUTS:
             tl, tt = self._tile_lists()
             tst, tdev, tlaunch = self._lane_struct(tl, dev, device)
             ttdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in tt.items()}
             tiles = _lib.SparseLaneTilesStruct(num_tiles=int(tt["tile_tgt"].shape[0]), num_steps=int(tt["step_src"].shape[0]),
                                                tile_tgt=ttdev["tile_tgt"].data_ptr(), step_ptr=ttdev["step_ptr"].data_ptr(),
                                                step_src=ttdev["step_src"].data_ptr())
-            self._dev.update(lane_tiled=tst, tiles=tiles, tkeep=(tdev, tlaunch, ttdev))
+            self._dev.update({self._layout: tst}, tiles=tiles, tkeep=(tdev, tlaunch, ttdev))
         return self._dev
 
     def _lane_struct(self, ln, dev, device):
@@ -146,9 +152,9 @@ class BaspachoSparseSolver(LinearSolver):
         return lst, ldev, launches
 
     def _tile_lists(self):
-        """Work lists of the opt-in layout 'lane_tiled' (sparse.tile_lane_lists), computed on first use."""
+        """Work lists of the opt-in layouts 'lane_tiled' / 'lane_tiled_root' (sparse.tile_lane_lists), computed on first use."""
         if not hasattr(self, "_tiles"):
-            self._tiles = tile_lane_lists(self._plan)
+            self._tiles = tile_lane_lists(self._plan, self._root_split()[0] if self._layout in _ROOT_LAYOUTS else None)
         return self._tiles
 
     # ---- numeric phase (baspacho_sparse_autograd.py:21-65) ----
@@ -207,7 +213,7 @@ class BaspachoSparseSolver(LinearSolver):
                              work=torch.empty(shape(P.n), dtype=torch.float64, device=device),
                              Atb=torch.empty(B, P.n, dtype=torch.float64, device=device),
                              info=torch.empty(B, dtype=torch.int32, device=device))
-            if layout == "lane_root":
+            if layout in _ROOT_LAYOUTS:
                 nt = d["nt"]
                 d["bufs"].update(S=torch.empty(B, nt, nt, dtype=torch.float64, device=device),
                                  ws=torch.empty(int(lib.thb_potrf_workspace_bytes(B, nt)), dtype=torch.uint8, device=device),
@@ -220,18 +226,18 @@ class BaspachoSparseSolver(LinearSolver):
         self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
         # every structurally non-zero block of L that is not in AtA (fill-in) must start at zero
         _lib.check(lib.thb_fill_zero(_lib.ptr(factor), factor.numel() * 8, s), "fill_zero")
-        if layout in ("lane", "lane_root", "lane_tiled"):
-            lplan = d[layout]   # lane_root: launch list = bottom columns + the root's assembly updates; lane_tiled: + tile launches
+        if layout != "item":
+            lplan = d[layout]   # *_root: launch list = bottom columns + the root's assembly updates; lane_tiled*: + tile launches
             _lib.check(lib.thb_sparse_lane_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(factor), s), "gram(lane)")
             _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, None, 0, _lib.ptr(Atb), None, s), "Atb")
             if alpha is not None:
                 _lib.check(lib.thb_sparse_lane_damp_f64(C.byref(d["lane"]), _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta), B, s), "lane_damp")
-            if layout == "lane_tiled":
+            if layout in _TILED_LAYOUTS:
                 _lib.check(lib.thb_sparse_lane_factor_tiled_f64(C.byref(lplan), C.byref(d["tiles"]), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info),
                                                                 B, s), "lane_factor_tiled")
             else:
                 _lib.check(lib.thb_sparse_lane_factor_f64(C.byref(lplan), _lib.ptr(factor), _lib.ptr(diag), _lib.ptr(info), B, s), "lane_factor")
-            if layout == "lane_root":   # dense root: copy the assembled Schur complement out and factor it on the DMMA kernel
+            if layout in _ROOT_LAYOUTS:   # dense root: copy the assembled Schur complement out and factor it on the DMMA kernel
                 _lib.check(lib.thb_sparse_lane_root_gather_f64(C.byref(d["root"]), _lib.ptr(factor), _lib.ptr(bufs["S"]), B, s), "root_gather")
                 _lib.check(lib.thb_potrf_f64(_lib.ptr(bufs["S"]), None, None, _lib.ptr(bufs["info_root"]), B, d["nt"], _lib.ptr(bufs["ws"]),
                                              bufs["ws"].numel(), s), "root_potrf")
@@ -257,9 +263,9 @@ class BaspachoSparseSolver(LinearSolver):
         if layout in ("lane", "lane_tiled"):
             _lib.check(lib.thb_sparse_lane_solve_f64(C.byref(d[layout]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
                                                      _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "lane_solve")
-        elif layout == "lane_root":
+        elif layout in _ROOT_LAYOUTS:
             s = _lib.stream_ptr()
-            lp, rt = C.byref(d["lane_root"]), C.byref(d["root"])
+            lp, rt = C.byref(d[layout]), C.byref(d["root"])
             F, D, W = _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(bufs["work"])
             _lib.check(lib.thb_sparse_lane_forward_f64(lp, F, D, _lib.ptr(rhs), W, B, s), "lane_forward")
             _lib.check(lib.thb_sparse_lane_root_rhs_f64(lp, rt, F, _lib.ptr(rhs), W, _lib.ptr(bufs["rhs_root"]), B, s), "root_rhs")
