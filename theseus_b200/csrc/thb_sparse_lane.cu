@@ -633,8 +633,13 @@ static int lane_factor_impl(const thb_sparse_lane_plan* p, const thb_sparse_lane
       constexpr int TR = THB_TILE_ROWS, TC = THB_TILE_COLS;
       constexpr int smem = 2 * (TR + TC) * 36 * 32 * (int)sizeof(double);
       auto kern = thb::lane_tile_update_kernel<6, TR, TC>;
-      static bool smem_opted_in = false;   // idempotent; not a stream operation (legal under CUDA-graph capture)
-      if (!smem_opted_in) { THB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_opted_in = true; }
+      static bool smem_opted_in[64] = {};   // per device; idempotent, not a stream operation (legal under CUDA-graph capture)
+      int dev = 0;
+      THB_CUDA(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !smem_opted_in[dev]) {
+        THB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (dev >= 0 && dev < 64) smem_opted_in[dev] = true;
+      }
       thb::LaneTileArgs ta;
       ta.tile_tgt = tiles->tile_tgt; ta.step_ptr = tiles->step_ptr; ta.step_src = tiles->step_src;
       ta.begin = a.begin; ta.Bp = a.Bp;
