@@ -109,21 +109,46 @@ def reprojection_error_jacobians(X, p, f, z, k1, k2, want_jac=True):
     return [Jp[..., :6], Jp[..., 6:]], err
 
 
-def robust_apply(robust, jacs, e):
-    """theseus/core/robust_cost_function.py:87-135 with the losses of robust_loss.py:33-52.
-    robust = (kind, log_radius [..,1]); e weighted error [...,dim].  With jacs: linearisation rescale; without: the
-    'hacky' error whose squared norm equals rho(||e||^2)."""
-    kind, log_radius = robust
-    radius = np.exp(log_radius)
-    x = (e ** 2).sum(axis=-1, keepdims=True)
-    if jacs is not None:
-        lin = np.exp(-x / (radius + 1e-20)) if kind == "welsch" else np.sqrt(radius / np.maximum(x, radius) + 1e-20)
-        sc = np.sqrt(lin + 1e-20)
-        return [sc[..., None] * J for J in jacs], sc * e
+def _robust_rho(kind, x, radius, mu):
+    """rho(x) of robust_loss.py:33-118 (x = squared norm, radius = exp(log_radius), mu = GNC control value of Geman-McClure)."""
     if kind == "welsch":
-        val = radius - radius * np.exp(-x / (radius + 1e-20))
-    else:
-        val = np.where(x > radius, 2 * np.sqrt(radius * np.maximum(x, radius) + 1e-20) - radius, x)
+        return radius - radius * np.exp(-x / (radius + 1e-20))
+    if kind == "huber":
+        return np.where(x > radius, 2 * np.sqrt(radius * np.maximum(x, radius) + 1e-20) - radius, x)
+    if kind == "hinge":
+        return np.where(x > radius, np.sqrt(x) - np.sqrt(radius), 1e-20)
+    if kind == "geman":
+        return mu * radius * x / (mu * radius + x + 1e-20)
+    raise ValueError(kind)
+
+
+def _robust_drho(kind, x, radius, mu):
+    """rho'(x) as the reference's `linearize` gives it (same lines)."""
+    if kind == "welsch":
+        return np.exp(-x / (radius + 1e-20))
+    if kind == "huber":
+        return np.sqrt(radius / np.maximum(x, radius) + 1e-20)
+    if kind == "hinge":
+        return np.where(x > radius, 1.0 / (2 * np.sqrt(x) + 1e-20), 0.0)
+    if kind == "geman":
+        return (mu * radius) ** 2 / ((mu * radius + x) ** 2 + 1e-20)
+    raise ValueError(kind)
+
+
+def robust_apply(robust, jacs, e, flatten_dims=False):
+    """theseus/core/robust_cost_function.py:87-135 with the losses of robust_loss.py:33-118.
+    robust = (kind, log_radius [..,1]) or (kind, log_radius, mu); e weighted error [...,dim].  With jacs: linearisation rescale;
+    without: the 'hacky' error whose squared norm equals rho(||e||^2).  flatten_dims: the loss per error dimension."""
+    kind, log_radius = robust[0], robust[1]
+    mu = robust[2] if len(robust) > 2 else None
+    radius = np.exp(log_radius)
+    x = e ** 2 if flatten_dims else (e ** 2).sum(axis=-1, keepdims=True)
+    if jacs is not None:
+        sc = np.sqrt(_robust_drho(kind, x, radius, mu) + 1e-20)
+        return [sc[..., None] * J for J in jacs], sc * e
+    val = _robust_rho(kind, x, radius, mu)
+    if flatten_dims:
+        return None, np.sqrt(val + 1e-20)
     return None, np.ones_like(e) * np.sqrt(val / e.shape[-1] + 1e-20)
 
 
@@ -150,8 +175,9 @@ def eval_costs(spec, values, want_jac=True):
     def put(f, jac_list, err):
         c = spec["costs"][f]
         if c.get("robust") is not None:
-            rk, lr = c["robust"]
-            jac_list, err = robust_apply((rk, _bcast(np.asarray(lr, dtype=dt), B)), jac_list, err)
+            rk, lr = c["robust"][0], c["robust"][1]
+            extra = tuple(_bcast(np.asarray(m, dtype=dt), B) for m in c["robust"][2:])   # GNC control value (Geman-McClure)
+            jac_list, err = robust_apply((rk, _bcast(np.asarray(lr, dtype=dt), B)) + extra, jac_list, err)
         out[f] = (jac_list, err)
 
     for (kind, grp, wkind), idx in groups.items():

@@ -131,6 +131,10 @@ def _pgo_objective(th, num_poses, B, seed, dtype, loop_closure_ratio=0.2, init_p
         cf = th.Between(pg.poses[edge.i], pg.poses[edge.j], edge.relative_pose, edge.weight)
         if robust == "welsch":  # as examples/pose_graph/pose_graph_synthetic.py builds its robust relative-pose costs
             cf = th.RobustCostFunction(cf, th.WelschLoss, log_loss_radius, name=f"robust_{cf.name}")
+        elif robust == "geman":  # graduated non-convexity wrapper, control value 3
+            if not objective.has_aux_var("gnc_mu"):
+                gnc_mu = th.Vector(tensor=torch.tensor([[3.0]], dtype=dtype), name="gnc_mu")
+            cf = th.GNCRobustCostFunction(cf, th.GemanMcClureLoss, log_loss_radius, gnc_mu, name=f"robust_{cf.name}")
         objective.add(cf)
     prior = th.Difference(var=pg.poses[0], cost_weight=th.ScaleCostWeight(torch.tensor(1e-3, dtype=dtype)),
                           target=pg.poses[0].copy(new_name=pg.poses[0].name + "__PRIOR"))
@@ -152,6 +156,8 @@ def make_pgo(th, name, num_poses, B, seed, iters, lm_kwargs, method="lm", full_t
     out["prior_w"] = np.array(1e-3)
     out["robust"] = np.array(robust or "")
     out["log_loss_radius"] = np.array([[0.5]])
+    if robust == "geman":
+        out["gnc_mu"] = np.array([[3.0]])
     cls = {"lm": th.LevenbergMarquardt, "gn": th.GaussNewton, "dogleg": th.Dogleg}[method]
     opt = cls(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=iters,
               step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0)
@@ -682,6 +688,46 @@ def make_moving_frame(th):
     print("moving_frame_kat", {k: v.shape for k, v in out.items()})
 
 
+def make_robust(th):
+    """RobustCostFunction / GNCRobustCostFunction (core/robust_cost_function.py, core/robust_loss.py) around Between(SE3) and a Vector
+    Difference: weighted Jacobians + error (linearisation rescale) and weighted_error (the loss value spread over `dim` entries), for every
+    loss of the reference, with and without flatten_dims.  Squared norms straddle the radius (both branches of Huber / Hinge)."""
+    import torch
+    torch.manual_seed(17)
+    d = torch.float64
+    B = 8
+    X0, X1 = th.SE3.rand(B, dtype=d), th.SE3.rand(B, dtype=d)
+    # measurements close to / far from the current relative pose: small and large residuals
+    scale = torch.tensor([1e-3, 0.05, 0.2, 0.5, 1.0, 2.0, 0.3, 0.7], dtype=d).view(B, 1)
+    Z = th.SE3(tensor=X0.between(X1).compose(th.SE3.exp_map(scale * (2 * torch.rand(B, 6, dtype=d) - 1))).tensor)
+    w = torch.rand(1, 6, dtype=d) + 0.5
+    log_radius = torch.tensor([[-0.7]], dtype=d)
+    mu = torch.tensor([[3.0]], dtype=d)
+    V, Vt = th.Vector(tensor=torch.randn(B, 4, dtype=d) * scale), th.Vector(tensor=torch.zeros(B, 4, dtype=d))
+    wv = torch.tensor(1.3, dtype=d)
+    out = dict(X0=X0.tensor.numpy(), X1=X1.tensor.numpy(), Z=Z.tensor.numpy(), w=w.numpy(), log_radius=log_radius.numpy(), mu=mu.numpy(),
+               V=V.tensor.numpy(), Vt=Vt.tensor.numpy(), wv=np.array(float(wv)))
+    losses = dict(welsch=th.WelschLoss, huber=th.HuberLoss, hinge=th.HingeLoss, geman=th.GemanMcClureLoss)
+    for name, cls in losses.items():
+        for flat in (False, True):
+            for cname, inner in (("between", lambda: th.Between(X0, X1, Z, th.DiagonalCostWeight(w))),
+                                 ("vecdiff", lambda: th.Difference(V, Vt, th.ScaleCostWeight(wv)))):
+                lr = th.Vector(tensor=log_radius.clone(), name=f"lr_{name}_{flat}_{cname}")
+                if name == "geman":
+                    cf = th.GNCRobustCostFunction(inner(), cls, lr, th.Vector(tensor=mu.clone(), name=f"mu_{flat}_{cname}"), flatten_dims=flat)
+                else:
+                    cf = th.RobustCostFunction(inner(), cls, lr, flatten_dims=flat)
+                jacs, e = cf.weighted_jacobians_error()
+                key = f"{name}_{'flat' if flat else 'full'}_{cname}"
+                out[key + "_J"] = np.stack([j.numpy() for j in jacs], 0)
+                out[key + "_e"] = e.numpy()
+                out[key + "_val"] = cf.weighted_error().numpy()
+    x = (th.Between(X0, X1, Z, th.DiagonalCostWeight(w)).weighted_error() ** 2).sum(1)
+    print("robust_kat: squared norms", x.numpy().round(4), "radius", float(log_radius.exp()))
+    np.savez_compressed(os.path.join(HERE, "robust_kat.npz"), **out)
+    print("robust_kat", len(out), "arrays")
+
+
 def tactile_problem(th, torch, inputs, device="cpu"):
     """A planar-pushing (tactile-style, config C4's cost set) objective shared by generator and tests: T object poses o_t and T
     effector poses e_t (SE2); per step: EffectorObjectContactPlanar(o_t, e_t), Difference(e_t, measured effector pose);
@@ -854,6 +900,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "io":
         make_io(th)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "robust":
+        make_robust(th)
+        make_pgo(th, "pgo_small_geman", num_poses=10, B=3, seed=13, iters=8, lm_kwargs=dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True),
+                 loop_closure_ratio=0.6, robust="geman", outlier_ratio=0.3, init_perturb=0.0)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "backward_lie":
         make_backward_lie(th)
         sys.exit(0)
@@ -885,3 +936,6 @@ if __name__ == "__main__":
     make_backward_pgo(th)
     make_moving_frame(th)
     make_tactile(th)
+    make_robust(th)
+    make_pgo(th, "pgo_small_geman", num_poses=10, B=3, seed=13, iters=8, lm_kwargs=lm, loop_closure_ratio=0.6, robust="geman",
+             outlier_ratio=0.3, init_perturb=0.0)

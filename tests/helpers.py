@@ -32,7 +32,7 @@ def pgo_spec(g, dtype=np.float64):
         c = dict(kind="between", group="SE3", vars=(int(edges[e, 0]), int(edges[e, 1])),
                  aux=meas[e].astype(dtype), weight=("diag", edge_w[e].astype(dtype)))
         if robust:
-            c["robust"] = (robust, g["log_loss_radius"].astype(dtype))
+            c["robust"] = (robust, g["log_loss_radius"].astype(dtype)) + ((g["gnc_mu"].astype(dtype),) if robust == "geman" else ())
         spec["costs"].append(c)
     spec["costs"].append(dict(kind="local", group="SE3", vars=(0,), aux=poses0[0].astype(dtype),
                               weight=("scale", np.full((1, 1), float(g["prior_w"]), dtype=dtype))))
@@ -53,8 +53,12 @@ def pgo_objective(th, g, device="cuda", dtype=None):
         z = th.SE3(tensor=torch.from_numpy(meas[e]).to(dtype), name=f"EDGE_SE3__{e}_{i}_{j}")
         w = th.DiagonalCostWeight(th.Variable(torch.from_numpy(edge_w[e]).to(dtype), name=f"EDGE_WEIGHT__{e}"))
         cf = th.Between(poses[i], poses[j], z, w, name=f"between_{e}")
-        if robust:
-            cf = th.RobustCostFunction(cf, th.WelschLoss, llr, name=f"robust_between_{e}")
+        if robust == "geman":
+            mu = th.Vector(tensor=torch.from_numpy(g["gnc_mu"]).to(dtype), name="gnc_mu")
+            cf = th.GNCRobustCostFunction(cf, th.GemanMcClureLoss, llr, mu, name=f"robust_between_{e}")
+        elif robust:
+            cf = th.RobustCostFunction(cf, dict(welsch=th.WelschLoss, huber=th.HuberLoss, hinge=th.HingeLoss)[robust], llr,
+                                       name=f"robust_between_{e}")
         objective.add(cf)
     prior = th.Difference(poses[0], th.SE3(tensor=torch.from_numpy(poses0[0]).to(dtype), name="VERTEX_SE3__0__PRIOR"),
                           th.ScaleCostWeight(torch.tensor(float(g["prior_w"]), dtype=dtype)), name="prior")

@@ -147,3 +147,23 @@ def test_lane_tiled_layout_matches_lane_layout(B, tiled):
         res = np.einsum("bij,bj->bi", M, xs["lane_tiled"][k]) - Atb
         assert np.abs(res).max() < 1e-10 * np.abs(M).sum(axis=2).max() * max(1.0, np.abs(xs["lane_tiled"][k]).max())
         assert np.abs(xs["lane_tiled"][k] - xs["lane"][k]).max() < 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(xs["lane"][k]).max())
+
+
+def test_gnc_robust_costs_on_the_generic_route_match_reference_trace():
+    """GNCRobustCostFunction(Between, GemanMcClureLoss) has no fused kernel: the engine's generic route (torch.func Jacobians of the wrapped
+    Between, rescaled in torch: core.RobustCostFunction.generic_jacobians_error / generic_error) must reproduce the reference's LM trace
+    (tests/golden/pgo_small_geman.npz).  The torch functions themselves are checked on the CPU (tests/test_robust_losses.py), the oracle's
+    trace in tests/test_oracle_nls.py."""
+    from test_gpu_lm import _run
+    g = load("pgo_small_geman")
+    method, iters, kw, values, info, trace, poses, inputs = _run(g)
+    np.testing.assert_allclose(np.stack(trace["err"], 0), g["trace_err"], rtol=1e-8)
+    from helpers import pgo_spec
+    from oracle import nls
+    spec = pgo_spec(g)
+    err0 = nls.error_metric(spec, [v["value"] for v in spec["vars"]])
+    for it in range(decisive_iterations(err0, g["trace_err"])):
+        dref = g["trace_delta"][it]
+        rel = np.linalg.norm(trace["delta"][it] - dref, axis=1) / np.linalg.norm(dref, axis=1)
+        assert rel.max() < 1e-5, (it, rel)
+        np.testing.assert_allclose(trace["lam"][it], g["trace_lam"][it], rtol=1e-12)

@@ -271,31 +271,96 @@ class Reprojection(CostFunction):
         return COST_REPROJECTION, [self.focal_length, self.image_feature_point, self.calib_k1, self.calib_k2]
 
 
+_LOSS_EPS = 1e-20
+
+
 class RobustLoss:
-    """theseus/core/robust_loss.py:13-30 (only the kind is needed on the host; the formulas live in thb_costs.cu)."""
+    """theseus/core/robust_loss.py:13-30.  x = squared norm of the weighted error, radius = exp(log_radius).  Welsch and Huber are fused
+    into the linearize / error kernels (ROBUST_KIND = the kernels' enum, thb_costs.cu); every loss also has its torch form below, used
+    by the generic (torch.func) route and by the taped linearization of the backward modes."""
     ROBUST_KIND = 0
+    FUSED = False   # True: thb_costs.cu has the formulas
+
+    @classmethod
+    def evaluate(cls, x: torch.Tensor, log_radius: torch.Tensor, *extra: torch.Tensor) -> torch.Tensor:
+        return cls._evaluate_impl(x, log_radius.exp(), *extra)
+
+    @classmethod
+    def linearize(cls, x: torch.Tensor, log_radius: torch.Tensor, *extra: torch.Tensor) -> torch.Tensor:
+        return cls._linearize_impl(x, log_radius.exp(), *extra)
 
 
 class WelschLoss(RobustLoss):
-    """robust_loss.py:33-41."""
+    """robust_loss.py:33-41: rho(x) = r - r exp(-x/r)."""
     ROBUST_KIND = 1
+    FUSED = True
+
+    @staticmethod
+    def _evaluate_impl(x, radius):
+        return radius - radius * torch.exp(-x / (radius + _LOSS_EPS))
+
+    @staticmethod
+    def _linearize_impl(x, radius):
+        return torch.exp(-x / (radius + _LOSS_EPS))
 
 
 class HuberLoss(RobustLoss):
-    """robust_loss.py:43-52."""
+    """robust_loss.py:43-52: rho(x) = x below the radius, 2 sqrt(r x) - r above."""
     ROBUST_KIND = 2
+    FUSED = True
+
+    @staticmethod
+    def _evaluate_impl(x, radius):
+        return torch.where(x > radius, 2 * torch.sqrt(radius * torch.max(x, radius) + _LOSS_EPS) - radius, x)
+
+    @staticmethod
+    def _linearize_impl(x, radius):
+        return torch.sqrt(radius / torch.max(x, radius) + _LOSS_EPS)
+
+
+class HingeLoss(RobustLoss):
+    """robust_loss.py:55-62: rho(x) = sqrt(x) - sqrt(r) above the radius, (numerically) zero below."""
+    ROBUST_KIND = 3
+
+    @staticmethod
+    def _evaluate_impl(x, radius):
+        return torch.where(x > radius, torch.sqrt(x) - torch.sqrt(radius), torch.full_like(x, _LOSS_EPS))
+
+    @staticmethod
+    def _linearize_impl(x, radius):
+        return torch.where(x > radius, 1.0 / (2 * torch.sqrt(x) + _LOSS_EPS), torch.zeros_like(x))
+
+
+class GNCRobustLoss(RobustLoss):
+    """robust_loss.py:65-91: losses with a graduated-non-convexity control value mu (third argument)."""
+
+
+class GemanMcClureLoss(GNCRobustLoss):
+    """robust_loss.py:96-118: rho(x) = mu r x / (mu r + x); mu = 1: Geman-McClure, mu -> inf: quadratic."""
+    ROBUST_KIND = 4
+
+    @staticmethod
+    def _evaluate_impl(x, radius, mu):
+        return mu * radius * x / (mu * radius + x + _LOSS_EPS)
+
+    @staticmethod
+    def _linearize_impl(x, radius, mu):
+        return (mu * radius) ** 2 / ((mu * radius + x) ** 2 + _LOSS_EPS)
 
 
 class RobustCostFunction(CostFunction):
     """theseus/core/robust_cost_function.py:16-160: wraps a cost function; linearisation rescales J and e by
-    sqrt(rho'(||w e||^2) + 1e-20), the error metric sees rho(||w e||^2).  Fused into the wrapped schema's kernels."""
+    sqrt(rho'(||w e||^2) + 1e-20), the error metric sees rho(||w e||^2).
+
+    Welsch / Huber around a cost function with a CUDA schema are fused into that schema's kernels.  Everything else -- Hinge,
+    Geman-McClure (GNCRobustCostFunction), flatten_dims=True, wrapped AutoDiff / Vector-difference costs -- takes the generic route of
+    the engine (torch.func Jacobians of the wrapped cost, rescaled here in torch, scattered into the batched CSR)."""
+    _EPS = 1e-20
 
     def __init__(self, cost_function: CostFunction, loss_cls, log_loss_radius: Variable, flatten_dims: bool = False,
                  name: Optional[str] = None):
-        if flatten_dims:
-            raise NotImplementedError("RobustCostFunction(flatten_dims=True) is not built in theseus_b200 r1")
         if not (isinstance(loss_cls, type) and issubclass(loss_cls, RobustLoss) and loss_cls.ROBUST_KIND > 0):
-            raise NotImplementedError("supported robust losses: WelschLoss, HuberLoss")
+            raise NotImplementedError("loss_cls must be one of WelschLoss, HuberLoss, HingeLoss, GemanMcClureLoss")
         self.cost_function = cost_function
         super().__init__(cost_function.weight, name=name)
         for attr in cost_function._optim_vars_attr_names:
@@ -307,30 +372,61 @@ class RobustCostFunction(CostFunction):
         self.log_loss_radius = log_loss_radius
         self._aux_vars_attr_names.append("log_loss_radius")
         self.loss = loss_cls()
+        self.flatten_dims = bool(flatten_dims)
         self.robust_kind = loss_cls.ROBUST_KIND
 
     def dim(self) -> int:
         return self.cost_function.dim()
 
+    def _loss_args(self):
+        return (self.log_loss_radius.tensor,)
+
     def generic_jacobians_error(self, optim_tensors, differentiable: bool = False):
-        """robust_cost_function.py:115-135: J, e of the wrapped cost rescaled by sqrt(rho'(||w e||^2) + eps)."""
+        """robust_cost_function.py:115-135: J, e of the wrapped cost rescaled by sqrt(rho'(||w e||^2) + eps)
+        (flatten_dims: per error dimension, rho'((w e)_i^2))."""
         jacs, err = self.cost_function.generic_jacobians_error(optim_tensors, differentiable=differentiable)
-        radius = self.log_loss_radius.tensor.exp()
-        x = (err ** 2).sum(dim=1, keepdim=True)
-        if self.robust_kind == WelschLoss.ROBUST_KIND:
-            lin = torch.exp(-x / (radius + 1e-20))                        # robust_loss.py:33-41
+        if self.flatten_dims:
+            x = err ** 2
+            sc = torch.sqrt(self.loss.linearize(x.reshape(-1, 1), *self._loss_args()) + self._EPS).reshape(err.shape)
         else:
-            lin = torch.sqrt(radius / torch.max(x, radius) + 1e-20)       # robust_loss.py:43-52 (Huber)
-        sc = torch.sqrt(lin + 1e-20)
+            x = (err ** 2).sum(dim=1, keepdim=True)
+            sc = torch.sqrt(self.loss.linearize(x, *self._loss_args()) + self._EPS)
         if not differentiable:
             sc = sc.detach()
         return [sc.unsqueeze(2) * J for J in jacs], sc * err
 
+    def generic_error(self, optim_tensors) -> torch.Tensor:
+        """robust_cost_function.py:87-109: an error whose squared norm is rho(||w e||^2): every entry sqrt(rho/dim + eps)
+        (flatten_dims: entry i = sqrt(rho((w e)_i^2) + eps))."""
+        err = self.cost_function.generic_error(optim_tensors)
+        if self.flatten_dims:
+            val = self.loss.evaluate((err ** 2).reshape(-1, 1), *self._loss_args()).reshape(err.shape)
+            return torch.sqrt(val + self._EPS)
+        val = self.loss.evaluate((err ** 2).sum(dim=1, keepdim=True), *self._loss_args())
+        return torch.ones_like(err) * torch.sqrt(val / self.dim() + self._EPS)
+
     def schema(self):
         kind, aux = self.cost_function.schema()
-        if kind == COST_LOCAL_VECTOR or kind is None:
-            raise NotImplementedError("RobustCostFunction over Vector differences / AutoDiff costs is not built in theseus_b200 r1")
-        return kind, aux
+        aux = list(aux) if isinstance(aux, (list, tuple)) else [aux]
+        if kind is None or kind == COST_LOCAL_VECTOR or not type(self.loss).FUSED or self.flatten_dims:
+            return None, aux   # generic route (engine: torch.func Jacobians through generic_jacobians_error / generic_error)
+        return kind, (aux if len(aux) > 1 else aux[0])
+
+
+class GNCRobustCostFunction(RobustCostFunction):
+    """robust_cost_function.py:181-240: robust cost whose loss takes the graduated-non-convexity control value `gnc_control_val`
+    (annealed by the caller between optimisations)."""
+
+    def __init__(self, cost_function: CostFunction, loss_cls, log_loss_radius: Variable, gnc_control_val: Variable,
+                 flatten_dims: bool = False, name: Optional[str] = None):
+        if not (isinstance(loss_cls, type) and issubclass(loss_cls, GNCRobustLoss)):
+            raise RuntimeError(f"{loss_cls} must be GNCRobustLoss type to initialize GNCRobustCostFunction.")
+        super().__init__(cost_function, loss_cls, log_loss_radius, flatten_dims=flatten_dims, name=name)
+        self.gnc_control_val = gnc_control_val
+        self._aux_vars_attr_names.append("gnc_control_val")
+
+    def _loss_args(self):
+        return (self.log_loss_radius.tensor, self.gnc_control_val.tensor)
 
 
 class AutogradMode(Enum):
