@@ -416,3 +416,38 @@ def se2_adjoint(T):
 
 def se2_retract(T, delta):
     return se2_compose(T, se2_exp(delta))
+
+
+# ---- SO2: storage [cos, sin], tangent [theta] (theseus/geometry/so2.py) ----
+def so2_exp(theta):
+    """so2.py:99-100, :167-186."""
+    return np.concatenate([np.cos(theta), np.sin(theta)], axis=-1)
+
+
+def so2_log(X):
+    """so2.py:206-222: atan2(sin, cos)."""
+    return np.arctan2(X[..., 1], X[..., 0])[..., None]
+
+
+def so2_compose(A, B):
+    """so2.py:224-230."""
+    return np.stack([A[..., 0] * B[..., 0] - A[..., 1] * B[..., 1], A[..., 1] * B[..., 0] + A[..., 0] * B[..., 1]], axis=-1)
+
+
+def so2_inverse(X):
+    """so2.py:232-234."""
+    return np.stack([X[..., 0], -X[..., 1]], axis=-1)
+
+
+def so2_jlog(X):
+    """so2.py:209-219: the log Jacobian is 1.  Returns (J[...,1,1], theta)."""
+    return np.ones(X.shape[:-1] + (1, 1), dtype=X.dtype), so2_log(X)
+
+
+def so2_adjoint(X):
+    """so2.py:116-117."""
+    return np.ones(X.shape[:-1] + (1, 1), dtype=X.dtype)
+
+
+def so2_retract(X, delta):
+    return so2_compose(X, so2_exp(delta))

@@ -27,6 +27,8 @@ _GROUP = {
                 log=lie.so3_log, adjoint=lie.so3_adjoint, exp=lie.so3_exp),
     "SE2": dict(dof=3, inverse=lie.se2_inverse, compose=lie.se2_compose, jlog=lie.se2_jlog,
                 log=lie.se2_log, adjoint=lie.se2_adjoint, exp=lie.se2_exp),
+    "SO2": dict(dof=1, inverse=lie.so2_inverse, compose=lie.so2_compose, jlog=lie.so2_jlog,
+                log=lie.so2_log, adjoint=lie.so2_adjoint, exp=lie.so2_exp),
 }
 
 
@@ -386,6 +388,8 @@ def retract(spec, values, delta, ignore_mask=None):
             new = lie.so3_retract(values[i], d)
         elif v["kind"] == "SE2":
             new = lie.se2_retract(values[i], d)
+        elif v["kind"] == "SO2":
+            new = lie.so2_retract(values[i], d)
         elif v["kind"] == "Vector":
             new = values[i] + d
         else:

@@ -728,6 +728,68 @@ def make_robust(th):
     print("robust_kat", len(out), "arrays")
 
 
+def so2_problem(th, torch, thetas0, meas, edges, w_edge, w_prior, device="cpu"):
+    """Rotation averaging on SO2, shared by generator and tests: N angles, Between edges (i, j) with measured relative rotations, a
+    prior on the first.  thetas0 [N,B,1], meas [E,B,1]."""
+    d = thetas0.dtype
+    vs = [th.SO2(theta=thetas0[i].to(device), name=f"R{i}") for i in range(thetas0.shape[0])]
+    objective = th.Objective(dtype=d)
+    for e, (i, j) in enumerate(edges):
+        objective.add(th.Between(vs[i], vs[j], th.SO2(theta=meas[e].to(device), name=f"Z{e}"),
+                                 th.ScaleCostWeight(torch.tensor(float(w_edge[e]), dtype=d, device=device)), name=f"between_{e}"))
+    objective.add(th.Difference(vs[0], th.SO2(theta=thetas0[0].to(device), name="R0_prior"),
+                                th.ScaleCostWeight(torch.tensor(float(w_prior), dtype=d, device=device)), name="prior"))
+    return objective, vs
+
+
+def make_so2(th):
+    """SO2 (geometry/so2.py): exp / log / compose / inverse / adjoint / project known answers, Between and Difference weighted
+    Jacobians, and an LM trace of a small rotation-averaging problem (dense Cholesky)."""
+    import torch
+    torch.manual_seed(23)
+    d = torch.float64
+    B = 12
+    theta = torch.cat([torch.tensor([0.0, 1e-9, -1e-9, np.pi - 1e-9, -np.pi + 1e-9, np.pi / 2], dtype=d), 6 * torch.rand(B - 6, dtype=d) - 3]).view(B, 1)
+    X = th.SO2(theta=theta)
+    Y = th.SO2.rand(B, dtype=d)
+    out = dict(theta=theta.numpy(), X=X.tensor.numpy(), Y=Y.tensor.numpy(), log_X=X.log_map().numpy(), compose=X.compose(Y).tensor.numpy(),
+               inverse=X.inverse().tensor.numpy(), adjoint=X.adjoint().numpy(), local=X.local(Y).numpy(),
+               retract=X.retract(theta.flip(0) * 0.3).tensor.numpy(), retract_delta=(theta.flip(0) * 0.3).numpy())
+    G = torch.randn(B, 5, 2, dtype=d)
+    out["proj_in"], out["proj_out"] = G.numpy(), X.project(G, is_sparse=True).numpy()
+    Z = th.SO2.rand(B, dtype=d)
+    cf = th.Between(X, Y, Z, th.ScaleCostWeight(torch.tensor(0.7, dtype=d)))
+    (J0, J1), e = cf.weighted_jacobians_error()
+    cl = th.Difference(X, Z, th.ScaleCostWeight(torch.tensor(1.3, dtype=d)))
+    (Jl,), el = cl.weighted_jacobians_error()
+    out.update(Z=Z.tensor.numpy(), between_J0=J0.numpy(), between_J1=J1.numpy(), between_e=e.numpy(), local_J=Jl.numpy(), local_e=el.numpy())
+    # LM trace
+    N, Bp = 7, 4
+    gt = 2 * np.pi * torch.rand(N, Bp, 1, dtype=d) - np.pi
+    edges = [(i, (i + 1) % N) for i in range(N)] + [(0, 3), (2, 5), (1, 4)]
+    meas = torch.stack([(gt[j] - gt[i]) + 0.05 * torch.randn(Bp, 1, dtype=d) for (i, j) in edges], 0)
+    thetas0 = gt + 0.4 * torch.randn(N, Bp, 1, dtype=d)
+    w_edge = (torch.rand(len(edges), dtype=d) + 0.5).numpy()
+    objective, vs = so2_problem(th, torch, thetas0, meas, edges, w_edge, 0.1)
+    iters = 6
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, vectorize=True, max_iterations=iters, step_size=1.0,
+                                abs_err_tolerance=0, rel_err_tolerance=0)
+    assert [v.name for v in opt.linear_solver.linearization.ordering] == [v.name for v in vs]
+    tr = dict(err=[], delta=[])
+
+    def cb(optimizer, info, delta, it):
+        tr["err"].append(info.last_err.numpy().copy()); tr["delta"].append(delta.detach().numpy().copy())
+    with torch.no_grad():
+        objective.update()
+        err0 = objective.error_metric().numpy().copy()
+        opt.optimize(end_iter_callback=cb, damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)
+    out.update(lm_thetas0=thetas0.numpy(), lm_meas=meas.numpy(), lm_edges=np.array(edges, dtype=np.int64), lm_w_edge=w_edge, lm_w_prior=np.array(0.1),
+               lm_err0=err0, lm_trace_err=np.stack(tr["err"], 0), lm_trace_delta=np.stack(tr["delta"], 0),
+               lm_final=np.stack([v.tensor.numpy() for v in vs], 0))
+    np.savez_compressed(os.path.join(HERE, "so2_kat.npz"), **out)
+    print("so2_kat", len(out), "arrays; LM err", err0, "->", tr["err"][-1])
+
+
 def tactile_problem(th, torch, inputs, device="cpu"):
     """A planar-pushing (tactile-style, config C4's cost set) objective shared by generator and tests: T object poses o_t and T
     effector poses e_t (SE2); per step: EffectorObjectContactPlanar(o_t, e_t), Difference(e_t, measured effector pose);
@@ -905,6 +967,9 @@ if __name__ == "__main__":
         make_pgo(th, "pgo_small_geman", num_poses=10, B=3, seed=13, iters=8, lm_kwargs=dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True),
                  loop_closure_ratio=0.6, robust="geman", outlier_ratio=0.3, init_perturb=0.0)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "so2":
+        make_so2(th)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "backward_lie":
         make_backward_lie(th)
         sys.exit(0)
@@ -936,6 +1001,7 @@ if __name__ == "__main__":
     make_backward_pgo(th)
     make_moving_frame(th)
     make_tactile(th)
+    make_so2(th)
     make_robust(th)
     make_pgo(th, "pgo_small_geman", num_poses=10, B=3, seed=13, iters=8, lm_kwargs=lm, loop_closure_ratio=0.6, robust="geman",
              outlier_ratio=0.3, init_perturb=0.0)

@@ -167,3 +167,29 @@ def test_gnc_robust_costs_on_the_generic_route_match_reference_trace():
         rel = np.linalg.norm(trace["delta"][it] - dref, axis=1) / np.linalg.norm(dref, axis=1)
         assert rel.max() < 1e-5, (it, rel)
         np.testing.assert_allclose(trace["lam"][it], g["trace_lam"][it], rtol=1e-12)
+
+
+def test_so2_rotation_averaging_lm_trace():
+    """SO2 variables (geometry.SO2, retracted by the fused retract kernel's THB_VAR_SO2 branch) with Between / Difference costs on the
+    engine's generic route: LM trace against the reference (tests/golden/so2_kat.npz; the oracle reproduces the same trace on the CPU,
+    tests/test_so2.py)."""
+    G, g = _golden_module(), load("so2_kat")
+    objective, vs = G.so2_problem(th, torch, torch.from_numpy(g["lm_thetas0"]), torch.from_numpy(g["lm_meas"]),
+                                  [tuple(int(x) for x in e) for e in g["lm_edges"]], g["lm_w_edge"], float(g["lm_w_prior"]), device="cuda")
+    iters = g["lm_trace_err"].shape[0]
+    for skw in (dict(linear_solver_cls=th.CholeskyDenseSolver),
+                dict(linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization)):
+        for i, v in enumerate(vs):
+            v.update(th.SO2(theta=torch.from_numpy(g["lm_thetas0"][i]).cuda()).tensor)
+        opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw)
+        errs, deltas = [], []
+
+        def cb(optimizer, info, delta, it):
+            errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+        with torch.no_grad():
+            np.testing.assert_allclose(objective.error_metric().cpu().numpy(), g["lm_err0"], rtol=1e-12)
+            opt.optimize(end_iter_callback=cb, damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)
+        np.testing.assert_allclose(np.stack(errs, 0), g["lm_trace_err"], rtol=1e-9)
+        for it in range(iters):
+            np.testing.assert_allclose(deltas[it], g["lm_trace_delta"][it], rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose(np.stack([v.tensor.cpu().numpy() for v in vs], 0), g["lm_final"], rtol=0, atol=1e-9)

@@ -11,7 +11,7 @@ facebookresearch/theseus (linearize -> solve -> retract), behind the reference's
 All arithmetic runs in libthb200.so (hand-written CUDA behind the C ABI of include/thb200.h); there is no CPU
 or PyTorch fallback.  Importing the package does not require a GPU; evaluating anything does.
 """
-from .geometry import Variable, Manifold, LieGroup, Vector, Point2, Point3, SE2, SE3, SO3, as_variable  # noqa: F401
+from .geometry import Variable, Manifold, LieGroup, Vector, Point2, Point3, SE2, SE3, SO2, SO3, as_variable  # noqa: F401
 from .core import (AutogradMode, CostWeight, ScaleCostWeight, DiagonalCostWeight, CostFunction, Between, Difference, Local,  # noqa: F401
                    Reprojection, AutoDiffCostFunction, RobustCostFunction, GNCRobustCostFunction, RobustLoss, WelschLoss, HuberLoss,
                    HingeLoss, GNCRobustLoss, GemanMcClureLoss, Objective)
@@ -23,7 +23,8 @@ from .optimizer import (VariableOrdering, Linearization, DenseLinearization, Spa
 from .sparse_solver import BaspachoSparseSolver, BlockSparseSolver, CholmodSparseSolver, LUCudaSparseSolver  # noqa: F401
 from .layer import TheseusLayer  # noqa: F401
 from .functional import (adjoint, between, compose, exp_map, inverse, local, log_map, retract, rand_vector, randn_vector,  # noqa: F401
-                         rand_point2, randn_point2, rand_point3, randn_point3, rand_so3, randn_so3, rand_se3, randn_se3, rand_se2, randn_se2)
+                         rand_point2, randn_point2, rand_point3, randn_point3, rand_so3, randn_so3, rand_se3, randn_se3, rand_se2, randn_se2,
+                         rand_so2, randn_so2)
 from . import io_formats  # noqa: F401  (g2o / BAL readers: th.io_formats.read_3D_g2o_file, load_bal_dataset)
 
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence, Union
 
 import torch
 
-from .geometry import LieGroup, Manifold, Point2, Point3, SE2, SE3, SO3, Variable, Vector, as_variable
+from .geometry import LieGroup, Manifold, Point2, Point3, SE2, SE3, SO2, SO3, Variable, Vector, as_variable
 
 # enum thb_cost_kind / thb_weight_kind (include/thb200.h)
 COST_BETWEEN_SE3, COST_LOCAL_SE3, COST_BETWEEN_SO3, COST_LOCAL_SO3, COST_LOCAL_VECTOR, COST_REPROJECTION = 0, 1, 2, 3, 4, 5
@@ -199,6 +199,8 @@ class Between(CostFunction):
             return COST_BETWEEN_SO3, self.measurement
         if isinstance(self.v0, SE2):
             return COST_BETWEEN_SE2, self.measurement
+        if isinstance(self.v0, SO2):
+            return None, [self.measurement]   # generic route: torch.func Jacobians of _torch_error (engine.py)
         return super().schema()
 
 
@@ -229,6 +231,8 @@ class Difference(CostFunction):
             return COST_LOCAL_SO3, self.target
         if isinstance(self.var, SE2):
             return COST_LOCAL_SE2, self.target
+        if isinstance(self.var, SO2):
+            return None, [self.target]        # generic route
         if isinstance(self.var, Vector):
             return COST_LOCAL_VECTOR, self.target
         return super().schema()

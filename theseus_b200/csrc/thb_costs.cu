@@ -576,6 +576,19 @@ __global__ void __launch_bounds__(128) retract_kernel(VarDev<T> v, int64_t B, co
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) op[q] = O[q];
+  } else if (kind == THB_VAR_SO2) {  // storage [cos, sin], tangent theta: X * exp(theta) (geometry/so2.py:167-186 exp_map, :224-230 compose)
+    const T* xp = v.x[i] + b * 2;
+    T* op = v.out[i] + b * 2;
+    const T c0 = xp[0], s0 = xp[1];
+    if (keep) {
+      op[0] = c0;
+      op[1] = s0;
+    } else {
+      T s1, c1;
+      t_sincos(d[0] * step, &s1, &c1);
+      op[0] = c0 * c1 - s0 * s1;
+      op[1] = s0 * c1 + c0 * s1;
+    }
   } else {  // Vector / Point: x + delta
     const int dof = v.dof[i];
     const T* xp = v.x[i] + b * dof;

@@ -7,7 +7,7 @@ from typing import Optional
 import torch
 
 from . import lie_torch
-from .geometry import SE2, SE3, SO3, LieGroup, Point2, Point3, Vector
+from .geometry import SE2, SE3, SO2, SO3, LieGroup, Point2, Point3, Vector
 
 
 def adjoint(group: LieGroup) -> torch.Tensor:
@@ -68,6 +68,9 @@ def _make(cls_name):
         elif cls_name == "se3":
             R = lie_torch._so3_exp_parts(_rand_so3_tangent(B, generator, dtype, device, _normal))[0]
             out = SE3(tensor=torch.cat((R, _gen(generator, B, 3, 1, dtype=dtype, device=device, normal=_normal)), dim=2))
+        elif cls_name == "so2":   # so2.py:50-94: uniform angle in [-pi, pi) / normal angle
+            ang = _gen(generator, B, 1, dtype=dtype, device=device, normal=_normal)
+            out = SO2(theta=ang if _normal else 2 * math.pi * ang - math.pi)
         else:  # se2
             th_ = _gen(generator, B, 1, dtype=dtype, device=device, normal=_normal) * (1.0 if _normal else 2 * math.pi) - (0.0 if _normal else math.pi)
             out = SE2(x_y_theta=torch.cat((_gen(generator, B, 2, dtype=dtype, device=device, normal=_normal), th_), dim=1))
@@ -86,3 +89,4 @@ rand_point3, randn_point3 = _make("point3")
 rand_so3, randn_so3 = _make("so3")
 rand_se3, randn_se3 = _make("se3")
 rand_se2, randn_se2 = _make("se2")
+rand_so2, randn_so2 = _make("so2")

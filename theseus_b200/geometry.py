@@ -366,6 +366,79 @@ class SE2(LieGroup):
         return torch.stack(((g_xy * cs).sum(-1), (g_xy * perp).sum(-1), (g_cs * perp).sum(-1)), dim=-1)
 
 
-SO3._GROUP_SHAPE, SE2._GROUP_SHAPE = (3, 3), (4,)
+class SO2(LieGroup):
+    """theseus/geometry/so2.py:19-340 -- storage [B,2] = [cos, sin], tangent [theta].  Retraction inside the optimizer: the fused retract
+    kernel (thb_retract, kind THB_VAR_SO2); cost functions on SO2 variables take the engine's generic (torch.func) route.  The group
+    arithmetic below is two-element torch arithmetic on whatever device the tensor lives on, as in the reference."""
+    KIND = 4  # THB_VAR_SO2
+
+    def __init__(self, theta: Optional[torch.Tensor] = None, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None,
+                 dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
+        if theta is not None and tensor is not None:
+            raise ValueError("Please provide only one of theta or tensor.")
+        if theta is not None:
+            if theta.ndim == 1:
+                theta = theta.unsqueeze(1)
+            if theta.ndim != 2 or theta.shape[1] != 1:
+                raise ValueError("Argument theta must be have ndim = 1, or ndim=2 and shape[1] = 1.")   # so2.py:33-37
+            tensor = torch.cat([theta.cos(), theta.sin()], dim=1)
+        if tensor is None:
+            tensor = torch.tensor([[1.0, 0.0]], dtype=dtype or torch.get_default_dtype())
+        if tensor.ndim != 2 or tensor.shape[1] != 2:
+            raise ValueError("SO2 data tensors can only be 2D vectors.")   # so2.py:189-190
+        super().__init__(tensor, name=name)
+
+    def dof(self) -> int:
+        return 1
+
+    @staticmethod
+    def project_tensor(group: torch.Tensor, euclidean_grad: torch.Tensor) -> torch.Tensor:
+        perp = torch.stack((-group[:, 1], group[:, 0]), dim=1)[:, None]     # so2.py:119-129 (is_sparse branch)
+        return (euclidean_grad * perp).sum(-1, keepdim=True)
+
+    @staticmethod
+    def exp_map(tangent_vector: torch.Tensor) -> "SO2":
+        from . import lie_torch
+        return SO2(tensor=lie_torch.so2_exp(tangent_vector))
+
+    def log_map(self, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        from . import lie_torch
+        if jacobians is not None:
+            jacobians.append(torch.ones(self.tensor.shape[0], 1, 1, dtype=self.tensor.dtype, device=self.tensor.device))  # so2.py:209-219
+        return lie_torch.so2_log(self.tensor)
+
+    def theta(self) -> torch.Tensor:
+        return self.log_map()
+
+    def adjoint(self) -> torch.Tensor:
+        return torch.ones(self.tensor.shape[0], 1, 1, dtype=self.tensor.dtype, device=self.tensor.device)   # so2.py:116-117
+
+    def inverse(self) -> "SO2":
+        from . import lie_torch
+        return SO2(tensor=lie_torch.so2_inverse(self.tensor))
+
+    def compose(self, other: "SO2") -> "SO2":
+        from . import lie_torch
+        return SO2(tensor=lie_torch.so2_compose(self.tensor, other.tensor))
+
+    def to_cos_sin(self):
+        return self.tensor[:, 0], self.tensor[:, 1]
+
+    def to_matrix(self) -> torch.Tensor:
+        c, s = self.to_cos_sin()
+        return torch.stack((torch.stack((c, -s), dim=1), torch.stack((s, c), dim=1)), dim=1)   # so2.py:311-318
+
+    def rotate(self, point) -> "Point2":
+        p = point.tensor if isinstance(point, Variable) else point
+        c, s = self.to_cos_sin()
+        return Point2(tensor=torch.stack((c * p[:, 0] - s * p[:, 1], s * p[:, 0] + c * p[:, 1]), dim=1))   # so2.py:257-291
+
+    def unrotate(self, point) -> "Point2":
+        p = point.tensor if isinstance(point, Variable) else point
+        c, s = self.to_cos_sin()
+        return Point2(tensor=torch.stack((c * p[:, 0] + s * p[:, 1], -s * p[:, 0] + c * p[:, 1]), dim=1))  # so2.py:293-306
+
+
+SO3._GROUP_SHAPE, SE2._GROUP_SHAPE, SO2._GROUP_SHAPE = (3, 3), (4,), (2,)
 _group_ops(SO3, "so3", 3, (3, 3))   # torchlie.functional.SO3: exp / log (+jlog) / adjoint / inv / compose
 _group_ops(SE2, "se2", 3, (3, 3))   # theseus.geometry.SE2: exp_map / log_map (+Jacobian) / adjoint / inverse / compose

@@ -64,8 +64,28 @@ def se2_retract(T: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
                         c0 * c1 - s0 * s1, s0 * c1 + c0 * s1), dim=-1)
 
 
+def so2_exp(theta: torch.Tensor) -> torch.Tensor:
+    """theseus/geometry/so2.py:99-100, :167-186: tangent [B,1] -> storage [cos, sin]."""
+    return torch.cat((theta.cos(), theta.sin()), dim=-1)
+
+
+def so2_log(X: torch.Tensor) -> torch.Tensor:
+    """so2.py:206-222: atan2(sin, cos) -> [B,1]."""
+    return torch.atan2(X[..., 1], X[..., 0]).unsqueeze(-1)
+
+
+def so2_inverse(X: torch.Tensor) -> torch.Tensor:
+    return torch.stack((X[..., 0], -X[..., 1]), dim=-1)   # so2.py:232-234
+
+
+def so2_compose(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    return torch.stack((A[..., 0] * B[..., 0] - A[..., 1] * B[..., 1], A[..., 1] * B[..., 0] + A[..., 0] * B[..., 1]), dim=-1)  # so2.py:224-230
+
+
 def retract(kind: int, X: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
-    """kind = Manifold.KIND (thb_var_kind): 0 SE3, 1 SO3, 2 Vector, 3 SE2."""
+    """kind = Manifold.KIND (thb_var_kind): 0 SE3, 1 SO3, 2 Vector, 3 SE2, 4 SO2."""
+    if kind == 4:
+        return so2_compose(X, so2_exp(delta))
     if kind == 2:
         return X + delta.view(delta.shape[0], *X.shape[1:])
     if kind == 0:
@@ -166,6 +186,8 @@ def local(kind: int, X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
         return so3_log(X.transpose(-1, -2) @ Y)[0]
     if kind == 3:
         return se2_log(se2_compose(se2_inverse(X), Y))
+    if kind == 4:
+        return so2_log(so2_compose(so2_inverse(X), Y))
     raise NotImplementedError(f"local() for variable kind {kind}")
 
 
@@ -177,6 +199,8 @@ def between(kind: int, X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
         return X.transpose(-1, -2) @ Y
     if kind == 3:
         return se2_compose(se2_inverse(X), Y)
+    if kind == 4:
+        return so2_compose(so2_inverse(X), Y)
     raise NotImplementedError(f"between() for variable kind {kind}")
 
 
@@ -195,5 +219,7 @@ def velocity_to_tangent(kind: int, D: torch.Tensor, dD: torch.Tensor) -> torch.T
         vx = c * dD[..., 0] + s_ * dD[..., 1]
         vy = -s_ * dD[..., 0] + c * dD[..., 1]
         return torch.stack((vx, vy, c * dD[..., 3] - s_ * dD[..., 2]), dim=-1)
+    if kind == 4:   # SO2 storage [cos, sin]: theta' = cos dsin - sin dcos
+        return (D[:, None, 0] * dD[..., 1] - D[:, None, 1] * dD[..., 0]).unsqueeze(-1)
     raise NotImplementedError(f"velocity_to_tangent for variable kind {kind}")
 
