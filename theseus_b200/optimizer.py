@@ -694,7 +694,7 @@ class NonlinearLeastSquares:
             inner = getattr(cf, "cost_function", cf)
             return type(inner)._torch_error is not CostFunction._torch_error
         bad_cf = [cf.name for cf in self.objective.cost_functions.values() if not has_torch(cf)]
-        bad_v = [v.name for v in self.ordering if v.KIND not in (0, 1, 2, 3)]
+        bad_v = [v.name for v in self.ordering if v.KIND not in (0, 1, 2, 3, 4)]
         if bad_cf or bad_v:
             raise NotImplementedError(
                 f"theseus_b200: cost functions {bad_cf[:3]} / variables {bad_v[:3]} have no torch restatement, so they cannot be put on "
