@@ -193,3 +193,37 @@ def test_so2_rotation_averaging_lm_trace():
         for it in range(iters):
             np.testing.assert_allclose(deltas[it], g["lm_trace_delta"][it], rtol=1e-6, atol=1e-10)
         np.testing.assert_allclose(np.stack([v.tensor.cpu().numpy() for v in vs], 0), g["lm_final"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("solver", ["dense", "sparse"])
+def test_custom_variable_ordering_gives_the_same_iterates(solver):
+    """A custom VariableOrdering (reversed pose order) permutes the columns of the linear system and nothing else: same error trace and
+    same final poses as the default order, delta permuted blockwise (theseus/optimizer/variable_ordering.py, linearization.py:20-38)."""
+    from helpers import pgo_objective, lm_kwargs_of
+    g = load("pgo_small_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(
+        linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization)
+    runs = {}
+    for mode in ("default", "reversed"):
+        objective, poses = pgo_objective(th, g)
+        lkw = {}
+        if mode == "reversed":
+            order = th.VariableOrdering(objective, default_order=False)
+            order.extend(list(reversed(poses)))
+            lkw = dict(linearization_kwargs=dict(ordering=order))
+        opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw, **lkw)
+        errs, deltas = [], []
+
+        def cb(optimizer, info, delta, it):
+            errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+        with torch.no_grad():
+            opt.optimize(end_iter_callback=cb, **kw)
+        runs[mode] = (np.stack(errs, 0), np.stack(deltas, 0), np.stack([p.tensor.cpu().numpy() for p in poses], 0))
+    np.testing.assert_allclose(runs["reversed"][0], g["trace_err"], rtol=1e-8)
+    N = len(runs["default"][2])
+    d_def = runs["default"][1].reshape(iters, -1, N, 6)
+    d_rev = runs["reversed"][1].reshape(iters, -1, N, 6)[:, :, ::-1]
+    rel = np.linalg.norm((d_def - d_rev).reshape(iters, -1), axis=1) / np.linalg.norm(d_def.reshape(iters, -1), axis=1)
+    assert rel[:2].max() < 1e-6, rel
+    np.testing.assert_allclose(runs["reversed"][2], g["poses_final"], rtol=1e-6, atol=1e-6)

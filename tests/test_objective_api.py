@@ -65,3 +65,69 @@ def test_random_generators_give_valid_group_elements():
     assert X.shape == (6, 4) and torch.allclose(X[:, 2] ** 2 + X[:, 3] ** 2, torch.ones(6, dtype=torch.float64), atol=1e-14)
     assert th.rand_vector(3, 7, generator=g).tensor.shape == (3, 7) and th.randn_point3(2, generator=g).tensor.shape == (2, 3)
     assert th.rand_point2(2, generator=g).tensor.shape == (2, 2)
+
+
+def _pair_objective(num_variables, rng):
+    vs = [th.Vector(1, name=f"var{i}") for i in range(num_variables)]
+    pairs = [(a, b) for i, a in enumerate(vs) for b in vs[i + 1:]]
+    rng.shuffle(pairs)
+    objective, expected = th.Objective(), []
+    w = th.ScaleCostWeight(1.0)
+    for k, (a, b) in enumerate(pairs):
+        objective.add(th.AutoDiffCostFunction([a, b], lambda optim_vars, aux_vars: optim_vars[0].tensor - optim_vars[1].tensor, 1, cost_weight=w,
+                                              name=f"cf{k}"))
+        for v in (a, b):
+            if v not in expected:
+                expected.append(v)
+    return objective, vs, expected
+
+
+def test_variable_ordering_default_append_remove_iterate():
+    """The reference's own checks (tests/theseus_tests/optimizer/test_variable_ordering.py): default order = first appearance; append /
+    remove / extend / complete / iteration of a hand-built order."""
+    import random
+    rng = random.Random(0)
+    for n in range(2, 9):
+        objective, vs, expected = _pair_objective(n, rng)
+        order = th.VariableOrdering(objective)
+        assert [order.index_of(v.name) for v in expected] == list(range(n)) and order.complete
+    objective, vs, _ = _pair_objective(8, rng)
+    for _ in range(10):
+        rng.shuffle(vs)
+        order = th.VariableOrdering(objective, default_order=False)
+        assert not order.complete
+        order.extend(vs[:3])
+        for v in vs[3:]:
+            order.append(v)
+        assert order.complete and [order.index_of(v.name) for v in vs] == list(range(8)) and [v for v in order] == vs and order[2] is vs[2]
+        with pytest.raises(ValueError):
+            order.append(vs[0])
+        rng.shuffle(vs)
+        for v in vs:
+            order.remove(v)
+            assert not order.complete and v not in order._var_order and v.name not in order._var_name_to_index
+        with pytest.raises(ValueError):
+            order.append(th.Vector(1, name="stranger"))
+
+
+def test_custom_variable_ordering_is_recorded_for_the_engine():
+    """A Linearization with a custom VariableOrdering records the column order on the objective (the engine is compiled for it on first
+    use, on the GPU); the default order records nothing; an incomplete order is refused like in the reference (linearization.py:29-30)."""
+    import random
+    from theseus_b200.optimizer import Linearization
+    objective, vs, expected = _pair_objective(5, random.Random(1))
+    lin = Linearization(objective)
+    assert objective._engine_ordering is None and lin.var_start_cols == [0, 1, 2, 3, 4]
+    order = th.VariableOrdering(objective, default_order=False)
+    order.extend(list(reversed(expected)))
+    lin = Linearization(objective, ordering=order)
+    assert objective._engine_ordering == tuple(v.name for v in reversed(expected))
+    assert [v.name for v in lin.ordering] == list(objective._engine_ordering)
+    with pytest.raises(RuntimeError, match="CUDA"):      # no CPU engine: building it fails loudly, after the order has been accepted
+        lin.engine
+    Linearization(objective)
+    assert objective._engine_ordering is None
+    short = th.VariableOrdering(objective, default_order=False)
+    short.append(expected[0])
+    with pytest.raises(ValueError, match="not complete"):
+        Linearization(objective, ordering=short)

@@ -655,10 +655,20 @@ class Objective:
         self._resolve_batch_size()
 
     # ---- evaluation (CUDA) ----
-    def engine(self):
+    def engine(self, ordering=None):
+        """The compiled form of this objective (engine.Engine).  `ordering`: variable names in column order (a Linearization passes its
+        VariableOrdering); None keeps the order recorded by the last Linearization built on this objective (default: order of first
+        appearance, variable_ordering.py:19-27).  A different order rebuilds the engine."""
         from .engine import Engine
-        if self._engine is None or self._engine.structure_version != self._structure_version:
-            self._engine = Engine(self)
+        if ordering is not None:
+            ordering = tuple(ordering)
+            self._engine_ordering = None if list(ordering) == list(self.optim_vars.keys()) else ordering
+        want = getattr(self, "_engine_ordering", None)
+        if want is not None and set(want) != set(self.optim_vars.keys()):
+            want = self._engine_ordering = None    # recorded for an earlier structure of this objective
+        if (self._engine is None or self._engine.structure_version != self._structure_version
+                or self._engine.custom_ordering != want):
+            self._engine = Engine(self, want)
         return self._engine
 
     def error_metric(self, input_tensors: Optional[Dict[str, torch.Tensor]] = None, also_update: bool = False) -> torch.Tensor:

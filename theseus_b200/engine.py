@@ -38,8 +38,9 @@ class _Group:
 
 
 class Engine:
-    def __init__(self, objective):
+    def __init__(self, objective, ordering_names=None):
         self.objective = objective
+        self.custom_ordering = None if ordering_names is None else tuple(ordering_names)   # None = default order (Objective.engine)
         self.structure_version = objective._structure_version
         self.device = torch.device(objective.device)
         if self.device.type != "cuda":
@@ -53,7 +54,8 @@ class Engine:
         self.lib = _lib.load()
 
         # ---- ordering (theseus/optimizer/variable_ordering.py:19-27: order of first appearance) ----
-        self.ordering: List[Manifold] = list(objective.optim_vars.values())
+        self.ordering: List[Manifold] = (list(objective.optim_vars.values()) if ordering_names is None
+                                         else [objective.optim_vars[n] for n in ordering_names])
         self.var_index = {v.name: i for i, v in enumerate(self.ordering)}
         costs = list(objective.cost_functions.values())
         self.costs = costs

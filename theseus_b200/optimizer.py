@@ -34,6 +34,24 @@ class VariableOrdering:
     def index_of(self, key: str) -> int:
         return self._var_name_to_index[key]
 
+    def append(self, var):
+        """variable_ordering.py:38-48."""
+        if var.name in self._var_name_to_index:
+            raise ValueError(f"Variable {var.name} has already been added to the order.")
+        if var.name not in self.objective.optim_vars:
+            raise ValueError(f"Variable {var.name} is not an optimization variable for the objective.")
+        self._var_order.append(var)
+        self._var_name_to_index[var.name] = len(self._var_order) - 1
+
+    def remove(self, var):
+        self._var_order.remove(var)
+        del self._var_name_to_index[var.name]
+        self._var_name_to_index = {v.name: i for i, v in enumerate(self._var_order)}
+
+    def extend(self, variables):
+        for var in variables:
+            self.append(var)
+
     def __getitem__(self, index):
         return self._var_order[index]
 
@@ -53,11 +71,13 @@ class Linearization:
 
     def __init__(self, objective: Objective, ordering: Optional[VariableOrdering] = None, **kwargs):
         self.objective = objective
-        if ordering is not None and [v.name for v in ordering] != list(objective.optim_vars.keys()):
-            raise NotImplementedError("theseus_b200 r1 supports the default variable ordering only")
         self.ordering = ordering or VariableOrdering(objective)
         if not self.ordering.complete:
             raise ValueError("Given variable ordering is not complete.")
+        # the objective's engine (pointer tables, CSR structure, column layout of delta) is compiled for ONE variable order: a custom
+        # order is recorded on the objective here and the engine is (re)built for it on first use (core.Objective.engine)
+        self._ordering_names = tuple(v.name for v in self.ordering)
+        objective._engine_ordering = None if list(self._ordering_names) == list(objective.optim_vars.keys()) else self._ordering_names
         self.var_dims = [v.dof() for v in self.ordering]
         self.var_start_cols = list(np.concatenate([[0], np.cumsum(self.var_dims)[:-1]]).astype(int)) if self.var_dims else []
         self.num_cols = int(sum(self.var_dims))
@@ -65,7 +85,7 @@ class Linearization:
 
     @property
     def engine(self):
-        return self.objective.engine()
+        return self.objective.engine(self._ordering_names)
 
     def linearize(self, _detach_hessian: bool = False, differentiable: bool = False):
         """differentiable=True (backward modes): the Jacobian values / residuals come out as autograd tensors built from the
