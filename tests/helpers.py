@@ -48,13 +48,13 @@ def pgo_objective(th, g, device="cuda", dtype=None):
     objective = th.Objective(dtype=dtype)
     robust = str(g["robust"]) if "robust" in g.files else ""
     llr = th.Vector(tensor=torch.from_numpy(g["log_loss_radius"]).to(dtype), name="log_loss_radius") if robust else None
+    mu = th.Vector(tensor=torch.from_numpy(g["gnc_mu"]).to(dtype), name="gnc_mu") if robust == "geman" else None
     for e in range(edges.shape[0]):
         i, j = int(edges[e, 0]), int(edges[e, 1])
         z = th.SE3(tensor=torch.from_numpy(meas[e]).to(dtype), name=f"EDGE_SE3__{e}_{i}_{j}")
         w = th.DiagonalCostWeight(th.Variable(torch.from_numpy(edge_w[e]).to(dtype), name=f"EDGE_WEIGHT__{e}"))
         cf = th.Between(poses[i], poses[j], z, w, name=f"between_{e}")
         if robust == "geman":
-            mu = th.Vector(tensor=torch.from_numpy(g["gnc_mu"]).to(dtype), name="gnc_mu")
             cf = th.GNCRobustCostFunction(cf, th.GemanMcClureLoss, llr, mu, name=f"robust_between_{e}")
         elif robust:
             cf = th.RobustCostFunction(cf, dict(welsch=th.WelschLoss, huber=th.HuberLoss, hinge=th.HingeLoss)[robust], llr,

@@ -227,3 +227,24 @@ def test_custom_variable_ordering_gives_the_same_iterates(solver):
     rel = np.linalg.norm((d_def - d_rev).reshape(iters, -1), axis=1) / np.linalg.norm(d_def.reshape(iters, -1), axis=1)
     assert rel[:2].max() < 1e-6, rel
     np.testing.assert_allclose(runs["reversed"][2], g["poses_final"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["pgo_small_welsch", "pgo_small_geman"])
+def test_batched_torch_route_equals_per_cost_loop_on_the_gpu(name, monkeypatch):
+    """THB_BATCHED_TORCH_ROUTE=1 (torch_route.py: one vmap(jacrev) per group of stackable cost functions) against the per-cost loop, inside
+    the engine: taped linearization of every cost function, and linearization + error metric of the generic ones (Geman-McClure).  The
+    route itself is compared with the loop on the CPU for every kind of objective (tests/test_torch_route.py)."""
+    from helpers import pgo_objective
+    g = load(name)
+    objective, poses = pgo_objective(th, g)
+    eng = objective.engine()
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("THB_BATCHED_TORCH_ROUTE", flag)
+        A, b = eng.linearize_sparse_differentiable()
+        A2, b2 = eng.linearize_sparse()
+        outs[flag] = (A.detach().cpu().numpy(), b.detach().cpu().numpy(), A2.cpu().numpy().copy(), b2.cpu().numpy().copy(),
+                      eng.error_metric().cpu().numpy().copy())
+    for x0, x1 in zip(outs["0"], outs["1"]):
+        np.testing.assert_allclose(x1, x0, rtol=1e-12, atol=1e-13 * np.abs(x0).max())
+    np.testing.assert_allclose(outs["1"][0], outs["1"][2], rtol=1e-9, atol=1e-11 * np.abs(outs["1"][2]).max())   # taped == fused-kernel values

@@ -12,6 +12,7 @@ stable across LM iterations (no table rebuilds, CUDA-graph friendly); `Variable.
 optimisation variable is a [B, ...] view into the pool.
 """
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -24,6 +25,12 @@ from .structure import build_gram_plan, build_structure
 
 def _dev(arr: np.ndarray, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+
+
+def _batched_torch_route() -> bool:
+    """Opt-in (THB_BATCHED_TORCH_ROUTE=1): evaluate the torch-route cost functions per group of equal signature (torch_route.py) instead of
+    one by one.  CPU-verified against the per-cost loop (tests/test_torch_route.py); default off until it has run on a GPU."""
+    return os.environ.get("THB_BATCHED_TORCH_ROUTE", "0") == "1"
 
 
 class _Group:
@@ -326,6 +333,9 @@ class Engine:
         for g in self.groups:
             _lib.check(fn(C.byref(g.bound["cur"][0]), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, s), "linearize_group")
         S = self.structure
+        if self.generic and _batched_torch_route():
+            self._route("generic").linearize(lambda v: self._expand(v.tensor), B, A_val, b, differentiable=False)
+            return A_val, b
         for f in self.generic:
             cf = self.costs[f]
             jacs, err = cf.generic_jacobians_error([self._expand(v.tensor) for v in cf.optim_vars])
@@ -344,6 +354,8 @@ class Engine:
         B, S = self.batch_size, self.structure
         A_val = torch.zeros(B, self.nnz, dtype=self.dtype, device=self.device)
         b = torch.zeros(B, self.m, dtype=self.dtype, device=self.device)
+        if _batched_torch_route():   # one vmap(jacrev) per group of stackable cost functions instead of one per cost function
+            return self._route("all").linearize(lambda v: self._expand(v.tensor), B, A_val, b, differentiable=True)
         for f, cf in enumerate(self.costs):  # every cost function through its torch restatement (O(#costs) torch calls: taped steps only)
             jacs, err = cf.generic_jacobians_error([self._expand(v.tensor) for v in cf.optim_vars], differentiable=True)
             d, st, off = int(S.cost_dims[f]), int(S.stride[f]), int(S.row_block_starts[f])
@@ -353,6 +365,16 @@ class Engine:
                 blk[:, :, p0:p0 + J.shape[2]] = J
             b[:, int(S.cost_row0[f]):int(S.cost_row0[f]) + d] = -err
         return A_val, b
+
+    def _route(self, which: str):
+        """torch_route.TorchRoute over the generic cost functions ("generic") or over all of them ("all", taped linearization)."""
+        if not hasattr(self, "_routes"):
+            self._routes = {}
+        if which not in self._routes:
+            from .torch_route import TorchRoute
+            ids = list(self.generic) if which == "generic" else list(range(len(self.costs)))
+            self._routes[which] = TorchRoute(self.costs, ids, self.structure)
+        return self._routes[which]
 
     def _expand(self, t):
         B = self.batch_size
@@ -372,6 +394,10 @@ class Engine:
             _lib.check(fn(C.byref(g.bound[which][0]), B, _lib.ptr(partial[row:]), s), "error_group")
             row += nc
         _lib.check(getattr(self.lib, f"thb_error_reduce_{self.sfx}")(_lib.ptr(partial), self.total_chunks, B, _lib.ptr(out), s), "error_reduce")
+        if self.generic and _batched_torch_route():
+            of = (lambda v: self.tmp_views[self.var_index[v.name]]) if which == "tmp" else (lambda v: self._expand(v.tensor))
+            out += self._route("generic").half_squared_error(of, B)
+            return out
         for f in self.generic:
             cf = self.costs[f]
             ts = [self.tmp_views[self.var_index[v.name]] if which == "tmp" else self._expand(v.tensor) for v in cf.optim_vars]
