@@ -575,3 +575,122 @@ def test_fill_reducing_quality_on_pose_graph_ring():
     a = analyze(sizes, np.array(ptrs), np.array(inds), "mindeg")
     b = analyze(sizes, np.array(ptrs), np.array(inds), "natural")
     assert a.stats["nnz_L"] < 0.8 * b.stats["nnz_L"]
+
+
+def run_piece_solve_numpy(plan, ps, F, DL, rhs):
+    """Interpret sparse.piece_solve_lists on a finished factor (F = blocks of L below the diagonal, DL = diagonal factors with reciprocal
+    diagonal, as the lane kernels leave them): forward then backward, piece launches in order; inside a launch the pieces are independent
+    (checked: a piece only reads y / x entries written by EARLIER launches or by itself)."""
+    A = plan.arrays
+    N, dims, cs = plan.N, plan.dims, plan.col_start
+    cut = ps["cut"]
+
+    def diag(j):
+        d = dims[j]
+        Lr = DL[A["winv_off"][j]:A["winv_off"][j] + d * d].reshape(d, d).copy()
+        Lr[np.arange(d), np.arange(d)] = 1.0 / np.diag(Lr)
+        return np.tril(Lr)
+
+    y = [None] * N
+    for (lv, d, b0, b1) in ps["launches"]:
+        written = []
+        for p in ps["order"][b0:b1]:
+            j0, w = ps["first"][p], ps["width"][p]
+            s = []
+            for jj in range(j0, j0 + w):                          # external parts: independent of each other
+                assert dims[jj] == d
+                acc = rhs[cs[jj]:cs[jj] + d].copy()
+                for q in range(A["fr_ptr"][jj], ps["fr_ext_end"][jj]):
+                    k = A["fr_k"][q]
+                    assert y[k] is not None and k not in written
+                    acc -= F[A["fr_off"][q]:A["fr_off"][q] + d * dims[k]].reshape(d, dims[k]) @ y[k]
+                s.append(acc)
+            for c, jj in enumerate(range(j0, j0 + w)):            # internal triangle, in order
+                for q in range(ps["fr_ext_end"][jj], A["fr_ptr"][jj + 1]):
+                    k = A["fr_k"][q]
+                    assert j0 <= k < jj
+                    s[c] -= F[A["fr_off"][q]:A["fr_off"][q] + d * d].reshape(d, d) @ y[k]
+                y[jj] = np.linalg.solve(diag(jj), s[c])
+            written.extend(range(j0, j0 + w))
+    return y
+
+
+def run_piece_backward_numpy(plan, ps, F, DL, y, x_known):
+    A = plan.arrays
+    N, dims = plan.N, plan.dims
+
+    def diag(j):
+        d = dims[j]
+        Lr = DL[A["winv_off"][j]:A["winv_off"][j] + d * d].reshape(d, d).copy()
+        Lr[np.arange(d), np.arange(d)] = 1.0 / np.diag(Lr)
+        return np.tril(Lr)
+
+    x = list(x_known)
+    for (lv, d, b0, b1) in ps["launches"][::-1]:
+        written = []
+        for p in ps["order"][b0:b1]:
+            j0, w = ps["first"][p], ps["width"][p]
+            j1 = j0 + w - 1
+            s = [y[jj].copy() for jj in range(j0, j1 + 1)]
+            n_ext = A["bc_ptr"][j1 + 1] - ps["bc_int_end"][j1]
+            for e in range(n_ext):                                 # every external x_i is fetched once for the whole piece
+                i = A["bc_i"][ps["bc_int_end"][j1] + e]
+                assert x[i] is not None and i not in written
+                for c, jj in enumerate(range(j0, j1 + 1)):
+                    q = ps["bc_int_end"][jj] + e
+                    assert A["bc_i"][q] == i
+                    s[c] -= F[A["bc_off"][q]:A["bc_off"][q] + dims[i] * d].reshape(dims[i], d).T @ x[i]
+            for c, jj in reversed(list(enumerate(range(j0, j1 + 1)))):
+                for q in range(A["bc_ptr"][jj], ps["bc_int_end"][jj]):
+                    i = A["bc_i"][q]
+                    assert jj < i <= j1
+                    s[c] -= F[A["bc_off"][q]:A["bc_off"][q] + d * d].reshape(d, d).T @ x[i]
+                x[jj] = np.linalg.solve(diag(jj).T, s[c])
+            written.extend(range(j0, j1 + 1))
+    return x
+
+
+def _factor_numpy(plan, M):
+    """Block Cholesky in the plan's storage, as the lane kernels leave it."""
+    N, dims, cs = plan.N, plan.dims, plan.col_start
+    order_start = plan.pstart
+    n = int(dims.sum())
+    perm = np.concatenate([np.arange(cs[j], cs[j] + dims[j]) for j in range(N)])
+    L = np.linalg.cholesky(M[np.ix_(perm, perm)])
+    F = np.zeros(plan.data_size)
+    DL = np.zeros(plan.winv_size)
+    for (i, j), t in plan.blk_index.items():
+        blk = L[order_start[i]:order_start[i] + dims[i], order_start[j]:order_start[j] + dims[j]]
+        if i == j:
+            Lr = blk.copy()
+            Lr[np.arange(dims[j]), np.arange(dims[j])] = 1.0 / np.diag(blk)
+            DL[plan.arrays["winv_off"][j]:plan.arrays["winv_off"][j] + blk.size] = Lr.reshape(-1)
+        else:
+            F[plan.blk_off[t]:plan.blk_off[t] + blk.size] = blk.reshape(-1)
+    return F, DL, perm, L
+
+
+@pytest.mark.parametrize("sizes,fill,ordering,width", [
+    ([6] * 14, 0.9, "natural", 4), ([6] * 40, 0.06, "mindeg", 4), ([6] * 40, 0.06, "mindeg", 2), ([6] * 30 + [3] * 10, 0.07, "mindeg", 4),
+    ([1, 2, 3, 6, 3, 3, 6, 6, 2, 1, 6], 0.25, "mindeg", 8), ([3] * 30 + [6] * 5, 0.08, "mindeg", 4)])
+def test_piece_solve_schedule_solves_system(sizes, fill, ordering, width):
+    """sparse.piece_solve_lists: supernodal (chain-piece) forward / backward substitution schedule against a dense solve."""
+    from theseus_b200.sparse import piece_solve_lists
+    rng = np.random.default_rng(len(sizes) + int(fill * 100) + 11 * width)
+    M, ptrs, inds = random_block_spd(rng, sizes, fill)
+    plan = analyze(np.array(sizes), ptrs, inds, ordering=ordering)
+    ps = piece_solve_lists(plan, max_width=width)
+    P = len(ps["first"])
+    assert int(ps["width"].sum()) == plan.N and ps["width"].max() <= width
+    assert sum(b1 - b0 for (_, _, b0, b1) in ps["launches"]) == P and sorted(ps["order"].tolist()) == list(range(P))
+    nlev = int(ps["level"].max()) + 1
+    assert nlev <= int(plan.level.max()) + 1
+    F, DL, perm, L = _factor_numpy(plan, M)
+    rhs = rng.standard_normal(M.shape[0])
+    y = run_piece_solve_numpy(plan, ps, F, DL, rhs)
+    x = run_piece_backward_numpy(plan, ps, F, DL, y, [None] * plan.N)
+    xs = np.zeros_like(rhs)
+    for j in range(plan.N):
+        xs[plan.col_start[j]:plan.col_start[j] + plan.dims[j]] = x[j]
+    assert np.abs(M @ xs - rhs).max() < 1e-9
+    print(f"columns {plan.N}, pieces {P}, piece levels {nlev} (column levels {int(plan.level.max()) + 1})")

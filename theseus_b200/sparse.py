@@ -15,7 +15,7 @@ elimination -> column structures, (3) elimination-tree levels (columns of one le
 (6) flat per-level work-item arrays for the CUDA kernels (thb_sparse.cu).
 """
 from dataclasses import dataclass
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -685,3 +685,63 @@ def tile_lane_lists(plan: SparsePlan, sp=None) -> Tuple[Dict[str, np.ndarray], D
     tiles = dict(tile_tgt=np.array(tile_tgt, dtype=i64).reshape(-1, TILE_ROWS * TILE_COLS), step_ptr=np.array(step_ptr, dtype=i64),
                  step_src=np.array(step_src, dtype=i64).reshape(-1, TILE_ROWS + TILE_COLS))
     return lane, tiles
+
+
+def piece_solve_lists(plan: SparsePlan, max_width: int = 4, cut: Optional[int] = None):
+    """Round-2 building block (host side, specification level; checked by a numpy interpreter in tests/test_sparse_symbolic.py; no kernel
+    consumes it yet): the SUPERNODAL schedule of the substitutions.  Today every elimination-tree level is a launch and the top of the tree
+    is one column per level (C5: 215 launches per pass, each a latency-bound list walk).  Consecutive columns of a chain (fundamental
+    supernode) depend on each other only through a small dense triangle, so a PIECE of <= max_width chain columns (same pieces as
+    chain_tiles; additionally cut where the block size changes) can be one work item:
+
+      forward   per column j of the piece, in parallel: s_j = rhs_j - sum_{k < j0} L_jk y_k   (EXTERNAL part: a prefix of row j's list
+                fr_*, because the list is sorted by k), then inside the work item, in order: s_j -= sum_{j0 <= k < j} L_jk y_k,
+                y_j = L_jj^-1 s_j
+      backward  the rows i > j1 below the piece are the SAME for all its columns (struct(j) = {j+1..j1} + struct(j1)): every x_i is
+                loaded once and used by all columns: s_j = y_j - sum_{i > j1} L_ij^T x_i, then in reverse order
+                s_j -= sum_{j < i <= j1} L_ij^T x_i, x_j = L_jj^-T s_j
+
+    Pieces are levelled by their own dependency tree.  `cut`: only columns < cut (the bottom of a root split).
+    Returns dict(first [P], width [P], dim [P], level [P], fr_ext_end [N] (index into fr_*: end of the external prefix of column j's row
+    list), bc_int_end [N] (index into bc_*: end of the internal prefix of column j's column list), order [P] (pieces sorted by level,
+    then block size), launches [(level, dim, begin, end)] into `order`)."""
+    N, dims, A = plan.N, plan.dims, plan.arrays
+    cut = N if cut is None else int(cut)
+    first, width = [], []
+    piece_of = np.full(N, -1, dtype=np.int64)
+    j = 0
+    while j < cut:
+        e = j
+        while (e + 1 < cut and plan.chain_of[e + 1] == plan.chain_of[j] and e + 1 - j < max_width and dims[e + 1] == dims[j]):
+            e += 1
+        piece_of[j:e + 1] = len(first)
+        first.append(j); width.append(e + 1 - j)
+        j = e + 1
+    P = len(first)
+    fr_ext_end = np.array(A["fr_ptr"][1:], dtype=np.int64).copy()
+    bc_int_end = np.array(A["bc_ptr"][:-1], dtype=np.int64).copy()
+    level = np.zeros(P, dtype=np.int64)
+    for p in range(P):                      # pieces are numbered in elimination order: dependencies have smaller numbers
+        j0, j1 = first[p], first[p] + width[p] - 1
+        for jj in range(j0, j1 + 1):
+            p0, p1 = int(A["fr_ptr"][jj]), int(A["fr_ptr"][jj + 1])
+            ks = A["fr_k"][p0:p1]
+            n_ext = int(np.searchsorted(ks, j0, side="left"))
+            assert (ks[:n_ext] < j0).all() and (ks[n_ext:] >= j0).all() and n_ext + (jj - j0) == p1 - p0   # chain: all of j0..jj-1 are there
+            fr_ext_end[jj] = p0 + n_ext
+            if n_ext:
+                level[p] = max(level[p], int(level[piece_of[ks[:n_ext]]].max()) + 1)
+            q0, q1 = int(A["bc_ptr"][jj]), int(A["bc_ptr"][jj + 1])
+            rows = A["bc_i"][q0:q1]
+            assert np.array_equal(rows[:j1 - jj], np.arange(jj + 1, j1 + 1))
+            bc_int_end[jj] = q0 + (j1 - jj)
+        ext_rows = [A["bc_i"][bc_int_end[jj]:A["bc_ptr"][jj + 1]] for jj in range(j0, j1 + 1)]
+        assert all(np.array_equal(r, ext_rows[0]) for r in ext_rows)    # shared external rows
+    order = sorted(range(P), key=lambda p: (int(level[p]), int(dims[first[p]]), p))
+    launches, b0 = [], 0
+    for q in range(1, P + 1):
+        if q == P or (level[order[q]], dims[first[order[q]]]) != (level[order[b0]], dims[first[order[b0]]]):
+            launches.append((int(level[order[b0]]), int(dims[first[order[b0]]]), b0, q)); b0 = q
+    return dict(first=np.array(first, dtype=np.int64), width=np.array(width, dtype=np.int64),
+                dim=np.array([dims[f] for f in first], dtype=np.int64), level=level, fr_ext_end=fr_ext_end, bc_int_end=bc_int_end,
+                order=np.array(order, dtype=np.int64), launches=np.array(launches, dtype=np.int64).reshape(-1, 4), cut=cut)
