@@ -361,6 +361,25 @@ typedef struct thb_sparse_lane_tiles {
 /* thb_sparse_lane_factor_f64 for a launch list that may contain THB_LANE_TU rows */
 int thb_sparse_lane_factor_tiled_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_tiles* t, double* factor, double* diagl,
                                      int32_t* info, int64_t B, thb_stream_t stream);
+/* Supernodal substitutions (opt-in; host lists: theseus_b200/sparse.py:piece_solve_lists).  A work item is a PIECE of <= 4 consecutive
+ * columns of a fundamental supernode with equal block size: their external sums are independent (forward) or share every x_i (backward),
+ * the dense triangle inside the piece is solved by one warp -- BaSpaCho's per-supernode solveL / solveLt (NumericDecomposition::solve,
+ * extlib/baspacho_solver.cpp:201-246).  One launch per piece level and block size instead of one per elimination-tree level.
+ * Same contract as thb_sparse_lane_forward_f64 / _backward_f64 (which they replace for the columns the pieces cover: all, or the columns
+ * below a dense root).  Device arrays except `launches` (HOST, [num_launches, 3] = block size, begin, end into `order`). */
+typedef struct thb_sparse_lane_pieces {
+  int64_t num_pieces, num_launches;
+  const int32_t* launches;      /* HOST */
+  const int64_t* first;         /* [num_pieces] first column (elimination position) */
+  const int32_t* width;         /* [num_pieces] 1..4 columns */
+  const int64_t* fr_ext_end;    /* [N] end (index into fr_off) of the prefix of column j's row list that lies before its piece */
+  const int64_t* bc_int_end;    /* [N] end (index into bc_off) of the prefix of column j's column list that lies inside its piece */
+  const int64_t* order;         /* [num_pieces] pieces sorted by (level, block size) */
+} thb_sparse_lane_pieces;
+int thb_sparse_lane_piece_forward_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_pieces* pc, const double* factor, const double* diagl,
+                                      const double* rhs, double* work, int64_t B, thb_stream_t stream);
+int thb_sparse_lane_piece_backward_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_pieces* pc, const double* factor, const double* diagl,
+                                       double* work, double* x, int64_t B, thb_stream_t stream);
 /* rhs, x: [B, n] row-major in the ORIGINAL variable order (scramble / unscramble folded into the substitutions) */
 int thb_sparse_lane_solve_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, const double* rhs,
                               double* x, double* work, int64_t B, thb_stream_t stream);

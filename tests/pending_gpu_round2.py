@@ -248,3 +248,34 @@ def test_batched_torch_route_equals_per_cost_loop_on_the_gpu(name, monkeypatch):
     for x0, x1 in zip(outs["0"], outs["1"]):
         np.testing.assert_allclose(x1, x0, rtol=1e-12, atol=1e-13 * np.abs(x0).max())
     np.testing.assert_allclose(outs["1"][0], outs["1"][2], rtol=1e-9, atol=1e-11 * np.abs(outs["1"][2]).max())   # taped == fused-kernel values
+
+
+@pytest.mark.parametrize("layout", ["lane", "lane_root", "lane_tiled_root"])
+@pytest.mark.parametrize("B", [32, 70])
+def test_supernodal_substitutions_match_per_column_substitutions(layout, B):
+    """supernodal_solve=True (chain-piece forward / backward kernels, thb_sparse_lane.cu:lane_piece_forward_kernel / _backward_kernel,
+    lists sparse.piece_solve_lists) against the per-column substitution kernels on the same factor, and the dense residual.  The schedule
+    is verified on the CPU: tests/test_sparse_symbolic.py::test_piece_solve_schedule_solves_system."""
+    from theseus_b200.structure import build_structure
+    from test_gpu_sparse_solver import _dense_system
+    rng = np.random.default_rng(19 + B)
+    N = 60
+    costs = [(3, [i, (i + 1) % N]) for i in range(N)] + [(3, [i, (i + 7) % N]) for i in range(N)] + [(6, [i]) for i in range(N)]
+    costs = [(d, sorted(vs)) for d, vs in costs]
+    S = build_structure([6] * N, costs)
+    A_val = torch.from_numpy(rng.standard_normal((B, S.nnz))).cuda()
+    b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
+    alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
+    xs = {}
+    for sn in (True, False):
+        solver = th.BaspachoSparseSolver.from_structure(S, layout=layout, supernodal_solve=sn)
+        solver.linearization.A_val, solver.linearization.b = A_val, b
+        xs[sn] = solver.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-6).cpu().numpy()
+        assert ("pieces" in solver._dev) == sn
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    M = AtA.copy()
+    M[:, idx, idx] = M[:, idx, idx] * (1 + alpha.cpu().numpy()[:, None]) + 1e-6
+    res = np.einsum("bij,bj->bi", M, xs[True]) - Atb
+    assert np.abs(res).max() < 1e-10 * np.abs(M).sum(axis=2).max() * max(1.0, np.abs(xs[True]).max())
+    assert np.abs(xs[True] - xs[False]).max() < 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(xs[False]).max())

@@ -78,7 +78,13 @@ class SparseLaneTilesStruct(C.Structure):
     _fields_ = [("num_tiles", c_i64), ("num_steps", c_i64), ("tile_tgt", c_vp), ("step_ptr", c_vp), ("step_src", c_vp)]
 
 
+class SparseLanePiecesStruct(C.Structure):
+    _fields_ = [("num_pieces", c_i64), ("num_launches", c_i64)] + [(k, c_vp) for k in (
+        "launches", "first", "width", "fr_ext_end", "bc_int_end", "order")]
+
+
 _PR = C.POINTER(SparseLaneRootStruct)
+_PP = C.POINTER(SparseLanePiecesStruct)
 _PT = C.POINTER(SparseLaneTilesStruct)
 SIGNATURES = {
     "thb_version": (c_i32, []),
@@ -119,6 +125,8 @@ SIGNATURES = {
     "thb_sparse_lane_solve_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_forward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_backward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_piece_forward_f64": (c_i32, [_PL, _PP, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_piece_backward_f64": (c_i32, [_PL, _PP, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_root_gather_f64": (c_i32, [_PR, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_root_rhs_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_root_scatter_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_i64, c_vp]),

@@ -430,6 +430,189 @@ __global__ void __launch_bounds__(32 * LS_WARPS, 1) lane_backward_kernel(LaneSol
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
+// Supernodal substitutions (sparse.py:piece_solve_lists): one work item = a PIECE of <= LP_MAXW consecutive chain columns of equal block
+// size x 32 batch lanes.  Forward: the CTA's 16 warps split the EXTERNAL parts of the row lists of all columns of the piece (column
+// c = warp % w), warp 0 then walks the piece's dense triangle in order.  Backward: the rows below the piece are the same for all its
+// columns, so a warp loads x_i once and applies it to every column; warp 0 finishes the triangle in reverse order.  Launches: one per
+// piece level and block size instead of one per elimination-tree level (C5 below the dense root: 39 instead of 119 per pass).
+constexpr int LP_MAXW = 4;
+struct LanePieceArgs {
+  const int64_t* first; const int32_t* width; const int64_t* fr_ext_end; const int64_t* bc_int_end; const int64_t* order;
+};
+
+// s[r] -= sum_c l[r][c] v[c] with v in registers (L: DJ x DK row-major at off)
+template <int DJ, int DK>
+__device__ __forceinline__ void blk_mv_reg(double (&s)[DJ], const double* Fb, int64_t off, const double (&v)[DK], int64_t Bp) {
+  double l[DJ * DK];
+#pragma unroll
+  for (int e = 0; e < DJ * DK; e++) l[e] = Fb[(off + e) * Bp];
+  loads_issued(l);
+#pragma unroll
+  for (int r = 0; r < DJ; r++)
+#pragma unroll
+    for (int c = 0; c < DK; c++) s[r] -= l[r * DK + c] * v[c];
+}
+// s[c] -= sum_r l[r][c] v[r] with v in registers (L: DI x DJ row-major at off)
+template <int DJ, int DI>
+__device__ __forceinline__ void blk_tmv_reg(double (&s)[DJ], const double* Fb, int64_t off, const double (&v)[DI], int64_t Bp) {
+  double l[DI * DJ];
+#pragma unroll
+  for (int e = 0; e < DI * DJ; e++) l[e] = Fb[(off + e) * Bp];
+  loads_issued(l);
+#pragma unroll
+  for (int r = 0; r < DI; r++)
+#pragma unroll
+    for (int c = 0; c < DJ; c++) s[c] -= l[r * DJ + c] * v[r];
+}
+
+template <int DJ>
+__global__ void __launch_bounds__(32 * LS_WARPS, 1) lane_piece_forward_kernel(LaneSolveArgs p, LanePieceArgs pc, const double* F,
+                                                                           const double* __restrict__ DL, const double* __restrict__ rhs,
+                                                                           double* Y) {
+  __shared__ double red[LS_WARPS * DJ * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int64_t piece = pc.order[p.begin + (blockIdx.x / p.nbx)];
+  const bool live = b < p.B;
+  const int64_t j0 = pc.first[piece];
+  const int w = pc.width[piece];
+  const double* Fb = F + (live ? b : 0);
+  double* Yb = Y + (live ? b : 0);
+  {  // external parts: warp -> column c = warp % w, every (LS_WARPS / w)-th entry of its list
+    const int c = warp % w, sub = warp / w, nsub = (LS_WARPS - 1 - c) / w + 1;
+    const int64_t j = j0 + c;
+    double s[DJ];
+#pragma unroll
+    for (int r = 0; r < DJ; r++) s[r] = 0.0;
+    if (live) {
+      const int64_t q1 = pc.fr_ext_end[j];
+      for (int64_t q = p.fr_ptr[j] + sub; q < q1; q += nsub) {
+        const int dk = p.fr_d[q], pk = p.fr_p[q];
+        const int64_t off = p.fr_off[q];
+        if (dk == 6) blk_mv<DJ, 6>(s, Fb, off, Yb, pk, p.Bp);
+        else if (dk == 3) blk_mv<DJ, 3>(s, Fb, off, Yb, pk, p.Bp);
+        else if (dk == 2) blk_mv<DJ, 2>(s, Fb, off, Yb, pk, p.Bp);
+        else blk_mv<DJ, 1>(s, Fb, off, Yb, pk, p.Bp);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < DJ; r++) red[(warp * DJ + r) * 32 + lane] = s[r];
+  }
+  __syncthreads();
+  if (warp != 0 || !live) return;
+  double y[LP_MAXW][DJ];
+#pragma unroll
+  for (int cc = 0; cc < LP_MAXW; cc++) {
+    if (cc < w) {
+      const int64_t jj = j0 + cc;
+      double t[DJ];
+#pragma unroll
+      for (int r = 0; r < DJ; r++) {
+        double v = rhs[b * p.n + p.col_start[jj] + r];  // scramble on load
+        for (int ww = cc; ww < LS_WARPS; ww += w) v += red[(ww * DJ + r) * 32 + lane];  // fixed order: deterministic
+        t[r] = v;
+      }
+      const int64_t qi = pc.fr_ext_end[jj];  // internal entries: k = j0 .. jj-1 in this order (the row list is sorted by k)
+#pragma unroll
+      for (int ci = 0; ci < LP_MAXW; ci++)
+        if (ci < cc) blk_mv_reg<DJ, DJ>(t, Fb, p.fr_off[qi + ci], y[ci], p.Bp);
+      double dl[DJ * DJ];
+      const double* Dl = DL + p.dl_off[jj] * p.Bp + b;
+#pragma unroll
+      for (int r = 0; r < DJ; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) dl[r * DJ + c] = Dl[(r * DJ + c) * p.Bp];
+      const int pj = p.pstart[jj];
+#pragma unroll
+      for (int r = 0; r < DJ; r++) {
+        double v = t[r];
+#pragma unroll
+        for (int c = 0; c < r; c++) v -= dl[r * DJ + c] * y[cc][c];
+        y[cc][r] = v * dl[r * DJ + r];
+        Yb[(int64_t)(pj + r) * p.Bp] = y[cc][r];
+      }
+    }
+  }
+}
+
+template <int DJ, int DI>
+__device__ __forceinline__ void piece_ext_row(double (&s)[LP_MAXW][DJ], int w, const double* Fb, const double* Yb, const LaneSolveArgs& p,
+                                              const LanePieceArgs& pc, int64_t j0, int64_t e, int pi) {
+  double v[DI];
+#pragma unroll
+  for (int r = 0; r < DI; r++) v[r] = Yb[(int64_t)(pi + r) * p.Bp];
+#pragma unroll
+  for (int cc = 0; cc < LP_MAXW; cc++)
+    if (cc < w) blk_tmv_reg<DJ, DI>(s[cc], Fb, p.bc_off[pc.bc_int_end[j0 + cc] + e], v, p.Bp);
+}
+
+template <int DJ>
+__global__ void __launch_bounds__(32 * LS_WARPS, 1) lane_piece_backward_kernel(LaneSolveArgs p, LanePieceArgs pc, const double* F,
+                                                                            const double* __restrict__ DL, double* Y, double* __restrict__ x) {
+  __shared__ double red[(LS_WARPS - 1) * DJ * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)(blockIdx.x % p.nbx) * 32 + lane;
+  const int64_t piece = pc.order[p.begin + (blockIdx.x / p.nbx)];
+  const bool live = b < p.B;
+  const int64_t j0 = pc.first[piece];
+  const int w = pc.width[piece];
+  const int64_t j1 = j0 + w - 1;
+  const double* Fb = F + (live ? b : 0);
+  double* Yb = Y + (live ? b : 0);
+  double s[LP_MAXW][DJ];
+#pragma unroll
+  for (int cc = 0; cc < LP_MAXW; cc++)
+#pragma unroll
+    for (int c = 0; c < DJ; c++) s[cc][c] = 0.0;
+  if (live) {  // external rows i > j1: the same rows for every column of the piece; x_i is loaded once per row
+    const int64_t qe = pc.bc_int_end[j1], n_ext = p.bc_ptr[j1 + 1] - qe;
+    for (int64_t e = warp; e < n_ext; e += LS_WARPS) {
+      const int di = p.bc_d[qe + e], pi = p.bc_p[qe + e];
+      if (di == 6) piece_ext_row<DJ, 6>(s, w, Fb, Yb, p, pc, j0, e, pi);
+      else if (di == 3) piece_ext_row<DJ, 3>(s, w, Fb, Yb, p, pc, j0, e, pi);
+      else if (di == 2) piece_ext_row<DJ, 2>(s, w, Fb, Yb, p, pc, j0, e, pi);
+      else piece_ext_row<DJ, 1>(s, w, Fb, Yb, p, pc, j0, e, pi);
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < LP_MAXW; cc++) {  // one reduction round per column (the buffer is reused; w is uniform across the CTA)
+    if (cc < w) {
+      reduce_to_warp0<DJ>(s[cc], red, warp, lane);
+      __syncthreads();
+    }
+  }
+  if (warp != 0 || !live) return;
+#pragma unroll
+  for (int cc = LP_MAXW - 1; cc >= 0; cc--) {
+    if (cc < w) {
+      const int64_t jj = j0 + cc;
+      const int pj = p.pstart[jj];
+#pragma unroll
+      for (int c = 0; c < DJ; c++) s[cc][c] += Yb[(int64_t)(pj + c) * p.Bp];
+      const int64_t qi = p.bc_ptr[jj];  // internal entries: i = jj+1 .. j1 in this order
+#pragma unroll
+      for (int ci = 0; ci < LP_MAXW; ci++)
+        if (ci > cc && ci < w) blk_tmv_reg<DJ, DJ>(s[cc], Fb, p.bc_off[qi + (ci - cc - 1)], s[ci], p.Bp);
+      double dl[DJ * DJ];
+      const double* Dl = DL + p.dl_off[jj] * p.Bp + b;
+#pragma unroll
+      for (int r = 0; r < DJ; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) dl[r * DJ + c] = Dl[(r * DJ + c) * p.Bp];
+#pragma unroll
+      for (int c = DJ - 1; c >= 0; c--) {
+        double v = s[cc][c];
+#pragma unroll
+        for (int r = c + 1; r < DJ; r++) v -= dl[r * DJ + c] * s[cc][r];
+        s[cc][c] = v * dl[c * DJ + c];
+        Yb[(int64_t)(pj + c) * p.Bp] = s[cc][c];
+        x[b * p.n + p.col_start[jj] + c] = s[cc][c];  // unscramble on store
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
 // Dense root (sparse.py:root_split): the top chain of the elimination tree is a dense trailing block; it is copied out of the
 // lane-interleaved storage into a batch-major dense matrix, factored / solved by the dense DMMA kernels (thb_potrf_f64 /
 // thb_potrs_f64), and its part of the solution copied back.
@@ -715,6 +898,47 @@ int thb_sparse_lane_forward_f64(const thb_sparse_lane_plan* p, const double* fac
 int thb_sparse_lane_backward_f64(const thb_sparse_lane_plan* p, const double* factor, const double* diagl, double* work, double* x, int64_t B,
                                  thb_stream_t s) {
   return lane_solve_passes(p, factor, diagl, nullptr, x, work, B, 2, s);
+}
+
+static int lane_piece_passes(const thb_sparse_lane_plan* p, const thb_sparse_lane_pieces* pc, const double* factor, const double* diagl,
+                             const double* rhs, double* x, double* work, int64_t B, int passes, thb_stream_t s) {
+  if (p == nullptr || pc == nullptr || factor == nullptr || diagl == nullptr || work == nullptr || B < 0) return THB_ERR_BAD_ARG;
+  if (((passes & 1) && rhs == nullptr) || ((passes & 2) && x == nullptr)) return THB_ERR_BAD_ARG;
+  if (B == 0 || pc->num_pieces == 0) return THB_OK;
+  cudaStream_t cs = thb_cs(s);
+  thb::LaneSolveArgs a = lane_solve_args(p, B);
+  thb::LanePieceArgs g;
+  g.first = pc->first; g.width = pc->width; g.fr_ext_end = pc->fr_ext_end; g.bc_int_end = pc->bc_int_end; g.order = pc->order;
+  for (int pass = 0; pass < 2; pass++) {
+    if (!(passes & (1 << pass))) continue;
+    for (int64_t q = 0; q < pc->num_launches; q++) {
+      const int64_t l = pass == 0 ? q : pc->num_launches - 1 - q;
+      const int32_t* L = pc->launches + 3 * l;
+      const int dj = L[0];
+      a.begin = L[1]; a.end = L[2];
+      const int items = a.end - a.begin;
+      if (items <= 0) continue;
+      const unsigned grid_w = (unsigned)(items * a.nbx);
+      if (pass == 0) {
+#define CALL_PF(DJ) thb::lane_piece_forward_kernel<DJ><<<grid_w, 32 * thb::LS_WARPS, 0, cs>>>(a, g, factor, diagl, rhs, work)
+        LN_SWITCH1(dj, CALL_PF)
+      } else {
+#define CALL_PB(DJ) thb::lane_piece_backward_kernel<DJ><<<grid_w, 32 * thb::LS_WARPS, 0, cs>>>(a, g, factor, diagl, work, x)
+        LN_SWITCH1(dj, CALL_PB)
+      }
+      THB_CHECK_LAUNCH();
+    }
+  }
+  return THB_OK;
+}
+
+int thb_sparse_lane_piece_forward_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_pieces* pc, const double* factor, const double* diagl,
+                                      const double* rhs, double* work, int64_t B, thb_stream_t s) {
+  return lane_piece_passes(p, pc, factor, diagl, rhs, nullptr, work, B, 1, s);
+}
+int thb_sparse_lane_piece_backward_f64(const thb_sparse_lane_plan* p, const thb_sparse_lane_pieces* pc, const double* factor, const double* diagl,
+                                       double* work, double* x, int64_t B, thb_stream_t s) {
+  return lane_piece_passes(p, pc, factor, diagl, nullptr, x, work, B, 2, s);
 }
 
 static thb::LaneRootArgs lane_root_args(const thb_sparse_lane_root* r) {

@@ -16,7 +16,7 @@ from . import _lib
 from .autograd import LinearSolveFunction, wants_grad
 from .core import Objective
 from .optimizer import (Linearization, LinearSolver, SparseLinearization, convert_to_alpha_beta_damping_tensors)
-from .sparse import LANE_DIMS, analyze, gram_out_offsets, root_lane_lists, root_split, tile_lane_lists
+from .sparse import LANE_DIMS, analyze, gram_out_offsets, piece_solve_lists, root_lane_lists, root_split, tile_lane_lists
 from .structure import ata_block_structure, build_gram_plan
 
 
@@ -27,7 +27,8 @@ _TILED_LAYOUTS = ("lane_tiled", "lane_tiled_root")   # supernodal tile kernel fo
 class BaspachoSparseSolver(LinearSolver):
     def __init__(self, objective: Objective, linearization_cls: Optional[Type[Linearization]] = None,
                  linearization_kwargs: Optional[Dict[str, Any]] = None, num_solver_contexts=1, batch_size: Optional[int] = None,
-                 auto_reset: bool = True, dev: Optional[str] = None, ordering: str = "mindeg", layout: Optional[str] = None, **kwargs):
+                 auto_reset: bool = True, dev: Optional[str] = None, ordering: str = "mindeg", layout: Optional[str] = None,
+                 supernodal_solve: bool = False, **kwargs):
         linearization_cls = linearization_cls or SparseLinearization
         if not linearization_cls == SparseLinearization:
             raise RuntimeError(
@@ -37,12 +38,14 @@ class BaspachoSparseSolver(LinearSolver):
         self.linearization: SparseLinearization = self.linearization
         self._ordering = ordering
         self._layout = layout
+        self._supernodal_solve = bool(supernodal_solve)   # opt-in: chain-piece substitution kernels (lane layouts only; not yet run on a GPU)
         self._plan = None
         self._dev = None
         self.reset()
 
     @classmethod
-    def from_structure(cls, structure, ordering: str = "mindeg", layout: Optional[str] = None) -> "BaspachoSparseSolver":
+    def from_structure(cls, structure, ordering: str = "mindeg", layout: Optional[str] = None,
+                       supernodal_solve: bool = False) -> "BaspachoSparseSolver":
         """Solver over a bare CSR structure with hand-filled `linearization.A_val / b` -- the pattern of the reference's own
         solver tests (void Objective + filled linearization, tests/theseus_tests/optimizer/linear/test_baspacho_sparse_solver.py:15-41)."""
         class _Lin:
@@ -56,6 +59,7 @@ class BaspachoSparseSolver(LinearSolver):
         self = cls.__new__(cls)
         self.linearization = _Lin(structure)
         self._ordering, self._plan, self._dev, self._layout = ordering, None, None, layout
+        self._supernodal_solve = bool(supernodal_solve)
         self.reset()
         return self
 
@@ -131,6 +135,14 @@ class BaspachoSparseSolver(LinearSolver):
                                                tile_tgt=ttdev["tile_tgt"].data_ptr(), step_ptr=ttdev["step_ptr"].data_ptr(),
                                                step_src=ttdev["step_src"].data_ptr())
             self._dev.update({self._layout: tst}, tiles=tiles, tkeep=(tdev, tlaunch, ttdev))
+        if getattr(self, "_supernodal_solve", False) and all(int(d) in LANE_DIMS for d in P.dims):
+            ps = piece_solve_lists(P, cut=self._root_split()[0]["cut"] if self._layout in _ROOT_LAYOUTS else None)
+            pdev = {k: torch.from_numpy(np.ascontiguousarray(ps[k] if k != "width" else ps[k].astype(np.int32))).to(device)
+                    for k in ("first", "width", "fr_ext_end", "bc_int_end", "order")}
+            plaunch = np.ascontiguousarray(ps["launches"][:, 1:], dtype=np.int32)    # (block size, begin, end); the level is implicit in the order
+            pst = _lib.SparseLanePiecesStruct(num_pieces=int(ps["first"].shape[0]), num_launches=int(plaunch.shape[0]), launches=plaunch.ctypes.data,
+                                              **{k: pdev[k].data_ptr() for k in pdev})
+            self._dev.update(pieces=pst, pkeep=(pdev, plaunch, ps))
         return self._dev
 
     def _lane_struct(self, ln, dev, device):
@@ -260,19 +272,31 @@ class BaspachoSparseSolver(LinearSolver):
         lib = _lib.load()
         rhs = rhs.contiguous()
         x = torch.empty(B, P.n, dtype=torch.float64, device=rhs.device)
-        if layout in ("lane", "lane_tiled"):
+        pieces = C.byref(d["pieces"]) if (layout != "item" and "pieces" in d) else None
+        if layout in ("lane", "lane_tiled") and pieces is not None:
+            s = _lib.stream_ptr()
+            lp, F, D, W = C.byref(d[layout]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(bufs["work"])
+            _lib.check(lib.thb_sparse_lane_piece_forward_f64(lp, pieces, F, D, _lib.ptr(rhs), W, B, s), "piece_forward")
+            _lib.check(lib.thb_sparse_lane_piece_backward_f64(lp, pieces, F, D, W, _lib.ptr(x), B, s), "piece_backward")
+        elif layout in ("lane", "lane_tiled"):
             _lib.check(lib.thb_sparse_lane_solve_f64(C.byref(d[layout]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
                                                      _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "lane_solve")
         elif layout in _ROOT_LAYOUTS:
             s = _lib.stream_ptr()
             lp, rt = C.byref(d[layout]), C.byref(d["root"])
             F, D, W = _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(bufs["work"])
-            _lib.check(lib.thb_sparse_lane_forward_f64(lp, F, D, _lib.ptr(rhs), W, B, s), "lane_forward")
+            if pieces is not None:
+                _lib.check(lib.thb_sparse_lane_piece_forward_f64(lp, pieces, F, D, _lib.ptr(rhs), W, B, s), "piece_forward")
+            else:
+                _lib.check(lib.thb_sparse_lane_forward_f64(lp, F, D, _lib.ptr(rhs), W, B, s), "lane_forward")
             _lib.check(lib.thb_sparse_lane_root_rhs_f64(lp, rt, F, _lib.ptr(rhs), W, _lib.ptr(bufs["rhs_root"]), B, s), "root_rhs")
             _lib.check(lib.thb_potrs_f64(_lib.ptr(bufs["rhs_root"]), _lib.ptr(bufs["x_root"]), B, d["nt"], _lib.ptr(bufs["ws"]), bufs["ws"].numel(), s),
                        "root_potrs")
             _lib.check(lib.thb_sparse_lane_root_scatter_f64(lp, rt, _lib.ptr(bufs["x_root"]), W, _lib.ptr(x), B, s), "root_scatter")
-            _lib.check(lib.thb_sparse_lane_backward_f64(lp, F, D, W, _lib.ptr(x), B, s), "lane_backward")
+            if pieces is not None:
+                _lib.check(lib.thb_sparse_lane_piece_backward_f64(lp, pieces, F, D, W, _lib.ptr(x), B, s), "piece_backward")
+            else:
+                _lib.check(lib.thb_sparse_lane_backward_f64(lp, F, D, W, _lib.ptr(x), B, s), "lane_backward")
         else:
             _lib.check(lib.thb_sparse_solve_f64(C.byref(d["plan"]), _lib.ptr(bufs["factor"]), _lib.ptr(bufs["diag"]), _lib.ptr(rhs), _lib.ptr(x),
                                                 _lib.ptr(bufs["work"]), B, _lib.stream_ptr()), "sparse_solve")
