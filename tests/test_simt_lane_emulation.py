@@ -1,0 +1,170 @@
+"""The batch-lane sparse kernels (theseus_b200/csrc/thb_sparse_lane.cu) executed on the CPU: the same source compiled for the host with
+one OS thread per CUDA thread (tests/simt/), driven through BaspachoSparseSolver's own host code (layouts, plan structs, buffers, call
+order).  The entry points that live in other translation units (zero fill, Atb, the dense Cholesky of the root) are replaced by numpy
+stand-ins here; everything named thb_sparse_lane_* is the real kernel source.  Checks index arithmetic, the split of work over warps,
+shared-memory layouts and barrier placement of every lane kernel -- including the ones written after the round-1 GPU budget was spent
+(tile update, dense-root gather / rhs / scatter, supernodal substitutions) -- without a GPU."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import theseus_b200 as th
+from theseus_b200 import _lib
+from theseus_b200.structure import build_structure
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_REAL_LIB = _lib.load()
+
+
+def _emu_lib():
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(HERE, "simt", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build())
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if name.startswith("thb_sparse_lane_"):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def _np_at(ptr, shape, dtype=np.float64):
+    n = int(np.prod(shape))
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr if isinstance(ptr, int) else ptr.value)
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+class _HybridLib:
+    """thb_sparse_lane_* -> the emulated kernels; the few other entry points the solver calls -> numpy stand-ins."""
+
+    def __init__(self, emu, S):
+        self._emu, self._S = emu, S
+
+    def __getattr__(self, name):
+        if name.startswith("thb_sparse_lane_"):
+            return getattr(self._emu, name)
+        if name.startswith("thb_symbolic_"):
+            return getattr(_REAL_LIB, name)          # host-only C++ (symbolic analysis): the real library
+        raise AttributeError(f"{name}: a CUDA entry point without a stand-in in this test")
+
+    def thb_fill_zero(self, ptr, nbytes, stream):
+        C.memset(ptr, 0, int(nbytes))
+        return 0
+
+    def thb_gram_f64(self, plan, B, A_val, nnz, b, m, AtA, ata_stride, Atb, diag, stream):
+        assert AtA is None and diag is None                      # the lane layouts only ask for Atb here
+        S = self._S
+        A = _np_at(A_val, (B, nnz)); bb = _np_at(b, (B, m)); out = _np_at(Atb, (B, S.num_cols))
+        out[:] = 0.0
+        for r in range(S.num_rows):
+            cols = S.A_col_ind[S.A_row_ptr[r]:S.A_row_ptr[r + 1]]
+            out[:, cols] += A[:, S.A_row_ptr[r]:S.A_row_ptr[r + 1]] * bb[:, r:r + 1]
+        return 0
+
+    def thb_potrf_workspace_bytes(self, B, n):
+        return int(B) * int(n) * int(n) * 8
+
+    def thb_potrf_f64(self, Sptr, alpha, beta, info, B, n, ws, ws_bytes, stream):
+        assert alpha is None and beta is None
+        M = _np_at(Sptr, (B, n, n))
+        M = np.tril(M) + np.transpose(np.tril(M, -1), (0, 2, 1))
+        L = _np_at(ws, (B, n, n))
+        L[:] = np.linalg.cholesky(M)
+        _np_at(info, (B,), np.int32)[:] = 0
+        return 0
+
+    def thb_potrs_f64(self, rhs, x, B, n, ws, ws_bytes, stream):
+        L = _np_at(ws, (B, n, n)); r = _np_at(rhs, (B, n)); out = _np_at(x, (B, n))
+        for i in range(B):
+            out[i] = np.linalg.solve(L[i].T, np.linalg.solve(L[i], r[i]))
+        return 0
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return _emu_lib()
+
+
+def _ring_structure(N, dims=None, chord=7):
+    dims = dims or [6] * N
+    costs = [(3, [i, (i + 1) % N]) for i in range(N)] + [(3, [i, (i + chord) % N]) for i in range(N)] + [(dims[i], [i]) for i in range(N)]
+    return build_structure(dims, [(d, sorted(vs)) for d, vs in costs])
+
+
+def _dense_system(S, A_val, b):
+    B = A_val.shape[0]
+    A = np.zeros((B, S.num_rows, S.num_cols))
+    for r in range(S.num_rows):
+        A[:, r, S.A_col_ind[S.A_row_ptr[r]:S.A_row_ptr[r + 1]]] = A_val[:, S.A_row_ptr[r]:S.A_row_ptr[r + 1]]
+    return np.einsum("bri,brj->bij", A, A), np.einsum("bri,br->bi", A, b)
+
+
+def _solve(monkeypatch, emu, S, layout, supernodal, A_val, b, alpha):
+    solver = th.BaspachoSparseSolver.from_structure(S, layout=layout, supernodal_solve=supernodal)
+    hybrid = _HybridLib(emu, S)
+    monkeypatch.setattr(_lib, "load", lambda: hybrid)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+    solver.linearization.A_val, solver.linearization.b = torch.from_numpy(A_val), torch.from_numpy(b)
+    x = solver.solve(damping=torch.from_numpy(alpha), ellipsoidal_damping=True, damping_eps=1e-6)
+    return solver, x.numpy()
+
+
+@pytest.mark.parametrize("layout,supernodal", [("lane", False), ("lane", True), ("lane_root", False), ("lane_tiled", False),
+                                               ("lane_tiled_root", True)])
+def test_lane_layouts_on_the_emulated_kernels(monkeypatch, emu, layout, supernodal):
+    rng = np.random.default_rng(3)
+    N, B = 40, 35                                   # B = 35: a full warp of lanes + a ragged one; ring + chords: ends in a dense separator
+    S = _ring_structure(N)
+    A_val = rng.standard_normal((B, S.nnz))
+    b = rng.standard_normal((B, S.num_rows))
+    alpha = rng.random(B) * 0.1
+    solver, x = _solve(monkeypatch, emu, S, layout, supernodal, A_val, b, alpha)
+    if "tiled" in layout:
+        assert solver._tiles[1]["tile_tgt"].shape[0] > 0
+    if "root" in layout:
+        assert solver._dev["nt"] >= 48
+    assert ("pieces" in solver._dev) == supernodal
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    M = AtA.copy()
+    M[:, idx, idx] = M[:, idx, idx] * (1 + alpha[:, None]) + 1e-6
+    ref = np.linalg.solve(M, Atb[..., None])[..., 0]
+    res = np.einsum("bij,bj->bi", M, x) - Atb
+    assert np.abs(res).max() < 1e-10 * np.abs(M).sum(axis=2).max() * max(1.0, np.abs(x).max())
+    assert np.abs(x - ref).max() <= 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(ref).max())
+
+
+def test_mixed_block_sizes_and_not_positive_definite_on_the_emulated_kernels(monkeypatch, emu):
+    rng = np.random.default_rng(4)
+    dims = [6, 3, 6, 2, 1, 6, 3, 3, 6, 6, 2, 6]
+    S = _ring_structure(len(dims), dims, chord=5)
+    B = 33
+    A_val = rng.standard_normal((B, S.nnz)); b = rng.standard_normal((B, S.num_rows)); alpha = rng.random(B) * 0.1
+    _, x0 = _solve(monkeypatch, emu, S, "lane", False, A_val, b, alpha)
+    _, x1 = _solve(monkeypatch, emu, S, "lane_tiled", True, A_val, b, alpha)      # tiles only where every block is 6x6; pieces cut at size changes
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    M = AtA.copy(); M[:, idx, idx] = M[:, idx, idx] * (1 + alpha[:, None]) + 1e-6
+    ref = np.linalg.solve(M, Atb[..., None])[..., 0]
+    for x in (x0, x1):
+        assert np.abs(x - ref).max() <= 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(ref).max())
+    # a variable without any Jacobian entry: its diagonal block of AtA is exactly zero -> pivot 0, no damping.  (The all-ones system of
+    # tests/test_gpu_sparse_solver.py fails through a rounding-level negative pivot, which depends on how rsqrt rounds.)
+    S2 = build_structure([2, 2], [(2, [0, 1])])
+    solver = th.BaspachoSparseSolver.from_structure(S2, layout="lane")
+    hybrid = _HybridLib(emu, S2)
+    monkeypatch.setattr(_lib, "load", lambda: hybrid)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+    A2 = torch.ones(3, S2.nnz, dtype=torch.float64)
+    for r in range(S2.num_rows):
+        cols = S2.A_col_ind[S2.A_row_ptr[r]:S2.A_row_ptr[r + 1]]
+        A2[:, S2.A_row_ptr[r]:S2.A_row_ptr[r + 1]][:, cols >= 2] = 0.0
+    A2[:, 1] = 2.0                                                                   # the first variable's block is regular
+    solver.linearization.A_val = A2
+    solver.linearization.b = torch.ones(3, S2.num_rows, dtype=torch.float64)
+    with pytest.raises(RuntimeError, match=r"batch element 0: matrix is not positive definite \(pivot 3\)"):
+        solver.solve()

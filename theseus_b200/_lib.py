@@ -84,7 +84,7 @@ class SparseLanePiecesStruct(C.Structure):
 
 
 _PR = C.POINTER(SparseLaneRootStruct)
-_PP = C.POINTER(SparseLanePiecesStruct)
+_PPIECES = C.POINTER(SparseLanePiecesStruct)
 _PT = C.POINTER(SparseLaneTilesStruct)
 SIGNATURES = {
     "thb_version": (c_i32, []),
@@ -125,8 +125,8 @@ SIGNATURES = {
     "thb_sparse_lane_solve_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_forward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_backward_f64": (c_i32, [_PL, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "thb_sparse_lane_piece_forward_f64": (c_i32, [_PL, _PP, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "thb_sparse_lane_piece_backward_f64": (c_i32, [_PL, _PP, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_piece_forward_f64": (c_i32, [_PL, _PPIECES, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "thb_sparse_lane_piece_backward_f64": (c_i32, [_PL, _PPIECES, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_root_gather_f64": (c_i32, [_PR, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_root_rhs_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_root_scatter_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_i64, c_vp]),

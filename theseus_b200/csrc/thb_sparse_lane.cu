@@ -31,6 +31,7 @@ constexpr int LN_WARPS = 4;  // warps per CTA; one warp = 32 batch lanes of one 
 // register, which turns 36-72 independent loads into a chain of dependent memory latencies (measured: 10 us per 6x6 block).
 template <int N>
 __device__ __forceinline__ void loads_issued(double (&x)[N]) {
+#ifndef THB_SIMT_EMU  // (tests/simt: the same source compiled for the host, one OS thread per CUDA thread)
   constexpr int G = 12;
 #pragma unroll
   for (int i = 0; i + G <= N; i += G)
@@ -38,6 +39,7 @@ __device__ __forceinline__ void loads_issued(double (&x)[N]) {
                  "+d"(x[i + 7]), "+d"(x[i + 8]), "+d"(x[i + 9]), "+d"(x[i + 10]), "+d"(x[i + 11]));
 #pragma unroll
   for (int i = N / G * G; i < N; i++) asm volatile("" : "+d"(x[i]));
+#endif
 }
 
 // acc[r][c] -= sum_k A[r][k] B[c][k]   (A: di x DK at a_off, B: dj x DK at b_off, both row-major, lane-interleaved)
@@ -156,6 +158,7 @@ struct LaneTileArgs {
   int begin; int64_t Bp;
 };
 
+#ifndef THB_SIMT_EMU
 __device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -163,6 +166,11 @@ __device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else  // host emulation: the copy is synchronous, groups are no-ops (the barriers of the kernel still order buffer reuse)
+inline void cp_async_8(double* smem_dst, const double* gmem_src) { *smem_dst = *gmem_src; }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
+#endif
 
 template <int D, int TR, int TC>
 __global__ void __launch_bounds__(32 * TR * TC, 1) lane_tile_update_kernel(LaneTileArgs p, double* F) {

@@ -211,11 +211,11 @@ class BaspachoSparseSolver(LinearSolver):
     def _numeric(self, A_val, b, alpha, beta):
         """add_MtM -> damp -> factor (+ Atb) on fp64 inputs; leaves the factor in the solver's buffers."""
         B, device = A_val.shape[0], A_val.device
+        layout = self.layout_for(B)     # validates an explicit layout (e.g. no dense root for 'lane_root') before anything is built
         d = self._device_plan(device)
         P = self._plan
         lib = _lib.load()
         s = _lib.stream_ptr()
-        layout = self.layout_for(B)
         key = (B, layout)
         if d["bufs"].get("key") != key:
             Bp = int(lib.thb_sparse_lane_padded_batch(B))
