@@ -64,3 +64,40 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/thb200.h parsed and compared with _lib.SIGNATURES argument by argument: count, struct-pointer types
+    (a wrong POINTER(struct) makes ctypes refuse the call at run time -- on the GPU box), integer / floating scalar widths, return type."""
+    import ctypes as C
+    src = open(os.path.join(ROOT, "include", "thb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef struct \w+ \{.*?\} \w+;", "", src, flags=re.S)
+    structs = {"thb_cost_group": _lib.CostGroup, "thb_var_table": _lib.VarTable, "thb_gram_plan": _lib.GramPlan,
+               "thb_sparse_plan": _lib.SparsePlanStruct, "thb_sparse_lane_plan": _lib.SparseLanePlanStruct,
+               "thb_sparse_lane_root": _lib.SparseLaneRootStruct, "thb_sparse_lane_tiles": _lib.SparseLaneTilesStruct,
+               "thb_sparse_lane_pieces": _lib.SparseLanePiecesStruct}
+    scalars = {"int64_t": C.c_int64, "int32_t": C.c_int32, "int": C.c_int32, "double": C.c_double, "float": C.c_float,
+               "thb_stream_t": C.c_void_p, "uint8_t": C.c_uint8}
+    protos = re.findall(r"\b(int64_t|int32_t|int|void|double)\s+(thb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) == len(_lib.SIGNATURES), (len(protos), len(_lib.SIGNATURES))
+    for ret, name, params in protos:
+        res, args = _lib.SIGNATURES[name]
+        assert res == {"int64_t": C.c_int64, "int32_t": C.c_int32, "int": C.c_int32, "void": None, "double": C.c_double}[ret], name
+        plist = [p.strip() for p in params.split(",")] if params.strip() not in ("", "void") else []
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        for i, (p, a) in enumerate(zip(plist, args)):
+            ptype = re.sub(r"\s+\w+$", "", p).replace("const ", "").strip()    # drop the parameter name
+            if ptype.endswith("*"):
+                base = ptype.rstrip("*").strip()
+                if base in structs:
+                    assert a == C.POINTER(structs[base]), f"{name} argument {i}: header says {base}*, ctypes says {a}"
+                elif base == "char":
+                    assert a == C.c_char_p, f"{name} argument {i} ({p}): ctypes says {a}"
+                elif base == "thb_symbolic*":      # thb_symbolic** out-parameter
+                    assert a in (C.c_void_p, C.POINTER(C.c_void_p)), f"{name} argument {i} ({p}): ctypes says {a}"
+                else:
+                    assert a == C.c_void_p, f"{name} argument {i} ({p}): expected a raw pointer, ctypes says {a}"
+            else:
+                assert ptype in scalars, (name, p)
+                assert a == scalars[ptype], f"{name} argument {i} ({p}): ctypes says {a}"
