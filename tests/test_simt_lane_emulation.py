@@ -168,3 +168,26 @@ def test_mixed_block_sizes_and_not_positive_definite_on_the_emulated_kernels(mon
     solver.linearization.b = torch.ones(3, S2.num_rows, dtype=torch.float64)
     with pytest.raises(RuntimeError, match=r"batch element 0: matrix is not positive definite \(pivot 3\)"):
         solver.solve()
+
+
+def test_bundle_adjustment_like_structure_with_dense_camera_root(monkeypatch, emu):
+    """Points (3) seen by a few of 14 cameras (6): mixed block shapes in every list, the cameras end up as the dense root (its assembly
+    goes through the split-K update kernel: the sources are 6x3 blocks, no tile applies), pieces are cut where the block size changes;
+    B = 5: a single ragged warp of lanes."""
+    rng = np.random.default_rng(5)
+    P_, Cn, B = 50, 14, 5
+    dims = [6] * Cn + [3] * P_
+    costs = []
+    for p in range(P_):
+        for c in rng.choice(Cn, size=5, replace=False):
+            costs.append((2, sorted([int(c), Cn + p])))
+    costs += [(dims[i], [i]) for i in range(len(dims))]
+    S = build_structure(dims, costs)
+    A_val = rng.standard_normal((B, S.nnz)); b = rng.standard_normal((B, S.num_rows)); alpha = rng.random(B) * 0.1
+    solver, x = _solve(monkeypatch, emu, S, "lane_root", True, A_val, b, alpha)
+    assert solver._dev["nt"] >= 48 and (solver._dev["lkeep"][1][:, 0] == 3).any() and len(set(solver._dev["pkeep"][2]["dim"].tolist())) == 2
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    M = AtA.copy(); M[:, idx, idx] = M[:, idx, idx] * (1 + alpha[:, None]) + 1e-6
+    ref = np.linalg.solve(M, Atb[..., None])[..., 0]
+    assert np.abs(x - ref).max() <= 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(ref).max())
