@@ -247,7 +247,7 @@ def test_batched_torch_route_equals_per_cost_loop_on_the_gpu(name, monkeypatch):
                       eng.error_metric().cpu().numpy().copy())
     for x0, x1 in zip(outs["0"], outs["1"]):
         np.testing.assert_allclose(x1, x0, rtol=1e-12, atol=1e-13 * np.abs(x0).max())
-    np.testing.assert_allclose(outs["1"][0], outs["1"][2], rtol=1e-9, atol=1e-11 * np.abs(outs["1"][2]).max())   # taped == fused-kernel values
+    np.testing.assert_allclose(outs["1"][0], outs["1"][2], rtol=1e-7, atol=1e-9 * np.abs(outs["1"][2]).max())   # taped (autodiff) == fused-kernel (analytic) values
 
 
 @pytest.mark.parametrize("layout", ["lane", "lane_root", "lane_tiled_root"])

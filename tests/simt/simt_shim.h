@@ -8,7 +8,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <barrier>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -26,22 +28,49 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
 inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 inline std::barrier<>* simt_block_barrier = nullptr;
+// warp-level exchange for __shfl_*_sync: the 32 threads of a warp meet at their own barrier around a 32-slot buffer
+struct SimtWarp {
+  std::barrier<> bar;
+  unsigned long long slot[32];
+  explicit SimtWarp(int n) : bar(n) {}
+};
+inline thread_local SimtWarp* simt_warp = nullptr;
+inline thread_local int simt_lane = 0;
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  memcpy(&simt_warp->slot[simt_lane], &v, sizeof(T));
+  simt_warp->bar.arrive_and_wait();
+  T r;
+  memcpy(&r, &simt_warp->slot[(simt_lane ^ lane_mask) & 31], sizeof(T));
+  simt_warp->bar.arrive_and_wait();
+  return r;
+}
+inline int atomicAdd(int* addr, int val) { return __sync_fetch_and_add(addr, val); }
 inline char* simt_dyn_smem_ptr = nullptr;
 inline void __syncthreads() { simt_block_barrier->arrive_and_wait(); }
 template <typename T> inline T* simt_dyn_smem() { return reinterpret_cast<T*>(simt_dyn_smem_ptr); }
 
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+using std::max;
+using std::min;
 inline int atomicCAS(int* addr, int compare, int val) { return __sync_val_compare_and_swap(addr, compare, val); }
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 template <typename K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
-inline int64_t thb_launch_counter_ = 0;
+extern "C" int64_t thb_launch_counter_;   // defined by thb_costs.cu, like in the product
 #define THB_CHECK_LAUNCH() do { ++thb_launch_counter_; } while (0)
 #define THB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return static_cast<int>(_e); } while (0)
 static inline cudaStream_t thb_cs(thb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -56,6 +85,8 @@ void simt_launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, A... args) 
         std::barrier<> bar(nthreads);
         simt_block_barrier = &bar;
         simt_dyn_smem_ptr = smem.data();
+        std::vector<std::unique_ptr<SimtWarp>> warps;
+        for (unsigned w = 0; w * 32 < nthreads; w++) warps.emplace_back(new SimtWarp((int)std::min(32u, nthreads - 32 * w)));
         std::vector<std::thread> ts;
         ts.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; t++)
@@ -64,7 +95,10 @@ void simt_launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, A... args) 
             blockIdx = dim3(bx, by, bz);
             blockDim = block;
             gridDim = grid;
+            simt_warp = warps[t / 32].get();
+            simt_lane = (int)(t % 32);
             kernel(args...);
+            simt_warp->bar.arrive_and_drop();
             bar.arrive_and_drop();  // an exited thread no longer takes part in the block's barriers
           });
         for (auto& th : ts) th.join();

@@ -33,6 +33,15 @@ def _batched_torch_route() -> bool:
     return os.environ.get("THB_BATCHED_TORCH_ROUTE", "0") == "1"
 
 
+def _require_cuda_device(device):
+    """The product has no CPU path: fail loudly.  (tests/test_simt_engine_emulation.py replaces this guard AND the library by a host
+    emulation of the kernels to exercise the host code without a GPU; nothing in the package does.)"""
+    if device.type != "cuda":
+        raise RuntimeError(
+            "theseus_b200: the objective must live on a CUDA device (call objective.to('cuda')); "
+            "there is no CPU implementation of the linearize/solve/retract path in this package")
+
+
 class _Group:
     """One cost-function schema: static placement arrays + (re)bindable pointer tables."""
 
@@ -50,10 +59,7 @@ class Engine:
         self.custom_ordering = None if ordering_names is None else tuple(ordering_names)   # None = default order (Objective.engine)
         self.structure_version = objective._structure_version
         self.device = torch.device(objective.device)
-        if self.device.type != "cuda":
-            raise RuntimeError(
-                "theseus_b200: the objective must live on a CUDA device (call objective.to('cuda')); "
-                "there is no CPU implementation of the linearize/solve/retract path in this package")
+        _require_cuda_device(self.device)
         self.dtype = objective.dtype
         if self.dtype not in (torch.float64, torch.float32):
             raise ValueError(f"unsupported dtype {self.dtype}")
