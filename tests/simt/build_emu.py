@@ -1,4 +1,4 @@
-"""Build tests/simt/_build/libthb_emu.so: theseus_b200/csrc/{thb_sparse_lane,thb_costs,thb_gram}.cu compiled for the HOST with g++ on
+"""Build tests/simt/_build/libthb_emu.so: theseus_b200/csrc/{thb_sparse_lane,thb_costs,thb_gram,thb_sparse,thb_lie_ops}.cu compiled for the HOST with g++ on
 top of simt_shim.h (one OS thread per CUDA thread).  The sources are used as they are except for three mechanical rewrites done here:
   kernel<<<grid, block, smem, stream>>>(args)  ->  SIMT_LAUNCH(kernel, grid, block, smem, args)
   extern __shared__ T name[];                   ->  T* name = simt_dyn_smem<T>();
@@ -10,7 +10,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "..", "theseus_b200", "csrc")
-SOURCES = ["thb_sparse_lane.cu", "thb_costs.cu", "thb_gram.cu"]     # + the headers they include (thb_lie.cuh)
+SOURCES = ["thb_sparse_lane.cu", "thb_costs.cu", "thb_gram.cu", "thb_sparse.cu", "thb_lie_ops.cu"]     # + the headers they include (thb_lie.cuh)
 HEADERS = ["thb_lie.cuh"]
 OUT_DIR = os.path.join(HERE, "_build")
 

@@ -20,6 +20,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
@@ -51,6 +52,7 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   simt_warp->bar.arrive_and_wait();
   return r;
 }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt_warp->bar.arrive_and_wait(); }
 inline int atomicAdd(int* addr, int val) { return __sync_fetch_and_add(addr, val); }
 inline char* simt_dyn_smem_ptr = nullptr;
 inline void __syncthreads() { simt_block_barrier->arrive_and_wait(); }

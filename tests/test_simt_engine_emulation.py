@@ -3,7 +3,6 @@ traces, with the CUDA library replaced by its host emulation (tests/simt/: thb_c
 unchanged, one OS thread per CUDA thread) plus numpy stand-ins for the dense DMMA Cholesky.  Nothing here is a product path: the engine's
 CUDA guard and the library loader are replaced explicitly by the test.  What it buys: every change of the host code and of these kernels'
 logic is exercised against the reference goldens without a GPU (the GPU suite stays the parity gate)."""
-import ctypes as C
 import importlib.util
 import os
 
@@ -12,90 +11,27 @@ import pytest
 import torch
 
 import theseus_b200 as th
-from theseus_b200 import _lib, engine as engine_mod, optimizer as optimizer_mod
 from oracle import nls
 from helpers import load, pgo_spec, pgo_objective, lm_kwargs_of, decisive_iterations
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_REAL_LIB = _lib.load()
 
 
-def _np_at(ptr, shape, dtype=np.float64):
-    n = int(np.prod(shape))
-    addr = ptr if isinstance(ptr, int) else ptr.value
-    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr)
-    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
-
-
-class _EmulatedLib:
-    """Every entry point the emulation library exports -> the emulated kernels; symbolic analysis (host C++) -> the real library; the dense
-    Cholesky (DMMA, not emulated) -> numpy with the same contract (thb200.h: damping fused into the load, info = failing pivot)."""
-
-    def __init__(self, emu):
-        self._emu = emu
-
-    def __getattr__(self, name):
-        if hasattr(self._emu, name) and name in _lib.SIGNATURES and not name.startswith("thb_potr"):
-            return getattr(self._emu, name)
-        if name.startswith("thb_symbolic_"):
-            return getattr(_REAL_LIB, name)
-        raise AttributeError(f"{name}: a CUDA entry point without an emulation or stand-in in this test")
-
-    @staticmethod
-    def _damped(Aptr, alpha, beta, B, n):
-        M = _np_at(Aptr, (B, n, n)).copy()
-        M = np.tril(M) + np.transpose(np.tril(M, -1), (0, 2, 1))
-        idx = np.arange(n)
-        if alpha is not None and getattr(alpha, "value", alpha) is not None:
-            M[:, idx, idx] = M[:, idx, idx] * (1.0 + _np_at(alpha, (B,))[:, None]) + _np_at(beta, (B,))[:, None]
-        return M
-
-    def thb_potrf_workspace_bytes(self, B, n):
-        return int(B) * int(n) * int(n) * 8 + 256
-
-    def thb_potrf_f64(self, Aptr, alpha, beta, info, B, n, ws, ws_bytes, stream):
-        M = self._damped(Aptr, alpha, beta, B, n)
-        L, inf = _np_at(ws, (B, n, n)), _np_at(info, (B,), np.int32)
-        for i in range(B):
-            try:
-                L[i] = np.linalg.cholesky(M[i]); inf[i] = 0
-            except np.linalg.LinAlgError:
-                inf[i] = 1
-        return 0
-
-    def thb_potrs_f64(self, rhs, x, B, n, ws, ws_bytes, stream):
-        L, r, out = _np_at(ws, (B, n, n)), _np_at(rhs, (B, n)), _np_at(x, (B, n))
-        for i in range(B):
-            out[i] = np.linalg.solve(L[i].T, np.linalg.solve(L[i], r[i]))
-        return 0
-
-    def thb_potrf_potrs_f64(self, Aptr, rhs, alpha, beta, x, info, B, n, ws, ws_bytes, stream):
-        self.thb_potrf_f64(Aptr, alpha, beta, info, B, n, ws, ws_bytes, stream)
-        if not _np_at(info, (B,), np.int32).any():
-            self.thb_potrs_f64(rhs, x, B, n, ws, ws_bytes, stream)
-        return 0
+def _emulation_mode():
+    spec = importlib.util.spec_from_file_location("emulation_mode", os.path.join(HERE, "simt", "emulation_mode.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 @pytest.fixture(scope="module")
 def emu_lib():
-    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(HERE, "simt", "build_emu.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    lib = C.CDLL(mod.build())
-    for name, (res, args) in _lib.SIGNATURES.items():
-        if hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.restype, fn.argtypes = res, args
-    return _EmulatedLib(lib)
+    return _emulation_mode().load_emulated_lib()
 
 
 @pytest.fixture
 def emulated(monkeypatch, emu_lib):
-    monkeypatch.setattr(_lib, "load", lambda: emu_lib)
-    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
-    monkeypatch.setattr(engine_mod, "_require_cuda_device", lambda device: None)
-    # the one host read per LM iteration goes through pinned memory and a stream synchronisation on the GPU
-    monkeypatch.setattr(optimizer_mod.LevenbergMarquardt, "_read_stats", lambda self, stats, B: int(stats[0]) == B)
+    _emulation_mode().patch_host(monkeypatch.setattr, emu_lib)
     return emu_lib
 
 
