@@ -11,7 +11,11 @@ count (abs/rel tolerance 0) with LM kwargs damping=1e-3, adaptive_damping=True, 
 value = LM iterations per second for the whole job (all ranks' batches advance one iteration together).
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel = the DMMA Cholesky),
-cpu_baseline (oracle port on the host cores, bounded sample), e2e (host buffers -> public API -> host result).
+cpu_baseline (oracle port on the host cores, bounded sample), e2e (host buffers -> public API -> host result), and
+`sparse_c5` -- a SECOND, separately timed workload reported beside the headline (never mixed into `value`): BASELINE.json's
+config C5 (2 500-pose sphere pose graph, batch 512 per GPU = 4096 on 8 GPUs, LM + block-sparse Cholesky), same barrier /
+CUDA-event / max-over-ranks timing, 1 warm-up + 2 timed solves; `--no-c5` skips it, a failure inside it is reported as
+`sparse_c5.error` and leaves the headline untouched.
 """
 import argparse
 import json
@@ -127,6 +131,55 @@ def cpu_baseline_run(data, sample_items, iters=LM_ITERS):
     return dt, out
 
 
+C5_RINGS, C5_PER_RING, C5_BATCH = 50, 50, 512
+
+
+def sparse_c5_leg(th, device, rank, world, pg, timed, steps=2, warmup=1):
+    """Config C5 beside the headline: sphere-like pose graph (50 rings x 50 = 2 500 SE3 poses, 4 949 edges: sphere2500's counts),
+    batch 512 per GPU (weak scaling: 4096 problems on 8 GPUs), LM (10 iterations, same kwargs) + BaspachoSparseSolver (block-sparse
+    Cholesky, batch-lane kernels) on SparseLinearization, device-resident inputs.  Returns a dict for the JSON line."""
+    import torch
+    from theseus_b200.datasets import build_pose_graph_objective, pose_graph_sphere
+    data = pose_graph_sphere(C5_RINGS, C5_PER_RING, C5_BATCH, seed=rank)
+    objective, poses = build_pose_graph_objective(th, data, device)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
+                                max_iterations=LM_ITERS, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, process_group=pg)
+    layer = th.TheseusLayer(opt)
+    inputs = {p.name: data["poses"][i].to(device) for i, p in enumerate(poses)}
+    out = {}
+
+    def step():
+        with torch.no_grad():
+            out["values"], out["info"] = layer.forward(inputs, optimizer_kwargs=LM_KW)
+
+    for _ in range(max(warmup, 1)):
+        step()
+    ms_step = timed(step, steps) / steps
+    info = out["info"]
+    lin = opt.linear_solver.linearization
+    res = dict(workload="C5: sphere-like SE3 pose graph (2 500 poses, 4 949 edges + 1 prior), batch=512 per GPU, LM(10 it, adaptive+ellipsoidal "
+                        "damping) + BaspachoSparseSolver (block-sparse Cholesky) on SparseLinearization, fp64, device-resident inputs",
+               value=LM_ITERS * 1e3 / ms_step * world, unit="LM iterations/s (one iteration = one LM step of a 512-problem batch; aggregate over GPUs)",
+               ms_per_step=ms_step, steps=steps, warmup=max(warmup, 1), batch_per_gpu=C5_BATCH, global_batch=C5_BATCH * world,
+               num_poses=len(poses), num_edges=len(data["edges"]), rows=int(lin.num_rows), cols=int(lin.num_cols),
+               problem_iterations_per_s=LM_ITERS * 1e3 / ms_step * world * C5_BATCH, layout=opt.linear_solver.layout_for(C5_BATCH),
+               final_err_mean=float(info.last_err.mean().item()))
+    try:
+        res["symbolic"] = {k: float(v) for k, v in dict(opt.linear_solver.symbolic_stats).items()}
+    except Exception:
+        pass
+    try:  # phase split of one iteration (same calls as scratch/bench_sparse.py, which produced profiles/r01f_*)
+        lam = torch.full((C5_BATCH,), 1e-3, dtype=torch.float64, device=device)
+        ms_lin = timed(lin.linearize, 3) / 3
+        ms_solve = timed(lambda: opt.linear_solver.solve(damping=lam, ellipsoidal_damping=True, damping_eps=1e-8), 3) / 3
+        res["ms_linearize"], res["ms_linear_solve"] = ms_lin, ms_solve
+        if "flops" in res.get("symbolic", {}):
+            res["factor_gflops_per_item"] = res["symbolic"]["flops"] / 1e9
+    except Exception as e:  # the split is a by-product; all ranks take the same path (deterministic), so no rank is left in a barrier
+        res["phase_split_error"] = repr(e)[:200]
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; /root/reference is Python and cannot travel to the
     GPU box) on the host cores, same metric/config; each step = a bounded sample (sample_items of the 256 batch items)."""
@@ -162,6 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the separately reported config-C5 (block-sparse) workload")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -294,6 +348,14 @@ def main():
     del a, bm
     peaks, peaks_src = _measured_peaks()
 
+    # ---- config C5 (block-sparse path), reported beside the headline; every rank runs it (weak scaling) ----
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = sparse_c5_leg(th, device, rank, world, pg, timed)
+        except Exception as e:
+            c5 = dict(error=repr(e)[:300])
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -333,7 +395,7 @@ def main():
                       peak_source="fp64 cuBLAS dgemm 8192^3 measured live in this run (MEASURED_PEAKS.json carries no fp64 figure; "
                                   f"its bf16/HBM entries [{peaks_src}]: {peaks.get('bf16_tflops')} TF/s, {peaks.get('hbm_gbs')} GB/s)",
                       share_of_step=ms_factor * LM_ITERS / ms_step),
-        cpu_baseline=cpu, final_err_mean=final_err)
+        cpu_baseline=cpu, final_err_mean=final_err, sparse_c5=c5)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

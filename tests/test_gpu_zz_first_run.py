@@ -1,0 +1,290 @@
+"""FIRST-RUN GPU tests: everything here was written after round 1's GPU budget was spent and has never executed on a device.  The file
+sorts last among the GPU test files and every test is `xfail(strict=False)`: the round-end run on the B200 box reports each one as
+XPASS (works on the device) or xfail (does not, yet) without turning the GPU-verified suite red.  Remove the mark from what XPASSes.
+
+What stands behind them without a GPU: the same kernels compiled unchanged for the host (tests/simt) run these very tests on the CPU
+(`THB_SIMT_EMULATION=1 python -m pytest tests/test_gpu_zz_first_run.py -m gpu`), the host work lists run through numpy interpreters
+(tests/test_sparse_symbolic.py), the torch routes and the oracle are checked against the reference's goldens (tests/test_torch_*.py,
+tests/test_so2.py, tests/test_robust_losses.py).  Order: host-side / torch-route features on GPU-verified kernels first, the kernels that
+are new (dense root, chain-piece substitutions, tiled updates) last.
+
+Contents: a custom VariableOrdering; GNC (Geman-McClure) costs on the engine's generic route; the batched torch route; SO2 rotation
+averaging (THB_VAR_SO2 branch of the retract kernel); config C4's cost set (planar pushing / tactile pose estimation:
+QuasiStaticPushingPlanar, EffectorObjectContactPlanar, MovingFrameBetween, SE2 priors) through the GPU engine -- LM trace and
+implicit-mode gradients against the reference (tests/golden/tactile_kat.npz); config C5's pose graph at full size; the opt-in sparse
+layouts `lane_root`, `lane_tiled`, `lane_tiled_root` and `supernodal_solve=True`."""
+import numpy as np
+import pytest
+import torch
+
+import theseus_b200 as th
+from helpers import load, decisive_iterations
+from test_gpu_backward import _golden_module
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first device run: written after the round-1 GPU budget was spent (host emulation green)")]
+LM = dict(damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)
+
+
+def _inputs(g):
+    return {k: torch.from_numpy(g[k]) for k in ("obj", "eff", "eff_meas", "mfb_meas", "c_square", "eff_radius", "sdf", "sdf_origin", "sdf_cell")}
+
+
+@pytest.mark.parametrize("solver", ["dense", "sparse"])
+def test_custom_variable_ordering_gives_the_same_iterates(solver):
+    """A custom VariableOrdering (reversed pose order) permutes the columns of the linear system and nothing else: same error trace and
+    same final poses as the default order, delta permuted blockwise (theseus/optimizer/variable_ordering.py, linearization.py:20-38)."""
+    from helpers import pgo_objective, lm_kwargs_of
+    g = load("pgo_small_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(
+        linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization)
+    runs = {}
+    for mode in ("default", "reversed"):
+        objective, poses = pgo_objective(th, g)
+        lkw = {}
+        if mode == "reversed":
+            order = th.VariableOrdering(objective, default_order=False)
+            order.extend(list(reversed(poses)))
+            lkw = dict(linearization_kwargs=dict(ordering=order))
+        opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw, **lkw)
+        errs, deltas = [], []
+
+        def cb(optimizer, info, delta, it):
+            errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+        with torch.no_grad():
+            opt.optimize(end_iter_callback=cb, **kw)
+        runs[mode] = (np.stack(errs, 0), np.stack(deltas, 0), np.stack([p.tensor.cpu().numpy() for p in poses], 0))
+    np.testing.assert_allclose(runs["reversed"][0], g["trace_err"], rtol=1e-8)
+    N = len(runs["default"][2])
+    d_def = runs["default"][1].reshape(iters, -1, N, 6)
+    d_rev = runs["reversed"][1].reshape(iters, -1, N, 6)[:, :, ::-1]
+    rel = np.linalg.norm((d_def - d_rev).reshape(iters, -1), axis=1) / np.linalg.norm(d_def.reshape(iters, -1), axis=1)
+    assert rel[:2].max() < 1e-6, rel
+    np.testing.assert_allclose(runs["reversed"][2], g["poses_final"], rtol=1e-6, atol=1e-6)
+
+
+def test_gnc_robust_costs_on_the_generic_route_match_reference_trace():
+    """GNCRobustCostFunction(Between, GemanMcClureLoss) has no fused kernel: the engine's generic route (torch.func Jacobians of the wrapped
+    Between, rescaled in torch: core.RobustCostFunction.generic_jacobians_error / generic_error) must reproduce the reference's LM trace
+    (tests/golden/pgo_small_geman.npz).  The torch functions themselves are checked on the CPU (tests/test_robust_losses.py), the oracle's
+    trace in tests/test_oracle_nls.py."""
+    from test_gpu_lm import _run
+    g = load("pgo_small_geman")
+    method, iters, kw, values, info, trace, poses, inputs = _run(g)
+    np.testing.assert_allclose(np.stack(trace["err"], 0), g["trace_err"], rtol=1e-8)
+    from helpers import pgo_spec
+    from oracle import nls
+    spec = pgo_spec(g)
+    err0 = nls.error_metric(spec, [v["value"] for v in spec["vars"]])
+    for it in range(decisive_iterations(err0, g["trace_err"])):
+        dref = g["trace_delta"][it]
+        rel = np.linalg.norm(trace["delta"][it] - dref, axis=1) / np.linalg.norm(dref, axis=1)
+        assert rel.max() < 1e-5, (it, rel)
+        np.testing.assert_allclose(trace["lam"][it], g["trace_lam"][it], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["pgo_small_welsch", "pgo_small_geman"])
+def test_batched_torch_route_equals_per_cost_loop_on_the_gpu(name, monkeypatch):
+    """THB_BATCHED_TORCH_ROUTE=1 (torch_route.py: one vmap(jacrev) per group of stackable cost functions) against the per-cost loop, inside
+    the engine: taped linearization of every cost function, and linearization + error metric of the generic ones (Geman-McClure).  The
+    route itself is compared with the loop on the CPU for every kind of objective (tests/test_torch_route.py)."""
+    from helpers import pgo_objective
+    g = load(name)
+    objective, poses = pgo_objective(th, g)
+    eng = objective.engine()
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("THB_BATCHED_TORCH_ROUTE", flag)
+        A, b = eng.linearize_sparse_differentiable()
+        A2, b2 = eng.linearize_sparse()
+        outs[flag] = (A.detach().cpu().numpy(), b.detach().cpu().numpy(), A2.cpu().numpy().copy(), b2.cpu().numpy().copy(),
+                      eng.error_metric().cpu().numpy().copy())
+    for x0, x1 in zip(outs["0"], outs["1"]):
+        np.testing.assert_allclose(x1, x0, rtol=1e-12, atol=1e-13 * np.abs(x0).max())
+    np.testing.assert_allclose(outs["1"][0], outs["1"][2], rtol=1e-7, atol=1e-9 * np.abs(outs["1"][2]).max())   # taped (autodiff) == fused-kernel (analytic) values
+
+
+def test_so2_rotation_averaging_lm_trace():
+    """SO2 variables (geometry.SO2, retracted by the fused retract kernel's THB_VAR_SO2 branch) with Between / Difference costs on the
+    engine's generic route: LM trace against the reference (tests/golden/so2_kat.npz; the oracle reproduces the same trace on the CPU,
+    tests/test_so2.py)."""
+    G, g = _golden_module(), load("so2_kat")
+    objective, vs = G.so2_problem(th, torch, torch.from_numpy(g["lm_thetas0"]), torch.from_numpy(g["lm_meas"]),
+                                  [tuple(int(x) for x in e) for e in g["lm_edges"]], g["lm_w_edge"], float(g["lm_w_prior"]), device="cuda")
+    iters = g["lm_trace_err"].shape[0]
+    for skw in (dict(linear_solver_cls=th.CholeskyDenseSolver),
+                dict(linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization)):
+        for i, v in enumerate(vs):
+            v.update(th.SO2(theta=torch.from_numpy(g["lm_thetas0"][i]).cuda()).tensor)
+        opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw)
+        errs, deltas = [], []
+
+        def cb(optimizer, info, delta, it):
+            errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+        with torch.no_grad():
+            np.testing.assert_allclose(objective.error_metric().cpu().numpy(), g["lm_err0"], rtol=1e-12)
+            opt.optimize(end_iter_callback=cb, damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)
+        np.testing.assert_allclose(np.stack(errs, 0), g["lm_trace_err"], rtol=1e-9)
+        for it in range(iters):
+            np.testing.assert_allclose(deltas[it], g["lm_trace_delta"][it], rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose(np.stack([v.tensor.cpu().numpy() for v in vs], 0), g["lm_final"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("solver", ["dense", "sparse"])
+def test_tactile_lm_trace(solver):
+    G, g = _golden_module(), load("tactile_kat")
+    objective, objs, effs, leaves = G.tactile_problem(th, torch, _inputs(g), device="cuda")
+    skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(
+        linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization)
+    opt = th.LevenbergMarquardt(objective, max_iterations=g["trace_err"].shape[0], step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw)
+    errs, deltas = [], []
+
+    def cb(optimizer, info, delta, it):
+        errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+    with torch.no_grad():
+        np.testing.assert_allclose(objective.error_metric().cpu().numpy(), g["err0"], rtol=1e-10)
+        opt.optimize(end_iter_callback=cb, **LM)
+    np.testing.assert_allclose(np.stack(errs, 0), g["trace_err"], rtol=1e-7)
+    k = decisive_iterations(g["err0"], g["trace_err"])
+    for it in range(k):
+        rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
+        assert rel.max() < 1e-5, (it, rel)
+    np.testing.assert_allclose(np.stack([o.tensor.cpu().numpy() for o in objs], 0), g["final_obj"], rtol=1e-5, atol=1e-6)
+
+
+def test_tactile_implicit_gradients():
+    G, g = _golden_module(), load("tactile_kat")
+    objective, objs, effs, leaves = G.tactile_problem(th, torch, _inputs(g), device="cuda")
+    for v in leaves.values():
+        v.tensor.requires_grad_(True)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=8, step_size=1.0, abs_err_tolerance=0,
+                                rel_err_tolerance=0)
+    sol, info = th.TheseusLayer(opt).forward({v.name: v.tensor.clone() for v in objs + effs}, optimizer_kwargs=dict(LM, backward_mode="implicit"))
+    gen = torch.Generator().manual_seed(5)
+    P = torch.stack([sol[o.name] for o in objs], 0)
+    (P * torch.randn(P.shape, generator=gen, dtype=torch.float64).cuda()).sum().backward()
+    for k, v in leaves.items():
+        ref = g["grad_" + k]
+        assert np.abs(v.tensor.grad.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), k
+
+
+@pytest.mark.parametrize("layout", ["item", "lane", "lane_root"])
+def test_c5_full_size_sparse_lm_trace(layout):
+    """Config C5's pose graph at full size (2 500 poses, n = 15 000), one batch item: the block-sparse solver's LM trace against the
+    reference's dense-solver trace (tests/golden/pgo_c5_lm.npz, generated on the CPU by make_golden.py c5).  Same parked status."""
+    from helpers import pgo_objective, lm_kwargs_of
+    g = load("pgo_c5_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
+                                max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0,
+                                linear_solver_kwargs=dict(layout=layout))
+    errs, deltas = [], []
+
+    def cb(optimizer, info, delta, it):
+        errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+    with torch.no_grad():
+        np.testing.assert_allclose(objective.error_metric().cpu().numpy(), g["err0"], rtol=1e-10)
+        opt.optimize(end_iter_callback=cb, **kw)
+    np.testing.assert_allclose(np.stack(errs, 0), g["trace_err"], rtol=1e-7)
+    for it in range(decisive_iterations(g["err0"], g["trace_err"])):
+        rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
+        assert rel.max() < 1e-5, (it, rel)
+
+
+def test_lane_root_layout_matches_lane_layout():
+    """Opt-in layout='lane_root' (dense DMMA factorisation of the top chain of the elimination tree, sparse.root_split) against the plain
+    lane layout and the dense residual, on a ring-with-chords structure whose minimum-degree order ends in a dense separator chain.
+    The host half (work lists) is verified on the CPU: tests/test_sparse_symbolic.py::test_root_split_solves_system."""
+    from theseus_b200.structure import build_structure
+    from test_gpu_sparse_solver import _dense_system
+    rng = np.random.default_rng(5)
+    N, B = 60, 70
+    costs = [(3, [i, (i + 1) % N]) for i in range(N)] + [(3, [i, (i + 7) % N]) for i in range(N)] + [(6, [i]) for i in range(N)]
+    costs = [(d, sorted(vs)) for d, vs in costs]
+    S = build_structure([6] * N, costs)
+    A_val = torch.from_numpy(rng.standard_normal((B, S.nnz))).cuda()
+    b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
+    alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
+    xs = {}
+    for layout in ("lane_root", "lane"):
+        solver = th.BaspachoSparseSolver.from_structure(S, layout=layout)
+        solver.linearization.A_val, solver.linearization.b = A_val, b
+        xs[layout] = (solver.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-6).cpu().numpy(), solver.solve().cpu().numpy())
+        if layout == "lane_root":
+            assert solver._root is not None and solver._dev["nt"] >= 48
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    for k, (mul, add) in enumerate(((1 + alpha.cpu().numpy()[:, None], 1e-6), (1.0, 0.0))):
+        M = AtA.copy()
+        M[:, idx, idx] = M[:, idx, idx] * mul + add
+        res = np.einsum("bij,bj->bi", M, xs["lane_root"][k]) - Atb
+        assert np.abs(res).max() < 1e-10 * np.abs(M).sum(axis=2).max() * max(1.0, np.abs(xs["lane_root"][k]).max())
+        assert np.abs(xs["lane_root"][k] - xs["lane"][k]).max() < 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(xs["lane"][k]).max())
+
+
+@pytest.mark.parametrize("layout", ["lane", "lane_root", "lane_tiled_root"])
+@pytest.mark.parametrize("B", [32, 70])
+def test_supernodal_substitutions_match_per_column_substitutions(layout, B):
+    """supernodal_solve=True (chain-piece forward / backward kernels, thb_sparse_lane.cu:lane_piece_forward_kernel / _backward_kernel,
+    lists sparse.piece_solve_lists) against the per-column substitution kernels on the same factor, and the dense residual.  The schedule
+    is verified on the CPU: tests/test_sparse_symbolic.py::test_piece_solve_schedule_solves_system."""
+    from theseus_b200.structure import build_structure
+    from test_gpu_sparse_solver import _dense_system
+    rng = np.random.default_rng(19 + B)
+    N = 60
+    costs = [(3, [i, (i + 1) % N]) for i in range(N)] + [(3, [i, (i + 7) % N]) for i in range(N)] + [(6, [i]) for i in range(N)]
+    costs = [(d, sorted(vs)) for d, vs in costs]
+    S = build_structure([6] * N, costs)
+    A_val = torch.from_numpy(rng.standard_normal((B, S.nnz))).cuda()
+    b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
+    alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
+    xs = {}
+    for sn in (True, False):
+        solver = th.BaspachoSparseSolver.from_structure(S, layout=layout, supernodal_solve=sn)
+        solver.linearization.A_val, solver.linearization.b = A_val, b
+        xs[sn] = solver.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-6).cpu().numpy()
+        assert ("pieces" in solver._dev) == sn
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    M = AtA.copy()
+    M[:, idx, idx] = M[:, idx, idx] * (1 + alpha.cpu().numpy()[:, None]) + 1e-6
+    res = np.einsum("bij,bj->bi", M, xs[True]) - Atb
+    assert np.abs(res).max() < 1e-10 * np.abs(M).sum(axis=2).max() * max(1.0, np.abs(xs[True]).max())
+    assert np.abs(xs[True] - xs[False]).max() < 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(xs[False]).max())
+
+
+@pytest.mark.parametrize("tiled", ["lane_tiled", "lane_tiled_root"])
+@pytest.mark.parametrize("B", [32, 70])
+def test_lane_tiled_layout_matches_lane_layout(B, tiled):
+    """Opt-in layouts 'lane_tiled' / 'lane_tiled_root' (the latter: + dense root, its assembly as one tile launch) (external updates of chain pieces as 4x4 tiles with the source blocks staged in shared memory,
+    thb_sparse_lane.cu:lane_tile_update_kernel) against the plain lane layout and the dense residual; same ring-with-chords structure
+    (its elimination tree has chains of every width up to the dense separator).  The host half (flat tile arrays) is verified on the
+    CPU: tests/test_sparse_symbolic.py::test_tiled_lane_lists_solve_system."""
+    from theseus_b200.structure import build_structure
+    from test_gpu_sparse_solver import _dense_system
+    rng = np.random.default_rng(11 + B)
+    N = 60
+    costs = [(3, [i, (i + 1) % N]) for i in range(N)] + [(3, [i, (i + 7) % N]) for i in range(N)] + [(6, [i]) for i in range(N)]
+    costs = [(d, sorted(vs)) for d, vs in costs]
+    S = build_structure([6] * N, costs)
+    A_val = torch.from_numpy(rng.standard_normal((B, S.nnz))).cuda()
+    b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
+    alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
+    xs = {}
+    for layout in (tiled, "lane"):
+        solver = th.BaspachoSparseSolver.from_structure(S, layout=layout)
+        solver.linearization.A_val, solver.linearization.b = A_val, b
+        xs[layout] = (solver.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-6).cpu().numpy(), solver.solve().cpu().numpy())
+        if layout == tiled:
+            assert solver._tiles[1]["tile_tgt"].shape[0] > 0
+    xs["lane_tiled"] = xs[tiled]
+    AtA, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    for k, (mul, add) in enumerate(((1 + alpha.cpu().numpy()[:, None], 1e-6), (1.0, 0.0))):
+        M = AtA.copy()
+        M[:, idx, idx] = M[:, idx, idx] * mul + add
+        res = np.einsum("bij,bj->bi", M, xs["lane_tiled"][k]) - Atb
+        assert np.abs(res).max() < 1e-10 * np.abs(M).sum(axis=2).max() * max(1.0, np.abs(xs["lane_tiled"][k]).max())
+        assert np.abs(xs["lane_tiled"][k] - xs["lane"][k]).max() < 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(xs["lane"][k]).max())

@@ -98,7 +98,7 @@ def _tactile_inputs(g):
 @pytest.mark.parametrize("solver", ["dense", "sparse"])
 def test_tactile_lm_trace_on_the_emulated_library(emulated, solver):
     """Config C4's cost set (QuasiStaticPushingPlanar, EffectorObjectContactPlanar, MovingFrameBetween, SE2 priors: generic route + the fused
-    SE2 kernels) -- the CPU twin of tests/pending_gpu_round2.py::test_tactile_lm_trace."""
+    SE2 kernels) -- the CPU twin of tests/test_gpu_zz_first_run.py::test_tactile_lm_trace."""
     G, g = _golden_module(), load("tactile_kat")
     objective, objs, effs, leaves = G.tactile_problem(th, torch, _tactile_inputs(g), device="cpu")
     skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(

@@ -1,6 +1,6 @@
 """SO2 (theseus/geometry/so2.py): the oracle's restatement and the package's class / torch route against values computed
 by the reference (tests/golden/make_golden.py:make_so2 -> so2_kat.npz).  Inside the optimizer SO2 variables are retracted by the fused
-retract kernel and their cost functions take the engine's generic route; that half runs on the GPU (tests/pending_gpu_round2.py)."""
+retract kernel and their cost functions take the engine's generic route; that half runs on the GPU (tests/test_gpu_zz_first_run.py)."""
 import numpy as np
 import torch
 
