@@ -134,7 +134,7 @@ def cpu_baseline_run(data, sample_items, iters=LM_ITERS):
 C5_RINGS, C5_PER_RING, C5_BATCH = 50, 50, 512
 
 
-def sparse_c5_leg(th, device, rank, world, pg, timed, steps=2, warmup=1):
+def sparse_c5_leg(th, device, rank, world, pg, timed, steps=2, warmup=1, layout=None, supernodal=False):
     """Config C5 beside the headline: sphere-like pose graph (50 rings x 50 = 2 500 SE3 poses, 4 949 edges: sphere2500's counts),
     batch 512 per GPU (weak scaling: 4096 problems on 8 GPUs), LM (10 iterations, same kwargs) + BaspachoSparseSolver (block-sparse
     Cholesky, batch-lane kernels) on SparseLinearization, device-resident inputs.  Returns a dict for the JSON line."""
@@ -143,7 +143,8 @@ def sparse_c5_leg(th, device, rank, world, pg, timed, steps=2, warmup=1):
     data = pose_graph_sphere(C5_RINGS, C5_PER_RING, C5_BATCH, seed=rank)
     objective, poses = build_pose_graph_objective(th, data, device)
     opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
-                                max_iterations=LM_ITERS, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, process_group=pg)
+                                max_iterations=LM_ITERS, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, process_group=pg,
+                                linear_solver_kwargs=dict(layout=layout, supernodal_solve=bool(supernodal)))
     layer = th.TheseusLayer(opt)
     inputs = {p.name: data["poses"][i].to(device) for i, p in enumerate(poses)}
     out = {}
@@ -162,7 +163,7 @@ def sparse_c5_leg(th, device, rank, world, pg, timed, steps=2, warmup=1):
                value=LM_ITERS * 1e3 / ms_step * world, unit="LM iterations/s (one iteration = one LM step of a 512-problem batch; aggregate over GPUs)",
                ms_per_step=ms_step, steps=steps, warmup=max(warmup, 1), batch_per_gpu=C5_BATCH, global_batch=C5_BATCH * world,
                num_poses=len(poses), num_edges=len(data["edges"]), rows=int(lin.num_rows), cols=int(lin.num_cols),
-               problem_iterations_per_s=LM_ITERS * 1e3 / ms_step * world * C5_BATCH, layout=opt.linear_solver.layout_for(C5_BATCH),
+               problem_iterations_per_s=LM_ITERS * 1e3 / ms_step * world * C5_BATCH, layout=opt.linear_solver.layout_for(C5_BATCH), supernodal_solve=bool(supernodal),
                final_err_mean=float(info.last_err.mean().item()))
     try:
         res["symbolic"] = {k: float(v) for k, v in dict(opt.linear_solver.symbolic_stats).items()}
@@ -178,6 +179,60 @@ def sparse_c5_leg(th, device, rank, world, pg, timed, steps=2, warmup=1):
     except Exception as e:  # the split is a by-product; all ranks take the same path (deterministic), so no rank is left in a barrier
         res["phase_split_error"] = repr(e)[:200]
     return res
+
+
+FIRST_RUN_LAYOUTS = (("lane_root", "lane_root", False), ("lane_tiled_root", "lane_tiled_root", False),
+                     ("lane_tiled_root+supernodal_solve", "lane_tiled_root", True))
+
+
+def run_c5_layout_child(args):
+    """`bench.py --c5-layout L [--c5-supernodal]`: the C5 workload with ONE explicit sparse layout on cuda:0, one JSON line.  Used by the
+    parent run (N=1) for the opt-in layouts that had not run on a device when round 1's GPU budget ended -- a separate process, so a
+    failing kernel cannot touch the parent's CUDA context or its headline numbers."""
+    import torch
+    import theseus_b200 as th
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return float(e0.elapsed_time(e1))
+
+    res = sparse_c5_leg(th, device, 0, 1, None, timed, layout=args.c5_layout, supernodal=args.c5_supernodal)
+    for k in ("workload", "unit", "symbolic"):
+        res.pop(k, None)
+    print(json.dumps(res))
+
+
+def first_run_layouts(lane_result, timeout_s=200):
+    """N=1 only, after everything else is measured: the opt-in sparse layouts, each in its own process (run_c5_layout_child) under a
+    timeout.  Same data as the parent's `lane` run (seed 0), so `final_err_mean` must agree with it."""
+    out = {}
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    for tag, layout, supernodal in FIRST_RUN_LAYOUTS:
+        cmd = [sys.executable, os.path.abspath(__file__), "--c5-layout", layout] + (["--c5-supernodal"] if supernodal else [])
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and lines:
+                res = json.loads(lines[-1])
+                ref = (lane_result or {}).get("final_err_mean")
+                if ref:
+                    res["final_err_rel_diff_vs_lane"] = abs(res["final_err_mean"] - ref) / abs(ref)
+                out[tag] = res
+            else:
+                out[tag] = dict(error=f"exit code {r.returncode}", stderr_tail=r.stderr[-400:])
+        except subprocess.TimeoutExpired:
+            out[tag] = dict(error=f"timeout after {timeout_s} s")
+        except Exception as e:
+            out[tag] = dict(error=repr(e)[:300])
+    return out
 
 
 def run_reference(args):
@@ -216,9 +271,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the separately reported config-C5 (block-sparse) workload")
+    ap.add_argument("--no-first-run-layouts", action="store_true", help="skip the child runs of the opt-in sparse layouts (N=1 only)")
+    ap.add_argument("--c5-layout", default=None, help="child mode: config C5 with this sparse layout on cuda:0, one JSON line")
+    ap.add_argument("--c5-supernodal", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.c5_layout is not None:
+        return run_c5_layout_child(args)
 
     import torch
     import torch.distributed as dist
@@ -396,6 +456,8 @@ def main():
                                   f"its bf16/HBM entries [{peaks_src}]: {peaks.get('bf16_tflops')} TF/s, {peaks.get('hbm_gbs')} GB/s)",
                       share_of_step=ms_factor * LM_ITERS / ms_step),
         cpu_baseline=cpu, final_err_mean=final_err, sparse_c5=c5)
+    if world == 1 and c5 is not None and "error" not in c5 and not args.no_first_run_layouts:
+        c5["first_run_layouts"] = first_run_layouts(c5)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
