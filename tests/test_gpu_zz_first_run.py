@@ -8,7 +8,7 @@ What stands behind them without a GPU: the same kernels compiled unchanged for t
 tests/test_so2.py, tests/test_robust_losses.py).  Order: host-side / torch-route features on GPU-verified kernels first, the kernels that
 are new (dense root, chain-piece substitutions, tiled updates) last.
 
-Contents: a custom VariableOrdering; GNC (Geman-McClure) costs on the engine's generic route; the batched torch route; SO2 rotation
+Contents: a custom VariableOrdering; user-defined CostFunction / CostWeight subclasses (tests/user_costs.py); GNC (Geman-McClure) costs on the engine's generic route; the batched torch route; SO2 rotation
 averaging (THB_VAR_SO2 branch of the retract kernel); config C4's cost set (planar pushing / tactile pose estimation:
 QuasiStaticPushingPlanar, EffectorObjectContactPlanar, MovingFrameBetween, SE2 priors) through the GPU engine -- LM trace and
 implicit-mode gradients against the reference (tests/golden/tactile_kat.npz); config C5's pose graph at full size; the opt-in sparse
@@ -167,6 +167,60 @@ def test_tactile_implicit_gradients():
     for k, v in leaves.items():
         ref = g["grad_" + k]
         assert np.abs(v.tensor.grad.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), k
+
+
+def test_user_defined_costs_linearize_exactly_on_the_gpu():
+    """User-defined CostFunction / CostWeight subclasses (the reference's plugin contract) through the engine's generic route on the
+    device: the hand-written 6 x 10 system of the reference's linearization tests, dense and sparse (tests/user_costs.py; CPU twin on
+    the host emulation: tests/test_user_defined_costs.py)."""
+    import user_costs
+    objective, ordering, A, b = user_costs.mock_linear_system(th, device="cuda")
+    lin = th.DenseLinearization(objective, ordering=ordering)
+    lin.linearize()
+    np.testing.assert_allclose(lin.A.cpu().numpy(), A.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(lin.b.cpu().numpy(), b.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(lin.AtA.cpu().numpy(), (A.transpose(1, 2) @ A).numpy(), rtol=1e-14)
+    Atb = (A.transpose(1, 2) @ b.unsqueeze(2)).squeeze(2).numpy()
+    np.testing.assert_allclose(lin.Atb.cpu().numpy().reshape(A.shape[0], -1), Atb, rtol=1e-14)
+    slin = th.SparseLinearization(objective, ordering=ordering)
+    slin.linearize()
+    rp, ci, val = np.asarray(slin.A_row_ptr), np.asarray(slin.A_col_ind), slin.A_val.cpu().numpy()
+    dense = np.zeros(A.shape)
+    for r in range(A.shape[1]):
+        dense[:, r, ci[rp[r]:rp[r + 1]]] = val[:, rp[r]:rp[r + 1]]
+    np.testing.assert_allclose(dense, A.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(slin.Atb.cpu().numpy().reshape(A.shape[0], -1), Atb, rtol=1e-14)
+    v = torch.randn(A.shape[0], A.shape[2], generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    np.testing.assert_allclose(slin.Av(v.cuda()).cpu().numpy(), (A @ v.unsqueeze(2)).squeeze(2).numpy(), rtol=1e-13)
+    np.testing.assert_allclose(slin.diagonal_scaling(v.cuda()).cpu().numpy(), ((A * A).sum(dim=1) * v).numpy(), rtol=1e-13)
+
+
+_LM_GRID = [dict(damping=d, ellipsoidal_damping=e, adaptive_damping=a, damping_eps=0.0)
+            for d in (0.0, 0.001, 0.01, 0.1) for e in (True, False) for a in (True, False)]
+
+
+@pytest.mark.parametrize("multivar", [False, True])
+@pytest.mark.parametrize("case", [("gn", {}), ("dogleg", {})] + [("lm", kw) for kw in _LM_GRID])
+def test_regression_with_user_defined_costs_on_the_gpu(case, multivar):
+    """The reference's optimizer-level check (tests/theseus_tests/optimizer/nonlinear/common.py:118-215, the whole LM grid of
+    test_levenberg_marquardt.py:25-39, batch 32, 50 points): every variant recovers the true coefficients with user-defined cost
+    functions; info bookkeeping as in common.py:91-97."""
+    import user_costs
+    method, kw = case
+    batch_size, iters = 32, 20
+    objective, variables = user_costs.regression_problem(th, multivar, device="cuda", batch_size=batch_size)
+    initial_error = objective.error_metric().clone()
+    opt = {"gn": th.GaussNewton, "lm": th.LevenbergMarquardt, "dogleg": th.Dogleg}[method](objective)
+    opt.set_params(max_iterations=iters)
+    with torch.no_grad():
+        info = opt.optimize(track_best_solution=True, track_err_history=True, **kw)
+    coeffs = torch.cat([v.tensor for v in variables], dim=1).cpu().numpy()
+    np.testing.assert_allclose(coeffs, np.ones((batch_size, 5)), rtol=1e-5, atol=1e-6)
+    hist = info.err_history.cpu()
+    assert hist.shape == (batch_size, iters + 1)
+    assert torch.allclose(hist[:, 0], initial_error.cpu().to(hist.dtype))
+    assert torch.equal(hist.argmin(dim=1), info.best_iter.cpu() + 1)
+    assert torch.allclose(hist[:, int(info.converged_iter.max())], objective.error_metric().cpu().to(hist.dtype))
 
 
 @pytest.mark.parametrize("layout", ["item", "lane", "lane_root"])

@@ -1,0 +1,138 @@
+"""The reference's plugin contract for cost functions and cost weights -- subclass th.CostFunction / th.CostWeight, register variables,
+implement error() / jacobians() / dim() (theseus/core/cost_function.py:64-149, cost_weight.py:20-55) -- through the engine's generic route,
+on the CPU with the CUDA library replaced by its host emulation (tests/simt).  Problems: tests/user_costs.py (restatements of the
+reference's own linearization_test_utils.py:122-196 and nonlinear/common.py:14-315).  The GPU twins are in tests/test_gpu_zz_first_run.py."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import theseus_b200 as th
+import user_costs
+from test_simt_engine_emulation import emu_lib, emulated  # noqa: F401  (fixtures)
+
+
+def test_dense_linearization_of_user_defined_costs_is_exact(emulated):
+    """test_dense_linearization.py:15-31: A, b, AtA, Atb of the 6 x 10 system, custom column order, custom matrix weights."""
+    objective, ordering, A, b = user_costs.mock_linear_system(th)
+    lin = th.DenseLinearization(objective, ordering=ordering)
+    lin.linearize()
+    assert lin.b.ndim == 2 and lin.A.shape == A.shape
+    np.testing.assert_allclose(lin.A.numpy(), A.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(lin.b.numpy(), b.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(lin.AtA.numpy(), (A.transpose(1, 2) @ A).numpy(), rtol=1e-14)
+    np.testing.assert_allclose(lin.Atb.numpy().reshape(A.shape[0], -1), (A.transpose(1, 2) @ b.unsqueeze(2)).squeeze(2).numpy(), rtol=1e-14)
+
+
+def test_sparse_linearization_of_user_defined_costs_is_exact(emulated):
+    """test_sparse_linearization.py:15-49: CSR -> dense equals A; Atb, Av and diagonal_scaling against the dense forms."""
+    objective, ordering, A, b = user_costs.mock_linear_system(th)
+    lin = th.SparseLinearization(objective, ordering=ordering)
+    lin.linearize()
+    B = A.shape[0]
+    rp, ci = np.asarray(lin.A_row_ptr), np.asarray(lin.A_col_ind)
+    dense = np.zeros(A.shape)
+    for r in range(A.shape[1]):
+        dense[:, r, ci[rp[r]:rp[r + 1]]] = lin.A_val.numpy()[:, rp[r]:rp[r + 1]]
+    np.testing.assert_allclose(dense, A.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(lin.b.numpy(), b.numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(lin.Atb.numpy().reshape(B, -1), (A.transpose(1, 2) @ b.unsqueeze(2)).squeeze(2).numpy(), rtol=1e-14)
+    v = torch.randn(B, A.shape[2], generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    np.testing.assert_allclose(lin.Av(v).numpy(), (A @ v.unsqueeze(2)).squeeze(2).numpy(), rtol=1e-13)
+    diag = (A * A).sum(dim=1)
+    np.testing.assert_allclose(lin.diagonal_scaling(v).numpy(), (diag * v).numpy(), rtol=1e-13)
+
+
+def _check_info(info, batch_size, max_iterations, initial_error, objective):
+    """nonlinear/common.py:91-97."""
+    assert info.err_history.shape == (batch_size, max_iterations + 1)
+    hist = info.err_history                      # float32 on the CPU, like the reference's (nonlinear_optimizer.py:131-150)
+    assert torch.allclose(hist[:, 0], initial_error.cpu().to(hist.dtype))
+    assert torch.equal(info.err_history.argmin(dim=1), info.best_iter + 1)
+    last = objective.error_metric().cpu()
+    assert torch.allclose(hist[:, int(info.converged_iter.max())], last.to(hist.dtype))
+
+
+LM_GRID = [dict(damping=d, ellipsoidal_damping=e, adaptive_damping=a, damping_eps=0.0)
+           for d in (0.0, 0.001, 0.1) for e in (True, False) for a in (True, False)]
+
+
+@pytest.mark.parametrize("multivar", [False, True])
+@pytest.mark.parametrize("case", [("gn", {})] + [("lm", kw) for kw in LM_GRID[::3]] + [("dogleg", {})])
+def test_regression_with_user_defined_costs_recovers_coefficients(emulated, case, multivar):
+    """test_gauss_newton.py / test_levenberg_marquardt.py:25-39 / test_dogleg.py through nonlinear/common.py:118-215 (a subset of the LM
+    grid here; the GPU twin runs all of it)."""
+    method, kw = case
+    batch_size, iters = 8, 20
+    objective, variables = user_costs.regression_problem(th, multivar, batch_size=batch_size, npoints=20)
+    initial_error = objective.error_metric().clone()
+    cls = {"gn": th.GaussNewton, "lm": th.LevenbergMarquardt, "dogleg": th.Dogleg}[method]
+    opt = cls(objective)
+    assert isinstance(opt.linear_solver, th.CholeskyDenseSolver)
+    opt.set_params(max_iterations=iters)
+    calls = []
+
+    def cb(o, info, delta, it):
+        assert o is opt and isinstance(info, th.OptimizerInfo) and torch.is_tensor(delta) and it == len(calls)
+        calls.append(it)
+    with torch.no_grad():
+        info = opt.optimize(track_best_solution=True, track_err_history=True, end_iter_callback=cb, **kw)
+    coeffs = torch.cat([v.tensor for v in variables], dim=1)
+    np.testing.assert_allclose(coeffs.numpy(), np.ones((batch_size, 5)), rtol=1e-5, atol=1e-6)   # torch.allclose defaults, as in the reference
+    _check_info(info, batch_size, iters, initial_error, objective)
+
+
+def test_singular_system_of_a_user_defined_cost_fails_like_the_reference(emulated):
+    """nonlinear/common.py:215-280: a singular system raises RuntimeError with gradients enabled and, under no_grad, warns and reports
+    status FAIL for every batch item."""
+    class ZeroJacobianCost(th.CostFunction):
+        def __init__(self, var, cost_weight):
+            super().__init__(cost_weight)
+            self.var = var
+            self.register_optim_var("var")
+
+        def dim(self):
+            return 1
+
+        def error(self):
+            return torch.ones_like(self.var.tensor)
+
+        def jacobians(self):
+            return [torch.zeros(self.var.tensor.shape[0], 1, 1, dtype=self.var.dtype)], self.error()
+
+    objective = th.Objective(dtype=torch.float64)
+    objective.add(ZeroJacobianCost(th.Vector(1, name="dummy", dtype=torch.float64), th.ScaleCostWeight(torch.ones(1, dtype=torch.float64))))
+    objective.update({"dummy": torch.zeros(3, 1, dtype=torch.float64)})
+    opt = th.GaussNewton(objective, max_iterations=5)
+    with pytest.raises(RuntimeError):
+        opt.optimize(track_best_solution=True)
+    with pytest.warns(RuntimeWarning):
+        with torch.no_grad():
+            info = opt.optimize(track_best_solution=True, track_err_history=True)
+    assert (info.status == th.NonlinearOptimizerStatus.FAIL).all()
+
+
+def test_public_cost_function_interface_on_built_in_costs():
+    """cost_function.py:85-122 on a built-in cost function (torch restatement, no library call): error / jacobians /
+    weighted_error / weighted_jacobians_error are consistent with each other and with the cost weight."""
+    gen = torch.Generator().manual_seed(3)
+    a = th.rand_se3(4, generator=gen, dtype=torch.float64)
+    b = th.rand_se3(4, generator=gen, dtype=torch.float64)
+    z = th.rand_se3(4, generator=gen, dtype=torch.float64)
+    w = th.DiagonalCostWeight(torch.linspace(0.5, 3.0, 6, dtype=torch.float64).view(1, 6))
+    cf = th.Between(a, b, z, w)
+    with torch.no_grad():
+        e = cf.error()
+        jacs, e2 = cf.jacobians()
+        we = cf.weighted_error()
+        wj, we2 = cf.weighted_jacobians_error()
+    assert e.shape == (4, 6) and [tuple(J.shape) for J in jacs] == [(4, 6, 6), (4, 6, 6)]
+    torch.testing.assert_close(e, e2)
+    torch.testing.assert_close(we, e * w.diagonal.tensor)
+    torch.testing.assert_close(we, we2)
+    for J, WJ in zip(jacs, wj):
+        torch.testing.assert_close(WJ, J * w.diagonal.tensor.unsqueeze(2))
+    wj3, we3 = w.weight_jacobians_and_error(jacs, e)
+    torch.testing.assert_close(we3, we)
+    torch.testing.assert_close(wj3[1], wj[1])

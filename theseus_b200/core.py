@@ -27,16 +27,44 @@ WEIGHT_SCALE, WEIGHT_DIAGONAL = 0, 1
 
 
 class CostWeight:
+    """theseus/core/cost_weight.py:20-55.  A user-defined subclass (WEIGHT_KIND -1) registers its auxiliary variables and implements
+    weight_error / weight_jacobians_and_error; cost functions carrying one take the engine's generic route."""
     WEIGHT_KIND = -1
 
     def __init__(self, name: Optional[str] = None):
         self.name = name or f"{self.__class__.__name__}__{id(self)}"
+        self._aux_vars_attr_names: List[str] = []
+
+    def register_aux_var(self, name: str):
+        self._aux_vars_attr_names.append(name)
+
+    def register_aux_vars(self, names: Sequence[str]):
+        self._aux_vars_attr_names.extend(names)
+
+    @property
+    def aux_vars(self) -> List[Variable]:
+        if self.WEIGHT_KIND >= 0:
+            return [self.weight_tensor()]
+        return [getattr(self, n) for n in getattr(self, "_aux_vars_attr_names", [])]
 
     def weight_tensor(self) -> Variable:
         raise NotImplementedError
 
+    def weight_error(self, error: torch.Tensor) -> torch.Tensor:
+        """cost_weight.py:33-35."""
+        return self.weight_jacobians_and_error([], error)[1]
+
+    def weight_jacobians_and_error(self, jacobians, error):
+        """cost_weight.py:37-43 (Scale: :81-90, Diagonal: :125-136): (w J_i, w e)."""
+        if self.WEIGHT_KIND < 0:
+            raise NotImplementedError
+        w = self.weight_tensor().tensor
+        w = w.view(-1, 1) if self.WEIGHT_KIND == WEIGHT_SCALE else w
+        return [J * (w.unsqueeze(2) if w.ndim == 2 else w) for J in jacobians], error * w
+
     def to(self, *args, **kwargs):
-        self.weight_tensor().to(*args, **kwargs)
+        for v in self.aux_vars:
+            v.to(*args, **kwargs)
 
 
 class ScaleCostWeight(CostWeight):
@@ -102,6 +130,12 @@ class CostFunction:
     def register_aux_vars(self, names: Sequence[str]):
         self._aux_vars_attr_names.extend(names)
 
+    def register_optim_var(self, name: str):
+        self.register_optim_vars([name])
+
+    def register_aux_var(self, name: str):
+        self.register_aux_vars([name])
+
     @property
     def optim_vars(self):
         return [getattr(self, n) for n in self._optim_vars_attr_names]
@@ -120,9 +154,54 @@ class CostFunction:
         raise NotImplementedError
 
     def schema(self):
-        """(cost kind enum, aux variable) for the CUDA linearize/error kernels."""
+        """(cost kind enum, aux variables) for the CUDA linearize/error kernels; kind None = the engine's generic route.  A user-defined
+        subclass written against the reference's plugin contract (error() + jacobians() + dim(), cost_function.py:64-105) takes the
+        generic route with its own analytic Jacobians."""
+        if self._user_defined("error") and self._user_defined("jacobians"):
+            return None, list(self.aux_vars)
         raise NotImplementedError(
-            f"{self.__class__.__name__} has no CUDA schema in libthb200; supported: Between/Difference on SE3, SO3, Vector")
+            f"{self.__class__.__name__} has no CUDA schema in libthb200 and does not define error() and jacobians(); "
+            "built in: Between/Difference on SE3, SO3, SE2, SO2, Vector, Reprojection, the tactile costs, AutoDiffCostFunction")
+
+    # ---- the reference's public cost-function interface (core/cost_function.py:64-149) ----
+    def _user_defined(self, what: str) -> bool:
+        return getattr(type(self), what) is not getattr(CostFunction, what)
+
+    class _at:
+        """The optimisation variables' tensors temporarily replaced (the engine evaluates user code at candidate values); the swap goes
+        around the `tensor` setter so that no pointer table is invalidated."""
+
+        def __init__(self, cf, tensors):
+            self._vars, self._new = cf.optim_vars, list(tensors)
+
+        def __enter__(self):
+            self._old = [v._tensor for v in self._vars]
+            for v, t in zip(self._vars, self._new):
+                v._tensor = t
+
+        def __exit__(self, *exc):
+            for v, t in zip(self._vars, self._old):
+                v._tensor = t
+            return False
+
+    def error(self) -> torch.Tensor:
+        """Unweighted error [B, dim] at the variables' current tensors (cost_function.py:85-87).  Built-in cost functions: their torch
+        restatement; user-defined subclasses override this."""
+        return self._torch_error(tuple(v.tensor for v in self.optim_vars), tuple(v.tensor for v in self._torch_aux()))
+
+    def jacobians(self):
+        """([J_i [B, dim, dof_i]], error) unweighted (cost_function.py:99-105).  Built-in cost functions: torch.func Jacobians of the
+        torch restatement projected to the tangent space (equal to the fused kernels' analytic blocks, tests/test_torch_restatements.py);
+        user-defined subclasses override this."""
+        return self._generic_unweighted([v.tensor for v in self.optim_vars], differentiable=torch.is_grad_enabled())
+
+    def weighted_error(self) -> torch.Tensor:
+        """cost_function.py:107-110."""
+        return self.generic_error([v.tensor for v in self.optim_vars])
+
+    def weighted_jacobians_error(self):
+        """cost_function.py:112-122: (weighted Jacobians, weighted error)."""
+        return self.generic_jacobians_error([v.tensor for v in self.optim_vars], differentiable=torch.is_grad_enabled())
 
     def to(self, *args, **kwargs):
         for v in self.optim_vars + self.aux_vars:
@@ -138,6 +217,11 @@ class CostFunction:
         return self.aux_vars
 
     def _weight(self, err: torch.Tensor, jacs):
+        if self.weight.WEIGHT_KIND < 0:   # user-defined CostWeight
+            if jacs is None:
+                return None, self.weight.weight_error(err)
+            wj, we = self.weight.weight_jacobians_and_error(list(jacs), err)
+            return list(wj), we
         w = self.weight.weight_tensor().tensor
         w = w.view(-1, 1) if self.weight.WEIGHT_KIND == WEIGHT_SCALE else w
         err = err * w
@@ -146,9 +230,24 @@ class CostFunction:
         return jacs, err
 
     def generic_jacobians_error(self, optim_tensors: Sequence[torch.Tensor], differentiable: bool = False):
-        """(weighted Jacobians [B,dim,dof_i], weighted error [B,dim]) by vmap(jacrev(error)) + tangent-space projection
-        (cost_function.py:318-393, v.project(jac, is_sparse=True)).  differentiable=True keeps the graph to the aux variables /
-        weights / variable values (backward modes)."""
+        """(weighted Jacobians [B,dim,dof_i], weighted error [B,dim]): _generic_unweighted + the cost weight.  differentiable=True keeps
+        the graph to the aux variables / weights / variable values (backward modes)."""
+        jacs, err = self._generic_unweighted(optim_tensors, differentiable)
+        return self._weight(err, jacs)
+
+    def _generic_unweighted(self, optim_tensors: Sequence[torch.Tensor], differentiable: bool = False):
+        """(Jacobians [B,dim,dof_i], error [B,dim]), unweighted.  User-defined subclass: its own jacobians() evaluated at `optim_tensors`;
+        otherwise vmap(jacrev(_torch_error)) + tangent-space projection (cost_function.py:318-393, v.project(jac, is_sparse=True))."""
+        if self._user_defined("jacobians"):
+            with CostFunction._at(self, optim_tensors):
+                jacs, err = self.jacobians()
+            jacs = list(jacs)
+            if len(jacs) != self.num_optim_vars() or err.ndim != 2 or err.shape[1] != self.dim():
+                raise ValueError(f"{self.name}: jacobians() must return one [B, {self.dim()}, dof] block per optimisation variable and an "
+                                 f"error of shape [B, {self.dim()}]")
+            if differentiable:
+                return jacs, err
+            return [j.detach() for j in jacs], err.detach()
         from torch.func import jacrev, vmap
         ovars = self.optim_vars
         aux = tuple(v.tensor for v in self._torch_aux())
@@ -164,11 +263,15 @@ class CostFunction:
             err = self._torch_error(opt_t, aux_t)
         jacs = [type(v).project_tensor(t, j) for v, t, j in zip(ovars, opt_t, jacs)]  # Euclidean -> tangent space (identity for Vector)
         if differentiable:
-            return self._weight(err, jacs)
-        return self._weight(err.detach(), [j.detach() for j in jacs])
+            return jacs, err
+        return [j.detach() for j in jacs], err.detach()
 
     def generic_error(self, optim_tensors: Sequence[torch.Tensor]) -> torch.Tensor:
         """Weighted error [B, dim] at the given optimisation-variable tensors."""
+        if self._user_defined("error"):
+            with CostFunction._at(self, optim_tensors):
+                err = self.error()
+            return self._weight(err, None)[1]
         return self._weight(self._torch_error(tuple(optim_tensors), tuple(v.tensor for v in self._torch_aux())), None)[1]
 
 
@@ -521,7 +624,7 @@ class Objective:
         """objective.py:210-300: registers the cost function and its variables (first-appearance order)."""
         if cost_function.name in self.cost_functions:
             raise ValueError(f"Two different cost function objects with the same name ({cost_function.name}) are not allowed in the same objective.")
-        for v in cost_function.optim_vars + cost_function.aux_vars + [cost_function.weight.weight_tensor()]:
+        for v in cost_function.optim_vars + cost_function.aux_vars + cost_function.weight.aux_vars:
             if v.dtype != self.dtype:
                 raise ValueError(f"Tried to add cost function with dtype {v.dtype} variable {v.name} to objective of dtype {self.dtype}.")
         self.cost_functions[cost_function.name] = cost_function
@@ -529,7 +632,7 @@ class Objective:
             if v.name in self.optim_vars and self.optim_vars[v.name] is not v:
                 raise ValueError(f"Two different variable objects with the same name ({v.name}) are not allowed in the same objective.")
             self.optim_vars.setdefault(v.name, v)
-        for v in cost_function.aux_vars + [cost_function.weight.weight_tensor()]:
+        for v in cost_function.aux_vars + cost_function.weight.aux_vars:
             if v.name in self.aux_vars and self.aux_vars[v.name] is not v:
                 raise ValueError(f"Two different variable objects with the same name ({v.name}) are not allowed in the same objective.")
             self.aux_vars.setdefault(v.name, v)
@@ -551,7 +654,7 @@ class Objective:
         return name in self.aux_vars
 
     def _cost_variables(self, cf: CostFunction):
-        return cf.optim_vars, cf.aux_vars + [cf.weight.weight_tensor()]
+        return cf.optim_vars, cf.aux_vars + cf.weight.aux_vars
 
     def get_functions_connected_to_optim_var(self, variable: Union[str, Manifold]) -> List[CostFunction]:
         name = variable if isinstance(variable, str) else variable.name

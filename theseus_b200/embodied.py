@@ -41,7 +41,7 @@ class MovingFrameBetween(CostFunction):
         f1, f2, p1, p2 = optim_tensors
         return lie_torch.between(k, lie_torch.between(k, f1, p1), lie_torch.between(k, f2, p2))
 
-    def generic_jacobians_error(self, optim_tensors, differentiable: bool = False):
+    def _generic_unweighted(self, optim_tensors, differentiable: bool = False):
         import torch
         from torch.func import jacrev, vmap
         from . import lie_torch
@@ -66,8 +66,8 @@ class MovingFrameBetween(CostFunction):
             Jin = Jin.movedim(-1, 1)                                                  # [B, dof, *out] : one velocity dD per column
             jacs.append(lie_torch.velocity_to_tangent(k, D, Jin).transpose(1, 2))     # [B, dof_out, dof_in]
         if differentiable:
-            return self._weight(err, jacs)
-        return self._weight(err.detach(), [j.detach() for j in jacs])
+            return jacs, err
+        return [j.detach() for j in jacs], err.detach()
 
     def schema(self):
         return None, []

@@ -84,7 +84,7 @@ class Engine:
         for f, cf in enumerate(costs):
             kind, aux = cf.schema()
             self._aux_of.append(list(aux) if isinstance(aux, (list, tuple)) else [aux])
-            if kind is None:
+            if kind is None or cf.weight.WEIGHT_KIND < 0:   # no fused kernel for this cost function / a user-defined CostWeight
                 self.generic.append(f)
                 continue
             key = (kind, cf.weight.WEIGHT_KIND, cf.dim(), int(getattr(cf, "robust_kind", 0)))
@@ -339,7 +339,7 @@ class Engine:
         for g in self.groups:
             _lib.check(fn(C.byref(g.bound["cur"][0]), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, s), "linearize_group")
         S = self.structure
-        if self.generic and _batched_torch_route():
+        if self.generic and _batched_torch_route() and not self._user_costs(self.generic):
             self._route("generic").linearize(lambda v: self._expand(v.tensor), B, A_val, b, differentiable=False)
             return A_val, b
         for f in self.generic:
@@ -360,7 +360,7 @@ class Engine:
         B, S = self.batch_size, self.structure
         A_val = torch.zeros(B, self.nnz, dtype=self.dtype, device=self.device)
         b = torch.zeros(B, self.m, dtype=self.dtype, device=self.device)
-        if _batched_torch_route():   # one vmap(jacrev) per group of stackable cost functions instead of one per cost function
+        if _batched_torch_route() and not self._user_costs(range(len(self.costs))):   # one vmap(jacrev) per group of stackable cost functions instead of one per cost function
             return self._route("all").linearize(lambda v: self._expand(v.tensor), B, A_val, b, differentiable=True)
         for f, cf in enumerate(self.costs):  # every cost function through its torch restatement (O(#costs) torch calls: taped steps only)
             jacs, err = cf.generic_jacobians_error([self._expand(v.tensor) for v in cf.optim_vars], differentiable=True)
@@ -371,6 +371,11 @@ class Engine:
                 blk[:, :, p0:p0 + J.shape[2]] = J
             b[:, int(S.cost_row0[f]):int(S.cost_row0[f]) + d] = -err
         return A_val, b
+
+    def _user_costs(self, ids) -> bool:
+        """True if any of these cost functions is a user-defined subclass (own error() / jacobians()): those run per cost function."""
+        return any(self.costs[f]._user_defined("jacobians") or self.costs[f]._user_defined("error") or self.costs[f].weight.WEIGHT_KIND < 0
+                   or getattr(getattr(self.costs[f], "cost_function", None), "_user_defined", lambda w: False)("jacobians") for f in ids)
 
     def _route(self, which: str):
         """torch_route.TorchRoute over the generic cost functions ("generic") or over all of them ("all", taped linearization)."""
@@ -400,7 +405,7 @@ class Engine:
             _lib.check(fn(C.byref(g.bound[which][0]), B, _lib.ptr(partial[row:]), s), "error_group")
             row += nc
         _lib.check(getattr(self.lib, f"thb_error_reduce_{self.sfx}")(_lib.ptr(partial), self.total_chunks, B, _lib.ptr(out), s), "error_reduce")
-        if self.generic and _batched_torch_route():
+        if self.generic and _batched_torch_route() and not self._user_costs(self.generic):
             of = (lambda v: self.tmp_views[self.var_index[v.name]]) if which == "tmp" else (lambda v: self._expand(v.tensor))
             out += self._route("generic").half_squared_error(of, B)
             return out

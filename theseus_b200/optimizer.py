@@ -561,7 +561,7 @@ class NonlinearLeastSquares:
                 delta = self.compute_delta(**kwargs)
             except RuntimeError as run_err:
                 msg = f"There was an error while running the linear optimizer. Original error message: {run_err}."
-                if torch.is_grad_enabled():
+                if torch.is_grad_enabled() or getattr(self, "_grad_mode_at_entry", False):
                     raise RuntimeError(msg + " Backward pass will not work. To obtain the best solution seen before the error, run with torch.no_grad()")
                 warnings.warn(msg, RuntimeWarning)
                 info.status[:] = NonlinearOptimizerStatus.FAIL
@@ -659,7 +659,10 @@ class NonlinearLeastSquares:
             try:
                 solver.check_info()
             except RuntimeError as run_err:
-                warnings.warn(f"There was an error while running the linear optimizer. Original error message: {run_err}.", RuntimeWarning)
+                msg = f"There was an error while running the linear optimizer. Original error message: {run_err}."
+                if getattr(self, "_grad_mode_at_entry", False):
+                    raise RuntimeError(msg + " Backward pass will not work. To obtain the best solution seen before the error, run with torch.no_grad()")
+                warnings.warn(msg, RuntimeWarning)
                 info.status[:] = NonlinearOptimizerStatus.FAIL
                 return iters_done
             if all_rejected:
@@ -691,12 +694,18 @@ class NonlinearLeastSquares:
         eng = self.objective.engine()
         eng.adopt_optim_vars()
         self.reset(**kwargs_plus)
-        with torch.no_grad():
-            info = self._init_info(track_best_solution, track_err_history, track_state_history)
-            if verbose:
-                print(f"Nonlinear optimizer. Iteration: 0. Error: {info.last_err.mean().item()}")
-            self._optimize_loop(num_iter=self.params.max_iterations, info=info, verbose=verbose,
-                                end_iter_callback=end_iter_callback, **kwargs)
+        # nothing requires grad: the loop runs without a tape, but a failing linear solve is still reported the way the caller's grad
+        # mode asks for (nonlinear_least_squares.py:138-151: RuntimeError with gradients enabled, warning + status FAIL under no_grad)
+        self._grad_mode_at_entry = torch.is_grad_enabled()
+        try:
+            with torch.no_grad():
+                info = self._init_info(track_best_solution, track_err_history, track_state_history)
+                if verbose:
+                    print(f"Nonlinear optimizer. Iteration: 0. Error: {info.last_err.mean().item()}")
+                self._optimize_loop(num_iter=self.params.max_iterations, info=info, verbose=verbose,
+                                    end_iter_callback=end_iter_callback, **kwargs)
+        finally:
+            self._grad_mode_at_entry = False
         info.converged_iter[torch.from_numpy(info.status == NonlinearOptimizerStatus.MAX_ITERATIONS).to(info.converged_iter.device)] = -1
         return info
 
