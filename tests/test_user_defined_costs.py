@@ -136,3 +136,66 @@ def test_public_cost_function_interface_on_built_in_costs():
     wj3, we3 = w.weight_jacobians_and_error(jacs, e)
     torch.testing.assert_close(we3, we)
     torch.testing.assert_close(wj3[1], wj[1])
+
+
+class _TorchSolveSolver(th.LinearSolver):
+    """A user-defined LinearSolver (theseus/optimizer/linear/linear_solver.py:15-37): reads the linearization's AtA / Atb, applies the
+    damping of dense_solver.py:38-64 and solves with torch."""
+
+    def __init__(self, objective, linearization_cls=None, linearization_kwargs=None, **kwargs):
+        super().__init__(objective, linearization_cls or th.DenseLinearization, linearization_kwargs, **kwargs)
+
+    def solve(self, damping=None, ellipsoidal_damping=True, damping_eps=1e-8, **kwargs):
+        AtA, Atb = self.linearization.AtA, self.linearization.Atb
+        if damping is not None:
+            d = torch.as_tensor(damping, dtype=AtA.dtype, device=AtA.device).view(-1, 1)
+            diag = torch.diagonal(AtA, dim1=1, dim2=2)
+            AtA = AtA + torch.diag_embed(d * diag + damping_eps if ellipsoidal_damping else d.expand_as(diag))
+        return torch.linalg.solve(AtA, Atb.reshape(AtA.shape[0], -1, 1)).squeeze(2)
+
+
+@pytest.mark.parametrize("method", ["gn", "lm"])
+def test_user_defined_linear_solver_gives_the_library_solvers_iterates(emulated, method):
+    """linear_solver_cls is a plugin point (nonlinear_least_squares.py:88-96): a user's solver over DenseLinearization must walk the same
+    iterates as CholeskyDenseSolver."""
+    kw = dict(damping=0.01, adaptive_damping=True, ellipsoidal_damping=True) if method == "lm" else {}
+    cls = th.LevenbergMarquardt if method == "lm" else th.GaussNewton
+    runs = []
+    for solver_cls in (_TorchSolveSolver, th.CholeskyDenseSolver):
+        objective, variables = user_costs.regression_problem(th, False, batch_size=4, npoints=20)
+        opt = cls(objective, linear_solver_cls=solver_cls, max_iterations=8, abs_err_tolerance=0, rel_err_tolerance=0)
+        assert isinstance(opt.linear_solver, solver_cls)
+        with torch.no_grad():
+            info = opt.optimize(track_err_history=True, **kw)
+        runs.append((info.err_history.clone(), variables[0].tensor.clone()))
+    torch.testing.assert_close(runs[0][0], runs[1][0], rtol=1e-6, atol=1e-12)
+    torch.testing.assert_close(runs[0][1], runs[1][1], rtol=1e-9, atol=1e-12)
+
+
+def test_user_defined_linearization_with_a_singular_system_fails_like_the_reference(emulated):
+    """nonlinear/common.py:215-280 as written there: the solver's linearization replaced by a user subclass of Linearization that
+    returns AtA = 0, Atb = 1."""
+    class ZeroHessian(th.optimizer.Linearization):
+        def _linearize_jacobian_impl(self):
+            pass
+
+        def _linearize_hessian_impl(self, _detach_hessian=False):
+            B = self.objective.batch_size
+            self._AtA = torch.zeros(B, self.num_cols, self.num_cols, dtype=torch.float64)
+            self._Atb = torch.ones(B, self.num_cols, 1, dtype=torch.float64)
+
+        def _ata_impl(self):
+            return self._AtA
+
+        def _atb_impl(self):
+            return self._Atb
+
+    objective, variables = user_costs.regression_problem(th, False, batch_size=2, npoints=3)
+    opt = th.GaussNewton(objective, max_iterations=5)
+    opt.linear_solver.linearization = ZeroHessian(objective)
+    with pytest.raises(RuntimeError):
+        opt.optimize(track_best_solution=True)
+    with pytest.warns(RuntimeWarning):
+        with torch.no_grad():
+            info = opt.optimize(track_best_solution=True, track_err_history=True)
+    assert (info.status == th.NonlinearOptimizerStatus.FAIL).all()
