@@ -199,3 +199,70 @@ def test_user_defined_linearization_with_a_singular_system_fails_like_the_refere
         with torch.no_grad():
             info = opt.optimize(track_best_solution=True, track_err_history=True)
     assert (info.status == th.NonlinearOptimizerStatus.FAIL).all()
+
+
+def test_linear_optimizer_solves_a_linear_problem_in_one_step(emulated):
+    """theseus/optimizer/linear/linear_optimizer.py:25-83 (tests/theseus_tests/optimizer/linear/test_linear_optimizer.py pattern): one
+    linearize + solve + retract; for a linear least-squares objective that is the minimiser."""
+    d = torch.float64
+    x, y = th.Vector(3, name="x", dtype=d), th.Vector(3, name="y", dtype=d)
+    tx = th.Vector(tensor=torch.tensor([[1.0, 2.0, 3.0], [0.5, -1.0, 2.0]], dtype=d), name="tx")
+    ty = th.Vector(tensor=torch.tensor([[-1.0, 0.0, 4.0], [3.0, 3.0, 3.0]], dtype=d), name="ty")
+    w = th.ScaleCostWeight(torch.tensor(2.0, dtype=d))
+    objective = th.Objective(dtype=d)
+    objective.add(th.Difference(x, tx, w, name="px"))
+    objective.add(th.Difference(y, ty, w, name="py"))
+    objective.add(th.Between(x, y, th.Vector(tensor=(ty.tensor - tx.tensor), name="z"), w, name="b"))
+    objective.update({"x": torch.zeros(2, 3, dtype=d), "y": torch.ones(2, 3, dtype=d)})
+    opt = th.LinearOptimizer(objective, th.CholeskyDenseSolver)
+    with torch.no_grad():
+        info = opt.optimize()
+    assert (info.status == th.LinearOptimizerStatus.CONVERGED).all()
+    torch.testing.assert_close(x.tensor, tx.tensor, rtol=0, atol=1e-12)
+    torch.testing.assert_close(y.tensor, ty.tensor, rtol=0, atol=1e-12)
+    torch.testing.assert_close(info.best_solution["x"], tx.tensor)
+    assert float(objective.error_metric().abs().max()) < 1e-20
+    th.Vectorize(objective)   # by name only: the engine always evaluates per schema group
+    assert objective.vectorized
+
+
+def test_lie_group_checks_at_construction_follow_the_reference():
+    """manifold.py:44-68,123-146 + lie_group_check.py: SE2 / SO2 storage is validated at construction (strict: ValueError, else
+    normalised with a warning; silenced / skipped by the contexts and by disable_checks); the SO3 / SE3 matrix checks live in torchlie and
+    are off unless its enable_checks context is active (check_contexts.py:12-44) -- the reference's observable behaviour, checked here
+    against values computed with the reference (see the comment per case)."""
+    from theseus_b200 import geometry as G
+    d = torch.float64
+    bad2 = torch.tensor([[1.0, 2.0, 0.0, 3.0], [0.0, 0.0, 0.6, 0.8]], dtype=d)
+    with pytest.raises(ValueError):
+        th.SE2(tensor=bad2, strict_checks=True)
+    with pytest.warns(UserWarning, match="has been normalized"):
+        fixed = th.SE2(tensor=bad2)
+    torch.testing.assert_close(fixed.tensor, torch.tensor([[1.0, 2.0, 0.0, 1.0], [0.0, 0.0, 0.6, 0.8]], dtype=d))
+    with pytest.warns(UserWarning):
+        assert th.SO2(tensor=torch.zeros(1, 2, dtype=d)).tensor.tolist() == [[1.0, 0.0]]      # so2.py:193-204: zero norm -> identity
+    assert torch.equal(th.SE2(tensor=bad2, disable_checks=True).tensor, bad2)
+    with th.no_lie_group_check(silent=True):
+        assert torch.equal(th.SE2(tensor=bad2).tensor, bad2)
+        with th.enable_lie_group_check():
+            with pytest.raises(ValueError):
+                th.SE2(tensor=bad2, strict_checks=True)
+    with th.set_lie_group_check_enabled(False, silent=True):
+        assert torch.equal(th.SO2(tensor=bad2[:, 2:]).tensor, bad2[:, 2:])
+    with pytest.warns(RuntimeWarning, match="checks are disabled"):
+        with th.no_lie_group_check(silent=True):
+            with th.set_lie_group_check_enabled(False, silent=False):
+                th.SE2(tensor=bad2)
+    # SE3 / SO3: not validated by default (the reference keeps a scaled rotation block as it is) ...
+    X = th.rand_se3(3, generator=torch.Generator().manual_seed(0), dtype=d).tensor
+    bad3 = X.clone()
+    bad3[:, :, :3] *= 1.01
+    assert torch.equal(th.SE3(tensor=bad3).tensor, bad3) and torch.equal(th.SE3(tensor=bad3, strict_checks=True).tensor, bad3)
+    # ... and validated / normalised by SVD under torchlie's enable_checks (so3_impl.py:30-48, 1133-1141)
+    with G.enable_checks():
+        with pytest.raises(ValueError):
+            th.SO3(tensor=bad3[:, :, :3], strict_checks=True)
+        with pytest.warns(UserWarning, match="has been normalized"):
+            fixed3 = th.SE3(tensor=bad3)
+        assert torch.equal(th.SE3(tensor=X).tensor, X)
+    torch.testing.assert_close(fixed3.tensor, X, rtol=0, atol=1e-13)      # nearest rotation of 1.01 R is R; translation untouched

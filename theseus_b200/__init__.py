@@ -19,12 +19,14 @@ from . import embodied as eb  # noqa: F401  (th.eb.Reprojection, like the refere
 from .optimizer import (VariableOrdering, Linearization, DenseLinearization, SparseLinearization, LinearSolver,  # noqa: F401
                         DenseSolver, CholeskyDenseSolver, LUDenseSolver, NonlinearLeastSquares, GaussNewton,
                         LevenbergMarquardt, TrustRegion, Dogleg, NonlinearOptimizerStatus, NonlinearOptimizerInfo, OptimizerInfo,
-                        NonlinearOptimizerParams, BackwardMode, convert_to_alpha_beta_damping_tensors)
+                        NonlinearOptimizerParams, BackwardMode, convert_to_alpha_beta_damping_tensors, LinearOptimizer, LinearOptimizerStatus, Vectorize)
 from .sparse_solver import BaspachoSparseSolver, BlockSparseSolver, CholmodSparseSolver, LUCudaSparseSolver  # noqa: F401
 from .layer import TheseusLayer  # noqa: F401
 from .functional import (adjoint, between, compose, exp_map, inverse, local, log_map, retract, rand_vector, randn_vector,  # noqa: F401
                          rand_point2, randn_point2, rand_point3, randn_point3, rand_so3, randn_so3, rand_se3, randn_se3, rand_se2, randn_se2,
                          rand_so2, randn_so2)
 from . import io_formats  # noqa: F401  (g2o / BAL readers: th.io_formats.read_3D_g2o_file, load_bal_dataset)
+
+from .geometry import enable_lie_group_check, no_lie_group_check, set_lie_group_check_enabled  # noqa: F401,E402
 
 __version__ = "0.1.0"

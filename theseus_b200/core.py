@@ -302,7 +302,7 @@ class Between(CostFunction):
             return COST_BETWEEN_SO3, self.measurement
         if isinstance(self.v0, SE2):
             return COST_BETWEEN_SE2, self.measurement
-        if isinstance(self.v0, SO2):
+        if isinstance(self.v0, (SO2, Vector)):
             return None, [self.measurement]   # generic route: torch.func Jacobians of _torch_error (engine.py)
         return super().schema()
 

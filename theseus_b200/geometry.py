@@ -9,6 +9,9 @@ The group arithmetic runs in the CUDA library (theseus_b200/csrc/thb_lie.cuh thr
 compute method on a CPU tensor raises -- there is no CPU implementation in the product.
 """
 import itertools
+import threading
+import warnings
+from contextlib import contextmanager
 from typing import List, Optional
 
 import torch
@@ -19,6 +22,105 @@ from . import _lib
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"theseus_b200.{what}: tensors must live on a CUDA device (B200); the product has no CPU path")
+
+
+# ---- consistency checks of group tensors at construction (theseus/geometry/lie_group_check.py:10-105, manifold.py:44-68,123-146) ----
+class _LieGroupCheckContext:
+    contexts = threading.local()
+
+    @classmethod
+    def get_context(cls):
+        if not hasattr(cls.contexts, "check_lie_group"):
+            cls.contexts.check_lie_group, cls.contexts.silent, cls.contexts.silence_internal_warnings = True, False, False
+        return cls.contexts.check_lie_group, cls.contexts.silent, cls.contexts.silence_internal_warnings
+
+    @classmethod
+    def set_context(cls, check_lie_group: bool, silent: bool, silence_internal_warnings: bool):
+        if not check_lie_group and not silent:
+            print("Warnings for disabled Lie group checks can be turned off by passing silent=True.")
+        cls.contexts.check_lie_group, cls.contexts.silent, cls.contexts.silence_internal_warnings = check_lie_group, silent, silence_internal_warnings
+
+
+@contextmanager
+def set_lie_group_check_enabled(mode: bool, silent: bool = False, silence_internal_warnings: bool = False):
+    """lie_group_check.py:39-54: whether group tensors are checked (and, if invalid and not strict, normalised) at construction."""
+    prev = _LieGroupCheckContext.get_context()
+    _LieGroupCheckContext.set_context(mode, silent, silence_internal_warnings)
+    try:
+        yield
+    finally:
+        _LieGroupCheckContext.set_context(*prev)
+
+
+@contextmanager
+def enable_lie_group_check(silent: bool = False, silence_internal_warnings: bool = False):
+    with set_lie_group_check_enabled(True, silent, silence_internal_warnings):
+        yield
+
+
+@contextmanager
+def no_lie_group_check(silent: bool = False, silence_internal_warnings: bool = False):
+    with set_lie_group_check_enabled(False, silent, silence_internal_warnings):
+        yield
+
+
+# eps of the checks: torchlie/global_params.py:44-58 (so3 matrix), theseus/global_params.py:46-59 (so2 matrix / norm)
+_SO3_MATRIX_EPS = {torch.float32: 4e-4, torch.float64: 1e-6}
+_SO2_MATRIX_EPS = {torch.float32: 1e-5, torch.float64: 4e-7}
+_SO2_NORM_EPS = {torch.float32: 1e-12, torch.float64: 1e-12}
+
+
+class enable_checks:
+    """torchlie/functional/check_contexts.py:12-36: the SO3 / SE3 matrix checks live in torchlie and are OFF unless this context is
+    active (thread-local) -- with the reference's defaults a rotation block is therefore never validated or normalised at construction,
+    while the SE2 / SO2 checks (theseus' own, so2.py:132-146) always run.  Mirrored as is."""
+    _ctx = threading.local()
+
+    @classmethod
+    def active(cls) -> bool:
+        return getattr(cls._ctx, "on", False)
+
+    def __enter__(self) -> None:
+        self.prev = enable_checks.active()
+        enable_checks._ctx.on = True
+
+    def __exit__(self, typ, value, traceback) -> None:
+        enable_checks._ctx.on = self.prev
+
+
+def _so3_valid(R: torch.Tensor) -> bool:
+    """so3_impl.py:30-48 under check_contexts.checks_base: max |R R^T - I| < eps and max |det R - 1| < eps, evaluated in fp64."""
+    if not enable_checks.active():
+        return True
+    eps = _SO3_MATRIX_EPS[R.dtype]
+    with torch.no_grad():
+        R = R.double()
+        ortho = (R @ R.transpose(-1, -2) - torch.eye(3, dtype=R.dtype, device=R.device)).abs().max()
+        det = (R[..., 0] * torch.linalg.cross(R[..., 1], R[..., 2], dim=-1)).sum(-1)
+        return bool(((ortho < eps) & ((det - 1).abs().max() < eps)).item())
+
+
+def _so3_normalize(R: torch.Tensor) -> torch.Tensor:
+    """so3_impl.py:1133-1141: nearest rotation by SVD, U diag(1, 1, det(U V^T)) V^T."""
+    u, _, vh = torch.linalg.svd(R)
+    v = vh.transpose(-1, -2)
+    sign = torch.linalg.det(u @ v).view(-1, 1, 1)
+    vt = torch.cat((v[..., :2], torch.where(sign > 0, v[..., 2:], -v[..., 2:])), dim=-1).transpose(-1, -2)
+    return u @ vt
+
+
+def _so2_valid(cs: torch.Tensor) -> bool:
+    """so2.py:132-146."""
+    with torch.no_grad():
+        return bool(((torch.linalg.norm(cs.double(), dim=1) - 1).abs().max() <= _SO2_MATRIX_EPS[cs.dtype]).item())
+
+
+def _so2_normalize(cs: torch.Tensor) -> torch.Tensor:
+    """so2.py:188-204."""
+    norm = torch.norm(cs, dim=1, keepdim=True)
+    near_zero = norm < _SO2_NORM_EPS[cs.dtype]
+    default = torch.tensor([1, 0], dtype=cs.dtype, device=cs.device).expand(cs.shape[0], 2)
+    return torch.where(near_zero, default, cs / torch.where(near_zero, torch.ones_like(norm), norm))
 
 
 class Variable:
@@ -117,7 +219,40 @@ class Manifold(Variable):
     def copy(self, new_name: Optional[str] = None):
         if not new_name:
             new_name = f"{self.name}_copy"
-        return self.__class__(tensor=self.tensor.clone(), name=new_name)
+        with no_lie_group_check(silent=True):       # a copy of a checked tensor
+            return self.__class__(tensor=self.tensor.clone(), name=new_name)
+
+    # ---- construction-time checks (manifold.py:44-68, 123-146) ----
+    @staticmethod
+    def _check_tensor_impl(tensor: torch.Tensor) -> bool:
+        return True
+
+    @staticmethod
+    def normalize(tensor: torch.Tensor) -> torch.Tensor:
+        return tensor
+
+    @classmethod
+    def _check_tensor(cls, tensor: torch.Tensor, strict: bool = True, silent_normalization: bool = False) -> torch.Tensor:
+        if not cls._check_tensor_impl(tensor):
+            if strict:
+                raise ValueError(f"The input tensor is not valid for {cls.__name__}.")
+            tensor = cls.normalize(tensor)
+            if not silent_normalization:
+                warnings.warn(f"The input tensor is not valid for {cls.__name__} and has been normalized.")
+        return tensor
+
+    @classmethod
+    def _checked(cls, tensor: torch.Tensor, strict_checks: bool, disable_checks: bool) -> torch.Tensor:
+        """What Manifold.__init__ does with a user-given tensor: check it (strict: raise; else normalise with a warning) unless checks
+        are disabled by the argument or by the thread's check context."""
+        if disable_checks:
+            return tensor
+        enabled, silent, silence_internal = _LieGroupCheckContext.get_context()
+        if enabled:
+            return cls._check_tensor(tensor, strict_checks, silent_normalization=silence_internal)
+        if not silent:
+            warnings.warn(f"Manifold consistency checks are disabled for {cls.__name__}.", RuntimeWarning)
+        return tensor
 
     @staticmethod
     def project_tensor(group: torch.Tensor, euclidean_grad: torch.Tensor) -> torch.Tensor:
@@ -208,7 +343,7 @@ def _group_ops(cls, prefix: str, dof: int, jshape):
         t = tangent_vector.contiguous()
         out = torch.empty((t.shape[0],) + cls._GROUP_SHAPE, dtype=t.dtype, device=t.device)
         _lib.check(getattr(_lib.load(), f"thb_{prefix}_exp_{_sfx(t)}")(_lib.ptr(t), _lib.ptr(out), t.shape[0], _lib.stream_ptr()), f"{prefix}_exp")
-        return cls(tensor=out)
+        return cls(tensor=out, disable_checks=True)
 
     def log_map(self, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
         g = self.tensor.contiguous()
@@ -232,7 +367,7 @@ def _group_ops(cls, prefix: str, dof: int, jshape):
         _require_cuda(g, f"{cls.__name__}.inverse")
         out = torch.empty_like(g)
         _lib.check(getattr(_lib.load(), f"thb_{prefix}_inverse_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), g.shape[0], _lib.stream_ptr()), f"{prefix}_inverse")
-        return cls(tensor=out)
+        return cls(tensor=out, disable_checks=True)
 
     def compose(self, other):
         a, b = self.tensor.contiguous(), other.tensor.contiguous()
@@ -242,7 +377,7 @@ def _group_ops(cls, prefix: str, dof: int, jshape):
             a, b = a.expand((B,) + _shape(a)).contiguous(), b.expand((B,) + _shape(b)).contiguous()
         out = torch.empty_like(a)
         _lib.check(getattr(_lib.load(), f"thb_{prefix}_compose_{_sfx(a)}")(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], _lib.stream_ptr()), f"{prefix}_compose")
-        return cls(tensor=out)
+        return cls(tensor=out, disable_checks=True)
 
     cls.exp_map = staticmethod(exp_map)
     cls.log_map, cls.adjoint, cls.inverse, cls.compose = log_map, adjoint, inverse, compose
@@ -254,11 +389,20 @@ class SE3(LieGroup):
 
     def __init__(self, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None,
                  dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
+        given = tensor
         if tensor is None:
             tensor = torch.eye(3, 4, dtype=dtype or torch.get_default_dtype()).view(1, 3, 4)
         if tensor.ndim != 3 or tensor.shape[1:] != (3, 4):
             raise ValueError("SE3 data tensors can only be 3x4 matrices.")  # geometry/se3.py:117-125
-        super().__init__(tensor, name=name)
+        super().__init__(tensor if given is None else self._checked(tensor, strict_checks, disable_checks), name=name)
+
+    @staticmethod
+    def _check_tensor_impl(tensor: torch.Tensor) -> bool:
+        return _so3_valid(tensor[..., :3])          # se3_impl.py check_group_tensor: the rotation block
+
+    @staticmethod
+    def normalize(tensor: torch.Tensor) -> torch.Tensor:
+        return torch.cat((_so3_normalize(tensor[..., :3]), tensor[..., 3:]), dim=-1)
 
     def dof(self) -> int:
         return 6
@@ -277,7 +421,7 @@ class SE3(LieGroup):
         t = tangent_vector.contiguous()
         out = torch.empty(t.shape[0], 3, 4, dtype=t.dtype, device=t.device)
         _lib.check(getattr(lib, f"thb_se3_exp_{_sfx(t)}")(_lib.ptr(t), _lib.ptr(out), t.shape[0], _lib.stream_ptr()), "se3_exp")
-        return SE3(tensor=out)
+        return SE3(tensor=out, disable_checks=True)
 
     def log_map(self, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
         g = self.tensor.contiguous()
@@ -304,7 +448,7 @@ class SE3(LieGroup):
         lib = _lib.load()
         out = torch.empty_like(g)
         _lib.check(getattr(lib, f"thb_se3_inverse_{_sfx(g)}")(_lib.ptr(g), _lib.ptr(out), g.shape[0], _lib.stream_ptr()), "se3_inverse")
-        return SE3(tensor=out)
+        return SE3(tensor=out, disable_checks=True)
 
     def compose(self, other: "SE3") -> "SE3":
         a, b = self.tensor.contiguous(), other.tensor.contiguous()
@@ -315,7 +459,7 @@ class SE3(LieGroup):
         lib = _lib.load()
         out = torch.empty_like(a)
         _lib.check(getattr(lib, f"thb_se3_compose_{_sfx(a)}")(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], _lib.stream_ptr()), "se3_compose")
-        return SE3(tensor=out)
+        return SE3(tensor=out, disable_checks=True)
 
 
 class SO3(LieGroup):
@@ -324,11 +468,20 @@ class SO3(LieGroup):
 
     def __init__(self, tensor: Optional[torch.Tensor] = None, name: Optional[str] = None,
                  dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
+        given = tensor
         if tensor is None:
             tensor = torch.eye(3, dtype=dtype or torch.get_default_dtype()).view(1, 3, 3)
         if tensor.ndim != 3 or tensor.shape[1:] != (3, 3):
             raise ValueError("SO3 data tensors can only be 3x3 matrices.")
-        super().__init__(tensor, name=name)
+        super().__init__(tensor if given is None else self._checked(tensor, strict_checks, disable_checks), name=name)
+
+    @staticmethod
+    def _check_tensor_impl(tensor: torch.Tensor) -> bool:
+        return _so3_valid(tensor)
+
+    @staticmethod
+    def normalize(tensor: torch.Tensor) -> torch.Tensor:
+        return _so3_normalize(tensor)
 
     def dof(self) -> int:
         return 3
@@ -346,13 +499,22 @@ class SE2(LieGroup):
                  dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
         if x_y_theta is not None and tensor is not None:
             raise ValueError("Please provide only one of x_y_theta or tensor.")
+        given = tensor          # only a user-given storage tensor is checked (cos / sin of an angle are valid by construction)
         if x_y_theta is not None:
             tensor = torch.cat([x_y_theta[:, :2], x_y_theta[:, 2:3].cos(), x_y_theta[:, 2:3].sin()], dim=1)
         if tensor is None:
             tensor = torch.tensor([[0.0, 0.0, 1.0, 0.0]], dtype=dtype or torch.get_default_dtype())
         if tensor.ndim != 2 or tensor.shape[1] != 4:
             raise ValueError("SE2 data tensors can only be 4D vectors.")  # geometry/se2.py:219-224
-        super().__init__(tensor, name=name)
+        super().__init__(tensor if given is None else self._checked(tensor, strict_checks, disable_checks), name=name)
+
+    @staticmethod
+    def _check_tensor_impl(tensor: torch.Tensor) -> bool:
+        return _so2_valid(tensor[:, 2:])            # se2.py:231-236
+
+    @staticmethod
+    def normalize(tensor: torch.Tensor) -> torch.Tensor:
+        return torch.cat([tensor[:, :2], _so2_normalize(tensor[:, 2:])], dim=1)   # se2.py:303-307
 
     def dof(self) -> int:
         return 3
@@ -376,6 +538,7 @@ class SO2(LieGroup):
                  dtype: Optional[torch.dtype] = None, strict_checks: bool = False, disable_checks: bool = False):
         if theta is not None and tensor is not None:
             raise ValueError("Please provide only one of theta or tensor.")
+        given = tensor
         if theta is not None:
             if theta.ndim == 1:
                 theta = theta.unsqueeze(1)
@@ -386,7 +549,15 @@ class SO2(LieGroup):
             tensor = torch.tensor([[1.0, 0.0]], dtype=dtype or torch.get_default_dtype())
         if tensor.ndim != 2 or tensor.shape[1] != 2:
             raise ValueError("SO2 data tensors can only be 2D vectors.")   # so2.py:189-190
-        super().__init__(tensor, name=name)
+        super().__init__(tensor if given is None else self._checked(tensor, strict_checks, disable_checks), name=name)
+
+    @staticmethod
+    def _check_tensor_impl(tensor: torch.Tensor) -> bool:
+        return _so2_valid(tensor)
+
+    @staticmethod
+    def normalize(tensor: torch.Tensor) -> torch.Tensor:
+        return _so2_normalize(tensor)
 
     def dof(self) -> int:
         return 1
@@ -399,7 +570,7 @@ class SO2(LieGroup):
     @staticmethod
     def exp_map(tangent_vector: torch.Tensor) -> "SO2":
         from . import lie_torch
-        return SO2(tensor=lie_torch.so2_exp(tangent_vector))
+        return SO2(tensor=lie_torch.so2_exp(tangent_vector), disable_checks=True)
 
     def log_map(self, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
         from . import lie_torch
@@ -415,11 +586,11 @@ class SO2(LieGroup):
 
     def inverse(self) -> "SO2":
         from . import lie_torch
-        return SO2(tensor=lie_torch.so2_inverse(self.tensor))
+        return SO2(tensor=lie_torch.so2_inverse(self.tensor), disable_checks=True)
 
     def compose(self, other: "SO2") -> "SO2":
         from . import lie_torch
-        return SO2(tensor=lie_torch.so2_compose(self.tensor, other.tensor))
+        return SO2(tensor=lie_torch.so2_compose(self.tensor, other.tensor), disable_checks=True)
 
     def to_cos_sin(self):
         return self.tensor[:, 0], self.tensor[:, 1]

@@ -201,6 +201,8 @@ def between(kind: int, X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
         return se2_compose(se2_inverse(X), Y)
     if kind == 4:
         return so2_compose(so2_inverse(X), Y)
+    if kind == 2:
+        return Y - X            # Vector: the additive group (geometry/vector.py: inverse = -x, compose = x + y)
     raise NotImplementedError(f"between() for variable kind {kind}")
 
 

@@ -856,6 +856,57 @@ class NonlinearLeastSquares:
         raise NotImplementedError
 
 
+class Vectorize:
+    """theseus/core/vectorizer.py:38-90 by name only: the reference rewires an objective so that cost functions of equal schema are
+    evaluated in one batched call.  Here that grouping IS the engine (engine.py: one fused kernel launch per schema group, always on),
+    so constructing this marks the objective and changes nothing."""
+
+    def __init__(self, objective: Objective, empty_cuda_cache: bool = False):
+        self._objective = objective
+        objective.vectorized = True
+
+
+class LinearOptimizerStatus(Enum):
+    START = 0
+    CONVERGED = 1
+    FAIL = -1
+
+
+class LinearOptimizer:
+    """theseus/optimizer/linear/linear_optimizer.py:25-83: ONE linearize -> solve -> retract of the objective (the solution of a linear
+    least-squares problem), same constructor and failure convention as the reference."""
+
+    def __init__(self, objective: Objective, linear_solver_cls: Type[LinearSolver], *args, vectorize: bool = False,
+                 linearization_cls: Optional[Type[Linearization]] = None, linearization_kwargs: Optional[Dict[str, Any]] = None,
+                 linear_solver_kwargs: Optional[Dict[str, Any]] = None, **kwargs):
+        self.objective = objective
+        self.linear_solver = linear_solver_cls(objective, linearization_cls=linearization_cls, linearization_kwargs=linearization_kwargs or {},
+                                               **(linear_solver_kwargs or {}))
+
+    def optimize(self, **kwargs) -> OptimizerInfo:
+        return self._optimize_impl(**kwargs)
+
+    def _optimize_impl(self, **kwargs) -> OptimizerInfo:
+        info = OptimizerInfo(best_solution={}, status=np.array([LinearOptimizerStatus.START] * self.objective.batch_size))
+        lin = self.linear_solver.linearization
+        try:
+            self.objective.engine(getattr(lin, "_ordering_names", None)).adopt_optim_vars()
+            lin.linearize()
+            delta = self.linear_solver.solve()
+        except RuntimeError as run_err:
+            msg = f"There was an error while running the linear optimizer. Original error message: {run_err}."
+            if torch.is_grad_enabled():
+                raise RuntimeError(msg + " Backward pass will not work. To obtain the best solution seen before the error, run with torch.no_grad()")
+            warnings.warn(msg, RuntimeWarning)
+            info.status[:] = LinearOptimizerStatus.FAIL
+            return info
+        self.objective.retract_vars_sequence(delta, lin.ordering)
+        info.status[:] = LinearOptimizerStatus.CONVERGED
+        for var in lin.ordering:
+            info.best_solution[var.name] = var.tensor.clone().cpu()
+        return info
+
+
 class GaussNewton(NonlinearLeastSquares):
     """theseus/optimizer/nonlinear/gauss_newton.py:17-47."""
 
