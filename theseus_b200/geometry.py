@@ -244,8 +244,10 @@ class Manifold(Variable):
     @classmethod
     def _checked(cls, tensor: torch.Tensor, strict_checks: bool, disable_checks: bool) -> torch.Tensor:
         """What Manifold.__init__ does with a user-given tensor: check it (strict: raise; else normalise with a warning) unless checks
-        are disabled by the argument or by the thread's check context."""
-        if disable_checks:
+        are disabled by the argument or by the thread's check context.  Inside torch.func transforms (a user's err_fn building group
+        objects under vmap / jacrev) there is nothing to read back: the reference turns the checks off around those calls
+        (cost_function.py:343-393), here the wrapped tensor itself says so."""
+        if disable_checks or torch._C._functorch.is_batchedtensor(tensor) or torch._C._functorch.is_gradtrackingtensor(tensor):
             return tensor
         enabled, silent, silence_internal = _LieGroupCheckContext.get_context()
         if enabled:
