@@ -867,6 +867,73 @@ def make_tactile(th):
     print("tactile_kat err", out["err0"], "->", out["trace_err"][-1], "grads", {k: float(np.abs(out["grad_" + k]).max()) for k in leaves})
 
 
+
+def geometry_api_values(L, torch, I, tape, device="cpu", group_ops=True):
+    """Every public method of the geometry classes beyond the fused-kernel ones, called the same way on the reference (`L` = theseus) and
+    on theseus_b200: group operations (tape=True: operands require grad -> the differentiable route), actions on points with their
+    Jacobians, accessors, conversions, Vector arithmetic, projections.  `I`: dict of input tensors (make_geom_api).  Shared by the
+    generator and tests/test_geometry_api.py."""
+    out = {}
+    dev = lambda t: t.to(device)
+    mk = lambda t: dev(t).clone().requires_grad_(True) if tape else dev(t).clone()
+    T = lambda x: x.tensor if hasattr(x, "tensor") else x
+    for name, cls, X, Y, tv in (("se3", L.SE3, I["X3"], I["Y3"], I["t6"]), ("so3", L.SO3, I["R3"], I["S3"], I["t3"]),
+                                ("se2", L.SE2, I["X2"], I["Y2"], I["t3"]), ("so2", L.SO2, I["R2"], I["S2"], I["t1"])):
+        a, b = cls(tensor=mk(X)), cls(tensor=mk(Y))
+        if group_ops:
+            out[name + "_compose"] = T(a.compose(b)); out[name + "_inverse"] = T(a.inverse()); out[name + "_log"] = a.log_map()
+            out[name + "_exp"] = T(cls.exp_map(mk(tv))); out[name + "_adjoint"] = a.adjoint(); out[name + "_between"] = T(a.between(b))
+            out[name + "_local"] = a.local(b); out[name + "_retract"] = T(a.retract(mk(tv)))
+        out[name + "_to_matrix"] = a.to_matrix(); out[name + "_hat"] = cls.hat(dev(tv)); out[name + "_vee"] = cls.vee(cls.hat(dev(tv)))
+    a3, a2, r3, r2 = L.SE3(tensor=mk(I["X3"])), L.SE2(tensor=mk(I["X2"])), L.SO3(tensor=mk(I["R3"])), L.SO2(tensor=mk(I["R2"]))
+    p3, p2 = dev(I["p3"]), dev(I["p2"])
+    for nm, obj, meth, pt in (("se3_tf", a3, "transform_from", p3), ("se3_tt", a3, "transform_to", p3), ("so3_rot", r3, "rotate", p3),
+                              ("so3_unrot", r3, "unrotate", p3), ("se2_tf", a2, "transform_from", p2), ("se2_tt", a2, "transform_to", p2),
+                              ("so2_rot", r2, "rotate", p2), ("so2_unrot", r2, "unrotate", p2)):
+        J = []
+        out[nm] = T(getattr(obj, meth)(pt, jacobians=J)); out[nm + "_Jg"], out[nm + "_Jp"] = J
+        out[nm + "_pt"] = T(getattr(obj, meth)((L.Point3 if pt.shape[1] == 3 else L.Point2)(tensor=pt)))
+    out["se3_rot"], out["se3_trans"] = T(a3.rotation()), T(a3.translation())
+    out["se2_rot"], out["se2_trans"], out["se2_theta"], out["se2_xy"] = T(a2.rotation), T(a2.translation), a2.theta(), T(a2.xy())
+    J = []; a2.theta(jacobians=J); out["se2_theta_J"] = J[0]
+    J = []; a2.xy(jacobians=J); out["se2_xy_J"] = J[0]
+    out["so2_theta"] = r2.theta(); out["so2_cs0"], out["so2_cs1"] = r2.to_cos_sin()
+    out["so3_quat"] = r3.to_quaternion(); out["so3_from_quat"] = T(L.SO3.unit_quaternion_to_SO3(dev(I["q"])))
+    out["se3_xyzq"] = a3.to_x_y_z_quaternion(); out["se3_from_xyzq"] = T(L.SE3.x_y_z_unit_quaternion_to_SE3(torch.cat((p3, dev(I["q"])), 1)))
+    v, w = L.Vector(tensor=p3.clone()), L.Vector(tensor=dev(I["t3"]).clone())
+    out["v_add"], out["v_sub"], out["v_neg"], out["v_mul"] = T(v + w), T(v - w), T(-v), T(v * w)
+    out["v_dot"], out["v_outer"], out["v_abs"], out["v_norm"] = v.dot(w), v.outer(w), T(v.abs()), v.norm()
+    out["v_cat"], out["v_between"], out["v_compose"], out["v_inverse"], out["v_log"] = T(v.cat(w)), T(v.between(w)), T(v.compose(w)), T(v.inverse()), v.log_map()
+    pt = L.Point3(tensor=p3.clone()); out["p_x"], out["p_y"], out["p_z"] = pt.x(), pt.y(), pt.z()
+    out["se3_project"] = L.SE3(tensor=dev(I["X3"]).clone()).project(dev(I["g"]))
+    out["se3_project_sparse"] = L.SE3(tensor=dev(I["X3"]).clone()).project(dev(I["g2"]), is_sparse=True)
+    out["se2_project_sparse"] = L.SE2(tensor=dev(I["X2"]).clone()).project(dev(I["g2"])[:, :, 0], is_sparse=True)
+    return {k: v.detach().cpu() for k, v in out.items()}
+
+
+def make_geom_api(th):
+    """tests/golden/geom_api_kat.npz: inputs + the reference's outputs of geometry_api_values (operands on the tape)."""
+    import torch
+    d = torch.float64
+    gen = torch.Generator().manual_seed(1)
+    B = 4
+    I = dict(X3=th.SE3.rand(B, generator=gen, dtype=d).tensor, Y3=th.SE3.rand(B, generator=gen, dtype=d).tensor,
+             R3=th.SO3.rand(B, generator=gen, dtype=d).tensor, S3=th.SO3.rand(B, generator=gen, dtype=d).tensor,
+             X2=th.SE2.rand(B, generator=gen, dtype=d).tensor, Y2=th.SE2.rand(B, generator=gen, dtype=d).tensor,
+             R2=th.SO2.rand(B, generator=gen, dtype=d).tensor, S2=th.SO2.rand(B, generator=gen, dtype=d).tensor,
+             p3=torch.randn(B, 3, generator=gen, dtype=d), p2=torch.randn(B, 2, generator=gen, dtype=d),
+             t6=0.7 * torch.randn(B, 6, generator=gen, dtype=d), t3=0.7 * torch.randn(B, 3, generator=gen, dtype=d),
+             t1=torch.randn(B, 1, generator=gen, dtype=d), g=torch.randn(B, 3, 4, generator=gen, dtype=d),
+             g2=torch.randn(B, 5, 3, 4, generator=gen, dtype=d))
+    q = torch.randn(B, 4, generator=gen, dtype=d)
+    I["q"] = q / q.norm(dim=1, keepdim=True)
+    out = geometry_api_values(th, torch, I, tape=True)
+    arrays = {"in_" + k: v.numpy() for k, v in I.items()}
+    arrays.update({"out_" + k: v.numpy() for k, v in out.items()})
+    np.savez_compressed(os.path.join(HERE, "geom_api_kat.npz"), **arrays)
+    print("geom_api_kat:", len(out), "outputs")
+
+
 def make_c5(th):
     """Config C5's problem at full size (2 500 SE3 poses on a sphere, 4 949 edges + prior, n = 15 000), one batch item, 3 LM iterations
     with the reference's CholeskyDenseSolver on the CPU (dense A is 3.6 GB, AtA 1.8 GB: minutes).  Input data from this repository's
@@ -952,6 +1019,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c5":
         make_c5(th)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "geom_api":
+        make_geom_api(th)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tactile":
         make_tactile(th)

@@ -29,4 +29,7 @@ from . import io_formats  # noqa: F401  (g2o / BAL readers: th.io_formats.read_3
 
 from .geometry import enable_lie_group_check, no_lie_group_check, set_lie_group_check_enabled  # noqa: F401,E402
 
+from . import geometry_api as _geometry_api  # noqa: E402
+_geometry_api.install()
+
 __version__ = "0.1.0"

@@ -597,7 +597,11 @@ class AutoDiffCostFunction(CostFunction):
             return self.tensor[item]
 
     def _torch_error(self, optim_tensors, aux_tensors):
-        return self._err_fn(optim_vars=tuple(self._T(t) for t in optim_tensors), aux_vars=tuple(self._T(t) for t in aux_tensors))
+        # err_fn sees variables of the registered classes (SE3, Vector, ...) holding the traced tensors, like the reference's
+        # (cost_function.py:283-316): group methods called on them take the differentiable torch route (geometry_api.py)
+        from .geometry_api import typed_view
+        return self._err_fn(optim_vars=tuple(typed_view(v, t) for v, t in zip(self.optim_vars, optim_tensors)),
+                            aux_vars=tuple(typed_view(v, t) for v, t in zip(self._aux, aux_tensors)))
 
     def _torch_aux(self):
         return self._aux
