@@ -8,7 +8,7 @@ What stands behind them without a GPU: the same kernels compiled unchanged for t
 tests/test_so2.py, tests/test_robust_losses.py).  Order: host-side / torch-route features on GPU-verified kernels first, the kernels that
 are new (dense root, chain-piece substitutions, tiled updates) last.
 
-Contents: a custom VariableOrdering; user-defined CostFunction / CostWeight subclasses (tests/user_costs.py); GNC (Geman-McClure) costs on the engine's generic route; the batched torch route; SO2 rotation
+Contents: a custom VariableOrdering; user-defined CostFunction / CostWeight subclasses (tests/user_costs.py); the geometry classes' public methods on CUDA tensors; GNC (Geman-McClure) costs on the engine's generic route; the batched torch route; SO2 rotation
 averaging (THB_VAR_SO2 branch of the retract kernel); config C4's cost set (planar pushing / tactile pose estimation:
 QuasiStaticPushingPlanar, EffectorObjectContactPlanar, MovingFrameBetween, SE2 priors) through the GPU engine -- LM trace and
 implicit-mode gradients against the reference (tests/golden/tactile_kat.npz); config C5's pose graph at full size; the opt-in sparse
@@ -167,6 +167,19 @@ def test_tactile_implicit_gradients():
     for k, v in leaves.items():
         ref = g["grad_" + k]
         assert np.abs(v.tensor.grad.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), k
+
+
+@pytest.mark.parametrize("tape", [False, True])
+def test_geometry_methods_match_reference_on_the_gpu(tape):
+    """The geometry classes' public methods on CUDA tensors against the reference's values (tests/golden/geom_api_kat.npz; CPU twin:
+    tests/test_geometry_api.py): tape=False -> the group operations are the stand-alone kernels (thb_lie_ops.cu), everything else tensor
+    arithmetic on the device; tape=True -> the differentiable route."""
+    G, g = _golden_module(), load("geom_api_kat")
+    I = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in_")}
+    out = G.geometry_api_values(th, torch, I, tape=tape, device="cuda")
+    assert len(out) >= 100
+    for k, v in out.items():
+        np.testing.assert_allclose(v.numpy(), g["out_" + k], rtol=1e-11, atol=1e-12, err_msg=k)
 
 
 def test_user_defined_costs_linearize_exactly_on_the_gpu():

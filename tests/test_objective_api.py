@@ -131,3 +131,28 @@ def test_custom_variable_ordering_is_recorded_for_the_engine():
     short.append(expected[0])
     with pytest.raises(ValueError, match="not complete"):
         Linearization(objective, ordering=short)
+
+
+def test_objective_and_cost_function_copies_share_nothing_but_names():
+    """objective.py:643-700, theseus_function.py:90-108: copy() of an objective / cost function -- same names, dims and connectivity,
+    independent tensors; a variable or weight used by several cost functions stays ONE object in the copy."""
+    d = torch.float64
+    a, b = th.SE3(name="a", dtype=d), th.SE3(name="b", dtype=d)
+    z = th.SE3(name="z", dtype=d)
+    w = th.DiagonalCostWeight(th.Variable(torch.ones(1, 6, dtype=d), name="w"), name="cw")
+    obj = th.Objective(dtype=d)
+    obj.add(th.Between(a, b, z, w, name="e1"))
+    obj.add(th.Difference(a, th.SE3(name="t", dtype=d), w, name="p1"))
+    obj.add(th.RobustCostFunction(th.Between(b, a, z, w, name="e2"), th.HuberLoss, th.Variable(torch.zeros(1, 1, dtype=d), name="r"), name="rob"))
+    new = obj.copy()
+    assert list(new.cost_functions) == list(obj.cost_functions) and list(new.optim_vars) == list(obj.optim_vars)
+    assert sorted(new.aux_vars) == sorted(obj.aux_vars) and new.dim() == obj.dim()
+    assert new.optim_vars["a"] is not a and new.optim_vars["a"].tensor.data_ptr() != a.tensor.data_ptr()
+    assert new.cost_functions["e1"].optim_var_at(0) is new.cost_functions["p1"].optim_var_at(0) is new.optim_vars["a"]
+    assert new.cost_functions["e1"].weight is new.cost_functions["p1"].weight and new.cost_functions["e1"].weight is not w
+    assert new.cost_functions["rob"].cost_function.optim_var_at(1) is new.optim_vars["a"]
+    assert new.cost_functions["e1"].aux_var_at(0) is new.aux_vars["z"] and new.cost_functions["e1"].num_aux_vars() == 1
+    cf = obj.cost_functions["e1"].copy()
+    assert cf.name == "e1_copy" and cf.optim_var_at(0).name == "a_copy" and cf.weight is not w
+    cf.set_optim_var_at(0, b)
+    assert cf.optim_var_at(0) is b and obj.cost_functions["e1"].optim_var_at(0) is a

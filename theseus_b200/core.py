@@ -26,6 +26,24 @@ COST_BETWEEN_SE2, COST_LOCAL_SE2 = 6, 7
 WEIGHT_SCALE, WEIGHT_DIAGONAL = 0, 1
 
 
+def _shallow_clone_with_copied_vars(obj, attr_names, new_name):
+    """A copy of a cost function / cost weight that shares nothing mutable with the original: same class and plain attributes, every
+    registered variable replaced by its copy (one copy per distinct variable object)."""
+    import copy as _copy
+    new = _copy.copy(obj)
+    new.name = new_name
+    for lst in ("_optim_vars_attr_names", "_aux_vars_attr_names"):
+        if hasattr(obj, lst):
+            setattr(new, lst, list(getattr(obj, lst)))
+    memo = {}
+    for a in attr_names:
+        v = getattr(obj, a)
+        if id(v) not in memo:
+            memo[id(v)] = v.copy()
+        setattr(new, a, memo[id(v)])
+    return new
+
+
 class CostWeight:
     """theseus/core/cost_weight.py:20-55.  A user-defined subclass (WEIGHT_KIND -1) registers its auxiliary variables and implements
     weight_error / weight_jacobians_and_error; cost functions carrying one take the engine's generic route."""
@@ -49,6 +67,28 @@ class CostWeight:
 
     def weight_tensor(self) -> Variable:
         raise NotImplementedError
+
+    def num_aux_vars(self) -> int:
+        return len(self.aux_vars)
+
+    def aux_var_at(self, index: int) -> Variable:
+        return self.aux_vars[index]
+
+    def get_default_name(self) -> str:
+        return f"{self.__class__.__name__}__{id(self)}"
+
+    def copy(self, new_name: Optional[str] = None, keep_variable_names: bool = False) -> "CostWeight":
+        """theseus_function.py:90-108 for a user-defined weight: _copy_impl if the subclass has one, else a shallow clone whose registered
+        variables are copies."""
+        new_name = new_name or f"{self.name}_copy"
+        if hasattr(self, "_copy_impl"):
+            new = self._copy_impl(new_name=new_name)
+        else:
+            new = _shallow_clone_with_copied_vars(self, list(getattr(self, "_aux_vars_attr_names", [])), new_name)
+        if keep_variable_names:
+            for o, n in zip(self.aux_vars, new.aux_vars):
+                n.name = o.name
+        return new
 
     def weight_error(self, error: torch.Tensor) -> torch.Tensor:
         """cost_weight.py:33-35."""
@@ -84,8 +124,8 @@ class ScaleCostWeight(CostWeight):
     def is_zero(self) -> torch.Tensor:
         return self.scale.tensor.squeeze(1) == 0
 
-    def copy(self, new_name: Optional[str] = None):
-        return ScaleCostWeight(self.scale.copy(), name=new_name)
+    def copy(self, new_name: Optional[str] = None, keep_variable_names: bool = False):
+        return ScaleCostWeight(self.scale.copy(new_name=self.scale.name if keep_variable_names else None), name=new_name)
 
 
 class DiagonalCostWeight(CostWeight):
@@ -109,8 +149,8 @@ class DiagonalCostWeight(CostWeight):
     def is_zero(self) -> torch.Tensor:
         return (self.diagonal.tensor == 0).min(dim=1)[0].bool()
 
-    def copy(self, new_name: Optional[str] = None):
-        return DiagonalCostWeight(self.diagonal.copy(), name=new_name)
+    def copy(self, new_name: Optional[str] = None, keep_variable_names: bool = False):
+        return DiagonalCostWeight(self.diagonal.copy(new_name=self.diagonal.name if keep_variable_names else None), name=new_name)
 
 
 class CostFunction:
@@ -149,6 +189,48 @@ class CostFunction:
 
     def num_optim_vars(self) -> int:
         return len(self._optim_vars_attr_names)
+
+    def aux_var_at(self, index: int) -> Variable:
+        return getattr(self, self._aux_vars_attr_names[index])
+
+    def num_aux_vars(self) -> int:
+        return len(self._aux_vars_attr_names)
+
+    def set_optim_var_at(self, index: int, variable: Manifold):
+        """theseus_function.py:67-71."""
+        setattr(self, self._optim_vars_attr_names[index], variable)
+
+    def set_aux_var_at(self, index: int, variable: Variable):
+        setattr(self, self._aux_vars_attr_names[index], variable)
+
+    def register_vars(self, variables, is_optim_vars: bool = False):
+        """theseus_function.py:52-58: registers variables that are attributes named after themselves."""
+        for v in variables:
+            if hasattr(self, v.name):
+                raise RuntimeError(f"Variable name {v.name} is not allowed since it conflicts with an attribute of this function.")
+            setattr(self, v.name, v)
+            (self.register_optim_var if is_optim_vars else self.register_aux_var)(v.name)
+
+    def get_default_name(self) -> str:
+        return f"{self.__class__.__name__}__{CostFunction._ids}"
+
+    def copy(self, new_name: Optional[str] = None, keep_variable_names: bool = False) -> "CostFunction":
+        """theseus_function.py:90-108: a new cost function over COPIES of the variables and of the weight (a subclass's own
+        _copy_impl(new_name=...) is used if it has one)."""
+        new_name = new_name or f"{self.name}_copy"
+        if hasattr(self, "_copy_impl"):
+            new = self._copy_impl(new_name=new_name)
+        else:
+            new = _shallow_clone_with_copied_vars(self, self._optim_vars_attr_names + self._aux_vars_attr_names, new_name)
+            new.weight = self.weight.copy(new_name=None, keep_variable_names=keep_variable_names)
+            inner = getattr(self, "cost_function", None)          # robust wrappers share their inner function's variables and weight
+            if isinstance(inner, CostFunction):
+                new.cost_function = inner.copy(keep_variable_names=keep_variable_names)
+                new.weight = new.cost_function.weight
+        if keep_variable_names:
+            for o, n in zip(self.optim_vars + self.aux_vars, new.optim_vars + new.aux_vars):
+                n.name = o.name
+        return new
 
     def dim(self) -> int:
         raise NotImplementedError
@@ -643,6 +725,38 @@ class Objective:
         self._structure_version += 1
         self._engine = None
         self._batch_size = None
+
+    vectorized = False    # set by optimizer.Vectorize; the engine evaluates per schema group regardless (objective.py:916-960 by name)
+
+    def disable_vectorization(self):
+        self.vectorized = False
+
+    def update_vectorization_if_needed(self):
+        pass
+
+    def copy(self) -> "Objective":
+        """objective.py:643-700: copies of all cost functions, weights and variables with the same names and connectivity (a variable or
+        weight shared by several cost functions is ONE object in the copy, too)."""
+        new = Objective(dtype=self.dtype)
+        weights = {}
+        for cf in self.cost_functions.values():
+            if id(cf.weight) not in weights:
+                weights[id(cf.weight)] = cf.weight.copy(new_name=cf.weight.name, keep_variable_names=True)
+        for cf in self.cost_functions.values():
+            ncf = cf.copy(new_name=cf.name, keep_variable_names=True)
+            ncf.weight = weights[id(cf.weight)]
+            if isinstance(getattr(ncf, "cost_function", None), CostFunction):
+                ncf.cost_function.weight = ncf.weight
+            for target in [ncf] + ([ncf.cost_function] if isinstance(getattr(ncf, "cost_function", None), CostFunction) else []):
+                for i, v in enumerate(target.optim_vars):
+                    if v.name in new.optim_vars:
+                        target.set_optim_var_at(i, new.optim_vars[v.name])
+                for i, v in enumerate(target.aux_vars):
+                    if v.name in new.aux_vars:
+                        target.set_aux_var_at(i, new.aux_vars[v.name])
+            new.add(ncf)
+        new.device = self.device
+        return new
 
     # ---- queries / removal (objective.py:302-470) ----
     def get_cost_function(self, name: str) -> CostFunction:

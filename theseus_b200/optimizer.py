@@ -95,6 +95,28 @@ class Linearization:
         self._differentiable = differentiable
         self._linearize_hessian_impl(_detach_hessian=_detach_hessian)
 
+    # linearization.py:62-87: what a subclass provides
+    def _linearize_jacobian_impl(self):
+        raise NotImplementedError
+
+    def _linearize_hessian_impl(self, _detach_hessian: bool = False):
+        raise NotImplementedError
+
+    def _ata_impl(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def _atb_impl(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def Av(self, v: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def diagonal_scaling(self, v: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def hessian_approx(self):
+        return self.AtA
+
     @property
     def AtA(self) -> torch.Tensor:
         return self._ata_impl()
