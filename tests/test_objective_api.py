@@ -156,3 +156,19 @@ def test_objective_and_cost_function_copies_share_nothing_but_names():
     assert cf.name == "e1_copy" and cf.optim_var_at(0).name == "a_copy" and cf.weight is not w
     cf.set_optim_var_at(0, b)
     assert cf.optim_var_at(0) is b and obj.cost_functions["e1"].optim_var_at(0) is a
+
+
+def test_copy_of_an_autodiff_objective_is_independent():
+    d = torch.float64
+    x = th.Vector(1, name="x", dtype=d)
+    a = th.Variable(torch.ones(3, 5, dtype=d), name="a")
+    cf = th.AutoDiffCostFunction([x], lambda optim_vars, aux_vars: optim_vars[0].tensor * aux_vars[0].tensor, 5, aux_vars=[a], name="ad",
+                                 cost_weight=th.ScaleCostWeight(torch.ones(1, dtype=d)))
+    obj = th.Objective(dtype=d)
+    obj.add(cf)
+    new = obj.copy()
+    ncf = new.cost_functions["ad"]
+    assert new.aux_vars["a"] is ncf.aux_vars[0] and ncf.aux_vars[0] is not a
+    ncf.aux_vars[0].tensor = torch.full((3, 5), 3.0, dtype=d)
+    ncf.optim_vars[0].tensor = torch.full((3, 1), 2.0, dtype=d)
+    assert float(ncf.error()[0, 0]) == 6.0 and float(cf.error()[0, 0]) == 0.0

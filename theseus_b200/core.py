@@ -656,12 +656,10 @@ class AutoDiffCostFunction(CostFunction):
         for v in optim_vars:
             if not isinstance(v, Manifold):
                 raise ValueError("AutoDiffCostFunction optimisation variables must be Manifold instances")
-        self._optim = list(optim_vars)
-        self._aux = aux_vars
-        for i, v in enumerate(self._optim):
+        for i, v in enumerate(optim_vars):          # the registered attributes are the only references (copy() / set_*_var_at replace them)
             setattr(self, f"_optim_var_{i}", v)
             self._optim_vars_attr_names.append(f"_optim_var_{i}")
-        for i, v in enumerate(self._aux):
+        for i, v in enumerate(aux_vars):
             setattr(self, f"_aux_var_{i}", v)
             self._aux_vars_attr_names.append(f"_aux_var_{i}")
         self._err_fn = err_fn
@@ -683,10 +681,10 @@ class AutoDiffCostFunction(CostFunction):
         # (cost_function.py:283-316): group methods called on them take the differentiable torch route (geometry_api.py)
         from .geometry_api import typed_view
         return self._err_fn(optim_vars=tuple(typed_view(v, t) for v, t in zip(self.optim_vars, optim_tensors)),
-                            aux_vars=tuple(typed_view(v, t) for v, t in zip(self._aux, aux_tensors)))
+                            aux_vars=tuple(typed_view(v, t) for v, t in zip(self.aux_vars, aux_tensors)))
 
     def _torch_aux(self):
-        return self._aux
+        return self.aux_vars
 
     def schema(self):
         return None, []
