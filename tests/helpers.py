@@ -39,8 +39,33 @@ def pgo_spec(g, dtype=np.float64):
     return spec
 
 
-def pgo_objective(th, g, device="cuda", dtype=None):
-    """The product objective built exactly like examples/pose_graph/pose_graph_cube.py:56-83."""
+def user_local_cost_cls(th):
+    class UserLocal(th.CostFunction):
+        """A user-written twin of th.Difference (embodied/misc/local_cost_fn.py:15-70) on the reference's plugin contract: the error
+        and its Jacobian come from the library's own group methods, e = log(T^-1 X), J = dlog."""
+
+        def __init__(self, var, target, cost_weight, name=None):
+            super().__init__(cost_weight, name=name)
+            self.var, self.target = var, target
+            self.register_optim_var("var")
+            self.register_aux_var("target")
+
+        def dim(self):
+            return self.var.dof()
+
+        def error(self):
+            return self.target.local(self.var)
+
+        def jacobians(self):
+            J = []
+            err = self.target.between(self.var).log_map(jacobians=J)
+            return [J[0]], err
+    return UserLocal
+
+
+def pgo_objective(th, g, device="cuda", dtype=None, user_prior=False):
+    """The product objective built exactly like examples/pose_graph/pose_graph_cube.py:56-83.  user_prior=True: the gauge prior is a
+    user-defined cost function (user_local_cost_cls) instead of th.Difference -- same numbers, generic route next to the fused groups."""
     import torch
     dtype = dtype or torch.float64
     poses0, edges, meas, edge_w = g["poses0"], g["edges"], g["meas"], g["edge_w"]
@@ -60,8 +85,9 @@ def pgo_objective(th, g, device="cuda", dtype=None):
             cf = th.RobustCostFunction(cf, dict(welsch=th.WelschLoss, huber=th.HuberLoss, hinge=th.HingeLoss)[robust], llr,
                                        name=f"robust_between_{e}")
         objective.add(cf)
-    prior = th.Difference(poses[0], th.SE3(tensor=torch.from_numpy(poses0[0]).to(dtype), name="VERTEX_SE3__0__PRIOR"),
-                          th.ScaleCostWeight(torch.tensor(float(g["prior_w"]), dtype=dtype)), name="prior")
+    prior_cls = user_local_cost_cls(th) if user_prior else th.Difference
+    prior = prior_cls(poses[0], th.SE3(tensor=torch.from_numpy(poses0[0]).to(dtype), name="VERTEX_SE3__0__PRIOR"),
+                      th.ScaleCostWeight(torch.tensor(float(g["prior_w"]), dtype=dtype)), name="prior")
     objective.add(prior)
     objective.to(device)
     return objective, poses

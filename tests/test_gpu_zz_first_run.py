@@ -208,6 +208,30 @@ def test_user_defined_costs_linearize_exactly_on_the_gpu():
     np.testing.assert_allclose(slin.diagonal_scaling(v.cuda()).cpu().numpy(), ((A * A).sum(dim=1) * v).numpy(), rtol=1e-13)
 
 
+@pytest.mark.parametrize("solver", ["dense", "sparse"])
+def test_user_defined_cost_next_to_fused_groups_reproduces_the_reference_trace_on_the_gpu(solver):
+    """pgo_small_lm with its gauge prior as a user-defined cost function (helpers.user_local_cost_cls, error / Jacobian from the
+    library's group kernels) next to the fused Between groups: the reference's LM trace (CPU twin: tests/test_user_defined_costs.py)."""
+    from helpers import pgo_objective, lm_kwargs_of
+    g = load("pgo_small_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g, user_prior=True)
+    skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(
+        linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization)
+    opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw)
+    errs, deltas = [], []
+
+    def cb(o, info, delta, it):
+        errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+    with torch.no_grad():
+        opt.optimize(end_iter_callback=cb, **kw)
+    np.testing.assert_allclose(np.stack(errs, 0), g["trace_err"], rtol=1e-8)
+    for it in range(2):
+        rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
+        assert rel.max() < 1e-5, (it, rel)
+    np.testing.assert_allclose(np.stack([p.tensor.cpu().numpy() for p in poses], 0), g["poses_final"], rtol=1e-6, atol=1e-6)
+
+
 _LM_GRID = [dict(damping=d, ellipsoidal_damping=e, adaptive_damping=a, damping_eps=0.0)
             for d in (0.0, 0.001, 0.01, 0.1) for e in (True, False) for a in (True, False)]
 

@@ -266,3 +266,29 @@ def test_lie_group_checks_at_construction_follow_the_reference():
             fixed3 = th.SE3(tensor=bad3)
         assert torch.equal(th.SE3(tensor=X).tensor, X)
     torch.testing.assert_close(fixed3.tensor, X, rtol=0, atol=1e-13)      # nearest rotation of 1.01 R is R; translation untouched
+
+
+@pytest.mark.parametrize("solver", ["dense", "sparse"])
+def test_user_defined_cost_next_to_fused_groups_reproduces_the_reference_trace(emulated, solver):
+    """A pose graph whose gauge prior is a USER-DEFINED cost function (helpers.user_local_cost_cls: error / Jacobian from the library's
+    group methods) while the edges stay on the fused Between kernels: the LM trace must be the reference's (pgo_small_lm), i.e. the
+    generic route and the fused groups fill one linear system consistently, for both solvers."""
+    from helpers import load, pgo_objective, lm_kwargs_of
+    g = load("pgo_small_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g, device="cpu", user_prior=True)
+    skw = dict(linear_solver_cls=th.CholeskyDenseSolver) if solver == "dense" else dict(
+        linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization)
+    opt = th.LevenbergMarquardt(objective, max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0, **skw)
+    assert len(objective.engine().generic) == 1
+    errs, deltas = [], []
+
+    def cb(o, info, delta, it):
+        errs.append(info.last_err.numpy().copy()); deltas.append(delta.numpy().copy())
+    with torch.no_grad():
+        opt.optimize(end_iter_callback=cb, **kw)
+    np.testing.assert_allclose(np.stack(errs, 0), g["trace_err"], rtol=1e-8)
+    for it in range(2):
+        rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
+        assert rel.max() < 1e-5, (it, rel)
+    np.testing.assert_allclose(np.stack([p.tensor.numpy() for p in poses], 0), g["poses_final"], rtol=1e-6, atol=1e-6)
