@@ -292,3 +292,19 @@ def test_user_defined_cost_next_to_fused_groups_reproduces_the_reference_trace(e
         rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
         assert rel.max() < 1e-5, (it, rel)
     np.testing.assert_allclose(np.stack([p.tensor.numpy() for p in poses], 0), g["poses_final"], rtol=1e-6, atol=1e-6)
+
+
+def test_user_defined_manifold_as_optimisation_variable_is_refused_loudly(emulated):
+    """The one plugin point that is NOT accepted: the retract kernel knows the variable kinds of thb200.h."""
+    class MyManifold(th.Manifold):
+        def dof(self):
+            return self.tensor.shape[1]
+
+    objective, variables = user_costs.regression_problem(th, False, batch_size=2, npoints=2)
+    v = MyManifold(torch.zeros(2, 5, dtype=torch.float64), name="mine")
+    Cost = user_costs.squared_fit_cost_cls(th)
+    bad = th.Objective(dtype=torch.float64)
+    bad.add(Cost([v], th.ScaleCostWeight(torch.ones(1, dtype=torch.float64)), th.Variable(torch.ones(2, 5, dtype=torch.float64), name="p"),
+                 th.Variable(torch.ones(2, 1, dtype=torch.float64), name="t"), name="c"))
+    with pytest.raises(NotImplementedError, match="user-defined Manifold"):
+        th.GaussNewton(bad).optimize()

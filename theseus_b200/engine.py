@@ -70,6 +70,11 @@ class Engine:
         self.ordering: List[Manifold] = (list(objective.optim_vars.values()) if ordering_names is None
                                          else [objective.optim_vars[n] for n in ordering_names])
         self.var_index = {v.name: i for i, v in enumerate(self.ordering)}
+        for v in self.ordering:
+            if int(getattr(v, "KIND", -1)) not in (0, 1, 2, 3, 4):
+                raise NotImplementedError(
+                    f"optimisation variable {v.name} ({type(v).__name__}): the retract / commit kernels are compiled for the variable kinds of "
+                    "include/thb200.h (SE3, SO3, Vector / Point2 / Point3, SE2, SO2); a user-defined Manifold cannot be an optimisation variable")
         costs = list(objective.cost_functions.values())
         self.costs = costs
         cdesc = [(cf.dim(), [self.var_index[v.name] for v in cf.optim_vars]) for cf in costs]
