@@ -308,3 +308,23 @@ def test_user_defined_manifold_as_optimisation_variable_is_refused_loudly(emulat
                  th.Variable(torch.ones(2, 1, dtype=torch.float64), name="t"), name="c"))
     with pytest.raises(NotImplementedError, match="user-defined Manifold"):
         th.GaussNewton(bad).optimize()
+
+
+def test_masked_jacobians_and_masked_variables():
+    """core/cost_function.py:37-55, core/variable.py:134-148."""
+    gen = torch.Generator().manual_seed(2)
+    d = torch.float64
+    a, b, z = (th.rand_se3(5, generator=gen, dtype=d) for _ in range(3))
+    cf = th.Between(a, b, z, th.ScaleCostWeight(torch.ones(1, dtype=d)))
+    mask = torch.tensor([True, False, True, True, False])
+    with torch.no_grad():
+        full_j, full_e = cf.jacobians()
+        mj, me = th.masked_jacobians(cf, mask)
+    assert me.shape == full_e.shape and mj[0].shape == full_j[0].shape
+    torch.testing.assert_close(me[mask], full_e[mask])
+    torch.testing.assert_close(mj[1][mask], full_j[1][mask])
+    assert float(me[~mask].abs().max()) == 0.0 and float(mj[0][~mask].abs().max()) == 0.0
+    assert a.tensor.shape[0] == 5
+    with th.masked_variables([a, b], mask):
+        assert a.tensor.shape[0] == 3 and b.tensor.shape[0] == 3
+    assert a.tensor.shape[0] == 5

@@ -14,7 +14,7 @@ or PyTorch fallback.  Importing the package does not require a GPU; evaluating a
 from .geometry import Variable, Manifold, LieGroup, Vector, Point2, Point3, SE2, SE3, SO2, SO3, as_variable  # noqa: F401
 from .core import (AutogradMode, CostWeight, ScaleCostWeight, DiagonalCostWeight, CostFunction, Between, Difference, Local,  # noqa: F401
                    Reprojection, AutoDiffCostFunction, RobustCostFunction, GNCRobustCostFunction, RobustLoss, WelschLoss, HuberLoss,
-                   HingeLoss, GNCRobustLoss, GemanMcClureLoss, Objective)
+                   HingeLoss, GNCRobustLoss, GemanMcClureLoss, Objective, masked_jacobians, masked_variables)
 from . import embodied as eb  # noqa: F401  (th.eb.Reprojection, like the reference)
 from .optimizer import (VariableOrdering, Linearization, DenseLinearization, SparseLinearization, LinearSolver,  # noqa: F401
                         DenseSolver, CholeskyDenseSolver, LUDenseSolver, NonlinearLeastSquares, GaussNewton,

@@ -153,6 +153,39 @@ class DiagonalCostWeight(CostWeight):
         return DiagonalCostWeight(self.diagonal.copy(new_name=self.diagonal.name if keep_variable_names else None), name=new_name)
 
 
+class masked_variables:
+    """core/variable.py:134-148: inside the context every variable holds only the batch items selected by the boolean `mask`."""
+
+    def __init__(self, vars: Sequence[Variable], mask: torch.Tensor) -> None:
+        assert mask.dtype == torch.bool and mask.ndim == 1
+        self._vars, self._mask = list(vars), mask
+        self._original = [v.tensor for v in self._vars]
+
+    def __enter__(self) -> None:
+        for v in self._vars:
+            assert v.tensor.shape[0] == self._mask.shape[0]
+            v._tensor = v.tensor[self._mask]          # around the setter: a temporary view, no pointer table is invalidated
+
+    def __exit__(self, exc_type, exc_value, traceback) -> None:
+        for v, t in zip(self._vars, self._original):
+            v._tensor = t
+
+
+def masked_jacobians(cost_fn: "CostFunction", mask: torch.Tensor):
+    """core/cost_function.py:37-55: jacobians() / error of `cost_fn` evaluated only for the batch items selected by `mask`; outputs keep
+    the full batch shape, unselected items are zero."""
+    cf_vars = list(cost_fn.optim_vars) + list(cost_fn.aux_vars)
+    batch_size = max(v.tensor.shape[0] for v in cf_vars)
+    ref = cf_vars[0].tensor
+    jacobians = [ref.new_zeros(batch_size, cost_fn.dim(), v.dof()) for v in cost_fn.optim_vars]
+    err = ref.new_zeros(batch_size, cost_fn.dim())
+    with masked_variables(cf_vars, mask):
+        mj, err[mask] = cost_fn.jacobians()
+        for m, j in zip(mj, jacobians):
+            j[mask] = m
+    return jacobians, err
+
+
 class CostFunction:
     """theseus/core/cost_function.py:64-149.  Subclasses with a CUDA schema set COST_KIND via schema()."""
     _ids = 0
