@@ -465,6 +465,14 @@ int thb_se2_adjoint_f32(const float* group, float* adj, int64_t N, thb_stream_t 
 int thb_se2_inverse_f32(const float* group, float* out, int64_t N, thb_stream_t stream);
 int thb_se2_compose_f32(const float* g0, const float* g1, float* out, int64_t N, thb_stream_t stream);
 
+/* Exponential map together with its right Jacobian d exp(t) / d t (torchlie/functional/so3_impl.py:270-320 _jexp_impl,
+ * se3_impl.py:225-330 _jexp_impl_helper / _jexp_impl; what LieGroup.exp_map(tangent, jacobians=[...]) returns, lie_group.py:84-93).
+ * Shapes: SO3 tangent [N,3], group [N,3,3], jexp [N,3,3]; SE3 tangent [N,6], group [N,3,4], jexp [N,6,6].  `group` may be NULL. */
+int thb_so3_jexp_f64(const double* tangent, double* group /* may be NULL */, double* jexp, int64_t N, thb_stream_t stream);
+int thb_se3_jexp_f64(const double* tangent, double* group /* may be NULL */, double* jexp, int64_t N, thb_stream_t stream);
+int thb_so3_jexp_f32(const float* tangent, float* group /* may be NULL */, float* jexp, int64_t N, thb_stream_t stream);
+int thb_se3_jexp_f32(const float* tangent, float* group /* may be NULL */, float* jexp, int64_t N, thb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,6 +182,19 @@ def test_geometry_methods_match_reference_on_the_gpu(tape):
         np.testing.assert_allclose(v.numpy(), g["out_" + k], rtol=1e-11, atol=1e-12, err_msg=k)
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_exp_map_with_jacobians_on_the_gpu(dt):
+    """thb_so3_jexp / thb_se3_jexp on the device against the reference's values over its angle sweep (tests/golden/lie_kat.npz); CPU twin
+    on the host emulation: tests/test_geometry_api.py."""
+    g = load("lie_kat")
+    tol = dict(rtol=1e-9, atol=1e-11) if dt == "f64" else dict(rtol=2e-4, atol=2e-5)
+    for name, cls in (("so3", th.SO3), ("se3", th.SE3)):
+        J = []
+        G = cls.exp_map(torch.from_numpy(g[f"{name}_{dt}_tangent"]).cuda(), jacobians=J)
+        np.testing.assert_allclose(G.tensor.cpu().numpy(), g[f"{name}_{dt}_exp"], **tol, err_msg=name)
+        np.testing.assert_allclose(J[0].cpu().numpy(), g[f"{name}_{dt}_jexp"], **tol, err_msg=name)
+
+
 def test_user_defined_costs_linearize_exactly_on_the_gpu():
     """User-defined CostFunction / CostWeight subclasses (the reference's plugin contract) through the engine's generic route on the
     device: the hand-written 6 x 10 system of the reference's linearization tests, dense and sparse (tests/user_costs.py; CPU twin on

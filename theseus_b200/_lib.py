@@ -144,6 +144,8 @@ for _sfx, _ in (("f64", c_f64), ("f32", c_f32)):
     SIGNATURES[f"thb_se3_adjoint_{_sfx}"] = (c_i32, [c_vp, c_vp, c_i64, c_vp])
     SIGNATURES[f"thb_se3_inverse_{_sfx}"] = (c_i32, [c_vp, c_vp, c_i64, c_vp])
     SIGNATURES[f"thb_se3_compose_{_sfx}"] = (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp])
+    SIGNATURES[f"thb_se3_jexp_{_sfx}"] = (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp])
+    SIGNATURES[f"thb_so3_jexp_{_sfx}"] = (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp])
     for _g in ("so3", "se2"):
         SIGNATURES[f"thb_{_g}_exp_{_sfx}"] = (c_i32, [c_vp, c_vp, c_i64, c_vp])
         SIGNATURES[f"thb_{_g}_log_{_sfx}"] = (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp])

@@ -122,6 +122,82 @@ template <typename T> __device__ __forceinline__ void se3_exp(const T* xi, T* G)
   G[11] = c.sine_by_theta * v[2] + c.omc_by_theta2 * cz + tms * (w[2] * wv);
 }
 
+// Right Jacobian of the SO3 exponential (so3_impl.py:270-320, _jexp_impl): J[9] row-major,
+//   J = sin(t)/t I + (t - sin t)/t^3 w w^T - (1 - cos t)/t^2 [w]x     (near zero: the w w^T coefficient is 0, as in the reference).
+// `tms` is the caller's (theta - sine)/theta^3 coefficient for the rotation block.
+template <typename T> __device__ __forceinline__ void so3_jexp_from_coef(const T* w, const So3ExpCoef<T>& c, T tms_rot, T* J) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) J[i * 3 + j] = tms_rot * w[i] * w[j];
+  J[0] += c.sine_by_theta;
+  J[4] += c.sine_by_theta;
+  J[8] += c.sine_by_theta;
+  const T t0 = c.omc_by_theta2 * w[0], t1 = c.omc_by_theta2 * w[1], t2 = c.omc_by_theta2 * w[2];
+  J[1] += t2;
+  J[3] -= t2;
+  J[2] -= t1;
+  J[6] += t1;
+  J[5] += t0;
+  J[7] -= t0;
+}
+
+// SO3 exp + right Jacobian: w[3] -> R[9] (row stride 3), J[9].
+template <typename T> __device__ __forceinline__ void so3_exp_jexp(const T* w, T* R, T* J) {
+  const So3ExpCoef<T> c = so3_exp<T, 3>(w, R);
+  const T theta3_nz = c.theta_nz * c.theta2_nz;
+  const T tms = c.near_zero ? T(0) : ((c.theta - c.sine) / theta3_nz);
+  so3_jexp_from_coef(w, c, tms, J);
+}
+
+// SE3 exp + right Jacobian (se3_impl.py:225-330, _jexp_impl_helper / _jexp_impl): xi[6] = [v, w] -> G[12], J[36] row-major with
+//   J = [[Jr, R^T Jt], [0, Jr]],  Jr = the SO3 right Jacobian of w,  Jt = d t / d w assembled from the series coefficients below.
+template <typename T> __device__ __forceinline__ void se3_exp_jexp(const T* xi, T* G, T* J) {
+  const T* v = xi;
+  const T* w = xi + 3;
+  se3_exp(xi, G);
+  T Rtmp[9];
+  const So3ExpCoef<T> c = so3_exp<T, 3>(w, Rtmp);
+  const T theta3_nz = c.theta_nz * c.theta2_nz;
+  const T tms_t = c.near_zero ? (T(1.0 / 6) - c.theta2 / T(120)) : ((c.theta - c.sine) / theta3_nz);
+  const T tms_rot = c.near_zero ? T(0) : tms_t;
+  T Jr[9];
+  so3_jexp_from_coef(w, c, tms_rot, Jr);
+  const T d_omc = c.near_zero ? T(-1.0 / 12) : ((c.sine_by_theta - T(2) * c.omc_by_theta2) / c.theta2_nz);
+  const T d_tms = c.near_zero ? T(-1.0 / 60) : ((c.omc_by_theta2 - T(3) * tms_t) / c.theta2_nz);
+  const T wv[3] = {w[1] * v[2] - w[2] * v[1], w[2] * v[0] - w[0] * v[2], w[0] * v[1] - w[1] * v[0]};
+  const T wwv[3] = {w[1] * wv[2] - w[2] * wv[1], w[2] * wv[0] - w[0] * wv[2], w[0] * wv[1] - w[1] * wv[0]};
+  const T sw[3] = {tms_t * w[0], tms_t * w[1], tms_t * w[2]};
+  T Jt[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Jt[i * 3 + j] = (d_omc * wv[i] + d_tms * wwv[i]) * w[j] - v[i] * sw[j];
+  const T tv[3] = {-c.omc_by_theta2 * v[0] - tms_t * wv[0], -c.omc_by_theta2 * v[1] - tms_t * wv[1], -c.omc_by_theta2 * v[2] - tms_t * wv[2]};
+  // + hat(tv)
+  Jt[1] -= tv[2];
+  Jt[2] += tv[1];
+  Jt[3] += tv[2];
+  Jt[5] -= tv[0];
+  Jt[6] -= tv[1];
+  Jt[7] += tv[0];
+  const T sv = sw[0] * v[0] + sw[1] * v[1] + sw[2] * v[2];
+  Jt[0] += sv;
+  Jt[4] += sv;
+  Jt[8] += sv;
+#pragma unroll
+  for (int q = 0; q < 36; q++) J[q] = T(0);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      J[i * 6 + j] = Jr[i * 3 + j];
+      J[(i + 3) * 6 + (j + 3)] = Jr[i * 3 + j];
+      // R^T Jt, R = rotation block of G (row stride 4)
+      J[i * 6 + (j + 3)] = G[0 * 4 + i] * Jt[0 * 3 + j] + G[1 * 4 + i] * Jt[1 * 3 + j] + G[2 * 4 + i] * Jt[2 * 3 + j];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // SO3 log (so3_impl.py:390-433).  R has row stride RS.  Returns theta, sine, cosine for jlog.
 template <typename T> struct So3LogAux {

@@ -112,6 +112,36 @@ template <typename T> __global__ void k_se2_compose(const T* __restrict__ A, con
   for (int q = 0; q < 4; q++) O[i * 4 + q] = o[q];
 }
 
+// exp + right Jacobian of exp (so3_impl.py:270-320, se3_impl.py:225-330); `group` may be NULL
+template <typename T> __global__ void k_so3_jexp(const T* __restrict__ w, T* __restrict__ R, T* __restrict__ J, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  T x[3], r[9], j[9];
+#pragma unroll
+  for (int q = 0; q < 3; q++) x[q] = w[i * 3 + q];
+  so3_exp_jexp(x, r, j);
+#pragma unroll
+  for (int q = 0; q < 9; q++) J[i * 9 + q] = j[q];
+  if (R != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 9; q++) R[i * 9 + q] = r[q];
+  }
+}
+template <typename T> __global__ void k_se3_jexp(const T* __restrict__ xi, T* __restrict__ G, T* __restrict__ J, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  T x[6], g[12], j[36];
+#pragma unroll
+  for (int q = 0; q < 6; q++) x[q] = xi[i * 6 + q];
+  se3_exp_jexp(x, g, j);
+#pragma unroll
+  for (int q = 0; q < 36; q++) J[i * 36 + q] = j[q];
+  if (G != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 12; q++) G[i * 12 + q] = g[q];
+  }
+}
+
 }  // namespace thb
 
 #define THB_OPS_ENTRY(KERNEL, ...)                                                 \
@@ -133,7 +163,9 @@ extern "C" {
   int thb_se2_log_##SFX(const T* g, T* t, T* j, int64_t N, thb_stream_t s) THB_OPS_ENTRY(thb::k_se2_log<T>, g, t, j, N)                       \
   int thb_se2_adjoint_##SFX(const T* g, T* a, int64_t N, thb_stream_t s) THB_OPS_ENTRY(thb::k_se2_adjoint<T>, g, a, N)                        \
   int thb_se2_inverse_##SFX(const T* g, T* o, int64_t N, thb_stream_t s) THB_OPS_ENTRY(thb::k_se2_inverse<T>, g, o, N)                        \
-  int thb_se2_compose_##SFX(const T* a, const T* b, T* o, int64_t N, thb_stream_t s) THB_OPS_ENTRY(thb::k_se2_compose<T>, a, b, o, N)
+  int thb_se2_compose_##SFX(const T* a, const T* b, T* o, int64_t N, thb_stream_t s) THB_OPS_ENTRY(thb::k_se2_compose<T>, a, b, o, N)         \
+  int thb_so3_jexp_##SFX(const T* t, T* g, T* j, int64_t N, thb_stream_t s) THB_OPS_ENTRY(thb::k_so3_jexp<T>, t, g, j, N)                     \
+  int thb_se3_jexp_##SFX(const T* t, T* g, T* j, int64_t N, thb_stream_t s) THB_OPS_ENTRY(thb::k_se3_jexp<T>, t, g, j, N)
 THB_OPS_FOR(double, f64)
 THB_OPS_FOR(float, f32)
 }  // extern "C"

@@ -57,14 +57,58 @@ def _adjoint_torch(kind: int, g: torch.Tensor) -> torch.Tensor:
     return torch.ones(g.shape[0], 1, 1, dtype=g.dtype, device=g.device)
 
 
+_SE2_NEAR_ZERO = {torch.float32: 3e-2, torch.float64: 1e-6}     # theseus/global_params.py:46-59
+
+
+def _exp_with_jacobian(cls, tangent_vector: torch.Tensor, jacobians: List[torch.Tensor]):
+    """LieGroup.exp_map(tangent, jacobians=[]) (lie_group.py:84-93): the group element and d exp / d tangent (right Jacobian).
+    SO3 / SE3: one kernel for both (thb_so3_jexp / thb_se3_jexp: so3_impl.py:270-320, se3_impl.py:225-330); SE2 / SO2: the closed form
+    of se2.py:239-300 / so2.py:222-234 in the few tensor operations the reference uses."""
+    from . import _lib
+    from .geometry import _require_cuda, _sfx
+    LieGroup._check_jacobians_list(jacobians)
+    kind = cls.KIND
+    if kind in (0, 1):
+        if on_tape(tangent_vector):
+            raise NotImplementedError(f"{cls.__name__}.exp_map(..., jacobians=[...]) of a tensor on the autograd tape")
+        _require_cuda(tangent_vector, f"{cls.__name__}.exp_map")
+        t = tangent_vector.contiguous()
+        n, gshape, name = (6, (3, 4), "se3") if kind == 0 else (3, (3, 3), "so3")
+        out = torch.empty((t.shape[0],) + gshape, dtype=t.dtype, device=t.device)
+        J = torch.empty(t.shape[0], n, n, dtype=t.dtype, device=t.device)
+        _lib.check(getattr(_lib.load(), f"thb_{name}_jexp_{_sfx(t)}")(_lib.ptr(t), _lib.ptr(out), _lib.ptr(J), t.shape[0], _lib.stream_ptr()), f"{name}_jexp")
+        jacobians.append(J)
+        return cls(tensor=out, disable_checks=True)
+    group = cls.exp_map(tangent_vector)         # SE2 / SO2: the element first (it may refuse the tensor), then the closed-form Jacobian
+    if kind == 4:
+        jacobians.append(torch.ones(tangent_vector.shape[0], 1, 1, dtype=tangent_vector.dtype, device=tangent_vector.device))
+        return group
+    u, theta = tangent_vector[:, :2], tangent_vector[:, 2]
+    cosine, sine = theta.cos(), theta.sin()
+    small = theta.abs() < _SE2_NEAR_ZERO[tangent_vector.dtype]
+    one = torch.ones((), dtype=theta.dtype, device=theta.device)
+    theta2, theta3 = theta ** 2, theta ** 3
+    theta_nz, theta2_nz = torch.where(small, one, theta), torch.where(small, one, theta2)
+    sbt = torch.where(small, 1 - theta2 / 6, sine / theta_nz)
+    cm1bt = torch.where(small, -theta / 2 + theta3 / 24, (cosine - 1) / theta_nz)
+    tmsbt2 = torch.where(small, theta - theta3 / 120, (theta - sine) / theta2_nz)
+    cm1bt2 = torch.where(small, -0.5 + theta2 / 24, (cosine - 1) / theta2_nz)
+    z, o = torch.zeros_like(theta), torch.ones_like(theta)
+    jacobians.append(torch.stack((torch.stack((sbt, -cm1bt, tmsbt2 * u[:, 0] + cm1bt2 * u[:, 1]), -1),
+                                  torch.stack((cm1bt, sbt, tmsbt2 * u[:, 1] - cm1bt2 * u[:, 0]), -1), torch.stack((z, z, o), -1)), -2))
+    return group
+
+
 def _install_tape_route(cls):
     kind = cls.KIND
     k_exp, k_log, k_inv, k_mul, k_adj = cls.exp_map, cls.log_map, cls.inverse, cls.compose, getattr(cls, "adjoint", None)
 
     def exp_map(tangent_vector: torch.Tensor, jacobians: Optional[List[torch.Tensor]] = None):
-        if jacobians is None and on_tape(tangent_vector):
+        if jacobians is not None:
+            return _exp_with_jacobian(cls, tangent_vector, jacobians)
+        if on_tape(tangent_vector):
             return cls(tensor=_EXP[kind](tangent_vector), disable_checks=True)
-        return k_exp(tangent_vector) if jacobians is None else k_exp(tangent_vector, jacobians)
+        return k_exp(tangent_vector)
 
     def log_map(self, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
         if jacobians is None and on_tape(self.tensor):
