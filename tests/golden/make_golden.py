@@ -884,6 +884,13 @@ def geometry_api_values(L, torch, I, tape, device="cpu", group_ops=True):
             out[name + "_compose"] = T(a.compose(b)); out[name + "_inverse"] = T(a.inverse()); out[name + "_log"] = a.log_map()
             out[name + "_exp"] = T(cls.exp_map(mk(tv))); out[name + "_adjoint"] = a.adjoint(); out[name + "_between"] = T(a.between(b))
             out[name + "_local"] = a.local(b); out[name + "_retract"] = T(a.retract(mk(tv)))
+            if not tape:     # the optional Jacobian outputs (lie_group.py:125-195), plain operands
+                J = []; a.compose(b, jacobians=J); out[name + "_compose_J0"], out[name + "_compose_J1"] = J
+                J = []; a.inverse(jacobian=J); out[name + "_inverse_J"] = J[0]
+                J = []; a.between(b, jacobians=J); out[name + "_between_J0"], out[name + "_between_J1"] = J
+                J = []; a.local(b, jacobians=J); out[name + "_local_J0"], out[name + "_local_J1"] = J
+                J = []; a.log_map(jacobians=J); out[name + "_log_J"] = J[0]
+                J = []; cls.exp_map(dev(tv), jacobians=J); out[name + "_exp_J"] = J[0]
         out[name + "_to_matrix"] = a.to_matrix(); out[name + "_hat"] = cls.hat(dev(tv)); out[name + "_vee"] = cls.vee(cls.hat(dev(tv)))
     a3, a2, r3, r2 = L.SE3(tensor=mk(I["X3"])), L.SE2(tensor=mk(I["X2"])), L.SO3(tensor=mk(I["R3"])), L.SO2(tensor=mk(I["R2"]))
     p3, p2 = dev(I["p3"]), dev(I["p2"])
@@ -928,6 +935,7 @@ def make_geom_api(th):
     q = torch.randn(B, 4, generator=gen, dtype=d)
     I["q"] = q / q.norm(dim=1, keepdim=True)
     out = geometry_api_values(th, torch, I, tape=True)
+    out.update(geometry_api_values(th, torch, I, tape=False))      # + the Jacobian outputs of the group operations
     arrays = {"in_" + k: v.numpy() for k, v in I.items()}
     arrays.update({"out_" + k: v.numpy() for k, v in out.items()})
     np.savez_compressed(os.path.join(HERE, "geom_api_kat.npz"), **arrays)

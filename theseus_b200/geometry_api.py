@@ -464,6 +464,55 @@ def _project(self, euclidean_grad: torch.Tensor, is_sparse: bool = False) -> tor
     return type(self).project_tensor(self.tensor, euclidean_grad.unsqueeze(1)).squeeze(1)
 
 
+def _install_group_jacobians(cls):
+    """lie_group.py:125-195: the optional Jacobian outputs of compose / inverse / between / local, assembled from adjoints and dlog exactly
+    as the reference does (d compose = [Ad(g2^-1), I], d inverse = -Ad(g), d between = [Ad(g2^-1) (-Ad(g1)), I],
+    d local = [-Ad(diff^-1) dlog, dlog])."""
+    base_compose, base_inverse = cls.compose, cls.inverse
+
+    def _eye(g):
+        return torch.eye(g.dof(), dtype=g.dtype, device=g.device).repeat(g.tensor.shape[0], 1, 1)
+
+    def compose(self, variable2, jacobians: Optional[List[torch.Tensor]] = None):
+        if type(self) is not type(variable2):
+            raise ValueError("Lie groups for compose must be of the same type.")
+        out = base_compose(self, variable2)
+        if jacobians is not None:
+            LieGroup._check_jacobians_list(jacobians)
+            jacobians.extend([base_inverse(variable2).adjoint(), _eye(variable2)])
+        return out
+
+    def inverse(self, jacobian: Optional[List[torch.Tensor]] = None):
+        out = base_inverse(self)
+        if jacobian is not None:
+            LieGroup._check_jacobians_list(jacobian)
+            jacobian.append(-self.adjoint())
+        return out
+
+    def between(self, variable2, jacobians: Optional[List[torch.Tensor]] = None):
+        v1_inverse = base_inverse(self)
+        out = base_compose(v1_inverse, variable2)
+        if jacobians is not None:
+            LieGroup._check_jacobians_list(jacobians)
+            jacobians.extend([base_inverse(variable2).adjoint() @ (-self.adjoint()), _eye(variable2)])
+        return out
+
+    def local(self, variable2, jacobians: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        diff = between(self, variable2)
+        if jacobians is None:
+            return diff.log_map()
+        LieGroup._check_jacobians_list(jacobians)
+        dlog: List[torch.Tensor] = []
+        ret = diff.log_map(dlog)
+        jacobians.extend([-(base_inverse(diff).adjoint() @ dlog[0]), dlog[0]])
+        return ret
+
+    def retract(self, delta: torch.Tensor):
+        return base_compose(self, cls.exp_map(delta))
+
+    cls.compose, cls.inverse, cls.between, cls.local, cls.retract = compose, inverse, between, local, retract
+
+
 def typed_view(var: Variable, tensor: torch.Tensor) -> Variable:
     """A variable of `var`'s class and name around another tensor (what the reference's AutoDiffCostFunction hands to err_fn:
     copies of the variables holding the traced tensors, cost_function.py:283-316) -- built without the constructor: no checks, no
@@ -478,6 +527,7 @@ def install():
     LieGroup._check_jacobians_list = staticmethod(_check_jacobians_list)
     for cls in (SE3, SO3, SE2, SO2):
         _install_tape_route(cls)
+        _install_group_jacobians(cls)
         cls.project = _project
     SE3.rotation, SE3.translation = _se3_rotation, _se3_translation
     SE3.transform_from, SE3.transform_to, SE3.to_matrix = _se3_transform_from, _se3_transform_to, _se3_to_matrix
