@@ -210,15 +210,21 @@ def run_c5_layout_child(args):
     print(json.dumps(res))
 
 
-def first_run_layouts(lane_result, timeout_s=200):
+def first_run_layouts(lane_result, timeout_s=150, total_s=330):
     """N=1 only, after everything else is measured: the opt-in sparse layouts, each in its own process (run_c5_layout_child) under a
-    timeout.  Same data as the parent's `lane` run (seed 0), so `final_err_mean` must agree with it."""
+    timeout (and all of them under `total_s`, so the default run stays within minutes whatever happens in a child).  Same data as the
+    parent's `lane` run (seed 0), so `final_err_mean` must agree with it."""
     out = {}
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    t_start = time.perf_counter()
     for tag, layout, supernodal in FIRST_RUN_LAYOUTS:
+        left = total_s - (time.perf_counter() - t_start)
+        if left < 30:
+            out[tag] = dict(error="skipped: the time set aside for the first-run layouts is used up")
+            continue
         cmd = [sys.executable, os.path.abspath(__file__), "--c5-layout", layout] + (["--c5-supernodal"] if supernodal else [])
         try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=min(timeout_s, left), env=env, cwd=ROOT)
             lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             if r.returncode == 0 and lines:
                 res = json.loads(lines[-1])
@@ -229,7 +235,7 @@ def first_run_layouts(lane_result, timeout_s=200):
             else:
                 out[tag] = dict(error=f"exit code {r.returncode}", stderr_tail=r.stderr[-400:])
         except subprocess.TimeoutExpired:
-            out[tag] = dict(error=f"timeout after {timeout_s} s")
+            out[tag] = dict(error=f"timeout after {min(timeout_s, left):.0f} s")
         except Exception as e:
             out[tag] = dict(error=repr(e)[:300])
     return out
