@@ -3,7 +3,7 @@
 # Runs everything that was written after the round-1 GPU budget was spent (tests/test_gpu_zz_first_run.py), then times the new sparse
 # layouts on the C5 shape.  Every step under its own timeout; logs in gpurun_out/.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_zz_first_run.py -m gpu -q -rxX --timeout=400 -p no:cacheprovider > gpurun_out/r02_pending.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_zz_first_run.py tests/first_run_kernels.py -m gpu -q -rxX --timeout=400 -p no:cacheprovider > gpurun_out/r02_pending.log 2>&1
 echo "pending rc=$?" >> gpurun_out/r02_pending.log
 tail -5 gpurun_out/r02_pending.log
 for B in 128 512; do
