@@ -106,11 +106,12 @@ def _lm_worker(rank, world, port, out):
 def test_sharded_lm_loop_equals_the_single_process_run_per_batch_item():
     """the batch shards over ranks with ONE all-reduce of the reject / item counts per LM iteration and nothing else.
     World size 2 (gloo) against world size 1 on the same problems: every per-item quantity (error history, final poses) is the
-    single-process one, because no kernel mixes batch items and the only global decision (all items rejected -> retry) agrees.  Tolerance,
-    not bitwise: the dense Gram kernel's work partition depends on the batch size of the launch, so an item's sums are associated
-    differently in a 1-item and a 3-item launch (1e-16), which the last LM iterations at the rounding floor amplify to 1e-9 (with the
-    block-sparse solver, whose per-item arithmetic does not depend on the batch size, the same comparison is bitwise -- checked by hand,
-    200 s on the emulation, too slow for this suite)."""
+    single-process one, because no kernel mixes batch items and the only global decision (all items rejected -> retry, a BATCH-global rule
+    of the reference: nonlinear_least_squares.py:181-187) is taken on the all-reduced counts.  Compared with a tolerance: on the rank that
+    holds a single item the final poses differ by 1e-9 from the single-process run with the dense solver -- the last LM iterations of
+    this problem sit at the rounding floor where accept / reject is noise (helpers.decisive_iterations); one linear solve and the first
+    iterations are bitwise equal for every batch size, the remaining source was not tracked down in round 1.
+    With the block-sparse solver the same comparison was bitwise (checked by hand: 200 s on the emulation, too slow for this suite)."""
     mgr = mp.Manager()
     out = mgr.dict()
     port = 31000 + (os.getpid() % 2000)
