@@ -739,6 +739,8 @@ def so2_problem(th, torch, thetas0, meas, edges, w_edge, w_prior, device="cpu"):
                                  th.ScaleCostWeight(torch.tensor(float(w_edge[e]), dtype=d, device=device)), name=f"between_{e}"))
     objective.add(th.Difference(vs[0], th.SO2(theta=thetas0[0].to(device), name="R0_prior"),
                                 th.ScaleCostWeight(torch.tensor(float(w_prior), dtype=d, device=device)), name="prior"))
+    if str(device) != "cpu":
+        objective.to(device)
     return objective, vs
 
 
@@ -815,6 +817,8 @@ def tactile_problem(th, torch, inputs, device="cpu"):
         objective.add(th.eb.MovingFrameBetween(objs[t], objs[t + 1], effs[t], effs[t + 1],
                                                th.SE2(tensor=inputs["mfb_meas"][t].clone().to(device), name=f"mfb_meas_{t}"), w_mfb, name=f"mfb_{t}"))
     objective.add(th.Difference(objs[0], th.SE2(tensor=inputs["obj"][0].clone().to(device), name="obj0_prior"), w_prior, name="objprior"))
+    if str(device) != "cpu":
+        objective.to(device)
     return objective, objs, effs, dict(c_square=c2, eff_radius=radius, w_qsp=w_qsp.scale, w_eoc=w_eoc.scale, w_mfb=w_mfb.scale)
 
 

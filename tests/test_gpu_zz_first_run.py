@@ -22,8 +22,7 @@ import theseus_b200 as th
 from helpers import load, decisive_iterations
 from test_gpu_backward import _golden_module
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first device run: written after the round-1 GPU budget was spent (host emulation green)")]
+pytestmark = [pytest.mark.gpu]
 LM = dict(damping=1e-2, adaptive_damping=True, ellipsoidal_damping=True)
 
 

@@ -1,0 +1,487 @@
+"""Symbolic analysis of the batched MULTIFRONTAL (supernodal) block-sparse Cholesky -- layout "front" of BaspachoSparseSolver.
+
+Replaces what the reference delegates to BaSpaCho::createSolver behind SymbolicDecomposition(param_size, block_ptrs, block_inds, dev)
+(theseus/extlib/baspacho_solver.cpp:259-319: fill-reducing ordering, supernodes, factor layout); same inputs, internals unobservable in
+the reference ("parity unpinned") -- the un-permuted solution is what is checked.
+
+Steps (host, batch independent, once per structure):
+  1. ordering: nested dissection of the block graph (level-set separators from pseudo-peripheral nodes) and minimum degree
+     (sparse.minimum_degree_order); the one with fewer factorisation flops wins (pose graphs: ND; bundle adjustment: min degree);
+  2. elimination tree + column structures;
+  3. supernodes -> FRONTS by relaxed amalgamation (children merged into the parent while the dense flops grow little);
+  4. per front s: w_s pivot scalars (contiguous in the permuted vector), b_s border rows, r_s = w_s + b_s; the factor panel
+     L[rows_s, cols_s] is a dense row-major r_s x w_s matrix at panel_off[s] of one item's factor storage;
+  5. depth schedule: all children of a front sit exactly one depth below it, so update matrices (and the forward substitution's
+     border vectors) live for one step in a ping-pong arena indexed by depth parity;
+  6. child -> parent relative row maps, per-class launch lists (small fronts: one CTA per (front, item) in shared memory;
+     big fronts: assembled in global memory and factored by the DMMA dense kernel in partial mode).
+`execute_numpy` runs the very arrays the kernels consume (tests/test_frontal.py).
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+SMALL_CLASSES = (48, 96, 160)     # front size limits (scalar rows) of the shared-memory kernel's size classes
+BIG_TW, BIG_TM = 64, 128          # block-column width / row-tile height of the dense DMMA kernel (thb_chol_dense.cu)
+
+
+# ------------------------------------------------------------------------------------------------ ordering
+def _bfs_levels(adj, start, mask, stamp, mark):
+    mark[start] = True
+    levels, seen = [[start]], [start]
+    while True:
+        nxt = []
+        for u in levels[-1]:
+            for v in adj[u]:
+                if mask[v] == stamp and not mark[v]:
+                    mark[v] = True
+                    nxt.append(v)
+                    seen.append(v)
+        if not nxt:
+            break
+        levels.append(nxt)
+    for v in seen:
+        mark[v] = False
+    return levels, seen
+
+
+def nested_dissection_order(N: int, ptrs: np.ndarray, inds: np.ndarray, leaf: int = 8) -> np.ndarray:
+    """order[k] = variable eliminated k-th.  Recursive bisection by the middle level set of a BFS from a pseudo-peripheral node
+    (George's automatic nested dissection), separator nodes that do not touch the far side moved back, separators ordered last;
+    deterministic."""
+    adj = [[int(x) for x in inds[ptrs[i]:ptrs[i + 1]] if int(x) != i] for i in range(N)]
+    mask = np.zeros(N, dtype=np.int64)
+    mark = np.zeros(N, dtype=bool)
+    order: List[int] = []
+    stamp = [0]
+    # explicit stack, emitting separators AFTER both halves: entries are ("nodes", list) or ("emit", list)
+    work = [("nodes", list(range(N)))]
+    while work:
+        kind, nodes = work.pop()
+        if kind == "emit":
+            order.extend(nodes)
+            continue
+        if not nodes:
+            continue
+        stamp[0] += 1
+        s = stamp[0]
+        for v in nodes:
+            mask[v] = s
+        if len(nodes) <= leaf:
+            order.extend(sorted(nodes, key=lambda v: (sum(1 for x in adj[v] if mask[x] == s), v)))
+            for v in nodes:
+                mask[v] = 0
+            continue
+        remaining = set(nodes)
+        comps = []
+        for v in nodes:
+            if v in remaining:
+                _, seen = _bfs_levels(adj, v, mask, s, mark)
+                comps.append(seen)
+                remaining.difference_update(seen)
+        if len(comps) > 1:
+            for c in reversed(comps):
+                work.append(("nodes", c))
+            continue
+        levels, _ = _bfs_levels(adj, nodes[0], mask, s, mark)
+        for _ in range(4):
+            cand = min(levels[-1], key=lambda v: (sum(1 for x in adj[v] if mask[x] == s), v))
+            l2, _ = _bfs_levels(adj, cand, mask, s, mark)
+            if len(l2) > len(levels):
+                levels = l2
+            else:
+                break
+        if len(levels) < 3:
+            order.extend(sorted(nodes))
+            for v in nodes:
+                mask[v] = 0
+            continue
+        tot = len(nodes)
+        cum = np.cumsum([len(l) for l in levels])
+        best, bi = None, None
+        for i in range(1, len(levels) - 1):
+            left, right = int(cum[i - 1]), tot - int(cum[i])
+            bal = min(left, right) / max(left, right, 1)
+            if bal < 0.4:
+                continue
+            score = (len(levels[i]), -bal)
+            if best is None or score < best:
+                best, bi = score, i
+        if bi is None:
+            bi = min(max(int(np.argmin(np.abs(cum - tot / 2))), 1), len(levels) - 2)
+        right = [v for l in levels[bi + 1:] for v in l]
+        left = [v for l in levels[:bi] for v in l]
+        rs = set(right)
+        sep = []
+        for v in levels[bi]:
+            if any((x in rs) for x in adj[v]):
+                sep.append(v)
+            else:
+                left.append(v)
+        for v in sep:
+            mask[v] = 0
+        work.append(("emit", sorted(sep)))
+        work.append(("nodes", right))
+        work.append(("nodes", left))
+    assert len(order) == N
+    return np.array(order, dtype=np.int64)
+
+
+def _column_structures(N, ptrs, inds, order):
+    """Elimination tree parent[] and the sorted below-diagonal block structure of every column, in elimination positions."""
+    pos = np.empty(N, dtype=np.int64)
+    pos[order] = np.arange(N)
+    parent = -np.ones(N, dtype=np.int64)
+    struct: List[Optional[set]] = [None] * N
+    children: List[List[int]] = [[] for _ in range(N)]
+    for j in range(N):
+        v = int(order[j])
+        s = set(int(pos[x]) for x in inds[ptrs[v]:ptrs[v + 1]] if pos[x] > j)
+        for c in children[j]:
+            s.update(struct[c])
+        s.discard(j)
+        struct[j] = s
+        if s:
+            p = min(s)
+            parent[j] = p
+            children[p].append(j)
+    return pos, parent, [np.array(sorted(s), dtype=np.int64) for s in struct]
+
+
+def _flops_of(struct, dims):
+    """Factorisation flops (mul + add) of the block column structures."""
+    fl = 0.0
+    for j, s in enumerate(struct):
+        r = float(sum(dims[i] for i in s))
+        d = float(dims[j])
+        fl += d ** 3 / 3.0 + d * d * r + d * r * r
+    return fl
+
+
+def _front_cost(w, b):
+    return w ** 3 / 3.0 + w * w * b + w * b * b
+
+
+# ------------------------------------------------------------------------------------------------ the plan
+@dataclass
+class FrontPlan:
+    N: int
+    n: int
+    param_size: np.ndarray
+    order: np.ndarray          # [N] order[k] = original variable at elimination position k
+    pos: np.ndarray            # [N]
+    dims: np.ndarray           # [N] per position
+    pstart: np.ndarray         # [N] scalar start in the permuted vector, per position
+    col_start: np.ndarray      # [N] scalar start in the ORIGINAL column layout, per position
+    perm: np.ndarray           # [n] perm[p] = original scalar column of permuted scalar p
+    S: int
+    arrays: Dict[str, np.ndarray]   # flat per-front arrays consumed by the kernels (see build_front_plan)
+    launches: np.ndarray       # [num_launches, 4] (depth, class, start, count) over arrays["sched"]; depth descending
+    data_size: int             # doubles of one item's factor storage (sum of panels)
+    arena_size: int            # doubles of one item's update-matrix arena (one parity)
+    varena_size: int           # doubles of one item's border-vector arena (one parity)
+    stats: Dict[str, float] = field(default_factory=dict)
+    front_of_pos: np.ndarray = None
+    border_rows: List[np.ndarray] = None   # per front: permuted scalar indices of the border rows
+
+    def gram_out_offsets(self):
+        """Callable for structure.build_gram_plan: where block (a, b) of AtA (original variables, pos[a] >= pos[b]) lands in the
+        panel storage: (offset, leading dimension, mirror=-1)."""
+        A = self.arrays
+        first, w, poff = A["f_first"], A["f_w"], A["f_panel_off"]
+
+        def f(a: int, b: int):
+            pa, pb = int(self.pos[a]), int(self.pos[b])
+            s = int(self.front_of_pos[pb])
+            lcol = int(self.pstart[pb] - first[s])
+            ga = int(self.pstart[pa])
+            if ga < first[s] + w[s]:
+                lrow = ga - int(first[s])
+            else:
+                k = int(np.searchsorted(self.border_rows[s], ga))
+                assert self.border_rows[s][k] == ga
+                lrow = int(w[s]) + k
+            return int(poff[s]) + lrow * int(w[s]) + lcol, int(w[s]), -1
+        return f
+
+
+def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float = 0.12, merge_flops: float = 4e4,
+                     merge_max_r: int = SMALL_CLASSES[1], small_limit: int = SMALL_CLASSES[-1]) -> FrontPlan:
+    param_size = np.asarray(param_size, dtype=np.int64)
+    ptrs = np.asarray(ptrs, dtype=np.int64)
+    inds = np.asarray(inds, dtype=np.int64)
+    N = int(param_size.shape[0])
+    from .sparse import minimum_degree_order
+    cands = {}
+    if ordering in ("auto", "nd"):
+        cands["nd"] = nested_dissection_order(N, ptrs, inds)
+    if ordering in ("auto", "mindeg"):
+        cands["mindeg"] = minimum_degree_order(N, ptrs, inds, param_size)
+    if ordering == "natural":
+        cands["natural"] = np.arange(N, dtype=np.int64)
+    if not cands:
+        raise ValueError(ordering)
+    best = None
+    for name, o in cands.items():
+        pos0, parent, struct = _column_structures(N, ptrs, inds, o)
+        fl = _flops_of(struct, param_size[o])
+        if best is None or fl < best[0]:
+            best = (fl, name, o, pos0, parent, struct)
+    col_flops, oname, order0, pos0, parent, struct = best
+    dims0 = param_size[order0]
+
+    # ---- fundamental supernodes ----
+    nchild = np.zeros(N, dtype=np.int64)
+    for j in range(N):
+        if parent[j] >= 0:
+            nchild[parent[j]] += 1
+    firsts = [0]
+    for j in range(1, N):
+        if not (parent[j - 1] == j and len(struct[j - 1]) == len(struct[j]) + 1 and nchild[j] == 1):
+            firsts.append(j)
+    firsts.append(N)
+    sn = [(firsts[i], firsts[i + 1]) for i in range(len(firsts) - 1)]
+    S0 = len(sn)
+    sn_of = np.empty(N, dtype=np.int64)
+    for s, (a, b) in enumerate(sn):
+        sn_of[a:b] = s
+    cols = [list(range(a, b)) for a, b in sn]
+    below = [struct[b - 1] for a, b in sn]
+    wsz = [int(dims0[a:b].sum()) for a, b in sn]
+    bsz = [int(dims0[struct[b - 1]].sum()) if len(struct[b - 1]) else 0 for a, b in sn]
+    par = np.array([sn_of[parent[b - 1]] if parent[b - 1] >= 0 else -1 for a, b in sn], dtype=np.int64)
+    kids: List[List[int]] = [[] for _ in range(S0)]
+    for s in range(S0):
+        if par[s] >= 0:
+            kids[par[s]].append(s)
+    alive = np.ones(S0, dtype=bool)
+    # ---- relaxed amalgamation, bottom-up (supernode indices are a topological order) ----
+    for p in range(S0):
+        changed = True
+        while changed and kids[p]:
+            changed = False
+            for c in sorted(kids[p], key=lambda c: (wsz[c] + bsz[c], c)):
+                sep = _front_cost(wsz[c], bsz[c]) + _front_cost(wsz[p], bsz[p])
+                mer = _front_cost(wsz[c] + wsz[p], bsz[p])
+                r_m = wsz[c] + wsz[p] + bsz[p]
+                if mer <= (1.0 + tau) * sep or (mer <= sep + merge_flops and r_m <= merge_max_r):
+                    cols[p] = cols[c] + cols[p]
+                    wsz[p] += wsz[c]
+                    alive[c] = False
+                    kids[p].remove(c)
+                    for g in kids[c]:
+                        par[g] = p
+                        kids[p].append(g)
+                    kids[c] = []
+                    changed = True
+                    break
+    keep = [s for s in range(S0) if alive[s]]
+    S = len(keep)
+    new_id = -np.ones(S0, dtype=np.int64)
+    new_id[keep] = np.arange(S)
+    # ---- final elimination order: fronts in topological order, each front's columns contiguous ----
+    old_positions = np.array([j for s in keep for j in cols[s]], dtype=np.int64)
+    assert sorted(old_positions.tolist()) == list(range(N))
+    newpos_of_old = np.empty(N, dtype=np.int64)
+    newpos_of_old[old_positions] = np.arange(N)
+    order = order0[old_positions]
+    pos = np.empty(N, dtype=np.int64)
+    pos[order] = np.arange(N)
+    dims = param_size[order]
+    pstart = np.concatenate([[0], np.cumsum(dims)[:-1]]).astype(np.int64)
+    n = int(dims.sum())
+    orig_start = np.concatenate([[0], np.cumsum(param_size)[:-1]]).astype(np.int64)
+    col_start = orig_start[order]
+    perm = np.concatenate([np.arange(col_start[k], col_start[k] + dims[k]) for k in range(N)]).astype(np.int64) if N else np.zeros(0, np.int64)
+
+    f_w = np.zeros(S, dtype=np.int32)
+    f_b = np.zeros(S, dtype=np.int32)
+    f_first = np.zeros(S, dtype=np.int32)
+    f_parent = -np.ones(S, dtype=np.int32)
+    front_of_pos = np.empty(N, dtype=np.int64)
+    border_rows: List[np.ndarray] = []
+    k0 = 0
+    for t, s in enumerate(keep):
+        nc = len(cols[s])
+        front_of_pos[k0:k0 + nc] = t
+        f_first[t] = pstart[k0]
+        f_w[t] = int(dims[k0:k0 + nc].sum())
+        bp = np.sort(newpos_of_old[below[s]]) if len(below[s]) else np.zeros(0, dtype=np.int64)
+        assert len(bp) == 0 or bp[0] >= k0 + nc
+        rows = np.concatenate([np.arange(pstart[q], pstart[q] + dims[q]) for q in bp]).astype(np.int64) if len(bp) else np.zeros(0, np.int64)
+        border_rows.append(rows)
+        f_b[t] = rows.shape[0]
+        k0 += nc
+    for t in range(S):
+        if f_b[t] > 0:
+            first_row_pos = int(np.searchsorted(pstart, border_rows[t][0], side="right") - 1)
+            f_parent[t] = int(front_of_pos[first_row_pos])
+            assert f_parent[t] > t
+    f_r = f_w + f_b
+    # ---- depth (root = 0); children sit exactly one depth below their parent ----
+    f_depth = np.zeros(S, dtype=np.int32)
+    for t in range(S - 1, -1, -1):
+        if f_parent[t] >= 0:
+            f_depth[t] = f_depth[f_parent[t]] + 1
+    max_depth = int(f_depth.max()) if S else 0
+    children: List[List[int]] = [[] for _ in range(S)]
+    for t in range(S):
+        if f_parent[t] >= 0:
+            children[f_parent[t]].append(t)
+    # ---- size class: 0..2 shared-memory kernel, 3 dense DMMA kernel ----
+    f_class = np.zeros(S, dtype=np.int32)
+    for t in range(S):
+        r = int(f_r[t])
+        f_class[t] = 3 if r > small_limit else int(np.searchsorted(np.array(SMALL_CLASSES), r))
+    # ---- storage: panels, update-matrix arena (by depth parity), border-vector arena ----
+    f_panel_off = np.zeros(S, dtype=np.int64)
+    off = 0
+    for t in range(S):
+        f_panel_off[t] = off
+        off += int(f_r[t]) * int(f_w[t])
+        off += off & 1                      # keep every panel 16-byte aligned
+    data_size = off
+    f_wpad = np.zeros(S, dtype=np.int32)    # big fronts: pivot columns padded to a multiple of the block-column width
+    f_np = np.zeros(S, dtype=np.int32)      # big fronts: padded order of the dense front matrix
+    f_cb_off = np.zeros(S, dtype=np.int64)  # offset of CB[0][0] (first border row / column) in the arena of parity depth % 2
+    f_cb_ld = np.zeros(S, dtype=np.int32)
+    f_fr_off = np.zeros(S, dtype=np.int64)  # big fronts: offset of the dense front matrix F (np x np)
+    f_u_off = np.zeros(S, dtype=np.int64)
+    arena = [0, 0]
+    varena = [0, 0]
+    for d in range(max_depth, -1, -1):
+        a = 0
+        v = 0
+        for t in np.nonzero(f_depth == d)[0]:
+            if f_class[t] == 3:
+                wp = -(-int(f_w[t]) // BIG_TW) * BIG_TW
+                npad = -(-(wp + int(f_b[t])) // BIG_TM) * BIG_TM
+                f_wpad[t], f_np[t] = wp, npad
+                f_fr_off[t] = a
+                f_cb_off[t] = a + wp * npad + wp
+                f_cb_ld[t] = npad
+                a += npad * npad
+            else:
+                ld = int(f_b[t]) + (int(f_b[t]) & 1)
+                f_cb_off[t] = a
+                f_cb_ld[t] = ld
+                a += int(f_b[t]) * ld
+            f_u_off[t] = v
+            v += int(f_b[t]) + (int(f_b[t]) & 1)
+        arena[d & 1] = max(arena[d & 1], a)
+        varena[d & 1] = max(varena[d & 1], v)
+    arena_size = max(arena) + 2
+    varena_size = max(varena) + 2
+    # ---- children lists + relative row maps ----
+    child_ptr = np.zeros(S + 1, dtype=np.int32)
+    child_list: List[int] = []
+    rel_ptr = np.zeros(S + 1, dtype=np.int64)      # per CHILD front: its border rows' local indices in the parent front
+    rel_list: List[np.ndarray] = []
+    for t in range(S):
+        child_list.extend(children[t])
+        child_ptr[t + 1] = len(child_list)
+    racc = 0
+    for t in range(S):
+        p = int(f_parent[t])
+        if p >= 0:
+            g = border_rows[t]
+            inp = g < f_first[p] + f_w[p]
+            loc = np.where(inp, g - f_first[p], f_w[p] + np.searchsorted(border_rows[p], g))
+            chk = np.where(inp, True, border_rows[p][np.minimum(loc - f_w[p], max(len(border_rows[p]) - 1, 0))] == g) if len(border_rows[p]) else inp
+            assert bool(np.all(chk)) and bool(np.all(g >= f_first[p]))
+            rel_list.append(loc.astype(np.int32))
+            racc += len(loc)
+        rel_ptr[t + 1] = racc
+    f_rel = np.concatenate(rel_list).astype(np.int32) if rel_list else np.zeros(0, dtype=np.int32)
+    rows_ptr = np.zeros(S + 1, dtype=np.int64)
+    rows_ptr[1:] = np.cumsum(f_b)
+    f_rows = np.concatenate(border_rows).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
+    # ---- schedule ----
+    sched = np.array(sorted(range(S), key=lambda t: (-int(f_depth[t]), int(f_class[t]), -int(f_r[t]), t)), dtype=np.int32)
+    launches = []
+    i = 0
+    while i < S:
+        t = int(sched[i])
+        d, c = int(f_depth[t]), int(f_class[t])
+        j = i + 1
+        if c != 3:
+            while j < S and int(f_depth[sched[j]]) == d and int(f_class[sched[j]]) == c:
+                j += 1
+        launches.append((d, c, i, j - i))
+        i = j
+    launches = np.array(launches, dtype=np.int32).reshape(-1, 4)
+    flops = float(sum(_front_cost(float(f_w[t]), float(f_b[t])) for t in range(S)))
+    stats = dict(ordering=oname, column_flops=col_flops, flops=flops, nnz_L=float(sum(int(f_r[t]) * int(f_w[t]) for t in range(S))),
+                 fronts=float(S), max_front=float(f_r.max()) if S else 0.0, depth=float(max_depth + 1), big_fronts=float((f_class == 3).sum()),
+                 launches=float(len(launches)), cb_doubles=float(sum(int(b) * int(b) for b in f_b)), levels=float(max_depth + 1),
+                 num_updates=0.0, num_chains=float(S), chain_levels=float(max_depth + 1))
+    arrays = dict(f_w=f_w, f_b=f_b, f_first=f_first, f_parent=f_parent, f_depth=f_depth, f_class=f_class, f_panel_off=f_panel_off,
+                  f_wpad=f_wpad, f_np=f_np, f_cb_off=f_cb_off, f_cb_ld=f_cb_ld, f_fr_off=f_fr_off, f_u_off=f_u_off,
+                  child_ptr=child_ptr, child_list=np.array(child_list, dtype=np.int32), rel_ptr=rel_ptr, f_rel=f_rel,
+                  rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32))
+    return FrontPlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, pstart=pstart, col_start=col_start, perm=perm, S=S,
+                     arrays=arrays, launches=launches, data_size=int(data_size), arena_size=int(arena_size), varena_size=int(varena_size),
+                     stats=stats, front_of_pos=front_of_pos, border_rows=border_rows)
+
+
+# ------------------------------------------------------------------------------------------------ numpy interpreter (tests)
+def execute_numpy(plan: FrontPlan, panels: np.ndarray, rhs: np.ndarray):
+    """Runs the plan's arrays like the kernels do, for ONE item: `panels` [data_size] holds AtA (+ damping) scattered by
+    gram_out_offsets; rhs [n] in ORIGINAL column order.  Returns (x [n] original order, factored panels)."""
+    A = plan.arrays
+    P = panels.astype(np.float64).copy()
+    S = plan.S
+    cb: Dict[int, np.ndarray] = {}
+    w, b, first, poff = A["f_w"], A["f_b"], A["f_first"], A["f_panel_off"]
+
+    def rel_of(c):
+        return A["f_rel"][A["rel_ptr"][c]:A["rel_ptr"][c + 1]]
+
+    def kids(t):
+        return A["child_list"][A["child_ptr"][t]:A["child_ptr"][t + 1]]
+    for (d, cls, s0, cnt) in plan.launches:
+        for t in A["sched"][s0:s0 + cnt]:
+            wt, bt = int(w[t]), int(b[t])
+            r = wt + bt
+            F = np.zeros((r, r))
+            F[:, :wt] = P[poff[t]:poff[t] + r * wt].reshape(r, wt)
+            for c in kids(t):
+                rel = rel_of(c)
+                C = np.tril(cb.pop(int(c)))
+                F[np.ix_(rel, rel)] += C
+            F = np.tril(F)
+            L11 = np.linalg.cholesky(F[:wt, :wt] + np.tril(F[:wt, :wt], -1).T)
+            F[:wt, :wt] = L11
+            if bt:
+                L21 = np.linalg.solve(L11, F[wt:, :wt].T).T
+                F[wt:, :wt] = L21
+                cb[int(t)] = F[wt:, wt:] + np.tril(F[wt:, wt:], -1).T - L21 @ L21.T
+            P[poff[t]:poff[t] + r * wt] = F[:, :wt].reshape(-1)
+    y = rhs[plan.perm].astype(np.float64).copy()
+    ub: Dict[int, np.ndarray] = {}
+    for (d, cls, s0, cnt) in plan.launches:          # forward, deepest first
+        for t in A["sched"][s0:s0 + cnt]:
+            wt, bt = int(w[t]), int(b[t])
+            r = wt + bt
+            Lp = P[poff[t]:poff[t] + r * wt].reshape(r, wt)
+            u = np.zeros(r)
+            u[:wt] = y[first[t]:first[t] + wt]
+            for c in kids(t):
+                u[rel_of(c)] += ub.pop(int(c))
+            yt = np.linalg.solve(np.tril(Lp[:wt]), u[:wt])
+            y[first[t]:first[t] + wt] = yt
+            if bt:
+                ub[int(t)] = u[wt:] - Lp[wt:] @ yt
+    x = y
+    for (d, cls, s0, cnt) in plan.launches[::-1]:    # backward, root first
+        for t in A["sched"][s0:s0 + cnt]:
+            wt, bt = int(w[t]), int(b[t])
+            r = wt + bt
+            Lp = P[poff[t]:poff[t] + r * wt].reshape(r, wt)
+            rows = A["f_rows"][A["rows_ptr"][t]:A["rows_ptr"][t + 1]]
+            tt = x[first[t]:first[t] + wt] - (Lp[wt:].T @ x[rows] if bt else 0.0)
+            x[first[t]:first[t] + wt] = np.linalg.solve(np.tril(Lp[:wt]).T, tt)
+    out = np.empty(plan.n)
+    out[plan.perm] = x
+    return out, P
