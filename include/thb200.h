@@ -402,6 +402,60 @@ int thb_lm_control_f32(const float* delta, const float* Atb, const float* diag, 
                        float down_ratio, float up_ratio, uint8_t* reject, float* err_out, int32_t* stats, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * MULTIFRONTAL (supernodal) batched block-sparse Cholesky -- layout "front" of the Python BaspachoSparseSolver.
+ * Replaces BaSpaCho's batched supernodal factor / solve behind NumericDecomposition::factor / solve
+ * (theseus/extlib/baspacho_solver_cuda.cu:203-214, 282-287; baspacho_solver.cpp:291) for batches that share one structure.
+ * The symbolic side (theseus_b200/frontal.py: nested-dissection / minimum-degree ordering, relaxed supernode amalgamation ->
+ * FRONTS, depth schedule) hands over flat per-front arrays; all pointers are device arrays.
+ *   front t: w pivot scalars (contiguous in the permuted vector from f_first[t]), b border rows, r = w + b.
+ *   factor storage of one item: per front a dense ROW-MAJOR r x w panel at f_panel_off[t] (leading dimension w):
+ *     rows 0..w-1 the pivot block (lower triangle = L_tt), rows w.. the border rows L[border, pivots].
+ *     add_MtM scatters AtA into the same panels (thb_gram_f64 with frontal.FrontPlan.gram_out_offsets, item-major
+ *     [B, data_size]); the caller zero-fills first.  Damping (alpha, beta) is applied while a panel is loaded.
+ *   update matrices (Schur complements) live for one depth step in arena [2][B][arena_size] (parity = depth & 1):
+ *     small fronts: lower triangle of a b x b matrix at f_cb_off[t], leading dimension f_cb_ld[t];
+ *     big fronts (f_class == 3): the whole padded front matrix F [np x np] at f_fr_off[t] (pivot columns padded to f_wpad[t],
+ *     a multiple of 64, identity on the padding), factored in place by the DMMA dense kernel in partial mode
+ *     (thb_potrf_partial_inplace_f64); its trailing block IS the update matrix (f_cb_off / f_cb_ld point into it).
+ *   child -> parent maps: f_rel[rel_ptr[c] .. rel_ptr[c+1]) = local row index in the parent front of child c's border rows.
+ * `launches` is a HOST array [num_launches][10] (int64) in factorisation order (deepest fronts first):
+ *   (depth, class, begin, count [into sched], dynamic smem bytes of the factor kernel, np, pivot block columns, f_fr_off,
+ *    f_first [info base], front index) -- the last five for class-3 launches (one front each).
+ * No atomics on data: results are bitwise reproducible and independent of the batch size.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thb_front_plan {
+  int64_t S;            /* number of fronts */
+  int64_t n;            /* scalar dimension */
+  int64_t data_size;    /* doubles per item in `factor` */
+  int64_t arena_size;   /* doubles per item and parity in `arena` */
+  int64_t varena_size;  /* doubles per item and parity in `varena` (border vectors of the forward substitution) */
+  const int32_t* f_w; const int32_t* f_b; const int32_t* f_first; const int32_t* f_class;
+  const int32_t* f_wpad; const int32_t* f_np; const int32_t* f_cb_ld; const int32_t* f_depth;
+  const int64_t* f_panel_off; const int64_t* f_cb_off; const int64_t* f_fr_off; const int64_t* f_u_off;
+  const int32_t* child_ptr; const int32_t* child_list;   /* children of front t: child_list[child_ptr[t] .. child_ptr[t+1]) */
+  const int64_t* rel_ptr; const int32_t* f_rel;
+  const int64_t* rows_ptr; const int32_t* f_rows;        /* border rows of front t as permuted scalar indices */
+  const int32_t* sched;                                  /* [S] fronts in launch order */
+  const int32_t* perm;                                   /* [n] original scalar column of permuted scalar p */
+} thb_front_plan;
+
+#define THB_FRONT_LAUNCH_COLS 10
+/* dynamic shared memory (bytes) the small-front factor kernel needs for a front with w pivots and b border rows */
+int64_t thb_front_small_smem_bytes(int32_t w, int32_t b);
+/* factor: in-place on `factor` [B, data_size] (AtA + fill-in zeros in, L out); dense_ws: workspace of
+ * thb_potrf_partial_workspace_bytes(B, max np) bytes (may be NULL when there is no class-3 front);
+ * info[b] = 0 or 1 + permuted index of a non-positive pivot (cleared here). */
+int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* alpha,
+                         const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes, int32_t* info, int64_t B,
+                         thb_stream_t stream);
+/* x = (L L^T)^-1 rhs; rhs, x [B, n] in ORIGINAL column order; work [B, n], varena [2, B, varena_size] scratch */
+int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, const double* factor, const double* rhs,
+                        double* x, double* work, double* varena, int64_t B, thb_stream_t stream);
+int64_t thb_potrf_partial_workspace_bytes(int64_t B, int64_t np);
+int thb_potrf_partial_inplace_f64(double* F, int64_t bstride, int64_t np, int32_t nb_piv, int32_t info_base, int32_t* info, int64_t B,
+                                  void* workspace, int64_t workspace_bytes, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Batched CSR helpers (same semantics as theseus/extlib/mat_mult.cu:359-400, int64 indices):
  *   thb_mat_vec : y[b,row]  = sum_k A_val[b,k] v[b,col_k]          (mat_vec,  mat_mult.cu:134-214)
  *   thb_tmat_vec: y[b,col] += A_val[b,k] v[b,row]  (deterministic) (tmat_vec, mat_mult.cu:216-295)

@@ -10,7 +10,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "..", "theseus_b200", "csrc")
-SOURCES = ["thb_sparse_lane.cu", "thb_costs.cu", "thb_gram.cu", "thb_sparse.cu", "thb_lie_ops.cu"]     # + the headers they include (thb_lie.cuh)
+SOURCES = ["thb_sparse_lane.cu", "thb_costs.cu", "thb_gram.cu", "thb_sparse.cu", "thb_lie_ops.cu", "thb_front.cu"]     # + the headers they include (thb_lie.cuh)
 HEADERS = ["thb_lie.cuh"]
 OUT_DIR = os.path.join(HERE, "_build")
 

@@ -91,7 +91,14 @@ def patch_host(setattr_fn, lib):
     setattr_fn(engine_mod, "_require_cuda_device", lambda device: None)
     setattr_fn(geometry_mod, "_require_cuda", lambda t, what: None)
     # the one host read per LM iteration goes through pinned memory and a stream synchronisation on the GPU
-    setattr_fn(optimizer_mod.LevenbergMarquardt, "_read_stats", lambda self, stats, B: int(stats[0]) == B)
+    def _read_stats(self, stats, B):
+        if self.process_group is not None:      # same collective as the product's _read_stats (the sharded-loop test relies on it)
+            from theseus_b200.distributed import reduce_counts
+            stats[1] = B
+            reduce_counts(stats, self.process_group)
+            return int(stats[0]) == int(stats[1])
+        return int(stats[0]) == B
+    setattr_fn(optimizer_mod.LevenbergMarquardt, "_read_stats", _read_stats)
 
 
 def _is_cuda(d):

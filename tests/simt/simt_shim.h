@@ -52,6 +52,16 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   simt_warp->bar.arrive_and_wait();
   return r;
 }
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  memcpy(&simt_warp->slot[simt_lane], &v, sizeof(T));
+  simt_warp->bar.arrive_and_wait();
+  T r;
+  memcpy(&r, &simt_warp->slot[src_lane & 31], sizeof(T));
+  simt_warp->bar.arrive_and_wait();
+  return r;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { simt_warp->bar.arrive_and_wait(); }
 inline int atomicAdd(int* addr, int val) { return __sync_fetch_and_add(addr, val); }
 inline char* simt_dyn_smem_ptr = nullptr;

@@ -1,0 +1,159 @@
+"""Multifrontal block-sparse Cholesky (layout "front": theseus_b200/frontal.py + csrc/thb_front.cu) on the GPU, through the C ABI:
+random block-sparse systems like the reference's solver tests (tests/theseus_tests/extlib/test_baspacho.py:16-150: residual of
+(AtA + damping) x = Atb), small fronts (shared-memory kernel, DMMA rank-w updates) and big fronts (padded dense front matrices, the DMMA
+dense kernel in partial mode), the not-positive-definite report, equality with the lane layout, batch-size independence, and config C5's
+full-size LM trace against the reference's dense-solver trace."""
+import numpy as np
+import pytest
+import torch
+
+import theseus_b200 as th
+from theseus_b200.structure import build_structure
+from helpers import load, pgo_objective, lm_kwargs_of, decisive_iterations
+from test_gpu_sparse_solver import _random_structure, _dense_system
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid_structure(rows, cols, dim=6):
+    N = rows * cols
+    costs = []
+    for i in range(rows):
+        for j in range(cols):
+            if j + 1 < cols: costs.append((dim, [i * cols + j, i * cols + j + 1]))
+            if i + 1 < rows: costs.append((dim, [i * cols + j, (i + 1) * cols + j]))
+    costs += [(dim, [v]) for v in range(N)]
+    return build_structure([dim] * N, costs)
+
+
+def _check(S, B, seed, front_options=None, ordering="mindeg", tol=1e-10):
+    rng = np.random.default_rng(seed)
+    solver = th.BaspachoSparseSolver.from_structure(S, layout="front", ordering=ordering, front_options=front_options)
+    A_val = torch.from_numpy(rng.standard_normal((B, S.nnz))).cuda()
+    b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
+    solver.linearization.A_val, solver.linearization.b = A_val, b
+    alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
+    AtA0, Atb = _dense_system(S, A_val, b)
+    idx = np.arange(S.num_cols)
+    out = None
+    for ell, damping in ((True, alpha), (False, alpha), (False, 0.37), (None, None)):
+        x = solver.solve(damping=damping, ellipsoidal_damping=bool(ell), damping_eps=1e-6) if damping is not None else solver.solve()
+        AtA = AtA0.copy()
+        if damping is not None:
+            dv = damping.cpu().numpy() if torch.is_tensor(damping) else np.full(B, damping)
+            if ell:
+                AtA[:, idx, idx] = AtA[:, idx, idx] * (1 + dv[:, None]) + 1e-6
+            else:
+                AtA[:, idx, idx] += dv[:, None]
+        res = np.einsum("bij,bj->bi", AtA, x.cpu().numpy()) - Atb
+        scale = np.abs(AtA).sum(axis=2).max() * max(1.0, np.abs(x.cpu().numpy()).max())
+        assert np.abs(res).max() < tol * scale, (ell, np.abs(res).max(), scale)
+        out = out if out is not None else x
+    return solver, out, (A_val, b, alpha)
+
+
+@pytest.mark.parametrize("B,num_cols,psr,fill", [(1, 30, (2, 6), 0.05), (32, 30, (2, 6), 0.05), (128, 70, (1, 13), 0.02), (33, 70, (2, 6), 0.05)])
+@pytest.mark.parametrize("ordering", ["mindeg", "natural", "nd"])
+def test_random_block_sparse_systems_front(B, num_cols, psr, fill, ordering):
+    rng = np.random.default_rng(B + num_cols)
+    S = _random_structure(rng, num_cols, psr, fill, num_rows_blocks=3 * num_cols)
+    _check(S, B, B + num_cols, ordering=ordering)
+
+
+def test_small_front_classes_on_a_grid():
+    """14 x 14 grid of 6-dof blocks: fronts of every shared-memory size class (r <= 48, 96, 160), several depths."""
+    solver, _, _ = _check(_grid_structure(14, 14), 37, 5)
+    cls = solver._plan.arrays["f_class"]
+    assert (cls == 0).any() and (cls == 1).any() and solver._plan.stats["depth"] >= 4
+
+
+@pytest.mark.parametrize("small_limit", [40, 100])
+def test_big_fronts_go_through_the_partial_dense_kernel(small_limit):
+    """small_limit forces fronts above it onto the big path: assembled into padded dense matrices, factored by chol_col_kernel in partial
+    mode (pivot block columns factored, the trailing block becomes the Schur complement in place), panels extracted; children of big fronts
+    are both small and big fronts, and small parents read big children's update matrices through (offset, leading dimension)."""
+    S = _grid_structure(12, 12)
+    solver, x_big, (A_val, b, alpha) = _check(S, 19, 11, front_options=dict(small_limit=small_limit))
+    assert (solver._plan.arrays["f_class"] == 3).sum() >= 2
+    ref = th.BaspachoSparseSolver.from_structure(S, layout="front")
+    ref.linearization.A_val, ref.linearization.b = A_val, b
+    x_small = ref.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-6)
+    assert (ref._plan.arrays["f_class"] < 3).all()
+    assert (x_big - x_small).abs().max() <= 1e-9 * x_small.abs().max()
+
+
+def test_front_equals_lane_and_is_independent_of_the_batch_size():
+    S = _grid_structure(9, 9)
+    rng = np.random.default_rng(2)
+    B = 40
+    A_val = torch.from_numpy(rng.standard_normal((B, S.nnz))).cuda()
+    b = torch.from_numpy(rng.standard_normal((B, S.num_rows))).cuda()
+    alpha = torch.from_numpy(rng.random(B) * 0.1).cuda()
+    xs = {}
+    for layout in ("front", "lane"):
+        s = th.BaspachoSparseSolver.from_structure(S, layout=layout)
+        s.linearization.A_val, s.linearization.b = A_val, b
+        xs[layout] = s.solve(damping=alpha, ellipsoidal_damping=True, damping_eps=1e-8).clone()
+    assert (xs["front"] - xs["lane"]).abs().max() <= 1e-9 * xs["lane"].abs().max()
+    s = th.BaspachoSparseSolver.from_structure(S, layout="front")
+    s.linearization.A_val, s.linearization.b = A_val[7:8].contiguous(), b[7:8].contiguous()
+    x1 = s.solve(damping=alpha[7:8].contiguous(), ellipsoidal_damping=True, damping_eps=1e-8)
+    assert torch.equal(x1[0], xs["front"][7])       # no atomics, fixed summation order: bitwise whatever the batch size
+
+
+def test_front_not_positive_definite_is_reported():
+    S2 = build_structure([2, 2], [(2, [0, 1])])
+    solver = th.BaspachoSparseSolver.from_structure(S2, layout="front")
+    A2 = torch.ones(3, S2.nnz, dtype=torch.float64)
+    for r in range(S2.num_rows):
+        cols = S2.A_col_ind[S2.A_row_ptr[r]:S2.A_row_ptr[r + 1]]
+        A2[:, S2.A_row_ptr[r]:S2.A_row_ptr[r + 1]][:, cols >= 2] = 0.0
+    A2[:, 1] = 2.0
+    solver.linearization.A_val = A2.cuda()
+    solver.linearization.b = torch.ones(3, S2.num_rows, dtype=torch.float64).cuda()
+    with pytest.raises(RuntimeError, match=r"batch element 0: matrix is not positive definite"):
+        solver.solve()
+
+
+@pytest.mark.parametrize("name", ["pgo_small_lm", "pgo64_lm"])
+def test_lm_trace_with_front_layout(name):
+    g = load(name)
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
+                                max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0,
+                                linear_solver_kwargs=dict(layout="front"))
+    errs, deltas = [], []
+
+    def cb(optimizer, info, delta, it):
+        errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+    with torch.no_grad():
+        opt.optimize(end_iter_callback=cb, **kw)
+    np.testing.assert_allclose(np.stack(errs, 0), g["trace_err"], rtol=1e-8)
+    for it in range(2):
+        rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
+        assert rel.max() < 1e-5, (it, rel)
+    np.testing.assert_allclose(np.stack([p.tensor.cpu().numpy() for p in poses], 0), g["poses_final"], rtol=1e-6, atol=1e-6)
+
+
+def test_c5_full_size_lm_trace_front():
+    """Config C5's pose graph at full size (2 500 poses, n = 15 000), one batch item: 54 big fronts (up to 462 pivots) + ~1 050 small
+    ones; LM trace against the reference's dense-solver trace (tests/golden/pgo_c5_lm.npz)."""
+    g = load("pgo_c5_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g)
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
+                                max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0,
+                                linear_solver_kwargs=dict(layout="front"))
+    assert opt.linear_solver.symbolic_stats["big_fronts"] > 10
+    errs, deltas = [], []
+
+    def cb(optimizer, info, delta, it):
+        errs.append(info.last_err.cpu().numpy().copy()); deltas.append(delta.cpu().numpy().copy())
+    with torch.no_grad():
+        np.testing.assert_allclose(objective.error_metric().cpu().numpy(), g["err0"], rtol=1e-10)
+        opt.optimize(end_iter_callback=cb, **kw)
+    np.testing.assert_allclose(np.stack(errs, 0), g["trace_err"], rtol=1e-7)
+    for it in range(decisive_iterations(g["err0"], g["trace_err"])):
+        rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
+        assert rel.max() < 1e-5, (it, rel)

@@ -204,3 +204,24 @@ def test_batched_torch_route_inside_the_engine(emulated, name, monkeypatch):
     for x0, x1 in zip(outs["0"], outs["1"]):
         np.testing.assert_allclose(x1, x0, rtol=1e-12, atol=1e-13 * np.abs(x0).max())
     np.testing.assert_allclose(outs["1"][0], outs["1"][2], rtol=1e-7, atol=1e-9 * np.abs(outs["1"][2]).max())   # taped (autodiff) == fused-kernel (analytic) values
+
+
+def test_returned_solutions_are_not_overwritten_by_the_next_forward(emulated):
+    """TheseusLayer.forward hands out a snapshot of the engine-owned variable pool: a second forward (new inputs, same objective) must
+    leave the tensors returned by the first one untouched -- the reference rebinds fresh tensors (core/variable.py:42-72)."""
+    g = load("pgo_small_lm")
+    method, iters, kw = lm_kwargs_of(g)
+    objective, poses = pgo_objective(th, g, device="cpu")
+    opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.CholeskyDenseSolver, max_iterations=3, step_size=1.0)
+    layer = th.TheseusLayer(opt)
+    inputs = {p.name: p.tensor.clone() for p in poses}
+    with torch.no_grad():
+        sol1, _ = layer.forward(inputs, optimizer_kwargs=kw)
+        keep = {k: v.clone() for k, v in sol1.items()}
+        inputs2 = {k: v.clone() for k, v in inputs.items()}
+        inputs2[poses[1].name] = sol1[poses[1].name].clone()
+        sol2, _ = layer.forward(inputs2, optimizer_kwargs=kw)
+    for k in keep:
+        assert torch.equal(sol1[k], keep[k]), k
+        assert sol1[k].data_ptr() != sol2[k].data_ptr()
+    assert any(not torch.equal(sol1[k], sol2[k]) for k in keep)

@@ -299,6 +299,11 @@ struct CholArgs {
   int32_t* info;       // [B]
   int64_t B, n, np;
   int nb, ntr;
+  int* ticket;         // tile queue: a CTA's position in the dependency order is the ticket it draws when it STARTS running
+  int nb_piv;          // block columns that are factored; block columns >= nb_piv only receive the update of the pivot columns
+                       // (partial factorisation of a frontal matrix: the trailing block becomes the Schur complement)
+  int64_t a_bstride, l_bstride;  // batch strides (doubles) of AtA and L; AtA == L (in place) for frontal matrices
+  int info_base;       // added to the reported pivot index (position of the front's first pivot in the permuted vector)
 };
 
 __device__ __forceinline__ void wait_ge(const int* addr, int target) {
@@ -312,25 +317,31 @@ __device__ __forceinline__ void wait_ge(const int* addr, int target) {
 __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // CTA -> (block column j, row tile i, matrix b).  CTAs are ordered by column, the diagonal tile of a column first,
-  // the matrix index fastest: every CTA only ever waits on CTAs with a smaller block index (in-order dispatch).
+  // Tile queue: the CTA draws a ticket when it starts RUNNING; ticket -> (block column j, row tile i, matrix b), ordered by
+  // column, the diagonal tile of a column first, the matrix index fastest.  A CTA only ever waits on tiles with a smaller
+  // ticket, and every smaller ticket was drawn by a CTA that is already running (or done): no deadlock whatever order the
+  // hardware dispatches blocks in (no reliance on in-order dispatch, MPS / preemption safe).
+  __shared__ int s_ticket;
+  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+  __syncthreads();
+  const int64_t bid = s_ticket;
   int j;
   {
-    int lo = 0, hi = p.nb;  // largest j with col_start[j] <= blockIdx.x
+    int lo = 0, hi = p.nb;  // largest j with col_start[j] <= bid
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if (p.col_start[mid] <= (int64_t)blockIdx.x) lo = mid; else hi = mid;
+      if (p.col_start[mid] <= bid) lo = mid; else hi = mid;
     }
     j = lo;
   }
-  const int64_t rel = (int64_t)blockIdx.x - p.col_start[j];
+  const int64_t rel = bid - p.col_start[j];
   const int i0 = j >> 1;                     // 128-row tile that contains the diagonal block of column j
   const int64_t b = rel % p.B;
   const int i = i0 + (int)(rel / p.B);
   const bool is_diag = (i == i0);
   const int roff = (j & 1) * 64;             // row offset of the diagonal block inside its tile
   const int64_t np = p.np;
-  double* Lb = p.L + b * np * np;
+  double* Lb = p.L + b * p.l_bstride;
   const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps -> 32 x 32 warp tiles
   const int lr = lane >> 2, lc = lane & 3;
 
@@ -340,7 +351,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   // while the cp.async pipeline fills, and C = AtA - sum L L^T is simply -acc at the end (AtA is read exactly once).
   double acc[4][4][2];
   {
-    const double* Ab = p.AtA + b * p.n * p.n;
+    const double* Ab = p.AtA + b * p.a_bstride;
     const double al = (p.alpha != nullptr) ? p.alpha[b] : 0.0;
     const double be = (p.beta != nullptr) ? p.beta[b] : 0.0;
 #pragma unroll
@@ -364,16 +375,17 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
     }
   }
   // dependencies: all earlier block columns of this row tile and of the row tile holding block row j are finished
-  if (j > 0) {
+  const int jdep = j < p.nb_piv ? j : p.nb_piv;   // pivot block columns this tile depends on
+  if (jdep > 0) {
     if (tid == 0) {
-      wait_ge(p.done + b * p.ntr + i, j);
-      if (i != i0) wait_ge(p.done + b * p.ntr + i0, j);
+      wait_ge(p.done + b * p.ntr + i, jdep);
+      if (i != i0) wait_ge(p.done + b * p.ntr + i0, jdep);
     }
     __syncthreads();
   }
 
   THB_TICK(1);
-  const int nk = j * (TN / KB);
+  const int nk = jdep * (TN / KB);
   const bool skip_mma = is_diag && (wm * 32 < roff);  // odd block columns: the upper 64 rows of the diagonal tile lie above the diagonal
   const double* Arow = Lb + (int64_t)i * TM * np;
   const double* Brow = Lb + (int64_t)j * TN * np;
@@ -419,6 +431,16 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   }
 
   THB_TICK(2);
+  if (j >= p.nb_piv) {
+    // trailing block column of a partial factorisation: the tile of the Schur complement  S = F - L L^T  goes back in place
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+      double* dst = Lb + ((int64_t)i * TM + wm * 32 + mi * 8 + lr) * np + (int64_t)j * TN + wn * 32 + lc * 2;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) *reinterpret_cast<double2*>(dst + ni * 8) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+    }
+    return;
+  }
   // ---------------- phase B: C = -acc, to shared memory ----------------
   double* Cs = smem;
 #pragma unroll
@@ -440,7 +462,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   if (is_diag) {
     // ---------------- phase C: blocked potrf + triangular inverse of the 64x64 diagonal block ----------------
     const int fail = diag64_factor_invert(Cs + roff * SC, smem + TM * SC, Lb + ((int64_t)j * TN) * np + (int64_t)j * TN, np, Wj);
-    if (tid == 0 && fail != 0) atomicCAS(p.info + b, 0, j * TN + fail);
+    if (tid == 0 && fail != 0) atomicCAS(p.info + b, 0, p.info_base + j * TN + fail);
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -644,6 +666,7 @@ struct Geometry {
   double* W;
   int* flags;
   int* done;
+  int* ticket;
   int64_t* col_start;
 };
 static inline Geometry geometry(void* workspace, int64_t B, int64_t n) {
@@ -655,7 +678,8 @@ static inline Geometry geometry(void* workspace, int64_t B, int64_t n) {
   g.ntr = (int)(g.np / TM);
   g.flags = reinterpret_cast<int*>(g.W + B * g.nb * TN * TN);
   g.done = g.flags + align_up(B * g.nb, 64);
-  g.col_start = reinterpret_cast<int64_t*>(g.done + align_up(B * g.ntr, 64));
+  g.ticket = g.done + align_up(B * g.ntr, 64);
+  g.col_start = reinterpret_cast<int64_t*>(g.ticket + 64);
   return g;
 }
 
@@ -680,6 +704,7 @@ int64_t thb_potrf_workspace_bytes(int64_t B, int64_t n) {
   bytes += B * nb * thb::TN * thb::TN * 8;                      // W
   bytes += thb::align_up(B * nb, 64) * 4;                       // flags (W_j ready)
   bytes += thb::align_up(B * (np / thb::TM), 64) * 4;           // finished-column counters per row tile
+  bytes += 64 * 4;                                              // tile-queue ticket counter
   bytes += (nb + 1) * 8;                                        // first CTA index of every block column
   return thb::align_up(bytes, 256);
 }
@@ -691,7 +716,7 @@ int thb_potrf_f64(const double* AtA, const double* alpha, const double* beta, in
   if (workspace_bytes < thb_potrf_workspace_bytes(B, n)) return THB_ERR_BAD_ARG;
   cudaStream_t cs = thb_cs(stream);
   thb::Geometry g = thb::geometry(workspace, B, n);
-  THB_CUDA(cudaMemsetAsync(g.flags, 0, (size_t)(thb::align_up(B * g.nb, 64) + thb::align_up(B * g.ntr, 64)) * 4, cs));
+  THB_CUDA(cudaMemsetAsync(g.flags, 0, (size_t)(thb::align_up(B * g.nb, 64) + thb::align_up(B * g.ntr, 64) + 64) * 4, cs));  // flags, done, ticket
   THB_CUDA(cudaMemsetAsync(info, 0, (size_t)B * 4, cs));
   // CTA index table (host-computed, tiny): column j owns (ntr - j/2) * B CTAs
   int64_t starts[1026];
@@ -710,6 +735,7 @@ int thb_potrf_f64(const double* AtA, const double* alpha, const double* beta, in
   a.AtA = AtA; a.alpha = alpha; a.beta = beta; a.L = g.L; a.W = g.W; a.flags = g.flags; a.done = g.done;
   a.col_start = g.col_start; a.info = info;
   a.B = B; a.n = n; a.np = g.np; a.nb = g.nb; a.ntr = g.ntr;
+  a.ticket = g.ticket; a.nb_piv = g.nb; a.a_bstride = n * n; a.l_bstride = g.np * g.np; a.info_base = 0;
   // ONE launch for the whole factorisation: block columns are chained through the per-tile counters, so there are
   // no per-column launch gaps and no per-column wave-quantisation tails.
   thb::chol_col_kernel<<<(unsigned)starts[g.nb], thb::CHOL_THREADS, thb::CHOL_SMEM, cs>>>(a);
@@ -732,6 +758,51 @@ int thb_potrs_f64(const double* rhs, double* x, int64_t B, int64_t n, const void
     solve_smem_set = ssm;
   }
   thb::chol_solve_kernel<<<(unsigned)B, thb::SOLVE_THREADS, ssm, thb_cs(stream)>>>(s);
+  THB_CHECK_LAUNCH();
+  return THB_OK;
+}
+
+/* Partial in-place factorisation of B frontal matrices (multifrontal block-sparse Cholesky, thb_front.cu): F_b = F + b * bstride is an
+ * np x np row-major matrix (np a multiple of 128; lower part + diagonal tiles read).  The first nb_piv 64-wide block columns are
+ * factored (L in place, zeros above the diagonal of the diagonal blocks), the trailing (np - 64 nb_piv)^2 block becomes the Schur
+ * complement F22 - L21 L21^T in place.  info[b] (NOT cleared here) receives info_base + 1 + index of the first non-positive pivot. */
+int64_t thb_potrf_partial_workspace_bytes(int64_t B, int64_t np) {
+  if (B <= 0 || np <= 0) return 0;
+  const int64_t nb = np / thb::TN;
+  int64_t bytes = B * nb * thb::TN * thb::TN * 8;               // W
+  bytes += thb::align_up(B * nb, 64) * 4 + thb::align_up(B * (np / thb::TM), 64) * 4 + 64 * 4 + (nb + 1) * 8;
+  return thb::align_up(bytes, 256);
+}
+
+int thb_potrf_partial_inplace_f64(double* F, int64_t bstride, int64_t np, int32_t nb_piv, int32_t info_base, int32_t* info, int64_t B,
+                                  void* workspace, int64_t workspace_bytes, thb_stream_t stream) {
+  if (B < 0 || np <= 0 || np % thb::TM != 0 || F == nullptr || info == nullptr || workspace == nullptr) return THB_ERR_BAD_ARG;
+  if (B == 0) return THB_OK;
+  if (workspace_bytes < thb_potrf_partial_workspace_bytes(B, np)) return THB_ERR_BAD_ARG;
+  const int nb = (int)(np / thb::TN), ntr = (int)(np / thb::TM);
+  if (nb_piv < 0 || nb_piv > nb || nb > 1024) return THB_ERR_BAD_ARG;
+  cudaStream_t cs = thb_cs(stream);
+  double* W = reinterpret_cast<double*>(workspace);
+  int* flags = reinterpret_cast<int*>(W + B * nb * thb::TN * thb::TN);
+  int* done = flags + thb::align_up(B * nb, 64);
+  int* ticket = done + thb::align_up(B * ntr, 64);
+  int64_t* col_start = reinterpret_cast<int64_t*>(ticket + 64);
+  THB_CUDA(cudaMemsetAsync(flags, 0, (size_t)(thb::align_up(B * nb, 64) + thb::align_up(B * ntr, 64) + 64) * 4, cs));
+  int64_t total = 0;
+  for (int j = 0; j < nb; j++) total += (int64_t)(ntr - (j >> 1)) * B;
+  if (total > 2147483647LL) return THB_ERR_UNSUPPORTED;
+  thb::chol_col_start_kernel<<<(unsigned)((nb + 1 + 255) / 256), 256, 0, cs>>>(col_start, nb, ntr, B);
+  THB_CHECK_LAUNCH();
+  static bool attr_set = false;
+  if (!attr_set) {
+    THB_CUDA(cudaFuncSetAttribute(thb::chol_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thb::CHOL_SMEM));
+    attr_set = true;
+  }
+  thb::CholArgs a;
+  a.AtA = F; a.alpha = nullptr; a.beta = nullptr; a.L = F; a.W = W; a.flags = flags; a.done = done; a.col_start = col_start; a.info = info;
+  a.B = B; a.n = np; a.np = np; a.nb = nb; a.ntr = ntr;
+  a.ticket = ticket; a.nb_piv = nb_piv; a.a_bstride = bstride; a.l_bstride = bstride; a.info_base = info_base;
+  thb::chol_col_kernel<<<(unsigned)total, thb::CHOL_THREADS, thb::CHOL_SMEM, cs>>>(a);
   THB_CHECK_LAUNCH();
   return THB_OK;
 }

@@ -41,3 +41,13 @@ def global_mean_abs_error(err_local: torch.Tensor, group=None) -> Tuple[float, i
     t = torch.stack([err_local.abs().sum().double(), torch.tensor(float(err_local.numel()), dtype=torch.float64, device=err_local.device)])
     reduce_counts(t, group)
     return float(t[0] / t[1]), int(t[1])
+
+
+def any_rank_true(flag_local: bool, group=None, device: Optional[torch.device] = None) -> bool:
+    """True iff `flag_local` is True on ANY rank (every rank must call it): exit decisions of the sharded loop -- a failed linear
+    solve on one rank ends the loop on all of them, so the per-iteration collectives stay matched."""
+    if group is None:
+        return bool(flag_local)
+    t = torch.tensor([1 if flag_local else 0], dtype=torch.int64, device=device)
+    reduce_counts(t, group)
+    return int(t[0]) > 0

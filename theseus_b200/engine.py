@@ -149,6 +149,7 @@ class Engine:
         total = int(offs[-1])
         self._pool_cur = torch.empty(total, dtype=self.dtype, device=self.device)
         self._pool_tmp = torch.empty(total, dtype=self.dtype, device=self.device)
+        self._view_offs, self._view_lens = offs, lens
         self.cur_views, self.tmp_views = [], []
         for i, v in enumerate(self.ordering):
             shp = (B,) + tuple(v.tensor.shape[1:])
@@ -177,6 +178,21 @@ class Engine:
             for v, view in zip(self.ordering, self.cur_views):
                 if v.tensor.data_ptr() != view.data_ptr():
                     v.tensor = view
+
+    def solution_tensors(self):
+        """name -> tensor of every optimisation variable, safe to hand to the caller: variables that live in the engine-owned pool (which
+        the next optimize() overwrites in place) are returned as views of ONE clone of the pool -- the reference rebinds fresh tensors
+        (Variable.update / torch.where, core/variable.py:42-72), so solutions it returned earlier never change."""
+        out, snap = {}, None
+        for i, v in enumerate(self.ordering):
+            t = v.tensor
+            if self._pool_cur is not None and i < len(getattr(self, "cur_views", ())) and t.data_ptr() == self.cur_views[i].data_ptr() and not t.requires_grad:
+                if snap is None:
+                    snap = self._pool_cur.clone()
+                o = int(self._view_offs[i])
+                t = snap[o:o + self._view_lens[i]].view(self.cur_views[i].shape)
+            out[v.name] = t
+        return out
 
     def _ptr_array(self, tensors) -> torch.Tensor:
         return _dev(np.fromiter((t.data_ptr() for t in tensors), dtype=np.int64, count=len(tensors)), self.device)

@@ -159,6 +159,19 @@ def _flops_of(struct, dims):
     return fl
 
 
+SMALL_SMEM_LIMIT = 220 * 1024
+
+
+def _pad_ld(x: int) -> int:
+    return ((x + 11) // 16) * 16 + 4
+
+
+def small_smem_bytes(w: int, b: int) -> int:
+    """Dynamic shared memory of front_small_kernel for a front (thb_front.cu / thb_front_small_smem_bytes)."""
+    b16, w4 = (b + 15) & ~15, (w + 3) & ~3
+    return ((w + b16) * _pad_ld(w4) + b16 * _pad_ld(b16)) * 8
+
+
 def _front_cost(w, b):
     return w ** 3 / 3.0 + w * w * b + w * b * b
 
@@ -177,7 +190,7 @@ class FrontPlan:
     perm: np.ndarray           # [n] perm[p] = original scalar column of permuted scalar p
     S: int
     arrays: Dict[str, np.ndarray]   # flat per-front arrays consumed by the kernels (see build_front_plan)
-    launches: np.ndarray       # [num_launches, 4] (depth, class, start, count) over arrays["sched"]; depth descending
+    launches: np.ndarray       # [num_launches, 10] int64, thb200.h THB_FRONT_LAUNCH_COLS; depth descending
     data_size: int             # doubles of one item's factor storage (sum of panels)
     arena_size: int            # doubles of one item's update-matrix arena (one parity)
     varena_size: int           # doubles of one item's border-vector arena (one parity)
@@ -256,18 +269,22 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
         if par[s] >= 0:
             kids[par[s]].append(s)
     alive = np.ones(S0, dtype=bool)
-    # ---- relaxed amalgamation, bottom-up (supernode indices are a topological order) ----
+    base = [_front_cost(wsz[s], bsz[s]) for s in range(S0)]   # flops of the fundamental supernodes merged into s so far
+    # ---- relaxed amalgamation, bottom-up (supernode indices are a topological order): a child joins its parent while the dense
+    # flops of the merged front stay within (1 + tau) of what its fundamental supernodes cost, or -- small fronts only -- within a
+    # fixed allowance (a front costs a CTA, a trip through the update-matrix arena and a slot in every level's launch) ----
     for p in range(S0):
         changed = True
         while changed and kids[p]:
             changed = False
             for c in sorted(kids[p], key=lambda c: (wsz[c] + bsz[c], c)):
-                sep = _front_cost(wsz[c], bsz[c]) + _front_cost(wsz[p], bsz[p])
+                sep = base[c] + base[p]
                 mer = _front_cost(wsz[c] + wsz[p], bsz[p])
                 r_m = wsz[c] + wsz[p] + bsz[p]
                 if mer <= (1.0 + tau) * sep or (mer <= sep + merge_flops and r_m <= merge_max_r):
                     cols[p] = cols[c] + cols[p]
                     wsz[p] += wsz[c]
+                    base[p] = sep
                     alive[c] = False
                     kids[p].remove(c)
                     for g in kids[c]:
@@ -333,7 +350,8 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     f_class = np.zeros(S, dtype=np.int32)
     for t in range(S):
         r = int(f_r[t])
-        f_class[t] = 3 if r > small_limit else int(np.searchsorted(np.array(SMALL_CLASSES), r))
+        f_class[t] = 3 if (r > small_limit or small_smem_bytes(int(f_w[t]), int(f_b[t])) > SMALL_SMEM_LIMIT) else int(
+            np.searchsorted(np.array(SMALL_CLASSES), r))
     # ---- storage: panels, update-matrix arena (by depth parity), border-vector arena ----
     f_panel_off = np.zeros(S, dtype=np.int64)
     off = 0
@@ -388,8 +406,12 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
             g = border_rows[t]
             inp = g < f_first[p] + f_w[p]
             loc = np.where(inp, g - f_first[p], f_w[p] + np.searchsorted(border_rows[p], g))
-            chk = np.where(inp, True, border_rows[p][np.minimum(loc - f_w[p], max(len(border_rows[p]) - 1, 0))] == g) if len(border_rows[p]) else inp
-            assert bool(np.all(chk)) and bool(np.all(g >= f_first[p]))
+            if len(border_rows[p]):
+                kk = np.clip(loc - f_w[p], 0, len(border_rows[p]) - 1)
+                assert bool(np.all(inp | (border_rows[p][kk] == g)))
+            else:
+                assert bool(np.all(inp))
+            assert bool(np.all(g >= f_first[p]))
             rel_list.append(loc.astype(np.int32))
             racc += len(loc)
         rel_ptr[t + 1] = racc
@@ -408,9 +430,12 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
         if c != 3:
             while j < S and int(f_depth[sched[j]]) == d and int(f_class[sched[j]]) == c:
                 j += 1
-        launches.append((d, c, i, j - i))
+            smem = max(small_smem_bytes(int(f_w[q]), int(f_b[q])) for q in sched[i:j])
+            launches.append((d, c, i, j - i, smem, 0, 0, 0, 0, 0))
+        else:   # one front: (.., np, pivot block columns, offset of F in the arena, first pivot [info base], front index)
+            launches.append((d, c, i, 1, 0, int(f_np[t]), int(f_wpad[t]) // BIG_TW, int(f_fr_off[t]), int(f_first[t]), t))
         i = j
-    launches = np.array(launches, dtype=np.int32).reshape(-1, 4)
+    launches = np.array(launches, dtype=np.int64).reshape(-1, 10)
     flops = float(sum(_front_cost(float(f_w[t]), float(f_b[t])) for t in range(S)))
     stats = dict(ordering=oname, column_flops=col_flops, flops=flops, nnz_L=float(sum(int(f_r[t]) * int(f_w[t]) for t in range(S))),
                  fronts=float(S), max_front=float(f_r.max()) if S else 0.0, depth=float(max_depth + 1), big_fronts=float((f_class == 3).sum()),
@@ -440,7 +465,7 @@ def execute_numpy(plan: FrontPlan, panels: np.ndarray, rhs: np.ndarray):
 
     def kids(t):
         return A["child_list"][A["child_ptr"][t]:A["child_ptr"][t + 1]]
-    for (d, cls, s0, cnt) in plan.launches:
+    for (d, cls, s0, cnt) in plan.launches[:, :4]:
         for t in A["sched"][s0:s0 + cnt]:
             wt, bt = int(w[t]), int(b[t])
             r = wt + bt
@@ -460,7 +485,7 @@ def execute_numpy(plan: FrontPlan, panels: np.ndarray, rhs: np.ndarray):
             P[poff[t]:poff[t] + r * wt] = F[:, :wt].reshape(-1)
     y = rhs[plan.perm].astype(np.float64).copy()
     ub: Dict[int, np.ndarray] = {}
-    for (d, cls, s0, cnt) in plan.launches:          # forward, deepest first
+    for (d, cls, s0, cnt) in plan.launches[:, :4]:   # forward, deepest first
         for t in A["sched"][s0:s0 + cnt]:
             wt, bt = int(w[t]), int(b[t])
             r = wt + bt
@@ -474,7 +499,7 @@ def execute_numpy(plan: FrontPlan, panels: np.ndarray, rhs: np.ndarray):
             if bt:
                 ub[int(t)] = u[wt:] - Lp[wt:] @ yt
     x = y
-    for (d, cls, s0, cnt) in plan.launches[::-1]:    # backward, root first
+    for (d, cls, s0, cnt) in plan.launches[::-1, :4]:    # backward, root first
         for t in A["sched"][s0:s0 + cnt]:
             wt, bt = int(w[t]), int(b[t])
             r = wt + bt

@@ -20,7 +20,9 @@ class TheseusLayer(torch.nn.Module):
         optimizer_kwargs = optimizer_kwargs or {}
         self.objective.update(input_tensors)  # theseus_layer.py:170
         info = self.optimizer.optimize(**optimizer_kwargs)  # theseus_layer.py:171-173
-        values = dict((var.name, var.tensor) for var in self.objective.optim_vars.values())
+        # the optimisation variables live in an engine-owned pool that the next forward() overwrites in place: hand out a snapshot
+        sol = self.objective.engine().solution_tensors()
+        values = dict((var.name, sol.get(var.name, var.tensor)) for var in self.objective.optim_vars.values())
         return values, info
 
     def to(self, *args, **kwargs):

@@ -579,9 +579,16 @@ class NonlinearLeastSquares:
         lin = self.linear_solver.linearization
         while it_ < num_iter:
             lin.linearize()
+            run_err = None
             try:
                 delta = self.compute_delta(**kwargs)
-            except RuntimeError as run_err:
+            except RuntimeError as e:
+                run_err = e
+            if self.process_group is not None:   # a failed solve on ANY rank ends the loop on every rank (collectives stay matched)
+                from .distributed import any_rank_true
+                if any_rank_true(run_err is not None, self.process_group, self.objective.device) and run_err is None:
+                    run_err = RuntimeError("the linear solve failed on another rank of the process group")
+            if run_err is not None:
                 msg = f"There was an error while running the linear optimizer. Original error message: {run_err}."
                 if torch.is_grad_enabled() or getattr(self, "_grad_mode_at_entry", False):
                     raise RuntimeError(msg + " Backward pass will not work. To obtain the best solution seen before the error, run with torch.no_grad()")
@@ -678,9 +685,16 @@ class NonlinearLeastSquares:
             all_rejected = False
             if stats is not None:
                 all_rejected = self._read_stats(stats, B)
+            run_err = None
             try:
                 solver.check_info()
-            except RuntimeError as run_err:
+            except RuntimeError as e:
+                run_err = e
+            if self.process_group is not None:
+                from .distributed import any_rank_true
+                if any_rank_true(run_err is not None, self.process_group, self.objective.device) and run_err is None:
+                    run_err = RuntimeError("the linear solve failed on another rank of the process group")
+            if run_err is not None:
                 msg = f"There was an error while running the linear optimizer. Original error message: {run_err}."
                 if getattr(self, "_grad_mode_at_entry", False):
                     raise RuntimeError(msg + " Backward pass will not work. To obtain the best solution seen before the error, run with torch.no_grad()")
@@ -741,6 +755,10 @@ class NonlinearLeastSquares:
         from .core import CostFunction
         if backward_mode == BackwardMode.DLM:
             raise NotImplementedError("BackwardMode.DLM is not built (SURVEY.md 8: out of scope)")
+        if self.process_group is not None:
+            # the taped loop takes local exits (all-converged / all-rejected decided per rank): refused rather than risking unmatched
+            # collectives; shard the batch OUTSIDE the layer for training (each rank its own objective), or run under no_grad
+            raise NotImplementedError("process_group is supported by the no-grad LM / GN loop only, not by the backward modes")
         def has_torch(cf):
             inner = getattr(cf, "cost_function", cf)
             return type(inner)._torch_error is not CostFunction._torch_error
@@ -1015,6 +1033,8 @@ class TrustRegion(NonlinearLeastSquares):
 
     def __init__(self, objective: Objective, *args, **kwargs):
         super().__init__(objective, *args, **kwargs)
+        if self.process_group is not None:   # its all-rejected decision is local (reject.all()): ranks could take different exits
+            raise NotImplementedError("process_group is supported by GaussNewton / LevenbergMarquardt only, not by the trust-region optimizers")
         self._trust_region: torch.Tensor = None
 
     def reset(self, trust_region_init: float = 0.5, **kwargs) -> None:

@@ -16,6 +16,7 @@ from . import _lib
 from .autograd import LinearSolveFunction, wants_grad
 from .core import Objective
 from .optimizer import (Linearization, LinearSolver, SparseLinearization, convert_to_alpha_beta_damping_tensors)
+from .frontal import build_front_plan
 from .sparse import LANE_DIMS, analyze, gram_out_offsets, piece_solve_lists, root_lane_lists, root_split, tile_lane_lists
 from .structure import ata_block_structure, build_gram_plan
 
@@ -28,7 +29,7 @@ class BaspachoSparseSolver(LinearSolver):
     def __init__(self, objective: Objective, linearization_cls: Optional[Type[Linearization]] = None,
                  linearization_kwargs: Optional[Dict[str, Any]] = None, num_solver_contexts=1, batch_size: Optional[int] = None,
                  auto_reset: bool = True, dev: Optional[str] = None, ordering: str = "mindeg", layout: Optional[str] = None,
-                 supernodal_solve: bool = False, **kwargs):
+                 supernodal_solve: bool = False, front_options: Optional[Dict[str, Any]] = None, **kwargs):
         linearization_cls = linearization_cls or SparseLinearization
         if not linearization_cls == SparseLinearization:
             raise RuntimeError(
@@ -39,13 +40,14 @@ class BaspachoSparseSolver(LinearSolver):
         self._ordering = ordering
         self._layout = layout
         self._supernodal_solve = bool(supernodal_solve)   # opt-in: chain-piece substitution kernels (lane layouts only; not yet run on a GPU)
+        self._front_options = dict(front_options or {})   # layout="front": frontal.build_front_plan keywords (tau, small_limit, ...)
         self._plan = None
         self._dev = None
         self.reset()
 
     @classmethod
     def from_structure(cls, structure, ordering: str = "mindeg", layout: Optional[str] = None,
-                       supernodal_solve: bool = False) -> "BaspachoSparseSolver":
+                       supernodal_solve: bool = False, front_options: Optional[Dict[str, Any]] = None) -> "BaspachoSparseSolver":
         """Solver over a bare CSR structure with hand-filled `linearization.A_val / b` -- the pattern of the reference's own
         solver tests (void Objective + filled linearization, tests/theseus_tests/optimizer/linear/test_baspacho_sparse_solver.py:15-41)."""
         class _Lin:
@@ -60,6 +62,7 @@ class BaspachoSparseSolver(LinearSolver):
         self.linearization = _Lin(structure)
         self._ordering, self._plan, self._dev, self._layout = ordering, None, None, layout
         self._supernodal_solve = bool(supernodal_solve)
+        self._front_options = dict(front_options or {})
         self.reset()
         return self
 
@@ -70,12 +73,20 @@ class BaspachoSparseSolver(LinearSolver):
         S = self.linearization.structure()
         param_size, ptrs, inds = ata_block_structure(S)
         self.param_size, self.block_ptrs, self.block_inds = param_size, ptrs, inds  # the reference's SymbolicDecomposition inputs
+        if self._layout == "front":
+            # multifrontal layout: own ordering (nested dissection / minimum degree, whichever costs fewer flops) and fronts
+            self._plan = build_front_plan(param_size, ptrs, inds, ordering="auto" if self._ordering == "mindeg" else self._ordering,
+                                          **getattr(self, "_front_options", {}))
+            self._gram_arrays = build_gram_plan(S, out_offsets=self._plan.gram_out_offsets(), pos=self._plan.pos)
+            return
         self._plan = analyze(param_size, ptrs, inds, ordering=self._ordering)
         self._gram_arrays = build_gram_plan(S, out_offsets=gram_out_offsets(self._plan), pos=self._plan.pos)
 
     def layout_for(self, B: int) -> str:
         """'lane' (batch-interleaved factor, one warp = 32 batch items, thb_sparse_lane.cu) or 'item' (one CTA per batch item,
         thb_sparse.cu).  Default: lane whenever a warp can be filled and every block size is one the lane kernels are built for."""
+        if self._layout == "front":
+            return "front"
         lane_ok = all(int(d) in LANE_DIMS for d in self._plan.dims)
         if self._layout is not None:
             if self._layout not in ("lane", "item", "lane_root", "lane_tiled", "lane_tiled_root"):
@@ -99,9 +110,15 @@ class BaspachoSparseSolver(LinearSolver):
     def symbolic_stats(self):
         return dict(self._plan.stats)
 
+    @property
+    def effective_layout(self):
+        return self._layout
+
     def _device_plan(self, device):
         if self._dev is not None and self._dev["device"] == device:
             return self._dev
+        if self._layout == "front":
+            return self._device_plan_front(device)
         P = self._plan
         dev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in P.arrays.items()}
         st = _lib.SparsePlanStruct(N=P.N, num_levels=int(P.stats["levels"]), max_dim=int(P.dims.max()) if P.N else 0, reserved=0,
@@ -144,6 +161,62 @@ class BaspachoSparseSolver(LinearSolver):
                                               **{k: pdev[k].data_ptr() for k in pdev})
             self._dev.update(pieces=pst, pkeep=(pdev, plaunch, ps))
         return self._dev
+
+    def _device_plan_front(self, device):
+        P = self._plan
+        dev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in P.arrays.items()}
+        st = _lib.FrontPlanStruct(S=P.S, n=P.n, data_size=P.data_size, arena_size=P.arena_size, varena_size=P.varena_size,
+                                  **{k: dev[k].data_ptr() for k in ("f_w", "f_b", "f_first", "f_class", "f_wpad", "f_np", "f_cb_ld", "f_depth",
+                                                                    "f_panel_off", "f_cb_off", "f_fr_off", "f_u_off", "child_ptr", "child_list",
+                                                                    "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm")})
+        g = self._gram_arrays
+        gdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in g.items() if isinstance(v, np.ndarray)}
+        launches = np.ascontiguousarray(P.launches, dtype=np.int64)
+        big = launches[launches[:, 1] == 3]
+        self._dev = dict(device=device, front=st, keep=dev, gram=_lib.make_gram_plan(g, gdev), gkeep=gdev, bufs={}, launches=launches,
+                         max_np=int(big[:, 5].max()) if len(big) else 0)
+        return self._dev
+
+    def _numeric_front(self, A_val, b, alpha, beta):
+        B, device = A_val.shape[0], A_val.device
+        d = self._device_plan(device)
+        P = self._plan
+        lib = _lib.load()
+        s = _lib.stream_ptr()
+        if d["bufs"].get("key") != (B, "front"):
+            ws_bytes = int(lib.thb_potrf_partial_workspace_bytes(B, d["max_np"])) if d["max_np"] else 0
+            d["bufs"] = dict(key=(B, "front"), factor=torch.empty(B, P.data_size, dtype=torch.float64, device=device),
+                             arena=torch.empty(2, B, P.arena_size, dtype=torch.float64, device=device),
+                             varena=torch.empty(2, B, P.varena_size, dtype=torch.float64, device=device),
+                             work=torch.empty(B, P.n, dtype=torch.float64, device=device),
+                             ws=torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=device),
+                             Atb=torch.empty(B, P.n, dtype=torch.float64, device=device),
+                             info=torch.empty(B, dtype=torch.int32, device=device))
+        bufs = d["bufs"]
+        factor, Atb, info = bufs["factor"], bufs["Atb"], bufs["info"]
+        nnz, m = A_val.shape[1], b.shape[1]
+        self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
+        _lib.check(lib.thb_fill_zero(_lib.ptr(factor), factor.numel() * 8, s), "fill_zero")   # fill-in entries of the panels start at zero
+        _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(factor), P.data_size,
+                                    _lib.ptr(Atb), None, s), "gram(front)")
+        L = d["launches"]
+        _lib.check(lib.thb_front_factor_f64(C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta),
+                                            _lib.ptr(bufs["arena"]), _lib.ptr(bufs["ws"]) if d["max_np"] else None, bufs["ws"].numel(),
+                                            _lib.ptr(info), B, s), "front_factor")
+        self._keep = (A_val, b, alpha, beta)
+        return Atb
+
+    def _substitute_front(self, rhs):
+        d, P = self._dev, self._plan
+        bufs = d["bufs"]
+        B = bufs["key"][0]
+        lib = _lib.load()
+        rhs = rhs.contiguous()
+        x = torch.empty(B, P.n, dtype=torch.float64, device=rhs.device)
+        L = d["launches"]
+        _lib.check(lib.thb_front_solve_f64(C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(bufs["factor"]), _lib.ptr(rhs), _lib.ptr(x),
+                                           _lib.ptr(bufs["work"]), _lib.ptr(bufs["varena"]), B, _lib.stream_ptr()), "front_solve")
+        return x
 
     def _lane_struct(self, ln, dev, device):
         """thb_sparse_lane_plan over the plan's batch-independent device arrays `dev` + the work lists `ln` (uploaded here).
@@ -212,6 +285,8 @@ class BaspachoSparseSolver(LinearSolver):
         """add_MtM -> damp -> factor (+ Atb) on fp64 inputs; leaves the factor in the solver's buffers."""
         B, device = A_val.shape[0], A_val.device
         layout = self.layout_for(B)     # validates an explicit layout (e.g. no dense root for 'lane_root') before anything is built
+        if layout == "front":
+            return self._numeric_front(A_val, b, alpha, beta)
         d = self._device_plan(device)
         P = self._plan
         lib = _lib.load()
@@ -269,6 +344,8 @@ class BaspachoSparseSolver(LinearSolver):
         d, P = self._dev, self._plan
         bufs = d["bufs"]
         B, layout = bufs["key"]
+        if layout == "front":
+            return self._substitute_front(rhs)
         lib = _lib.load()
         rhs = rhs.contiguous()
         x = torch.empty(B, P.n, dtype=torch.float64, device=rhs.device)
