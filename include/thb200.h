@@ -419,8 +419,8 @@ int thb_lm_control_f32(const float* delta, const float* Atb, const float* diag, 
  *     (thb_potrf_partial_inplace_f64); its trailing block IS the update matrix (f_cb_off / f_cb_ld point into it).
  *   child -> parent maps: f_rel[rel_ptr[c] .. rel_ptr[c+1]) = local row index in the parent front of child c's border rows.
  * `launches` is a HOST array [num_launches][10] (int64) in factorisation order (deepest fronts first):
- *   (depth, class, begin, count [into sched], dynamic smem bytes of the factor kernel, np, pivot block columns, f_fr_off,
- *    f_first [info base], front index) -- the last five for class-3 launches (one front each).
+ *   (depth, class, begin, count [into sched], dynamic smem bytes of the factor kernel, largest front of the launch [np for class 3],
+ *    pivot block columns, f_fr_off, f_first [info base], front index) -- the last four for class-3 launches (one front each).
  * No atomics on data: results are bitwise reproducible and independent of the batch size.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct thb_front_plan {

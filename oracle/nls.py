@@ -373,6 +373,47 @@ def dense_solve(AtA, Atb, damping=None, ellipsoidal=True, eps=1e-8):
 
 
 # ----------------------------------------------------------------------------- retract / error
+def _sparse_solve_item(args):
+    row_ptr, col_ind, shape, a_val, b_i, alpha, beta = args
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import splu
+    A = sp.csr_matrix((a_val, col_ind, row_ptr), shape=shape)
+    At = A.T.tocsr()
+    AtA = (At @ A).tocsc()
+    d = AtA.diagonal()
+    AtA.setdiag(d * (1.0 + alpha) + beta)
+    Atb = At @ b_i
+    x = splu(AtA, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0).solve(Atb)
+    return x, Atb, d
+
+
+def sparse_solve(struct, A_val, b, damping=None, ellipsoidal=True, eps=1e-8, n_jobs=1):
+    """BaspachoSolveFunction.forward (optimizer/autograd/baspacho_sparse_autograd.py:21-65: AtA = add_MtM, damp(alpha, beta), factor,
+    Atb = tmat_vec, solve) and CholmodSolveFunction.forward (optimizer/autograd/cholmod_sparse_autograd.py:25-61: a Python loop over
+    the batch, one sparse factorisation per item) on the CPU.  (alpha, beta) as linear/utils.py:14-33: ellipsoidal -> (damping, eps),
+    else (0, damping).  SuperLU (scipy) stands in for CHOLMOD / BaSpaCho, neither of which is importable here.
+    Returns (x [B,n], Atb [B,n], diag(AtA) [B,n]).  n_jobs > 1: items over a joblib process pool (the reference's loop is serial)."""
+    B = A_val.shape[0]
+    n = struct["num_cols"]
+    if damping is None:
+        alpha, beta = np.zeros(B), np.zeros(B)
+    else:
+        dv = np.broadcast_to(np.asarray(damping, dtype=np.float64), (B,))
+        alpha, beta = (dv, np.full(B, eps)) if ellipsoidal else (np.zeros(B), dv)
+    shape = (struct["num_rows"], n)
+    jobs = [(struct["A_row_ptr"], struct["A_col_ind"], shape, np.asarray(A_val[i], dtype=np.float64), np.asarray(b[i], dtype=np.float64),
+             float(alpha[i]), float(beta[i])) for i in range(B)]
+    if n_jobs > 1 and B > 1:
+        from joblib import Parallel, delayed
+        res = Parallel(n_jobs=min(n_jobs, B))(delayed(_sparse_solve_item)(j) for j in jobs)
+    else:
+        res = [_sparse_solve_item(j) for j in jobs]
+    x = np.stack([r[0] for r in res], 0)
+    Atb = np.stack([r[1] for r in res], 0)
+    diag = np.stack([r[2] for r in res], 0)
+    return x.astype(A_val.dtype), Atb.astype(A_val.dtype), diag.astype(A_val.dtype)
+
+
 def retract(spec, values, delta, ignore_mask=None):
     """core/objective.py:857-914 (retract_vars_sequence) + geometry/lie_group.py:197-198.
 
@@ -424,7 +465,7 @@ def check_convergence(err, last_err, abs_tol, rel_tol):
 
 def optimize(spec, method="lm", max_iterations=20, step_size=1.0, abs_err_tolerance=1e-10, rel_err_tolerance=1e-8,
              damping=1e-3, adaptive_damping=False, ellipsoidal_damping=False, damping_eps=1e-8,
-             down_damping_ratio=9.0, up_damping_ratio=11.0, damping_accept=0.1, sample_trace=True):
+             down_damping_ratio=9.0, up_damping_ratio=11.0, damping_accept=0.1, sample_trace=True, solver="dense", n_jobs=1):
     """nonlinear/nonlinear_least_squares.py:100-215 (_optimize_loop) with
     levenberg_marquardt.py:90-201 (reset / compute_delta / _check_accept) or gauss_newton.py:46-47.
 
@@ -440,22 +481,30 @@ def optimize(spec, method="lm", max_iterations=20, step_size=1.0, abs_err_tolera
     trace = []
     it, all_reject_attempts = 0, 0
     while it < max_iterations:
-        A, b, AtA, Atb = linearize_dense(spec, values)
-        if method == "lm":
-            delta = dense_solve(AtA, Atb, damping=lam, ellipsoidal=ellipsoidal_damping, eps=damping_eps)
+        if solver == "sparse":   # SparseLinearization + per-item sparse direct solves (the reference's CPU sparse path)
+            sstruct = sparse_structure(spec) if it == 0 and all_reject_attempts == 0 else sstruct
+            A_val, b = linearize_sparse(spec, values, sstruct)
+            delta, Atb2, AtA_diag = sparse_solve(sstruct, A_val, b, damping=lam if method == "lm" else None,
+                                                 ellipsoidal=ellipsoidal_damping, eps=damping_eps, n_jobs=n_jobs)
+            Atb, AtA = Atb2[:, :, None], None
         else:
-            delta = dense_solve(AtA, Atb)
+            A, b, AtA, Atb = linearize_dense(spec, values)
+            AtA_diag = AtA[:, np.arange(AtA.shape[1]), np.arange(AtA.shape[1])]
+            if method == "lm":
+                delta = dense_solve(AtA, Atb, damping=lam, ellipsoidal=ellipsoidal_damping, eps=damping_eps)
+            else:
+                delta = dense_solve(AtA, Atb)
         step = (delta * step_size).astype(dt)
         new_values = retract(spec, values, step, ignore_mask=converged)
         err = error_metric(spec, new_values)
         reject = None
         rec = dict(Atb=Atb[:, :, 0].copy(), delta=delta.copy(), lam=np.array(lam, dtype=dt, copy=True), new_err=err.copy())
         if sample_trace:
-            rec["AtA_diag"] = AtA[:, np.arange(AtA.shape[1]), np.arange(AtA.shape[1])].copy()
+            rec["AtA_diag"] = AtA_diag.copy()
         if method == "lm" and adaptive_damping:
             dmp = lam.reshape(-1, 1)
             if ellipsoidal_damping:
-                dmp = dmp * AtA[:, np.arange(AtA.shape[1]), np.arange(AtA.shape[1])]
+                dmp = dmp * AtA_diag
             den = (step * (dmp * step + Atb[:, :, 0])).sum(axis=1) / 2
             with np.errstate(divide="ignore", invalid="ignore"):
                 rho = (last_err - err) / den

@@ -986,6 +986,108 @@ def make_c5(th):
     print("pgo_c5_lm err0", g["err0"], "->", g["trace_err"][-1], "took", round(time.time() - t0, 1), "s")
 
 
+PGO_BENCHMARK_EXPECTED = dict(   # the literal values held by /root/reference/tests/theseus_tests/test_pgo_benchmark.py:34-39, 66-71
+    dense_or_lu=[-0.29886279606812166, -0.3054215856589109, -0.27485602196709225, -0.3005231105990632],
+    baspacho=[-0.2988627960682926, -0.30542158565900696, -0.27485602196705955, -0.3005231105991407])
+PGO_BENCHMARK_CFG = dict(seed=1, num_poses=64, batch_size=16, dataset_size=256, max_num_batches=4, translation_noise=0.05, rotation_noise=0.02,
+                         loop_closure_ratio=0.2, loop_closure_outlier_ratio=0.25, max_iters=10, step_size=0.75, reg_w=1e-3,
+                         ratio_known_poses=0.1, lr=0.1, optimizer_kwargs={"backward_mode": "implicit", "track_err_history": True, "adaptive_damping": True,
+                                                           "__keep_final_step_size__": True, "verbose": False})
+
+
+def pgo_benchmark_run(th, torch, g, device="cpu", solver_kwargs=None):
+    """examples/pose_graph/pose_graph_synthetic.py:87-286 (`run`) on the fixture's dataset, shared by generator (th = the reference) and
+    tests (th = theseus_b200): Welsch-robust Between per edge with a learnable log radius, regularising prior on pose 0, priors on the
+    known poses, LevenbergMarquardt(max 10 iterations, step 0.75) in implicit backward mode, one Adam step on the radius per batch.
+    Returns the list of per-batch losses (what test_pgo_benchmark.py compares at rel 1e-10)."""
+    cfg = PGO_BENCHMARK_CFG
+    d = torch.float64
+    Bsz, nb = cfg["batch_size"], cfg["max_num_batches"]
+    P, GT, M = (torch.from_numpy(g[k]).to(device) for k in ("poses", "gt_poses", "meas"))      # [N, nb*B, 3, 4], ..., [E, nb*B, 3, 4]
+    edges = [tuple(int(x) for x in e) for e in g["edges"]]
+    info = torch.from_numpy(g["info"]).to(device).view(1, -1)
+    N = P.shape[0]
+    known = [int(i) for i in g["known_poses"]]
+
+    def pose_loss(pose_tensors, gt_tensors):
+        a = th.SE3(tensor=torch.cat(list(pose_tensors)))
+        b_ = th.SE3(tensor=torch.cat(list(gt_tensors)))
+        return th.local(a, b_).norm(dim=1).sum().view(1)
+
+    sl0 = slice(0, Bsz)
+    poses = [th.SE3(tensor=P[i, sl0].clone(), name=f"VERTEX_SE3__{i}") for i in range(N)]
+    gts = [th.SE3(tensor=GT[i, sl0].clone(), name=f"VERTEX_SE3_GT__{i}") for i in range(N)]
+    log_loss_radius = th.Vector(1, name="log_loss_radius", dtype=d)
+    objective = th.Objective(dtype=d)
+    rel_vars = []
+    for e, (i, j) in enumerate(edges):
+        z = th.SE3(tensor=M[e, sl0].clone(), name=f"EDGE_SE3__{i}_{j}")
+        rel_vars.append(z)
+        w = th.DiagonalCostWeight(th.Variable(info.clone()), name=f"EDGE_WEIGHT__{i}_{j}")
+        objective.add(th.RobustCostFunction(cost_function=th.Between(poses[i], poses[j], z, w), loss_cls=th.WelschLoss,
+                                            log_loss_radius=log_loss_radius))
+    prior_t = th.SE3(tensor=P[0, sl0].clone(), name="VERTEX_SE3__0__PRIOR")
+    objective.add(th.Difference(var=poses[0], target=prior_t, cost_weight=th.ScaleCostWeight(torch.tensor(cfg["reg_w"], dtype=d, device=device))))
+    w100 = th.ScaleCostWeight(100 * torch.ones(1, dtype=d, device=device))
+    for i in known:
+        objective.add(th.Difference(poses[i], gts[i], w100, name=f"pose_diff_{i}"))
+    optimizer = th.LevenbergMarquardt(objective.to(device), max_iterations=cfg["max_iters"], step_size=cfg["step_size"],
+                                      **(solver_kwargs or dict(linear_solver_cls=th.CholeskyDenseSolver)))
+    layer = th.TheseusLayer(optimizer)
+    layer.to(device=device)
+    radius = torch.nn.Parameter(torch.tensor([[3.0]], device=device, dtype=d))
+    adam = torch.optim.Adam([radius], lr=cfg["lr"])
+    losses = []
+    for bi in range(nb):
+        sl = slice(bi * Bsz, (bi + 1) * Bsz)
+        inputs = {poses[i].name: P[i, sl] for i in range(N)}
+        inputs[poses[0].name + "__PRIOR"] = P[0, sl].clone()
+        inputs.update({gts[i].name: GT[i, sl] for i in known})
+        inputs.update({rel_vars[e].name: M[e, sl] for e in range(len(edges))})
+        inputs["log_loss_radius"] = radius.clone()
+        with torch.no_grad():
+            ref = pose_loss([P[i, sl] for i in range(N)], [GT[i, sl] for i in range(N)])
+        out, _ = layer.forward(input_tensors=inputs, optimizer_kwargs=dict(cfg["optimizer_kwargs"]))
+        adam.zero_grad()
+        loss = (pose_loss([out[poses[i].name] for i in range(N)], [GT[i, sl] for i in range(N)]) - ref) / ref
+        loss.backward()
+        adam.step()
+        losses.append(float(loss.item()))
+    return losses
+
+
+def make_pgo_benchmark(th):
+    """The dataset of the reference's own end-to-end KAT (tests/theseus_tests/test_pgo_benchmark.py: 64 poses, batch 16, 4 batches, seed
+    1): generated by PoseGraphDataset.generate_synthetic_3D exactly like examples/pose_graph/pose_graph_synthetic.py:89-106, checked here
+    (reference on the CPU, CholeskyDenseSolver) against the literal losses of the test, and stored with the known-pose draw."""
+    import random
+    import torch
+    import theseus.utils.examples as theg
+    cfg = PGO_BENCHMARK_CFG
+    torch.manual_seed(cfg["seed"]); np.random.seed(cfg["seed"]); random.seed(cfg["seed"])
+    rng = torch.Generator(); rng.manual_seed(0)
+    pg, _ = theg.PoseGraphDataset.generate_synthetic_3D(
+        num_poses=cfg["num_poses"], translation_noise=cfg["translation_noise"], rotation_noise=cfg["rotation_noise"],
+        loop_closure_ratio=cfg["loop_closure_ratio"], loop_closure_outlier_ratio=cfg["loop_closure_outlier_ratio"],
+        batch_size=cfg["batch_size"], dataset_size=cfg["dataset_size"], generator=rng, dtype=torch.float64)
+    known = [i for i in range(cfg["num_poses"]) if not (np.random.rand() > cfg["ratio_known_poses"])]   # same draw as the example's loop
+    n_items = cfg["batch_size"] * cfg["max_num_batches"]
+    g = dict(poses=np.stack([p.tensor[:n_items].numpy() for p in pg.poses], 0), gt_poses=np.stack([p.tensor[:n_items].numpy() for p in pg.gt_poses], 0),
+             meas=np.stack([e.relative_pose.tensor[:n_items].numpy() if e.relative_pose.tensor.shape[0] > 1 else
+                            e.relative_pose.tensor.expand(n_items, 3, 4).numpy() for e in pg.edges], 0),
+             edges=np.array([(e.i, e.j) for e in pg.edges], dtype=np.int64), info=pg.edges[0].weight.diagonal.tensor.numpy().reshape(-1),
+             known_poses=np.array(known, dtype=np.int64))
+    losses = pgo_benchmark_run(th, torch, g)
+    exp = PGO_BENCHMARK_EXPECTED["dense_or_lu"]
+    rel = max(abs(a - b) / abs(b) for a, b in zip(losses, exp))
+    print("pgo_benchmark: reference losses here", losses, "max rel diff vs the literal KAT", rel)
+    assert rel < 1e-9
+    g["losses_reference_here"] = np.array(losses)
+    np.savez_compressed(os.path.join(HERE, "pgo_benchmark_kat.npz"), **g)
+    print("pgo_benchmark_kat", {k: v.shape for k, v in g.items()})
+
+
+
 def make_backward(th):
     """End-to-end gradients through TheseusLayer (theseus_layer.py:45-97) in the reference's backward modes, dense solver, fp64."""
     import torch
@@ -1013,6 +1115,9 @@ def make_backward(th):
 
 if __name__ == "__main__":
     th, lieF = _import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "pgo_benchmark":
+        make_pgo_benchmark(th)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "backward":
         make_backward(th)
         sys.exit(0)

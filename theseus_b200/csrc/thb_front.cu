@@ -54,89 +54,226 @@ struct FrontArgs {
   int32_t* info;
 };
 
-// ------------------------------------------------------------------------------------------------ small fronts
+// ------------------------------------------------------------------------------------------------ fronts in shared memory
+// One CTA per (front, item).  Shared memory: PN [w8 + b16 + 8][ldp] = the panel: pivot rows, identity padding up to w8 = w rounded
+// to 8, the border rows from row w8 on (b16 = b rounded to 16, zero padding), Wd [8][20] = inverse of the current 8 x 8 diagonal block,
+// ST [32][ldc] = one 32-row stripe of the update matrix.
+//   1. panel <- AtA entries (+ damping) + the children's entries that land in the pivot columns
+//   2. blocked LEFT-LOOKING factorisation over 8-column blocks: warp 0 forms the diagonal block (DMMA), factors and inverts it in
+//      registers (shuffles); every warp then finishes 16-row tiles of that block column: X = A - sum_k L_ik L_jk^T, L_ij = X W^T,
+//      both products on the FP64 tensor pipe -- the pivot block's own rows and the border rows alike (no separate TRSM, no scalar loops)
+//   3. the update matrix is never resident: per 32-row stripe, children's contributions for those rows minus P_stripe P^T (DMMA), written once.
+constexpr int FRONT_STRIPE = 32;
+constexpr int FRONT_WD_LD = 20;
+
+__host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b) {
+  const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
+  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + (int64_t)FRONT_STRIPE * front_pad_ld(b16) + 2;
+}
+
+// One warp: Cholesky of the 8 x 8 block at T (row stride ld; lower part read, L written in place) and its inverse (full 8 x 8, zeros
+// above the diagonal) to Wd (row stride FRONT_WD_LD).  One row / one column per lane (lanes >= 8 shadow lane 0), pivots and
+// multipliers exchanged with shuffles.  Returns 0 or 1 + index of the first non-positive pivot.
+__device__ __forceinline__ int front_leaf8(double* __restrict__ T, int ld, double* __restrict__ Wd, int lane) {
+  const int ln = lane < 8 ? lane : 0;
+  double row[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) row[q] = T[ln * ld + q];
+  int fail = 0;
+  double invd = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const double d = __shfl_sync(0xffffffffu, row[c], c);
+    if (!(d > 0.0) && fail == 0) fail = c + 1;
+    double inv = rsqrt(d);
+    inv = inv * (1.5 - 0.5 * d * inv * inv);   // one Newton step on the hardware seed; sqrt(d) = d * rsqrt(d)
+    const double sq = d * inv;
+    if (lane == c) invd = inv;
+    const double lrc = (lane == c) ? sq : row[c] * inv;
+    row[c] = lrc;
+#pragma unroll
+    for (int q = c + 1; q < 8; q++) {
+      const double lqc = __shfl_sync(0xffffffffu, lrc, q);
+      row[q] -= lrc * lqc;
+    }
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (q <= lane) T[lane * ld + q] = row[q];
+  }
+  double x[8];
+#pragma unroll
+  for (int rr = 0; rr < 8; rr++) {
+    double sacc = (lane == rr) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < rr; k++) {
+      const double lrk = __shfl_sync(0xffffffffu, row[k], rr);
+      sacc -= lrk * x[k];
+    }
+    x[rr] = sacc * __shfl_sync(0xffffffffu, invd, rr);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) Wd[rr * FRONT_WD_LD + lane] = (rr >= lane) ? x[rr] : 0.0;
+  }
+  return fail;
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   extern __shared__ double sm[];
   const thb_front_plan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
+  const int lr = lane >> 2, lc = lane & 3;
   const int64_t item = blockIdx.x;
   const int t = p.sched[a.s0 + blockIdx.y];
   const int w = p.f_w[t], b = p.f_b[t], r = w + b;
-  const int b16 = (b + 15) & ~15, w4 = (w + 3) & ~3;
-  const int ldp = front_pad_ld(w4), ldc = front_pad_ld(b16);
-  const int prow = w + b16;
-  double* PN = sm;                 // [prow][ldp]  panel: pivot block on top, border rows below, zero padding
-  double* CB = sm + prow * ldp;    // [b16][ldc]   update matrix (lower triangle meaningful)
-  for (int e = tid; e < prow * ldp + b16 * ldc; e += THREADS) sm[e] = 0.0;
+  const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
+  const int ldp = front_pad_ld(w8), ldc = front_pad_ld(b16);
+  const int prow = w8 + b16 + 8;
+  double* PN = sm;                          // [prow][ldp]
+  double* Wd = PN + prow * ldp;             // [8][FRONT_WD_LD]
+  double* ST = Wd + 8 * FRONT_WD_LD;        // [FRONT_STRIPE][ldc]
+  for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
   __syncthreads();
+  if (tid < w8 - w) PN[(w + tid) * ldp + w + tid] = 1.0;   // identity on the padding of the pivot block
   double* Lg = a.factor + item * p.data_size + p.f_panel_off[t];
   {
     const double al = a.alpha != nullptr ? a.alpha[item] : 0.0;
     const double be = a.beta != nullptr ? a.beta[item] : 0.0;
+    int i = tid / w, j = tid - i * w;   // (i, j) of element e, advanced without a division
+    const int di = THREADS / w, dj = THREADS - di * w;
     for (int e = tid; e < r * w; e += THREADS) {
-      const int i = e / w, j = e - i * w;
       double v = Lg[e];
       if (i == j) v = v + (al * v + be);   // linear/utils.py:14-33: diag <- diag (1 + alpha) + beta
-      PN[i * ldp + j] = v;
+      PN[(i < w ? i : i + (w8 - w)) * ldp + j] = v;
+      i += di; j += dj;
+      if (j >= w) { j -= w; i++; }
     }
   }
   __syncthreads();
-  // ---- extend-add of the children's update matrices, one child after the other (fixed order) ----
-  for (int ci = p.child_ptr[t]; ci < p.child_ptr[t + 1]; ci++) {
+  // ---- children, part 1: the entries that land in the pivot columns (rel[j] < w); fixed child order ----
+  const int c_begin = p.child_ptr[t], c_end = p.child_ptr[t + 1];
+  for (int ci = c_begin; ci < c_end; ci++) {
     const int c = p.child_list[ci];
     const int bc = p.f_b[c], ldg = p.f_cb_ld[c];
     const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
     const int32_t* rel = p.f_rel + p.rel_ptr[c];
-    for (int i = warp; i < bc; i += NW) {
-      const int ri = rel[i];
-      const double* srow = src + (int64_t)i * ldg;
-      for (int j = lane; j <= i; j += 32) {
-        const int rj = rel[j];
-        const double v = srow[j];
-        if (rj < w) PN[ri * ldp + rj] += v;
-        else CB[(ri - w) * ldc + (rj - w)] += v;
+    int jw;   // first child row whose image is a border row of this front (rel is increasing)
+    {
+      int lo = 0, hi = bc;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < w) lo = mid + 1; else hi = mid; }
+      jw = lo;
+    }
+    if (jw > 0) {
+      for (int i = warp; i < bc; i += NW) {
+        const int ri = rel[i];
+        const int prw = ri < w ? ri : ri + (w8 - w);
+        const double* srow = src + (int64_t)i * ldg;
+        const int jend = i < jw ? i + 1 : jw;
+        for (int j = lane; j < jend; j += 32) PN[prw * ldp + rel[j]] += srow[j];
       }
+      __syncthreads();
+    }
+  }
+  // ---- blocked left-looking factorisation of the panel, 8 columns at a time ----
+  const int nbk = w8 / 8, nrt = (w8 + b16) / 8;
+  for (int jb = 0; jb < nbk; jb++) {
+    if (warp == 0) {
+      double c0 = 0.0, c1 = 0.0;
+      const double* Arow = PN + (8 * jb + lr) * ldp + lc;
+      for (int k = 0; k < 8 * jb; k += 4) {
+        const double av = Arow[k];
+        front_mma884(c0, c1, av, av);   // D -= L_j L_j^T : the column operand is the same 8 rows
+      }
+      double* d = PN + (8 * jb + lr) * ldp + 8 * jb + 2 * lc;
+      d[0] -= c0;
+      d[1] -= c1;
+      __syncwarp();
+      const int fail = front_leaf8(PN + (8 * jb) * ldp + 8 * jb, ldp, Wd, lane);
+      if (lane == 0 && fail != 0 && 8 * jb + fail <= w) atomicCAS(a.info + item, 0, p.f_first[t] + 8 * jb + fail);
+    }
+    __syncthreads();
+    const int npair = (nrt - jb) / 2;   // row tiles jb+1 .. nrt-1 in pairs (an odd last tile pairs with the zero tile after the end)
+    for (int q = warp; q < npair; q += NW) {
+      const int rt0 = jb + 1 + 2 * q;
+      double x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
+      const double* A0 = PN + (8 * rt0 + lr) * ldp + lc;
+      const double* Bj = PN + (8 * jb + lr) * ldp + lc;
+      for (int k = 0; k < 8 * jb; k += 4) {
+        const double bf = Bj[k];
+        front_mma884(x00, x01, A0[k], bf);
+        front_mma884(x10, x11, A0[8 * ldp + k], bf);
+      }
+      double* X0 = PN + (8 * rt0 + lr) * ldp + 8 * jb + 2 * lc;
+      X0[0] -= x00; X0[1] -= x01;
+      X0[8 * ldp] -= x10; X0[8 * ldp + 1] -= x11;
+      __syncwarp();
+      x00 = x01 = x10 = x11 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k += 4) {
+        const double bf = Wd[lr * FRONT_WD_LD + k + lc];   // B[k][n] = Winv[n][k]
+        front_mma884(x00, x01, A0[8 * jb + k], bf);
+        front_mma884(x10, x11, A0[8 * ldp + 8 * jb + k], bf);
+      }
+      __syncwarp();
+      X0[0] = x00; X0[1] = x01;
+      X0[8 * ldp] = x10; X0[8 * ldp + 1] = x11;
     }
     __syncthreads();
   }
-  // ---- pivots: right-looking on the r x w panel (columns k+1..w-1 of all rows; the rank-w update of C comes after) ----
-  for (int k = 0; k < w; k++) {
-    const double pkk = PN[k * ldp + k];
-    double s;
-    if (pkk > 0.0) {
-      s = 1.0 / sqrt(pkk);
-    } else {
-      s = 1.0;
-      if (tid == 0) atomicCAS(a.info + item, 0, p.f_first[t] + k + 1);
+  // ---- write the factored panel (zeros above the diagonal of the pivot block) ----
+  {
+    int i = tid / w, j = tid - i * w;
+    const int di = THREADS / w, dj = THREADS - di * w;
+    for (int e = tid; e < r * w; e += THREADS) {
+      Lg[e] = (j > i) ? 0.0 : PN[(i < w ? i : i + (w8 - w)) * ldp + j];
+      i += di; j += dj;
+      if (j >= w) { j -= w; i++; }
     }
-    for (int i = k + 1 + tid; i < r; i += THREADS) PN[i * ldp + k] *= s;
+  }
+  if (b == 0) return;
+  // ---- update matrix, stripe by stripe: C[s0 .. s0+32, 0 .. ] = sum over children - P_stripe P^T ----
+  double* dst = a.arena_cur + item * p.arena_size + p.f_cb_off[t];
+  const int ldg_out = p.f_cb_ld[t];
+  const double* P = PN + w8 * ldp;
+  for (int s0 = 0; s0 < b; s0 += FRONT_STRIPE) {
+    for (int e = tid; e < FRONT_STRIPE * ldc; e += THREADS) ST[e] = 0.0;
     __syncthreads();
-    if (tid == 0) PN[k * ldp + k] = pkk * s;
-    const int nc = w - k - 1;
-    if (nc > 0) {
-      for (int e = tid; e < nc * (r - k - 1); e += THREADS) {
-        const int i = k + 1 + e / nc, j = k + 1 + e % nc;
-        if (i >= j) PN[i * ldp + j] -= PN[i * ldp + k] * PN[j * ldp + k];
+    for (int ci = c_begin; ci < c_end; ci++) {
+      const int c = p.child_list[ci];
+      const int bc = p.f_b[c], ldg = p.f_cb_ld[c];
+      const int32_t* rel = p.f_rel + p.rel_ptr[c];
+      int lo = 0, hi = bc;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < w + s0) lo = mid + 1; else hi = mid; }
+      const int i0 = lo;
+      hi = bc;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < w + s0 + FRONT_STRIPE) lo = mid + 1; else hi = mid; }
+      const int i1 = lo;
+      if (i1 > i0) {      // uniform across the CTA
+        int jw;
+        { int l2 = 0, h2 = bc; while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rel[mid] < w) l2 = mid + 1; else h2 = mid; } jw = l2; }
+        const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
+        for (int i = i0 + warp; i < i1; i += NW) {
+          const int ri = rel[i] - w - s0;
+          const double* srow = src + (int64_t)i * ldg;
+          for (int j = jw + lane; j <= i; j += 32) ST[ri * ldc + rel[j] - w] += srow[j];
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
-  }
-  // ---- C -= P P^T on the FP64 tensor pipe: 16 x 16 macro tiles of the lower triangle, one warp each ----
-  if (b > 0) {
-    const int lr = lane >> 2, lc = lane & 3;
-    const int nt = b16 / 16, ntl = nt * (nt + 1) / 2;
-    const double* P = PN + w * ldp;
-    for (int q = warp; q < ntl; q += NW) {
-      int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-      while ((ti + 1) * (ti + 2) / 2 <= q) ti++;
-      while (ti * (ti + 1) / 2 > q) ti--;
-      const int tj = q - ti * (ti + 1) / 2;
+    // 16 x 16 macro tiles of the two macro rows of this stripe that lie in the lower triangle
+    const int R0 = s0 / 16;
+    const int n0 = R0 + 1, n1 = (s0 + 16 < b16) ? R0 + 2 : 0;
+    for (int q = warp; q < n0 + n1; q += NW) {
+      const int mr = q < n0 ? 0 : 1;
+      const int ct = q < n0 ? q : q - n0;
       double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-      const double* Pa = P + (16 * ti + lr) * ldp + lc;
-      const double* Pb = P + (16 * tj + lr) * ldp + lc;
-      for (int k4 = 0; k4 < w4; k4 += 4) {
+      const double* Pa = P + (16 * (R0 + mr) + lr) * ldp + lc;
+      const double* Pb = P + (16 * ct + lr) * ldp + lc;
+      for (int k4 = 0; k4 < w8; k4 += 4) {
         const double a0 = Pa[k4], a1 = Pa[8 * ldp + k4];
         const double b0 = Pb[k4], b1 = Pb[8 * ldp + k4];
         front_mma884(acc[0][0][0], acc[0][0][1], a0, b0);
@@ -148,23 +285,18 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
       for (int mi = 0; mi < 2; mi++)
 #pragma unroll
         for (int ni = 0; ni < 2; ni++) {
-          double* d = CB + (16 * ti + 8 * mi + lr) * ldc + 16 * tj + 8 * ni + 2 * lc;
+          double* d = ST + (16 * mr + 8 * mi + lr) * ldc + 16 * ct + 8 * ni + 2 * lc;
           d[0] -= acc[mi][ni][0];
           d[1] -= acc[mi][ni][1];
         }
     }
-  }
-  __syncthreads();
-  // ---- write back: the panel (zeros above the diagonal of the pivot block), the update matrix (lower triangle) ----
-  for (int e = tid; e < r * w; e += THREADS) {
-    const int i = e / w, j = e - i * w;
-    Lg[e] = (j > i) ? 0.0 : PN[i * ldp + j];
-  }
-  if (b > 0) {
-    double* dst = a.arena_cur + item * p.arena_size + p.f_cb_off[t];
-    const int ldg = p.f_cb_ld[t];
-    for (int i = warp; i < b; i += NW)
-      for (int j = lane; j <= i; j += 32) dst[(int64_t)i * ldg + j] = CB[i * ldc + j];
+    __syncthreads();
+    const int rows_here = min(FRONT_STRIPE, b - s0);
+    for (int i = warp; i < rows_here; i += NW) {
+      double* drow = dst + (int64_t)(s0 + i) * ldg_out;
+      for (int j = lane; j <= s0 + i; j += 32) drow[j] = ST[i * ldc + j];
+    }
+    __syncthreads();
   }
 }
 
@@ -395,10 +527,7 @@ static inline int front_set_smem(K kernel, size_t bytes, size_t* cache) {
 
 extern "C" {
 
-int64_t thb_front_small_smem_bytes(int32_t w, int32_t b) {
-  const int b16 = (b + 15) & ~15, w4 = (w + 3) & ~3;
-  return (int64_t)((w + b16) * thb::front_pad_ld(w4) + b16 * thb::front_pad_ld(b16)) * 8;
-}
+int64_t thb_front_small_smem_bytes(int32_t w, int32_t b) { return thb::front_smem_doubles(w, b) * 8; }
 
 int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* alpha,
                          const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes, int32_t* info, int64_t B,
@@ -476,7 +605,7 @@ int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_
       a.v_child = varena + (int64_t)((depth + 1) & 1) * B * p->varena_size;
       const int kc = cls > 2 ? 2 : cls;
       const int threads = thb::front_threads_of_class(kc);
-      const int64_t r_max = cls > 2 ? L[5] : (cls == 0 ? 48 : (cls == 1 ? 96 : 160));   // class-3 launches carry np >= r
+      const int64_t r_max = L[5];   // largest front of the launch (class-3 launches carry np >= r)
       const size_t smem = (size_t)(((r_max + 1) & ~1LL) + 32 * 33 + 1 + (pass == 1 ? threads : 0) + 2) * 8;
       const dim3 grid((unsigned)B, (unsigned)count);
       if (pass == 0) {

@@ -100,37 +100,74 @@ def build_pose_graph_objective(th, data, device, prior_weight: float = 1e-3, bat
     return objective, poses
 
 
+def _exp_se3_nd(xi: torch.Tensor) -> torch.Tensor:
+    """_exp_se3 over any leading dimensions, on xi's device."""
+    shp = xi.shape[:-1]
+    out = _exp_se3_dev(xi.reshape(-1, 6))
+    return out.view(*shp, 3, 4)
+
+
+def _exp_se3_dev(xi: torch.Tensor) -> torch.Tensor:
+    v, w = xi[:, :3], xi[:, 3:]
+    th = w.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    k = w / th
+    K = torch.zeros(xi.shape[0], 3, 3, dtype=xi.dtype, device=xi.device)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    s, c = torch.sin(th).unsqueeze(2), torch.cos(th).unsqueeze(2)
+    eye = torch.eye(3, dtype=xi.dtype, device=xi.device).expand_as(K)
+    KK = K @ K
+    R = eye + s * K + (1 - c) * KK
+    t3 = th.unsqueeze(2)
+    V = eye + ((1 - c) / t3) * K + ((t3 - s) / t3) * KK
+    return torch.cat([R, V @ v.unsqueeze(2)], dim=2)
+
+
+def _compose_nd(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    R = a[..., :3] @ b[..., :3]
+    t = a[..., :3] @ b[..., 3:] + a[..., 3:]
+    return torch.cat([R, t], dim=-1)
+
+
+def _inverse_nd(a: torch.Tensor) -> torch.Tensor:
+    Rt = a[..., :3].transpose(-1, -2)
+    return torch.cat([Rt, -(Rt @ a[..., 3:])], dim=-1)
+
+
 def pose_graph_sphere(rings: int, per_ring: int, batch_size: int, translation_noise: float = 0.05, rotation_noise: float = 0.02,
-                      radius: float = 10.0, seed: int = 0, dtype: torch.dtype = torch.float64):
+                      radius: float = 10.0, seed: int = 0, dtype: torch.dtype = torch.float64, device="cpu"):
     """sphere2500-like topology: `rings` x `per_ring` poses on a sphere, odometry chain
     i -> i+1 plus ring-to-ring edges i -> i+per_ring: E = N-1 + N-per_ring (2500 nodes -> 4949 edges).
     Measurements = ground-truth relative pose composed with uniform noise (the noise model of generate_synthetic_3D);
-    initial poses = ground truth composed with the same noise."""
-    gen = torch.Generator().manual_seed(seed)
+    initial poses = ground truth composed with the same noise.  Vectorised over poses / edges; `device` only says where the
+    fabrication runs (the tensors are returned on the CPU: inputs start in host memory)."""
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(seed)
     N, B = rings * per_ring, batch_size
 
-    def urand(n, scale_t, scale_r):
-        u = 2.0 * torch.rand(n, 6, generator=gen, dtype=dtype) - 1.0
-        return torch.cat([u[:, :3] * scale_t, u[:, 3:] * scale_r], dim=1)
+    def urand(shape, scale_t, scale_r):
+        u = 2.0 * torch.rand(*shape, 6, generator=gen, dtype=dtype, device=dev) - 1.0
+        return torch.cat([u[..., :3] * scale_t, u[..., 3:] * scale_r], dim=-1)
 
-    idx = torch.arange(N)
+    idx = torch.arange(N, device=dev)
     ring, k = idx // per_ring, idx % per_ring
     phi = (ring.to(dtype) + 0.5) / rings * np.pi           # polar angle
     theta = k.to(dtype) / per_ring * 2 * np.pi
     pos = radius * torch.stack([torch.sin(phi) * torch.cos(theta), torch.sin(phi) * torch.sin(theta), torch.cos(phi)], dim=1)
-    # orientation: yaw along the ring direction
-    R = torch.zeros(N, 3, 3, dtype=dtype)
+    R = torch.zeros(N, 3, 3, dtype=dtype, device=dev)     # orientation: yaw along the ring direction
     c, s = torch.cos(theta), torch.sin(theta)
     R[:, 0, 0], R[:, 0, 1], R[:, 1, 0], R[:, 1, 1], R[:, 2, 2] = c, -s, s, c, 1.0
     gt1 = torch.cat([R, pos.unsqueeze(2)], dim=2)                               # [N,3,4]
     # per-batch-item ground truth = shared shape perturbed a little per item
-    gt = [_compose(gt1[i:i + 1].expand(B, 3, 4), _exp_se3(urand(B, 0.2, 0.05))) for i in range(N)]
+    gt = _compose_nd(gt1.unsqueeze(1).expand(N, B, 3, 4), _exp_se3_nd(urand((N, B), 0.2, 0.05)))
     edges = [(i, i + 1) for i in range(N - 1)] + [(i, i + per_ring) for i in range(N - per_ring)]
-    meas = []
-    for (i, j) in edges:
-        rel = _compose(_inverse(gt[i]), gt[j])
-        meas.append(_compose(rel, _exp_se3(urand(B, translation_noise, rotation_noise))))
-    poses = [_compose(gt[i], _exp_se3(urand(B, translation_noise, rotation_noise))) for i in range(N)]
+    ei = torch.tensor([e[0] for e in edges], device=dev)
+    ej = torch.tensor([e[1] for e in edges], device=dev)
+    meas = torch.empty(len(edges), B, 3, 4, dtype=dtype, device=dev)
+    CH = 512                                                                     # chunks of edges bound the temporaries
+    for c0 in range(0, len(edges), CH):
+        a, b_ = ei[c0:c0 + CH], ej[c0:c0 + CH]
+        rel = _compose_nd(_inverse_nd(gt[a]), gt[b_])
+        meas[c0:c0 + CH] = _compose_nd(rel, _exp_se3_nd(urand((a.shape[0], B), translation_noise, rotation_noise)))
+    poses = _compose_nd(gt, _exp_se3_nd(urand((N, B), translation_noise, rotation_noise)))
     info = torch.tensor([1 / translation_noise] * 3 + [1 / rotation_noise] * 3, dtype=dtype)
-    return dict(poses=torch.stack(poses, 0).contiguous(), gt_poses=torch.stack(gt, 0).contiguous(), edges=edges,
-                meas=torch.stack(meas, 0).contiguous(), info=info)
+    return dict(poses=poses.contiguous().cpu(), gt_poses=gt.contiguous().cpu(), edges=edges, meas=meas.contiguous().cpu(), info=info)

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-SMALL_CLASSES = (48, 96, 160)     # front size limits (scalar rows) of the shared-memory kernel's size classes
+SMALL_CLASSES = (48, 96, 1 << 30)  # front sizes (scalar rows) of the shared-memory kernel's thread-count classes: 64 / 128 / 256 threads
 BIG_TW, BIG_TM = 64, 128          # block-column width / row-tile height of the dense DMMA kernel (thb_chol_dense.cu)
 
 
@@ -160,6 +160,7 @@ def _flops_of(struct, dims):
 
 
 SMALL_SMEM_LIMIT = 220 * 1024
+SMEM_BUCKETS = (27 * 1024, 36 * 1024, 55 * 1024, 74 * 1024, 112 * 1024)   # 8, 6, 4, 3, 2 CTAs per SM (227 KB usable), then 1
 
 
 def _pad_ld(x: int) -> int:
@@ -167,9 +168,13 @@ def _pad_ld(x: int) -> int:
 
 
 def small_smem_bytes(w: int, b: int) -> int:
-    """Dynamic shared memory of front_small_kernel for a front (thb_front.cu / thb_front_small_smem_bytes)."""
-    b16, w4 = (b + 15) & ~15, (w + 3) & ~3
-    return ((w + b16) * _pad_ld(w4) + b16 * _pad_ld(b16)) * 8
+    """Dynamic shared memory of front_small_kernel for a front (thb_front.cu: front_smem_doubles): padded panel + inverse of one 8 x 8
+    diagonal block + one 32-row stripe of the update matrix."""
+    b16, w4, w8 = (b + 15) & ~15, (w + 3) & ~3, (w + 7) & ~7
+    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 32 * _pad_ld(b16) + 2) * 8
+
+
+SMALL_MAX_W = 192    # pivot block columns of 8 are factored one after the other inside the CTA: wider pivot blocks go to the dense kernel
 
 
 def _front_cost(w, b):
@@ -220,7 +225,7 @@ class FrontPlan:
 
 
 def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float = 0.12, merge_flops: float = 4e4,
-                     merge_max_r: int = SMALL_CLASSES[1], small_limit: int = SMALL_CLASSES[-1]) -> FrontPlan:
+                     merge_max_r: int = SMALL_CLASSES[1], small_limit: Optional[int] = None) -> FrontPlan:
     param_size = np.asarray(param_size, dtype=np.int64)
     ptrs = np.asarray(ptrs, dtype=np.int64)
     inds = np.asarray(inds, dtype=np.int64)
@@ -350,8 +355,9 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     f_class = np.zeros(S, dtype=np.int32)
     for t in range(S):
         r = int(f_r[t])
-        f_class[t] = 3 if (r > small_limit or small_smem_bytes(int(f_w[t]), int(f_b[t])) > SMALL_SMEM_LIMIT) else int(
-            np.searchsorted(np.array(SMALL_CLASSES), r))
+        too_big = (small_limit is not None and r > small_limit) or int(f_w[t]) > SMALL_MAX_W or \
+            small_smem_bytes(int(f_w[t]), int(f_b[t])) > SMALL_SMEM_LIMIT
+        f_class[t] = 3 if too_big else min(int(np.searchsorted(np.array(SMALL_CLASSES), r)), 2)
     # ---- storage: panels, update-matrix arena (by depth parity), border-vector arena ----
     f_panel_off = np.zeros(S, dtype=np.int64)
     off = 0
@@ -420,18 +426,26 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     rows_ptr[1:] = np.cumsum(f_b)
     f_rows = np.concatenate(border_rows).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
     # ---- schedule ----
-    sched = np.array(sorted(range(S), key=lambda t: (-int(f_depth[t]), int(f_class[t]), -int(f_r[t]), t)), dtype=np.int32)
+    # a launch's dynamic shared memory is its largest front's: fronts of one (depth, class) are split by occupancy bucket
+    # (CTAs per SM that fit), so that a few large fronts do not cap the residency of the many small ones
+    def bucket(t):
+        if f_class[t] == 3:
+            return 0
+        sm = small_smem_bytes(int(f_w[t]), int(f_b[t]))
+        return int(np.searchsorted(np.array(SMEM_BUCKETS), sm))
+    f_bucket = np.array([bucket(t) for t in range(S)], dtype=np.int32)
+    sched = np.array(sorted(range(S), key=lambda t: (-int(f_depth[t]), int(f_class[t]), int(f_bucket[t]), -int(f_r[t]), t)), dtype=np.int32)
     launches = []
     i = 0
     while i < S:
         t = int(sched[i])
-        d, c = int(f_depth[t]), int(f_class[t])
+        d, c, bk = int(f_depth[t]), int(f_class[t]), int(f_bucket[t])
         j = i + 1
         if c != 3:
-            while j < S and int(f_depth[sched[j]]) == d and int(f_class[sched[j]]) == c:
+            while j < S and int(f_depth[sched[j]]) == d and int(f_class[sched[j]]) == c and int(f_bucket[sched[j]]) == bk:
                 j += 1
             smem = max(small_smem_bytes(int(f_w[q]), int(f_b[q])) for q in sched[i:j])
-            launches.append((d, c, i, j - i, smem, 0, 0, 0, 0, 0))
+            launches.append((d, c, i, j - i, smem, max(int(f_r[q]) for q in sched[i:j]), 0, 0, 0, 0))
         else:   # one front: (.., np, pivot block columns, offset of F in the arena, first pivot [info base], front index)
             launches.append((d, c, i, 1, 0, int(f_np[t]), int(f_wpad[t]) // BIG_TW, int(f_fr_off[t]), int(f_first[t]), t))
         i = j
