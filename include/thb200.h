@@ -402,6 +402,15 @@ int thb_lm_control_f32(const float* delta, const float* Atb, const float* diag, 
                        float down_ratio, float up_ratio, uint8_t* reject, float* err_out, int32_t* stats, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense batched Gram for GENUINELY dense Jacobians (AutoDiffCostFunction with dim >> dof):  AtA [B,n,n] = A^T A,  A [B,m,n] row-major.
+ * Replaces `At.bmm(A)` of theseus/optimizer/dense_linearization.py:58-62 where the block-sparse Gram (thb_gram_f64) has nothing to skip.
+ * TMA-staged tiles (one 3-D tensor map over [B,m,n], cp.async.bulk.tensor + mbarrier ring) feeding the FP64 tensor pipe (mma.sync DMMA;
+ * tcgen05 has no fp64 kind); the full symmetric matrix is written.  n must be even and A 16-byte aligned (else THB_ERR_UNSUPPORTED:
+ * the Python host then stays on thb_gram_f64).
+ * ---------------------------------------------------------------------------------------------- */
+int thb_gram_dense_f64(const double* A, double* AtA, int64_t B, int64_t m, int64_t n, thb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * MULTIFRONTAL (supernodal) batched block-sparse Cholesky -- layout "front" of the Python BaspachoSparseSolver.
  * Replaces BaSpaCho's batched supernodal factor / solve behind NumericDecomposition::factor / solve
  * (theseus/extlib/baspacho_solver_cuda.cu:203-214, 282-287; baspacho_solver.cpp:291) for batches that share one structure.
@@ -418,9 +427,9 @@ int thb_lm_control_f32(const float* delta, const float* Atb, const float* diag, 
  *     a multiple of 64, identity on the padding), factored in place by the DMMA dense kernel in partial mode
  *     (thb_potrf_partial_inplace_f64); its trailing block IS the update matrix (f_cb_off / f_cb_ld point into it).
  *   child -> parent maps: f_rel[rel_ptr[c] .. rel_ptr[c+1]) = local row index in the parent front of child c's border rows.
- * `launches` is a HOST array [num_launches][10] (int64) in factorisation order (deepest fronts first):
+ * `launches` is a HOST array [num_launches][12] (int64) in factorisation order (deepest fronts first):
  *   (depth, class, begin, count [into sched], dynamic smem bytes of the factor kernel, largest front of the launch [np for class 3],
- *    pivot block columns, f_fr_off, f_first [info base], front index) -- the last four for class-3 launches (one front each).
+ *    pivot block columns, f_fr_off, f_first [info base], front index, w, b) -- the last six for class-3 launches (one front each).
  * No atomics on data: results are bitwise reproducible and independent of the batch size.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct thb_front_plan {
@@ -437,9 +446,12 @@ typedef struct thb_front_plan {
   const int64_t* rows_ptr; const int32_t* f_rows;        /* border rows of front t as permuted scalar indices */
   const int32_t* sched;                                  /* [S] fronts in launch order */
   const int32_t* perm;                                   /* [n] original scalar column of permuted scalar p */
+  /* per CHILD front t of parent p: c_jw[t] = number of t's border rows that are pivots of p; c_sp[c_sp_ptr[t] + s] = first border row
+   * of t whose image lies at or after border row 32 s of p (s = 0 .. ceil(b_p / 32)): what the kernels would otherwise binary-search */
+  const int32_t* c_jw; const int64_t* c_sp_ptr; const int32_t* c_sp;
 } thb_front_plan;
 
-#define THB_FRONT_LAUNCH_COLS 10
+#define THB_FRONT_LAUNCH_COLS 12
 /* dynamic shared memory (bytes) the small-front factor kernel needs for a front with w pivots and b border rows */
 int64_t thb_front_small_smem_bytes(int32_t w, int32_t b);
 /* factor: in-place on `factor` [B, data_size] (AtA + fill-in zeros in, L out); dense_ws: workspace of
@@ -452,8 +464,8 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
 int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, const double* factor, const double* rhs,
                         double* x, double* work, double* varena, int64_t B, thb_stream_t stream);
 int64_t thb_potrf_partial_workspace_bytes(int64_t B, int64_t np);
-int thb_potrf_partial_inplace_f64(double* F, int64_t bstride, int64_t np, int32_t nb_piv, int32_t info_base, int32_t* info, int64_t B,
-                                  void* workspace, int64_t workspace_bytes, thb_stream_t stream);
+int thb_potrf_partial_inplace_f64(double* F, int64_t bstride, int64_t np, int32_t nb_piv, int32_t w_real, int32_t n_real, int32_t info_base,
+                                  int32_t* info, int64_t B, void* workspace, int64_t workspace_bytes, thb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched CSR helpers (same semantics as theseus/extlib/mat_mult.cu:359-400, int64 indices):

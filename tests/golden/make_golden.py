@@ -822,12 +822,12 @@ def tactile_problem(th, torch, inputs, device="cpu"):
     return objective, objs, effs, dict(c_square=c2, eff_radius=radius, w_qsp=w_qsp.scale, w_eoc=w_eoc.scale, w_mfb=w_mfb.scale)
 
 
-def make_tactile(th):
-    """LM trace + implicit-mode gradients of the planar-pushing objective above, by the reference (dense solver, fp64)."""
+def make_tactile(th, T=5, B=4, name="tactile_kat", seed=17, keep_deltas=True):
+    """LM trace + implicit-mode gradients of the planar-pushing objective above, by the reference (dense solver, fp64).
+    (T=25, B=512, name="tactile_c4_kat": BASELINE.json's config C4 at its real batch size.)"""
     import torch
-    torch.manual_seed(17)
+    torch.manual_seed(seed)
     d = torch.float64
-    T, B = 5, 4
     rows, cols = 16, 16
     yy, xx = torch.meshgrid(torch.arange(rows, dtype=d), torch.arange(cols, dtype=d), indexing="ij")
     sdf = (((xx - 7.5) * 0.05) ** 2 + ((yy - 7.5) * 0.05) ** 2).sqrt().unsqueeze(0) - 0.2    # disc of radius 0.2 centred in the object frame
@@ -854,7 +854,8 @@ def make_tactile(th):
         objective.update()
         out["err0"] = objective.error_metric().numpy()
         info = opt.optimize(end_iter_callback=cb, **lm)
-    out["trace_err"], out["trace_delta"] = np.stack(errs, 0), np.stack(deltas, 0)
+    out["trace_err"] = np.stack(errs, 0)
+    out["trace_delta"] = np.stack(deltas, 0) if keep_deltas else np.stack(deltas[:1], 0)
     out["final_obj"] = np.stack([o.tensor.numpy() for o in objs], 0)
     # implicit-mode gradients w.r.t. c_square, eff_radius and three cost weights
     objective, objs, effs, leaves = tactile_problem(th, torch, inputs)
@@ -867,8 +868,8 @@ def make_tactile(th):
     (P * torch.randn(P.shape, generator=gen, dtype=d)).sum().backward()
     for k, v in leaves.items():
         out["grad_" + k] = v.tensor.grad.numpy()
-    np.savez_compressed(os.path.join(HERE, "tactile_kat.npz"), **out)
-    print("tactile_kat err", out["err0"], "->", out["trace_err"][-1], "grads", {k: float(np.abs(out["grad_" + k]).max()) for k in leaves})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "err", out["err0"][:4], "->", out["trace_err"][-1][:4], "grads", {k: float(np.abs(out["grad_" + k]).max()) for k in leaves})
 
 
 
@@ -1115,6 +1116,9 @@ def make_backward(th):
 
 if __name__ == "__main__":
     th, lieF = _import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "tactile_c4":
+        make_tactile(th, T=25, B=512, name="tactile_c4_kat", seed=18, keep_deltas=False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pgo_benchmark":
         make_pgo_benchmark(th)
         sys.exit(0)

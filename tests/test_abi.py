@@ -76,7 +76,7 @@ def test_ctypes_signatures_match_the_header_prototypes():
     structs = {"thb_cost_group": _lib.CostGroup, "thb_var_table": _lib.VarTable, "thb_gram_plan": _lib.GramPlan,
                "thb_sparse_plan": _lib.SparsePlanStruct, "thb_sparse_lane_plan": _lib.SparseLanePlanStruct,
                "thb_sparse_lane_root": _lib.SparseLaneRootStruct, "thb_sparse_lane_tiles": _lib.SparseLaneTilesStruct,
-               "thb_sparse_lane_pieces": _lib.SparseLanePiecesStruct}
+               "thb_sparse_lane_pieces": _lib.SparseLanePiecesStruct, "thb_front_plan": _lib.FrontPlanStruct}
     scalars = {"int64_t": C.c_int64, "int32_t": C.c_int32, "int": C.c_int32, "double": C.c_double, "float": C.c_float,
                "thb_stream_t": C.c_void_p, "uint8_t": C.c_uint8}
     protos = re.findall(r"\b(int64_t|int32_t|int|void|double)\s+(thb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)

@@ -185,3 +185,14 @@ def test_front_kernels_report_a_non_positive_pivot(monkeypatch, emulated):
     solver.linearization.b = torch.ones(3, S2.num_rows, dtype=torch.float64)
     with pytest.raises(RuntimeError, match=r"batch element 0: matrix is not positive definite"):
         solver.solve()
+
+
+def test_front_solver_processes_the_batch_in_chunks(monkeypatch, emulated):
+    """front_options['chunk']: the update-matrix arena is sized for a chunk of the batch, the factor stays resident for every item."""
+    rng = np.random.default_rng(9)
+    S, B = _ring_structure(12), 3
+    A_val = rng.standard_normal((B, S.nnz)); b = rng.standard_normal((B, S.num_rows)); alpha = rng.random(B) * 0.1
+    _, x1 = _solve(monkeypatch, emulated, S, A_val, b, alpha)
+    solver, x2 = _solve(monkeypatch, emulated, S, A_val, b, alpha, front_options=dict(chunk=2))
+    assert solver._dev["bufs"]["arena"].shape[1] == 2
+    assert np.array_equal(x1, x2)

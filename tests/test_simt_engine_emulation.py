@@ -225,3 +225,15 @@ def test_returned_solutions_are_not_overwritten_by_the_next_forward(emulated):
         assert torch.equal(sol1[k], keep[k]), k
         assert sol1[k].data_ptr() != sol2[k].data_ptr()
     assert any(not torch.equal(sol1[k], sol2[k]) for k in keep)
+
+
+def test_error_vector_of_robust_costs_matches_the_error_metric(emulated):
+    """objective.py:562-641: error_metric() == 0.5 * ||error()||^2, also with RobustCostFunctions (whose weighted error is
+    sqrt(rho / dim + eps) per entry, not the sqrt(rho')-rescaled residual of the linearization)."""
+    g = load("pgo_small_welsch")
+    objective, poses = pgo_objective(th, g, device="cpu")
+    with torch.no_grad():
+        e = objective.error()
+        m = objective.error_metric()
+    assert e.shape[0] == m.shape[0] and e.shape[1] == objective.dim()
+    np.testing.assert_allclose(0.5 * (e ** 2).sum(dim=1).numpy(), m.numpy(), rtol=1e-10)

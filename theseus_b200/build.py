@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libthb200.so"
-SOURCES = ["thb_costs.cu", "thb_gram.cu", "thb_chol_dense.cu", "thb_sparse.cu", "thb_sparse_lane.cu", "thb_symbolic.cu", "thb_lie_ops.cu", "thb_front.cu"]
+SOURCES = ["thb_costs.cu", "thb_gram.cu", "thb_chol_dense.cu", "thb_sparse.cu", "thb_sparse_lane.cu", "thb_symbolic.cu", "thb_lie_ops.cu", "thb_front.cu", "thb_gram_dense.cu"]
 HEADERS = ["thb_common.cuh", "thb_lie.cuh", os.path.join("..", "..", "include", "thb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -942,13 +942,27 @@ class Objective:
             if not also_update:
                 old = {n: self.optim_vars[n].tensor for n in self.optim_vars}
             self.update(input_tensors)
-        eng = self.engine()
-        _, b = eng.linearize_sparse()
+        if any(isinstance(cf, RobustCostFunction) for cf in self.cost_functions.values()):
+            # -b of the linearization is the sqrt(rho')-rescaled residual; the reference's error() concatenates weighted_error(), which for
+            # a robust cost is sqrt(rho / dim + eps) per entry (robust_cost_function.py:87-109), so that error_metric == 0.5 * ||error()||^2
+            err = torch.cat([cf.weighted_error() for cf in self.cost_functions.values()], dim=1)
+        else:
+            eng = self.engine()
+            _, b = eng.linearize_sparse()   # (refreshes the engine's A_val / b buffers at the current variable values)
+            err = -b
         if input_tensors is not None and not also_update:
             self.update(old)
-        return -b
+        return err
 
     def retract_vars_sequence(self, delta: torch.Tensor, ordering, ignore_mask: Optional[torch.Tensor] = None,
                               force_update: bool = False):
         """objective.py:873-914: X_i <- X_i * exp(delta_i) for the variables in `ordering` (tmp containers)."""
-        self.engine().retract_into(delta, list(ordering), 1.0, None if force_update else ignore_mask)
+        eng = self.engine()
+        seq = list(ordering)
+        names = [v.name for v in seq]
+        if names != [v.name for v in eng.ordering]:
+            # the engine's retraction kernel walks its own column order; a subset / another order of variables would be paired with the
+            # wrong delta columns (the reference consumes delta sequentially over whatever sequence it is given, objective.py:857-871)
+            raise NotImplementedError("retract_vars_sequence: `ordering` must list the objective's optimisation variables in the "
+                                      f"linearization's column order ({len(eng.ordering)} variables), got {len(seq)}")
+        eng.retract_into(delta, seq, 1.0, None if force_update else ignore_mask)

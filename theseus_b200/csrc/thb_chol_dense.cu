@@ -304,6 +304,9 @@ struct CholArgs {
                        // (partial factorisation of a frontal matrix: the trailing block becomes the Schur complement)
   int64_t a_bstride, l_bstride;  // batch strides (doubles) of AtA and L; AtA == L (in place) for frontal matrices
   int info_base;       // added to the reported pivot index (position of the front's first pivot in the permuted vector)
+  int k_lim;           // partial mode: KB-steps of the k loop that hold real pivot columns (the identity padding of the last pivot
+                       // block column contributes nothing to the rows below it); the full factorisation uses nb * TN / KB
+  int n_real;          // partial mode: rows / columns >= n_real are padding (tiles that lie entirely there are skipped)
 };
 
 __device__ __forceinline__ void wait_ge(const int* addr, int target) {
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   const bool is_diag = (i == i0);
   const int roff = (j & 1) * 64;             // row offset of the diagonal block inside its tile
   const int64_t np = p.np;
+  if (j >= p.nb_piv && ((int64_t)j * TN >= p.n_real || (int64_t)i * TM >= p.n_real)) return;   // trailing tile entirely in the padding
   double* Lb = p.L + b * p.l_bstride;
   const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps -> 32 x 32 warp tiles
   const int lr = lane >> 2, lc = lane & 3;
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_col_kernel(CholArgs p) {
   }
 
   THB_TICK(1);
-  const int nk = jdep * (TN / KB);
+  const int nk = min(jdep * (TN / KB), p.k_lim);
   const bool skip_mma = is_diag && (wm * 32 < roff);  // odd block columns: the upper 64 rows of the diagonal tile lie above the diagonal
   const double* Arow = Lb + (int64_t)i * TM * np;
   const double* Brow = Lb + (int64_t)j * TN * np;
@@ -736,6 +740,7 @@ int thb_potrf_f64(const double* AtA, const double* alpha, const double* beta, in
   a.col_start = g.col_start; a.info = info;
   a.B = B; a.n = n; a.np = g.np; a.nb = g.nb; a.ntr = g.ntr;
   a.ticket = g.ticket; a.nb_piv = g.nb; a.a_bstride = n * n; a.l_bstride = g.np * g.np; a.info_base = 0;
+  a.k_lim = g.nb * (thb::TN / thb::KB); a.n_real = (int)g.np;
   // ONE launch for the whole factorisation: block columns are chained through the per-tile counters, so there are
   // no per-column launch gaps and no per-column wave-quantisation tails.
   thb::chol_col_kernel<<<(unsigned)starts[g.nb], thb::CHOL_THREADS, thb::CHOL_SMEM, cs>>>(a);
@@ -765,7 +770,9 @@ int thb_potrs_f64(const double* rhs, double* x, int64_t B, int64_t n, const void
 /* Partial in-place factorisation of B frontal matrices (multifrontal block-sparse Cholesky, thb_front.cu): F_b = F + b * bstride is an
  * np x np row-major matrix (np a multiple of 128; lower part + diagonal tiles read).  The first nb_piv 64-wide block columns are
  * factored (L in place, zeros above the diagonal of the diagonal blocks), the trailing (np - 64 nb_piv)^2 block becomes the Schur
- * complement F22 - L21 L21^T in place.  info[b] (NOT cleared here) receives info_base + 1 + index of the first non-positive pivot. */
+ * complement F22 - L21 L21^T in place.  w_real (> 0): number of real pivot columns -- the identity padding of the last pivot block column is
+ * skipped by the k loops; n_real (> 0): rows / columns from n_real on are padding -- trailing tiles entirely there are skipped.
+ * info[b] (NOT cleared here) receives info_base + 1 + index of the first non-positive pivot. */
 int64_t thb_potrf_partial_workspace_bytes(int64_t B, int64_t np) {
   if (B <= 0 || np <= 0) return 0;
   const int64_t nb = np / thb::TN;
@@ -774,8 +781,8 @@ int64_t thb_potrf_partial_workspace_bytes(int64_t B, int64_t np) {
   return thb::align_up(bytes, 256);
 }
 
-int thb_potrf_partial_inplace_f64(double* F, int64_t bstride, int64_t np, int32_t nb_piv, int32_t info_base, int32_t* info, int64_t B,
-                                  void* workspace, int64_t workspace_bytes, thb_stream_t stream) {
+int thb_potrf_partial_inplace_f64(double* F, int64_t bstride, int64_t np, int32_t nb_piv, int32_t w_real, int32_t n_real, int32_t info_base,
+                                  int32_t* info, int64_t B, void* workspace, int64_t workspace_bytes, thb_stream_t stream) {
   if (B < 0 || np <= 0 || np % thb::TM != 0 || F == nullptr || info == nullptr || workspace == nullptr) return THB_ERR_BAD_ARG;
   if (B == 0) return THB_OK;
   if (workspace_bytes < thb_potrf_partial_workspace_bytes(B, np)) return THB_ERR_BAD_ARG;
@@ -802,6 +809,8 @@ int thb_potrf_partial_inplace_f64(double* F, int64_t bstride, int64_t np, int32_
   a.AtA = F; a.alpha = nullptr; a.beta = nullptr; a.L = F; a.W = W; a.flags = flags; a.done = done; a.col_start = col_start; a.info = info;
   a.B = B; a.n = np; a.np = np; a.nb = nb; a.ntr = ntr;
   a.ticket = ticket; a.nb_piv = nb_piv; a.a_bstride = bstride; a.l_bstride = bstride; a.info_base = info_base;
+  a.k_lim = (w_real > 0 && nb_piv < nb) ? (w_real + thb::KB - 1) / thb::KB : nb * (thb::TN / thb::KB);
+  a.n_real = (n_real > 0 && n_real <= np) ? n_real : (int)np;
   thb::chol_col_kernel<<<(unsigned)total, thb::CHOL_THREADS, thb::CHOL_SMEM, cs>>>(a);
   THB_CHECK_LAUNCH();
   return THB_OK;

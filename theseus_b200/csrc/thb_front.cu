@@ -161,12 +161,7 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
     const int bc = p.f_b[c], ldg = p.f_cb_ld[c];
     const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
     const int32_t* rel = p.f_rel + p.rel_ptr[c];
-    int jw;   // first child row whose image is a border row of this front (rel is increasing)
-    {
-      int lo = 0, hi = bc;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < w) lo = mid + 1; else hi = mid; }
-      jw = lo;
-    }
+    const int jw = p.c_jw[c];   // first child row whose image is a border row of this front (rel is increasing)
     if (jw > 0) {
       for (int i = warp; i < bc; i += NW) {
         const int ri = rel[i];
@@ -244,17 +239,12 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
     __syncthreads();
     for (int ci = c_begin; ci < c_end; ci++) {
       const int c = p.child_list[ci];
-      const int bc = p.f_b[c], ldg = p.f_cb_ld[c];
+      const int ldg = p.f_cb_ld[c];
       const int32_t* rel = p.f_rel + p.rel_ptr[c];
-      int lo = 0, hi = bc;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < w + s0) lo = mid + 1; else hi = mid; }
-      const int i0 = lo;
-      hi = bc;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < w + s0 + FRONT_STRIPE) lo = mid + 1; else hi = mid; }
-      const int i1 = lo;
+      const int32_t* sp = p.c_sp + p.c_sp_ptr[c] + s0 / FRONT_STRIPE;   // precomputed stripe pointers (frontal.py)
+      const int i0 = sp[0], i1 = sp[1];
       if (i1 > i0) {      // uniform across the CTA
-        int jw;
-        { int l2 = 0, h2 = bc; while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rel[mid] < w) l2 = mid + 1; else h2 = mid; } jw = l2; }
+        const int jw = p.c_jw[c];
         const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
         for (int i = i0 + warp; i < i1; i += NW) {
           const int ri = rel[i] - w - s0;
@@ -314,14 +304,17 @@ __global__ void __launch_bounds__(ASM_THREADS) front_assemble_kernel(FrontArgs a
   const int64_t item = blockIdx.x;
   const int w = p.f_w[t], b = p.f_b[t], r = w + b, wpad = p.f_wpad[t], np = p.f_np[t];
   const int R0 = blockIdx.y * ASM_ROWS;
-  double* buf = sm;   // [ASM_ROWS][np]
-  for (int e = tid; e < ASM_ROWS * np; e += ASM_THREADS) buf[e] = 0.0;
+  // the dense kernel reads 128 x 64 tiles (i, j <= 2 i + 1): of row R only the columns below 128 (R / 128 + 1) are ever read
+  const int nc = min(np, 128 * (R0 / 128 + 1));
+  double* buf = sm;   // [ASM_ROWS][nc]
+  for (int e = tid; e < ASM_ROWS * nc; e += ASM_THREADS) buf[e] = 0.0;
   __syncthreads();
   const double* Lg = a.factor + item * p.data_size + p.f_panel_off[t];
   const double al = a.alpha != nullptr ? a.alpha[item] : 0.0;
   const double be = a.beta != nullptr ? a.beta[item] : 0.0;
-  for (int e = tid; e < ASM_ROWS * wpad; e += ASM_THREADS) {
-    const int rr = e / wpad, j = e - rr * wpad;
+  const int wlim = min(wpad, nc);
+  for (int e = tid; e < ASM_ROWS * wlim; e += ASM_THREADS) {
+    const int rr = e / wlim, j = e - rr * wlim;
     const int fr = R0 + rr;
     int i = -1;   // local front row
     if (fr < w) i = fr;
@@ -330,15 +323,15 @@ __global__ void __launch_bounds__(ASM_THREADS) front_assemble_kernel(FrontArgs a
       if (j < w && !(i < w && j > i)) {
         double v = Lg[(int64_t)i * w + j];
         if (i == j) v = v + (al * v + be);
-        buf[rr * np + j] = v;
+        buf[rr * nc + j] = v;
       }
     } else if (j == fr) {
-      buf[rr * np + j] = 1.0;   // padding inside the pivot columns
+      buf[rr * nc + j] = 1.0;   // padding inside the pivot columns
     }
   }
   for (int rr = tid; rr < ASM_ROWS; rr += ASM_THREADS) {
     const int fr = R0 + rr;
-    if (fr >= wpad + b) buf[rr * np + fr] = 1.0;   // padding after the border rows
+    if (fr >= wpad + b) buf[rr * nc + fr] = 1.0;   // padding after the border rows (fr < nc: the diagonal is always inside)
   }
   __syncthreads();
   for (int ci = p.child_ptr[t]; ci < p.child_ptr[t + 1]; ci++) {
@@ -354,16 +347,19 @@ __global__ void __launch_bounds__(ASM_THREADS) front_assemble_kernel(FrontArgs a
     const int i1 = lo;
     if (i1 > i0) {
       const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
-      const int nrow = i1 - i0;
-      for (int e = tid; e < nrow * bc; e += ASM_THREADS) {
-        const int i = i0 + e / bc, j = e % bc;
-        if (j <= i) buf[(front_map_big(rel[i], w, wpad) - R0) * np + front_map_big(rel[j], w, wpad)] += src[(int64_t)i * ldg + j];
+      for (int i = i0 + (tid >> 5); i < i1; i += ASM_THREADS / 32) {
+        const int fr = front_map_big(rel[i], w, wpad) - R0;
+        const double* srow = src + (int64_t)i * ldg;
+        for (int j = tid & 31; j <= i; j += 32) buf[fr * nc + front_map_big(rel[j], w, wpad)] += srow[j];
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   double* F = a.arena_cur + item * p.arena_size + p.f_fr_off[t] + (int64_t)R0 * np;
-  for (int e = tid; e < ASM_ROWS * np; e += ASM_THREADS) F[e] = buf[e];
+  for (int e = tid; e < ASM_ROWS * nc; e += ASM_THREADS) {
+    const int rr = e / nc, c = e - rr * nc;
+    F[(int64_t)rr * np + c] = buf[e];
+  }
 }
 
 // grid: x = item, y = chunk.  factor panel <- the pivot columns of the factored front matrix
@@ -575,8 +571,9 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
       int rc = thb::front_set_smem(thb::front_assemble_kernel, smem, &asm_set); if (rc) return rc;
       thb::front_assemble_kernel<<<dim3((unsigned)B, (unsigned)(np / thb::ASM_ROWS)), thb::ASM_THREADS, smem, cs>>>(a, t);
       THB_CHECK_LAUNCH();
-      rc = thb_potrf_partial_inplace_f64(a.arena_cur + fr_off, p->arena_size, np, (int32_t)nb_piv, (int32_t)first, info, B, dense_ws,
-                                         dense_ws_bytes, stream);
+      // w_real / n_real: the k loops stop at the real pivot columns, trailing tiles that lie in the padding are skipped
+      rc = thb_potrf_partial_inplace_f64(a.arena_cur + fr_off, p->arena_size, np, (int32_t)nb_piv, (int32_t)L[10], (int32_t)(nb_piv * 64 + L[11]),
+                                         (int32_t)first, info, B, dense_ws, dense_ws_bytes, stream);
       if (rc != THB_OK) return rc;
       thb::front_extract_kernel<<<dim3((unsigned)B, 8), 256, 0, cs>>>(a, t);
       THB_CHECK_LAUNCH();

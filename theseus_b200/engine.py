@@ -453,6 +453,13 @@ class Engine:
         Nothing downstream writes AtA (the damping is fused into the factorisation's load)."""
         B = self.batch_size
         s = _lib.stream_ptr()
+        if self.dense_jacobian(A_val):
+            # every cost function touches every variable: A_val IS the row-major dense Jacobian [B, m, n] -> TMA + DMMA Gram kernel
+            # (thb_gram_dense.cu); Atb / diag(AtA) from the column plan as usual
+            _lib.check(self.lib.thb_gram_dense_f64(_lib.ptr(A_val), _lib.ptr(AtA), B, self.m, self.n, s), "gram_dense")
+            self._zero_filled = None
+            self.atb(A_val, b, Atb, diag)
+            return
         plan = self.gram_plan_dense()
         key = (AtA.data_ptr(), AtA.numel())
         if self._zero_filled != key:
@@ -460,6 +467,12 @@ class Engine:
             self._zero_filled = key
         _lib.check(getattr(self.lib, f"thb_gram_{self.sfx}")(C.byref(plan), B, _lib.ptr(A_val), self.nnz, _lib.ptr(b), self.m, _lib.ptr(AtA),
                                                                self.n * self.n, _lib.ptr(Atb), _lib.ptr(diag), s), "gram")
+
+    def dense_jacobian(self, A_val) -> bool:
+        """True when the CSR pattern is full (nnz == m * n: A_val is the dense row-major Jacobian) and the dense Gram kernel applies
+        (fp64, even n, enough work to fill tiles)."""
+        return (self.nnz == self.m * self.n and A_val.dtype == torch.float64 and self.n % 2 == 0 and self.n >= 16 and self.m >= 64
+                and A_val.is_contiguous() and A_val.data_ptr() % 16 == 0 and os.environ.get("THB_DENSE_GRAM", "1") != "0")
 
     def atb(self, A_val, b, Atb, diag=None):
         plan = self.gram_plan_dense()

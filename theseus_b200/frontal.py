@@ -159,6 +159,7 @@ def _flops_of(struct, dims):
     return fl
 
 
+STRIPE = 32                          # rows of the update matrix produced at a time by the shared-memory kernel (thb_front.cu FRONT_STRIPE)
 SMALL_SMEM_LIMIT = 220 * 1024
 SMEM_BUCKETS = (27 * 1024, 36 * 1024, 55 * 1024, 74 * 1024, 112 * 1024)   # 8, 6, 4, 3, 2 CTAs per SM (227 KB usable), then 1
 
@@ -195,7 +196,7 @@ class FrontPlan:
     perm: np.ndarray           # [n] perm[p] = original scalar column of permuted scalar p
     S: int
     arrays: Dict[str, np.ndarray]   # flat per-front arrays consumed by the kernels (see build_front_plan)
-    launches: np.ndarray       # [num_launches, 10] int64, thb200.h THB_FRONT_LAUNCH_COLS; depth descending
+    launches: np.ndarray       # [num_launches, 12] int64, thb200.h THB_FRONT_LAUNCH_COLS; depth descending
     data_size: int             # doubles of one item's factor storage (sum of panels)
     arena_size: int            # doubles of one item's update-matrix arena (one parity)
     varena_size: int           # doubles of one item's border-vector arena (one parity)
@@ -422,6 +423,24 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
             racc += len(loc)
         rel_ptr[t + 1] = racc
     f_rel = np.concatenate(rel_list).astype(np.int32) if rel_list else np.zeros(0, dtype=np.int32)
+    # what the kernels would otherwise binary-search in global memory, per child front t of parent p:
+    #   c_jw[t]  = number of t's border rows that are PIVOTS of p (rel < w_p);
+    #   c_sp[c_sp_ptr[t] + s] = first border row of t whose image lies at or after border row 32 s of p (stripe pointers)
+    c_jw = np.zeros(S, dtype=np.int32)
+    c_sp_ptr = np.zeros(S + 1, dtype=np.int64)
+    c_sp_list: List[np.ndarray] = []
+    acc = 0
+    for t in range(S):
+        p = int(f_parent[t])
+        if p >= 0:
+            rel = f_rel[rel_ptr[t]:rel_ptr[t + 1]]
+            c_jw[t] = int(np.searchsorted(rel, int(f_w[p])))
+            ns = -(-int(f_b[p]) // STRIPE) + 1
+            sp = np.searchsorted(rel, int(f_w[p]) + STRIPE * np.arange(ns)).astype(np.int32)
+            c_sp_list.append(sp)
+            acc += ns
+        c_sp_ptr[t + 1] = acc
+    c_sp = np.concatenate(c_sp_list).astype(np.int32) if c_sp_list else np.zeros(1, dtype=np.int32)
     rows_ptr = np.zeros(S + 1, dtype=np.int64)
     rows_ptr[1:] = np.cumsum(f_b)
     f_rows = np.concatenate(border_rows).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
@@ -445,11 +464,11 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
             while j < S and int(f_depth[sched[j]]) == d and int(f_class[sched[j]]) == c and int(f_bucket[sched[j]]) == bk:
                 j += 1
             smem = max(small_smem_bytes(int(f_w[q]), int(f_b[q])) for q in sched[i:j])
-            launches.append((d, c, i, j - i, smem, max(int(f_r[q]) for q in sched[i:j]), 0, 0, 0, 0))
+            launches.append((d, c, i, j - i, smem, max(int(f_r[q]) for q in sched[i:j]), 0, 0, 0, 0, 0, 0))
         else:   # one front: (.., np, pivot block columns, offset of F in the arena, first pivot [info base], front index)
-            launches.append((d, c, i, 1, 0, int(f_np[t]), int(f_wpad[t]) // BIG_TW, int(f_fr_off[t]), int(f_first[t]), t))
+            launches.append((d, c, i, 1, 0, int(f_np[t]), int(f_wpad[t]) // BIG_TW, int(f_fr_off[t]), int(f_first[t]), t, int(f_w[t]), int(f_b[t])))
         i = j
-    launches = np.array(launches, dtype=np.int64).reshape(-1, 10)
+    launches = np.array(launches, dtype=np.int64).reshape(-1, 12)
     flops = float(sum(_front_cost(float(f_w[t]), float(f_b[t])) for t in range(S)))
     stats = dict(ordering=oname, column_flops=col_flops, flops=flops, nnz_L=float(sum(int(f_r[t]) * int(f_w[t]) for t in range(S))),
                  fronts=float(S), max_front=float(f_r.max()) if S else 0.0, depth=float(max_depth + 1), big_fronts=float((f_class == 3).sum()),
@@ -458,7 +477,7 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     arrays = dict(f_w=f_w, f_b=f_b, f_first=f_first, f_parent=f_parent, f_depth=f_depth, f_class=f_class, f_panel_off=f_panel_off,
                   f_wpad=f_wpad, f_np=f_np, f_cb_off=f_cb_off, f_cb_ld=f_cb_ld, f_fr_off=f_fr_off, f_u_off=f_u_off,
                   child_ptr=child_ptr, child_list=np.array(child_list, dtype=np.int32), rel_ptr=rel_ptr, f_rel=f_rel,
-                  rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32))
+                  rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32), c_jw=c_jw, c_sp_ptr=c_sp_ptr, c_sp=c_sp)
     return FrontPlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, pstart=pstart, col_start=col_start, perm=perm, S=S,
                      arrays=arrays, launches=launches, data_size=int(data_size), arena_size=int(arena_size), varena_size=int(varena_size),
                      stats=stats, front_of_pos=front_of_pos, border_rows=border_rows)

@@ -493,6 +493,12 @@ class NonlinearLeastSquares:
         if self._objectives_version != self.objective._structure_version:
             raise RuntimeError("The objective was modified after optimizer construction, which is currently not supported.")
         kwargs.pop("__FROM_THESEUS_LAYER_TOKEN__", None)
+        dev = self.objective.device
+        if isinstance(dev, torch.device) and dev.type == "cuda" and torch.cuda.is_available():
+            # the kernels are enqueued on torch's current stream OF THE CURRENT DEVICE: make the objective's device current for the call
+            # (an objective on cuda:1 while cuda:0 is current would otherwise launch into the wrong context)
+            with torch.cuda.device(dev):
+                return self._optimize_impl(**kwargs)
         return self._optimize_impl(**kwargs)
 
     # ---- bookkeeping (nonlinear_optimizer.py:109-213) ----

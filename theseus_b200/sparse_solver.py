@@ -76,7 +76,7 @@ class BaspachoSparseSolver(LinearSolver):
         if self._layout == "front":
             # multifrontal layout: own ordering (nested dissection / minimum degree, whichever costs fewer flops) and fronts
             self._plan = build_front_plan(param_size, ptrs, inds, ordering="auto" if self._ordering == "mindeg" else self._ordering,
-                                          **getattr(self, "_front_options", {}))
+                                          **{k: v for k, v in getattr(self, "_front_options", {}).items() if k != "chunk"})
             self._gram_arrays = build_gram_plan(S, out_offsets=self._plan.gram_out_offsets(), pos=self._plan.pos)
             return
         self._plan = analyze(param_size, ptrs, inds, ordering=self._ordering)
@@ -168,7 +168,7 @@ class BaspachoSparseSolver(LinearSolver):
         st = _lib.FrontPlanStruct(S=P.S, n=P.n, data_size=P.data_size, arena_size=P.arena_size, varena_size=P.varena_size,
                                   **{k: dev[k].data_ptr() for k in ("f_w", "f_b", "f_first", "f_class", "f_wpad", "f_np", "f_cb_ld", "f_depth",
                                                                     "f_panel_off", "f_cb_off", "f_fr_off", "f_u_off", "child_ptr", "child_list",
-                                                                    "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm")})
+                                                                    "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp")})
         g = self._gram_arrays
         gdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in g.items() if isinstance(v, np.ndarray)}
         launches = np.ascontiguousarray(P.launches, dtype=np.int64)
@@ -183,11 +183,14 @@ class BaspachoSparseSolver(LinearSolver):
         P = self._plan
         lib = _lib.load()
         s = _lib.stream_ptr()
+        # the factor of every item stays resident ([B, data_size]: the substitutions and the backward pass need it); the update-matrix
+        # arena, the border-vector arena and the dense workspace are per CHUNK of the batch (C5: 21 MB of arena per item)
+        chunk = int(min(B, self._front_options.get("chunk", 1024)))
         if d["bufs"].get("key") != (B, "front"):
-            ws_bytes = int(lib.thb_potrf_partial_workspace_bytes(B, d["max_np"])) if d["max_np"] else 0
-            d["bufs"] = dict(key=(B, "front"), factor=torch.empty(B, P.data_size, dtype=torch.float64, device=device),
-                             arena=torch.empty(2, B, P.arena_size, dtype=torch.float64, device=device),
-                             varena=torch.empty(2, B, P.varena_size, dtype=torch.float64, device=device),
+            ws_bytes = int(lib.thb_potrf_partial_workspace_bytes(chunk, d["max_np"])) if d["max_np"] else 0
+            d["bufs"] = dict(key=(B, "front"), chunk=chunk, factor=torch.empty(B, P.data_size, dtype=torch.float64, device=device),
+                             arena=torch.empty(2, chunk, P.arena_size, dtype=torch.float64, device=device),
+                             varena=torch.empty(2, chunk, P.varena_size, dtype=torch.float64, device=device),
                              work=torch.empty(B, P.n, dtype=torch.float64, device=device),
                              ws=torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=device),
                              Atb=torch.empty(B, P.n, dtype=torch.float64, device=device),
@@ -200,22 +203,28 @@ class BaspachoSparseSolver(LinearSolver):
         _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(factor), P.data_size,
                                     _lib.ptr(Atb), None, s), "gram(front)")
         L = d["launches"]
-        _lib.check(lib.thb_front_factor_f64(C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(factor), _lib.ptr(alpha), _lib.ptr(beta),
-                                            _lib.ptr(bufs["arena"]), _lib.ptr(bufs["ws"]) if d["max_np"] else None, bufs["ws"].numel(),
-                                            _lib.ptr(info), B, s), "front_factor")
+        for c0 in range(0, B, chunk):
+            nb = min(chunk, B - c0)
+            _lib.check(lib.thb_front_factor_f64(
+                C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(factor[c0:]), _lib.ptr(alpha[c0:]) if alpha is not None else None,
+                _lib.ptr(beta[c0:]) if beta is not None else None, _lib.ptr(bufs["arena"]), _lib.ptr(bufs["ws"]) if d["max_np"] else None,
+                bufs["ws"].numel(), _lib.ptr(info[c0:]), nb, s), "front_factor")
         self._keep = (A_val, b, alpha, beta)
         return Atb
 
     def _substitute_front(self, rhs):
         d, P = self._dev, self._plan
         bufs = d["bufs"]
-        B = bufs["key"][0]
+        B, chunk = bufs["key"][0], bufs["chunk"]
         lib = _lib.load()
         rhs = rhs.contiguous()
         x = torch.empty(B, P.n, dtype=torch.float64, device=rhs.device)
         L = d["launches"]
-        _lib.check(lib.thb_front_solve_f64(C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(bufs["factor"]), _lib.ptr(rhs), _lib.ptr(x),
-                                           _lib.ptr(bufs["work"]), _lib.ptr(bufs["varena"]), B, _lib.stream_ptr()), "front_solve")
+        for c0 in range(0, B, chunk):
+            nb = min(chunk, B - c0)
+            _lib.check(lib.thb_front_solve_f64(C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(bufs["factor"][c0:]), _lib.ptr(rhs[c0:]),
+                                               _lib.ptr(x[c0:]), _lib.ptr(bufs["work"][c0:]), _lib.ptr(bufs["varena"]), nb, _lib.stream_ptr()),
+                       "front_solve")
         return x
 
     def _lane_struct(self, ln, dev, device):
