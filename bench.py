@@ -46,7 +46,7 @@ WORKLOAD = ("C5: sphere-like SE3 pose graph (50 rings x 50 = 2 500 poses, 4 949 
 C2_POSES, C2_BATCH = 256, 256
 C2_WORKLOAD = ("C2: synthetic SE3 pose-graph (pose_graph_cube shape: 256 poses, loop_closure_ratio 0.2), batch=256 per GPU (weak), "
                "LM(10 it, adaptive+ellipsoidal damping) + CholeskyDenseSolver")
-CPU_SAMPLE_ITEMS = 16
+CPU_SAMPLE_ITEMS = 32
 
 
 def _measured_peaks():
@@ -442,7 +442,7 @@ def dense_c2_leg(th, lib, _lib, device, rank, world, pg, timed, peak_tf, steps, 
     # ---- GPU-library baseline: what the reference's dense path executes on this GPU for one linear solve of the same system ----
     if rank == 0:
         try:
-            S = lin.structure()
+            S = lin.engine.structure
             m = int(S.num_rows)
             rows = torch.from_numpy(np.repeat(np.arange(m), np.diff(S.A_row_ptr))).to(device)
             cols = torch.from_numpy(np.asarray(S.A_col_ind)).to(device)

@@ -1,0 +1,93 @@
+"""The reference's known-answer tests of its native solver module, run against theseus_b200.extlib (same API):
+ * tests/theseus_tests/extlib/test_baspacho_simple.py:15-112 -- the LITERAL 12 x 12 block-sparse SPD system (params [2,3,5,2], 2 batch
+   items, add_M / factor / solve, residual < 1e-10);
+ * tests/theseus_tests/extlib/test_baspacho.py:16-150 -- random systems through add_MtM + damp (residual < 1e-10 relative)."""
+import numpy as np
+import pytest
+import torch
+from scipy.sparse import csr_matrix, tril
+
+from theseus_b200.extlib import SymbolicDecomposition
+
+pytestmark = pytest.mark.gpu
+
+# fmt: off  (values of test_baspacho_simple.py:15-57)
+mRowPtr = [0, 1, 3, 5, 8, 11, 13, 15, 17, 20, 23, 25, 27]
+mColInd = [0,  0, 1,  1, 2,  0, 2, 3,  1, 3, 4,  2, 5,  3, 6,  4, 7,  2, 3, 8,  3, 4, 9,  1, 10,  0, 11]
+mVals = [[3,  .2, 3,  -.4, 3,  -.7, -1, 3,  .7, -1, 3,  .5, 3,  -1, 3,  1, 3,  -.3, .6, 3,  .3, -.2, 3,  1, 3,  -.4, 3],
+         [5,  .4, 5,  1, 5,  .7, -1, 5,  1, 3, 5,  -.8, 5,  -1, 5,  1, 5,  .7, -1, 5,  .3, .4, 5,  1, 5,  .8, 5]]
+bData = [[1, 2, 3, -2, -1, -3, 0, 4, -4, 1, 2, 3], [-5, -4, -3, -2, -1, 0, 1, 2, 3, 4, 5, 6]]
+# fmt: on
+
+
+def test_baspacho_simple_literal_system():
+    param_sizes = torch.tensor([2, 3, 5, 2], dtype=torch.int64)
+    ss_inds = torch.tensor([0, 0, 1, 1, 2, 0, 3], dtype=torch.int64)
+    ss_ptrs = torch.tensor([0, 1, 3, 5, 7], dtype=torch.int64)
+    s = SymbolicDecomposition(param_sizes, ss_ptrs, ss_inds, "cuda")
+    f = s.create_numeric_decomposition(2)
+    ms = [csr_matrix((val, mColInd, mRowPtr), (12, 12)) for val in mVals]
+    mFulls = [tril(m, -1).transpose().tocsr() + m for m in ms]
+    f.add_M(torch.tensor(mVals, dtype=torch.double).cuda(), torch.tensor(mRowPtr, dtype=torch.int64).cuda(), torch.tensor(mColInd, dtype=torch.int64).cuda())
+    f.factor()
+    b = torch.tensor(bData, dtype=torch.double)
+    x = b.clone().cuda()
+    f.solve(x)
+    x = x.cpu()
+    Mx = torch.tensor(np.array([mFulls[i] @ x[i].numpy() for i in range(2)]), dtype=torch.double)
+    residuals = b - Mx
+    assert all(np.linalg.norm(res) < 1e-10 for res in residuals.numpy())
+    for i in range(2):
+        np.testing.assert_allclose(x[i].numpy(), np.linalg.solve(mFulls[i].toarray(), np.array(bData[i], dtype=float)), rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("B,rows,cols,ps,fill", [(3, 50, 40, (2, 6), 0.1), (5, 80, 30, (1, 4), 0.08)])
+def test_add_mtm_damp_factor_solve_random(B, rows, cols, ps, fill):
+    """The flow of test_baspacho.py:check_baspacho: random M [rows x cols] with a block column structure, AtA = M^T M via add_MtM,
+    damp(alpha, beta), factor, solve; residual of (M^T M (1 + alpha on diag) + beta I) x = b."""
+    rng = np.random.default_rng(B + rows)
+    sizes = []
+    while sum(sizes) < cols:
+        sizes.append(int(rng.integers(*ps)))
+    sizes[-1] -= sum(sizes) - cols
+    if sizes[-1] <= 0:
+        sizes.pop(); sizes[-1] += cols - sum(sizes)
+    N = len(sizes)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    blocks_of_row = []
+    for _ in range(rows):
+        bl = [k for k in range(N) if rng.random() < fill] or [int(rng.integers(N))]
+        blocks_of_row.append(bl)
+    ptr, ind = [0], []
+    for bl in blocks_of_row:
+        for k in bl:
+            ind.extend(range(starts[k], starts[k + 1]))
+        ptr.append(len(ind))
+    ptr, ind = np.array(ptr, dtype=np.int64), np.array(ind, dtype=np.int64)
+    val = rng.standard_normal((B, len(ind)))
+    Ms = [csr_matrix((val[i], ind, ptr), (rows, cols)) for i in range(B)]
+    pat = (abs(Ms[0]).T @ abs(Ms[0])).tocsr()
+    to_block = np.repeat(np.arange(N), sizes)
+    bp = [set() for _ in range(N)]
+    for r in range(cols):
+        for c in pat.indices[pat.indptr[r]:pat.indptr[r + 1]]:
+            bp[to_block[r]].add(int(to_block[c]))
+    for k in range(N):
+        bp[k].add(k)
+    bptr = np.concatenate([[0], np.cumsum([len(x) for x in bp])]).astype(np.int64)
+    binds = np.array([c for x in bp for c in sorted(x)], dtype=np.int64)
+    s = SymbolicDecomposition(torch.tensor(sizes, dtype=torch.int64), torch.from_numpy(bptr), torch.from_numpy(binds), "cuda")
+    f = s.create_numeric_decomposition(B)
+    f.add_MtM(torch.from_numpy(val).cuda(), torch.from_numpy(ptr).cuda(), torch.from_numpy(ind).cuda())
+    alpha, beta = rng.random(B) * 0.3, rng.random(B) * 0.2 + 0.05
+    f.damp(torch.from_numpy(alpha).cuda(), torch.from_numpy(beta).cuda())
+    f.factor()
+    b = rng.standard_normal((B, cols))
+    x = torch.from_numpy(b.copy()).cuda()
+    f.solve(x)
+    x = x.cpu().numpy()
+    for i in range(B):
+        AtA = (Ms[i].T @ Ms[i]).toarray()
+        AtA[np.arange(cols), np.arange(cols)] = AtA.diagonal() * (1 + alpha[i]) + beta[i]
+        res = AtA @ x[i] - b[i]
+        assert np.linalg.norm(res) < 1e-10 * max(1.0, np.linalg.norm(b[i]) * np.linalg.cond(AtA) ** 0.5), np.linalg.norm(res)

@@ -66,9 +66,9 @@ struct FrontArgs {
 constexpr int FRONT_STRIPE = 32;
 constexpr int FRONT_WD_LD = 20;
 
-__host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b) {
+__host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b, int sr) {
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
-  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + (int64_t)FRONT_STRIPE * front_pad_ld(b16) + 2;
+  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + (int64_t)sr * front_pad_ld(b16) + 2;
 }
 
 // One warp: Cholesky of the 8 x 8 block at T (row stride ld; lower part read, L written in place) and its inverse (full 8 x 8, zeros
@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   const int prow = w8 + b16 + 8;
   double* PN = sm;                          // [prow][ldp]
   double* Wd = PN + prow * ldp;             // [8][FRONT_WD_LD]
-  double* ST = Wd + 8 * FRONT_WD_LD;        // [FRONT_STRIPE][ldc]
+  double* ST = Wd + 8 * FRONT_WD_LD;        // [sr][ldc]
+  const int sr = p.f_sr[t];                 // stripe height of this front: a multiple of 32 (frontal.py: as much of the update matrix as the
+                                            // launch's shared-memory budget holds -- every stripe costs one round of global-memory latency)
   for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
   __syncthreads();
   if (tid < w8 - w) PN[(w + tid) * ldp + w + tid] = 1.0;   // identity on the padding of the pivot block
@@ -163,16 +165,19 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
     const int32_t* rel = p.f_rel + p.rel_ptr[c];
     const int jw = p.c_jw[c];   // first child row whose image is a border row of this front (rel is increasing)
     if (jw > 0) {
-      for (int i = warp; i < bc; i += NW) {
+      // every target row belongs to ONE warp for all children: no barrier between children, the children still add in list order
+      for (int i = 0; i < bc; i++) {
         const int ri = rel[i];
         const int prw = ri < w ? ri : ri + (w8 - w);
+        if ((prw % NW) != warp) continue;
         const double* srow = src + (int64_t)i * ldg;
         const int jend = i < jw ? i + 1 : jw;
         for (int j = lane; j < jend; j += 32) PN[prw * ldp + rel[j]] += srow[j];
       }
-      __syncthreads();
     }
+    __syncwarp();   // two children may reach one target through different lanes of the owning warp: keep the children ordered
   }
+  __syncthreads();
   // ---- blocked left-looking factorisation of the panel, 8 columns at a time ----
   const int nbk = w8 / 8, nrt = (w8 + b16) / 8;
   for (int jb = 0; jb < nbk; jb++) {
@@ -234,54 +239,57 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   double* dst = a.arena_cur + item * p.arena_size + p.f_cb_off[t];
   const int ldg_out = p.f_cb_ld[t];
   const double* P = PN + w8 * ldp;
-  for (int s0 = 0; s0 < b; s0 += FRONT_STRIPE) {
-    for (int e = tid; e < FRONT_STRIPE * ldc; e += THREADS) ST[e] = 0.0;
+  const int nsp = (b + FRONT_STRIPE - 1) / FRONT_STRIPE;   // stripe pointers exist for rows 0, 32, ..., 32 nsp
+  for (int s0 = 0; s0 < b; s0 += sr) {
+    const int rows_here = min(sr, b - s0);
+    for (int e = tid; e < rows_here * ldc; e += THREADS) ST[e] = 0.0;
+    for (int e = rows_here * ldc + tid; e < min(sr, ((rows_here + 15) & ~15)) * ldc; e += THREADS) ST[e] = 0.0;
     __syncthreads();
     for (int ci = c_begin; ci < c_end; ci++) {
       const int c = p.child_list[ci];
       const int ldg = p.f_cb_ld[c];
       const int32_t* rel = p.f_rel + p.rel_ptr[c];
-      const int32_t* sp = p.c_sp + p.c_sp_ptr[c] + s0 / FRONT_STRIPE;   // precomputed stripe pointers (frontal.py)
-      const int i0 = sp[0], i1 = sp[1];
+      const int32_t* sp = p.c_sp + p.c_sp_ptr[c];   // precomputed stripe pointers at 32-row granularity (frontal.py)
+      const int i0 = sp[s0 / FRONT_STRIPE], i1 = sp[min((s0 + sr) / FRONT_STRIPE, nsp)];
       if (i1 > i0) {      // uniform across the CTA
         const int jw = p.c_jw[c];
         const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
-        for (int i = i0 + warp; i < i1; i += NW) {
+        for (int i = i0; i < i1; i++) {     // stripe rows are owned by warps (row % NW): no barrier between children
           const int ri = rel[i] - w - s0;
+          if ((ri % NW) != warp) continue;
           const double* srow = src + (int64_t)i * ldg;
           for (int j = jw + lane; j <= i; j += 32) ST[ri * ldc + rel[j] - w] += srow[j];
         }
-        __syncthreads();
       }
-    }
-    // 16 x 16 macro tiles of the two macro rows of this stripe that lie in the lower triangle
-    const int R0 = s0 / 16;
-    const int n0 = R0 + 1, n1 = (s0 + 16 < b16) ? R0 + 2 : 0;
-    for (int q = warp; q < n0 + n1; q += NW) {
-      const int mr = q < n0 ? 0 : 1;
-      const int ct = q < n0 ? q : q - n0;
-      double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-      const double* Pa = P + (16 * (R0 + mr) + lr) * ldp + lc;
-      const double* Pb = P + (16 * ct + lr) * ldp + lc;
-      for (int k4 = 0; k4 < w8; k4 += 4) {
-        const double a0 = Pa[k4], a1 = Pa[8 * ldp + k4];
-        const double b0 = Pb[k4], b1 = Pb[8 * ldp + k4];
-        front_mma884(acc[0][0][0], acc[0][0][1], a0, b0);
-        front_mma884(acc[0][1][0], acc[0][1][1], a0, b1);
-        front_mma884(acc[1][0][0], acc[1][0][1], a1, b0);
-        front_mma884(acc[1][1][0], acc[1][1][1], a1, b1);
-      }
-#pragma unroll
-      for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-        for (int ni = 0; ni < 2; ni++) {
-          double* d = ST + (16 * mr + 8 * mi + lr) * ldc + 16 * ct + 8 * ni + 2 * lc;
-          d[0] -= acc[mi][ni][0];
-          d[1] -= acc[mi][ni][1];
-        }
+      __syncwarp();   // (same: children ordered inside the owning warp)
     }
     __syncthreads();
-    const int rows_here = min(FRONT_STRIPE, b - s0);
+    // 16 x 16 macro tiles of this stripe's macro rows that lie in the lower triangle
+    const int R0 = s0 / 16, R1 = min((s0 + sr) / 16, b16 / 16);
+    for (int R = R0; R < R1; R++) {
+      for (int ct = warp; ct <= R; ct += NW) {
+        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+        const double* Pa = P + (16 * R + lr) * ldp + lc;
+        const double* Pb = P + (16 * ct + lr) * ldp + lc;
+        for (int k4 = 0; k4 < w8; k4 += 4) {
+          const double a0 = Pa[k4], a1 = Pa[8 * ldp + k4];
+          const double b0 = Pb[k4], b1 = Pb[8 * ldp + k4];
+          front_mma884(acc[0][0][0], acc[0][0][1], a0, b0);
+          front_mma884(acc[0][1][0], acc[0][1][1], a0, b1);
+          front_mma884(acc[1][0][0], acc[1][0][1], a1, b0);
+          front_mma884(acc[1][1][0], acc[1][1][1], a1, b1);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 2; ni++) {
+            double* d = ST + (16 * (R - R0) + 8 * mi + lr) * ldc + 16 * ct + 8 * ni + 2 * lc;
+            d[0] -= acc[mi][ni][0];
+            d[1] -= acc[mi][ni][1];
+          }
+      }
+    }
+    __syncthreads();
     for (int i = warp; i < rows_here; i += NW) {
       double* drow = dst + (int64_t)(s0 + i) * ldg_out;
       for (int j = lane; j <= s0 + i; j += 32) drow[j] = ST[i * ldc + j];
@@ -523,7 +531,7 @@ static inline int front_set_smem(K kernel, size_t bytes, size_t* cache) {
 
 extern "C" {
 
-int64_t thb_front_small_smem_bytes(int32_t w, int32_t b) { return thb::front_smem_doubles(w, b) * 8; }
+int64_t thb_front_small_smem_bytes(int32_t w, int32_t b, int32_t stripe_rows) { return thb::front_smem_doubles(w, b, stripe_rows) * 8; }
 
 int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* alpha,
                          const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes, int32_t* info, int64_t B,

@@ -161,6 +161,8 @@ def _flops_of(struct, dims):
 
 STRIPE = 32                          # rows of the update matrix produced at a time by the shared-memory kernel (thb_front.cu FRONT_STRIPE)
 SMALL_SMEM_LIMIT = 220 * 1024
+STRIPE_MAX_ROWS = None              # tests: cap the stripe height (a multiple of 32) to exercise the multi-stripe path on small fronts
+STRIPE_BUDGET = int(__import__("os").environ.get("THB_FRONT_STRIPE_BUDGET_KB", "110")) * 1024
 SMEM_BUCKETS = (27 * 1024, 36 * 1024, 55 * 1024, 74 * 1024, 112 * 1024)   # 8, 6, 4, 3, 2 CTAs per SM (227 KB usable), then 1
 
 
@@ -168,11 +170,25 @@ def _pad_ld(x: int) -> int:
     return ((x + 11) // 16) * 16 + 4
 
 
-def small_smem_bytes(w: int, b: int) -> int:
+def small_smem_bytes(w: int, b: int, sr: Optional[int] = None) -> int:
     """Dynamic shared memory of front_small_kernel for a front (thb_front.cu: front_smem_doubles): padded panel + inverse of one 8 x 8
-    diagonal block + one 32-row stripe of the update matrix."""
-    b16, w4, w8 = (b + 15) & ~15, (w + 3) & ~3, (w + 7) & ~7
-    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 32 * _pad_ld(b16) + 2) * 8
+    diagonal block + one stripe (sr rows; default: stripe_rows(w, b)) of the update matrix."""
+    b16, w8 = (b + 15) & ~15, (w + 7) & ~7
+    sr = stripe_rows(w, b) if sr is None else sr
+    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + sr * _pad_ld(b16) + 2) * 8
+
+
+def stripe_rows(w: int, b: int) -> int:
+    """Rows of the update matrix produced at a time: every stripe costs a round of global-memory latency for the children's
+    contributions, so as many rows as a shared-memory budget holds -- the whole matrix for small fronts (<= STRIPE_BUDGET keeps two
+    CTAs per SM), at least 32 rows for the largest."""
+    b16, w8 = (b + 15) & ~15, (w + 7) & ~7
+    base = ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 2) * 8
+    per_row = _pad_ld(b16) * 8
+    full = max(STRIPE, -(-b // STRIPE) * STRIPE)
+    limit = STRIPE_BUDGET if base + STRIPE * per_row <= STRIPE_BUDGET else SMALL_SMEM_LIMIT
+    sr = int(min(full, max(STRIPE, (limit - base) // per_row // STRIPE * STRIPE)))
+    return min(sr, STRIPE_MAX_ROWS) if STRIPE_MAX_ROWS else sr
 
 
 SMALL_MAX_W = 192    # pivot block columns of 8 are factored one after the other inside the CTA: wider pivot blocks go to the dense kernel
@@ -477,7 +493,8 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     arrays = dict(f_w=f_w, f_b=f_b, f_first=f_first, f_parent=f_parent, f_depth=f_depth, f_class=f_class, f_panel_off=f_panel_off,
                   f_wpad=f_wpad, f_np=f_np, f_cb_off=f_cb_off, f_cb_ld=f_cb_ld, f_fr_off=f_fr_off, f_u_off=f_u_off,
                   child_ptr=child_ptr, child_list=np.array(child_list, dtype=np.int32), rel_ptr=rel_ptr, f_rel=f_rel,
-                  rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32), c_jw=c_jw, c_sp_ptr=c_sp_ptr, c_sp=c_sp)
+                  rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32), c_jw=c_jw, c_sp_ptr=c_sp_ptr, c_sp=c_sp,
+                  f_sr=np.array([stripe_rows(int(f_w[t]), int(f_b[t])) for t in range(S)], dtype=np.int32))
     return FrontPlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, pstart=pstart, col_start=col_start, perm=perm, S=S,
                      arrays=arrays, launches=launches, data_size=int(data_size), arena_size=int(arena_size), varena_size=int(varena_size),
                      stats=stats, front_of_pos=front_of_pos, border_rows=border_rows)

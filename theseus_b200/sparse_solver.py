@@ -7,6 +7,7 @@ all in fp64 like the reference (baspacho_sparse_autograd.py:41,65), result cast 
 It is also what CholmodSparseSolver / LUCudaSparseSolver map to (same linear system).
 """
 import ctypes as C
+import os
 from typing import Any, Dict, Optional, Type, Union
 
 import numpy as np
@@ -75,8 +76,12 @@ class BaspachoSparseSolver(LinearSolver):
         self.param_size, self.block_ptrs, self.block_inds = param_size, ptrs, inds  # the reference's SymbolicDecomposition inputs
         if self._layout == "front":
             # multifrontal layout: own ordering (nested dissection / minimum degree, whichever costs fewer flops) and fronts
-            self._plan = build_front_plan(param_size, ptrs, inds, ordering="auto" if self._ordering == "mindeg" else self._ordering,
-                                          **{k: v for k, v in getattr(self, "_front_options", {}).items() if k != "chunk"})
+            opts = {k: v for k, v in getattr(self, "_front_options", {}).items() if k != "chunk"}
+            for env, key, cast in (("THB_FRONT_TAU", "tau", float), ("THB_FRONT_MERGE_FLOPS", "merge_flops", float),
+                                   ("THB_FRONT_MERGE_MAX_R", "merge_max_r", int)):      # tuning knobs of the amalgamation (experiments)
+                if env in os.environ and key not in opts:
+                    opts[key] = cast(os.environ[env])
+            self._plan = build_front_plan(param_size, ptrs, inds, ordering="auto" if self._ordering == "mindeg" else self._ordering, **opts)
             self._gram_arrays = build_gram_plan(S, out_offsets=self._plan.gram_out_offsets(), pos=self._plan.pos)
             return
         self._plan = analyze(param_size, ptrs, inds, ordering=self._ordering)
@@ -168,7 +173,7 @@ class BaspachoSparseSolver(LinearSolver):
         st = _lib.FrontPlanStruct(S=P.S, n=P.n, data_size=P.data_size, arena_size=P.arena_size, varena_size=P.varena_size,
                                   **{k: dev[k].data_ptr() for k in ("f_w", "f_b", "f_first", "f_class", "f_wpad", "f_np", "f_cb_ld", "f_depth",
                                                                     "f_panel_off", "f_cb_off", "f_fr_off", "f_u_off", "child_ptr", "child_list",
-                                                                    "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp")})
+                                                                    "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "f_sr")})
         g = self._gram_arrays
         gdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in g.items() if isinstance(v, np.ndarray)}
         launches = np.ascontiguousarray(P.launches, dtype=np.int64)
