@@ -449,12 +449,14 @@ typedef struct thb_front_plan {
   /* per CHILD front t of parent p: c_jw[t] = number of t's border rows that are pivots of p; c_sp[c_sp_ptr[t] + s] = first border row
    * of t whose image lies at or after border row 32 s of p (s = 0 .. ceil(b_p / 32)): what the kernels would otherwise binary-search */
   const int32_t* c_jw; const int64_t* c_sp_ptr; const int32_t* c_sp;
-  const int32_t* f_sr;   /* [S] rows of the update matrix the shared-memory kernel produces at a time for front t (a multiple of 32) */
+  /* per CHILD front t of parent p: c_inv[c_inv_ptr[t] + l] = border row of t whose image is row l of p's front (l < r_p), or -1:
+   * the shared-memory kernel GATHERS the children's update matrices through it (no scatter, no barriers) */
+  const int64_t* c_inv_ptr; const int32_t* c_inv;
 } thb_front_plan;
 
 #define THB_FRONT_LAUNCH_COLS 12
-/* dynamic shared memory (bytes) the shared-memory factor kernel needs for a front with w pivots, b border rows and a stripe height */
-int64_t thb_front_small_smem_bytes(int32_t w, int32_t b, int32_t stripe_rows);
+/* dynamic shared memory (bytes) the shared-memory factor kernel needs for a front with w pivots and b border rows (the panel) */
+int64_t thb_front_small_smem_bytes(int32_t w, int32_t b);
 /* factor: in-place on `factor` [B, data_size] (AtA + fill-in zeros in, L out); dense_ws: workspace of
  * thb_potrf_partial_workspace_bytes(B, max np) bytes (may be NULL when there is no class-3 front);
  * info[b] = 0 or 1 + permuted index of a non-positive pivot (cleared here). */

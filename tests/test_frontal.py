@@ -156,9 +156,9 @@ def test_front_kernels_on_the_host_emulation(monkeypatch, emulated, case):
         dims = [6, 3, 6, 2, 1, 6, 3, 3, 6, 6, 2, 6]
         S, B = _ring_structure(len(dims), dims, chord=5), 2
     else:
-        P_, Cn, B = 30, 8, 2
+        P_, Cn, B = 8, 4, 2          # (<= 8 children per front: more go to the dense path's scatter assembly, which needs the device)
         dims = [6] * Cn + [3] * P_
-        costs = [(2, sorted([int(c), Cn + p])) for p in range(P_) for c in rng.choice(Cn, size=4, replace=False)]
+        costs = [(2, sorted([int(c), Cn + p])) for p in range(P_) for c in rng.choice(Cn, size=3, replace=False)]
         costs += [(dims[i], [i]) for i in range(len(dims))]
         S = build_structure(dims, costs)
     A_val = rng.standard_normal((B, S.nnz)); b = rng.standard_normal((B, S.num_rows)); alpha = rng.random(B) * 0.1
@@ -196,18 +196,3 @@ def test_front_solver_processes_the_batch_in_chunks(monkeypatch, emulated):
     solver, x2 = _solve(monkeypatch, emulated, S, A_val, b, alpha, front_options=dict(chunk=2))
     assert solver._dev["bufs"]["arena"].shape[1] == 2
     assert np.array_equal(x1, x2)
-
-
-def test_update_matrix_in_several_stripes_on_the_emulation(monkeypatch, emulated):
-    """A capped stripe height forces the update matrices of the 48- and 60-row fronts to be produced in 32-row stripes (the path the large
-    fronts of config C5 take on the device): same solution as with whole-matrix stripes."""
-    import theseus_b200.frontal as frontal
-    rng = np.random.default_rng(21)
-    S, B = _ring_structure(40), 2
-    A_val = rng.standard_normal((B, S.nnz)); b = rng.standard_normal((B, S.num_rows)); alpha = rng.random(B) * 0.1
-    _, x_full = _solve(monkeypatch, emulated, S, A_val, b, alpha)
-    monkeypatch.setattr(frontal, "STRIPE_MAX_ROWS", 32)
-    solver, x_str = _solve(monkeypatch, emulated, S, A_val, b, alpha)
-    A = solver._plan.arrays
-    assert ((A["f_sr"] < A["f_b"]) & (A["f_class"] < 3)).any()
-    assert np.abs(x_full - x_str).max() <= 1e-12 * np.abs(x_full).max()

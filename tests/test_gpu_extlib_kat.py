@@ -91,3 +91,28 @@ def test_add_mtm_damp_factor_solve_random(B, rows, cols, ps, fill):
         AtA[np.arange(cols), np.arange(cols)] = AtA.diagonal() * (1 + alpha[i]) + beta[i]
         res = AtA @ x[i] - b[i]
         assert np.linalg.norm(res) < 1e-10 * max(1.0, np.linalg.norm(b[i]) * np.linalg.cond(AtA) ** 0.5), np.linalg.norm(res)
+
+
+@pytest.mark.parametrize("layout", ["front", "lane"])
+def test_float64_is_used_on_the_reference_bad_sparse_matrix(layout):
+    """tests/theseus_tests/optimizer/autograd/test_sparse_backward.py:65-76 (test_float64_used): the reference ships a float32 system
+    (bad_sparse_matrix.pth: 101 220 x 34 500, 1.2 M non-zeros, damping 1e-6) whose solution is < 1 in magnitude only if the sparse solve
+    runs in float64 (> 100 otherwise).  tests/golden/bad_sparse_matrix_kat.npz holds its values and block structure (make_golden-style
+    extraction in the build container; the CSR pattern rebuilt here is bit-identical to the pickled SparseStructure) and the float64
+    SuperLU solution of the same damped system."""
+    import theseus_b200 as th
+    from theseus_b200.structure import build_structure
+    from helpers import load
+    g = load("bad_sparse_matrix_kat")
+    nv = int(g["num_vars"])
+    costs = [(int(d), [int(v) for v in vs if v >= 0]) for d, vs in zip(g["cost_dim"], g["cost_vars"])]
+    S = build_structure([6] * nv, costs)
+    assert S.nnz == g["a"].shape[0] and S.num_rows == g["b"].shape[0]
+    solver = th.BaspachoSparseSolver.from_structure(S, layout=layout)
+    solver.linearization.A_val = torch.from_numpy(g["a"]).view(1, -1).cuda()        # float32, like the reference's file
+    solver.linearization.b = torch.from_numpy(g["b"]).view(1, -1).cuda()
+    delta = solver.solve(damping=1e-6, ellipsoidal_damping=False)
+    assert delta.dtype == torch.float32                                              # cast back (baspacho_sparse_autograd.py:65)
+    assert float(delta.abs().max()) < 1.0
+    ref = g["delta_fp64_scipy"]
+    assert np.abs(delta.double().cpu().numpy()[0] - ref).max() <= 1e-4 * np.abs(ref).max()

@@ -158,3 +158,19 @@ def test_c5_full_size_lm_trace_front():
     for it in range(decisive_iterations(g["err0"], g["trace_err"])):
         rel = np.linalg.norm(deltas[it] - g["trace_delta"][it], axis=1) / np.linalg.norm(g["trace_delta"][it], axis=1)
         assert rel.max() < 1e-5, (it, rel)
+
+
+def test_front_with_many_children_takes_the_scatter_assembly():
+    """Bundle-adjustment-like structure: 60 points (3 dof) seen by 4 of 10 cameras (6 dof): the camera front has dozens of children --
+    more than the gather kernel keeps in registers -- so it is assembled by the dense path's scatter kernel and factored by the partial
+    DMMA kernel; min-degree ordering wins (points first)."""
+    rng = np.random.default_rng(5)
+    P_, Cn = 60, 10
+    dims = [6] * Cn + [3] * P_
+    costs = [(2, sorted([int(c), Cn + p])) for p in range(P_) for c in rng.choice(Cn, size=4, replace=False)]
+    costs += [(dims[i], [i]) for i in range(len(dims))]
+    S = build_structure(dims, costs)
+    solver, _, _ = _check(S, 9, 3)
+    A = solver._plan.arrays
+    nchild = np.diff(A["child_ptr"])
+    assert (A["f_class"][nchild > 8] == 3).all() and (nchild > 8).any()

@@ -50,7 +50,8 @@ def test_dense_linearization_routes_dense_jacobians_to_the_tma_kernel(monkeypatc
         x = th.Vector(tensor=torch.linspace(-1, 1, B * n, dtype=torch.float64).view(B, n).cuda(), name="x")
         Wv = th.Variable(W.unsqueeze(0), name="W")
         objective = th.Objective(dtype=torch.float64)
-        objective.add(th.AutoDiffCostFunction([x], err_fn, m, aux_vars=[Wv], name="dense_cost"))
+        cw = th.ScaleCostWeight(torch.tensor(1.0, dtype=torch.float64).cuda())
+        objective.add(th.AutoDiffCostFunction([x], err_fn, m, cost_weight=cw, aux_vars=[Wv], name="dense_cost"))
         objective.to("cuda")
         lin = th.DenseLinearization(objective)
         l0 = _lib.total_launches()

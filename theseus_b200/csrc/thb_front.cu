@@ -55,20 +55,23 @@ struct FrontArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ fronts in shared memory
-// One CTA per (front, item).  Shared memory: PN [w8 + b16 + 8][ldp] = the panel: pivot rows, identity padding up to w8 = w rounded
-// to 8, the border rows from row w8 on (b16 = b rounded to 16, zero padding), Wd [8][20] = inverse of the current 8 x 8 diagonal block,
-// ST [32][ldc] = one 32-row stripe of the update matrix.
-//   1. panel <- AtA entries (+ damping) + the children's entries that land in the pivot columns
+// One CTA per (front, item).  Shared memory holds ONLY the panel: PN [w8 + b16 + 8][ldp] = pivot rows, identity padding up to w8 = w
+// rounded to 8, the border rows from row w8 on (b16 = b rounded to 16, zero padding), and Wd [8][20] = the inverse of the current
+// 8 x 8 diagonal block.  The update matrix never exists on chip.
+//   1. panel <- AtA entries (+ damping) + GATHERED children: element (i, j) adds child c's update-matrix entry (inv_c[i], inv_c[j])
+//      where inv_c maps this front's rows to the child's border rows (-1: none).  No scatter, no barrier between children, every
+//      load independent (the latency of all of them overlaps); the children are added in list order: deterministic.
 //   2. blocked LEFT-LOOKING factorisation over 8-column blocks: warp 0 forms the diagonal block (DMMA), factors and inverts it in
 //      registers (shuffles); every warp then finishes 16-row tiles of that block column: X = A - sum_k L_ik L_jk^T, L_ij = X W^T,
-//      both products on the FP64 tensor pipe -- the pivot block's own rows and the border rows alike (no separate TRSM, no scalar loops)
-//   3. the update matrix is never resident: per 32-row stripe, children's contributions for those rows minus P_stripe P^T (DMMA), written once.
-constexpr int FRONT_STRIPE = 32;
+//      both products on the FP64 tensor pipe -- pivot rows and border rows alike.
+//   3. update matrix: per 16 x 16 tile of the lower triangle, -P_I P_J^T by DMMA straight from the panel, plus the gathered children,
+//      written once from registers.
 constexpr int FRONT_WD_LD = 20;
+constexpr int FRONT_MAX_CHILDREN = 8;   // fronts with more children are assembled by the scatter kernel of the dense path (frontal.py)
 
-__host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b, int sr) {
+__host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b) {
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
-  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + (int64_t)sr * front_pad_ld(b16) + 2;
+  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + 2;
 }
 
 // One warp: Cholesky of the 8 x 8 block at T (row stride ld; lower part read, L written in place) and its inverse (full 8 x 8, zeros
@@ -120,6 +123,12 @@ __device__ __forceinline__ int front_leaf8(double* __restrict__ T, int ld, doubl
   return fail;
 }
 
+struct FrontChild {       // one child of the front this CTA works on (registers / local array, <= FRONT_MAX_CHILDREN)
+  const double* src;      // its update matrix for this item
+  const int32_t* inv;     // [r of this front] -> child border row or -1
+  int ldg, lo, hi;        // leading dimension; range [lo, hi] of this front's rows the child reaches
+};
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   extern __shared__ double sm[];
@@ -131,13 +140,26 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   const int t = p.sched[a.s0 + blockIdx.y];
   const int w = p.f_w[t], b = p.f_b[t], r = w + b;
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
-  const int ldp = front_pad_ld(w8), ldc = front_pad_ld(b16);
+  const int ldp = front_pad_ld(w8);
   const int prow = w8 + b16 + 8;
   double* PN = sm;                          // [prow][ldp]
   double* Wd = PN + prow * ldp;             // [8][FRONT_WD_LD]
-  double* ST = Wd + 8 * FRONT_WD_LD;        // [sr][ldc]
-  const int sr = p.f_sr[t];                 // stripe height of this front: a multiple of 32 (frontal.py: as much of the update matrix as the
-                                            // launch's shared-memory budget holds -- every stripe costs one round of global-memory latency)
+  // ---- children descriptors ----
+  const int c_begin = p.child_ptr[t];
+  const int nch = min(p.child_ptr[t + 1] - c_begin, FRONT_MAX_CHILDREN);
+  FrontChild ch[FRONT_MAX_CHILDREN];
+#pragma unroll
+  for (int q = 0; q < FRONT_MAX_CHILDREN; q++) {
+    if (q < nch) {
+      const int c = p.child_list[c_begin + q];
+      ch[q].src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
+      ch[q].inv = p.c_inv + p.c_inv_ptr[c];
+      ch[q].ldg = p.f_cb_ld[c];
+      const int32_t* rel = p.f_rel + p.rel_ptr[c];
+      ch[q].lo = rel[0];
+      ch[q].hi = rel[p.f_b[c] - 1];
+    }
+  }
   for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
   __syncthreads();
   if (tid < w8 - w) PN[(w + tid) * ldp + w + tid] = 1.0;   // identity on the padding of the pivot block
@@ -148,34 +170,21 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
     int i = tid / w, j = tid - i * w;   // (i, j) of element e, advanced without a division
     const int di = THREADS / w, dj = THREADS - di * w;
     for (int e = tid; e < r * w; e += THREADS) {
-      double v = Lg[e];
-      if (i == j) v = v + (al * v + be);   // linear/utils.py:14-33: diag <- diag (1 + alpha) + beta
-      PN[(i < w ? i : i + (w8 - w)) * ldp + j] = v;
+      if (j <= i) {                      // lower triangle of the pivot block, all of the border rows
+        double v = Lg[e];
+        if (i == j) v = v + (al * v + be);   // linear/utils.py:14-33: diag <- diag (1 + alpha) + beta
+#pragma unroll
+        for (int q = 0; q < FRONT_MAX_CHILDREN; q++) {
+          if (q < nch && i >= ch[q].lo && j <= ch[q].hi) {
+            const int ci = ch[q].inv[i], cj = ch[q].inv[j];
+            if (ci >= 0 && cj >= 0) v += ch[q].src[(int64_t)ci * ch[q].ldg + cj];
+          }
+        }
+        PN[(i < w ? i : i + (w8 - w)) * ldp + j] = v;
+      }
       i += di; j += dj;
       if (j >= w) { j -= w; i++; }
     }
-  }
-  __syncthreads();
-  // ---- children, part 1: the entries that land in the pivot columns (rel[j] < w); fixed child order ----
-  const int c_begin = p.child_ptr[t], c_end = p.child_ptr[t + 1];
-  for (int ci = c_begin; ci < c_end; ci++) {
-    const int c = p.child_list[ci];
-    const int bc = p.f_b[c], ldg = p.f_cb_ld[c];
-    const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
-    const int32_t* rel = p.f_rel + p.rel_ptr[c];
-    const int jw = p.c_jw[c];   // first child row whose image is a border row of this front (rel is increasing)
-    if (jw > 0) {
-      // every target row belongs to ONE warp for all children: no barrier between children, the children still add in list order
-      for (int i = 0; i < bc; i++) {
-        const int ri = rel[i];
-        const int prw = ri < w ? ri : ri + (w8 - w);
-        if ((prw % NW) != warp) continue;
-        const double* srow = src + (int64_t)i * ldg;
-        const int jend = i < jw ? i + 1 : jw;
-        for (int j = lane; j < jend; j += 32) PN[prw * ldp + rel[j]] += srow[j];
-      }
-    }
-    __syncwarp();   // two children may reach one target through different lanes of the owning warp: keep the children ordered
   }
   __syncthreads();
   // ---- blocked left-looking factorisation of the panel, 8 columns at a time ----
@@ -235,66 +244,71 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
     }
   }
   if (b == 0) return;
-  // ---- update matrix, stripe by stripe: C[s0 .. s0+32, 0 .. ] = sum over children - P_stripe P^T ----
+  // ---- update matrix: per 16 x 16 tile of the lower triangle  C = gathered children - P_I P_J^T, written once from registers ----
   double* dst = a.arena_cur + item * p.arena_size + p.f_cb_off[t];
   const int ldg_out = p.f_cb_ld[t];
   const double* P = PN + w8 * ldp;
-  const int nsp = (b + FRONT_STRIPE - 1) / FRONT_STRIPE;   // stripe pointers exist for rows 0, 32, ..., 32 nsp
-  for (int s0 = 0; s0 < b; s0 += sr) {
-    const int rows_here = min(sr, b - s0);
-    for (int e = tid; e < rows_here * ldc; e += THREADS) ST[e] = 0.0;
-    for (int e = rows_here * ldc + tid; e < min(sr, ((rows_here + 15) & ~15)) * ldc; e += THREADS) ST[e] = 0.0;
-    __syncthreads();
-    for (int ci = c_begin; ci < c_end; ci++) {
-      const int c = p.child_list[ci];
-      const int ldg = p.f_cb_ld[c];
-      const int32_t* rel = p.f_rel + p.rel_ptr[c];
-      const int32_t* sp = p.c_sp + p.c_sp_ptr[c];   // precomputed stripe pointers at 32-row granularity (frontal.py)
-      const int i0 = sp[s0 / FRONT_STRIPE], i1 = sp[min((s0 + sr) / FRONT_STRIPE, nsp)];
-      if (i1 > i0) {      // uniform across the CTA
-        const int jw = p.c_jw[c];
-        const double* src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
-        for (int i = i0; i < i1; i++) {     // stripe rows are owned by warps (row % NW): no barrier between children
-          const int ri = rel[i] - w - s0;
-          if ((ri % NW) != warp) continue;
-          const double* srow = src + (int64_t)i * ldg;
-          for (int j = jw + lane; j <= i; j += 32) ST[ri * ldc + rel[j] - w] += srow[j];
-        }
-      }
-      __syncwarp();   // (same: children ordered inside the owning warp)
+  const int nmt = b16 / 16, ntl = nmt * (nmt + 1) / 2;
+  for (int q = warp; q < ntl; q += NW) {
+    int R = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+    while ((R + 1) * (R + 2) / 2 <= q) R++;
+    while (R * (R + 1) / 2 > q) R--;
+    const int ct = q - R * (R + 1) / 2;
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    const double* Pa = P + (16 * R + lr) * ldp + lc;
+    const double* Pb = P + (16 * ct + lr) * ldp + lc;
+    for (int k4 = 0; k4 < w8; k4 += 4) {
+      const double a0 = Pa[k4], a1 = Pa[8 * ldp + k4];
+      const double b0 = Pb[k4], b1 = Pb[8 * ldp + k4];
+      front_mma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      front_mma884(acc[0][1][0], acc[0][1][1], a0, b1);
+      front_mma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      front_mma884(acc[1][1][0], acc[1][1][1], a1, b1);
     }
-    __syncthreads();
-    // 16 x 16 macro tiles of this stripe's macro rows that lie in the lower triangle
-    const int R0 = s0 / 16, R1 = min((s0 + sr) / 16, b16 / 16);
-    for (int R = R0; R < R1; R++) {
-      for (int ct = warp; ct <= R; ct += NW) {
-        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-        const double* Pa = P + (16 * R + lr) * ldp + lc;
-        const double* Pb = P + (16 * ct + lr) * ldp + lc;
-        for (int k4 = 0; k4 < w8; k4 += 4) {
-          const double a0 = Pa[k4], a1 = Pa[8 * ldp + k4];
-          const double b0 = Pb[k4], b1 = Pb[8 * ldp + k4];
-          front_mma884(acc[0][0][0], acc[0][0][1], a0, b0);
-          front_mma884(acc[0][1][0], acc[0][1][1], a0, b1);
-          front_mma884(acc[1][0][0], acc[1][0][1], a1, b0);
-          front_mma884(acc[1][1][0], acc[1][1][1], a1, b1);
-        }
+    // front-local indices of this lane's 2 rows and 4 columns
+    const int li0 = w + 16 * R + lr, lj0 = w + 16 * ct + 2 * lc;
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        acc[mi][ni][0] = -acc[mi][ni][0];
+        acc[mi][ni][1] = -acc[mi][ni][1];
+      }
+#pragma unroll
+    for (int qc = 0; qc < FRONT_MAX_CHILDREN; qc++) {
+      if (qc < nch && w + 16 * R + 15 >= ch[qc].lo && w + 16 * ct <= ch[qc].hi) {   // warp-uniform: does the child reach this tile at all
+        const int32_t* inv = ch[qc].inv;
+        int ci[2], cj[2][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) ci[mi] = (li0 + 8 * mi < r) ? inv[li0 + 8 * mi] : -1;
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int u = 0; u < 2; u++) cj[ni][u] = (lj0 + 8 * ni + u < r) ? inv[lj0 + 8 * ni + u] : -1;
 #pragma unroll
         for (int mi = 0; mi < 2; mi++)
 #pragma unroll
-          for (int ni = 0; ni < 2; ni++) {
-            double* d = ST + (16 * (R - R0) + 8 * mi + lr) * ldc + 16 * ct + 8 * ni + 2 * lc;
-            d[0] -= acc[mi][ni][0];
-            d[1] -= acc[mi][ni][1];
+          for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+              if (ci[mi] >= 0 && cj[ni][u] >= 0 && cj[ni][u] <= ci[mi])
+                acc[mi][ni][u] += ch[qc].src[(int64_t)ci[mi] * ch[qc].ldg + cj[ni][u]];
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) {
+      const int i = 16 * R + 8 * mi + lr;
+      if (i < b) {
+        double* drow = dst + (int64_t)i * ldg_out;
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            const int jj = 16 * ct + 8 * ni + 2 * lc + u;
+            if (jj <= i) drow[jj] = acc[mi][ni][u];
           }
       }
     }
-    __syncthreads();
-    for (int i = warp; i < rows_here; i += NW) {
-      double* drow = dst + (int64_t)(s0 + i) * ldg_out;
-      for (int j = lane; j <= s0 + i; j += 32) drow[j] = ST[i * ldc + j];
-    }
-    __syncthreads();
   }
 }
 
@@ -314,6 +328,38 @@ __global__ void __launch_bounds__(ASM_THREADS) front_assemble_kernel(FrontArgs a
   const int R0 = blockIdx.y * ASM_ROWS;
   // the dense kernel reads 128 x 64 tiles (i, j <= 2 i + 1): of row R only the columns below 128 (R / 128 + 1) are ever read
   const int nc = min(np, 128 * (R0 / 128 + 1));
+  const int c_first = p.child_ptr[t], n_children = p.child_ptr[t + 1] - c_first;
+  if (n_children <= FRONT_MAX_CHILDREN) {
+    // GATHER form (few children): every entry of the row tile is computed by one thread from the panel and the children's update
+    // matrices through the inverse maps; independent loads, no shared memory, no barriers; children added in list order
+    const double* Lgg = a.factor + item * p.data_size + p.f_panel_off[t];
+    const double alg = a.alpha != nullptr ? a.alpha[item] : 0.0;
+    const double beg = a.beta != nullptr ? a.beta[item] : 0.0;
+    double* Fg = a.arena_cur + item * p.arena_size + p.f_fr_off[t] + (int64_t)R0 * np;
+    for (int e = tid; e < ASM_ROWS * nc; e += ASM_THREADS) {
+      const int rr = e / nc, fc = e - rr * nc;
+      const int fr = R0 + rr;
+      const int li = fr < w ? fr : ((fr >= wpad && fr - wpad + w < r) ? fr - wpad + w : -1);
+      const int lj = fc < w ? fc : ((fc >= wpad && fc - wpad + w < r) ? fc - wpad + w : -1);
+      double v = 0.0;
+      if (li < 0 || lj < 0) {
+        v = (fr == fc) ? 1.0 : 0.0;          // identity on the padding
+      } else if (lj <= li) {
+        if (lj < w) {
+          v = Lgg[(int64_t)li * w + lj];
+          if (li == lj) v = v + (alg * v + beg);
+        }
+        for (int q = 0; q < n_children; q++) {
+          const int c = p.child_list[c_first + q];
+          const int32_t* inv = p.c_inv + p.c_inv_ptr[c];
+          const int ci = inv[li], cj = inv[lj];
+          if (ci >= 0 && cj >= 0) v += a.arena_child[item * p.arena_size + p.f_cb_off[c] + (int64_t)ci * p.f_cb_ld[c] + cj];
+        }
+      }
+      Fg[(int64_t)rr * np + fc] = v;
+    }
+    return;
+  }
   double* buf = sm;   // [ASM_ROWS][nc]
   for (int e = tid; e < ASM_ROWS * nc; e += ASM_THREADS) buf[e] = 0.0;
   __syncthreads();
@@ -429,16 +475,20 @@ __global__ void __launch_bounds__(THREADS) front_forward_kernel(FrontSolveArgs a
   double* u = sm;            // [r]
   double* T = sm + ((r + 1) & ~1);   // [32][33]
   const double* Lg = a.factor + item * p.data_size + p.f_panel_off[t];
-  for (int i = tid; i < r; i += THREADS) u[i] = i < w ? a.rhs[item * p.n + p.perm[first + i]] : 0.0;
-  __syncthreads();
-  for (int ci = p.child_ptr[t]; ci < p.child_ptr[t + 1]; ci++) {
-    const int c = p.child_list[ci];
-    const int bc = p.f_b[c];
-    const double* uc = a.v_child + item * p.varena_size + p.f_u_off[c];
-    const int32_t* rel = p.f_rel + p.rel_ptr[c];
-    for (int i = tid; i < bc; i += THREADS) u[rel[i]] += uc[i];
-    __syncthreads();
+  {
+    // u = [rhs of the pivots; 0] + the children's border vectors, GATHERED through the inverse maps (fixed child order, no barriers)
+    const int c0 = p.child_ptr[t], c1 = p.child_ptr[t + 1];
+    for (int i = tid; i < r; i += THREADS) {
+      double v = i < w ? a.rhs[item * p.n + p.perm[first + i]] : 0.0;
+      for (int ci = c0; ci < c1; ci++) {
+        const int c = p.child_list[ci];
+        const int k = p.c_inv[p.c_inv_ptr[c] + i];
+        if (k >= 0) v += a.v_child[item * p.varena_size + p.f_u_off[c] + k];
+      }
+      u[i] = v;
+    }
   }
+  __syncthreads();
   for (int k0 = 0; k0 < w; k0 += 32) {
     const int cw = min(32, w - k0);
     for (int e = tid; e < cw * cw; e += THREADS) {
@@ -531,7 +581,7 @@ static inline int front_set_smem(K kernel, size_t bytes, size_t* cache) {
 
 extern "C" {
 
-int64_t thb_front_small_smem_bytes(int32_t w, int32_t b, int32_t stripe_rows) { return thb::front_smem_doubles(w, b, stripe_rows) * 8; }
+int64_t thb_front_small_smem_bytes(int32_t w, int32_t b) { return thb::front_smem_doubles(w, b) * 8; }
 
 int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* alpha,
                          const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes, int32_t* info, int64_t B,

@@ -161,8 +161,6 @@ def _flops_of(struct, dims):
 
 STRIPE = 32                          # rows of the update matrix produced at a time by the shared-memory kernel (thb_front.cu FRONT_STRIPE)
 SMALL_SMEM_LIMIT = 220 * 1024
-STRIPE_MAX_ROWS = None              # tests: cap the stripe height (a multiple of 32) to exercise the multi-stripe path on small fronts
-STRIPE_BUDGET = int(__import__("os").environ.get("THB_FRONT_STRIPE_BUDGET_KB", "110")) * 1024
 SMEM_BUCKETS = (27 * 1024, 36 * 1024, 55 * 1024, 74 * 1024, 112 * 1024)   # 8, 6, 4, 3, 2 CTAs per SM (227 KB usable), then 1
 
 
@@ -170,27 +168,14 @@ def _pad_ld(x: int) -> int:
     return ((x + 11) // 16) * 16 + 4
 
 
-def small_smem_bytes(w: int, b: int, sr: Optional[int] = None) -> int:
-    """Dynamic shared memory of front_small_kernel for a front (thb_front.cu: front_smem_doubles): padded panel + inverse of one 8 x 8
-    diagonal block + one stripe (sr rows; default: stripe_rows(w, b)) of the update matrix."""
+def small_smem_bytes(w: int, b: int) -> int:
+    """Dynamic shared memory of front_small_kernel for a front (thb_front.cu: front_smem_doubles): the padded panel + the inverse of one
+    8 x 8 diagonal block.  (The update matrix is never resident: its tiles go from registers to global memory.)"""
     b16, w8 = (b + 15) & ~15, (w + 7) & ~7
-    sr = stripe_rows(w, b) if sr is None else sr
-    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + sr * _pad_ld(b16) + 2) * 8
+    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 2) * 8
 
 
-def stripe_rows(w: int, b: int) -> int:
-    """Rows of the update matrix produced at a time: every stripe costs a round of global-memory latency for the children's
-    contributions, so as many rows as a shared-memory budget holds -- the whole matrix for small fronts (<= STRIPE_BUDGET keeps two
-    CTAs per SM), at least 32 rows for the largest."""
-    b16, w8 = (b + 15) & ~15, (w + 7) & ~7
-    base = ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 2) * 8
-    per_row = _pad_ld(b16) * 8
-    full = max(STRIPE, -(-b // STRIPE) * STRIPE)
-    limit = STRIPE_BUDGET if base + STRIPE * per_row <= STRIPE_BUDGET else SMALL_SMEM_LIMIT
-    sr = int(min(full, max(STRIPE, (limit - base) // per_row // STRIPE * STRIPE)))
-    return min(sr, STRIPE_MAX_ROWS) if STRIPE_MAX_ROWS else sr
-
-
+SMALL_MAX_CHILDREN = 8   # thb_front.cu FRONT_MAX_CHILDREN: the gather kernel keeps its children's descriptors in registers
 SMALL_MAX_W = 192    # pivot block columns of 8 are factored one after the other inside the CTA: wider pivot blocks go to the dense kernel
 
 
@@ -373,7 +358,7 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     for t in range(S):
         r = int(f_r[t])
         too_big = (small_limit is not None and r > small_limit) or int(f_w[t]) > SMALL_MAX_W or \
-            small_smem_bytes(int(f_w[t]), int(f_b[t])) > SMALL_SMEM_LIMIT
+            small_smem_bytes(int(f_w[t]), int(f_b[t])) > SMALL_SMEM_LIMIT or len(children[t]) > SMALL_MAX_CHILDREN
         f_class[t] = 3 if too_big else min(int(np.searchsorted(np.array(SMALL_CLASSES), r)), 2)
     # ---- storage: panels, update-matrix arena (by depth parity), border-vector arena ----
     f_panel_off = np.zeros(S, dtype=np.int64)
@@ -457,6 +442,20 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
             acc += ns
         c_sp_ptr[t + 1] = acc
     c_sp = np.concatenate(c_sp_list).astype(np.int32) if c_sp_list else np.zeros(1, dtype=np.int32)
+    #   c_inv[c_inv_ptr[t] + l] = border row of t whose image is row l of p's front, or -1 (the gather kernel's map)
+    c_inv_ptr = np.zeros(S + 1, dtype=np.int64)
+    c_inv_list: List[np.ndarray] = []
+    acc = 0
+    for t in range(S):
+        p = int(f_parent[t])
+        if p >= 0:
+            inv = -np.ones(int(f_r[p]), dtype=np.int32)
+            rel = f_rel[rel_ptr[t]:rel_ptr[t + 1]]
+            inv[rel] = np.arange(rel.shape[0], dtype=np.int32)
+            c_inv_list.append(inv)
+            acc += inv.shape[0]
+        c_inv_ptr[t + 1] = acc
+    c_inv = np.concatenate(c_inv_list).astype(np.int32) if c_inv_list else np.zeros(1, dtype=np.int32)
     rows_ptr = np.zeros(S + 1, dtype=np.int64)
     rows_ptr[1:] = np.cumsum(f_b)
     f_rows = np.concatenate(border_rows).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
@@ -494,7 +493,7 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
                   f_wpad=f_wpad, f_np=f_np, f_cb_off=f_cb_off, f_cb_ld=f_cb_ld, f_fr_off=f_fr_off, f_u_off=f_u_off,
                   child_ptr=child_ptr, child_list=np.array(child_list, dtype=np.int32), rel_ptr=rel_ptr, f_rel=f_rel,
                   rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32), c_jw=c_jw, c_sp_ptr=c_sp_ptr, c_sp=c_sp,
-                  f_sr=np.array([stripe_rows(int(f_w[t]), int(f_b[t])) for t in range(S)], dtype=np.int32))
+                  c_inv_ptr=c_inv_ptr, c_inv=c_inv)
     return FrontPlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, pstart=pstart, col_start=col_start, perm=perm, S=S,
                      arrays=arrays, launches=launches, data_size=int(data_size), arena_size=int(arena_size), varena_size=int(varena_size),
                      stats=stats, front_of_pos=front_of_pos, border_rows=border_rows)
