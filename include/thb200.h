@@ -173,6 +173,11 @@ typedef struct thb_gram_plan {
   int64_t num_blocks;         /* NB */
   const int32_t* blk_rows;    /* device [NB] rows of the block (its columns are blk_ld for packed block storage) */
   const int32_t* blk_cols;    /* device [NB] columns of the block */
+  /* block-per-thread Gram kernels (one thread = one whole block of one item): blocks grouped by shape.  num_segments == 0 (some block
+   * shape outside {1,2,3,6} x {1,2,3,6}): the entry-per-thread kernel runs instead. */
+  int64_t num_segments;
+  const int32_t* segments;    /* HOST [num_segments,4] = (rows, cols, begin, end) into blk_order */
+  const int32_t* blk_order;   /* device [NB] block ids sorted by shape */
 } thb_gram_plan;
 
 /* out[b*out_bstride + ...] receives the blocks (dense AtA: out_bstride = n*n, caller pre-zeroes via
@@ -452,11 +457,16 @@ typedef struct thb_front_plan {
   /* per CHILD front t of parent p: c_inv[c_inv_ptr[t] + l] = border row of t whose image is row l of p's front (l < r_p), or -1:
    * the shared-memory kernel GATHERS the children's update matrices through it (no scatter, no barriers) */
   const int64_t* c_inv_ptr; const int32_t* c_inv;
+  /* flat descriptors of the shared-memory kernel: fd[q] (q = position in sched) = (front, w, b, f_first, f_panel_off, f_cb_off, f_cb_ld,
+   * child_begin | nchildren << 32);  pc[child_begin + k] = (f_cb_off, f_cb_ld, first and last front row reached, offset of the inverse
+   * map in c_inv, f_u_off) of the front's k-th child */
+  const int64_t* fd; const int64_t* pc;
 } thb_front_plan;
 
 #define THB_FRONT_LAUNCH_COLS 12
-/* dynamic shared memory (bytes) the shared-memory factor kernel needs for a front with w pivots and b border rows (the panel) */
-int64_t thb_front_small_smem_bytes(int32_t w, int32_t b);
+/* dynamic shared memory (bytes) the shared-memory factor kernel needs for a front with w pivots, b border rows and nchildren children
+ * (the padded panel + the children's inverse maps) */
+int64_t thb_front_small_smem_bytes(int32_t w, int32_t b, int32_t nchildren);
 /* factor: in-place on `factor` [B, data_size] (AtA + fill-in zeros in, L out); dense_ws: workspace of
  * thb_potrf_partial_workspace_bytes(B, max np) bytes (may be NULL when there is no class-3 front);
  * info[b] = 0 or 1 + permuted index of a non-positive pivot (cleared here). */

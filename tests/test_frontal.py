@@ -69,7 +69,7 @@ def _check_plan(N, edges, dims, seed=0, **kw):
             assert A["f_depth"][t] == A["f_depth"][p] + 1 and len(rel) == A["f_b"][t]
             assert np.all(np.diff(rel) > 0) and rel[-1] < A["f_w"][p] + A["f_b"][p]
         if A["f_class"][t] < 3:
-            assert small_smem_bytes(int(A["f_w"][t]), int(A["f_b"][t])) <= 220 * 1024
+            assert small_smem_bytes(int(A["f_w"][t]), int(A["f_b"][t]), int(A["child_ptr"][t + 1] - A["child_ptr"][t])) <= 220 * 1024
     depths = plan.launches[:, 0]
     assert np.all(np.diff(depths) <= 0)
     return plan

@@ -41,8 +41,8 @@ def test_dense_linearization_routes_dense_jacobians_to_the_tma_kernel(monkeypatc
     W = torch.randn(m, n, dtype=torch.float64).cuda()
 
     def err_fn(optim_vars, aux_vars):
-        x = optim_vars[0].tensor
-        return x @ aux_vars[0].tensor.squeeze(0).T + 0.1 * (x @ aux_vars[0].tensor.squeeze(0).T) ** 3
+        y = torch.einsum("...n,...mn->...m", optim_vars[0].tensor, aux_vars[0].tensor)   # (works batched [B,n] x [1,m,n] and under vmap)
+        return y + 0.1 * y ** 3
 
     outs = {}
     for flag in ("1", "0"):

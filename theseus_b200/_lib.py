@@ -31,7 +31,8 @@ class GramPlan(C.Structure):
                 ("blk_out", c_vp), ("blk_ld", c_vp), ("blk_mirror", c_vp), ("blk_cptr", c_vp),
                 ("c_off", c_vp), ("c_stride", c_vp), ("c_rows", c_vp), ("c_bpa", c_vp), ("c_bpb", c_vp),
                 ("n", c_i64), ("col_cptr", c_vp), ("cc_off", c_vp), ("cc_stride", c_vp), ("cc_rows", c_vp),
-                ("cc_row0", c_vp), ("num_blocks", c_i64), ("blk_rows", c_vp), ("blk_cols", c_vp)]
+                ("cc_row0", c_vp), ("num_blocks", c_i64), ("blk_rows", c_vp), ("blk_cols", c_vp),
+                ("num_segments", c_i64), ("segments", c_vp), ("blk_order", c_vp)]
 
 
 def make_gram_plan(arrs, dev):
@@ -44,7 +45,8 @@ def make_gram_plan(arrs, dev):
         c_bpb=dev["c_bpb"].data_ptr(), n=int(arrs["n"]), col_cptr=dev["col_cptr"].data_ptr(),
         cc_off=dev["cc_off"].data_ptr(), cc_stride=dev["cc_stride"].data_ptr(), cc_rows=dev["cc_rows"].data_ptr(),
         cc_row0=dev["cc_row0"].data_ptr(), num_blocks=int(arrs["blk_out"].shape[0]), blk_rows=dev["blk_rows"].data_ptr(),
-        blk_cols=dev["blk_cols"].data_ptr())
+        blk_cols=dev["blk_cols"].data_ptr(), num_segments=int(arrs["segments"].shape[0]), segments=arrs["segments"].ctypes.data,
+        blk_order=dev["blk_order"].data_ptr())
 
 
 class SparsePlanStruct(C.Structure):
@@ -87,7 +89,7 @@ class FrontPlanStruct(C.Structure):
     """thb_front_plan (include/thb200.h): multifrontal block-sparse Cholesky, arrays of theseus_b200/frontal.py."""
     _fields_ = [("S", c_i64), ("n", c_i64), ("data_size", c_i64), ("arena_size", c_i64), ("varena_size", c_i64)] + [(k, c_vp) for k in (
         "f_w", "f_b", "f_first", "f_class", "f_wpad", "f_np", "f_cb_ld", "f_depth", "f_panel_off", "f_cb_off", "f_fr_off", "f_u_off",
-        "child_ptr", "child_list", "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv")]
+        "child_ptr", "child_list", "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv", "fd", "pc")]
 
 
 _PF = C.POINTER(FrontPlanStruct)
@@ -139,7 +141,7 @@ SIGNATURES = {
     "thb_sparse_lane_root_rhs_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_sparse_lane_root_scatter_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_gram_dense_f64": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
-    "thb_front_small_smem_bytes": (c_i64, [c_i32, c_i32]),
+    "thb_front_small_smem_bytes": (c_i64, [c_i32, c_i32, c_i32]),
     "thb_front_factor_f64": (c_i32, [_PF, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "thb_front_solve_f64": (c_i32, [_PF, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_potrf_partial_workspace_bytes": (c_i64, [c_i64, c_i64]),

@@ -69,9 +69,9 @@ struct FrontArgs {
 constexpr int FRONT_WD_LD = 20;
 constexpr int FRONT_MAX_CHILDREN = 8;   // fronts with more children are assembled by the scatter kernel of the dense path (frontal.py)
 
-__host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b) {
+__host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b, int nchildren) {
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
-  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + 2;
+  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + 2 + ((int64_t)nchildren * (w + b) + 1) / 2;   // + int32 inverse maps
 }
 
 // One warp: Cholesky of the 8 x 8 block at T (row stride ld; lower part read, L written in place) and its inverse (full 8 x 8, zeros
@@ -123,9 +123,8 @@ __device__ __forceinline__ int front_leaf8(double* __restrict__ T, int ld, doubl
   return fail;
 }
 
-struct FrontChild {       // one child of the front this CTA works on (registers / local array, <= FRONT_MAX_CHILDREN)
+struct FrontChild {       // one child of the front this CTA works on (registers, <= FRONT_MAX_CHILDREN)
   const double* src;      // its update matrix for this item
-  const int32_t* inv;     // [r of this front] -> child border row or -1
   int ldg, lo, hi;        // leading dimension; range [lo, hi] of this front's rows the child reaches
 };
 
@@ -137,53 +136,75 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   constexpr int NW = THREADS / 32;
   const int lr = lane >> 2, lc = lane & 3;
   const int64_t item = blockIdx.x;
-  const int t = p.sched[a.s0 + blockIdx.y];
-  const int w = p.f_w[t], b = p.f_b[t], r = w + b;
+  // flat descriptors (frontal.py): one record per front in LAUNCH order, one per (parent, child) pair in the parent's child order --
+  // two dependent loads from kernel start to the first data load instead of five through the per-field arrays
+  const int64_t* FD = p.fd + (int64_t)(a.s0 + blockIdx.y) * 8;
+  const int t = (int)FD[0];
+  const int w = (int)FD[1], b = (int)FD[2], r = w + b;
+  const int f_first = (int)FD[3];
+  const int64_t f_panel_off = FD[4], f_cb_off = FD[5];
+  const int f_cb_ld = (int)FD[6];
+  const int c_begin = (int)(FD[7] & 0xffffffffLL);
+  const int nch = min((int)(FD[7] >> 32), FRONT_MAX_CHILDREN);
+  (void)t;
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
   const int ldp = front_pad_ld(w8);
   const int prow = w8 + b16 + 8;
   double* PN = sm;                          // [prow][ldp]
   double* Wd = PN + prow * ldp;             // [8][FRONT_WD_LD]
-  // ---- children descriptors ----
-  const int c_begin = p.child_ptr[t];
-  const int nch = min(p.child_ptr[t + 1] - c_begin, FRONT_MAX_CHILDREN);
+  int32_t* INV = reinterpret_cast<int32_t*>(Wd + 8 * FRONT_WD_LD + 2);   // [nch][r] inverse maps of the children (front row -> child row / -1)
+  // ---- children descriptors; their inverse maps go to shared memory (one round trip, then every lookup is on chip) ----
   FrontChild ch[FRONT_MAX_CHILDREN];
 #pragma unroll
   for (int q = 0; q < FRONT_MAX_CHILDREN; q++) {
     if (q < nch) {
-      const int c = p.child_list[c_begin + q];
-      ch[q].src = a.arena_child + item * p.arena_size + p.f_cb_off[c];
-      ch[q].inv = p.c_inv + p.c_inv_ptr[c];
-      ch[q].ldg = p.f_cb_ld[c];
-      const int32_t* rel = p.f_rel + p.rel_ptr[c];
-      ch[q].lo = rel[0];
-      ch[q].hi = rel[p.f_b[c] - 1];
+      const int64_t* PC = p.pc + (int64_t)(c_begin + q) * 6;   // (cb_off, cb_ld, lo, hi, inv_off, u_off) of this child
+      ch[q].src = a.arena_child + item * p.arena_size + PC[0];
+      ch[q].ldg = (int)PC[1];
+      ch[q].lo = (int)PC[2];
+      ch[q].hi = (int)PC[3];
+      const int32_t* inv = p.c_inv + PC[4];
+      for (int l = tid; l < r; l += THREADS) INV[q * r + l] = inv[l];
     }
   }
   for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
   __syncthreads();
   if (tid < w8 - w) PN[(w + tid) * ldp + w + tid] = 1.0;   // identity on the padding of the pivot block
-  double* Lg = a.factor + item * p.data_size + p.f_panel_off[t];
+  double* Lg = a.factor + item * p.data_size + f_panel_off;
   {
     const double al = a.alpha != nullptr ? a.alpha[item] : 0.0;
     const double be = a.beta != nullptr ? a.beta[item] : 0.0;
-    int i = tid / w, j = tid - i * w;   // (i, j) of element e, advanced without a division
-    const int di = THREADS / w, dj = THREADS - di * w;
-    for (int e = tid; e < r * w; e += THREADS) {
-      if (j <= i) {                      // lower triangle of the pivot block, all of the border rows
-        double v = Lg[e];
-        if (i == j) v = v + (al * v + be);   // linear/utils.py:14-33: diag <- diag (1 + alpha) + beta
+    const int total = r * w;
+    // four panel elements per thread and pass: their global loads (AtA entry + one per contributing child) are independent and in flight together
+    for (int e0 = tid; e0 < total; e0 += 4 * THREADS) {
+      int ii[4], jj[4];
+      double v[4];
 #pragma unroll
-        for (int q = 0; q < FRONT_MAX_CHILDREN; q++) {
-          if (q < nch && i >= ch[q].lo && j <= ch[q].hi) {
-            const int ci = ch[q].inv[i], cj = ch[q].inv[j];
-            if (ci >= 0 && cj >= 0) v += ch[q].src[(int64_t)ci * ch[q].ldg + cj];
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * THREADS;
+        ii[u] = e / w;
+        jj[u] = e - ii[u] * w;
+        if (e >= total || jj[u] > ii[u]) ii[u] = -1;   // outside, or above the diagonal of the pivot block
+        v[u] = ii[u] >= 0 ? Lg[e] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (ii[u] >= 0 && ii[u] == jj[u]) v[u] = v[u] + (al * v[u] + be);   // linear/utils.py:14-33: diag <- diag (1 + alpha) + beta
+#pragma unroll
+      for (int q = 0; q < FRONT_MAX_CHILDREN; q++) {
+        if (q < nch) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (ii[u] >= ch[q].lo && jj[u] <= ch[q].hi) {
+              const int ci = INV[q * r + ii[u]], cj = INV[q * r + jj[u]];
+              if (ci >= 0 && cj >= 0) v[u] += ch[q].src[(int64_t)ci * ch[q].ldg + cj];
+            }
           }
         }
-        PN[(i < w ? i : i + (w8 - w)) * ldp + j] = v;
       }
-      i += di; j += dj;
-      if (j >= w) { j -= w; i++; }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (ii[u] >= 0) PN[(ii[u] < w ? ii[u] : ii[u] + (w8 - w)) * ldp + jj[u]] = v[u];
     }
   }
   __syncthreads();
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
       d[1] -= c1;
       __syncwarp();
       const int fail = front_leaf8(PN + (8 * jb) * ldp + 8 * jb, ldp, Wd, lane);
-      if (lane == 0 && fail != 0 && 8 * jb + fail <= w) atomicCAS(a.info + item, 0, p.f_first[t] + 8 * jb + fail);
+      if (lane == 0 && fail != 0 && 8 * jb + fail <= w) atomicCAS(a.info + item, 0, f_first + 8 * jb + fail);
     }
     __syncthreads();
     const int npair = (nrt - jb) / 2;   // row tiles jb+1 .. nrt-1 in pairs (an odd last tile pairs with the zero tile after the end)
@@ -245,8 +266,8 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   }
   if (b == 0) return;
   // ---- update matrix: per 16 x 16 tile of the lower triangle  C = gathered children - P_I P_J^T, written once from registers ----
-  double* dst = a.arena_cur + item * p.arena_size + p.f_cb_off[t];
-  const int ldg_out = p.f_cb_ld[t];
+  double* dst = a.arena_cur + item * p.arena_size + f_cb_off;
+  const int ldg_out = f_cb_ld;
   const double* P = PN + w8 * ldp;
   const int nmt = b16 / 16, ntl = nmt * (nmt + 1) / 2;
   for (int q = warp; q < ntl; q += NW) {
@@ -277,7 +298,7 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
 #pragma unroll
     for (int qc = 0; qc < FRONT_MAX_CHILDREN; qc++) {
       if (qc < nch && w + 16 * R + 15 >= ch[qc].lo && w + 16 * ct <= ch[qc].hi) {   // warp-uniform: does the child reach this tile at all
-        const int32_t* inv = ch[qc].inv;
+        const int32_t* inv = INV + qc * r;
         int ci[2], cj[2][2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) ci[mi] = (li0 + 8 * mi < r) ? inv[li0 + 8 * mi] : -1;
@@ -581,7 +602,7 @@ static inline int front_set_smem(K kernel, size_t bytes, size_t* cache) {
 
 extern "C" {
 
-int64_t thb_front_small_smem_bytes(int32_t w, int32_t b) { return thb::front_smem_doubles(w, b) * 8; }
+int64_t thb_front_small_smem_bytes(int32_t w, int32_t b, int32_t nchildren) { return thb::front_smem_doubles(w, b, nchildren) * 8; }
 
 int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* alpha,
                          const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes, int32_t* info, int64_t B,

@@ -148,6 +148,77 @@ __global__ void __launch_bounds__(256) solve_backward_kernel(int64_t B, int64_t 
 
 }  // namespace thb
 
+namespace thb {
+
+// Block-per-thread Gram: one thread forms a whole DI x DJ block of AtA for one batch item in registers -- every Jacobian entry of a
+// contribution is loaded once per block (12 loads for 36 FMAs with 6 x 6 blocks; the entry-per-thread kernel above issues 2 per FMA
+// and is bound by load instructions at 0.14 of HBM) and the block's rows are written as DJ consecutive values.  Blocks are grouped by
+// shape on the host (thb_gram_plan.segments); threads of a warp = consecutive blocks of ONE item, i.e. neighbouring cost functions'
+// row blocks of A_val.  Contributions are visited in the plan's fixed order: deterministic, no atomics.
+template <typename T, int DI, int DJ>
+__global__ void __launch_bounds__(128) gram_block_kernel(thb_gram_plan p, int64_t B, const T* __restrict__ A_val, int64_t nnz,
+                                                         T* __restrict__ out, int64_t out_bstride, int seg_begin, int count) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)count * B) return;
+  const int64_t b = t / count;
+  const int blk = p.blk_order[seg_begin + (int)(t - b * count)];
+  const T* A = A_val + b * nnz;
+  T acc[DI][DJ];
+#pragma unroll
+  for (int i = 0; i < DI; i++)
+#pragma unroll
+    for (int j = 0; j < DJ; j++) acc[i][j] = T(0);
+  const int c1 = p.blk_cptr[blk + 1];
+  for (int c = p.blk_cptr[blk]; c < c1; c++) {
+    const T* base = A + p.c_off[c];
+    const int stride = p.c_stride[c], rows = p.c_rows[c];
+    const T* pa = base + p.c_bpa[c];
+    const T* pb = base + p.c_bpb[c];
+    for (int r = 0; r < rows; r++) {
+      T av[DI], bv[DJ];
+#pragma unroll
+      for (int i = 0; i < DI; i++) av[i] = pa[r * stride + i];
+#pragma unroll
+      for (int j = 0; j < DJ; j++) bv[j] = pb[r * stride + j];
+#pragma unroll
+      for (int i = 0; i < DI; i++)
+#pragma unroll
+        for (int j = 0; j < DJ; j++) acc[i][j] += av[i] * bv[j];
+    }
+  }
+  T* o = out + b * out_bstride;
+  const int ld = p.blk_ld[blk];
+  T* o0 = o + p.blk_out[blk];
+#pragma unroll
+  for (int i = 0; i < DI; i++)
+#pragma unroll
+    for (int j = 0; j < DJ; j++) o0[(int64_t)i * ld + j] = acc[i][j];
+  const int64_t mo = p.blk_mirror[blk];
+  if (mo >= 0) {
+    T* o1 = o + mo;
+#pragma unroll
+    for (int j = 0; j < DJ; j++)
+#pragma unroll
+      for (int i = 0; i < DI; i++) o1[(int64_t)j * ld + i] = acc[i][j];
+  }
+}
+
+template <typename T, int DI>
+static int gram_block_launch_dj(int dj, const thb_gram_plan& p, int64_t B, const T* A_val, int64_t nnz, T* out, int64_t bs, int begin, int count,
+                                cudaStream_t cs) {
+  const int64_t total = (int64_t)count * B;
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  switch (dj) {
+    case 1: gram_block_kernel<T, DI, 1><<<grid, 128, 0, cs>>>(p, B, A_val, nnz, out, bs, begin, count); return 1;
+    case 2: gram_block_kernel<T, DI, 2><<<grid, 128, 0, cs>>>(p, B, A_val, nnz, out, bs, begin, count); return 1;
+    case 3: gram_block_kernel<T, DI, 3><<<grid, 128, 0, cs>>>(p, B, A_val, nnz, out, bs, begin, count); return 1;
+    case 6: gram_block_kernel<T, DI, 6><<<grid, 128, 0, cs>>>(p, B, A_val, nnz, out, bs, begin, count); return 1;
+    default: return 0;
+  }
+}
+
+}  // namespace thb
+
 template <typename T>
 static int gram_impl(const thb_gram_plan* p, int64_t B, const T* A_val, int64_t nnz, const T* b, int64_t m, T* out, int64_t out_bstride,
                      T* Atb, T* diag, thb_stream_t s) {
@@ -155,9 +226,28 @@ static int gram_impl(const thb_gram_plan* p, int64_t B, const T* A_val, int64_t 
   if (B == 0) return THB_OK;
   cudaStream_t cs = thb_cs(s);
   if (out != nullptr && p->num_entries > 0) {
-    const int64_t total = p->num_entries * B;
-    thb::gram_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(*p, B, A_val, nnz, out, out_bstride, nullptr);
-    THB_CHECK_LAUNCH();
+    if (p->num_segments > 0 && p->segments != nullptr && p->blk_order != nullptr) {
+      // every block shape is one the block-per-thread kernels are built for (the host only fills `segments` then)
+      for (int64_t sgi = 0; sgi < p->num_segments; sgi++) {
+        const int32_t* sg = p->segments + 4 * sgi;   // (di, dj, begin, end) into blk_order
+        const int count = sg[3] - sg[2];
+        if (count <= 0) continue;
+        int ok = 0;
+        switch (sg[0]) {
+          case 1: ok = thb::gram_block_launch_dj<T, 1>(sg[1], *p, B, A_val, nnz, out, out_bstride, sg[2], count, cs); break;
+          case 2: ok = thb::gram_block_launch_dj<T, 2>(sg[1], *p, B, A_val, nnz, out, out_bstride, sg[2], count, cs); break;
+          case 3: ok = thb::gram_block_launch_dj<T, 3>(sg[1], *p, B, A_val, nnz, out, out_bstride, sg[2], count, cs); break;
+          case 6: ok = thb::gram_block_launch_dj<T, 6>(sg[1], *p, B, A_val, nnz, out, out_bstride, sg[2], count, cs); break;
+          default: ok = 0;
+        }
+        if (!ok) return THB_ERR_BAD_ARG;
+        THB_CHECK_LAUNCH();
+      }
+    } else {
+      const int64_t total = p->num_entries * B;
+      thb::gram_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(*p, B, A_val, nnz, out, out_bstride, nullptr);
+      THB_CHECK_LAUNCH();
+    }
   }
   if (Atb != nullptr && p->n > 0) {
     const int64_t total = p->n * B;

@@ -442,7 +442,7 @@ class Engine:
             arrs = build_gram_plan(self.structure)
             dev = {k: _dev(v, self.device) for k, v in arrs.items() if isinstance(v, np.ndarray)}
             st = _lib.make_gram_plan(arrs, dev)
-            self._gram_dense = (st, dev)
+            self._gram_dense = (st, dev, arrs)   # arrs keeps the HOST segment table of the struct alive
         return self._gram_dense[0]
 
     def gram_dense(self, A_val, b, AtA, Atb, diag):

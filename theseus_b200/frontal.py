@@ -168,11 +168,12 @@ def _pad_ld(x: int) -> int:
     return ((x + 11) // 16) * 16 + 4
 
 
-def small_smem_bytes(w: int, b: int) -> int:
-    """Dynamic shared memory of front_small_kernel for a front (thb_front.cu: front_smem_doubles): the padded panel + the inverse of one
-    8 x 8 diagonal block.  (The update matrix is never resident: its tiles go from registers to global memory.)"""
+def small_smem_bytes(w: int, b: int, nchildren: int = 0) -> int:
+    """Dynamic shared memory of front_small_kernel for a front (thb_front.cu: front_smem_doubles): the padded panel, the inverse of one
+    8 x 8 diagonal block and the children's int32 inverse maps.  (The update matrix is never resident: its tiles go from registers to
+    global memory.)"""
     b16, w8 = (b + 15) & ~15, (w + 7) & ~7
-    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 2) * 8
+    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 2 + (min(nchildren, SMALL_MAX_CHILDREN) * (w + b) + 1) // 2) * 8
 
 
 SMALL_MAX_CHILDREN = 8   # thb_front.cu FRONT_MAX_CHILDREN: the gather kernel keeps its children's descriptors in registers
@@ -358,7 +359,7 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     for t in range(S):
         r = int(f_r[t])
         too_big = (small_limit is not None and r > small_limit) or int(f_w[t]) > SMALL_MAX_W or \
-            small_smem_bytes(int(f_w[t]), int(f_b[t])) > SMALL_SMEM_LIMIT or len(children[t]) > SMALL_MAX_CHILDREN
+            small_smem_bytes(int(f_w[t]), int(f_b[t]), len(children[t])) > SMALL_SMEM_LIMIT or len(children[t]) > SMALL_MAX_CHILDREN
         f_class[t] = 3 if too_big else min(int(np.searchsorted(np.array(SMALL_CLASSES), r)), 2)
     # ---- storage: panels, update-matrix arena (by depth parity), border-vector arena ----
     f_panel_off = np.zeros(S, dtype=np.int64)
@@ -465,7 +466,7 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     def bucket(t):
         if f_class[t] == 3:
             return 0
-        sm = small_smem_bytes(int(f_w[t]), int(f_b[t]))
+        sm = small_smem_bytes(int(f_w[t]), int(f_b[t]), len(children[t]))
         return int(np.searchsorted(np.array(SMEM_BUCKETS), sm))
     f_bucket = np.array([bucket(t) for t in range(S)], dtype=np.int32)
     sched = np.array(sorted(range(S), key=lambda t: (-int(f_depth[t]), int(f_class[t]), int(f_bucket[t]), -int(f_r[t]), t)), dtype=np.int32)
@@ -478,12 +479,23 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
         if c != 3:
             while j < S and int(f_depth[sched[j]]) == d and int(f_class[sched[j]]) == c and int(f_bucket[sched[j]]) == bk:
                 j += 1
-            smem = max(small_smem_bytes(int(f_w[q]), int(f_b[q])) for q in sched[i:j])
+            smem = max(small_smem_bytes(int(f_w[q]), int(f_b[q]), len(children[q])) for q in sched[i:j])
             launches.append((d, c, i, j - i, smem, max(int(f_r[q]) for q in sched[i:j]), 0, 0, 0, 0, 0, 0))
         else:   # one front: (.., np, pivot block columns, offset of F in the arena, first pivot [info base], front index)
             launches.append((d, c, i, 1, 0, int(f_np[t]), int(f_wpad[t]) // BIG_TW, int(f_fr_off[t]), int(f_first[t]), t, int(f_w[t]), int(f_b[t])))
         i = j
     launches = np.array(launches, dtype=np.int64).reshape(-1, 12)
+    # flat descriptors for the shared-memory kernel (see thb200.h): per front in launch order, per (parent, child) pair
+    fd = np.zeros((max(S, 1), 8), dtype=np.int64)
+    pc = np.zeros((max(int(child_ptr[S]), 1), 6), dtype=np.int64)
+    for q in range(S):
+        t = int(sched[q])
+        cb, ce = int(child_ptr[t]), int(child_ptr[t + 1])
+        fd[q] = (t, int(f_w[t]), int(f_b[t]), int(f_first[t]), int(f_panel_off[t]), int(f_cb_off[t]), int(f_cb_ld[t]), cb | ((ce - cb) << 32))
+    for t in range(S):
+        for k, c in enumerate(children[t]):
+            rel = f_rel[rel_ptr[c]:rel_ptr[c + 1]]
+            pc[int(child_ptr[t]) + k] = (int(f_cb_off[c]), int(f_cb_ld[c]), int(rel[0]), int(rel[-1]), int(c_inv_ptr[c]), int(f_u_off[c]))
     flops = float(sum(_front_cost(float(f_w[t]), float(f_b[t])) for t in range(S)))
     stats = dict(ordering=oname, column_flops=col_flops, flops=flops, nnz_L=float(sum(int(f_r[t]) * int(f_w[t]) for t in range(S))),
                  fronts=float(S), max_front=float(f_r.max()) if S else 0.0, depth=float(max_depth + 1), big_fronts=float((f_class == 3).sum()),
@@ -493,7 +505,7 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
                   f_wpad=f_wpad, f_np=f_np, f_cb_off=f_cb_off, f_cb_ld=f_cb_ld, f_fr_off=f_fr_off, f_u_off=f_u_off,
                   child_ptr=child_ptr, child_list=np.array(child_list, dtype=np.int32), rel_ptr=rel_ptr, f_rel=f_rel,
                   rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32), c_jw=c_jw, c_sp_ptr=c_sp_ptr, c_sp=c_sp,
-                  c_inv_ptr=c_inv_ptr, c_inv=c_inv)
+                  c_inv_ptr=c_inv_ptr, c_inv=c_inv, fd=fd.reshape(-1), pc=pc.reshape(-1))
     return FrontPlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, pstart=pstart, col_start=col_start, perm=perm, S=S,
                      arrays=arrays, launches=launches, data_size=int(data_size), arena_size=int(arena_size), varena_size=int(varena_size),
                      stats=stats, front_of_pos=front_of_pos, border_rows=border_rows)

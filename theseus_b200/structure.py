@@ -173,7 +173,20 @@ def build_gram_plan(s: Structure, out_offsets=None, pos=None):
     def cat(lst, dt):
         return np.concatenate(lst).astype(dt) if lst else np.zeros(0, dtype=dt)
 
+    # blocks grouped by shape for the block-per-thread kernels (thb_gram.cu: gram_block_kernel<DI, DJ>)
+    shapes = sorted(set(zip(blk_rows, blk_cols)))
+    if all(di in (1, 2, 3, 6) and dj in (1, 2, 3, 6) for di, dj in shapes):
+        order, segments = [], []
+        for di, dj in shapes:
+            ids = [k for k in range(len(blocks)) if blk_rows[k] == di and blk_cols[k] == dj]
+            segments.append((di, dj, len(order), len(order) + len(ids)))
+            order.extend(ids)
+        blk_order = np.array(order, dtype=np.int32)
+        segments = np.ascontiguousarray(np.array(segments, dtype=np.int32).reshape(-1, 4))
+    else:
+        blk_order, segments = np.zeros(1, dtype=np.int32), np.zeros((0, 4), dtype=np.int32)
     return dict(
+        blk_order=blk_order, segments=segments,
         ent_blk=cat(ent_blk, np.int32), ent_p=cat(ent_p, np.int16), ent_q=cat(ent_q, np.int16),
         blk_out=np.array(blk_out, dtype=np.int64), blk_ld=np.array(blk_ld, dtype=np.int32),
         blk_mirror=np.array(blk_mirror, dtype=np.int64), blk_cptr=np.array(blk_cptr, dtype=np.int32),
