@@ -491,20 +491,23 @@ __global__ void __launch_bounds__(THREADS) front_forward_kernel(FrontSolveArgs a
   const thb_front_plan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t item = blockIdx.x;
-  const int t = p.sched[a.s0 + blockIdx.y];
-  const int w = p.f_w[t], b = p.f_b[t], r = w + b, first = p.f_first[t];
+  const int64_t* FD = p.fd + (int64_t)(a.s0 + blockIdx.y) * 8;   // flat descriptor of the front (frontal.py)
+  const int t = (int)FD[0];
+  const int w = (int)FD[1], b = (int)FD[2], r = w + b, first = (int)FD[3];
   double* u = sm;            // [r]
   double* T = sm + ((r + 1) & ~1);   // [32][33]
-  const double* Lg = a.factor + item * p.data_size + p.f_panel_off[t];
+  const double* Lg = a.factor + item * p.data_size + FD[4];
   {
     // u = [rhs of the pivots; 0] + the children's border vectors, GATHERED through the inverse maps (fixed child order, no barriers)
-    const int c0 = p.child_ptr[t], c1 = p.child_ptr[t + 1];
+    const int c0 = (int)(FD[7] & 0xffffffffLL), nchild = (int)(FD[7] >> 32);
     for (int i = tid; i < r; i += THREADS) {
       double v = i < w ? a.rhs[item * p.n + p.perm[first + i]] : 0.0;
-      for (int ci = c0; ci < c1; ci++) {
-        const int c = p.child_list[ci];
-        const int k = p.c_inv[p.c_inv_ptr[c] + i];
-        if (k >= 0) v += a.v_child[item * p.varena_size + p.f_u_off[c] + k];
+      for (int q = 0; q < nchild; q++) {
+        const int64_t* PC = p.pc + (int64_t)(c0 + q) * 6;
+        if (i >= (int)PC[2] && i <= (int)PC[3]) {
+          const int k = p.c_inv[PC[4] + i];
+          if (k >= 0) v += a.v_child[item * p.varena_size + PC[5] + k];
+        }
       }
       u[i] = v;
     }
@@ -543,12 +546,13 @@ __global__ void __launch_bounds__(THREADS) front_backward_kernel(FrontSolveArgs 
   const thb_front_plan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t item = blockIdx.x;
-  const int t = p.sched[a.s0 + blockIdx.y];
-  const int w = p.f_w[t], b = p.f_b[t], r = w + b, first = p.f_first[t];
+  const int64_t* FD = p.fd + (int64_t)(a.s0 + blockIdx.y) * 8;
+  const int t = (int)FD[0];
+  const int w = (int)FD[1], b = (int)FD[2], r = w + b, first = (int)FD[3];
   double* xf = sm;                       // [r] pivots (y, then x) followed by the border rows' x
   double* T = sm + ((r + 1) & ~1);       // [32][33]
   double* part = T + 32 * 33 + 1;        // [THREADS]
-  const double* Lg = a.factor + item * p.data_size + p.f_panel_off[t];
+  const double* Lg = a.factor + item * p.data_size + FD[4];
   double* wk = a.work + item * p.n;
   const int32_t* rows = p.f_rows + p.rows_ptr[t];
   for (int i = tid; i < r; i += THREADS) xf[i] = i < w ? wk[first + i] : wk[rows[i - w]];

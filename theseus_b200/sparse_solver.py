@@ -44,6 +44,7 @@ class BaspachoSparseSolver(LinearSolver):
         self._front_options = dict(front_options or {})   # layout="front": frontal.build_front_plan keywords (tau, small_limit, ...)
         self._plan = None
         self._dev = None
+        self.param_size = None
         self.reset()
 
     @classmethod
@@ -64,6 +65,7 @@ class BaspachoSparseSolver(LinearSolver):
         self._ordering, self._plan, self._dev, self._layout = ordering, None, None, layout
         self._supernodal_solve = bool(supernodal_solve)
         self._front_options = dict(front_options or {})
+        self.param_size = None
         self.reset()
         return self
 
@@ -72,8 +74,12 @@ class BaspachoSparseSolver(LinearSolver):
         if self._plan is not None:
             return
         S = self.linearization.structure()
-        param_size, ptrs, inds = ata_block_structure(S)
-        self.param_size, self.block_ptrs, self.block_inds = param_size, ptrs, inds  # the reference's SymbolicDecomposition inputs
+        if getattr(self, "param_size", None) is None:
+            param_size, ptrs, inds = ata_block_structure(S)
+            self.param_size, self.block_ptrs, self.block_inds = param_size, ptrs, inds  # the reference's SymbolicDecomposition inputs
+        param_size, ptrs, inds = self.param_size, self.block_ptrs, self.block_inds
+        if self._layout is None:
+            return      # default layout: chosen at the first solve, when the batch size is known (layout_for); the plan is built then
         if self._layout == "front":
             # multifrontal layout: own ordering (nested dissection / minimum degree, whichever costs fewer flops) and fronts
             opts = {k: v for k, v in getattr(self, "_front_options", {}).items() if k != "chunk"}
@@ -90,6 +96,10 @@ class BaspachoSparseSolver(LinearSolver):
     def layout_for(self, B: int) -> str:
         """'lane' (batch-interleaved factor, one warp = 32 batch items, thb_sparse_lane.cu) or 'item' (one CTA per batch item,
         thb_sparse.cu).  Default: lane whenever a warp can be filled and every block size is one the lane kernels are built for."""
+        if self._layout is None:
+            # default: the multifrontal layout for batches that fill the GPU (any block sizes); one CTA per item for small batches
+            self._layout = os.environ.get("THB_SPARSE_LAYOUT") or ("front" if B >= 32 else "item")
+            self.reset()
         if self._layout == "front":
             return "front"
         lane_ok = all(int(d) in LANE_DIMS for d in self._plan.dims)
@@ -113,6 +123,9 @@ class BaspachoSparseSolver(LinearSolver):
 
     @property
     def symbolic_stats(self):
+        if self._plan is None:      # default layout not resolved yet: report the multifrontal plan (what large batches get)
+            self._layout = os.environ.get("THB_SPARSE_LAYOUT") or "front"
+            self.reset()
         return dict(self._plan.stats)
 
     @property
