@@ -71,7 +71,8 @@ constexpr int FRONT_MAX_CHILDREN = 8;   // fronts with more children are assembl
 
 __host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b, int nchildren) {
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
-  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + 2 + ((int64_t)nchildren * (w + b) + 1) / 2;   // + int32 inverse maps
+  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN     // + children descriptors
+         + ((int64_t)nchildren * (w + b) + 1) / 2 + 2;                                           // + int32 inverse maps
 }
 
 // One warp: Cholesky of the 8 x 8 block at T (row stride ld; lower part read, L written in place) and its inverse (full 8 x 8, zeros
@@ -123,13 +124,14 @@ __device__ __forceinline__ int front_leaf8(double* __restrict__ T, int ld, doubl
   return fail;
 }
 
-struct FrontChild {       // one child of the front this CTA works on (registers, <= FRONT_MAX_CHILDREN)
+struct FrontChild {       // one child of the front this CTA works on (shared memory, <= FRONT_MAX_CHILDREN)
   const double* src;      // its update matrix for this item
-  int ldg, lo, hi;        // leading dimension; range [lo, hi] of this front's rows the child reaches
+  int ldg, lo, hi, pad;   // leading dimension; range [lo, hi] of this front's rows the child reaches
 };
 
+// Registers are capped at 64 per thread (1 024 threads per SM): the kernel is bound by the latency chain of a CTA, so resident warps count.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 1024 / THREADS)) front_small_kernel(FrontArgs a) {
   extern __shared__ double sm[];
   const thb_front_plan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -152,20 +154,19 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
   const int prow = w8 + b16 + 8;
   double* PN = sm;                          // [prow][ldp]
   double* Wd = PN + prow * ldp;             // [8][FRONT_WD_LD]
-  int32_t* INV = reinterpret_cast<int32_t*>(Wd + 8 * FRONT_WD_LD + 2);   // [nch][r] inverse maps of the children (front row -> child row / -1)
-  // ---- children descriptors; their inverse maps go to shared memory (one round trip, then every lookup is on chip) ----
-  FrontChild ch[FRONT_MAX_CHILDREN];
-#pragma unroll
-  for (int q = 0; q < FRONT_MAX_CHILDREN; q++) {
-    if (q < nch) {
-      const int64_t* PC = p.pc + (int64_t)(c_begin + q) * 6;   // (cb_off, cb_ld, lo, hi, inv_off, u_off) of this child
+  FrontChild* ch = reinterpret_cast<FrontChild*>(Wd + 8 * FRONT_WD_LD);               // [FRONT_MAX_CHILDREN] (24 bytes each)
+  int32_t* INV = reinterpret_cast<int32_t*>(Wd + 8 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN);   // [nch][r] front row -> child row / -1
+  // ---- children descriptors and inverse maps go to shared memory (one round trip, then every lookup is on chip) ----
+  for (int q = 0; q < nch; q++) {
+    const int64_t* PC = p.pc + (int64_t)(c_begin + q) * 6;   // (cb_off, cb_ld, lo, hi, inv_off, u_off) of this child
+    if (tid == 0) {
       ch[q].src = a.arena_child + item * p.arena_size + PC[0];
       ch[q].ldg = (int)PC[1];
       ch[q].lo = (int)PC[2];
       ch[q].hi = (int)PC[3];
-      const int32_t* inv = p.c_inv + PC[4];
-      for (int l = tid; l < r; l += THREADS) INV[q * r + l] = inv[l];
     }
+    const int32_t* inv = p.c_inv + PC[4];
+    for (int l = tid; l < r; l += THREADS) INV[q * r + l] = inv[l];
   }
   for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
   __syncthreads();
@@ -190,15 +191,15 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
 #pragma unroll
       for (int u = 0; u < 4; u++)
         if (ii[u] >= 0 && ii[u] == jj[u]) v[u] = v[u] + (al * v[u] + be);   // linear/utils.py:14-33: diag <- diag (1 + alpha) + beta
+      for (int q = 0; q < nch; q++) {
+        const double* src = ch[q].src;
+        const int ldg = ch[q].ldg, lo = ch[q].lo, hi = ch[q].hi;
+        const int32_t* inv = INV + q * r;
 #pragma unroll
-      for (int q = 0; q < FRONT_MAX_CHILDREN; q++) {
-        if (q < nch) {
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            if (ii[u] >= ch[q].lo && jj[u] <= ch[q].hi) {
-              const int ci = INV[q * r + ii[u]], cj = INV[q * r + jj[u]];
-              if (ci >= 0 && cj >= 0) v[u] += ch[q].src[(int64_t)ci * ch[q].ldg + cj];
-            }
+        for (int u = 0; u < 4; u++) {
+          if (ii[u] >= lo && jj[u] <= hi) {
+            const int ci = inv[ii[u]], cj = inv[jj[u]];
+            if (ci >= 0 && cj >= 0) v[u] += src[(int64_t)ci * ldg + cj];
           }
         }
       }
@@ -295,10 +296,11 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
         acc[mi][ni][0] = -acc[mi][ni][0];
         acc[mi][ni][1] = -acc[mi][ni][1];
       }
-#pragma unroll
-    for (int qc = 0; qc < FRONT_MAX_CHILDREN; qc++) {
-      if (qc < nch && w + 16 * R + 15 >= ch[qc].lo && w + 16 * ct <= ch[qc].hi) {   // warp-uniform: does the child reach this tile at all
+    for (int qc = 0; qc < nch; qc++) {
+      if (w + 16 * R + 15 >= ch[qc].lo && w + 16 * ct <= ch[qc].hi) {   // warp-uniform: does the child reach this tile at all
         const int32_t* inv = INV + qc * r;
+        const double* src = ch[qc].src;
+        const int ldg = ch[qc].ldg;
         int ci[2], cj[2][2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) ci[mi] = (li0 + 8 * mi < r) ? inv[li0 + 8 * mi] : -1;
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(THREADS) front_small_kernel(FrontArgs a) {
 #pragma unroll
             for (int u = 0; u < 2; u++)
               if (ci[mi] >= 0 && cj[ni][u] >= 0 && cj[ni][u] <= ci[mi])
-                acc[mi][ni][u] += ch[qc].src[(int64_t)ci[mi] * ch[qc].ldg + cj[ni][u]];
+                acc[mi][ni][u] += src[(int64_t)ci[mi] * ldg + cj[ni][u]];
       }
     }
 #pragma unroll
@@ -616,7 +618,7 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
   if (B > 65535LL * 32768LL) return THB_ERR_UNSUPPORTED;
   cudaStream_t cs = thb_cs(stream);
   THB_CUDA(cudaMemsetAsync(info, 0, (size_t)B * 4, cs));
-  static size_t smem_set[3] = {0, 0, 0}, asm_set = 0;
+  static size_t smem_set[4] = {0, 0, 0, 0}, asm_set = 0;
   for (int64_t l = 0; l < num_launches; l++) {
     const int64_t* L = launches + l * THB_FRONT_LAUNCH_COLS;
     const int depth = (int)L[0], cls = (int)L[1], begin = (int)L[2], count = (int)L[3];
@@ -637,9 +639,12 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
       } else if (cls == 1) {
         int rc = thb::front_set_smem(thb::front_small_kernel<128>, smem, &smem_set[1]); if (rc) return rc;
         thb::front_small_kernel<128><<<grid, 128, smem, cs>>>(a);
-      } else {
+      } else if (smem <= 113 * 1024) {
         int rc = thb::front_set_smem(thb::front_small_kernel<256>, smem, &smem_set[2]); if (rc) return rc;
         thb::front_small_kernel<256><<<grid, 256, smem, cs>>>(a);
+      } else {   // one CTA per SM anyway: twice the warps for the tile phases
+        int rc = thb::front_set_smem(thb::front_small_kernel<512>, smem, &smem_set[3]); if (rc) return rc;
+        thb::front_small_kernel<512><<<grid, 512, smem, cs>>>(a);
       }
       THB_CHECK_LAUNCH();
     } else {

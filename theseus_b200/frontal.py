@@ -173,9 +173,11 @@ def small_smem_bytes(w: int, b: int, nchildren: int = 0) -> int:
     8 x 8 diagonal block and the children's int32 inverse maps.  (The update matrix is never resident: its tiles go from registers to
     global memory.)"""
     b16, w8 = (b + 15) & ~15, (w + 7) & ~7
-    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 2 + (min(nchildren, SMALL_MAX_CHILDREN) * (w + b) + 1) // 2) * 8
+    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 3 * SMALL_MAX_CHILDREN + 2 + (min(nchildren, SMALL_MAX_CHILDREN) * (w + b) + 1) // 2) * 8
 
 
+SPLIT_MAX_W = 96         # pivot columns of one piece when a wide supernode is split into a chain of fronts
+SPLIT_ROOT_W = 256       # borderless fronts wider than this stay whole (dense path)
 SMALL_MAX_CHILDREN = 8   # thb_front.cu FRONT_MAX_CHILDREN: the gather kernel keeps its children's descriptors in registers
 SMALL_MAX_W = 192    # pivot block columns of 8 are factored one after the other inside the CTA: wider pivot blocks go to the dense kernel
 
@@ -228,7 +230,7 @@ class FrontPlan:
 
 
 def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float = 0.12, merge_flops: float = 4e4,
-                     merge_max_r: int = SMALL_CLASSES[1], small_limit: Optional[int] = None) -> FrontPlan:
+                     merge_max_r: int = SMALL_CLASSES[1], small_limit: Optional[int] = None, split_wide: bool = True) -> FrontPlan:
     param_size = np.asarray(param_size, dtype=np.int64)
     ptrs = np.asarray(ptrs, dtype=np.int64)
     inds = np.asarray(inds, dtype=np.int64)
@@ -301,10 +303,39 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
                     kids[c] = []
                     changed = True
                     break
-    keep = [s for s in range(S0) if alive[s]]
-    S = len(keep)
-    new_id = -np.ones(S0, dtype=np.int64)
-    new_id[keep] = np.arange(S)
+    # ---- wide supernodes are SPLIT into a chain of fronts that fit the shared-memory kernel (a supernode's columns form a dense
+    # trapezoid: piece k = its columns as pivots, the later pieces' columns + the supernode's border as border rows; same flops, one
+    # more trip of an update matrix through the arena).  Left whole -- for the dense path -- : borderless fronts wider than
+    # SPLIT_ROOT_W (a plain dense Cholesky: the tiled DMMA kernel is the better engine) and fronts whose single columns do not fit. ----
+    fr_cols: List[List[int]] = []
+    fr_below: List[np.ndarray] = []
+    for sidx in (q for q in range(S0) if alive[q]):
+        cs, bl = cols[sidx], np.asarray(below[sidx], dtype=np.int64)
+        wtot, btot = int(dims0[cs].sum()), (int(dims0[bl].sum()) if len(bl) else 0)
+        fits = wtot <= SMALL_MAX_W and small_smem_bytes(wtot, btot, 4) <= SMALL_SMEM_LIMIT
+        if fits or not split_wide or (btot == 0 and wtot > SPLIT_ROOT_W):
+            fr_cols.append(list(cs)); fr_below.append(bl)
+            continue
+        pieces, i0 = [], 0
+        while i0 < len(cs):
+            i1, wacc = i0, 0
+            rest = int(dims0[cs[i0:]].sum())
+            while i1 < len(cs):
+                wn = wacc + int(dims0[cs[i1]])
+                if i1 > i0 and (wn > SPLIT_MAX_W or small_smem_bytes(wn, rest - wn + btot, 4) > SMALL_SMEM_LIMIT):
+                    break
+                wacc, i1 = wn, i1 + 1
+            pieces.append((i0, i1))
+            i0 = i1
+        if any(small_smem_bytes(int(dims0[cs[a:b_]].sum()), int(dims0[cs[b_:]].sum()) + btot, 4) > SMALL_SMEM_LIMIT for a, b_ in pieces):
+            fr_cols.append(list(cs)); fr_below.append(bl)       # even single columns do not fit: dense path
+            continue
+        for a, b_ in pieces:
+            fr_cols.append(list(cs[a:b_]))
+            fr_below.append(np.concatenate([np.asarray(cs[b_:], dtype=np.int64), bl]))
+    S = len(fr_cols)
+    keep = list(range(S))
+    cols, below = fr_cols, fr_below
     # ---- final elimination order: fronts in topological order, each front's columns contiguous ----
     old_positions = np.array([j for s in keep for j in cols[s]], dtype=np.int64)
     assert sorted(old_positions.tolist()) == list(range(N))
