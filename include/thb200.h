@@ -461,18 +461,23 @@ typedef struct thb_front_plan {
    * child_begin | nchildren << 32);  pc[child_begin + k] = (f_cb_off, f_cb_ld, first and last front row reached, offset of the inverse
    * map in c_inv, f_u_off) of the front's k-th child */
   const int64_t* fd; const int64_t* pc;
+  /* panel map: pmap[o] for offset o of one item's factor storage = offset of that AtA entry in the COMPACT block storage written by
+   * thb_gram_f64 (frontal.FrontPlan.gram_compact_offsets), or -1 for fill-in.  With it the factorisation reads AtA where it is
+   * non-zero and the panels need no zero fill. */
+  const int32_t* pmap;
 } thb_front_plan;
 
 #define THB_FRONT_LAUNCH_COLS 12
 /* dynamic shared memory (bytes) the shared-memory factor kernel needs for a front with w pivots, b border rows and nchildren children
  * (the padded panel + the children's inverse maps) */
 int64_t thb_front_small_smem_bytes(int32_t w, int32_t b, int32_t nchildren);
-/* factor: in-place on `factor` [B, data_size] (AtA + fill-in zeros in, L out); dense_ws: workspace of
+/* factor: `factor` [B, data_size] receives L.  Input: either ata != NULL = compact AtA blocks [B, ata_stride] read through p->pmap (no zero
+ * fill, no scatter into the panels), or ata == NULL = the panels of `factor` already hold AtA + zeros (the extlib flow); dense_ws: workspace of
  * thb_potrf_partial_workspace_bytes(B, max np) bytes (may be NULL when there is no class-3 front);
  * info[b] = 0 or 1 + permuted index of a non-positive pivot (cleared here). */
-int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* alpha,
-                         const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes, int32_t* info, int64_t B,
-                         thb_stream_t stream);
+int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* ata,
+                         int64_t ata_stride, const double* alpha, const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes,
+                         int32_t* info, int64_t B, thb_stream_t stream);
 /* x = (L L^T)^-1 rhs; rhs, x [B, n] in ORIGINAL column order; work [B, n], varena [2, B, varena_size] scratch */
 int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, const double* factor, const double* rhs,
                         double* x, double* work, double* varena, int64_t B, thb_stream_t stream);

@@ -89,7 +89,7 @@ class FrontPlanStruct(C.Structure):
     """thb_front_plan (include/thb200.h): multifrontal block-sparse Cholesky, arrays of theseus_b200/frontal.py."""
     _fields_ = [("S", c_i64), ("n", c_i64), ("data_size", c_i64), ("arena_size", c_i64), ("varena_size", c_i64)] + [(k, c_vp) for k in (
         "f_w", "f_b", "f_first", "f_class", "f_wpad", "f_np", "f_cb_ld", "f_depth", "f_panel_off", "f_cb_off", "f_fr_off", "f_u_off",
-        "child_ptr", "child_list", "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv", "fd", "pc")]
+        "child_ptr", "child_list", "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv", "fd", "pc", "pmap")]
 
 
 _PF = C.POINTER(FrontPlanStruct)
@@ -142,7 +142,7 @@ SIGNATURES = {
     "thb_sparse_lane_root_scatter_f64": (c_i32, [_PL, _PR, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_gram_dense_f64": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "thb_front_small_smem_bytes": (c_i64, [c_i32, c_i32, c_i32]),
-    "thb_front_factor_f64": (c_i32, [_PF, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "thb_front_factor_f64": (c_i32, [_PF, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "thb_front_solve_f64": (c_i32, [_PF, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "thb_potrf_partial_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "thb_potrf_partial_inplace_f64": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp]),

@@ -256,10 +256,11 @@ __device__ __forceinline__ void se2_cost(const GroupDev<T>& g, int k, int64_t b,
 template <typename T, int KIND>
 __global__ void __launch_bounds__(128) linearize_kernel(GroupDev<T> g, int64_t B, T* __restrict__ A_val, int64_t nnz,
                                                         T* __restrict__ bvec, int64_t m) {
+  extern __shared__ double lin_stage_raw[];
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)g.K * B) return;
-  const int k = (int)(t / B);
-  const int64_t b = t - (int64_t)k * B;
+  const bool valid = t < (int64_t)g.K * B;     // (no early exit: every lane takes part in the warp-cooperative store below)
+  const int k = valid ? (int)(t / B) : 0;
+  const int64_t b = valid ? t - (int64_t)k * B : 0;
   constexpr int DIM = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_LOCAL_SE3) ? 6 : 3;
   constexpr bool BETWEEN = (KIND == THB_COST_BETWEEN_SE3 || KIND == THB_COST_BETWEEN_SO3 || KIND == THB_COST_BETWEEN_SE2);
   constexpr bool IS_SE2 = (KIND == THB_COST_BETWEEN_SE2 || KIND == THB_COST_LOCAL_SE2);
@@ -287,23 +288,44 @@ __global__ void __launch_bounds__(128) linearize_kernel(GroupDev<T> g, int64_t B
 #pragma unroll
     for (int i = 0; i < DIM * DIM; i++) { J0[i] *= sc; if (BETWEEN) J1[i] *= sc; }
   }
+  // A cost function's rows of A_val are ONE contiguous run of DIM * stride values per batch item (stride = its row length), but the
+  // items of a warp lie nnz values apart: storing from the computing thread writes 8 bytes to 32 different sectors per instruction.
+  // Stage the warp's 32 runs in shared memory and let the whole warp store each run with consecutive lanes (256-byte segments).
   T* Arow = A_val + b * nnz + g.a_off[k];
   const int stride = g.a_stride[k];
+  constexpr int NVMAX = DIM * DIM * (BETWEEN ? 2 : 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* stage = reinterpret_cast<T*>(lin_stage_raw) + (size_t)warp * 32 * (NVMAX + 1);
+  T* mine = stage + lane * (NVMAX + 1);
+  const int nv = DIM * stride;                 // <= NVMAX by construction of the groups (stride = DIM or 2 DIM)
   const int bp0 = g.bp[k * 2 + 0];
 #pragma unroll
   for (int r = 0; r < DIM; r++)
 #pragma unroll
-    for (int c = 0; c < DIM; c++) Arow[r * stride + bp0 + c] = J0[r * DIM + c];
+    for (int c = 0; c < DIM; c++) mine[r * stride + bp0 + c] = J0[r * DIM + c];
   if (BETWEEN) {
     const int bp1 = g.bp[k * 2 + 1];
 #pragma unroll
     for (int r = 0; r < DIM; r++)
 #pragma unroll
-      for (int c = 0; c < DIM; c++) Arow[r * stride + bp1 + c] = J1[r * DIM + c];
+      for (int c = 0; c < DIM; c++) mine[r * stride + bp1 + c] = J1[r * DIM + c];
   }
-  T* brow = bvec + b * m + g.row0[k];
+  __syncwarp();
+  const unsigned long long my_dst = valid ? reinterpret_cast<unsigned long long>(Arow) : 0ull;
+  for (int i = 0; i < 32; i++) {
+    const unsigned long long d = __shfl_sync(0xffffffffu, my_dst, i);
+    const int nvi = __shfl_sync(0xffffffffu, nv, i);
+    if (d != 0ull) {
+      T* dst = reinterpret_cast<T*>(d);
+      const T* src = stage + i * (NVMAX + 1);
+      for (int v = lane; v < nvi; v += 32) dst[v] = src[v];
+    }
+  }
+  if (valid) {
+    T* brow = bvec + b * m + g.row0[k];
 #pragma unroll
-  for (int r = 0; r < DIM; r++) brow[r] = -e[r];
+    for (int r = 0; r < DIM; r++) brow[r] = -e[r];
+  }
 }
 
 // Reprojection (theseus/embodied/measurements/reprojection.py:54-94): q = R p + t, proj = -q_xy/q_z,
@@ -710,13 +732,23 @@ static int linearize_group(const thb_cost_group* g, int64_t B, T* A_val, int64_t
   const int64_t total = (int64_t)g->K * B;
   const unsigned grid = grid_for(total, 128);
   cudaStream_t cs = thb_cs(s);
+#define THB_LIN_LAUNCH(KIND, NV)                                                                                              \
+  do {                                                                                                                      \
+    const size_t smem_ = (size_t)4 * 32 * ((NV) + 1) * sizeof(T);                                                           \
+    static bool attr_ = false;                                                                                              \
+    if (!attr_ && smem_ > 48 * 1024) {                                                                                      \
+      THB_CUDA(cudaFuncSetAttribute(linearize_kernel<T, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));   \
+      attr_ = true;                                                                                                         \
+    }                                                                                                                       \
+    linearize_kernel<T, KIND><<<grid, 128, smem_, cs>>>(d, B, A_val, nnz, b, m);                                            \
+  } while (0)
   switch (g->kind) {
-    case THB_COST_BETWEEN_SE3: linearize_kernel<T, THB_COST_BETWEEN_SE3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
-    case THB_COST_LOCAL_SE3: linearize_kernel<T, THB_COST_LOCAL_SE3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
-    case THB_COST_BETWEEN_SO3: linearize_kernel<T, THB_COST_BETWEEN_SO3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
-    case THB_COST_LOCAL_SO3: linearize_kernel<T, THB_COST_LOCAL_SO3><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
-    case THB_COST_BETWEEN_SE2: linearize_kernel<T, THB_COST_BETWEEN_SE2><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
-    case THB_COST_LOCAL_SE2: linearize_kernel<T, THB_COST_LOCAL_SE2><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
+    case THB_COST_BETWEEN_SE3: THB_LIN_LAUNCH(THB_COST_BETWEEN_SE3, 72); break;
+    case THB_COST_LOCAL_SE3: THB_LIN_LAUNCH(THB_COST_LOCAL_SE3, 36); break;
+    case THB_COST_BETWEEN_SO3: THB_LIN_LAUNCH(THB_COST_BETWEEN_SO3, 18); break;
+    case THB_COST_LOCAL_SO3: THB_LIN_LAUNCH(THB_COST_LOCAL_SO3, 9); break;
+    case THB_COST_BETWEEN_SE2: THB_LIN_LAUNCH(THB_COST_BETWEEN_SE2, 18); break;
+    case THB_COST_LOCAL_SE2: THB_LIN_LAUNCH(THB_COST_LOCAL_SE2, 9); break;
     case THB_COST_LOCAL_VECTOR: linearize_vector_kernel<T><<<grid, 128, 0, cs>>>(d, B, A_val, nnz, b, m); break;
     case THB_COST_REPROJECTION:
       if (g->aux2 == nullptr || g->aux3 == nullptr || g->aux4 == nullptr || g->bstride2 == nullptr) return THB_ERR_BAD_ARG;

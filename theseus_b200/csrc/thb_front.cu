@@ -52,7 +52,17 @@ struct FrontArgs {
   double* arena_cur;        // [B, arena_size] of this depth's parity
   const double* arena_child;
   int32_t* info;
+  const double* ata;        // [B, ata_stride] compact AtA blocks (thb_gram_f64 with the plan's compact offsets), or null: the panels
+  int64_t ata_stride;       //   in `factor` already hold AtA (zero-filled + scattered by the caller: the extlib-style flow)
 };
+
+// AtA entry of panel element e of the front whose panel starts at `poff`: through the plan's panel map when the compact block storage
+// is given (pmap[poff + e] = offset in one item's `ata`, or -1 = fill-in), else from the pre-filled panel itself
+__device__ __forceinline__ double front_panel_in(const FrontArgs& a, const double* Lg, int64_t poff, int64_t item, int64_t e) {
+  if (a.ata == nullptr) return Lg[e];
+  const int32_t m = a.p.pmap[poff + e];
+  return m >= 0 ? a.ata[item * a.ata_stride + m] : 0.0;
+}
 
 // ------------------------------------------------------------------------------------------------ fronts in shared memory
 // One CTA per (front, item).  Shared memory holds ONLY the panel: PN [w8 + b16 + 8][ldp] = pivot rows, identity padding up to w8 = w
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 1024 / THREADS)
         ii[u] = e / w;
         jj[u] = e - ii[u] * w;
         if (e >= total || jj[u] > ii[u]) ii[u] = -1;   // outside, or above the diagonal of the pivot block
-        v[u] = ii[u] >= 0 ? Lg[e] : 0.0;
+        v[u] = ii[u] >= 0 ? front_panel_in(a, Lg, f_panel_off, item, e) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 4; u++)
@@ -369,7 +379,7 @@ __global__ void __launch_bounds__(ASM_THREADS) front_assemble_kernel(FrontArgs a
         v = (fr == fc) ? 1.0 : 0.0;          // identity on the padding
       } else if (lj <= li) {
         if (lj < w) {
-          v = Lgg[(int64_t)li * w + lj];
+          v = front_panel_in(a, Lgg, p.f_panel_off[t], item, (int64_t)li * w + lj);
           if (li == lj) v = v + (alg * v + beg);
         }
         for (int q = 0; q < n_children; q++) {
@@ -398,7 +408,7 @@ __global__ void __launch_bounds__(ASM_THREADS) front_assemble_kernel(FrontArgs a
     else if (fr >= wpad && fr - wpad + w < r) i = fr - wpad + w;
     if (i >= 0) {
       if (j < w && !(i < w && j > i)) {
-        double v = Lg[(int64_t)i * w + j];
+        double v = front_panel_in(a, Lg, p.f_panel_off[t], item, (int64_t)i * w + j);
         if (i == j) v = v + (al * v + be);
         buf[rr * nc + j] = v;
       }
@@ -610,9 +620,9 @@ extern "C" {
 
 int64_t thb_front_small_smem_bytes(int32_t w, int32_t b, int32_t nchildren) { return thb::front_smem_doubles(w, b, nchildren) * 8; }
 
-int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* alpha,
-                         const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes, int32_t* info, int64_t B,
-                         thb_stream_t stream) {
+int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64_t num_launches, double* factor, const double* ata,
+                         int64_t ata_stride, const double* alpha, const double* beta, double* arena, void* dense_ws, int64_t dense_ws_bytes,
+                         int32_t* info, int64_t B, thb_stream_t stream) {
   if (p == nullptr || launches == nullptr || factor == nullptr || arena == nullptr || info == nullptr || B < 0) return THB_ERR_BAD_ARG;
   if (B == 0 || p->S == 0) return THB_OK;
   if (B > 65535LL * 32768LL) return THB_ERR_UNSUPPORTED;
@@ -624,6 +634,7 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
     const int depth = (int)L[0], cls = (int)L[1], begin = (int)L[2], count = (int)L[3];
     thb::FrontArgs a;
     a.p = *p; a.s0 = begin; a.B = B; a.factor = factor; a.alpha = alpha; a.beta = beta; a.info = info;
+    a.ata = (ata != nullptr && p->pmap != nullptr) ? ata : nullptr; a.ata_stride = ata_stride;
     a.arena_cur = arena + (int64_t)(depth & 1) * B * p->arena_size;
     a.arena_child = arena + (int64_t)((depth + 1) & 1) * B * p->arena_size;
     if (cls < 3) {

@@ -156,32 +156,38 @@ namespace thb {
 // shape on the host (thb_gram_plan.segments); threads of a warp = consecutive blocks of ONE item, i.e. neighbouring cost functions'
 // row blocks of A_val.  Contributions are visited in the plan's fixed order: deterministic, no atomics.
 template <typename T, int DI, int DJ>
-__global__ void __launch_bounds__(128) gram_block_kernel(thb_gram_plan p, int64_t B, const T* __restrict__ A_val, int64_t nnz,
-                                                         T* __restrict__ out, int64_t out_bstride, int seg_begin, int count) {
+__global__ void __launch_bounds__(128, (DI * DJ > 18 ? 8 : 4)) gram_block_kernel(thb_gram_plan p, int64_t B, const T* __restrict__ A_val, int64_t nnz,
+                                                                                 T* __restrict__ out, int64_t out_bstride, int seg_begin, int count) {
+  // blocks with more than 18 entries are shared by two threads (rows [0, DI/2) and [DI/2, DI)): 18 accumulators + 9 operands fit 64
+  // registers, so eight CTAs of 128 threads are resident and twice as many loads are in flight (the kernel is bound by memory latency)
+  constexpr int SPLIT = (DI * DJ > 18 && DI % 2 == 0) ? 2 : 1;
+  constexpr int RI = DI / SPLIT;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)count * B) return;
-  const int64_t b = t / count;
-  const int blk = p.blk_order[seg_begin + (int)(t - b * count)];
+  if (t >= (int64_t)count * B * SPLIT) return;
+  const int64_t b = t / ((int64_t)count * SPLIT);
+  const int rem = (int)(t - b * (int64_t)count * SPLIT);
+  const int blk = p.blk_order[seg_begin + rem / SPLIT];
+  const int r0 = (rem % SPLIT) * RI;
   const T* A = A_val + b * nnz;
-  T acc[DI][DJ];
+  T acc[RI][DJ];
 #pragma unroll
-  for (int i = 0; i < DI; i++)
+  for (int i = 0; i < RI; i++)
 #pragma unroll
     for (int j = 0; j < DJ; j++) acc[i][j] = T(0);
   const int c1 = p.blk_cptr[blk + 1];
   for (int c = p.blk_cptr[blk]; c < c1; c++) {
     const T* base = A + p.c_off[c];
     const int stride = p.c_stride[c], rows = p.c_rows[c];
-    const T* pa = base + p.c_bpa[c];
+    const T* pa = base + p.c_bpa[c] + r0;
     const T* pb = base + p.c_bpb[c];
     for (int r = 0; r < rows; r++) {
-      T av[DI], bv[DJ];
+      T av[RI], bv[DJ];
 #pragma unroll
-      for (int i = 0; i < DI; i++) av[i] = pa[r * stride + i];
+      for (int i = 0; i < RI; i++) av[i] = pa[r * stride + i];
 #pragma unroll
       for (int j = 0; j < DJ; j++) bv[j] = pb[r * stride + j];
 #pragma unroll
-      for (int i = 0; i < DI; i++)
+      for (int i = 0; i < RI; i++)
 #pragma unroll
         for (int j = 0; j < DJ; j++) acc[i][j] += av[i] * bv[j];
     }
@@ -190,23 +196,23 @@ __global__ void __launch_bounds__(128) gram_block_kernel(thb_gram_plan p, int64_
   const int ld = p.blk_ld[blk];
   T* o0 = o + p.blk_out[blk];
 #pragma unroll
-  for (int i = 0; i < DI; i++)
+  for (int i = 0; i < RI; i++)
 #pragma unroll
-    for (int j = 0; j < DJ; j++) o0[(int64_t)i * ld + j] = acc[i][j];
+    for (int j = 0; j < DJ; j++) o0[(int64_t)(r0 + i) * ld + j] = acc[i][j];
   const int64_t mo = p.blk_mirror[blk];
   if (mo >= 0) {
     T* o1 = o + mo;
 #pragma unroll
     for (int j = 0; j < DJ; j++)
 #pragma unroll
-      for (int i = 0; i < DI; i++) o1[(int64_t)j * ld + i] = acc[i][j];
+      for (int i = 0; i < RI; i++) o1[(int64_t)j * ld + r0 + i] = acc[i][j];
   }
 }
 
 template <typename T, int DI>
 static int gram_block_launch_dj(int dj, const thb_gram_plan& p, int64_t B, const T* A_val, int64_t nnz, T* out, int64_t bs, int begin, int count,
                                 cudaStream_t cs) {
-  const int64_t total = (int64_t)count * B;
+  const int64_t total = (int64_t)count * B * ((DI * dj > 18 && DI % 2 == 0) ? 2 : 1);
   const unsigned grid = (unsigned)((total + 127) / 128);
   switch (dj) {
     case 1: gram_block_kernel<T, DI, 1><<<grid, 128, 0, cs>>>(p, B, A_val, nnz, out, bs, begin, count); return 1;

@@ -60,7 +60,7 @@ class SymbolicDecomposition:
             P = self.plan
             dev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in P.arrays.items()}
             keys = ("f_w", "f_b", "f_first", "f_class", "f_wpad", "f_np", "f_cb_ld", "f_depth", "f_panel_off", "f_cb_off", "f_fr_off", "f_u_off",
-                    "child_ptr", "child_list", "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv", "fd", "pc")
+                    "child_ptr", "child_list", "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv", "fd", "pc", "pmap")
             st = _lib.FrontPlanStruct(S=P.S, n=P.n, data_size=P.data_size, arena_size=P.arena_size, varena_size=P.varena_size,
                                       **{k: dev[k].data_ptr() for k in keys})
             launches = np.ascontiguousarray(P.launches, dtype=np.int64)
@@ -173,7 +173,7 @@ class NumericDecomposition:
     def factor(self):
         dev, bufs, lib = self.sym._device_plan(), self._buffers(), _lib.load()
         L = dev["launches"]
-        _lib.check(lib.thb_front_factor_f64(C.byref(dev["front"]), L.ctypes.data, L.shape[0], _lib.ptr(self.data), None, None, _lib.ptr(bufs["arena"]),
+        _lib.check(lib.thb_front_factor_f64(C.byref(dev["front"]), L.ctypes.data, L.shape[0], _lib.ptr(self.data), None, 0, None, None, _lib.ptr(bufs["arena"]),
                                             _lib.ptr(bufs["ws"]) if dev["max_np"] else None, bufs["ws"].numel(), _lib.ptr(bufs["info"]), self.B,
                                             _lib.stream_ptr()), "front_factor")
         bad = bufs["info"].nonzero()

@@ -208,6 +208,22 @@ class FrontPlan:
     front_of_pos: np.ndarray = None
     border_rows: List[np.ndarray] = None   # per front: permuted scalar indices of the border rows
 
+    def gram_compact_offsets(self, blocks_dims):
+        """Compact AtA block storage for the panel-map flow: `blocks_dims` = [(a, b, di, dj)] in the Gram plan's block order (original
+        variables, pos[a] >= pos[b]).  Fills arrays["pmap"] (panel offset -> compact offset, -1 = fill-in) and returns
+        (callable for structure.build_gram_plan, doubles per item)."""
+        f = self.gram_out_offsets()
+        pmap = self.arrays["pmap"]
+        pmap[:] = -1
+        table, off = {}, 0
+        for (a, b, di, dj) in blocks_dims:
+            po, ld, _ = f(a, b)
+            idx = po + np.arange(di)[:, None] * ld + np.arange(dj)[None, :]
+            pmap[idx] = off + np.arange(di)[:, None] * dj + np.arange(dj)[None, :]
+            table[(a, b)] = (off, dj, -1)
+            off += di * dj
+        return (lambda a, b: table[(int(a), int(b))]), off
+
     def gram_out_offsets(self):
         """Callable for structure.build_gram_plan: where block (a, b) of AtA (original variables, pos[a] >= pos[b]) lands in the
         panel storage: (offset, leading dimension, mirror=-1)."""
@@ -536,7 +552,8 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
                   f_wpad=f_wpad, f_np=f_np, f_cb_off=f_cb_off, f_cb_ld=f_cb_ld, f_fr_off=f_fr_off, f_u_off=f_u_off,
                   child_ptr=child_ptr, child_list=np.array(child_list, dtype=np.int32), rel_ptr=rel_ptr, f_rel=f_rel,
                   rows_ptr=rows_ptr, f_rows=f_rows, sched=sched, perm=perm.astype(np.int32), c_jw=c_jw, c_sp_ptr=c_sp_ptr, c_sp=c_sp,
-                  c_inv_ptr=c_inv_ptr, c_inv=c_inv, fd=fd.reshape(-1), pc=pc.reshape(-1))
+                  c_inv_ptr=c_inv_ptr, c_inv=c_inv, fd=fd.reshape(-1), pc=pc.reshape(-1),
+                  pmap=-np.ones(max(int(data_size), 1), dtype=np.int32))
     return FrontPlan(N=N, n=n, param_size=param_size, order=order, pos=pos, dims=dims, pstart=pstart, col_start=col_start, perm=perm, S=S,
                      arrays=arrays, launches=launches, data_size=int(data_size), arena_size=int(arena_size), varena_size=int(varena_size),
                      stats=stats, front_of_pos=front_of_pos, border_rows=border_rows)

@@ -88,7 +88,13 @@ class BaspachoSparseSolver(LinearSolver):
                 if env in os.environ and key not in opts:
                     opts[key] = cast(os.environ[env])
             self._plan = build_front_plan(param_size, ptrs, inds, ordering="auto" if self._ordering == "mindeg" else self._ordering, **opts)
-            self._gram_arrays = build_gram_plan(S, out_offsets=self._plan.gram_out_offsets(), pos=self._plan.pos)
+            # AtA goes to a COMPACT block storage; the factorisation reads it through the plan's panel map (no zero fill of the panels,
+            # no reads of their structural zeros)
+            from .structure import lower_blocks
+            blocks, _ = lower_blocks(S, self._plan.pos)
+            dims_of = S.var_dims
+            f, self._ata_size = self._plan.gram_compact_offsets([(a, b, int(dims_of[a]), int(dims_of[b])) for a, b in blocks])
+            self._gram_arrays = build_gram_plan(S, out_offsets=f, pos=self._plan.pos)
             return
         self._plan = analyze(param_size, ptrs, inds, ordering=self._ordering)
         self._gram_arrays = build_gram_plan(S, out_offsets=gram_out_offsets(self._plan), pos=self._plan.pos)
@@ -186,7 +192,7 @@ class BaspachoSparseSolver(LinearSolver):
         st = _lib.FrontPlanStruct(S=P.S, n=P.n, data_size=P.data_size, arena_size=P.arena_size, varena_size=P.varena_size,
                                   **{k: dev[k].data_ptr() for k in ("f_w", "f_b", "f_first", "f_class", "f_wpad", "f_np", "f_cb_ld", "f_depth",
                                                                     "f_panel_off", "f_cb_off", "f_fr_off", "f_u_off", "child_ptr", "child_list",
-                                                                    "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv", "fd", "pc")})
+                                                                    "rel_ptr", "f_rel", "rows_ptr", "f_rows", "sched", "perm", "c_jw", "c_sp_ptr", "c_sp", "c_inv_ptr", "c_inv", "fd", "pc", "pmap")})
         g = self._gram_arrays
         gdev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in g.items() if isinstance(v, np.ndarray)}
         launches = np.ascontiguousarray(P.launches, dtype=np.int64)
@@ -207,6 +213,7 @@ class BaspachoSparseSolver(LinearSolver):
         if d["bufs"].get("key") != (B, "front"):
             ws_bytes = int(lib.thb_potrf_partial_workspace_bytes(chunk, d["max_np"])) if d["max_np"] else 0
             d["bufs"] = dict(key=(B, "front"), chunk=chunk, factor=torch.empty(B, P.data_size, dtype=torch.float64, device=device),
+                             ata=torch.empty(B, self._ata_size, dtype=torch.float64, device=device),
                              arena=torch.empty(2, chunk, P.arena_size, dtype=torch.float64, device=device),
                              varena=torch.empty(2, chunk, P.varena_size, dtype=torch.float64, device=device),
                              work=torch.empty(B, P.n, dtype=torch.float64, device=device),
@@ -217,14 +224,15 @@ class BaspachoSparseSolver(LinearSolver):
         factor, Atb, info = bufs["factor"], bufs["Atb"], bufs["info"]
         nnz, m = A_val.shape[1], b.shape[1]
         self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
-        _lib.check(lib.thb_fill_zero(_lib.ptr(factor), factor.numel() * 8, s), "fill_zero")   # fill-in entries of the panels start at zero
-        _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(factor), P.data_size,
+        ata = bufs["ata"]
+        _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(ata), self._ata_size,
                                     _lib.ptr(Atb), None, s), "gram(front)")
         L = d["launches"]
         for c0 in range(0, B, chunk):
             nb = min(chunk, B - c0)
             _lib.check(lib.thb_front_factor_f64(
-                C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(factor[c0:]), _lib.ptr(alpha[c0:]) if alpha is not None else None,
+                C.byref(d["front"]), L.ctypes.data, L.shape[0], _lib.ptr(factor[c0:]), _lib.ptr(ata[c0:]), self._ata_size,
+                _lib.ptr(alpha[c0:]) if alpha is not None else None,
                 _lib.ptr(beta[c0:]) if beta is not None else None, _lib.ptr(bufs["arena"]), _lib.ptr(bufs["ws"]) if d["max_np"] else None,
                 bufs["ws"].numel(), _lib.ptr(info[c0:]), nb, s), "front_factor")
         self._keep = (A_val, b, alpha, beta)
