@@ -447,7 +447,7 @@ def dense_c2_leg(th, lib, _lib, device, rank, world, pg, timed, peak_tf, steps, 
             rows = torch.from_numpy(np.repeat(np.arange(m), np.diff(S.A_row_ptr))).to(device)
             cols = torch.from_numpy(np.asarray(S.A_col_ind)).to(device)
             A = torch.zeros(B, m, n, dtype=torch.float64, device=device)
-            A[:, rows, cols] = lin.A_val
+            A[:, rows, cols] = lin._A_val
             bvec = lin.b
 
             def lib_solve():

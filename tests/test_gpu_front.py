@@ -138,7 +138,7 @@ def test_lm_trace_with_front_layout(name):
 
 
 def test_c5_full_size_lm_trace_front():
-    """Config C5's pose graph at full size (2 500 poses, n = 15 000), one batch item: ~10 big fronts (up to 462 pivots) + ~1 090 on-chip
+    """Config C5's pose graph at full size (2 500 poses, n = 15 000), one batch item: the 462-pivot root on the dense path + ~1 100 fronts on chip
     ones; LM trace against the reference's dense-solver trace (tests/golden/pgo_c5_lm.npz)."""
     g = load("pgo_c5_lm")
     method, iters, kw = lm_kwargs_of(g)
@@ -146,7 +146,7 @@ def test_c5_full_size_lm_trace_front():
     opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
                                 max_iterations=iters, step_size=1.0, abs_err_tolerance=0, rel_err_tolerance=0,
                                 linear_solver_kwargs=dict(layout="front"))
-    assert opt.linear_solver.symbolic_stats["big_fronts"] >= 3
+    assert opt.linear_solver.symbolic_stats["big_fronts"] >= 1
     errs, deltas = [], []
 
     def cb(optimizer, info, delta, it):

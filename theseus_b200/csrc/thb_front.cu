@@ -286,26 +286,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 1024 / THREADS)
     while ((R + 1) * (R + 2) / 2 <= q) R++;
     while (R * (R + 1) / 2 > q) R--;
     const int ct = q - R * (R + 1) / 2;
-    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-    const double* Pa = P + (16 * R + lr) * ldp + lc;
-    const double* Pb = P + (16 * ct + lr) * ldp + lc;
-    for (int k4 = 0; k4 < w8; k4 += 4) {
-      const double a0 = Pa[k4], a1 = Pa[8 * ldp + k4];
-      const double b0 = Pb[k4], b1 = Pb[8 * ldp + k4];
-      front_mma884(acc[0][0][0], acc[0][0][1], a0, b0);
-      front_mma884(acc[0][1][0], acc[0][1][1], a0, b1);
-      front_mma884(acc[1][0][0], acc[1][0][1], a1, b0);
-      front_mma884(acc[1][1][0], acc[1][1][1], a1, b1);
-    }
-    // front-local indices of this lane's 2 rows and 4 columns
-    const int li0 = w + 16 * R + lr, lj0 = w + 16 * ct + 2 * lc;
-#pragma unroll
-    for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-      for (int ni = 0; ni < 2; ni++) {
-        acc[mi][ni][0] = -acc[mi][ni][0];
-        acc[mi][ni][1] = -acc[mi][ni][1];
-      }
+    // gathered children first: their loads are in flight while the tensor pipe works on -P_I P_J^T
+    double gch[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    const int li0 = w + 16 * R + lr, lj0 = w + 16 * ct + 2 * lc;   // front-local indices of this lane's 2 rows and 4 columns
     for (int qc = 0; qc < nch; qc++) {
       if (w + 16 * R + 15 >= ch[qc].lo && w + 16 * ct <= ch[qc].hi) {   // warp-uniform: does the child reach this tile at all
         const int32_t* inv = INV + qc * r;
@@ -324,10 +307,27 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 1024 / THREADS)
           for (int ni = 0; ni < 2; ni++)
 #pragma unroll
             for (int u = 0; u < 2; u++)
-              if (ci[mi] >= 0 && cj[ni][u] >= 0 && cj[ni][u] <= ci[mi])
-                acc[mi][ni][u] += src[(int64_t)ci[mi] * ldg + cj[ni][u]];
+              if (ci[mi] >= 0 && cj[ni][u] >= 0 && cj[ni][u] <= ci[mi]) gch[mi][ni][u] += src[(int64_t)ci[mi] * ldg + cj[ni][u]];
       }
     }
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    const double* Pa = P + (16 * R + lr) * ldp + lc;
+    const double* Pb = P + (16 * ct + lr) * ldp + lc;
+    for (int k4 = 0; k4 < w8; k4 += 4) {
+      const double a0 = Pa[k4], a1 = Pa[8 * ldp + k4];
+      const double b0 = Pb[k4], b1 = Pb[8 * ldp + k4];
+      front_mma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      front_mma884(acc[0][1][0], acc[0][1][1], a0, b1);
+      front_mma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      front_mma884(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) {
+        acc[mi][ni][0] = gch[mi][ni][0] - acc[mi][ni][0];
+        acc[mi][ni][1] = gch[mi][ni][1] - acc[mi][ni][1];
+      }
 #pragma unroll
     for (int mi = 0; mi < 2; mi++) {
       const int i = 16 * R + 8 * mi + lr;
@@ -690,19 +690,30 @@ int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_
   if (B == 0 || p->S == 0) return THB_OK;
   cudaStream_t cs = thb_cs(stream);
   static size_t fw_set[3] = {0, 0, 0}, bw_set[3] = {0, 0, 0};
+  // one launch per DEPTH and pass (the factor launches of a depth -- split by thread-count class and occupancy bucket -- are
+  // consecutive in `launches` and in sched): the substitutions are short kernels, fewer launches matter more than tuned block sizes
   for (int pass = 0; pass < 2; pass++) {
-    for (int64_t q = 0; q < num_launches; q++) {
-      const int64_t l = pass == 0 ? q : num_launches - 1 - q;   // forward: deepest first; backward: roots first
-      const int64_t* L = launches + l * THB_FRONT_LAUNCH_COLS;
-      const int depth = (int)L[0], cls = (int)L[1], begin = (int)L[2], count = (int)L[3];
+    int64_t q = pass == 0 ? 0 : num_launches - 1;
+    while (q >= 0 && q < num_launches) {
+      const int depth = (int)launches[q * THB_FRONT_LAUNCH_COLS];
+      int64_t q0 = q, q1 = q;   // [q0, q1] = launches of this depth
+      if (pass == 0) { while (q1 + 1 < num_launches && (int)launches[(q1 + 1) * THB_FRONT_LAUNCH_COLS] == depth) q1++; q = q1 + 1; }
+      else { while (q0 - 1 >= 0 && (int)launches[(q0 - 1) * THB_FRONT_LAUNCH_COLS] == depth) q0--; q = q0 - 1; }
+      int begin = (int)launches[q0 * THB_FRONT_LAUNCH_COLS + 2], count = 0;
+      int64_t r_max = 0;
+      for (int64_t l = q0; l <= q1; l++) {
+        const int64_t* L = launches + l * THB_FRONT_LAUNCH_COLS;
+        count += (int)L[3];
+        r_max = L[5] > r_max ? L[5] : r_max;
+      }
       thb::FrontSolveArgs a;
       a.p = *p; a.s0 = begin; a.B = B; a.factor = factor; a.rhs = rhs; a.x = x; a.work = work;
       a.v_cur = varena + (int64_t)(depth & 1) * B * p->varena_size;
       a.v_child = varena + (int64_t)((depth + 1) & 1) * B * p->varena_size;
-      const int kc = cls > 2 ? 2 : cls;
+      const int kc = r_max <= 48 ? 0 : (r_max <= 128 ? 1 : 2);
       const int threads = thb::front_threads_of_class(kc);
-      const int64_t r_max = L[5];   // largest front of the launch (class-3 launches carry np >= r)
       const size_t smem = (size_t)(((r_max + 1) & ~1LL) + 32 * 33 + 1 + (pass == 1 ? threads : 0) + 2) * 8;
+      if (count > 65535) return THB_ERR_UNSUPPORTED;
       const dim3 grid((unsigned)B, (unsigned)count);
       if (pass == 0) {
         if (kc == 0) { int rc = thb::front_set_smem(thb::front_forward_kernel<64>, smem, &fw_set[0]); if (rc) return rc;
