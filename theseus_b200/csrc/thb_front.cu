@@ -690,30 +690,20 @@ int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_
   if (B == 0 || p->S == 0) return THB_OK;
   cudaStream_t cs = thb_cs(stream);
   static size_t fw_set[3] = {0, 0, 0}, bw_set[3] = {0, 0, 0};
-  // one launch per DEPTH and pass (the factor launches of a depth -- split by thread-count class and occupancy bucket -- are
-  // consecutive in `launches` and in sched): the substitutions are short kernels, fewer launches matter more than tuned block sizes
   for (int pass = 0; pass < 2; pass++) {
-    int64_t q = pass == 0 ? 0 : num_launches - 1;
-    while (q >= 0 && q < num_launches) {
-      const int depth = (int)launches[q * THB_FRONT_LAUNCH_COLS];
-      int64_t q0 = q, q1 = q;   // [q0, q1] = launches of this depth
-      if (pass == 0) { while (q1 + 1 < num_launches && (int)launches[(q1 + 1) * THB_FRONT_LAUNCH_COLS] == depth) q1++; q = q1 + 1; }
-      else { while (q0 - 1 >= 0 && (int)launches[(q0 - 1) * THB_FRONT_LAUNCH_COLS] == depth) q0--; q = q0 - 1; }
-      int begin = (int)launches[q0 * THB_FRONT_LAUNCH_COLS + 2], count = 0;
-      int64_t r_max = 0;
-      for (int64_t l = q0; l <= q1; l++) {
-        const int64_t* L = launches + l * THB_FRONT_LAUNCH_COLS;
-        count += (int)L[3];
-        r_max = L[5] > r_max ? L[5] : r_max;
-      }
+    for (int64_t q = 0; q < num_launches; q++) {
+      const int64_t l = pass == 0 ? q : num_launches - 1 - q;   // forward: deepest first; backward: roots first
+      const int64_t* L = launches + l * THB_FRONT_LAUNCH_COLS;
+      const int depth = (int)L[0], cls = (int)L[1], begin = (int)L[2], count = (int)L[3];
       thb::FrontSolveArgs a;
       a.p = *p; a.s0 = begin; a.B = B; a.factor = factor; a.rhs = rhs; a.x = x; a.work = work;
       a.v_cur = varena + (int64_t)(depth & 1) * B * p->varena_size;
       a.v_child = varena + (int64_t)((depth + 1) & 1) * B * p->varena_size;
-      const int kc = r_max <= 48 ? 0 : (r_max <= 128 ? 1 : 2);
+      // (merging the launches of a depth into one was measured: slower -- small fronts on 256-thread CTAs)
+      const int kc = cls > 2 ? 2 : cls;
       const int threads = thb::front_threads_of_class(kc);
+      const int64_t r_max = L[5];   // largest front of the launch (class-3 launches carry np >= r)
       const size_t smem = (size_t)(((r_max + 1) & ~1LL) + 32 * 33 + 1 + (pass == 1 ? threads : 0) + 2) * 8;
-      if (count > 65535) return THB_ERR_UNSUPPORTED;
       const dim3 grid((unsigned)B, (unsigned)count);
       if (pass == 0) {
         if (kc == 0) { int rc = thb::front_set_smem(thb::front_forward_kernel<64>, smem, &fw_set[0]); if (rc) return rc;
