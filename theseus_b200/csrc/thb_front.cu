@@ -141,7 +141,7 @@ struct FrontChild {       // one child of the front this CTA works on (shared me
 
 // Registers are capped at 64 per thread (1 024 threads per SM): the kernel is bound by the latency chain of a CTA, so resident warps count.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 1024 / THREADS)) front_small_kernel(FrontArgs a) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(FrontArgs a) {
   extern __shared__ double sm[];
   const thb_front_plan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -628,7 +628,7 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
   if (B > 65535LL * 32768LL) return THB_ERR_UNSUPPORTED;
   cudaStream_t cs = thb_cs(stream);
   THB_CUDA(cudaMemsetAsync(info, 0, (size_t)B * 4, cs));
-  static size_t smem_set[4] = {0, 0, 0, 0}, asm_set = 0;
+  static size_t smem_set[5] = {0, 0, 0, 0, 0}, asm_set = 0;
   for (int64_t l = 0; l < num_launches; l++) {
     const int64_t* L = launches + l * THB_FRONT_LAUNCH_COLS;
     const int depth = (int)L[0], cls = (int)L[1], begin = (int)L[2], count = (int)L[3];
@@ -650,12 +650,15 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
       } else if (cls == 1) {
         int rc = thb::front_set_smem(thb::front_small_kernel<128>, smem, &smem_set[1]); if (rc) return rc;
         thb::front_small_kernel<128><<<grid, 128, smem, cs>>>(a);
-      } else if (smem <= 113 * 1024) {
+      } else if (smem <= 56 * 1024) {   // class 2 (> 96 rows): threads so that ~32 warps are resident whatever the panel size
         int rc = thb::front_set_smem(thb::front_small_kernel<256>, smem, &smem_set[2]); if (rc) return rc;
         thb::front_small_kernel<256><<<grid, 256, smem, cs>>>(a);
-      } else {   // one CTA per SM anyway: twice the warps for the tile phases
+      } else if (smem <= 113 * 1024) {
         int rc = thb::front_set_smem(thb::front_small_kernel<512>, smem, &smem_set[3]); if (rc) return rc;
         thb::front_small_kernel<512><<<grid, 512, smem, cs>>>(a);
+      } else {                          // one CTA per SM: all 1 024 threads
+        int rc = thb::front_set_smem(thb::front_small_kernel<1024>, smem, &smem_set[4]); if (rc) return rc;
+        thb::front_small_kernel<1024><<<grid, 1024, smem, cs>>>(a);
       }
       THB_CHECK_LAUNCH();
     } else {

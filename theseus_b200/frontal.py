@@ -176,7 +176,7 @@ def small_smem_bytes(w: int, b: int, nchildren: int = 0) -> int:
     return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 3 * SMALL_MAX_CHILDREN + 2 + (min(nchildren, SMALL_MAX_CHILDREN) * (w + b) + 1) // 2) * 8
 
 
-SPLIT_MAX_W = 96         # pivot columns of one piece when a wide supernode is split into a chain of fronts
+SPLIT_MAX_W = int(__import__("os").environ.get("THB_FRONT_SPLIT_W", "96"))   # pivot columns of one piece when a wide supernode is split into a chain
 SPLIT_ROOT_W = 256       # borderless fronts wider than this stay whole (dense path)
 SMALL_MAX_CHILDREN = 8   # thb_front.cu FRONT_MAX_CHILDREN: the gather kernel keeps its children's descriptors in registers
 SMALL_MAX_W = 192    # pivot block columns of 8 are factored one after the other inside the CTA: wider pivot blocks go to the dense kernel

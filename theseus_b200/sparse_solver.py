@@ -209,7 +209,7 @@ class BaspachoSparseSolver(LinearSolver):
         s = _lib.stream_ptr()
         # the factor of every item stays resident ([B, data_size]: the substitutions and the backward pass need it); the update-matrix
         # arena, the border-vector arena and the dense workspace are per CHUNK of the batch (C5: 21 MB of arena per item)
-        chunk = int(min(B, self._front_options.get("chunk", 1024)))
+        chunk = int(min(B, self._front_options.get("chunk", int(os.environ.get("THB_FRONT_CHUNK", "1024")))))
         if d["bufs"].get("key") != (B, "front"):
             ws_bytes = int(lib.thb_potrf_partial_workspace_bytes(chunk, d["max_np"])) if d["max_np"] else 0
             d["bufs"] = dict(key=(B, "front"), chunk=chunk, factor=torch.empty(B, P.data_size, dtype=torch.float64, device=device),
