@@ -458,7 +458,7 @@ typedef struct thb_front_plan {
    * the shared-memory kernel GATHERS the children's update matrices through it (no scatter, no barriers) */
   const int64_t* c_inv_ptr; const int32_t* c_inv;
   /* flat descriptors of the shared-memory kernel: fd[q] (q = position in sched) = (front, w, b, f_first, f_panel_off, f_cb_off, f_cb_ld,
-   * child_begin | nchildren << 32);  pc[child_begin + k] = (f_cb_off, f_cb_ld, first and last front row reached, offset of the inverse
+   * child_begin | nchildren << 32);  pc[child_begin + k] = (f_cb_off, f_cb_ld | b << 32, first and last front row reached, offset of the inverse
    * map in c_inv, f_u_off) of the front's k-th child */
   const int64_t* fd; const int64_t* pc;
   /* panel map: pmap[o] for offset o of one item's factor storage = offset of that AtA entry in the COMPACT block storage written by

@@ -17,6 +17,8 @@
 //   shuffles, the rest of the panel is a row-contiguous mat-vec; the forward pass hands border vectors to the parent through a
 //   second ping-pong arena, the backward pass gathers the ancestors' solution.  The permutation is folded into the first load /
 //   last store.  No atomics on data anywhere: bitwise reproducible, independent of B.
+#include <stdlib.h>
+
 #include "thb_common.cuh"
 
 namespace thb {
@@ -52,6 +54,7 @@ struct FrontArgs {
   double* arena_cur;        // [B, arena_size] of this depth's parity
   const double* arena_child;
   int32_t* info;
+  int prefetch;             // ask L2 for the children's update matrices at kernel start (THB_FRONT_PREFETCH=0 switches it off: A/B runs)
   const double* ata;        // [B, ata_stride] compact AtA blocks (thb_gram_f64 with the plan's compact offsets), or null: the panels
   int64_t ata_stride;       //   in `factor` already hold AtA (zero-filled + scattered by the caller: the extlib-style flow)
 };
@@ -169,14 +172,24 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
   // ---- children descriptors and inverse maps go to shared memory (one round trip, then every lookup is on chip) ----
   for (int q = 0; q < nch; q++) {
     const int64_t* PC = p.pc + (int64_t)(c_begin + q) * 6;   // (cb_off, cb_ld, lo, hi, inv_off, u_off) of this child
+    const double* csrc = a.arena_child + item * p.arena_size + PC[0];
+    const int cld = (int)(PC[1] & 0xffffffffLL), cbc = (int)(PC[1] >> 32);
     if (tid == 0) {
-      ch[q].src = a.arena_child + item * p.arena_size + PC[0];
-      ch[q].ldg = (int)PC[1];
+      ch[q].src = csrc;
+      ch[q].ldg = cld;
       ch[q].lo = (int)PC[2];
       ch[q].hi = (int)PC[3];
     }
     const int32_t* inv = p.c_inv + PC[4];
     for (int l = tid; l < r; l += THREADS) INV[q * r + l] = inv[l];
+#ifndef THB_SIMT_EMU
+    // the child's update matrix (lower triangle) is read element by element by the gathers below: ask L2 for its lines now, so that the
+    // gathers find them on chip (fire and forget: no register, no stall; the ncu source view showed 45 % of all stall samples on those loads)
+    for (int off = tid * 16; a.prefetch != 0 && off < cbc * cld; off += THREADS * 16) {
+      const int i = off / cld, j = off - i * cld;
+      if (j <= i) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(csrc + off));
+    }
+#endif
   }
   for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
   __syncthreads();
@@ -629,12 +642,18 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
   cudaStream_t cs = thb_cs(stream);
   THB_CUDA(cudaMemsetAsync(info, 0, (size_t)B * 4, cs));
   static size_t smem_set[5] = {0, 0, 0, 0, 0}, asm_set = 0;
+  static int front_prefetch_flag = -1;
+  if (front_prefetch_flag < 0) {
+    const char* e = getenv("THB_FRONT_PREFETCH");
+    front_prefetch_flag = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
   for (int64_t l = 0; l < num_launches; l++) {
     const int64_t* L = launches + l * THB_FRONT_LAUNCH_COLS;
     const int depth = (int)L[0], cls = (int)L[1], begin = (int)L[2], count = (int)L[3];
     thb::FrontArgs a;
     a.p = *p; a.s0 = begin; a.B = B; a.factor = factor; a.alpha = alpha; a.beta = beta; a.info = info;
     a.ata = (ata != nullptr && p->pmap != nullptr) ? ata : nullptr; a.ata_stride = ata_stride;
+    a.prefetch = front_prefetch_flag;
     a.arena_cur = arena + (int64_t)(depth & 1) * B * p->arena_size;
     a.arena_child = arena + (int64_t)((depth + 1) & 1) * B * p->arena_size;
     if (cls < 3) {

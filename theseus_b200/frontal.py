@@ -542,7 +542,8 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
     for t in range(S):
         for k, c in enumerate(children[t]):
             rel = f_rel[rel_ptr[c]:rel_ptr[c + 1]]
-            pc[int(child_ptr[t]) + k] = (int(f_cb_off[c]), int(f_cb_ld[c]), int(rel[0]), int(rel[-1]), int(c_inv_ptr[c]), int(f_u_off[c]))
+            pc[int(child_ptr[t]) + k] = (int(f_cb_off[c]), int(f_cb_ld[c]) | (int(f_b[c]) << 32), int(rel[0]), int(rel[-1]), int(c_inv_ptr[c]),
+                                         int(f_u_off[c]))
     flops = float(sum(_front_cost(float(f_w[t]), float(f_b[t])) for t in range(S)))
     stats = dict(ordering=oname, column_flops=col_flops, flops=flops, nnz_L=float(sum(int(f_r[t]) * int(f_w[t]) for t in range(S))),
                  fronts=float(S), max_front=float(f_r.max()) if S else 0.0, depth=float(max_depth + 1), big_fronts=float((f_class == 3).sum()),
