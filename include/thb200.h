@@ -434,7 +434,7 @@ int thb_gram_dense_f64(const double* A, double* AtA, int64_t B, int64_t m, int64
  *   child -> parent maps: f_rel[rel_ptr[c] .. rel_ptr[c+1]) = local row index in the parent front of child c's border rows.
  * `launches` is a HOST array [num_launches][12] (int64) in factorisation order (deepest fronts first):
  *   (depth, class, begin, count [into sched], dynamic smem bytes of the factor kernel, largest front of the launch [np for class 3],
- *    pivot block columns, f_fr_off, f_first [info base], front index, w, b) -- the last six for class-3 launches (one front each).
+ *    largest panel (r * w) of the launch [pivot block columns for class 3], f_fr_off, f_first [info base], front index, w, b) -- the last six for class-3 launches (one front each).
  * No atomics on data: results are bitwise reproducible and independent of the batch size.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct thb_front_plan {

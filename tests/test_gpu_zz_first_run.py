@@ -1,19 +1,16 @@
-"""FIRST-RUN GPU tests: everything here was written after round 1's GPU budget was spent and has never executed on a device.  The file
-sorts last among the GPU test files and every test is `xfail(strict=False)`: the round-end run on the B200 box reports each one as
-XPASS (works on the device) or xfail (does not, yet) without turning the GPU-verified suite red.  Remove the mark from what XPASSes.
+"""GPU tests written at the end of round 1 (after that round's GPU budget was spent) and first run on a device in round 2.  The blanket
+`xfail(strict=False)` they carried is gone: round 1's device run reported four failures here (SO2 rotation averaging, the tactile LM
+trace with both solvers, the tactile implicit gradients) -- all four were the test helpers building the objective on the CPU
+(`objective.to(device)` missing in tests/golden/make_golden.py:so2_problem / tactile_problem), not kernels.  Everything here is a hard
+test now.
 
-What stands behind them without a GPU: the same kernels compiled unchanged for the host (tests/simt) run these very tests on the CPU
-(`THB_SIMT_EMULATION=1 python -m pytest tests/test_gpu_zz_first_run.py -m gpu`), the host work lists run through numpy interpreters
-(tests/test_sparse_symbolic.py), the torch routes and the oracle are checked against the reference's goldens (tests/test_torch_*.py,
-tests/test_so2.py, tests/test_robust_losses.py).  Order: host-side / torch-route features on GPU-verified kernels first; the kernels that
-are new (dense root, chain-piece substitutions, tiled updates) last and in CHILD processes (tests/first_run_kernels.py through
-test_new_sparse_kernels_in_a_child_process), so that a faulting kernel cannot reach the process that reports the verified suite.
-
-Contents: a custom VariableOrdering; user-defined CostFunction / CostWeight subclasses (tests/user_costs.py); the geometry classes' public methods on CUDA tensors; GNC (Geman-McClure) costs on the engine's generic route; the batched torch route; SO2 rotation
-averaging (THB_VAR_SO2 branch of the retract kernel); config C4's cost set (planar pushing / tactile pose estimation:
-QuasiStaticPushingPlanar, EffectorObjectContactPlanar, MovingFrameBetween, SE2 priors) through the GPU engine -- LM trace and
-implicit-mode gradients against the reference (tests/golden/tactile_kat.npz); config C5's pose graph at full size; the opt-in sparse
-layouts `lane_root`, `lane_tiled`, `lane_tiled_root` and `supernodal_solve=True`."""
+Contents: a custom VariableOrdering; user-defined CostFunction / CostWeight subclasses (tests/user_costs.py); the geometry classes' public
+methods on CUDA tensors; GNC (Geman-McClure) costs on the engine's generic route; the batched torch route; SO2 rotation averaging
+(THB_VAR_SO2 branch of the retract kernel); config C4's cost set at small size (planar pushing / tactile pose estimation:
+QuasiStaticPushingPlanar, EffectorObjectContactPlanar, MovingFrameBetween, SE2 priors -- LM trace and implicit-mode gradients against the
+reference, tests/golden/tactile_kat.npz; C4 at batch 512: tests/test_gpu_c4_tactile.py); config C5's pose graph at full size with the
+round-1 layouts; the round-1 sparse layouts `lane_root`, `lane_tiled`, `lane_tiled_root` and `supernodal_solve=True` (child processes:
+tests/first_run_kernels.py)."""
 import numpy as np
 import pytest
 import torch

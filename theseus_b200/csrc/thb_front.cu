@@ -487,6 +487,8 @@ struct FrontSolveArgs {
   double* work;             // [B, n] permuted: y after the forward pass, x after the backward pass
   double* v_cur;            // border vectors of this depth's parity
   const double* v_child;
+  int stage_doubles;        // panels of at most this many doubles are staged in shared memory at kernel start (one coalesced pass) and
+                            // every later read is on chip; larger panels are streamed chunk by chunk from global memory
 };
 
 // One warp: solve T y = u (lower triangular cw x cw, row stride 33) -- lane i owns u_i
@@ -522,6 +524,11 @@ __global__ void __launch_bounds__(THREADS) front_forward_kernel(FrontSolveArgs a
   double* u = sm;            // [r]
   double* T = sm + ((r + 1) & ~1);   // [32][33]
   const double* Lg = a.factor + item * p.data_size + FD[4];
+  if (r * w <= a.stage_doubles) {
+    double* Ls = T + 32 * 33 + 1 + (THREADS & ~1) + 2;
+    for (int e = tid; e < r * w; e += THREADS) Ls[e] = Lg[e];
+    Lg = Ls;
+  }
   {
     // u = [rhs of the pivots; 0] + the children's border vectors, GATHERED through the inverse maps (fixed child order, no barriers)
     const int c0 = (int)(FD[7] & 0xffffffffLL), nchild = (int)(FD[7] >> 32);
@@ -578,6 +585,11 @@ __global__ void __launch_bounds__(THREADS) front_backward_kernel(FrontSolveArgs 
   double* T = sm + ((r + 1) & ~1);       // [32][33]
   double* part = T + 32 * 33 + 1;        // [THREADS]
   const double* Lg = a.factor + item * p.data_size + FD[4];
+  if (r * w <= a.stage_doubles) {
+    double* Ls = T + 32 * 33 + 1 + (THREADS & ~1) + 2;
+    for (int e = tid; e < r * w; e += THREADS) Ls[e] = Lg[e];
+    Lg = Ls;
+  }
   double* wk = a.work + item * p.n;
   const int32_t* rows = p.f_rows + p.rows_ptr[t];
   for (int i = tid; i < r; i += THREADS) xf[i] = i < w ? wk[first + i] : wk[rows[i - w]];
@@ -725,7 +737,10 @@ int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_
       const int kc = cls > 2 ? 2 : cls;
       const int threads = thb::front_threads_of_class(kc);
       const int64_t r_max = L[5];   // largest front of the launch (class-3 launches carry np >= r)
-      const size_t smem = (size_t)(((r_max + 1) & ~1LL) + 32 * 33 + 1 + (pass == 1 ? threads : 0) + 2) * 8;
+      // panels up to 40 KB are staged on chip (L[6] = largest r * w of a shared-memory launch; class-3 launches stream)
+      const int64_t stage = (cls < 3 && L[6] > 0) ? (L[6] < 5120 ? L[6] : 5120) : 0;
+      a.stage_doubles = (int)stage;
+      const size_t smem = (size_t)(((r_max + 1) & ~1LL) + 32 * 33 + 1 + threads + 2 + stage + 2) * 8;
       const dim3 grid((unsigned)B, (unsigned)count);
       if (pass == 0) {
         if (kc == 0) { int rc = thb::front_set_smem(thb::front_forward_kernel<64>, smem, &fw_set[0]); if (rc) return rc;

@@ -527,7 +527,8 @@ def build_front_plan(param_size, ptrs, inds, ordering: str = "auto", tau: float 
             while j < S and int(f_depth[sched[j]]) == d and int(f_class[sched[j]]) == c and int(f_bucket[sched[j]]) == bk:
                 j += 1
             smem = max(small_smem_bytes(int(f_w[q]), int(f_b[q]), len(children[q])) for q in sched[i:j])
-            launches.append((d, c, i, j - i, smem, max(int(f_r[q]) for q in sched[i:j]), 0, 0, 0, 0, 0, 0))
+            launches.append((d, c, i, j - i, smem, max(int(f_r[q]) for q in sched[i:j]), max(int(f_r[q]) * int(f_w[q]) for q in sched[i:j]),
+                             0, 0, 0, 0, 0))
         else:   # one front: (.., np, pivot block columns, offset of F in the arena, first pivot [info base], front index)
             launches.append((d, c, i, 1, 0, int(f_np[t]), int(f_wpad[t]) // BIG_TW, int(f_fr_off[t]), int(f_first[t]), t, int(f_w[t]), int(f_b[t])))
         i = j
