@@ -80,6 +80,9 @@ __device__ __forceinline__ double front_panel_in(const FrontArgs& a, const doubl
 //   3. update matrix: per 16 x 16 tile of the lower triangle, -P_I P_J^T by DMMA straight from the panel, plus the gathered children,
 //      written once from registers.
 constexpr int FRONT_WD_LD = 20;
+#ifndef FRONT_PL
+#define FRONT_PL 4   // panel elements a thread gathers per pass (their global loads are in flight together; 8 measured 2 % slower)
+#endif
 constexpr int FRONT_MAX_CHILDREN = 8;   // fronts with more children are assembled by the scatter kernel of the dense path (frontal.py)
 
 __host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b, int nchildren) {
@@ -199,12 +202,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
     const double al = a.alpha != nullptr ? a.alpha[item] : 0.0;
     const double be = a.beta != nullptr ? a.beta[item] : 0.0;
     const int total = r * w;
-    // four panel elements per thread and pass: their global loads (AtA entry + one per contributing child) are independent and in flight together
-    for (int e0 = tid; e0 < total; e0 += 4 * THREADS) {
-      int ii[4], jj[4];
-      double v[4];
+    // FRONT_PL panel elements per thread and pass: their global loads (AtA entry + one per contributing child) are independent and in flight together
+    for (int e0 = tid; e0 < total; e0 += FRONT_PL * THREADS) {
+      int ii[FRONT_PL], jj[FRONT_PL];
+      double v[FRONT_PL];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < FRONT_PL; u++) {
         const int e = e0 + u * THREADS;
         ii[u] = e / w;
         jj[u] = e - ii[u] * w;
@@ -212,14 +215,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
         v[u] = ii[u] >= 0 ? front_panel_in(a, Lg, f_panel_off, item, e) : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int u = 0; u < FRONT_PL; u++)
         if (ii[u] >= 0 && ii[u] == jj[u]) v[u] = v[u] + (al * v[u] + be);   // linear/utils.py:14-33: diag <- diag (1 + alpha) + beta
       for (int q = 0; q < nch; q++) {
         const double* src = ch[q].src;
         const int ldg = ch[q].ldg, lo = ch[q].lo, hi = ch[q].hi;
         const int32_t* inv = INV + q * r;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < FRONT_PL; u++) {
           if (ii[u] >= lo && jj[u] <= hi) {
             const int ci = inv[ii[u]], cj = inv[jj[u]];
             if (ci >= 0 && cj >= 0) v[u] += src[(int64_t)ci * ldg + cj];
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int u = 0; u < FRONT_PL; u++)
         if (ii[u] >= 0) PN[(ii[u] < w ? ii[u] : ii[u] + (w8 - w)) * ldp + jj[u]] = v[u];
     }
   }
@@ -382,27 +385,64 @@ __global__ void __launch_bounds__(ASM_THREADS) front_assemble_kernel(FrontArgs a
     const double alg = a.alpha != nullptr ? a.alpha[item] : 0.0;
     const double beg = a.beta != nullptr ? a.beta[item] : 0.0;
     double* Fg = a.arena_cur + item * p.arena_size + p.f_fr_off[t] + (int64_t)R0 * np;
-    for (int e = tid; e < ASM_ROWS * nc; e += ASM_THREADS) {
-      const int rr = e / nc, fc = e - rr * nc;
-      const int fr = R0 + rr;
-      const int li = fr < w ? fr : ((fr >= wpad && fr - wpad + w < r) ? fr - wpad + w : -1);
-      const int lj = fc < w ? fc : ((fc >= wpad && fc - wpad + w < r) ? fc - wpad + w : -1);
-      double v = 0.0;
-      if (li < 0 || lj < 0) {
-        v = (fr == fc) ? 1.0 : 0.0;          // identity on the padding
-      } else if (lj <= li) {
-        if (lj < w) {
-          v = front_panel_in(a, Lgg, p.f_panel_off[t], item, (int64_t)li * w + lj);
-          if (li == lj) v = v + (alg * v + beg);
-        }
-        for (int q = 0; q < n_children; q++) {
-          const int c = p.child_list[c_first + q];
-          const int32_t* inv = p.c_inv + p.c_inv_ptr[c];
-          const int ci = inv[li], cj = inv[lj];
-          if (ci >= 0 && cj >= 0) v += a.arena_child[item * p.arena_size + p.f_cb_off[c] + (int64_t)ci * p.f_cb_ld[c] + cj];
+    // children descriptors once per CTA (the per-element chain child_list -> c_inv_ptr -> inv -> update matrix was four dependent
+    // global loads per child and element); then four entries per thread and pass, their loads in flight together
+    __shared__ const double* s_src[FRONT_MAX_CHILDREN];
+    __shared__ const int32_t* s_inv[FRONT_MAX_CHILDREN];
+    __shared__ int s_ld[FRONT_MAX_CHILDREN];
+    if (tid < n_children) {
+      const int c = p.child_list[c_first + tid];
+      s_src[tid] = a.arena_child + item * p.arena_size + p.f_cb_off[c];
+      s_inv[tid] = p.c_inv + p.c_inv_ptr[c];
+      s_ld[tid] = p.f_cb_ld[c];
+    }
+    __syncthreads();
+    const int64_t poff = p.f_panel_off[t];
+    const int total = ASM_ROWS * nc;
+    for (int e0 = tid; e0 < total; e0 += 4 * ASM_THREADS) {
+      int li[4], lj[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * ASM_THREADS;
+        const int rr = e / nc, fc = e - rr * nc;
+        const int fr = R0 + rr;
+        li[u] = fr < w ? fr : ((fr >= wpad && fr - wpad + w < r) ? fr - wpad + w : -1);
+        lj[u] = fc < w ? fc : ((fc >= wpad && fc - wpad + w < r) ? fc - wpad + w : -1);
+        v[u] = 0.0;
+        if (e >= total) {
+          li[u] = lj[u] = -2;                         // past the end: nothing to store
+        } else if (li[u] < 0 || lj[u] < 0) {
+          v[u] = (fr == fc) ? 1.0 : 0.0;              // identity on the padding
+          li[u] = -1;
+        } else if (lj[u] > li[u]) {
+          li[u] = -1;                                 // above the diagonal: zero
+        } else if (lj[u] < w) {
+          v[u] = front_panel_in(a, Lgg, poff, item, (int64_t)li[u] * w + lj[u]);
         }
       }
-      Fg[(int64_t)rr * np + fc] = v;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (li[u] >= 0 && li[u] == lj[u] && lj[u] < w) v[u] = v[u] + (alg * v[u] + beg);
+      for (int q = 0; q < n_children; q++) {
+        const double* src = s_src[q];
+        const int32_t* inv = s_inv[q];
+        const int ldg = s_ld[q];
+        int ci[4], cj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          ci[u] = li[u] >= 0 ? inv[li[u]] : -1;
+          cj[u] = li[u] >= 0 ? inv[lj[u]] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (ci[u] >= 0 && cj[u] >= 0) v[u] += src[(int64_t)ci[u] * ldg + cj[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * ASM_THREADS;
+        if (e < total) Fg[e + (int64_t)(e / nc) * (np - nc)] = v[u];
+      }
     }
     return;
   }
@@ -557,6 +597,8 @@ __global__ void __launch_bounds__(THREADS) front_forward_kernel(FrontSolveArgs a
       if (lane < cw) u[k0 + lane] = ui;
     }
     __syncthreads();
+    // rows below the chunk, one row per thread: its 32 consecutive doubles are two cache lines, read once from DRAM (the variant with
+    // G lanes per row and a shuffle reduction measured 5-30 % slower: profiles/README_r02.md)
     for (int i = k0 + cw + tid; i < r; i += THREADS) {
       const double* row = Lg + (int64_t)i * w + k0;
       double s = 0.0;
@@ -600,14 +642,26 @@ __global__ void __launch_bounds__(THREADS) front_backward_kernel(FrontSolveArgs 
     // t_k = y_k - sum_{i >= k0 + cw} L[i][k0 + k] x_i : cw consecutive threads per row, THREADS / cw rows per pass
     const int RG = THREADS / cw;
     const int kk = tid % cw, rg = tid / cw;
-    double acc = 0.0;
-    if (rg < RG)
-      for (int i = k0 + cw + rg; i < r; i += RG) acc += Lg[(int64_t)i * w + k0 + kk] * xf[i];
-    part[tid] = acc;
     for (int e = tid; e < cw * cw; e += THREADS) {
       const int i = e / cw, j = e - i * cw;
       T[i * 33 + j] = Lg[(int64_t)(k0 + i) * w + k0 + j];
     }
+    double acc = 0.0;
+    if (rg < RG) {
+      // four loads in flight per thread, summed in row order (the un-unrolled loop had one: ncu, 68 % of the samples on its load)
+      const double* col = Lg + k0 + kk;
+      int i = k0 + cw + rg;
+      for (; i + 3 * RG < r; i += 4 * RG) {
+        const double l0 = col[(int64_t)i * w], l1 = col[(int64_t)(i + RG) * w], l2 = col[(int64_t)(i + 2 * RG) * w],
+                     l3 = col[(int64_t)(i + 3 * RG) * w];
+        acc += l0 * xf[i];
+        acc += l1 * xf[i + RG];
+        acc += l2 * xf[i + 2 * RG];
+        acc += l3 * xf[i + 3 * RG];
+      }
+      for (; i < r; i += RG) acc += col[(int64_t)i * w] * xf[i];
+    }
+    part[tid] = acc;
     __syncthreads();
     if (warp == 0) {
       double tk = 0.0;
@@ -654,6 +708,9 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
   cudaStream_t cs = thb_cs(stream);
   THB_CUDA(cudaMemsetAsync(info, 0, (size_t)B * 4, cs));
   static size_t smem_set[5] = {0, 0, 0, 0, 0}, asm_set = 0;
+  // tuning knobs: threads per CTA of the two smallest classes (THB_FRONT_T0: 64 | 128 | 256, THB_FRONT_T1: 128 | 256)
+  static const int thr_cls[2] = {[] { const char* e = getenv("THB_FRONT_T0"); const int v = e ? atoi(e) : 64; return (v == 128 || v == 256) ? v : 64; }(),
+                                 [] { const char* e = getenv("THB_FRONT_T1"); const int v = e ? atoi(e) : 128; return v == 256 ? 256 : 128; }()};
   static int front_prefetch_flag = -1;
   if (front_prefetch_flag < 0) {
     const char* e = getenv("THB_FRONT_PREFETCH");
@@ -675,13 +732,13 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
 #endif
       const dim3 grid((unsigned)B, (unsigned)count);
       if (count > 65535) return THB_ERR_UNSUPPORTED;
-      if (cls == 0) {
+      if (cls == 0 && thr_cls[0] == 64) {
         int rc = thb::front_set_smem(thb::front_small_kernel<64>, smem, &smem_set[0]); if (rc) return rc;
         thb::front_small_kernel<64><<<grid, 64, smem, cs>>>(a);
-      } else if (cls == 1) {
+      } else if ((cls == 0 && thr_cls[0] == 128) || (cls == 1 && thr_cls[1] == 128)) {
         int rc = thb::front_set_smem(thb::front_small_kernel<128>, smem, &smem_set[1]); if (rc) return rc;
         thb::front_small_kernel<128><<<grid, 128, smem, cs>>>(a);
-      } else if (smem <= 56 * 1024) {   // class 2 (> 96 rows): threads so that ~32 warps are resident whatever the panel size
+      } else if (cls <= 1 || smem <= 56 * 1024) {   // class 2 (> 96 rows): threads so that ~32 warps are resident whatever the panel size
         int rc = thb::front_set_smem(thb::front_small_kernel<256>, smem, &smem_set[2]); if (rc) return rc;
         thb::front_small_kernel<256><<<grid, 256, smem, cs>>>(a);
       } else if (smem <= 113 * 1024) {
@@ -724,6 +781,8 @@ int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_
   if (B == 0 || p->S == 0) return THB_OK;
   cudaStream_t cs = thb_cs(stream);
   static size_t fw_set[3] = {0, 0, 0}, bw_set[3] = {0, 0, 0};
+  // tuning knob: largest panel (doubles) the substitution kernels stage in shared memory
+  static const int64_t stage_cap = [] { const char* e = getenv("THB_SOLVE_STAGE"); return e != nullptr ? (int64_t)atoll(e) : (int64_t)0; }();
   for (int pass = 0; pass < 2; pass++) {
     for (int64_t q = 0; q < num_launches; q++) {
       const int64_t l = pass == 0 ? q : num_launches - 1 - q;   // forward: deepest first; backward: roots first
@@ -738,7 +797,7 @@ int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_
       const int threads = thb::front_threads_of_class(kc);
       const int64_t r_max = L[5];   // largest front of the launch (class-3 launches carry np >= r)
       // panels up to 40 KB are staged on chip (L[6] = largest r * w of a shared-memory launch; class-3 launches stream)
-      const int64_t stage = (cls < 3 && L[6] > 0) ? (L[6] < 5120 ? L[6] : 5120) : 0;
+      const int64_t stage = (cls < 3 && L[6] > 0) ? (L[6] < stage_cap ? L[6] : stage_cap) : 0;
       a.stage_doubles = (int)stage;
       const size_t smem = (size_t)(((r_max + 1) & ~1LL) + 32 * 33 + 1 + threads + 2 + stage + 2) * 8;
       const dim3 grid((unsigned)B, (unsigned)count);
