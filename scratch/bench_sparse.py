@@ -15,7 +15,7 @@ t0 = time.time()
 objective, poses = build_pose_graph_objective(th, data, torch.device("cuda", 0))
 opt = th.LevenbergMarquardt(objective, linear_solver_cls=th.BaspachoSparseSolver, linearization_cls=th.SparseLinearization,
                             max_iterations=iters, abs_err_tolerance=0, rel_err_tolerance=0, linear_solver_kwargs=dict(layout=layout, supernodal_solve=supernodal),
-                            cuda_graph="graph" in sys.argv[4:])
+                            cuda_graph=("graph" in sys.argv[4:] or os.environ.get("BENCH_GRAPH") == "1"))
 print("objective+symbolic", round(time.time() - t0, 1), "s", opt.linear_solver.symbolic_stats, flush=True)
 kw = dict(damping=1e-3, adaptive_damping=True, ellipsoidal_damping=True)
 inputs = {p.name: data["poses"][i].cuda() for i, p in enumerate(poses)}

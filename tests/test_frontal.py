@@ -169,6 +169,10 @@ def test_front_kernels_on_the_host_emulation(monkeypatch, emulated, case):
     M = AtA.copy(); M[:, idx, idx] = M[:, idx, idx] * (1 + alpha[:, None]) + 1e-6
     ref = np.linalg.solve(M, Atb[..., None])[..., 0]
     assert np.abs(x - ref).max() <= 1e-11 * np.linalg.cond(M).max() * max(1.0, np.abs(ref).max())
+    # A^T b and diag(A^T A) of the Gram pass: what the LM accept test reads from the linearization instead of a second Atb kernel
+    bufs = solver._dev["bufs"]
+    assert np.allclose(bufs["Atb"].numpy(), Atb, rtol=1e-12, atol=1e-12)
+    assert np.allclose(bufs["AtA_diag"].numpy(), AtA[:, idx, idx], rtol=1e-12, atol=1e-12)
 
 
 def test_front_kernels_report_a_non_positive_pivot(monkeypatch, emulated):

@@ -23,6 +23,36 @@
 
 namespace thb {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may start while its predecessor in the stream drains;
+// its CTAs run their prologue (plan descriptors, inverse maps, zero fill -- nothing the predecessor writes) and then wait for the
+// predecessor's completion (griddepcontrol.wait, which also orders its memory) before the first dependent read or any global write.
+// ~300 launches per linear solve of 10-200 us each: the launch gap, the tail of the last wave and the prologue are what this was meant to
+// hide.  MEASURED (C5, B = 512): numeric phase unchanged, substitutions 7.6 -> 11.4 ms (early CTAs sit on the SMs' thread slots while
+// they wait) -- so the attribute is only set with THB_FRONT_PDL=1; without it the two instructions are no-ops.
+#ifdef THB_SIMT_EMU
+#define THB_PDL_TRIGGER() do { } while (0)
+#define THB_PDL_WAIT() do { } while (0)
+#define FRONT_LAUNCH(K, grid, block, smem, cs, arg) K<<<grid, block, smem, cs>>>(arg)
+#else
+#define THB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define THB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define FRONT_LAUNCH(K, grid, block, smem, cs, arg) thb::front_launch_pdl(K, grid, block, smem, cs, arg)
+static inline bool front_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("THB_FRONT_PDL"); return e != nullptr && e[0] == '1'; }();   // opt-in: measured SLOWER at C5 B=512 (substitutions 7.6 -> 11.4 ms)
+  return on;
+}
+template <typename A>
+static inline void front_launch_pdl(void (*kernel)(A), dim3 grid, dim3 block, size_t smem, cudaStream_t cs, const A& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = cs;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = front_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, arg);   // errors surface through THB_CHECK_LAUNCH (cudaGetLastError) at the call site
+}
+#endif
+
 #ifdef THB_SIMT_EMU
 // host emulation (tests/simt): the m8n8k4 fragment semantics with shuffles
 __device__ inline void front_mma884(double& c0, double& c1, double a, double b) {
@@ -156,6 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
   const int64_t item = blockIdx.x;
   // flat descriptors (frontal.py): one record per front in LAUNCH order, one per (parent, child) pair in the parent's child order --
   // two dependent loads from kernel start to the first data load instead of five through the per-field arrays
+  THB_PDL_TRIGGER();
   const int64_t* FD = p.fd + (int64_t)(a.s0 + blockIdx.y) * 8;
   const int t = (int)FD[0];
   const int w = (int)FD[1], b = (int)FD[2], r = w + b;
@@ -185,16 +216,23 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
     }
     const int32_t* inv = p.c_inv + PC[4];
     for (int l = tid; l < r; l += THREADS) INV[q * r + l] = inv[l];
+    (void)cbc;
+  }
+  for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
+  THB_PDL_WAIT();   // everything above reads the plan only; below: the children's update matrices, AtA, and every global write
 #ifndef THB_SIMT_EMU
-    // the child's update matrix (lower triangle) is read element by element by the gathers below: ask L2 for its lines now, so that the
-    // gathers find them on chip (fire and forget: no register, no stall; the ncu source view showed 45 % of all stall samples on those loads)
-    for (int off = tid * 16; a.prefetch != 0 && off < cbc * cld; off += THREADS * 16) {
+  // the children's update matrices (lower triangles) are read element by element by the gathers below: ask L2 for their lines now, so that
+  // the gathers find them on chip (fire and forget: no register, no stall; the ncu source view showed 45 % of all stall samples on those loads)
+  for (int q = 0; a.prefetch != 0 && q < nch; q++) {
+    const int64_t* PC = p.pc + (int64_t)(c_begin + q) * 6;
+    const double* csrc = a.arena_child + item * p.arena_size + PC[0];
+    const int cld = (int)(PC[1] & 0xffffffffLL), cbc = (int)(PC[1] >> 32);
+    for (int off = tid * 16; off < cbc * cld; off += THREADS * 16) {
       const int i = off / cld, j = off - i * cld;
       if (j <= i) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(csrc + off));
     }
-#endif
   }
-  for (int e = tid; e < prow * ldp; e += THREADS) sm[e] = 0.0;
+#endif
   __syncthreads();
   if (tid < w8 - w) PN[(w + tid) * ldp + w + tid] = 1.0;   // identity on the padding of the pivot block
   double* Lg = a.factor + item * p.data_size + f_panel_off;
@@ -558,9 +596,11 @@ __global__ void __launch_bounds__(THREADS) front_forward_kernel(FrontSolveArgs a
   const thb_front_plan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t item = blockIdx.x;
+  THB_PDL_TRIGGER();
   const int64_t* FD = p.fd + (int64_t)(a.s0 + blockIdx.y) * 8;   // flat descriptor of the front (frontal.py)
   const int t = (int)FD[0];
   const int w = (int)FD[1], b = (int)FD[2], r = w + b, first = (int)FD[3];
+  THB_PDL_WAIT();
   double* u = sm;            // [r]
   double* T = sm + ((r + 1) & ~1);   // [32][33]
   const double* Lg = a.factor + item * p.data_size + FD[4];
@@ -620,9 +660,11 @@ __global__ void __launch_bounds__(THREADS) front_backward_kernel(FrontSolveArgs 
   const thb_front_plan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t item = blockIdx.x;
+  THB_PDL_TRIGGER();
   const int64_t* FD = p.fd + (int64_t)(a.s0 + blockIdx.y) * 8;
   const int t = (int)FD[0];
   const int w = (int)FD[1], b = (int)FD[2], r = w + b, first = (int)FD[3];
+  THB_PDL_WAIT();
   double* xf = sm;                       // [r] pivots (y, then x) followed by the border rows' x
   double* T = sm + ((r + 1) & ~1);       // [32][33]
   double* part = T + 32 * 33 + 1;        // [THREADS]
@@ -734,19 +776,19 @@ int thb_front_factor_f64(const thb_front_plan* p, const int64_t* launches, int64
       if (count > 65535) return THB_ERR_UNSUPPORTED;
       if (cls == 0 && thr_cls[0] == 64) {
         int rc = thb::front_set_smem(thb::front_small_kernel<64>, smem, &smem_set[0]); if (rc) return rc;
-        thb::front_small_kernel<64><<<grid, 64, smem, cs>>>(a);
+        FRONT_LAUNCH(thb::front_small_kernel<64>, grid, 64, smem, cs, a);
       } else if ((cls == 0 && thr_cls[0] == 128) || (cls == 1 && thr_cls[1] == 128)) {
         int rc = thb::front_set_smem(thb::front_small_kernel<128>, smem, &smem_set[1]); if (rc) return rc;
-        thb::front_small_kernel<128><<<grid, 128, smem, cs>>>(a);
+        FRONT_LAUNCH(thb::front_small_kernel<128>, grid, 128, smem, cs, a);
       } else if (cls <= 1 || smem <= 56 * 1024) {   // class 2 (> 96 rows): threads so that ~32 warps are resident whatever the panel size
         int rc = thb::front_set_smem(thb::front_small_kernel<256>, smem, &smem_set[2]); if (rc) return rc;
-        thb::front_small_kernel<256><<<grid, 256, smem, cs>>>(a);
+        FRONT_LAUNCH(thb::front_small_kernel<256>, grid, 256, smem, cs, a);
       } else if (smem <= 113 * 1024) {
         int rc = thb::front_set_smem(thb::front_small_kernel<512>, smem, &smem_set[3]); if (rc) return rc;
-        thb::front_small_kernel<512><<<grid, 512, smem, cs>>>(a);
+        FRONT_LAUNCH(thb::front_small_kernel<512>, grid, 512, smem, cs, a);
       } else {                          // one CTA per SM: all 1 024 threads
         int rc = thb::front_set_smem(thb::front_small_kernel<1024>, smem, &smem_set[4]); if (rc) return rc;
-        thb::front_small_kernel<1024><<<grid, 1024, smem, cs>>>(a);
+        FRONT_LAUNCH(thb::front_small_kernel<1024>, grid, 1024, smem, cs, a);
       }
       THB_CHECK_LAUNCH();
     } else {
@@ -803,18 +845,18 @@ int thb_front_solve_f64(const thb_front_plan* p, const int64_t* launches, int64_
       const dim3 grid((unsigned)B, (unsigned)count);
       if (pass == 0) {
         if (kc == 0) { int rc = thb::front_set_smem(thb::front_forward_kernel<64>, smem, &fw_set[0]); if (rc) return rc;
-                       thb::front_forward_kernel<64><<<grid, 64, smem, cs>>>(a); }
+                       FRONT_LAUNCH(thb::front_forward_kernel<64>, grid, 64, smem, cs, a); }
         else if (kc == 1) { int rc = thb::front_set_smem(thb::front_forward_kernel<128>, smem, &fw_set[1]); if (rc) return rc;
-                            thb::front_forward_kernel<128><<<grid, 128, smem, cs>>>(a); }
+                            FRONT_LAUNCH(thb::front_forward_kernel<128>, grid, 128, smem, cs, a); }
         else { int rc = thb::front_set_smem(thb::front_forward_kernel<256>, smem, &fw_set[2]); if (rc) return rc;
-               thb::front_forward_kernel<256><<<grid, 256, smem, cs>>>(a); }
+               FRONT_LAUNCH(thb::front_forward_kernel<256>, grid, 256, smem, cs, a); }
       } else {
         if (kc == 0) { int rc = thb::front_set_smem(thb::front_backward_kernel<64>, smem, &bw_set[0]); if (rc) return rc;
-                       thb::front_backward_kernel<64><<<grid, 64, smem, cs>>>(a); }
+                       FRONT_LAUNCH(thb::front_backward_kernel<64>, grid, 64, smem, cs, a); }
         else if (kc == 1) { int rc = thb::front_set_smem(thb::front_backward_kernel<128>, smem, &bw_set[1]); if (rc) return rc;
-                            thb::front_backward_kernel<128><<<grid, 128, smem, cs>>>(a); }
+                            FRONT_LAUNCH(thb::front_backward_kernel<128>, grid, 128, smem, cs, a); }
         else { int rc = thb::front_set_smem(thb::front_backward_kernel<256>, smem, &bw_set[2]); if (rc) return rc;
-               thb::front_backward_kernel<256><<<grid, 256, smem, cs>>>(a); }
+               FRONT_LAUNCH(thb::front_backward_kernel<256>, grid, 256, smem, cs, a); }
       }
       THB_CHECK_LAUNCH();
     }

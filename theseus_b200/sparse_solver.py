@@ -219,14 +219,18 @@ class BaspachoSparseSolver(LinearSolver):
                              work=torch.empty(B, P.n, dtype=torch.float64, device=device),
                              ws=torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=device),
                              Atb=torch.empty(B, P.n, dtype=torch.float64, device=device),
+                             AtA_diag=torch.empty(B, P.n, dtype=torch.float64, device=device),
                              info=torch.empty(B, dtype=torch.int32, device=device))
         bufs = d["bufs"]
         factor, Atb, info = bufs["factor"], bufs["Atb"], bufs["info"]
+        lin = self.linearization
+        if getattr(lin, "_Atb", None) is Atb:   # the buffers are about to be overwritten: the linearization must not keep them as its Atb / diag
+            lin._Atb = lin._AtA_diag = None
         nnz, m = A_val.shape[1], b.shape[1]
         self._factor_stamp = getattr(self, "_factor_stamp", 0) + 1
         ata = bufs["ata"]
         _lib.check(lib.thb_gram_f64(C.byref(d["gram"]), B, _lib.ptr(A_val), nnz, _lib.ptr(b), m, _lib.ptr(ata), self._ata_size,
-                                    _lib.ptr(Atb), None, s), "gram(front)")
+                                    _lib.ptr(Atb), _lib.ptr(bufs["AtA_diag"]), s), "gram(front)")
         L = d["launches"]
         for c0 in range(0, B, chunk):
             nb = min(chunk, B - c0)
@@ -287,7 +291,13 @@ class BaspachoSparseSolver(LinearSolver):
         if wants_grad(A_val, b):
             detach = bool(getattr(lin, "detached_hessian", False))
             return LinearSolveFunction.apply(A_val, b, self, damping, ellipsoidal_damping, damping_eps, detach)
-        return self._solve_nograd(A_val, b, damping, ellipsoidal_damping, damping_eps)[0]
+        x = self._solve_nograd(A_val, b, damping, ellipsoidal_damping, damping_eps)[0]
+        bufs = self._dev["bufs"] if self._dev is not None else {}
+        if "AtA_diag" in bufs and A_val.dtype == torch.float64 and A_val.is_contiguous() and b.is_contiguous() and getattr(lin, "_Atb", 0) is None:
+            # A^T b and diag(A^T A) of THIS linearization came out of the Gram pass: the LM accept test (optimizer._check_accept) reads them
+            # from the linearization instead of running the Atb kernel a second time
+            lin._Atb, lin._AtA_diag = bufs["Atb"], bufs["AtA_diag"]
+        return x
 
     def _solve_nograd(self, A_val, b, damping, ellipsoidal_damping, damping_eps):
         out_dtype = A_val.dtype
