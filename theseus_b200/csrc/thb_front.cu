@@ -110,6 +110,9 @@ __device__ __forceinline__ double front_panel_in(const FrontArgs& a, const doubl
 //   3. update matrix: per 16 x 16 tile of the lower triangle, -P_I P_J^T by DMMA straight from the panel, plus the gathered children,
 //      written once from registers.
 constexpr int FRONT_WD_LD = 20;
+#ifndef FRONT_LOOKAHEAD
+#define FRONT_LOOKAHEAD 1   // 0: the two-barrier form of the panel factorisation
+#endif
 #ifndef FRONT_PL
 #define FRONT_PL 4   // panel elements a thread gathers per pass (their global loads are in flight together; 8 measured 2 % slower)
 #endif
@@ -117,7 +120,7 @@ constexpr int FRONT_MAX_CHILDREN = 8;   // fronts with more children are assembl
 
 __host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b, int nchildren) {
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
-  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN     // + children descriptors
+  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 16 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN    // + 2 inverse blocks + children descriptors
          + ((int64_t)nchildren * (w + b) + 1) / 2 + 2;                                           // + int32 inverse maps
 }
 
@@ -170,6 +173,52 @@ __device__ __forceinline__ int front_leaf8(double* __restrict__ T, int ld, doubl
   return fail;
 }
 
+// Warp: the 8 x 8 diagonal block jb of the panel  D <- D - L_j L_j^T (DMMA over the columns already factored), then its Cholesky factor
+// in place and its inverse to Wd (front_leaf8); a non-positive pivot inside the real columns is recorded once per item.
+__device__ __forceinline__ void front_diag_block(double* PN, int ldp, int jb, double* Wd, int lane, int w, int first, int32_t* info) {
+  const int lr = lane >> 2, lc = lane & 3;
+  double c0 = 0.0, c1 = 0.0;
+  const double* Arow = PN + (8 * jb + lr) * ldp + lc;
+  for (int k = 0; k < 8 * jb; k += 4) {
+    const double av = Arow[k];
+    front_mma884(c0, c1, av, av);   // the column operand is the same 8 rows
+  }
+  double* d = PN + (8 * jb + lr) * ldp + 8 * jb + 2 * lc;
+  d[0] -= c0;
+  d[1] -= c1;
+  __syncwarp();
+  const int fail = front_leaf8(PN + (8 * jb) * ldp + 8 * jb, ldp, Wd, lane);
+  if (lane == 0 && fail != 0 && 8 * jb + fail <= w) atomicCAS(info, 0, first + 8 * jb + fail);
+}
+
+// Warp: block column jb of the row tiles rt0 (and rt0 + 1 when TWO):  X = A - sum_k L_tile,k L_jb,k^T,  L = X W_jb^T, in place.
+template <bool TWO>
+__device__ __forceinline__ void front_tile_column(double* PN, int ldp, int jb, int rt0, const double* Wd, int lane) {
+  const int lr = lane >> 2, lc = lane & 3;
+  double x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
+  const double* A0 = PN + (8 * rt0 + lr) * ldp + lc;
+  const double* Bj = PN + (8 * jb + lr) * ldp + lc;
+  for (int k = 0; k < 8 * jb; k += 4) {
+    const double bf = Bj[k];
+    front_mma884(x00, x01, A0[k], bf);
+    if (TWO) front_mma884(x10, x11, A0[8 * ldp + k], bf);
+  }
+  double* X0 = PN + (8 * rt0 + lr) * ldp + 8 * jb + 2 * lc;
+  X0[0] -= x00; X0[1] -= x01;
+  if (TWO) { X0[8 * ldp] -= x10; X0[8 * ldp + 1] -= x11; }
+  __syncwarp();
+  x00 = x01 = x10 = x11 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k += 4) {
+    const double bf = Wd[lr * FRONT_WD_LD + k + lc];   // B[k][n] = Winv[n][k]
+    front_mma884(x00, x01, A0[8 * jb + k], bf);
+    if (TWO) front_mma884(x10, x11, A0[8 * ldp + 8 * jb + k], bf);
+  }
+  __syncwarp();
+  X0[0] = x00; X0[1] = x01;
+  if (TWO) { X0[8 * ldp] = x10; X0[8 * ldp + 1] = x11; }
+}
+
 struct FrontChild {       // one child of the front this CTA works on (shared memory, <= FRONT_MAX_CHILDREN)
   const double* src;      // its update matrix for this item
   int ldg, lo, hi, pad;   // leading dimension; range [lo, hi] of this front's rows the child reaches
@@ -200,9 +249,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
   const int ldp = front_pad_ld(w8);
   const int prow = w8 + b16 + 8;
   double* PN = sm;                          // [prow][ldp]
-  double* Wd = PN + prow * ldp;             // [8][FRONT_WD_LD]
-  FrontChild* ch = reinterpret_cast<FrontChild*>(Wd + 8 * FRONT_WD_LD);               // [FRONT_MAX_CHILDREN] (24 bytes each)
-  int32_t* INV = reinterpret_cast<int32_t*>(Wd + 8 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN);   // [nch][r] front row -> child row / -1
+  double* Wd = PN + prow * ldp;             // [2][8][FRONT_WD_LD]: inverse of the current diagonal block, and of the next one (look-ahead)
+  FrontChild* ch = reinterpret_cast<FrontChild*>(Wd + 16 * FRONT_WD_LD);              // [FRONT_MAX_CHILDREN] (24 bytes each)
+  int32_t* INV = reinterpret_cast<int32_t*>(Wd + 16 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN);  // [nch][r] front row -> child row / -1
   // ---- children descriptors and inverse maps go to shared memory (one round trip, then every lookup is on chip) ----
   for (int q = 0; q < nch; q++) {
     const int64_t* PC = p.pc + (int64_t)(c_begin + q) * 6;   // (cb_off, cb_ld, lo, hi, inv_off, u_off) of this child
@@ -275,50 +324,33 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
   __syncthreads();
   // ---- blocked left-looking factorisation of the panel, 8 columns at a time ----
   const int nbk = w8 / 8, nrt = (w8 + b16) / 8;
+#if FRONT_LOOKAHEAD
+  // LOOK-AHEAD: in step jb warp 0 finishes row tile jb + 1 alone and goes straight on to the NEXT diagonal block (factor + inverse into
+  // the other Wd buffer) while the other warps work through the remaining tiles of block column jb: one barrier per step instead of two,
+  // and nobody waits for the diagonal block's dependent chain (ncu, round 2: 18 % of the warp samples of the big classes sat at those
+  // two barriers).  Same arithmetic per tile as the two-barrier form: bitwise the same factor.
+  if (warp == 0) front_diag_block(PN, ldp, 0, Wd, lane, w, f_first, a.info + item);
+  __syncthreads();
   for (int jb = 0; jb < nbk; jb++) {
+    const double* Wc = Wd + (jb & 1) * 8 * FRONT_WD_LD;
     if (warp == 0) {
-      double c0 = 0.0, c1 = 0.0;
-      const double* Arow = PN + (8 * jb + lr) * ldp + lc;
-      for (int k = 0; k < 8 * jb; k += 4) {
-        const double av = Arow[k];
-        front_mma884(c0, c1, av, av);   // D -= L_j L_j^T : the column operand is the same 8 rows
-      }
-      double* d = PN + (8 * jb + lr) * ldp + 8 * jb + 2 * lc;
-      d[0] -= c0;
-      d[1] -= c1;
+      if (jb + 1 < nrt) front_tile_column<false>(PN, ldp, jb, jb + 1, Wc, lane);
       __syncwarp();
-      const int fail = front_leaf8(PN + (8 * jb) * ldp + 8 * jb, ldp, Wd, lane);
-      if (lane == 0 && fail != 0 && 8 * jb + fail <= w) atomicCAS(a.info + item, 0, f_first + 8 * jb + fail);
+      if (jb + 1 < nbk) front_diag_block(PN, ldp, jb + 1, Wd + ((jb + 1) & 1) * 8 * FRONT_WD_LD, lane, w, f_first, a.info + item);
     }
-    __syncthreads();
-    const int npair = (nrt - jb) / 2;   // row tiles jb+1 .. nrt-1 in pairs (an odd last tile pairs with the zero tile after the end)
-    for (int q = warp; q < npair; q += NW) {
-      const int rt0 = jb + 1 + 2 * q;
-      double x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
-      const double* A0 = PN + (8 * rt0 + lr) * ldp + lc;
-      const double* Bj = PN + (8 * jb + lr) * ldp + lc;
-      for (int k = 0; k < 8 * jb; k += 4) {
-        const double bf = Bj[k];
-        front_mma884(x00, x01, A0[k], bf);
-        front_mma884(x10, x11, A0[8 * ldp + k], bf);
-      }
-      double* X0 = PN + (8 * rt0 + lr) * ldp + 8 * jb + 2 * lc;
-      X0[0] -= x00; X0[1] -= x01;
-      X0[8 * ldp] -= x10; X0[8 * ldp + 1] -= x11;
-      __syncwarp();
-      x00 = x01 = x10 = x11 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k += 4) {
-        const double bf = Wd[lr * FRONT_WD_LD + k + lc];   // B[k][n] = Winv[n][k]
-        front_mma884(x00, x01, A0[8 * jb + k], bf);
-        front_mma884(x10, x11, A0[8 * ldp + 8 * jb + k], bf);
-      }
-      __syncwarp();
-      X0[0] = x00; X0[1] = x01;
-      X0[8 * ldp] = x10; X0[8 * ldp + 1] = x11;
-    }
+    const int npair = (nrt - jb - 1) / 2;   // row tiles jb+2 .. nrt-1 in pairs (an odd last tile pairs with the zero tile after the end)
+    for (int q = (warp + NW - 1) % NW; q < npair; q += NW) front_tile_column<true>(PN, ldp, jb, jb + 2 + 2 * q, Wc, lane);
     __syncthreads();
   }
+#else
+  for (int jb = 0; jb < nbk; jb++) {
+    if (warp == 0) front_diag_block(PN, ldp, jb, Wd, lane, w, f_first, a.info + item);
+    __syncthreads();
+    const int npair = (nrt - jb) / 2;   // row tiles jb+1 .. nrt-1 in pairs (an odd last tile pairs with the zero tile after the end)
+    for (int q = warp; q < npair; q += NW) front_tile_column<true>(PN, ldp, jb, jb + 1 + 2 * q, Wd, lane);
+    __syncthreads();
+  }
+#endif
   // ---- write the factored panel (zeros above the diagonal of the pivot block) ----
   {
     int i = tid / w, j = tid - i * w;
