@@ -110,9 +110,6 @@ __device__ __forceinline__ double front_panel_in(const FrontArgs& a, const doubl
 //   3. update matrix: per 16 x 16 tile of the lower triangle, -P_I P_J^T by DMMA straight from the panel, plus the gathered children,
 //      written once from registers.
 constexpr int FRONT_WD_LD = 20;
-#ifndef FRONT_LOOKAHEAD
-#define FRONT_LOOKAHEAD 1   // 0: the two-barrier form of the panel factorisation
-#endif
 #ifndef FRONT_PL
 #define FRONT_PL 4   // panel elements a thread gathers per pass (their global loads are in flight together; 8 measured 2 % slower)
 #endif
@@ -120,7 +117,7 @@ constexpr int FRONT_MAX_CHILDREN = 8;   // fronts with more children are assembl
 
 __host__ __device__ __forceinline__ int64_t front_smem_doubles(int w, int b, int nchildren) {
   const int b16 = (b + 15) & ~15, w8 = (w + 7) & ~7;
-  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 16 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN    // + 2 inverse blocks + children descriptors
+  return (int64_t)(w8 + b16 + 8) * front_pad_ld(w8) + 8 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN     // + children descriptors
          + ((int64_t)nchildren * (w + b) + 1) / 2 + 2;                                           // + int32 inverse maps
 }
 
@@ -249,9 +246,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
   const int ldp = front_pad_ld(w8);
   const int prow = w8 + b16 + 8;
   double* PN = sm;                          // [prow][ldp]
-  double* Wd = PN + prow * ldp;             // [2][8][FRONT_WD_LD]: inverse of the current diagonal block, and of the next one (look-ahead)
-  FrontChild* ch = reinterpret_cast<FrontChild*>(Wd + 16 * FRONT_WD_LD);              // [FRONT_MAX_CHILDREN] (24 bytes each)
-  int32_t* INV = reinterpret_cast<int32_t*>(Wd + 16 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN);  // [nch][r] front row -> child row / -1
+  double* Wd = PN + prow * ldp;             // [8][FRONT_WD_LD]
+  FrontChild* ch = reinterpret_cast<FrontChild*>(Wd + 8 * FRONT_WD_LD);               // [FRONT_MAX_CHILDREN] (24 bytes each)
+  int32_t* INV = reinterpret_cast<int32_t*>(Wd + 8 * FRONT_WD_LD + 3 * FRONT_MAX_CHILDREN);   // [nch][r] front row -> child row / -1
   // ---- children descriptors and inverse maps go to shared memory (one round trip, then every lookup is on chip) ----
   for (int q = 0; q < nch; q++) {
     const int64_t* PC = p.pc + (int64_t)(c_begin + q) * 6;   // (cb_off, cb_ld, lo, hi, inv_off, u_off) of this child
@@ -324,25 +321,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
   __syncthreads();
   // ---- blocked left-looking factorisation of the panel, 8 columns at a time ----
   const int nbk = w8 / 8, nrt = (w8 + b16) / 8;
-#if FRONT_LOOKAHEAD
-  // LOOK-AHEAD: in step jb warp 0 finishes row tile jb + 1 alone and goes straight on to the NEXT diagonal block (factor + inverse into
-  // the other Wd buffer) while the other warps work through the remaining tiles of block column jb: one barrier per step instead of two,
-  // and nobody waits for the diagonal block's dependent chain (ncu, round 2: 18 % of the warp samples of the big classes sat at those
-  // two barriers).  Same arithmetic per tile as the two-barrier form: bitwise the same factor.
-  if (warp == 0) front_diag_block(PN, ldp, 0, Wd, lane, w, f_first, a.info + item);
-  __syncthreads();
-  for (int jb = 0; jb < nbk; jb++) {
-    const double* Wc = Wd + (jb & 1) * 8 * FRONT_WD_LD;
-    if (warp == 0) {
-      if (jb + 1 < nrt) front_tile_column<false>(PN, ldp, jb, jb + 1, Wc, lane);
-      __syncwarp();
-      if (jb + 1 < nbk) front_diag_block(PN, ldp, jb + 1, Wd + ((jb + 1) & 1) * 8 * FRONT_WD_LD, lane, w, f_first, a.info + item);
-    }
-    const int npair = (nrt - jb - 1) / 2;   // row tiles jb+2 .. nrt-1 in pairs (an odd last tile pairs with the zero tile after the end)
-    for (int q = (warp + NW - 1) % NW; q < npair; q += NW) front_tile_column<true>(PN, ldp, jb, jb + 2 + 2 * q, Wc, lane);
-    __syncthreads();
-  }
-#else
+  // (A LOOK-AHEAD form -- warp 0 finishes row tile jb + 1 alone and factors the NEXT diagonal block while the other warps work through
+  // block column jb, one barrier per step -- was built and measured: numeric phase 28.30 vs 27.96 ms at C5 B = 512, i.e. no gain: with
+  // <= 1 tile pair per warp the step is bound by tile -> diagonal block -> tile, look-ahead or not.  Removed; git history has it.)
   for (int jb = 0; jb < nbk; jb++) {
     if (warp == 0) front_diag_block(PN, ldp, jb, Wd, lane, w, f_first, a.info + item);
     __syncthreads();
@@ -350,7 +331,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) front_small_kernel(Fr
     for (int q = warp; q < npair; q += NW) front_tile_column<true>(PN, ldp, jb, jb + 1 + 2 * q, Wd, lane);
     __syncthreads();
   }
-#endif
   // ---- write the factored panel (zeros above the diagonal of the pivot block) ----
   {
     int i = tid / w, j = tid - i * w;

@@ -173,7 +173,7 @@ def small_smem_bytes(w: int, b: int, nchildren: int = 0) -> int:
     8 x 8 diagonal block and the children's int32 inverse maps.  (The update matrix is never resident: its tiles go from registers to
     global memory.)"""
     b16, w8 = (b + 15) & ~15, (w + 7) & ~7
-    return ((w8 + b16 + 8) * _pad_ld(w8) + 16 * 20 + 3 * SMALL_MAX_CHILDREN + 2 + (min(nchildren, SMALL_MAX_CHILDREN) * (w + b) + 1) // 2) * 8
+    return ((w8 + b16 + 8) * _pad_ld(w8) + 8 * 20 + 3 * SMALL_MAX_CHILDREN + 2 + (min(nchildren, SMALL_MAX_CHILDREN) * (w + b) + 1) // 2) * 8
 
 
 SPLIT_MAX_W = int(__import__("os").environ.get("THB_FRONT_SPLIT_W", "96"))   # pivot columns of one piece when a wide supernode is split into a chain
