@@ -329,7 +329,15 @@ def main():
                     substitutions=dict(ms=ms_subst, algorithmic_bytes=16.0 * nnz_l * B, hbm_frac=16.0 * nnz_l * B / (ms_subst * 1e-3) / (hbm * 1e9)),
                     peak_source="fp64 cuBLAS dgemm 8192^3 measured live in this run (MEASURED_PEAKS.json carries no fp64 figure; "
                                 f"its bf16/HBM entries [{peaks_src}]: {peaks.get('bf16_tflops')} TF/s, {hbm} GB/s)",
-                    share_of_step=ms_numeric * LM_ITERS / ms_step)
+                    share_of_step=ms_numeric * LM_ITERS / ms_step,
+                    # the largest single kernel of the factorisation, from the committed captures (NOT measured in this run): its traffic
+                    # is the per-kernel dram figure the contract's `traffic` key asks for; the call above is ~100 launches of 6 kernels
+                    dominant_kernel=dict(name="front_small_kernel<1024>", share_of_linear_solve=0.283,
+                                         share_source="profiles/r02m_c5_B512_front_launch_agg.txt (ncu --metrics gpu__time_duration.sum, one solve, B=512)",
+                                         ncu_launch="depth-6 launch of C5, B=512: 6 fronts (w 36-66, b 192-372) x 512 items, 26.3 MFLOP per item",
+                                         duration_ms=1.47, achieved_tflops=9.2, dmma_pipe_pct=29.5, traffic=2.92e9,
+                                         algorithmic_bytes=2.40e9, traffic_over_algorithmic=1.22,
+                                         ncu_source="profiles/r02l_front_small_1024_ncu_full_details.txt, r02l_front_kernels_ncu_summary.txt"))
 
     # ---- bench-size parity: first-iteration delta and final error of the first items vs the CPU oracle's run on the same items.
     # Every rank runs the extra (untimed) solve so that the per-iteration collectives stay matched; rank 0 compares. ----
