@@ -47,6 +47,8 @@ C2_POSES, C2_BATCH = 256, 256
 C2_WORKLOAD = ("C2: synthetic SE3 pose-graph (pose_graph_cube shape: 256 poses, loop_closure_ratio 0.2), batch=256 per GPU (weak), "
                "LM(10 it, adaptive+ellipsoidal damping) + CholeskyDenseSolver")
 CPU_SAMPLE_ITEMS = 32
+# sparse CPU arms: one process per batch item, as many items as the host has cores (bounded: 16..128) -- the reference's per-item loop on ALL cores
+C5_CPU_ITEMS = int(os.environ.get("THB_BENCH_CPU_ITEMS", str(max(16, min(os.cpu_count() or 16, 128)))))
 
 
 def _measured_peaks():
@@ -145,12 +147,12 @@ def make_c5_data(batch, seed, device="cpu"):
 # ------------------------------------------------------------------------------------------------ --impl reference
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for the headline workload (oracle port; /root/reference is Python and does
-    not travel to the GPU box), all host cores, rank 0 only.  Each step = the LM solve of a bounded sample (CPU_SAMPLE_ITEMS of the 4096
+    not travel to the GPU box), all host cores, rank 0 only.  Each step = the LM solve of a bounded sample (C5_CPU_ITEMS of the 4096
     items); value = LM iterations/s of the 4096-batch assuming the reference's per-item loop scales linearly in the batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = CPU_SAMPLE_ITEMS
+    sample = C5_CPU_ITEMS
     data = make_c5_data(sample, seed=0)
     cores = None
     for _ in range(min(args.warmup, 1)):
@@ -170,7 +172,7 @@ def run_reference(args):
                             note="CPU oracle port of the reference path (SparseLinearization + one sparse direct factorisation per item, SuperLU "
                                  f"standing in for CHOLMOD/BaSpaCho-CPU); {sample}-item sample timed ({t_sample:.2f} s per LM solve), scaled linearly "
                                  "to the 4096-item batch"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, threads_used=used, kind="port",
+                cpu_baseline=dict(value=value, unit=UNIT, cores=used, host_cores=cores, kind="port",
                                   sample=f"{sample} of {C5_GLOBAL_BATCH} batch items x {LM_ITERS} LM iterations per step, {len(times)} steps"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -180,7 +182,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -342,7 +344,7 @@ def main():
     # ---- bench-size parity: first-iteration delta and final error of the first items vs the CPU oracle's run on the same items.
     # Every rank runs the extra (untimed) solve so that the per-iteration collectives stay matched; rank 0 compares. ----
     parity, cpu = None, None
-    k = min(CPU_SAMPLE_ITEMS, B)
+    k = min(C5_CPU_ITEMS, B)
     deltas = []
 
     def cb(optimizer, info, delta, it):
@@ -362,7 +364,7 @@ def main():
                       against="CPU oracle (oracle/nls.py, sparse path) on the same first items of rank 0's shard")
         if world == 1:
             t_full = dt * C5_GLOBAL_BATCH / k
-            cpu = dict(value=LM_ITERS / t_full, unit=UNIT, cores=cores, threads_used=used, kind="port",
+            cpu = dict(value=LM_ITERS / t_full, unit=UNIT, cores=used, host_cores=cores, kind="port",
                        sample=f"{k} of {C5_GLOBAL_BATCH} batch items x {LM_ITERS} LM iterations ({dt:.1f} s measured), scaled linearly in the batch; "
                               "SparseLinearization + per-item sparse direct factorisation (SuperLU standing in for CHOLMOD / BaSpaCho-CPU)",
                        final_err_mean_sample=float(e_ref.mean()))
@@ -496,7 +498,7 @@ def dense_c2_leg(th, lib, _lib, device, rank, world, pg, timed, peak_tf, steps, 
         dt, ora, cores, used = cpu_run(data, k, "dense")
         t_full = dt * C2_BATCH / k
         rel_err = float(np.max(np.abs(out["info"].last_err[:k].cpu().numpy() - ora["err_history"][:, -1]) / np.abs(ora["err_history"][:, -1])))
-        res["cpu_baseline"] = dict(value=LM_ITERS / t_full, cores=cores, threads_used=used, kind="port",
+        res["cpu_baseline"] = dict(value=LM_ITERS / t_full, cores=used, host_cores=cores, kind="port",
                                    sample=f"{k} of {C2_BATCH} items x {LM_ITERS} LM iterations ({dt:.1f} s), scaled linearly; dense A, BLAS A^T A, LAPACK potrf",
                                    final_err_rel_diff_vs_gpu_first_items=rel_err)
     return res
