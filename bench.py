@@ -255,7 +255,12 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = _lib.total_launches()
+    prof_range = os.environ.get("THB_BENCH_PROFILE_RANGE", "0") == "1"   # ncu --profile-from-start off: the launch list of the timed steps only
+    if prof_range:
+        torch.cuda.profiler.start()
     ms_step = timed(step_resident, args.steps) / args.steps
+    if prof_range:
+        torch.cuda.profiler.stop()
     launches = int(_lib.total_launches() - l0)
     clocks = sampler.stop() if rank == 0 else None
     value = LM_ITERS * 1e3 / ms_step
