@@ -36,6 +36,7 @@ def test_device_arm_does_not_run_without_cuda():
         import pytest
         pytest.skip("a CUDA device is present")
     r = _run(["--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-c2"], timeout=300)
+    assert r.returncode != 0
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]      # no number is printed
     assert "NVIDIA" in r.stderr or "CUDA" in r.stderr or "cuda" in r.stderr
 
