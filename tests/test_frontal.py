@@ -147,11 +147,16 @@ def _solve(monkeypatch, lib, S, A_val, b, alpha, **kw):
     return solver, x.numpy()
 
 
-@pytest.mark.parametrize("case", ["ring40", "mixed", "ba"])
+@pytest.mark.parametrize("case", ["ring40", "mixed", "ba", "islands"])
 def test_front_kernels_on_the_host_emulation(monkeypatch, emulated, case):
     rng = np.random.default_rng(7)
     if case == "ring40":
         S, B = _ring_structure(40), 3
+    elif case == "islands":
+        # disconnected components (several roots), an isolated variable that only has a prior, dof 1 and 7 next to 6, batch of ONE
+        dims = [6, 6, 6, 6, 6, 1, 7, 3, 3, 3]
+        costs = [(3, [0, 1]), (3, [1, 2]), (3, [2, 3]), (3, [0, 3]), (2, [7, 8]), (2, [8, 9]), (4, [5, 6])] + [(dims[i], [i]) for i in range(len(dims))]
+        S, B = build_structure(dims, [(d, sorted(vs)) for d, vs in costs]), 1
     elif case == "mixed":
         dims = [6, 3, 6, 2, 1, 6, 3, 3, 6, 6, 2, 6]
         S, B = _ring_structure(len(dims), dims, chord=5), 2
