@@ -161,7 +161,7 @@ def run_reference(args):
     for _ in range(args.steps):
         dt, _, cores, used = cpu_run(data, sample, "sparse")
         times.append(dt)
-        if sum(times) > 240.0:   # the whole run must end within a few minutes
+        if sum(times) > 120.0:   # the whole run must end within a few minutes (one step = ~47 s on 128 cores)
             break
     t_sample = float(np.mean(times))
     t_full = t_sample * C5_GLOBAL_BATCH / sample
